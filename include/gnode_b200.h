@@ -1,0 +1,232 @@
+/*
+ * gnode_b200.h -- C ABI of the B200-native GNODE hot path (libgnode_b200.so, sm_100a only).
+ *
+ * The reference (dkssud715/swarm-ode) has NO FFI / plugin layer for this path: it is plain
+ * nn.Modules calling two third-party Python libraries.  Each entry point below therefore cites
+ * the reference call it replaces (file:line under /root/reference) and, where the arithmetic
+ * lives in an un-vendored dependency, the upstream routine it stands for:
+ *
+ *   gnode_csr_build          edge_index consumption inside SAGEConv.propagate
+ *                            (scripts/train_gde.py:36,39,43; PyG scatter by dst)      [upstream PyG]
+ *   gnode_sage_fwd/_bwd      SAGEConv(in,out)(x, edge_index)   scripts/train_gde.py:27-29,36-43
+ *   gnode_rhs_fwd/_bwd       GraphODEFunc.forward(t,x,edge_index)  scripts/train_gde.py:33-45
+ *   gnode_integrate_fixed    odeint(..., method='euler'|'midpoint'|'rk4') scripts/train_gde.py:78-85,
+ *                            scripts/run_gnode.py:134-135                          [upstream torchdiffeq]
+ *   gnode_integrate_fixed_bwd  loss.backward() through the solver  scripts/train_gde.py:493
+ *   gnode_integrate_dopri5   odeint(..., method='dopri5') / default method  scripts/gnode.py:136-137,
+ *                            scripts/train_gde.py:78-85 with ode_solver='dopri5'   [upstream torchdiffeq]
+ *   gnode_decoder_fwd/_bwd   position_decoder over every time point  scripts/train_gde.py:88-94
+ *   gnode_mlp_ode_*          ODEFunction.forward(t,x) + odeint   scripts/gnode.py:136-137,160-174,
+ *                            scripts/run_gnode.py:134-135,153-167
+ *   gnode_spatial_edges      GraphConverter._compute_spatial_edges  scripts/train_gde.py:228-244
+ *
+ * Conventions
+ *   - every pointer documented "device" is a CUDA device pointer on the current device; "host" is
+ *     ordinary host memory.  No allocation happens inside the library: the caller passes a
+ *     workspace whose size comes from the matching *_workspace_bytes() query.
+ *   - all tensors are dense row-major float32 unless stated; node state is [n_nodes, node_dim].
+ *   - return value: 0 = ok, negative = error; gnode_last_error() returns a thread-local message.
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*); functions documented
+ *     "synchronises" wait for the stream before returning.
+ *   - no pointer is retained past the call.
+ */
+#ifndef GNODE_B200_H
+#define GNODE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* gnode_stream_t; /* cudaStream_t */
+
+#define GNODE_OK 0
+#define GNODE_ERR_ARG (-1)
+#define GNODE_ERR_CUDA (-2)
+#define GNODE_ERR_WORKSPACE (-3)
+#define GNODE_ERR_INDEX (-4)   /* edge index out of range */
+#define GNODE_ERR_SOLVER (-5)  /* dt underflow / non-finite state / max steps */
+
+/* solver methods (torchdiffeq names: 'euler', 'midpoint', 'rk4' (3/8 rule), 'dopri5') */
+#define GNODE_EULER 0
+#define GNODE_MIDPOINT 1
+#define GNODE_RK4_38 2
+#define GNODE_DOPRI5 3
+
+/* which kernels run the dense contractions */
+#define GNODE_ENGINE_AUTO 0  /* tcgen05 (3xTF32) where the shape allows, else SIMT */
+#define GNODE_ENGINE_SIMT 1  /* fp32 FFMA everywhere: the parity anchor */
+#define GNODE_ENGINE_TC 2    /* force the tcgen05 path (error if the shape is unsupported) */
+
+const char* gnode_last_error(void);
+int gnode_abi_version(void);
+/* process-wide selection of the GEMM engine (default AUTO); returns the previous value */
+int gnode_set_engine(int engine);
+/* number of kernels this library has launched since load (all threads) */
+int64_t gnode_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Graph: destination-sorted CSR (forward gather) + source-sorted CSR (transpose, for backward).
+ * Inside a row, neighbours are in ascending id order, so every reduction order is deterministic.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+  int64_t n_nodes;
+  int64_t n_edges;
+  const int32_t* rowptr;   /* device [n_nodes+1]  in-edges of node i: col[rowptr[i]..rowptr[i+1]) */
+  const int32_t* col;      /* device [n_edges]    source node ids                                 */
+  const int32_t* t_rowptr; /* device [n_nodes+1]  out-edges of node j                             */
+  const int32_t* t_col;    /* device [n_edges]    destination node ids                            */
+} gnode_graph;
+
+size_t gnode_csr_workspace_bytes(int64_t n_nodes, int64_t n_edges);
+/* edge_index: device int64 [2, n_edges] (row 0 = source j, row 1 = destination i), any order,
+ * as PyG lays it out.  Fills the four CSR arrays.  Synchronises; returns GNODE_ERR_INDEX if any
+ * index is outside [0, n_nodes). */
+int gnode_csr_build(const int64_t* edge_index, int64_t n_edges, int64_t n_nodes,
+                    int32_t* rowptr, int32_t* col, int32_t* t_rowptr, int32_t* t_col,
+                    void* workspace, size_t workspace_bytes, gnode_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * One SAGEConv layer:  out = mean_{j in N(i)} x_j @ wl^T + bl + x_i @ wr^T   (optional ReLU)
+ * wl, wr: [c_out, c_in] (PyG / nn.Linear layout), bl: [c_out].
+ * ---------------------------------------------------------------------------------------- */
+size_t gnode_sage_workspace_bytes(int64_t n_nodes, int32_t c_in, int32_t c_out);
+int gnode_sage_fwd(const gnode_graph* g, const float* x, int32_t c_in, int32_t c_out,
+                   const float* wl, const float* bl, const float* wr, int32_t relu,
+                   float* out, void* workspace, size_t workspace_bytes, gnode_stream_t stream);
+/* Backward of the layer above.  `out` is the layer output (used for the ReLU mask when relu=1).
+ * grad_x is overwritten; grad_wl / grad_bl / grad_wr are accumulated into (+=). Any grad pointer
+ * may be NULL to skip it. */
+int gnode_sage_bwd(const gnode_graph* g, const float* x, const float* out, const float* grad_out,
+                   int32_t c_in, int32_t c_out, const float* wl, const float* wr, int32_t relu,
+                   float* grad_x, float* grad_wl, float* grad_bl, float* grad_wr,
+                   void* workspace, size_t workspace_bytes, gnode_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * The GNODE vector field: three SAGE layers, ReLU between them (GraphODEFunc).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t node_dim;   /* D */
+  int32_t hidden_dim; /* H */
+  const float *w1l, *b1, *w1r; /* conv1: [H,D], [H], [H,D] */
+  const float *w2l, *b2, *w2r; /* conv2: [H,H], [H], [H,H] */
+  const float *w3l, *b3, *w3r; /* conv3: [D,H], [D], [D,H] */
+} gnode_sage3_params;
+
+typedef struct { /* same shapes as gnode_sage3_params; accumulated into (+=); device */
+  float *w1l, *b1, *w1r, *w2l, *b2, *w2r, *w3l, *b3, *w3r;
+} gnode_sage3_grads;
+
+size_t gnode_rhs_workspace_bytes(int64_t n_nodes, int32_t node_dim, int32_t hidden_dim);
+int gnode_rhs_fwd(const gnode_graph* g, const gnode_sage3_params* p, const float* x, float* dxdt,
+                  void* workspace, size_t workspace_bytes, gnode_stream_t stream);
+/* vector-Jacobian product of the field at x (forward is recomputed inside). grad_x overwritten. */
+int gnode_rhs_bwd(const gnode_graph* g, const gnode_sage3_params* p, const float* x,
+                  const float* grad_out, float* grad_x, const gnode_sage3_grads* grads,
+                  void* workspace, size_t workspace_bytes, gnode_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Fixed-grid integration (grid == t, as at every reference call site).
+ *   t: host float32 [n_t], strictly increasing.   sol: device [n_t, n_nodes, D]; sol[0] = y0.
+ * ---------------------------------------------------------------------------------------- */
+size_t gnode_integrate_fixed_workspace_bytes(int64_t n_nodes, int32_t node_dim, int32_t hidden_dim,
+                                             int32_t method, int32_t backward);
+int gnode_integrate_fixed(const gnode_graph* g, const gnode_sage3_params* p, int32_t method,
+                          const float* y0, const float* t, int32_t n_t, float* sol,
+                          void* workspace, size_t workspace_bytes, gnode_stream_t stream);
+/* Backprop through the solver (discretise-then-optimise, like autograd through torchdiffeq's
+ * fixed-grid loop).  sol is the forward output; grad_sol: device [n_t, n_nodes, D] (cotangent of
+ * every saved time point); grad_y0 overwritten; param grads accumulated (+=). Each step's stages
+ * are recomputed from sol[j]. */
+int gnode_integrate_fixed_bwd(const gnode_graph* g, const gnode_sage3_params* p, int32_t method,
+                              const float* sol, const float* t, int32_t n_t, const float* grad_sol,
+                              float* grad_y0, const gnode_sage3_grads* grads,
+                              void* workspace, size_t workspace_bytes, gnode_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Adaptive Dormand-Prince 5(4), torchdiffeq semantics (global RMS error norm over the whole
+ * state tensor, Hairer initial step, FSAL, quartic dense output, fp64 time / fp32 state).
+ * Synchronises once per attempted step (the accept/reject decision is made on the host).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+  int64_t nfe;          /* vector-field evaluations                       */
+  int64_t n_accepted;   /* steps with error_ratio <= 1                    */
+  int64_t n_attempted;
+  double first_step;    /* dt chosen by the initial-step heuristic        */
+  double last_dt;       /* dt proposed after the final step               */
+  double min_margin;    /* min over attempts of |error_ratio - 1|         */
+} gnode_dopri5_stats;
+
+/* Optional per-attempt trace, host arrays of capacity trace_cap (may be NULL / 0). */
+typedef struct {
+  double* error_ratio;
+  double* dt;
+  int32_t* accepted;
+  int64_t trace_cap;
+} gnode_dopri5_trace;
+
+/* Optional cross-rank hook: called on the host with the local (sum of squares, element count)
+ * of a norm; must return them summed over all ranks (torch.distributed all-reduce on the Python
+ * side).  NULL = single rank. */
+typedef void (*gnode_allreduce_fn)(double* sumsq_and_count /* [2], in/out */, void* user);
+
+size_t gnode_integrate_dopri5_workspace_bytes(int64_t n_nodes, int32_t node_dim, int32_t hidden_dim);
+int gnode_integrate_dopri5(const gnode_graph* g, const gnode_sage3_params* p, const float* y0,
+                           const double* t, int32_t n_t, double rtol, double atol, float* sol,
+                           gnode_dopri5_stats* stats, const gnode_dopri5_trace* trace,
+                           gnode_allreduce_fn allreduce, void* allreduce_user,
+                           int64_t max_num_steps, void* workspace, size_t workspace_bytes,
+                           gnode_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * position_decoder = Linear(D, 2) applied to every row of the solution.
+ *   x: [m, D] (m = n_t * n_nodes), w: [n_out, D], b: [n_out], out: [m, n_out]; n_out <= 8.
+ * ---------------------------------------------------------------------------------------- */
+size_t gnode_decoder_workspace_bytes(int64_t m, int32_t node_dim, int32_t n_out);
+int gnode_decoder_fwd(const float* x, int64_t m, int32_t node_dim, int32_t n_out, const float* w,
+                      const float* b, float* out, gnode_stream_t stream);
+/* grad_x overwritten (may be NULL); grad_w / grad_b accumulated (+=, may be NULL). */
+int gnode_decoder_bwd(const float* x, const float* grad_out, int64_t m, int32_t node_dim,
+                      int32_t n_out, const float* w, float* grad_x, float* grad_w, float* grad_b,
+                      void* workspace, size_t workspace_bytes, gnode_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Node-wise MLP vector field  Linear(H,h) tanh Linear(h,h) tanh Linear(h,H)  (ODEFunction),
+ * integrated with the same solvers (no graph).  Weights in nn.Linear layout.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t dim;        /* H  */
+  int32_t hidden_dim; /* h  */
+  const float *w0, *b0; /* [h,H], [h] */
+  const float *w1, *b1; /* [h,h], [h] */
+  const float *w2, *b2; /* [H,h], [H] */
+} gnode_mlp_params;
+
+size_t gnode_mlp_ode_workspace_bytes(int64_t m, int32_t dim, int32_t hidden_dim, int32_t method);
+int gnode_mlp_rhs_fwd(const gnode_mlp_params* p, const float* x, int64_t m, float* dxdt,
+                      void* workspace, size_t workspace_bytes, gnode_stream_t stream);
+int gnode_mlp_integrate_fixed(const gnode_mlp_params* p, int32_t method, const float* y0, int64_t m,
+                              const float* t, int32_t n_t, float* sol, void* workspace,
+                              size_t workspace_bytes, gnode_stream_t stream);
+int gnode_mlp_integrate_dopri5(const gnode_mlp_params* p, const float* y0, int64_t m, const double* t,
+                               int32_t n_t, double rtol, double atol, float* sol,
+                               gnode_dopri5_stats* stats, const gnode_dopri5_trace* trace,
+                               int64_t max_num_steps, void* workspace, size_t workspace_bytes,
+                               gnode_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Spatial edges of GraphConverter, batched over independent snapshots, bit-exact:
+ *   pos: device float32 [n_snap, n_agents, 2] (y, x).  For every snapshot, for i < j in
+ *   lexicographic order, if sqrtf((dy*dy) + (dx*dx)) < threshold (strict, float32) emit (i,j)
+ *   then (j,i).  counts[s] receives the number of directed edges of snapshot s; edges (local
+ *   ids, int32 pairs src,dst) are written at edges + 2 * s * n_agents*(n_agents-1).
+ * ---------------------------------------------------------------------------------------- */
+int gnode_spatial_edges(const float* pos, int64_t n_snap, int32_t n_agents, float threshold,
+                        int32_t* counts, int32_t* edges, gnode_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GNODE_B200_H */

@@ -1,0 +1,78 @@
+// Vector fields the integrators run on, and the Butcher tableaus of the solvers the reference can
+// select (torchdiffeq 'euler', 'midpoint', 'rk4' = 3/8 rule, 'dopri5').
+#pragma once
+#include "common.cuh"
+#include "rk.cuh"
+
+namespace gnode {
+
+constexpr int kMaxStages = 7;
+
+struct Tableau {
+  int S;                                  // stages
+  double beta[kMaxStages][kMaxStages];    // stage s input = y + dt * sum_{j<s} beta[s][j] k_j
+  double c_sol[kMaxStages];
+  double c_err[kMaxStages];
+  double c_mid[kMaxStages];
+};
+const Tableau* tableau_for(int method);
+
+// A vector field f(x) over a dense [rows, dim] fp32 state.
+struct Field {
+  virtual ~Field() {}
+  virtual int64_t rows() const = 0;
+  virtual int dim() const = 0;
+  // out = scale * f(x) (+ base if base != null).  `slot` selects where intermediates are kept for a
+  // later vjp (0 when nothing needs to be kept).  out may alias base.
+  virtual int eval(const float* x, float* out, const float* base, float scale, int slot, cudaStream_t s) = 0;
+  int64_t numel() const { return rows() * (int64_t)dim(); }
+};
+
+// ---- GraphODEFunc: three SAGE layers (scripts/train_gde.py:20-45) ----
+struct Sage3Ctx : Field {
+  gnode_graph g{};
+  int D = 0, H = 0;
+  int64_t N = 0;
+  const float *b1 = nullptr, *b2 = nullptr, *b3 = nullptr;
+  // packed weights (workspace): w1cat [2H, D] = [w1l; w1r], w2cat [H, 2H] = [w2l | w2r], w3cat [D, 2H] = [w3l | w3r]
+  float *w1cat = nullptr, *w2cat = nullptr, *w3cat = nullptr;
+  // transposes for the data gradients (NT form): w3catT [2H, D], w2catT [2H, H], w1catT [D, 2H]
+  float *w1catT = nullptr, *w2catT = nullptr, *w3catT = nullptr;
+  float* z = nullptr;                  // [N, 2H]  x @ w1cat^T
+  int n_slots = 1;
+  float* cat1[kMaxStages] = {};        // [N, 2H]  [ mean(h1) | h1 ]
+  float* cat2[kMaxStages] = {};        // [N, 2H]  [ mean(h2) | h2 ]
+  // backward scratch
+  float *gcat = nullptr, *gz = nullptr, *gv2 = nullptr, *partials = nullptr, *colpart = nullptr;
+  float *dW1cat = nullptr, *dW2cat = nullptr, *dW3cat = nullptr, *db1 = nullptr, *db2 = nullptr, *db3 = nullptr;
+
+  int64_t rows() const override { return N; }
+  int dim() const override { return D; }
+  int eval(const float* x, float* out, const float* base, float scale, int slot, cudaStream_t s) override;
+
+  // carve the workspace (measuring when the arena has no base)
+  void carve(Arena& a, int slots, bool backward);
+  int pack(const gnode_sage3_params& p, bool backward, cudaStream_t s);
+  int zero_param_grads(cudaStream_t s);
+  // grad_x = J_f(x)^T gk using the intermediates kept in `slot`; parameter gradients accumulate into dW*/db*
+  int vjp(const float* x, int slot, const float* gk, float* gx, cudaStream_t s);
+  int unpack_grads(const gnode_sage3_grads& gr, cudaStream_t s);
+};
+
+int check_graph(const gnode_graph* g, const char* who);
+int check_params(const gnode_sage3_params* p, const char* who);
+
+// ---- generic drivers (integrate.cu) ----
+int integrate_fixed(Field& f, int method, const float* y0, const float* t, int n_t, float* sol,
+                    float* const* kbuf /* S-1 buffers */, float* xs, cudaStream_t s);
+
+struct Dopri5Bufs {
+  float* k[7];
+  float* ya; float* yb; float* xs;
+  double* partials; double* dsum;   // device
+};
+int integrate_dopri5(Field& f, const float* y0, const double* t, int n_t, double rtol, double atol, float* sol,
+                     gnode_dopri5_stats* stats, const gnode_dopri5_trace* trace, gnode_allreduce_fn allreduce,
+                     void* allreduce_user, int64_t max_num_steps, const Dopri5Bufs& b, cudaStream_t s);
+
+}  // namespace gnode

@@ -1,0 +1,455 @@
+// ODE integration drivers: the solver loops of torchdiffeq.odeint restated as native host code that
+// enqueues the CUDA stages (reference call sites scripts/train_gde.py:78-85, scripts/gnode.py:136-137,
+// scripts/run_gnode.py:134-135), plus backprop through the fixed-grid solvers
+// (loss.backward(), scripts/train_gde.py:493).
+#include <cmath>
+#include <cstring>
+
+#include "field.cuh"
+
+namespace gnode {
+
+// ------------------------------------------------------------------------------------------------
+// Tableaus
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+Tableau make_euler() {
+  Tableau t{};
+  t.S = 1;
+  t.c_sol[0] = 1.0;
+  return t;
+}
+Tableau make_midpoint() {
+  Tableau t{};
+  t.S = 2;
+  t.beta[1][0] = 0.5;
+  t.c_sol[1] = 1.0;
+  return t;
+}
+// torchdiffeq 'rk4' is rk4_alt_step_func: the 3/8 rule
+Tableau make_rk4_38() {
+  Tableau t{};
+  t.S = 4;
+  t.beta[1][0] = 1.0 / 3.0;
+  t.beta[2][0] = -1.0 / 3.0; t.beta[2][1] = 1.0;
+  t.beta[3][0] = 1.0; t.beta[3][1] = -1.0; t.beta[3][2] = 1.0;
+  t.c_sol[0] = 0.125; t.c_sol[1] = 0.375; t.c_sol[2] = 0.375; t.c_sol[3] = 0.125;
+  return t;
+}
+Tableau make_dopri5() {
+  Tableau t{};
+  t.S = 7;
+  const double b[7][7] = {
+      {0},
+      {1.0 / 5},
+      {3.0 / 40, 9.0 / 40},
+      {44.0 / 45, -56.0 / 15, 32.0 / 9},
+      {19372.0 / 6561, -25360.0 / 2187, 64448.0 / 6561, -212.0 / 729},
+      {9017.0 / 3168, -355.0 / 33, 46732.0 / 5247, 49.0 / 176, -5103.0 / 18656},
+      {35.0 / 384, 0, 500.0 / 1113, 125.0 / 192, -2187.0 / 6784, 11.0 / 84},
+  };
+  std::memcpy(t.beta, b, sizeof(b));
+  const double cs[7] = {35.0 / 384, 0, 500.0 / 1113, 125.0 / 192, -2187.0 / 6784, 11.0 / 84, 0};
+  const double ce[7] = {35.0 / 384 - 1951.0 / 21600,
+                        0,
+                        500.0 / 1113 - 22642.0 / 50085,
+                        125.0 / 192 - 451.0 / 720,
+                        -2187.0 / 6784 - -12231.0 / 42400,
+                        11.0 / 84 - 649.0 / 6300,
+                        -1.0 / 60.0};
+  const double cm[7] = {6025192743.0 / 30085553152.0 / 2,
+                        0,
+                        51252292925.0 / 65400821598.0 / 2,
+                        -2691868925.0 / 45128329728.0 / 2,
+                        187940372067.0 / 1594534317056.0 / 2,
+                        -1776094331.0 / 19743644256.0 / 2,
+                        11237099.0 / 235043384.0 / 2};
+  std::memcpy(t.c_sol, cs, sizeof(cs));
+  std::memcpy(t.c_err, ce, sizeof(ce));
+  std::memcpy(t.c_mid, cm, sizeof(cm));
+  return t;
+}
+
+}  // namespace
+
+const Tableau* tableau_for(int method) {
+  static const Tableau euler = make_euler(), mid = make_midpoint(), rk4 = make_rk4_38(), dp = make_dopri5();
+  switch (method) {
+    case GNODE_EULER: return &euler;
+    case GNODE_MIDPOINT: return &mid;
+    case GNODE_RK4_38: return &rk4;
+    case GNODE_DOPRI5: return &dp;
+    default: return nullptr;
+  }
+}
+
+// x_s = y + dt * sum_{j<s} beta[s][j] * k_j     (coefficients formed in fp32 like the state dtype)
+static int stage_input(const Tableau& tb, int s_idx, const float* y, float* const* k, float dt, float* xs,
+                       int64_t n, cudaStream_t s) {
+  LinComb lc{};
+  lc.out = xs; lc.base = y; lc.n = n; lc.n_terms = 0;
+  for (int j = 0; j < s_idx; ++j) {
+    lc.in[lc.n_terms] = k[j];
+    lc.coef[lc.n_terms] = (float)tb.beta[s_idx][j] * dt;
+    ++lc.n_terms;
+  }
+  return lincomb(lc, s);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fixed grid: grid == t, solution[j+1] = y_j + step(y_j)
+// ------------------------------------------------------------------------------------------------
+int integrate_fixed(Field& f, int method, const float* y0, const float* t, int n_t, float* sol,
+                    float* const* kbuf, float* xs, cudaStream_t s) {
+  const Tableau* tbp = tableau_for(method);
+  if (!tbp || method == GNODE_DOPRI5) { set_error("integrate_fixed: bad method %d", method); return GNODE_ERR_ARG; }
+  const Tableau& tb = *tbp;
+  const int64_t n = f.numel();
+  if (sol != y0) GN_CUDA(cudaMemcpyAsync(sol, y0, sizeof(float) * n, cudaMemcpyDeviceToDevice, s));
+  for (int j = 0; j + 1 < n_t; ++j) {
+    const float dt = t[j + 1] - t[j];
+    const float* y = sol + (int64_t)j * n;
+    float* y1 = sol + (int64_t)(j + 1) * n;
+    const int S = tb.S;
+    for (int st = 0; st < S - 1; ++st) {
+      const float* x = y;
+      if (st > 0) { GN_TRY(stage_input(tb, st, y, kbuf, dt, xs, n, s)); x = xs; }
+      GN_TRY(f.eval(x, kbuf[st], nullptr, 1.f, 0, s));
+    }
+    // last stage: y1 = (y + dt * sum_{j<S-1} c_j k_j) + dt * c_{S-1} * f(x_{S-1}) fused into the field's epilogue
+    const float* x = y;
+    if (S > 1) { GN_TRY(stage_input(tb, S - 1, y, kbuf, dt, xs, n, s)); x = xs; }
+    const float* base = y;
+    if (S > 1) {
+      LinComb lc{};
+      lc.out = y1; lc.base = y; lc.n = n; lc.n_terms = 0;
+      for (int q = 0; q < S - 1; ++q) { lc.in[lc.n_terms] = kbuf[q]; lc.coef[lc.n_terms] = (float)tb.c_sol[q] * dt; ++lc.n_terms; }
+      GN_TRY(lincomb(lc, s));
+      base = y1;
+    }
+    GN_TRY(f.eval(x, y1, base, (float)tb.c_sol[S - 1] * dt, 0, s));
+  }
+  return GNODE_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Adaptive dopri5 (torchdiffeq RKAdaptiveStepsizeODESolver semantics)
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+struct NormCtx {
+  gnode_allreduce_fn allreduce; void* user; double* dsum; cudaStream_t s; int64_t n;
+  // rms over all ranks of a local sum of squares already sitting in *dsum (device)
+  int finish(float* out) {
+    double h[2];
+    if (cudaMemcpyAsync(&h[0], dsum, sizeof(double), cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+        cudaStreamSynchronize(s) != cudaSuccess) {
+      set_error("dopri5: device error while reading the error norm: %s", cudaGetErrorString(cudaGetLastError()));
+      return GNODE_ERR_CUDA;
+    }
+    h[1] = (double)n;
+    if (allreduce) allreduce(h, user);
+    *out = (float)std::sqrt(h[0] / h[1]);
+    return GNODE_OK;
+  }
+};
+
+}  // namespace
+
+int integrate_dopri5(Field& f, const float* y0, const double* t, int n_t, double rtol, double atol, float* sol,
+                     gnode_dopri5_stats* stats, const gnode_dopri5_trace* trace, gnode_allreduce_fn allreduce,
+                     void* allreduce_user, int64_t max_num_steps, const Dopri5Bufs& b, cudaStream_t s) {
+  const Tableau& tb = *tableau_for(GNODE_DOPRI5);
+  const int64_t n = f.numel();
+  const float rtolf = (float)rtol, atolf = (float)atol;
+  gnode_dopri5_stats st{};
+  st.min_margin = INFINITY;
+  NormCtx nc{allreduce, allreduce_user, b.dsum, s, n};
+
+  float* k[7];
+  for (int i = 0; i < 7; ++i) k[i] = b.k[i];
+  float* ya = b.ya;
+  float* yb = b.yb;
+
+  if (sol != y0) GN_CUDA(cudaMemcpyAsync(sol, y0, sizeof(float) * n, cudaMemcpyDeviceToDevice, s));
+  GN_CUDA(cudaMemcpyAsync(ya, y0, sizeof(float) * n, cudaMemcpyDeviceToDevice, s));
+  // f0
+  GN_TRY(f.eval(ya, k[0], nullptr, 1.f, 0, s));
+  st.nfe++;
+
+  // ---- _select_initial_step (order = 4), fp32 scalar arithmetic like the state dtype ----
+  double dt;
+  {
+    float d0, d1, d2;
+    GN_TRY(scaled_sumsq(ya, nullptr, ya, atolf, rtolf, n, b.partials, b.dsum, s));
+    GN_TRY(nc.finish(&d0));
+    GN_TRY(scaled_sumsq(k[0], nullptr, ya, atolf, rtolf, n, b.partials, b.dsum, s));
+    GN_TRY(nc.finish(&d1));
+    float h0;
+    if (d0 < 1e-5f || d1 < 1e-5f) h0 = 1e-6f; else h0 = 0.01f * d0 / d1;
+    h0 = fabsf(h0);
+    LinComb lc{};
+    lc.out = b.xs; lc.base = ya; lc.in[0] = k[0]; lc.coef[0] = h0; lc.n_terms = 1; lc.n = n;
+    GN_TRY(lincomb(lc, s));
+    GN_TRY(f.eval(b.xs, k[1], nullptr, 1.f, 0, s));
+    st.nfe++;
+    GN_TRY(scaled_sumsq(k[1], k[0], ya, atolf, rtolf, n, b.partials, b.dsum, s));
+    GN_TRY(nc.finish(&d2));
+    d2 = fabsf(d2 / h0);
+    float h1;
+    if (d1 <= 1e-15f && d2 <= 1e-15f) h1 = fmaxf(1e-6f, h0 * 1e-3f);
+    else h1 = powf(0.01f / fmaxf(d1, d2), 1.0f / 5.0f);
+    h1 = fabsf(h1);
+    dt = (double)fminf(100.f * h0, h1);
+  }
+  st.first_step = dt;
+
+  double t_cur = t[0];          // rk_state.t1
+  int next_out = 1;
+  int64_t n_steps = 0;
+  while (next_out < n_t) {
+    if (!(t[next_out] > t_cur)) {
+      // cannot happen for strictly increasing t after a step; kept for n_t points at/below t0
+      GN_CUDA(cudaMemcpyAsync(sol + (int64_t)next_out * n, ya, sizeof(float) * n, cudaMemcpyDeviceToDevice, s));
+      ++next_out;
+      continue;
+    }
+    if (n_steps >= max_num_steps) { set_error("dopri5: max_num_steps exceeded (%lld)", (long long)n_steps); return GNODE_ERR_SOLVER; }
+    const double t0 = t_cur, t1 = t0 + dt;
+    if (!(t0 + dt > t0)) { set_error("dopri5: underflow in dt %g", dt); return GNODE_ERR_SOLVER; }
+    const float dtf = (float)dt;
+    // stages 1..6 ; stage 6 input is the 5th-order solution y1 (FSAL)
+    for (int si = 1; si < 7; ++si) {
+      float* xs = (si == 6) ? yb : b.xs;
+      GN_TRY(stage_input(tb, si, ya, k, dtf, xs, n, s));
+      GN_TRY(f.eval(xs, k[si], nullptr, 1.f, 0, s));
+      st.nfe++;
+    }
+    // error ratio
+    LinComb le{};
+    le.n = n; le.n_terms = 0;
+    for (int q = 0; q < 7; ++q) { le.in[le.n_terms] = k[q]; le.coef[le.n_terms] = dtf * (float)tb.c_err[q]; ++le.n_terms; }
+    // zero coefficient (c_err[1] == 0) still multiplies in the reference; it contributes exactly +0
+    GN_TRY(error_sumsq(le, ya, yb, atolf, rtolf, b.partials, b.dsum, s));
+    float ratio;
+    GN_TRY(nc.finish(&ratio));
+    if (!std::isfinite(ratio)) { set_error("dopri5: non-finite values in state `y` (error ratio %g at t=%g, dt=%g)", (double)ratio, t0, dt); return GNODE_ERR_SOLVER; }
+    const bool accept = ratio <= 1.0f;
+    if (trace && trace->trace_cap > st.n_attempted) {
+      if (trace->error_ratio) trace->error_ratio[st.n_attempted] = ratio;
+      if (trace->dt) trace->dt[st.n_attempted] = dt;
+      if (trace->accepted) trace->accepted[st.n_attempted] = accept ? 1 : 0;
+    }
+    st.n_attempted++;
+    const double margin = std::fabs((double)ratio - 1.0);
+    if (margin < st.min_margin) st.min_margin = margin;
+    if (accept) {
+      st.n_accepted++;
+      // dense output for every requested time inside (t0, t1]
+      while (next_out < n_t && t[next_out] <= t1) {
+        const float x = (float)((t[next_out] - t0) / (t1 - t0));
+        LinComb lm{};
+        lm.n = n; lm.n_terms = 7;
+        for (int q = 0; q < 7; ++q) { lm.in[q] = k[q]; lm.coef[q] = dtf * (float)tb.c_mid[q]; }
+        GN_TRY(dopri_interp(lm, ya, yb, dtf, x, sol + (int64_t)next_out * n, s));
+        ++next_out;
+      }
+      float* tmp = ya; ya = yb; yb = tmp;
+      tmp = k[0]; k[0] = k[6]; k[6] = tmp;   // FSAL: f(t1, y1) is the next step's f0
+      t_cur = t1;
+    }
+    // _optimal_step_size
+    double factor;
+    if (ratio == 0.f) {
+      factor = 10.0;
+    } else {
+      const double dfactor = (ratio < 1.f) ? 1.0 : 0.2;
+      const double er = (double)ratio;
+      factor = std::fmin(10.0, std::fmax(0.9 / std::pow(er, 0.2), dfactor));
+    }
+    dt = dt * factor;
+    ++n_steps;
+  }
+  st.last_dt = dt;
+  if (stats) *stats = st;
+  return GNODE_OK;
+}
+
+}  // namespace gnode
+
+using namespace gnode;
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+struct FixedWs {
+  float* kbuf[kMaxStages];
+  float* xs[kMaxStages];
+  float* gk;
+  float* gcur;
+};
+
+void carve_fixed(Arena& a, Sage3Ctx& c, const Tableau& tb, bool backward, FixedWs& w) {
+  const size_t n = (size_t)c.N * c.D;
+  std::memset(&w, 0, sizeof(w));
+  if (!backward) {
+    c.carve(a, 1, false);
+    for (int i = 0; i < tb.S - 1; ++i) w.kbuf[i] = a.take<float>(n);
+    w.xs[0] = a.take<float>(n);
+  } else {
+    c.carve(a, tb.S, true);
+    for (int i = 0; i < tb.S; ++i) w.kbuf[i] = a.take<float>(n);
+    for (int i = 1; i < tb.S; ++i) w.xs[i] = a.take<float>(n);
+    w.gk = a.take<float>(n);
+    w.gcur = a.take<float>(n);
+  }
+}
+
+}  // namespace
+
+extern "C" size_t gnode_integrate_fixed_workspace_bytes(int64_t n_nodes, int32_t node_dim, int32_t hidden_dim,
+                                                        int32_t method, int32_t backward) {
+  const Tableau* tb = tableau_for(method);
+  if (!tb || method == GNODE_DOPRI5) return 0;
+  Sage3Ctx c;
+  c.N = n_nodes; c.D = node_dim; c.H = hidden_dim;
+  Arena a(nullptr, 0);
+  FixedWs w;
+  carve_fixed(a, c, *tb, backward != 0, w);
+  return a.off;
+}
+
+extern "C" int gnode_integrate_fixed(const gnode_graph* g, const gnode_sage3_params* p, int32_t method,
+                                     const float* y0, const float* t, int32_t n_t, float* sol, void* workspace,
+                                     size_t workspace_bytes, gnode_stream_t stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  GN_TRY(check_graph(g, "gnode_integrate_fixed"));
+  GN_TRY(check_params(p, "gnode_integrate_fixed"));
+  const Tableau* tb = tableau_for(method);
+  GN_ARG(tb && method != GNODE_DOPRI5, "gnode_integrate_fixed: method %d is not a fixed-grid solver", method);
+  GN_ARG(y0 && t && sol && n_t >= 1, "gnode_integrate_fixed: null pointer or empty time grid");
+  for (int j = 0; j + 1 < n_t; ++j)
+    GN_ARG(t[j + 1] > t[j], "gnode_integrate_fixed: t must be strictly increasing");
+  Sage3Ctx c;
+  c.g = *g; c.N = g->n_nodes; c.D = p->node_dim; c.H = p->hidden_dim;
+  Arena a(workspace, workspace_bytes);
+  FixedWs w;
+  carve_fixed(a, c, *tb, false, w);
+  GN_ARENA_OK(a, "gnode_integrate_fixed");
+  GN_TRY(c.pack(*p, false, s));
+  return integrate_fixed(c, method, y0, t, n_t, sol, w.kbuf, w.xs[0], s);
+}
+
+extern "C" int gnode_integrate_fixed_bwd(const gnode_graph* g, const gnode_sage3_params* p, int32_t method,
+                                         const float* sol, const float* t, int32_t n_t, const float* grad_sol,
+                                         float* grad_y0, const gnode_sage3_grads* grads, void* workspace,
+                                         size_t workspace_bytes, gnode_stream_t stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  GN_TRY(check_graph(g, "gnode_integrate_fixed_bwd"));
+  GN_TRY(check_params(p, "gnode_integrate_fixed_bwd"));
+  const Tableau* tbp = tableau_for(method);
+  GN_ARG(tbp && method != GNODE_DOPRI5, "gnode_integrate_fixed_bwd: method %d is not a fixed-grid solver", method);
+  GN_ARG(sol && t && grad_sol && grad_y0 && n_t >= 1, "gnode_integrate_fixed_bwd: null pointer or empty time grid");
+  const Tableau& tb = *tbp;
+  const int S = tb.S;
+  Sage3Ctx c;
+  c.g = *g; c.N = g->n_nodes; c.D = p->node_dim; c.H = p->hidden_dim;
+  Arena a(workspace, workspace_bytes);
+  FixedWs w;
+  carve_fixed(a, c, tb, true, w);
+  GN_ARENA_OK(a, "gnode_integrate_fixed_bwd");
+  GN_TRY(c.pack(*p, true, s));
+  GN_TRY(c.zero_param_grads(s));
+  const int64_t n = c.numel();
+
+  // gcur = cotangent of y_{j+1} (explicit part from grad_sol plus what flowed back from later steps)
+  GN_CUDA(cudaMemcpyAsync(w.gcur, grad_sol + (int64_t)(n_t - 1) * n, sizeof(float) * n, cudaMemcpyDeviceToDevice, s));
+  for (int j = n_t - 2; j >= 0; --j) {
+    const float dt = t[j + 1] - t[j];
+    const float* y = sol + (int64_t)j * n;
+    // ---- recompute the stages of step j, keeping x_s and the layer intermediates per stage ----
+    const float* xst[kMaxStages];
+    xst[0] = y;
+    for (int st = 0; st < S; ++st) {
+      if (st > 0) {
+        GN_TRY(stage_input(tb, st, y, w.kbuf, dt, w.xs[st], n, s));
+        xst[st] = w.xs[st];
+      }
+      // k of the last stage is never needed again (y_{j+1} is already known), but its layer
+      // intermediates are: evaluate it too, into kbuf[S-1].
+      GN_TRY(c.eval(xst[st], w.kbuf[st], nullptr, 1.f, st, s));
+    }
+    // ---- reverse sweep over the stages; kbuf[s] is reused to hold g_x[s] ----
+    for (int st = S - 1; st >= 0; --st) {
+      // g_k[st] = dt * c_st * gcur + dt * sum_{i > st} beta[i][st] * g_x[i]
+      LinComb lc{};
+      lc.out = w.gk; lc.base = nullptr; lc.n = n; lc.n_terms = 0;
+      lc.in[lc.n_terms] = w.gcur; lc.coef[lc.n_terms] = (float)tb.c_sol[st] * dt; ++lc.n_terms;
+      for (int i = st + 1; i < S; ++i) {
+        lc.in[lc.n_terms] = w.kbuf[i]; lc.coef[lc.n_terms] = (float)tb.beta[i][st] * dt; ++lc.n_terms;
+      }
+      bool any = false;
+      for (int q = 0; q < lc.n_terms; ++q) any = any || (lc.coef[q] != 0.f);
+      if (!any) {  // stage does not influence the output (cannot happen for the shipped tableaus)
+        GN_CUDA(cudaMemsetAsync(w.kbuf[st], 0, sizeof(float) * n, s));
+        continue;
+      }
+      GN_TRY(lincomb(lc, s));
+      GN_TRY(c.vjp(xst[st], st, w.gk, w.kbuf[st], s));
+    }
+    // gcur <- gcur + sum_s g_x[s] + grad_sol[j]
+    LinComb lc{};
+    lc.out = w.gcur; lc.base = w.gcur; lc.n = n; lc.n_terms = 0;
+    for (int st = 0; st < S; ++st) { lc.in[lc.n_terms] = w.kbuf[st]; lc.coef[lc.n_terms] = 1.f; ++lc.n_terms; }
+    lc.in[lc.n_terms] = grad_sol + (int64_t)j * n; lc.coef[lc.n_terms] = 1.f; ++lc.n_terms;
+    GN_TRY(lincomb(lc, s));
+  }
+  GN_CUDA(cudaMemcpyAsync(grad_y0, w.gcur, sizeof(float) * n, cudaMemcpyDeviceToDevice, s));
+  if (grads) GN_TRY(c.unpack_grads(*grads, s));
+  return GNODE_OK;
+}
+
+extern "C" size_t gnode_integrate_dopri5_workspace_bytes(int64_t n_nodes, int32_t node_dim, int32_t hidden_dim) {
+  Sage3Ctx c;
+  c.N = n_nodes; c.D = node_dim; c.H = hidden_dim;
+  Arena a(nullptr, 0);
+  c.carve(a, 1, false);
+  const size_t n = (size_t)n_nodes * node_dim;
+  for (int i = 0; i < 10; ++i) a.take<float>(n);
+  a.take<double>((size_t)norm_blocks((int64_t)n));
+  a.take<double>(2);
+  return a.off;
+}
+
+extern "C" int gnode_integrate_dopri5(const gnode_graph* g, const gnode_sage3_params* p, const float* y0,
+                                      const double* t, int32_t n_t, double rtol, double atol, float* sol,
+                                      gnode_dopri5_stats* stats, const gnode_dopri5_trace* trace,
+                                      gnode_allreduce_fn allreduce, void* allreduce_user, int64_t max_num_steps,
+                                      void* workspace, size_t workspace_bytes, gnode_stream_t stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  GN_TRY(check_graph(g, "gnode_integrate_dopri5"));
+  GN_TRY(check_params(p, "gnode_integrate_dopri5"));
+  GN_ARG(y0 && t && sol && n_t >= 1, "gnode_integrate_dopri5: null pointer or empty time grid");
+  GN_ARG(rtol > 0 || atol > 0, "gnode_integrate_dopri5: rtol and atol are both zero");
+  for (int j = 0; j + 1 < n_t; ++j)
+    GN_ARG(t[j + 1] > t[j], "gnode_integrate_dopri5: t must be strictly increasing");
+  Sage3Ctx c;
+  c.g = *g; c.N = g->n_nodes; c.D = p->node_dim; c.H = p->hidden_dim;
+  Arena a(workspace, workspace_bytes);
+  c.carve(a, 1, false);
+  const size_t n = (size_t)c.N * c.D;
+  Dopri5Bufs b{};
+  for (int i = 0; i < 7; ++i) b.k[i] = a.take<float>(n);
+  b.ya = a.take<float>(n);
+  b.yb = a.take<float>(n);
+  b.xs = a.take<float>(n);
+  b.partials = a.take<double>((size_t)norm_blocks((int64_t)n));
+  b.dsum = a.take<double>(2);
+  GN_ARENA_OK(a, "gnode_integrate_dopri5");
+  GN_TRY(c.pack(*p, false, s));
+  if (max_num_steps <= 0) max_num_steps = (1ll << 31) - 1;
+  return integrate_dopri5(c, y0, t, n_t, rtol, atol, sol, stats, trace, allreduce, allreduce_user, max_num_steps, b, s);
+}

@@ -1,0 +1,31 @@
+// Process-level state of libgnode_b200: error string, launch counter, engine switch.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+
+#include "common.cuh"
+
+namespace gnode {
+namespace {
+thread_local char g_err[1024] = "";
+std::atomic<int64_t> g_launches{0};
+std::atomic<int> g_engine{GNODE_ENGINE_AUTO};
+}  // namespace
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+int current_engine() { return g_engine.load(std::memory_order_relaxed); }
+}  // namespace gnode
+
+extern "C" const char* gnode_last_error(void) { return gnode::g_err; }
+extern "C" int gnode_abi_version(void) { return 1; }
+extern "C" int gnode_set_engine(int engine) {
+  if (engine < GNODE_ENGINE_AUTO || engine > GNODE_ENGINE_TC) return -1;
+  return gnode::g_engine.exchange(engine);
+}
+extern "C" int64_t gnode_launch_count(void) { return gnode::g_launches.load(std::memory_order_relaxed); }

@@ -1,0 +1,120 @@
+// One SAGEConv layer as a stand-alone operator (reference: SAGEConv(in, out)(x, edge_index),
+// scripts/train_gde.py:27-29; hetero sites scripts/gnode.py:92-97).
+//   out = act( mean_{j in N(i)} x_j @ wl^T + bl + x_i @ wr^T )
+// Forward picks the cheaper association: project-then-aggregate when c_out <= c_in, aggregate-then-
+// project otherwise, so the sparse gather always runs at min(c_in, c_out) width.
+#include "field.cuh"
+
+namespace gnode {
+namespace {
+
+struct SageWs {
+  float *wcat, *wcatT, *buf, *gz, *gm, *dwcat, *partials, *colpart;
+};
+
+// forward: wcat + buf ; backward: wcatT + gz + gm + dwcat + partials + colpart
+void carve_sage(Arena& a, int64_t N, int ci, int co, SageWs& w) {
+  const size_t n = (size_t)N;
+  const int wide = 2 * (co <= ci ? co : ci);
+  w.wcat = a.take<float>((size_t)2 * ci * co);
+  w.buf = a.take<float>(n * wide);
+  w.wcatT = a.take<float>((size_t)2 * ci * co);
+  w.gz = a.take<float>(n * 2 * co);
+  w.gm = a.take<float>(n * co);
+  w.dwcat = a.take<float>((size_t)2 * ci * co);
+  w.partials = a.take<float>(gemm_tn_workspace_floats(2 * co, ci, N));
+  w.colpart = a.take<float>(colsum_workspace_floats(co, N));
+}
+
+}  // namespace
+}  // namespace gnode
+
+using namespace gnode;
+
+extern "C" size_t gnode_sage_workspace_bytes(int64_t n_nodes, int32_t c_in, int32_t c_out) {
+  Arena a(nullptr, 0);
+  SageWs w;
+  carve_sage(a, n_nodes, c_in, c_out, w);
+  return a.off;
+}
+
+extern "C" int gnode_sage_fwd(const gnode_graph* g, const float* x, int32_t ci, int32_t co, const float* wl,
+                              const float* bl, const float* wr, int32_t relu, float* out, void* workspace,
+                              size_t workspace_bytes, gnode_stream_t stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  GN_TRY(check_graph(g, "gnode_sage_fwd"));
+  GN_ARG(ci > 0 && co > 0 && x && wl && wr && out, "gnode_sage_fwd: bad argument");
+  const int64_t N = g->n_nodes;
+  Arena a(workspace, workspace_bytes);
+  SageWs w;
+  carve_sage(a, N, ci, co, w);
+  GN_ARENA_OK(a, "gnode_sage_fwd");
+  if (co <= ci) {
+    // Z = x @ [wl; wr]^T  -> out = act(A(Z_l) + Z_r + bl)
+    PackSegHost sg[2] = {{w.wcat, wl, co, ci, ci, ci, 0, 0}, {w.wcat + (size_t)co * ci, wr, co, ci, ci, ci, 0, 0}};
+    GN_TRY(pack_segments(sg, 2, s));
+    GemmNT q{};
+    q.A = x; q.lda = ci; q.B = w.wcat; q.ldb = ci; q.C = w.buf; q.ldc = 2 * co; q.M = N; q.N = 2 * co; q.K = ci;
+    GN_TRY(gemm_nt(q, s));
+    GN_TRY(agg_mean_fwd(*g, w.buf, 2 * co, out, co, co, w.buf + co, 2 * co, bl, relu ? 1 : 0, s));
+  } else {
+    // cat = [A(x) | x] -> out = act(cat @ [wl | wr]^T + bl)
+    PackSegHost sg[3] = {{w.wcat, wl, co, ci, ci, 2 * ci, 0, 0},
+                         {w.wcat + ci, wr, co, ci, ci, 2 * ci, 0, 0},
+                         {w.buf + ci, x, (int)N, ci, ci, 2 * ci, 0, 0}};
+    GN_TRY(pack_segments(sg, 3, s));
+    GN_TRY(agg_mean_fwd(*g, x, ci, w.buf, 2 * ci, ci, nullptr, 0, nullptr, 0, s));
+    GemmNT q{};
+    q.A = w.buf; q.lda = 2 * ci; q.B = w.wcat; q.ldb = 2 * ci; q.C = out; q.ldc = co; q.M = N; q.N = co; q.K = 2 * ci;
+    q.bias = bl; q.relu = relu ? 1 : 0;
+    GN_TRY(gemm_nt(q, s));
+  }
+  return GNODE_OK;
+}
+
+extern "C" int gnode_sage_bwd(const gnode_graph* g, const float* x, const float* out, const float* grad_out,
+                              int32_t ci, int32_t co, const float* wl, const float* wr, int32_t relu, float* grad_x,
+                              float* grad_wl, float* grad_bl, float* grad_wr, void* workspace, size_t workspace_bytes,
+                              gnode_stream_t stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  GN_TRY(check_graph(g, "gnode_sage_bwd"));
+  GN_ARG(ci > 0 && co > 0 && x && grad_out && wl && wr, "gnode_sage_bwd: bad argument");
+  GN_ARG(!relu || out, "gnode_sage_bwd: the layer output is required for the ReLU mask");
+  const int64_t N = g->n_nodes;
+  Arena a(workspace, workspace_bytes);
+  SageWs w;
+  carve_sage(a, N, ci, co, w);
+  GN_ARENA_OK(a, "gnode_sage_bwd");
+  // gz = [A^T(gm) | gm] with gm = grad_out * act'(out)
+  const float* gm = grad_out;
+  if (relu) {
+    GN_TRY(relu_mask(grad_out, out, w.gm, N * (int64_t)co, s));
+    gm = w.gm;
+  }
+  {
+    PackSegHost sg[1] = {{w.gz + co, gm, (int)N, co, co, 2 * co, 0, 0}};
+    GN_TRY(pack_segments(sg, 1, s));
+  }
+  GN_TRY(agg_mean_bwd(*g, gm, co, w.gz, 2 * co, co, nullptr, 0, nullptr, 0, s));
+  if (grad_x) {
+    // grad_x = gz @ [wl; wr]   -> NT with wcatT [ci, 2co]
+    PackSegHost sg[2] = {{w.wcatT, wl, co, ci, ci, 2 * co, 1, 0}, {w.wcatT + co, wr, co, ci, ci, 2 * co, 1, 0}};
+    GN_TRY(pack_segments(sg, 2, s));
+    GemmNT q{};
+    q.A = w.gz; q.lda = 2 * co; q.B = w.wcatT; q.ldb = 2 * co; q.C = grad_x; q.ldc = ci; q.M = N; q.N = ci; q.K = 2 * co;
+    GN_TRY(gemm_nt(q, s));
+  }
+  if (grad_wl || grad_wr) {
+    GN_CUDA(cudaMemsetAsync(w.dwcat, 0, sizeof(float) * 2 * co * ci, s));
+    GemmTN q{};
+    q.A = w.gz; q.lda = 2 * co; q.P = 2 * co; q.B = x; q.ldb = ci; q.Q = ci; q.Nrows = N; q.C = w.dwcat; q.ldc = ci;
+    GN_TRY(gemm_tn(q, w.partials, s));
+    PackSegHost sg[2];
+    int n = 0;
+    if (grad_wl) sg[n++] = PackSegHost{grad_wl, w.dwcat, co, ci, ci, ci, 0, 1};
+    if (grad_wr) sg[n++] = PackSegHost{grad_wr, w.dwcat + (size_t)co * ci, co, ci, ci, ci, 0, 1};
+    GN_TRY(pack_segments(sg, n, s));
+  }
+  if (grad_bl) GN_TRY(colsum_accum(gm, co, N, co, grad_bl, 1.f, w.colpart, s));
+  return GNODE_OK;
+}

@@ -1,0 +1,229 @@
+"""Graph containers and graph construction for the GNODE path.
+
+Host-side mirror of the reference's input contract:
+
+* ``Data`` / ``Batch`` -- the attributes of ``torch_geometric.data.Data`` / ``Batch`` that the
+  reference path touches (``x``, ``edge_index``, ``batch``, ``ptr``, ``is_current_agent``, ``.to()``,
+  ``Batch.from_data_list``; scripts/train_gde.py:69-71,131,182,367,475).  A real PyG ``Batch`` is
+  accepted everywhere these duck types are.
+* ``GraphConverter`` -- same constructor / methods / outputs as scripts/train_gde.py:108-271, with the
+  O(n^2) Python pair loop replaced by vectorised float32 numpy (bit-exact: same expression
+  ``sqrt(sum((p_i - p_j)**2)) < thr`` in the observation dtype, same emission order).
+* ``spatial_edges_cuda`` -- the same edges for many snapshots at once on the GPU
+  (``gnode_spatial_edges``), bit-exact.
+* ``TrajectoryBatch`` / ``collate_trajectory_batches`` -- scripts/train_gde.py:273-276,363-375.
+"""
+from __future__ import annotations
+
+from collections import deque
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+class Data:
+    """Attribute bag with the ``Data`` surface the reference uses."""
+
+    def __init__(self, x: Optional[torch.Tensor] = None, edge_index: Optional[torch.Tensor] = None, **kwargs):
+        self.x = x
+        self.edge_index = edge_index
+        for k, v in kwargs.items():
+            setattr(self, k, v)
+
+    @property
+    def num_nodes(self) -> int:
+        return int(self.x.size(0))
+
+    @property
+    def num_edges(self) -> int:
+        return int(self.edge_index.size(1))
+
+    def keys(self):
+        return [k for k, v in self.__dict__.items() if not k.startswith("_") and v is not None]
+
+    def to(self, device, non_blocking: bool = False):
+        for k in self.keys():
+            v = getattr(self, k)
+            if torch.is_tensor(v):
+                setattr(self, k, v.to(device, non_blocking=non_blocking))
+        # cached device-side CSR (see graph_cache) does not survive a move
+        self.__dict__.pop("_gnode_csr", None)
+        return self
+
+    def pin_memory(self):
+        for k in self.keys():
+            v = getattr(self, k)
+            if torch.is_tensor(v) and not v.is_cuda:
+                setattr(self, k, v.pin_memory())
+        return self
+
+    def __repr__(self):
+        parts = [f"{k}={list(getattr(self, k).shape)}" if torch.is_tensor(getattr(self, k)) else f"{k}={getattr(self, k)}"
+                 for k in self.keys()]
+        return f"{type(self).__name__}({', '.join(parts)})"
+
+
+class Batch(Data):
+    """Disjoint union of graphs (``Batch.from_data_list`` semantics [upstream PyG])."""
+
+    @classmethod
+    def from_data_list(cls, data_list: Sequence[Data]) -> "Batch":
+        sizes = [int(d.x.size(0)) for d in data_list]
+        ptr = torch.zeros(len(sizes) + 1, dtype=torch.long)
+        ptr[1:] = torch.cumsum(torch.tensor(sizes, dtype=torch.long), 0)
+        out = cls(x=torch.cat([d.x for d in data_list], dim=0))
+        eis = [d.edge_index + int(off) for d, off in zip(data_list, ptr[:-1])]
+        out.edge_index = torch.cat(eis, dim=1) if eis else torch.empty((2, 0), dtype=torch.long)
+        out.batch = torch.repeat_interleave(torch.arange(len(sizes), dtype=torch.long),
+                                            torch.tensor(sizes, dtype=torch.long))
+        out.ptr = ptr
+        masks = [getattr(d, "is_current_agent", None) for d in data_list]
+        if all(m is not None for m in masks) and masks:
+            out.is_current_agent = torch.cat(masks, dim=0)
+        out.num_graphs = len(sizes)
+        return out
+
+    def shard(self, rank: int, world_size: int) -> "Batch":
+        """Contiguous range of whole graphs for one data-parallel rank (graphs never span ranks)."""
+        G = int(self.ptr.numel() - 1)
+        lo, hi = (G * rank) // world_size, (G * (rank + 1)) // world_size
+        n0, n1 = int(self.ptr[lo]), int(self.ptr[hi])
+        ei = self.edge_index
+        sel = (ei[1] >= n0) & (ei[1] < n1)
+        out = Batch(x=self.x[n0:n1], edge_index=ei[:, sel] - n0)
+        out.batch = self.batch[n0:n1] - lo
+        out.ptr = self.ptr[lo:hi + 1] - n0
+        if getattr(self, "is_current_agent", None) is not None:
+            out.is_current_agent = self.is_current_agent[n0:n1]
+        out.num_graphs = hi - lo
+        return out
+
+
+# ----------------------------------------------------------------------------------------------
+# GraphConverter
+# ----------------------------------------------------------------------------------------------
+def _pair_edges(loc: np.ndarray, threshold: float) -> np.ndarray:
+    """[2, E] int64 spatial edges of one snapshot, order (i,j),(j,i) for i<j lexicographic."""
+    n = loc.shape[0]
+    if n < 2:
+        return np.empty((2, 0), dtype=np.int64)
+    iu, ju = np.triu_indices(n, k=1)
+    diff = loc[iu] - loc[ju]
+    # same arithmetic as np.sqrt(np.sum((a - b) ** 2)) on a length-2 vector in loc.dtype
+    d = np.sqrt((diff[:, 0] ** 2) + (diff[:, 1] ** 2))
+    hit = d < threshold  # python-float threshold is a weak scalar: compared in loc.dtype, as in the reference
+    iu, ju = iu[hit], ju[hit]
+    e = np.empty((2, 2 * iu.size), dtype=np.int64)
+    e[0, 0::2], e[1, 0::2] = iu, ju
+    e[0, 1::2], e[1, 1::2] = ju, iu
+    return e
+
+
+class GraphConverter:
+    """Drop-in for scripts/train_gde.py:108-271 (same ctor, methods and output ``Data``)."""
+
+    def __init__(self, num_agvs, num_pickers, distance_threshold: float = 3.0, temporal_window: int = 5):
+        self.num_agvs = num_agvs
+        self.num_pickers = num_pickers
+        self.distance_threshold = distance_threshold
+        self.temporal_window = temporal_window
+        self.graph_history = deque(maxlen=temporal_window)
+
+    def reset_history(self):
+        self.graph_history.clear()
+
+    def _standardize_observations(self, observations) -> np.ndarray:
+        if isinstance(observations, np.ndarray) and observations.dtype == object:
+            rows = observations.tolist()
+        elif isinstance(observations, list):
+            rows = observations
+        else:
+            return observations
+        width = max(len(r) for r in rows)
+        out = np.zeros((len(rows), width), dtype=np.float32)
+        for i, r in enumerate(rows):
+            r = np.array(r, dtype=np.float32)
+            out[i, :len(r)] = r
+        return out
+
+    def _extract_locations_by_agent_type(self, observations: np.ndarray) -> np.ndarray:
+        n = len(observations)
+        agv = np.arange(n) < self.num_agvs
+        loc = np.empty((n, 2), dtype=observations.dtype)
+        loc[agv] = observations[agv][:, 3:5]
+        loc[~agv] = observations[~agv][:, 0:2]
+        return loc
+
+    def _compute_spatial_edges(self, locations: np.ndarray) -> torch.Tensor:
+        return torch.from_numpy(_pair_edges(np.asarray(locations), self.distance_threshold))
+
+    def _compute_temporal_edges_with_window(self, num_agents: int) -> torch.Tensor:
+        k = len(self.graph_history) - 1
+        if k <= 0:
+            return torch.empty((2, 0), dtype=torch.long)
+        a = torch.arange(num_agents, dtype=torch.long)
+        return torch.stack([(k - 1) * num_agents + a, k * num_agents + a], dim=0)
+
+    def _build_graph_from_observation(self, observations) -> Data:
+        obs = self._standardize_observations(observations)
+        n = len(obs)
+        x_t = torch.tensor(obs, dtype=torch.float32)
+        e_t = self._compute_spatial_edges(self._extract_locations_by_agent_type(obs))
+        self.graph_history.append(Data(x=x_t, edge_index=e_t))
+        k = len(self.graph_history) - 1
+        x = torch.cat([g.x for g in self.graph_history], dim=0)
+        parts = [self.graph_history[i].edge_index + i * n for i in range(k)]
+        if e_t.shape[1] > 0:
+            parts.append(e_t + k * n)
+        t_e = self._compute_temporal_edges_with_window(n)
+        if t_e.shape[1] > 0:
+            parts.append(t_e)
+        edge_index = torch.cat(parts, dim=1) if parts else torch.empty((2, 0), dtype=torch.long)
+        mask = torch.zeros(x.size(0), dtype=torch.bool)
+        mask[k * n:(k + 1) * n] = True
+        return Data(x=x, edge_index=edge_index, is_current_agent=mask)
+
+
+def spatial_edges_cuda(pos: torch.Tensor, threshold: float):
+    """Spatial edges of many snapshots at once on the GPU (bit-exact with ``GraphConverter``).
+
+    pos: CUDA float32 [n_snap, n_agents, 2] of (y, x).  Returns ``(counts int32 [n_snap],
+    edges int32 [n_snap, n_agents*(n_agents-1), 2])``; only the first ``counts[s]`` rows of
+    ``edges[s]`` are valid, each row = (src, dst), in the reference's emission order.
+    """
+    pos = _lib.require_cuda_f32(pos, "pos")
+    n_snap, n, two = pos.shape
+    assert two == 2
+    counts = torch.empty(n_snap, dtype=torch.int32, device=pos.device)
+    edges = torch.empty((n_snap, max(n * (n - 1), 1), 2), dtype=torch.int32, device=pos.device)
+    _lib.check(_lib.lib().gnode_spatial_edges(_lib.ptr(pos), n_snap, n, float(threshold), _lib.ptr(counts),
+                                              _lib.ptr(edges), _lib.stream_ptr(pos.device)), "gnode_spatial_edges")
+    return counts, edges
+
+
+# ----------------------------------------------------------------------------------------------
+# Batching (scripts/train_gde.py:273-276, 336-375)
+# ----------------------------------------------------------------------------------------------
+class TrajectoryBatch:
+    def __init__(self, graphs, next_positions: torch.Tensor):
+        self.graphs = graphs
+        self.next_positions = next_positions
+
+
+def extract_positions_from_graph(graph: Data, num_agvs: int, num_pickers: int) -> torch.Tensor:
+    """scripts/train_gde.py:336-355 (reads the first n rows of the window graph -- reference quirk kept)."""
+    parts = []
+    if num_agvs > 0:
+        parts.append(graph.x[:num_agvs][:, [4, 3]])
+    if num_pickers > 0:
+        parts.append(graph.x[num_agvs:num_agvs + num_pickers][:, [1, 0]])
+    return torch.cat(parts, dim=0)
+
+
+def collate_trajectory_batches(batch_list: List[TrajectoryBatch]) -> TrajectoryBatch:
+    graphs = Batch.from_data_list([b.graphs for b in batch_list])
+    nxt = torch.stack([b.next_positions for b in batch_list], dim=0)
+    return TrajectoryBatch(graphs=graphs, next_positions=nxt)

@@ -1,0 +1,81 @@
+"""Device-side CSR of a PyG-style ``edge_index`` (built once per batch, cached).
+
+The reference hands an unsorted int64 ``edge_index`` [2, E] to every SAGEConv of every RK stage
+(scripts/train_gde.py:74-75 -> :36,39,43).  Here the topology is bucketed once into
+destination-sorted and source-sorted int32 CSR (``gnode_csr_build``) and reused by every kernel.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from collections import OrderedDict
+from typing import Optional
+
+import torch
+
+from . import _lib
+
+
+class CSRGraph:
+    """int32 CSR (by destination) + transpose CSR (by source) living on one CUDA device."""
+
+    def __init__(self, edge_index: torch.Tensor, num_nodes: int):
+        if not edge_index.is_cuda:
+            raise _lib.GnodeError("edge_index must live on a CUDA device; libgnode_b200 has no CPU path")
+        if edge_index.dim() != 2 or edge_index.size(0) != 2:
+            raise _lib.GnodeError(f"edge_index must be [2, E] (got {list(edge_index.shape)})")
+        if edge_index.dtype != torch.int64:
+            edge_index = edge_index.to(torch.int64)
+        edge_index = edge_index.contiguous()
+        dev = edge_index.device
+        N, E = int(num_nodes), int(edge_index.size(1))
+        self.num_nodes, self.num_edges, self.device = N, E, dev
+        self.rowptr = torch.empty(N + 1, dtype=torch.int32, device=dev)
+        self.col = torch.empty(max(E, 1), dtype=torch.int32, device=dev)
+        self.t_rowptr = torch.empty(N + 1, dtype=torch.int32, device=dev)
+        self.t_col = torch.empty(max(E, 1), dtype=torch.int32, device=dev)
+        L = _lib.lib()
+        nbytes = L.gnode_csr_workspace_bytes(N, E)
+        ws = _lib.WORKSPACE.get(nbytes, dev, "csr")
+        with torch.cuda.device(dev):
+            _lib.check(L.gnode_csr_build(_lib.ptr(edge_index), E, N, _lib.ptr(self.rowptr), _lib.ptr(self.col),
+                                         _lib.ptr(self.t_rowptr), _lib.ptr(self.t_col), _lib.ptr(ws), ws.numel(),
+                                         _lib.stream_ptr(dev)), "gnode_csr_build")
+        self.struct = _lib.GnodeGraph(N, E, self.rowptr.data_ptr(), self.col.data_ptr(), self.t_rowptr.data_ptr(),
+                                      self.t_col.data_ptr())
+
+    def ref(self):
+        return C.byref(self.struct)
+
+
+_CACHE: "OrderedDict[tuple, tuple]" = OrderedDict()  # key -> (keyed edge_index tensor, CSRGraph)
+_CACHE_MAX = 8
+
+
+def csr_for(edge_index: torch.Tensor, num_nodes: int, holder: Optional[object] = None) -> CSRGraph:
+    """CSR of ``edge_index``; cached on ``holder`` (e.g. the batch object) and in a small LRU keyed by
+    the tensor's storage, shape and version counter.  Every cache entry keeps the keyed tensor alive,
+    so its address cannot be recycled for a different edge list while the entry exists."""
+    key = (edge_index.data_ptr(), tuple(edge_index.shape), edge_index._version, int(num_nodes), str(edge_index.device))
+    if holder is not None:
+        cached = getattr(holder, "__dict__", {}).get("_gnode_csr")
+        if cached is not None and cached[0] == key:
+            return cached[1]
+    entry = _CACHE.get(key)
+    if entry is None or entry[0] is not edge_index and entry[0].data_ptr() != edge_index.data_ptr():
+        entry = (edge_index, CSRGraph(edge_index, num_nodes))
+        _CACHE[key] = entry
+        while len(_CACHE) > _CACHE_MAX:
+            _CACHE.popitem(last=False)
+    else:
+        _CACHE.move_to_end(key)
+    g = entry[1]
+    if holder is not None:
+        try:
+            holder.__dict__["_gnode_csr"] = (key, g, edge_index)
+        except Exception:
+            pass
+    return g
+
+
+def clear_cache():
+    _CACHE.clear()

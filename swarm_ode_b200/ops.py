@@ -1,0 +1,362 @@
+"""torch.autograd bridges onto the C ABI (one Function per fused op).
+
+PyTorch is plumbing here: it owns device memory, streams and the parameter tensors; every FLOP of
+the GNODE path runs inside ``libgnode_b200.so``.  No function in this module has a CPU or eager
+fallback -- CPU tensors raise ``GnodeError``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Callable, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import METHODS, GnodeError
+from .graph import CSRGraph
+
+_f32 = _lib.require_cuda_f32
+
+
+def _ws(nbytes: int, device) -> torch.Tensor:
+    return _lib.WORKSPACE.get(nbytes, device)
+
+
+def _sage3_params(D: int, H: int, w: Sequence[torch.Tensor]) -> _lib.GnodeSage3Params:
+    shapes = [(H, D), (H,), (H, D), (H, H), (H,), (H, H), (D, H), (D,), (D, H)]
+    for t, shp in zip(w, shapes):
+        if tuple(t.shape) != shp:
+            raise GnodeError(f"GraphODEFunc parameter has shape {tuple(t.shape)}, expected {shp}")
+    return _lib.GnodeSage3Params(D, H, *[t.data_ptr() for t in w])
+
+
+def _float_array(vals) -> "C.Array":
+    return (C.c_float * len(vals))(*[float(v) for v in vals])
+
+
+# ----------------------------------------------------------------------------------------------
+# single SAGEConv layer
+# ----------------------------------------------------------------------------------------------
+class _SageConvFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, wl, bl, wr, graph: CSRGraph, relu: bool):
+        x, wl, bl, wr = _f32(x, "x"), _f32(wl, "lin_l.weight"), _f32(bl, "lin_l.bias"), _f32(wr, "lin_r.weight")
+        N, ci = x.shape
+        co = wl.shape[0]
+        if N != graph.num_nodes:
+            raise GnodeError(f"x has {N} rows but the graph has {graph.num_nodes} nodes")
+        out = torch.empty((N, co), dtype=torch.float32, device=x.device)
+        L = _lib.lib()
+        ws = _ws(L.gnode_sage_workspace_bytes(N, ci, co), x.device)
+        with torch.cuda.device(x.device):
+            _lib.check(L.gnode_sage_fwd(graph.ref(), _lib.ptr(x), ci, co, _lib.ptr(wl), _lib.ptr(bl), _lib.ptr(wr),
+                                        int(relu), _lib.ptr(out), _lib.ptr(ws), ws.numel(),
+                                        _lib.stream_ptr(x.device)), "gnode_sage_fwd")
+        ctx.graph, ctx.relu = graph, relu
+        ctx.save_for_backward(x, wl, wr, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, wl, wr, out = ctx.saved_tensors
+        g = _f32(g, "grad_out")
+        N, ci = x.shape
+        co = wl.shape[0]
+        need_x, need_wl, need_bl, need_wr = ctx.needs_input_grad[:4]
+        gx = torch.empty_like(x) if need_x else None
+        gwl = torch.zeros_like(wl) if need_wl else None
+        gbl = torch.zeros(co, dtype=torch.float32, device=x.device) if need_bl else None
+        gwr = torch.zeros_like(wr) if need_wr else None
+        L = _lib.lib()
+        ws = _ws(L.gnode_sage_workspace_bytes(N, ci, co), x.device)
+        with torch.cuda.device(x.device):
+            _lib.check(L.gnode_sage_bwd(ctx.graph.ref(), _lib.ptr(x), _lib.ptr(out), _lib.ptr(g), ci, co, _lib.ptr(wl),
+                                        _lib.ptr(wr), int(ctx.relu), _lib.ptr(gx), _lib.ptr(gwl), _lib.ptr(gbl),
+                                        _lib.ptr(gwr), _lib.ptr(ws), ws.numel(), _lib.stream_ptr(x.device)),
+                       "gnode_sage_bwd")
+        return gx, gwl, gbl, gwr, None, None
+
+
+def sage_conv(x, wl, bl, wr, graph: CSRGraph, relu: bool = False) -> torch.Tensor:
+    return _SageConvFn.apply(x, wl, bl, wr, graph, relu)
+
+
+# ----------------------------------------------------------------------------------------------
+# GraphODEFunc (three layers) -- one RHS evaluation
+# ----------------------------------------------------------------------------------------------
+class _RhsFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, graph: CSRGraph, *w):
+        x = _f32(x, "x")
+        w = [_f32(t, "param") for t in w]
+        N, D = x.shape
+        H = w[0].shape[0]
+        if N != graph.num_nodes:
+            raise GnodeError(f"x has {N} rows but the graph has {graph.num_nodes} nodes")
+        p = _sage3_params(D, H, w)
+        out = torch.empty_like(x)
+        L = _lib.lib()
+        ws = _ws(L.gnode_rhs_workspace_bytes(N, D, H), x.device)
+        with torch.cuda.device(x.device):
+            _lib.check(L.gnode_rhs_fwd(graph.ref(), C.byref(p), _lib.ptr(x), _lib.ptr(out), _lib.ptr(ws), ws.numel(),
+                                       _lib.stream_ptr(x.device)), "gnode_rhs_fwd")
+        ctx.graph = graph
+        ctx.save_for_backward(x, *w)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, *w = ctx.saved_tensors
+        g = _f32(g, "grad_out")
+        N, D = x.shape
+        H = w[0].shape[0]
+        p = _sage3_params(D, H, w)
+        gx = torch.empty_like(x)
+        gw = [torch.zeros_like(t) for t in w]
+        grads = _lib.GnodeSage3Grads(*[t.data_ptr() for t in gw])
+        L = _lib.lib()
+        ws = _ws(L.gnode_rhs_workspace_bytes(N, D, H), x.device)
+        with torch.cuda.device(x.device):
+            _lib.check(L.gnode_rhs_bwd(ctx.graph.ref(), C.byref(p), _lib.ptr(x), _lib.ptr(g), _lib.ptr(gx),
+                                       C.byref(grads), _lib.ptr(ws), ws.numel(), _lib.stream_ptr(x.device)),
+                       "gnode_rhs_bwd")
+        return (gx, None, *gw)
+
+
+def gnode_rhs(x, graph: CSRGraph, params: Sequence[torch.Tensor]) -> torch.Tensor:
+    """dx/dt of GraphODEFunc; ``params`` = (w1l, b1, w1r, w2l, b2, w2r, w3l, b3, w3r)."""
+    return _RhsFn.apply(x, graph, *params)
+
+
+# ----------------------------------------------------------------------------------------------
+# fixed-grid integration with backprop through the solver
+# ----------------------------------------------------------------------------------------------
+class _IntegrateFixedFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, y0, graph: CSRGraph, method: int, t_host: Tuple[float, ...], *w):
+        y0 = _f32(y0, "y0")
+        w = [_f32(t, "param") for t in w]
+        N, D = y0.shape
+        H = w[0].shape[0]
+        if N != graph.num_nodes:
+            raise GnodeError(f"y0 has {N} rows but the graph has {graph.num_nodes} nodes")
+        p = _sage3_params(D, H, w)
+        T = len(t_host)
+        sol = torch.empty((T, N, D), dtype=torch.float32, device=y0.device)
+        L = _lib.lib()
+        ws = _ws(L.gnode_integrate_fixed_workspace_bytes(N, D, H, method, 0), y0.device)
+        tarr = _float_array(t_host)
+        with torch.cuda.device(y0.device):
+            _lib.check(L.gnode_integrate_fixed(graph.ref(), C.byref(p), method, _lib.ptr(y0), tarr, T, _lib.ptr(sol),
+                                               _lib.ptr(ws), ws.numel(), _lib.stream_ptr(y0.device)),
+                       "gnode_integrate_fixed")
+        ctx.graph, ctx.method, ctx.t_host = graph, method, t_host
+        ctx.save_for_backward(sol, *w)
+        return sol
+
+    @staticmethod
+    def backward(ctx, gsol):
+        sol, *w = ctx.saved_tensors
+        gsol = _f32(gsol, "grad_solution")
+        T, N, D = sol.shape
+        H = w[0].shape[0]
+        p = _sage3_params(D, H, w)
+        gy0 = torch.empty((N, D), dtype=torch.float32, device=sol.device)
+        gw = [torch.zeros_like(t) for t in w]
+        grads = _lib.GnodeSage3Grads(*[t.data_ptr() for t in gw])
+        L = _lib.lib()
+        ws = _ws(L.gnode_integrate_fixed_workspace_bytes(N, D, H, ctx.method, 1), sol.device)
+        tarr = _float_array(ctx.t_host)
+        with torch.cuda.device(sol.device):
+            _lib.check(L.gnode_integrate_fixed_bwd(ctx.graph.ref(), C.byref(p), ctx.method, _lib.ptr(sol), tarr, T,
+                                                   _lib.ptr(gsol), _lib.ptr(gy0), C.byref(grads), _lib.ptr(ws),
+                                                   ws.numel(), _lib.stream_ptr(sol.device)),
+                       "gnode_integrate_fixed_bwd")
+        return (gy0, None, None, None, *gw)
+
+
+def _t_to_host(t) -> Tuple[float, ...]:
+    if torch.is_tensor(t):
+        return tuple(float(v) for v in t.detach().to("cpu", torch.float32).tolist())
+    return tuple(float(v) for v in t)
+
+
+def integrate_fixed(y0, graph: CSRGraph, params: Sequence[torch.Tensor], t, method: str) -> torch.Tensor:
+    """Solution [len(t), N, D] of the GraphODEFunc field on the fixed grid ``t``; differentiable."""
+    if method not in ("euler", "midpoint", "rk4"):
+        raise ValueError(f"not a fixed-grid method: {method}")
+    return _IntegrateFixedFn.apply(y0, graph, METHODS[method], _t_to_host(t), *params)
+
+
+# ----------------------------------------------------------------------------------------------
+# adaptive dopri5 (forward only)
+# ----------------------------------------------------------------------------------------------
+@dataclass
+class Dopri5Stats:
+    nfe: int = 0
+    n_accepted: int = 0
+    n_attempted: int = 0
+    first_step: float = float("nan")
+    last_dt: float = float("nan")
+    min_margin: float = float("nan")
+    error_ratios: Optional[List[float]] = None
+    dts: Optional[List[float]] = None
+    accepted: Optional[List[bool]] = None
+
+
+def _run_dopri5(call: Callable, trace_cap: int):
+    st = _lib.GnodeDopri5Stats()
+    er = (C.c_double * trace_cap)()
+    dts = (C.c_double * trace_cap)()
+    acc = (C.c_int32 * trace_cap)()
+    tr = _lib.GnodeDopri5Trace(C.cast(er, C.POINTER(C.c_double)), C.cast(dts, C.POINTER(C.c_double)),
+                               C.cast(acc, C.POINTER(C.c_int32)), trace_cap)
+    call(C.byref(st), C.byref(tr))
+    n = min(int(st.n_attempted), trace_cap)
+    return Dopri5Stats(nfe=int(st.nfe), n_accepted=int(st.n_accepted), n_attempted=int(st.n_attempted),
+                       first_step=float(st.first_step), last_dt=float(st.last_dt), min_margin=float(st.min_margin),
+                       error_ratios=[er[i] for i in range(n)], dts=[dts[i] for i in range(n)],
+                       accepted=[bool(acc[i]) for i in range(n)])
+
+
+def integrate_dopri5(y0, graph: CSRGraph, params: Sequence[torch.Tensor], t, rtol: float, atol: float,
+                     allreduce: Optional[Callable[[float, float], Tuple[float, float]]] = None,
+                     max_num_steps: int = 0, trace_cap: int = 4096):
+    """Adaptive Dormand-Prince integration of the GraphODEFunc field.  Returns ``(solution, Dopri5Stats)``.
+
+    ``allreduce(sumsq, count) -> (sumsq, count)`` (optional) sums the error-norm pieces over
+    data-parallel ranks so that all ranks take the step-size decisions of the unsharded batch.
+    """
+    y0 = _f32(y0.detach(), "y0")
+    w = [_f32(p.detach(), "param") for p in params]
+    N, D = y0.shape
+    H = w[0].shape[0]
+    if N != graph.num_nodes:
+        raise GnodeError(f"y0 has {N} rows but the graph has {graph.num_nodes} nodes")
+    p = _sage3_params(D, H, w)
+    t_host = [float(v) for v in (t.detach().to("cpu", torch.float64).tolist() if torch.is_tensor(t) else t)]
+    T = len(t_host)
+    tarr = (C.c_double * T)(*t_host)
+    sol = torch.empty((T, N, D), dtype=torch.float32, device=y0.device)
+    L = _lib.lib()
+    ws = _ws(L.gnode_integrate_dopri5_workspace_bytes(N, D, H), y0.device)
+
+    if allreduce is not None:
+        def _cb(buf, _user):
+            s, c = allreduce(buf[0], buf[1])
+            buf[0], buf[1] = float(s), float(c)
+        cb = _lib.ALLREDUCE_FN(_cb)
+    else:
+        cb = C.cast(None, _lib.ALLREDUCE_FN)
+
+    def call(st, tr):
+        with torch.cuda.device(y0.device):
+            _lib.check(L.gnode_integrate_dopri5(graph.ref(), C.byref(p), _lib.ptr(y0), tarr, T, float(rtol),
+                                                float(atol), _lib.ptr(sol), st, tr, cb, None, int(max_num_steps),
+                                                _lib.ptr(ws), ws.numel(), _lib.stream_ptr(y0.device)),
+                       "gnode_integrate_dopri5")
+
+    stats = _run_dopri5(call, trace_cap)
+    return sol, stats
+
+
+# ----------------------------------------------------------------------------------------------
+# position decoder
+# ----------------------------------------------------------------------------------------------
+class _DecoderFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, b):
+        x, w, b = _f32(x, "x"), _f32(w, "weight"), _f32(b, "bias")
+        D = x.shape[-1]
+        M = x.numel() // D
+        n_out = w.shape[0]
+        out = torch.empty(x.shape[:-1] + (n_out,), dtype=torch.float32, device=x.device)
+        L = _lib.lib()
+        with torch.cuda.device(x.device):
+            _lib.check(L.gnode_decoder_fwd(_lib.ptr(x), M, D, n_out, _lib.ptr(w), _lib.ptr(b), _lib.ptr(out),
+                                           _lib.stream_ptr(x.device)), "gnode_decoder_fwd")
+        ctx.save_for_backward(x, w)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, w = ctx.saved_tensors
+        g = _f32(g, "grad_out")
+        D = x.shape[-1]
+        M = x.numel() // D
+        n_out = w.shape[0]
+        need_x, need_w, need_b = ctx.needs_input_grad
+        gx = torch.empty_like(x) if need_x else None
+        gw = torch.zeros_like(w) if need_w else None
+        gb = torch.zeros(n_out, dtype=torch.float32, device=x.device) if need_b else None
+        L = _lib.lib()
+        ws = _ws(L.gnode_decoder_workspace_bytes(M, D, n_out), x.device)
+        with torch.cuda.device(x.device):
+            _lib.check(L.gnode_decoder_bwd(_lib.ptr(x), _lib.ptr(g), M, D, n_out, _lib.ptr(w), _lib.ptr(gx),
+                                           _lib.ptr(gw), _lib.ptr(gb), _lib.ptr(ws), ws.numel(),
+                                           _lib.stream_ptr(x.device)), "gnode_decoder_bwd")
+        return gx, gw, gb
+
+
+def decode_positions(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
+    """``F.linear(x, weight, bias)`` for a tall-skinny decoder (n_out <= 8) over [..., D]."""
+    return _DecoderFn.apply(x, weight, bias)
+
+
+# ----------------------------------------------------------------------------------------------
+# MLP vector field (ODEFunction), forward only
+# ----------------------------------------------------------------------------------------------
+def _mlp_params(w: Sequence[torch.Tensor]):
+    w0, b0, w1, b1, w2, b2 = w
+    h, H = w0.shape
+    if tuple(w1.shape) != (h, h) or tuple(w2.shape) != (H, h) or b0.numel() != h or b1.numel() != h or b2.numel() != H:
+        raise GnodeError("ODEFunction parameters have inconsistent shapes")
+    return _lib.GnodeMlpParams(H, h, *[t.data_ptr() for t in w]), H, h
+
+
+def mlp_rhs(x: torch.Tensor, params: Sequence[torch.Tensor]) -> torch.Tensor:
+    x = _f32(x.detach(), "x")
+    w = [_f32(p.detach(), "param") for p in params]
+    p, H, h = _mlp_params(w)
+    M = x.shape[0]
+    out = torch.empty_like(x)
+    L = _lib.lib()
+    ws = _ws(L.gnode_mlp_ode_workspace_bytes(M, H, h, 0), x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(L.gnode_mlp_rhs_fwd(C.byref(p), _lib.ptr(x), M, _lib.ptr(out), _lib.ptr(ws), ws.numel(),
+                                       _lib.stream_ptr(x.device)), "gnode_mlp_rhs_fwd")
+    return out
+
+
+def mlp_integrate(y0: torch.Tensor, params: Sequence[torch.Tensor], t, method: str, rtol: float = 1e-7,
+                  atol: float = 1e-9, max_num_steps: int = 0, trace_cap: int = 4096):
+    """Integrate the MLP field; returns ``(solution [T, M, H], Dopri5Stats | None)``."""
+    y0 = _f32(y0.detach(), "y0")
+    w = [_f32(p.detach(), "param") for p in params]
+    p, H, h = _mlp_params(w)
+    M = y0.shape[0]
+    L = _lib.lib()
+    m = METHODS[method]
+    ws = _ws(L.gnode_mlp_ode_workspace_bytes(M, H, h, m), y0.device)
+    if method == "dopri5":
+        t_host = [float(v) for v in (t.detach().to("cpu", torch.float64).tolist() if torch.is_tensor(t) else t)]
+        T = len(t_host)
+        tarr = (C.c_double * T)(*t_host)
+        sol = torch.empty((T, M, H), dtype=torch.float32, device=y0.device)
+
+        def call(st, tr):
+            with torch.cuda.device(y0.device):
+                _lib.check(L.gnode_mlp_integrate_dopri5(C.byref(p), _lib.ptr(y0), M, tarr, T, float(rtol), float(atol),
+                                                        _lib.ptr(sol), st, tr, int(max_num_steps), _lib.ptr(ws),
+                                                        ws.numel(), _lib.stream_ptr(y0.device)),
+                           "gnode_mlp_integrate_dopri5")
+        return sol, _run_dopri5(call, trace_cap)
+    t_host = _t_to_host(t)
+    T = len(t_host)
+    sol = torch.empty((T, M, H), dtype=torch.float32, device=y0.device)
+    with torch.cuda.device(y0.device):
+        _lib.check(L.gnode_mlp_integrate_fixed(C.byref(p), m, _lib.ptr(y0), M, _float_array(t_host), T, _lib.ptr(sol),
+                                               _lib.ptr(ws), ws.numel(), _lib.stream_ptr(y0.device)),
+                   "gnode_mlp_integrate_fixed")
+    return sol, None
