@@ -1,0 +1,381 @@
+#!/usr/bin/env python
+"""bench.py -- GNODE agent-state-steps/s on B200 (the reference's headline metric, BASELINE.json).
+
+    python bench.py --gpus N --steps K --warmup W              # this framework (CUDA, sm_100a)
+    python bench.py --impl reference --gpus N --steps K ...    # the reference's CPU path (oracle port)
+
+Workload (N=1): BASELINE.json configs[1] -- "GNODE, RK4 forward+backward training step, 4096
+trajectories on 1 B200 (fp32)", medium warehouse, 12 AGVs + 7 pickers, D=399, 95 nodes/graph.
+A step = one full training step of scripts/train_gde.py:478-495 (forward through the rk4 solver,
+masked MSE, backward through the solver, grad clip, Adam) over one synthetic batch.
+Metric unit = one node x one vector-field (RK stage) evaluation = "agent-state-step".
+With N GPUs every rank runs its own 4096-graph shard (weak scaling) and gradients are all-reduced.
+
+One JSON line is printed by rank 0; see DESIGN.md "Measurement" for every key.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch
+import torch.distributed as dist
+
+RK_STAGES = {"euler": 1, "midpoint": 2, "rk4": 4}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--graphs", type=int, default=4096, help="trajectories (graphs) per GPU")
+    ap.add_argument("--solver", default="rk4", choices=list(RK_STAGES))
+    ap.add_argument("--engine", default="auto", choices=["auto", "simt", "tc"])
+    ap.add_argument("--cpu-graphs", type=int, default=0, help="graphs per CPU-baseline step (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {"hbm_gbs": float(p["hbm_gbs"]), "bf16_tflops": float(p.get("bf16_tflops_sustained", p["bf16_tflops"])),
+                "bf16_tflops_burst": float(p["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1400.0, "bf16_tflops_burst": 1590.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def algorithmic_bytes_per_unit(D: int, mean_in_degree: float) -> float:
+    """Q = 4D (read stage input) + 4D (write stage derivative) + 4*dbar (CSR cols) + 4 (rowptr)."""
+    return 8.0 * D + 4.0 * mean_in_degree + 4.0
+
+
+def algorithmic_flops_per_unit(D: int, H: int) -> float:
+    return 8.0 * D * H + 4.0 * H * H
+
+
+# ------------------------------------------------------------------------------------------------
+def run_reference(args, rank: int, world: int):
+    """The reference's CPU path (pure-torch restatement of torch_geometric + torchdiffeq, oracle/) timed on
+    the box's host cores with all threads.  Rank 0 only."""
+    if rank != 0:
+        return
+    from oracle.train_gde_ref import GraphODERef, train_step_loss_ref
+    from oracle.pyg_ref import RefBatch
+    import swarm_ode_b200.synthetic as syn
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    B = args.cpu_graphs or 128
+    batch, nxt = syn.warehouse_batch(B, seed=0)
+    D = batch.x.shape[1]
+    model = GraphODERef(D, 12, 7, hidden_dim=64, ode_solver=args.solver)
+    syn.init_weights(model, seed=1, conv3_scale=0.1)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-4)
+    rb = RefBatch(x=batch.x, edge_index=batch.edge_index)
+    rb.batch, rb.is_current_agent = batch.batch, batch.is_current_agent
+    t = torch.tensor([0.0, 1.0])
+
+    def step():
+        opt.zero_grad()
+        loss = train_step_loss_ref(model, rb, nxt, t)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm=1.0)
+        opt.step()
+        return float(loss.detach())
+
+    for _ in range(max(args.warmup, 1)):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / args.steps
+    units = batch.x.shape[0] * RK_STAGES[args.solver]
+    value = units / dt
+    sample = f"{B} graphs ({batch.x.shape[0]} nodes) per step, full train step, {args.steps} steps"
+    line = {
+        "impl": "reference", "metric": "GNODE agent-state-steps/sec (RK stages)", "value": value,
+        "unit": "agent-state-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": f"GNODE {args.solver} fwd+bwd train step, medium warehouse 12 AGV + 7 pickers, D={D}, "
+                               f"{B} trajectories/step (bounded CPU sample of the 4096-trajectory config)",
+                   "graphs_per_step": B, "nodes_per_step": batch.x.shape[0], "node_dim": D, "hidden_dim": 64,
+                   "solver": args.solver},
+        "cpu_baseline": {"value": value, "unit": "agent-state-steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "agent-state-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline(args, D: int):
+    """Bounded oracle run (about 10-30 s) on rank 0 at N=1 for the 'cpu_baseline' object."""
+    from oracle.train_gde_ref import GraphODERef, train_step_loss_ref
+    from oracle.pyg_ref import RefBatch
+    import swarm_ode_b200.synthetic as syn
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    B = args.cpu_graphs or 128
+    batch, nxt = syn.warehouse_batch(B, seed=0)
+    model = GraphODERef(D, 12, 7, hidden_dim=64, ode_solver=args.solver)
+    syn.init_weights(model, seed=1, conv3_scale=0.1)
+    rb = RefBatch(x=batch.x, edge_index=batch.edge_index)
+    rb.batch, rb.is_current_agent = batch.batch, batch.is_current_agent
+    t = torch.tensor([0.0, 1.0])
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-4)
+
+    def step():
+        opt.zero_grad()
+        loss = train_step_loss_ref(model, rb, nxt, t)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm=1.0)
+        opt.step()
+
+    step()
+    t0 = time.perf_counter(); step(); one = time.perf_counter() - t0
+    reps = max(2, min(50, int(12.0 / max(one, 1e-3))))
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        step()
+    dt = (time.perf_counter() - t0) / reps
+    units = batch.x.shape[0] * RK_STAGES[args.solver]
+    return {"value": units / dt, "unit": "agent-state-steps/s", "cores": cores, "kind": "port",
+            "sample": f"{reps} train steps of {B} graphs ({batch.x.shape[0]} nodes), same solver/weights; "
+                      f"pure-torch restatement of the PyG+torchdiffeq reference path",
+            "ms_per_step": dt * 1e3}
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args, rank: int, world: int, local_rank: int):
+    import swarm_ode_b200 as S
+    from swarm_ode_b200 import _lib
+    from swarm_ode_b200.dist import masked_mse_train_step
+    from swarm_ode_b200 import graph as G
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU path)"
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    S.set_engine(args.engine)
+
+    # ---- synthetic batch: pinned on the host (e2e leg copies it every step), resident copy for `value`
+    host, nxt_host = S.synthetic.warehouse_batch(args.graphs, seed=rank)
+    host.pin_memory()
+    nxt_host = nxt_host.pin_memory()
+    D = host.x.shape[1]
+    H = 64
+    N_nodes, E = host.x.shape[0], host.edge_index.shape[1]
+    stages = RK_STAGES[args.solver]
+    units_per_step_rank = N_nodes * stages
+
+    model = S.GraphODE(D, 12, 7, hidden_dim=H, ode_solver=args.solver)
+    S.synthetic.init_weights(model, seed=1, conv3_scale=0.1)
+    model = model.to(dev)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-4)
+    t_dev = torch.tensor([0.0, 1.0], device=dev)
+
+    def to_device(non_blocking=True):
+        b = S.Batch(x=host.x.to(dev, non_blocking=non_blocking), edge_index=host.edge_index.to(dev, non_blocking=non_blocking))
+        b.batch = host.batch.to(dev, non_blocking=non_blocking)
+        b.is_current_agent = host.is_current_agent.to(dev, non_blocking=non_blocking)
+        return b, nxt_host.to(dev, non_blocking=non_blocking)
+
+    resident, nxt_res = to_device(False)
+
+    def step_resident():
+        G.clear_cache()
+        resident.__dict__.pop("_gnode_csr", None)      # a new batch every step: CSR is rebuilt inside the step
+        return masked_mse_train_step(model, opt, resident, nxt_res, t_dev)
+
+    def step_e2e():
+        G.clear_cache()
+        b, nx = to_device(True)
+        loss = masked_mse_train_step(model, opt, b, nx, t_dev)
+        return float(loss)                              # device -> host read of the step's result
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: inputs resident in HBM ----
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    launches0 = S.launch_count()
+    _lib.prof_enable(True)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        step_resident()
+    ev1.record()
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    launches = S.launch_count() - launches0
+    prof = _lib.prof_read()
+    _lib.prof_enable(False)
+    clocks = sampler.stop() if sampler else None
+    tmax = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms_step = float(tmax) / args.steps
+    value = units_per_step_rank * world / (ms_step * 1e-3)
+
+    # ---- e2e: host buffers in, loss out, every step ----
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step_e2e()
+    e1.record()
+    barrier()
+    te = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_ms = float(te) / args.steps
+    e2e_value = units_per_step_rank * world / (e2e_ms * 1e-3)
+    h2d = sum(t.numel() * t.element_size() for t in (host.x, host.edge_index, host.batch, host.is_current_agent, nxt_host))
+
+    if rank != 0:
+        return
+    pk = peaks()
+    # ---- roofline of the dominant kernel class (device time measured live with CUDA events) ----
+    prof = [p for p in prof if p["launches"] > 0 and not p["name"].startswith(("csr_build", "decoder_bwd"))]
+    prof.sort(key=lambda p: -p["ms"])
+    dom = prof[0] if prof else None
+    roof = None
+    if dom:
+        per_launch_ms = dom["ms"] / dom["launches"]
+        is_gemm = dom["name"].startswith("gemm")
+        if is_gemm:
+            ach = dom["flops"] / (dom["ms"] * 1e-3) / 1e12
+            roof = {"kernel": dom["name"], "bound": "tensor", "achieved": ach, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
+                    "frac": ach / pk["bf16_tflops"], "traffic": None,
+                    "peak_note": f"{pk['source']} cuBLAS bf16 sustained; fp32-accurate contraction (FFMA or 3xTF32)"}
+        else:
+            ach = dom["bytes"] / (dom["ms"] * 1e-3) / 1e9
+            roof = {"kernel": dom["name"], "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                    "frac": ach / pk["hbm_gbs"], "traffic": None, "peak_note": f"{pk['source']} copy bandwidth"}
+        roof["launches_per_step"] = dom["launches"] / args.steps
+        roof["ms_per_launch"] = per_launch_ms
+        roof["share_of_step"] = dom["ms"] / (ms_total if ms_total > 0 else 1)
+    dbar = E / N_nodes
+    Q = algorithmic_bytes_per_unit(D, dbar)
+    F = algorithmic_flops_per_unit(D, H)
+    # forward units + backward (F_bwd = 2F, Q_bwd = 2Q: SURVEY 8-d4)
+    step_bytes = units_per_step_rank * Q * 3.0
+    step_flops = units_per_step_rank * F * 3.0
+    step_roof = {"hbm_GBps_algorithmic": step_bytes / (ms_step * 1e-3) / 1e9,
+                 "hbm_frac": step_bytes / (ms_step * 1e-3) / 1e9 / pk["hbm_gbs"],
+                 "tflops_algorithmic": step_flops / (ms_step * 1e-3) / 1e12,
+                 "bytes_per_unit": Q, "flops_per_unit": F, "fwd_plus_bwd_factor": 3.0, "peak_source": pk["source"]}
+    kernels = [{"name": p["name"], "launches": p["launches"], "ms": round(p["ms"], 4),
+                "share": round(p["ms"] / ms_total, 4) if ms_total else None,
+                "TFLOPs": round(p["flops"] / (p["ms"] * 1e-3) / 1e12, 3) if p["ms"] > 0 else None,
+                "GBps": round(p["bytes"] / (p["ms"] * 1e-3) / 1e9, 1) if p["ms"] > 0 else None} for p in prof[:12]]
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline(args, D)
+
+    line = {
+        "metric": "GNODE agent-state-steps/sec (RK stages)", "value": value, "unit": "agent-state-steps/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"GNODE {args.solver} fwd+bwd train step (BASELINE configs[1]): medium warehouse, 12 AGV + 7 pickers, "
+                               f"D={D}, 95 nodes/graph, {args.graphs} trajectories per GPU",
+                   "graphs_per_gpu": args.graphs, "nodes_per_gpu": N_nodes, "edges_per_gpu": E, "node_dim": D,
+                   "hidden_dim": H, "solver": args.solver, "rk_stages": stages, "engine": args.engine,
+                   "parallelism": f"dp{world} (graphs sharded, gradient all-reduce only)",
+                   "l2": "inputs (x = %.0f MB per GPU) exceed the 126 MB L2; no explicit flush" % (host.x.numel() * 4 / 1e6),
+                   "csr": "rebuilt every step (new batch each step)"},
+        "e2e": {"value": e2e_value, "unit": "agent-state-steps/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": 4},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": roof,
+        "step_roofline": step_roof,
+        "kernels": kernels,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_ours(args, rank, world, local_rank)
+    finally:
+        if world > 1 and dist.is_initialized():
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

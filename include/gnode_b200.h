@@ -67,6 +67,18 @@ int gnode_set_engine(int engine);
 /* number of kernels this library has launched since load (all threads) */
 int64_t gnode_launch_count(void);
 
+/* Per-kernel-class timing (CUDA events on the launching stream) for roofline reporting.  Each entry
+ * carries the ALGORITHMIC flops / bytes of the launches it covers (computed from the shapes). */
+typedef struct {
+  char name[64];
+  int64_t launches;
+  double ms;     /* summed device time of the class */
+  double flops;  /* summed algorithmic flops         */
+  double bytes;  /* summed algorithmic bytes (compulsory global reads + writes) */
+} gnode_prof_entry;
+int gnode_prof_enable(int on);                        /* 1: reset and start collecting, 0: stop */
+int gnode_prof_read(gnode_prof_entry* out, int cap);  /* synchronises; returns the number of classes */
+
 /* ------------------------------------------------------------------------------------------
  * Graph: destination-sorted CSR (forward gather) + source-sorted CSR (transpose, for backward).
  * Inside a row, neighbours are in ascending id order, so every reduction order is deterministic.

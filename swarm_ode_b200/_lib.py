@@ -50,6 +50,11 @@ class GnodeMlpParams(C.Structure):
         (n, C.c_void_p) for n in ("w0", "b0", "w1", "b1", "w2", "b2")]
 
 
+class GnodeProfEntry(C.Structure):
+    _fields_ = [("name", C.c_char * 64), ("launches", C.c_int64), ("ms", C.c_double), ("flops", C.c_double),
+                ("bytes", C.c_double)]
+
+
 ALLREDUCE_FN = C.CFUNCTYPE(None, C.POINTER(C.c_double), C.c_void_p)
 
 _P = C.c_void_p
@@ -59,6 +64,8 @@ _SIGNATURES = {
     "gnode_abi_version": (C.c_int, []),
     "gnode_set_engine": (C.c_int, [C.c_int]),
     "gnode_launch_count": (C.c_int64, []),
+    "gnode_prof_enable": (C.c_int, [C.c_int]),
+    "gnode_prof_read": (C.c_int, [C.POINTER(GnodeProfEntry), C.c_int]),
     "gnode_csr_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int64]),
     "gnode_csr_build": (C.c_int, [_P, C.c_int64, C.c_int64, _P, _P, _P, _P, _P, C.c_size_t, _P]),
     "gnode_sage_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int32, C.c_int32]),
@@ -153,7 +160,8 @@ class Workspace:
         self._bufs = {}
 
     def get(self, nbytes: int, device, tag: str = "main") -> torch.Tensor:
-        key = (str(device), tag)
+        # one buffer per (device, stream): work on different streams may overlap in time
+        key = (str(device), tag, torch.cuda.current_stream(device).cuda_stream)
         buf = self._bufs.get(key)
         if buf is None or buf.numel() < nbytes:
             self._bufs.pop(key, None)
@@ -177,3 +185,17 @@ def set_engine(name: str) -> str:
 
 def launch_count() -> int:
     return int(lib().gnode_launch_count())
+
+
+def prof_enable(on: bool) -> None:
+    """Start (and reset) / stop per-kernel-class CUDA-event timing inside the library."""
+    lib().gnode_prof_enable(1 if on else 0)
+
+
+def prof_read():
+    """List of dicts {name, launches, ms, flops, bytes} accumulated since ``prof_enable(True)``."""
+    cap = 128
+    arr = (GnodeProfEntry * cap)()
+    n = min(lib().gnode_prof_read(arr, cap), cap)
+    return [dict(name=arr[i].name.decode(), launches=int(arr[i].launches), ms=float(arr[i].ms),
+                 flops=float(arr[i].flops), bytes=float(arr[i].bytes)) for i in range(n)]

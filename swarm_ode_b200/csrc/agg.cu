@@ -107,6 +107,8 @@ inline int lanes_per_row(int C, int vec) {
 int agg_mean_fwd(const gnode_graph& g, const float* in, int64_t ld_in, float* out, int64_t ld_out, int C,
                  const float* add, int64_t ld_add, const float* bias, int relu, cudaStream_t s) {
   if (g.n_nodes == 0 || C == 0) return GNODE_OK;
+  GN_PROF(s, (double)g.n_edges * C, 4.0 * ((double)g.n_edges * (C + 1) + (double)g.n_nodes * (C * (add ? 2 : 1) + 1)),
+          "agg_mean_fwd C=%d", C);
   const bool vec4 = (C % 4 == 0) && (ld_in % 4 == 0) && (ld_out % 4 == 0) && aligned16(in) && aligned16(out) &&
                     (!add || ((ld_add % 4 == 0) && aligned16(add))) && (!bias || aligned16(bias));
   const int vec = vec4 ? 4 : 1;
@@ -124,6 +126,8 @@ int agg_mean_fwd(const gnode_graph& g, const float* in, int64_t ld_in, float* ou
 int agg_mean_bwd(const gnode_graph& g, const float* gin, int64_t ld_gin, float* out, int64_t ld_out, int C,
                  const float* add, int64_t ld_add, const float* act, int64_t ld_act, cudaStream_t s) {
   if (g.n_nodes == 0 || C == 0) return GNODE_OK;
+  GN_PROF(s, (double)g.n_edges * C, 4.0 * ((double)g.n_edges * (C + 1) + (double)g.n_nodes * (C * (1 + (add ? 1 : 0) + (act ? 1 : 0)) + 1)),
+          "agg_mean_bwd C=%d", C);
   const bool vec4 = (C % 4 == 0) && (ld_gin % 4 == 0) && (ld_out % 4 == 0) && aligned16(gin) && aligned16(out) &&
                     (!add || ((ld_add % 4 == 0) && aligned16(add))) && (!act || ((ld_act % 4 == 0) && aligned16(act)));
   const int vec = vec4 ? 4 : 1;

@@ -4,7 +4,18 @@
 #include <stddef.h>
 #include <stdint.h>
 
+#include <cstdio>
+
 #include "../../include/gnode_b200.h"
+#include "prof.cuh"
+
+// Opens a profiling scope (no-op unless gnode_prof_enable(1)) covering the launches that follow in
+// the enclosing block; flops / bytes are the algorithmic work of those launches.
+#define GN_PROF(stream, flops, bytes, ...)                                                        \
+  char prof_label__[64];                                                                          \
+  prof_label__[0] = 0;                                                                            \
+  if (::gnode::prof_enabled()) std::snprintf(prof_label__, sizeof(prof_label__), __VA_ARGS__);   \
+  ::gnode::ProfScope prof_scope__(prof_label__, stream, (double)(flops), (double)(bytes))
 
 namespace gnode {
 

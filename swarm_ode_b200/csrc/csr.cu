@@ -221,6 +221,7 @@ extern "C" int gnode_csr_build(const int64_t* edge_index, int64_t E, int64_t N, 
   CsrWs w = carve(a, N, E);
   GN_ARENA_OK(a, "gnode_csr_build");
 
+  GN_PROF(s, 0.0, 16.0 * E + 8.0 * E + 8.0 * N, "csr_build");
   GN_CUDA(cudaMemsetAsync(w.cnt_in, 0, sizeof(int32_t) * (N + 1), s));
   GN_CUDA(cudaMemsetAsync(w.cnt_out, 0, sizeof(int32_t) * (N + 1), s));
   GN_CUDA(cudaMemsetAsync(w.flag, 0, sizeof(int32_t), s));

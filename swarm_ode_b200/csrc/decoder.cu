@@ -132,6 +132,7 @@ extern "C" int gnode_decoder_fwd(const float* x, int64_t m, int32_t node_dim, in
   GN_ARG(n_out >= 1 && n_out <= kMaxOut && node_dim >= 1, "gnode_decoder_fwd: n_out must be in [1, %d]", kMaxOut);
   GN_ARG(x && w && out, "gnode_decoder_fwd: null pointer");
   if (m == 0) return GNODE_OK;
+  GN_PROF(s, 2.0 * m * node_dim * n_out, 4.0 * (double)m * (node_dim + n_out), "decoder_fwd");
   int64_t blocks = ceil_div64(m * 32, DEC_THREADS);
   if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
   k_decoder_fwd<<<(unsigned)blocks, DEC_THREADS, 0, s>>>(x, m, node_dim, n_out, w, b, out);
@@ -146,6 +147,7 @@ extern "C" int gnode_decoder_bwd(const float* x, const float* grad_out, int64_t 
   GN_ARG(n_out >= 1 && n_out <= kMaxOut && node_dim >= 1, "gnode_decoder_bwd: n_out must be in [1, %d]", kMaxOut);
   GN_ARG(grad_out && w, "gnode_decoder_bwd: null pointer");
   if (m == 0) return GNODE_OK;
+  GN_PROF(s, 4.0 * m * node_dim * n_out, 4.0 * (double)m * (2 * node_dim + n_out), "decoder_bwd");
   if (grad_x) {
     int64_t blocks = ceil_div64(m * 32, DEC_THREADS);
     if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;

@@ -8,6 +8,9 @@ int gemm_nt_tc(const GemmNT& g, cudaStream_t s);
 
 int gemm_nt(const GemmNT& g, cudaStream_t s) {
   const int engine = current_engine();
+  const bool tc = engine != GNODE_ENGINE_SIMT && gemm_nt_tc_supported(g);
+  GN_PROF(s, 2.0 * g.M * g.N * g.K, 4.0 * ((double)g.M * g.K + (double)g.N * g.K + (double)g.M * g.N * (g.base ? 2 : 1)),
+          "gemm_nt[%s] N=%d K=%d", tc ? "tcgen05" : "ffma", g.N, g.K);
   if (engine == GNODE_ENGINE_SIMT) return gemm_nt_simt(g, s);
   if (gemm_nt_tc_supported(g)) return gemm_nt_tc(g, s);
   if (engine == GNODE_ENGINE_TC) {

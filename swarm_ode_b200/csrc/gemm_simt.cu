@@ -223,6 +223,8 @@ size_t gemm_tn_workspace_floats(int P, int Q, int64_t Nrows) {
 
 int gemm_tn(const GemmTN& g, float* partials, cudaStream_t s) {
   if (g.P == 0 || g.Q == 0) return GNODE_OK;
+  GN_PROF(s, 2.0 * g.P * g.Q * g.Nrows, 4.0 * ((double)g.Nrows * (g.P + g.Q) + (double)g.P * g.Q),
+          "gemm_tn[ffma] P=%d Q=%d", g.P, g.Q);
   const int S = tn_splits(g.P, g.Q, g.Nrows);
   int64_t kchunk = ceil_div64(ceil_div64(g.Nrows, S), BK) * BK;
   if (kchunk < BK) kchunk = BK;
@@ -252,6 +254,7 @@ size_t colsum_workspace_floats(int C, int64_t Nrows) { return (size_t)colsum_blo
 int colsum_accum(const float* X, int64_t ldx, int64_t Nrows, int C, float* out, float scale,
                  float* partials, cudaStream_t s) {
   if (C == 0) return GNODE_OK;
+  GN_PROF(s, (double)Nrows * C, 4.0 * (double)Nrows * C, "colsum C=%d", C);
   const int nb = colsum_blocks(Nrows);
   const int64_t rpb = ceil_div64(Nrows > 0 ? Nrows : 1, nb);
   k_colsum_partial<<<nb, CS_THREADS, 0, s>>>(X, ldx, Nrows, C, rpb, partials);

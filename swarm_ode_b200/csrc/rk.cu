@@ -210,6 +210,7 @@ int lincomb(const LinComb& lc_in, cudaStream_t s) {
     if (lc.out != lc.base) GN_CUDA(cudaMemcpyAsync(lc.out, lc.base, sizeof(float) * lc.n, cudaMemcpyDeviceToDevice, s));
     return GNODE_OK;
   }
+  GN_PROF(s, 2.0 * m * lc.n, 4.0 * (double)lc.n * (m + 1 + (lc.base ? 1 : 0)), "lincomb terms=%d", m);
   bool v4 = aligned16(lc.out) && (!lc.base || aligned16(lc.base));
   for (int j = 0; j < m; ++j) v4 = v4 && aligned16(lc.in[j]);
   if (v4 && lc.n >= 4) {
@@ -224,6 +225,7 @@ int lincomb(const LinComb& lc_in, cudaStream_t s) {
 
 int relu_mask(const float* g, const float* act, float* out, int64_t n, cudaStream_t s) {
   if (n == 0) return GNODE_OK;
+  GN_PROF(s, (double)n, 12.0 * (double)n, "act_mask");
   k_act_mask<<<ew_blocks(n), EW_THREADS, 0, s>>>(g, act, out, n, 1);
   GN_LAUNCHED();
   return GNODE_OK;
@@ -240,6 +242,7 @@ int norm_blocks(int64_t n) { return (int)ew_blocks(ceil_div64(n, 4)); }
 
 int scaled_sumsq(const float* a, const float* b, const float* y, float atol, float rtol, int64_t n,
                  double* partials, double* out, cudaStream_t s) {
+  GN_PROF(s, 6.0 * n, 4.0 * (double)n * (b ? 3 : 2), "scaled_sumsq");
   const int nb = norm_blocks(n);
   k_scaled_sumsq<<<nb, EW_THREADS, 0, s>>>(a, b, y, atol, rtol, n, partials);
   GN_LAUNCHED();
@@ -250,6 +253,7 @@ int scaled_sumsq(const float* a, const float* b, const float* y, float atol, flo
 
 int error_sumsq(const LinComb& lc, const float* y0, const float* y1, float atol, float rtol,
                 double* partials, double* out, cudaStream_t s) {
+  GN_PROF(s, 20.0 * lc.n, 4.0 * (double)lc.n * (lc.n_terms + 2), "dopri5_error_norm");
   const int nb = norm_blocks(lc.n);
   k_error_sumsq<<<nb, EW_THREADS, 0, s>>>(lc, y0, y1, atol, rtol, partials);
   GN_LAUNCHED();
@@ -259,6 +263,7 @@ int error_sumsq(const LinComb& lc, const float* y0, const float* y1, float atol,
 }
 
 int dopri_interp(const LinComb& lc, const float* y0, const float* y1, float dt, float x, float* out, cudaStream_t s) {
+  GN_PROF(s, 40.0 * lc.n, 4.0 * (double)lc.n * (lc.n_terms + 3), "dopri5_dense_output");
   k_dopri_interp<<<ew_blocks(lc.n), EW_THREADS, 0, s>>>(lc, y0, y1, dt, x, out);
   GN_LAUNCHED();
   return GNODE_OK;
@@ -273,6 +278,7 @@ int pack_segments(const PackSegHost* segs, int n, cudaStream_t s) {
     a.seg[i].dst = segs[i].dst; a.seg[i].src = segs[i].src; a.seg[i].rows = segs[i].rows; a.seg[i].cols = segs[i].cols;
     a.seg[i].ld_src = segs[i].ld_src; a.seg[i].ld_dst = segs[i].ld_dst; a.seg[i].transpose = segs[i].transpose; a.seg[i].accumulate = segs[i].accumulate;
   }
+  GN_PROF(s, 0.0, 0.0, "pack_segments");
   int64_t most = 1;
   for (int i = 0; i < n; ++i) {
     const int64_t tot = (int64_t)segs[i].rows * segs[i].cols;

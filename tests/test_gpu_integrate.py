@@ -1,0 +1,208 @@
+"""Trajectory parity of the integrators with the torch/torchdiffeq restatement (north_star gates):
+fp32 relative L2 <= 1e-4 at fixed step, identical accepted-step counts for dopri5."""
+import pytest
+import torch
+
+import swarm_ode_b200 as S
+from oracle.train_gde_ref import GraphODERef, train_step_loss_ref
+from tests._util import FIXED_TOL, rel_l2, to_ref_batch
+
+pytestmark = pytest.mark.gpu
+
+
+def _models(D, solver, cuda, conv3_scale=0.1, seed=1):
+    model = S.GraphODE(D, 12, 7, hidden_dim=64, ode_solver=solver)
+    S.synthetic.init_weights(model, seed=seed, conv3_scale=conv3_scale)
+    ref = GraphODERef(D, 12, 7, hidden_dim=64, ode_solver=solver)
+    ref.load_state_dict(model.state_dict())
+    return model.to(cuda), ref
+
+
+def test_state_dict_keys_match_reference_layout():
+    model = S.GraphODE(399, 3, 2)
+    keys = sorted(model.state_dict())
+    want = sorted([f"ode_func.conv{i}.lin_l.weight" for i in (1, 2, 3)] + [f"ode_func.conv{i}.lin_l.bias" for i in (1, 2, 3)] +
+                  [f"ode_func.conv{i}.lin_r.weight" for i in (1, 2, 3)] + ["position_decoder.weight", "position_decoder.bias"])
+    assert keys == want
+    assert model.ode_func.conv1.lin_l.weight.shape == (64, 399)
+    assert model.ode_func.conv3.lin_r.weight.shape == (399, 64)
+
+
+@pytest.mark.parametrize("solver", ["euler", "midpoint", "rk4"])
+def test_fixed_step_forward_dict(cuda, solver):
+    batch, _ = S.synthetic.warehouse_batch(16, seed=0)
+    D = batch.x.shape[1]
+    model, ref = _models(D, solver, cuda)
+    t = torch.tensor([0.0, 1.0])
+    want = ref(to_ref_batch(batch), t)
+    got = model(batch.to(cuda), t.to(cuda))
+    assert set(got) == {"trajectories", "node_features", "batch"}
+    assert got["node_features"].shape == want["node_features"].shape == (2, batch.x.shape[0], D)
+    assert got["trajectories"].shape == (2, batch.x.shape[0], 2)
+    assert torch.equal(got["node_features"][0].cpu(), batch.x.cpu())
+    assert rel_l2(got["node_features"], want["node_features"]) <= FIXED_TOL
+    assert rel_l2(got["trajectories"], want["trajectories"]) <= FIXED_TOL
+    assert torch.equal(got["batch"].cpu(), batch.batch.cpu())
+
+
+@pytest.mark.parametrize("solver,steps", [("euler", 5), ("rk4", 5), ("midpoint", 3)])
+def test_predict_trajectory_multi_step(cuda, solver, steps):
+    batch, _ = S.synthetic.warehouse_batch(4, seed=3)
+    D = batch.x.shape[1]
+    model, ref = _models(D, solver, cuda, conv3_scale=0.02)
+    want = ref.predict_trajectory(to_ref_batch(batch), steps)
+    got = model.predict_trajectory(batch.to(cuda), steps)
+    assert got.shape == (steps + 1, batch.x.shape[0], 2)
+    assert rel_l2(got, want) <= FIXED_TOL
+
+
+@pytest.mark.parametrize("solver,T", [("euler", 2), ("rk4", 2), ("midpoint", 2), ("rk4", 4)])
+def test_train_step_gradients(cuda, solver, T):
+    batch, nxt = S.synthetic.warehouse_batch(8, seed=1)
+    D = batch.x.shape[1]
+    model, ref = _models(D, solver, cuda, conv3_scale=0.05)
+    t = torch.linspace(0, 1, T)
+    rb = to_ref_batch(batch)
+    loss_ref = train_step_loss_ref(ref, rb, nxt, t)
+    loss_ref.backward()
+    gb = batch.to(cuda)
+    pred = model(gb, t.to(cuda))["trajectories"][1]
+    loss = torch.nn.functional.mse_loss(pred[gb.is_current_agent], nxt.to(cuda).view(-1, 2))
+    loss.backward()
+    assert abs(float(loss) - float(loss_ref)) <= 1e-4 * abs(float(loss_ref))
+    rp = dict(ref.named_parameters())
+    for name, p in model.named_parameters():
+        assert p.grad is not None, name
+        assert rel_l2(p.grad, rp[name].grad) <= FIXED_TOL, name
+
+
+def test_backward_wrt_initial_state_and_all_time_points(cuda):
+    batch, _ = S.synthetic.warehouse_batch(3, seed=5)
+    D = batch.x.shape[1]
+    model, ref = _models(D, "rk4", cuda, conv3_scale=0.05)
+    t = torch.tensor([0.0, 0.4, 1.0])
+    rb = to_ref_batch(batch)
+    rb.x.requires_grad_()
+    out_ref = ref(rb, t)
+    w = torch.randn_like(out_ref["node_features"])
+    (out_ref["node_features"] * w).sum().backward()
+    gb = batch.to(cuda)
+    gb.x.requires_grad_()
+    out = model(gb, t.to(cuda))
+    (out["node_features"] * w.to(cuda)).sum().backward()
+    assert rel_l2(gb.x.grad, rb.x.grad) <= FIXED_TOL
+
+
+def test_masked_mse_train_step_matches_reference_loop(cuda):
+    """Two optimiser steps of the reference loop (Adam, clip 1.0) stay on the oracle's trajectory."""
+    batch, nxt = S.synthetic.warehouse_batch(8, seed=2)
+    D = batch.x.shape[1]
+    model, ref = _models(D, "euler", cuda, conv3_scale=0.05)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-4)
+    opt_ref = torch.optim.Adam(ref.parameters(), lr=1e-3, weight_decay=1e-4)
+    gb, rb = batch.to(cuda), None
+    from swarm_ode_b200.dist import masked_mse_train_step
+    b2, _ = S.synthetic.warehouse_batch(8, seed=2)
+    rb = to_ref_batch(b2)
+    for _ in range(2):
+        loss = masked_mse_train_step(model, opt, gb, nxt.to(cuda))
+        opt_ref.zero_grad()
+        loss_ref = train_step_loss_ref(ref, rb, nxt)
+        loss_ref.backward()
+        torch.nn.utils.clip_grad_norm_(ref.parameters(), max_norm=1.0)
+        opt_ref.step()
+        assert abs(float(loss) - float(loss_ref)) <= 1e-4 * abs(float(loss_ref))
+    rp = dict(ref.named_parameters())
+    for name, p in model.named_parameters():
+        assert rel_l2(p, rp[name]) <= 1e-4, name
+
+
+# ---------------------------------------------------------------- dopri5
+@pytest.mark.parametrize("B,t_points,conv3_scale", [(8, [0.0, 1.0], 0.1), (4, [0.0, 0.25, 0.5, 1.0, 2.0], 0.1), (6, [0.0, 1.0], 0.3)])
+def test_dopri5_counts_and_values(cuda, B, t_points, conv3_scale):
+    batch, _ = S.synthetic.warehouse_batch(B, num_agvs=19, num_pickers=9, seed=4)
+    D = batch.x.shape[1]
+    assert D == 435
+    model, ref = _models(D, "dopri5", cuda, conv3_scale=conv3_scale)
+    t = torch.tensor(t_points)
+    with torch.no_grad():
+        want = ref(to_ref_batch(batch), t)
+        got = model(batch.to(cuda), t.to(cuda))
+    st, rst = model.last_stats, ref.last_stats
+    print(f"dopri5: accepted {st.n_accepted}/{rst.n_accepted} attempted {st.n_attempted}/{rst.n_attempted} "
+          f"first_step {st.first_step:.6g}/{rst.first_step:.6g} min|ratio-1| {st.min_margin:.3g}")
+    assert st.n_accepted == rst.n_accepted
+    assert st.n_attempted == rst.n_attempted
+    assert st.accepted == rst.accepted
+    assert st.nfe == rst.nfe
+    assert abs(st.first_step - rst.first_step) <= 1e-5 * rst.first_step
+    for a, b in zip(st.error_ratios, rst.error_ratios):
+        assert abs(a - b) <= 1e-3 * max(abs(b), 1e-6)
+    assert rel_l2(got["node_features"], want["node_features"]) <= FIXED_TOL
+    assert rel_l2(got["trajectories"], want["trajectories"]) <= FIXED_TOL
+
+
+def test_dopri5_backward_fails_loudly(cuda):
+    batch, _ = S.synthetic.warehouse_batch(2, seed=4)
+    model, _ = _models(batch.x.shape[1], "dopri5", cuda)
+    out = model(batch.to(cuda), torch.tensor([0.0, 1.0], device=cuda))
+    with pytest.raises(S.GnodeError, match="dopri5"):
+        out["trajectories"].sum().backward()
+
+
+def test_dopri5_two_rank_lockstep_reproduces_unsharded_decisions(cuda):
+    """Two data-parallel 'ranks' run as two host threads (own CUDA stream each) on one GPU; their
+    error-norm hooks rendezvous on the host and exchange (sum of squares, count) exactly as the NCCL /
+    gloo all-reduce does.  Every rank must then take the decisions of the unsharded batch."""
+    import threading
+
+    batch, _ = S.synthetic.warehouse_batch(6, num_agvs=19, num_pickers=9, seed=9)
+    D = batch.x.shape[1]
+    model, _ = _models(D, "dopri5", cuda)
+    params = [p.detach() for p in model.ode_func.param_list()]
+    t = [0.0, 0.5, 1.0]
+    full_batch = batch.to(cuda)
+    g_full = S.csr_for(full_batch.edge_index, full_batch.x.shape[0])
+    full, full_stats = S.ops.integrate_dopri5(full_batch.x, g_full, params, t, 1e-3, 1e-4)
+
+    b2, _ = S.synthetic.warehouse_batch(6, num_agvs=19, num_pickers=9, seed=9)
+    shards = [b2.shard(r, 2).to(cuda) for r in range(2)]
+    barrier = threading.Barrier(2)
+    slots = [None, None]
+    results, errors = [None, None], []
+
+    def hook_for(rank):
+        def hook(s, c):
+            slots[rank] = (s, c)
+            barrier.wait(timeout=60)
+            tot = (slots[0][0] + slots[1][0], slots[0][1] + slots[1][1])
+            barrier.wait(timeout=60)
+            return tot
+        return hook
+
+    def run(rank):
+        try:
+            stream = torch.cuda.Stream(device=cuda)
+            with torch.cuda.stream(stream):
+                sh = shards[rank]
+                g = S.CSRGraph(sh.edge_index, sh.x.shape[0])
+                results[rank] = S.ops.integrate_dopri5(sh.x, g, params, t, 1e-3, 1e-4, allreduce=hook_for(rank))
+                stream.synchronize()
+        except Exception as exc:  # pragma: no cover
+            errors.append(exc)
+            barrier.abort()
+
+    torch.cuda.synchronize()
+    threads = [threading.Thread(target=run, args=(r,)) for r in range(2)]
+    [th.start() for th in threads]
+    [th.join(timeout=120) for th in threads]
+    assert not errors, errors
+    torch.cuda.synchronize()
+    for r in range(2):
+        st = results[r][1]
+        assert st.accepted == full_stats.accepted
+        assert st.n_attempted == full_stats.n_attempted
+        for a, b in zip(st.error_ratios, full_stats.error_ratios):
+            assert abs(a - b) <= 1e-5 * max(abs(b), 1e-9)
+    got = torch.cat([results[0][0], results[1][0]], dim=1)
+    assert rel_l2(got, full) <= 1e-5
