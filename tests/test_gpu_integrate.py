@@ -137,9 +137,65 @@ def test_dopri5_counts_and_values(cuda, B, t_points, conv3_scale):
     assert st.nfe == rst.nfe
     assert abs(st.first_step - rst.first_step) <= 1e-5 * rst.first_step
     for a, b in zip(st.error_ratios, rst.error_ratios):
-        assert abs(a - b) <= 1e-3 * max(abs(b), 1e-6)
+        # tiny ratios are dominated by fp32 cancellation in the error estimate; decisions live near 1
+        assert abs(a - b) <= 2e-2 * abs(b) + 1e-6
     assert rel_l2(got["node_features"], want["node_features"]) <= FIXED_TOL
     assert rel_l2(got["trajectories"], want["trajectories"]) <= FIXED_TOL
+
+
+@pytest.mark.parametrize("scale,rtol,atol,t_points", [(3.0, 1e-5, 1e-6, [0.0, 5.0]), (6.0, 1e-4, 1e-5, [0.0, 1.0, 3.0]),
+                                                       (10.0, 1e-3, 1e-4, [0.0, 0.5, 1.0, 1.5, 2.0, 3.0]),
+                                                       (3.0, 1e-6, 1e-7, [0.0, 2.0])])
+def test_dopri5_many_steps_identical_decisions(cuda, scale, rtol, atol, t_points):
+    """Harder regimes (14-46 steps): every accept/reject decision, the step sizes and the dense outputs
+    must follow the torchdiffeq restatement."""
+    from oracle.torchdiffeq_ref import SolverStats, odeint_ref
+    from oracle.train_gde_ref import GraphODEFuncRef
+
+    batch, _ = S.synthetic.warehouse_batch(2, num_agvs=19, num_pickers=9, seed=4)
+    D = batch.x.shape[1]
+    fref = GraphODEFuncRef(D, 64)
+    S.synthetic.init_weights(fref, seed=1, conv3_scale=scale)
+    f = S.GraphODEFunc(D, 64)
+    f.load_state_dict(fref.state_dict())
+    f = f.to(cuda)
+    rst = SolverStats()
+    t = torch.tensor(t_points)
+    with torch.no_grad():
+        want = odeint_ref(lambda tt, x: fref(tt, x, batch.edge_index), batch.x, t, rtol=rtol, atol=atol, method="dopri5",
+                          stats=rst)
+        gb = batch.to(cuda)
+        g = S.csr_for(gb.edge_index, gb.x.shape[0])
+        got, st = S.ops.integrate_dopri5(gb.x, g, f.param_list(), t_points, rtol, atol)
+    print(f"dopri5[{scale},{rtol}]: accepted {st.n_accepted}/{rst.n_accepted} attempted {st.n_attempted}/{rst.n_attempted} "
+          f"min|ratio-1| {st.min_margin:.3g}")
+    assert rst.n_accepted >= 10
+    assert st.accepted == rst.accepted and st.n_attempted == rst.n_attempted and st.nfe == rst.nfe
+    for a, b in zip(st.dts, rst.dts):
+        assert abs(a - b) <= 1e-3 * abs(b)
+    assert rel_l2(got, want) <= FIXED_TOL
+
+
+def test_odeint_entry_point_signature(cuda):
+    """`odeint(func, y0, t, rtol=, atol=, method=)` with the reference's closure replaced by .bind()."""
+    from oracle.torchdiffeq_ref import odeint_ref
+    from oracle.train_gde_ref import GraphODEFuncRef
+
+    batch, _ = S.synthetic.warehouse_batch(2, seed=6)
+    D = batch.x.shape[1]
+    fref = GraphODEFuncRef(D, 64)
+    S.synthetic.init_weights(fref, seed=1, conv3_scale=0.1)
+    f = S.GraphODEFunc(D, 64)
+    f.load_state_dict(fref.state_dict())
+    f = f.to(cuda)
+    t = torch.tensor([0.0, 0.3, 1.0])
+    gb = batch.to(cuda)
+    for method in ("euler", "midpoint", "rk4", "dopri5", None):
+        with torch.no_grad():
+            want = odeint_ref(lambda tt, x: fref(tt, x, batch.edge_index), batch.x, t, rtol=1e-3, atol=1e-4, method=method)
+            got = S.odeint(f.bind(gb.edge_index), gb.x, t.to(cuda), rtol=1e-3, atol=1e-4, method=method)
+        assert got.shape == (3,) + tuple(batch.x.shape)
+        assert rel_l2(got, want) <= FIXED_TOL, method
 
 
 def test_dopri5_backward_fails_loudly(cuda):
