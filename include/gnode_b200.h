@@ -66,6 +66,9 @@ int gnode_abi_version(void);
 int gnode_set_engine(int engine);
 /* number of kernels this library has launched since load (all threads) */
 int64_t gnode_launch_count(void);
+/* Synchronises `stream` and reports whether a tcgen05 kernel hit one of its bounded barrier waits
+ * since the last call (GNODE_OK = healthy).  For tests / debugging; the hot path never calls it. */
+int gnode_tc_status(gnode_stream_t stream);
 
 /* Per-kernel-class timing (CUDA events on the launching stream) for roofline reporting.  Each entry
  * carries the ALGORITHMIC flops / bytes of the launches it covers (computed from the shapes). */
@@ -99,6 +102,19 @@ size_t gnode_csr_workspace_bytes(int64_t n_nodes, int64_t n_edges);
 int gnode_csr_build(const int64_t* edge_index, int64_t n_edges, int64_t n_nodes,
                     int32_t* rowptr, int32_t* col, int32_t* t_rowptr, int32_t* t_col,
                     void* workspace, size_t workspace_bytes, gnode_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Dense "NT" contraction on the selected engine (the per-node Linear layers of SAGEConv /
+ * ODEFunction; reference call sites scripts/train_gde.py:27-29, scripts/gnode.py:165-171):
+ *   C[m, n] = base[m, n] + scale * act( sum_k A[m, k] * B[n, k] + bias[n] )
+ * A: [m, k] row stride lda; B: [n, k] (nn.Linear weight layout) row stride ldb; bias / base may be
+ * NULL; act: 0 none, 1 relu, 2 tanh.  Engine AUTO/TC: tcgen05 3xTF32 (fp32-grade), SIMT: fp32 FFMA.
+ * ---------------------------------------------------------------------------------------- */
+size_t gnode_gemm_nt_workspace_bytes(int32_t n, int32_t k);
+int gnode_gemm_nt(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc,
+                  int64_t m, int32_t n, int32_t k, const float* bias, int32_t act, const float* base,
+                  int64_t ldbase, float scale, void* workspace, size_t workspace_bytes,
+                  gnode_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * One SAGEConv layer:  out = mean_{j in N(i)} x_j @ wl^T + bl + x_i @ wr^T   (optional ReLU)

@@ -64,10 +64,14 @@ _SIGNATURES = {
     "gnode_abi_version": (C.c_int, []),
     "gnode_set_engine": (C.c_int, [C.c_int]),
     "gnode_launch_count": (C.c_int64, []),
+    "gnode_tc_status": (C.c_int, [_P]),
     "gnode_prof_enable": (C.c_int, [C.c_int]),
     "gnode_prof_read": (C.c_int, [C.POINTER(GnodeProfEntry), C.c_int]),
     "gnode_csr_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int64]),
     "gnode_csr_build": (C.c_int, [_P, C.c_int64, C.c_int64, _P, _P, _P, _P, _P, C.c_size_t, _P]),
+    "gnode_gemm_nt_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
+    "gnode_gemm_nt": (C.c_int, [_P, C.c_int64, _P, C.c_int64, _P, C.c_int64, C.c_int64, C.c_int32, C.c_int32, _P,
+                                C.c_int32, _P, C.c_int64, C.c_float, _P, C.c_size_t, _P]),
     "gnode_sage_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int32, C.c_int32]),
     "gnode_sage_fwd": (C.c_int, [C.POINTER(GnodeGraph), _P, C.c_int32, C.c_int32, _P, _P, _P, C.c_int32, _P, _P,
                                  C.c_size_t, _P]),
@@ -125,6 +129,9 @@ def lib() -> C.CDLL:
             fn.restype = res
             fn.argtypes = args
         _lib = handle
+        env_engine = os.environ.get("GNODE_ENGINE")  # 'auto' | 'simt' | 'tc': initial GEMM engine
+        if env_engine:
+            handle.gnode_set_engine({"auto": ENGINE_AUTO, "simt": ENGINE_SIMT, "tc": ENGINE_TC}[env_engine])
     return _lib
 
 
@@ -199,3 +206,9 @@ def prof_read():
     n = min(lib().gnode_prof_read(arr, cap), cap)
     return [dict(name=arr[i].name.decode(), launches=int(arr[i].launches), ms=float(arr[i].ms),
                  flops=float(arr[i].flops), bytes=float(arr[i].bytes)) for i in range(n)]
+
+
+def tc_check(device=None) -> None:
+    """Synchronise and raise if a tcgen05 kernel reported a barrier timeout (tests / debugging)."""
+    dev = device if device is not None else torch.cuda.current_device()
+    check(lib().gnode_tc_status(stream_ptr(dev)), "gnode_tc_status")

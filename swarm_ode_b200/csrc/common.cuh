@@ -104,8 +104,13 @@ struct GemmNT {
   int relu = 0;
   const float* base = nullptr; int64_t ldbase = 0;
   float scale = 1.0f;
+  const float* Bsplit = nullptr;   // optional: B pre-split into tf32 hi/lo planes (presplit_weights) -> tcgen05 engine
 };
 int gemm_nt(const GemmNT& g, cudaStream_t s);
+// tf32 hi/lo planes of a row-major weight matrix, zero padded to multiples of 16 (gemm_tc.cu)
+size_t presplit_floats(int rows, int cols);
+int presplit_weights(const float* W, int rows, int cols, int64_t ld, float* planes, cudaStream_t s);
+int gemm_tc_status(cudaStream_t s, int* out);
 
 // C[p, q] (+)= scale * sum_n A[n, p] * B[n, q]        (reduction over rows, "TN": weight gradients)
 // Deterministic: split over row chunks into `partials` (workspace), reduced in fixed order.

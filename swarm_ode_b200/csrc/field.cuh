@@ -38,6 +38,9 @@ struct Sage3Ctx : Field {
   float *w1cat = nullptr, *w2cat = nullptr, *w3cat = nullptr;
   // transposes for the data gradients (NT form): w3catT [2H, D], w2catT [2H, H], w1catT [D, 2H]
   float *w1catT = nullptr, *w2catT = nullptr, *w3catT = nullptr;
+  // tf32 hi/lo planes of the six packed matrices for the tcgen05 engine (null -> FFMA engine)
+  float *s1 = nullptr, *s2 = nullptr, *s3 = nullptr, *s1T = nullptr, *s2T = nullptr, *s3T = nullptr;
+  bool use_tc = false;
   float* z = nullptr;                  // [N, 2H]  x @ w1cat^T
   int n_slots = 1;
   float* cat1[kMaxStages] = {};        // [N, 2H]  [ mean(h1) | h1 ]

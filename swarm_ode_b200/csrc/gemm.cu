@@ -20,3 +20,32 @@ int gemm_nt(const GemmNT& g, cudaStream_t s) {
   return gemm_nt_simt(g, s);
 }
 }  // namespace gnode
+
+// ------------------------------------------------------------------------------------------------
+// C ABI: the dense NT contraction on its own (used by the parity tests to isolate the engines)
+// ------------------------------------------------------------------------------------------------
+using namespace gnode;
+
+extern "C" size_t gnode_gemm_nt_workspace_bytes(int32_t n, int32_t k) {
+  return align_up(presplit_floats(n, k) * sizeof(float));
+}
+
+extern "C" int gnode_gemm_nt(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc,
+                             int64_t m, int32_t n, int32_t k, const float* bias, int32_t act, const float* base,
+                             int64_t ldbase, float scale, void* workspace, size_t workspace_bytes,
+                             gnode_stream_t stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  GN_ARG(A && B && C && m >= 0 && n > 0 && k > 0, "gnode_gemm_nt: bad argument");
+  GN_ARG(act >= 0 && act <= 2, "gnode_gemm_nt: act must be 0 (none), 1 (relu) or 2 (tanh)");
+  GemmNT q{};
+  q.A = A; q.lda = lda; q.B = B; q.ldb = ldb; q.C = C; q.ldc = ldc; q.M = m; q.N = n; q.K = k;
+  q.bias = bias; q.relu = act; q.base = base; q.ldbase = ldbase; q.scale = scale;
+  if (current_engine() != GNODE_ENGINE_SIMT) {
+    Arena a(workspace, workspace_bytes);
+    float* planes = a.take<float>(presplit_floats(n, k));
+    GN_ARENA_OK(a, "gnode_gemm_nt");
+    GN_TRY(presplit_weights(B, n, k, ldb, planes, s));
+    q.Bsplit = planes;
+  }
+  return gemm_nt(q, s);
+}

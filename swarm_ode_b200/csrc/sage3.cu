@@ -17,6 +17,9 @@ void Sage3Ctx::carve(Arena& a, int slots, bool backward) {
   w1cat = a.take<float>((size_t)2 * H * D);
   w2cat = a.take<float>((size_t)H * 2 * H);
   w3cat = a.take<float>((size_t)D * 2 * H);
+  s1 = a.take<float>(presplit_floats(2 * H, D));
+  s2 = a.take<float>(presplit_floats(H, 2 * H));
+  s3 = a.take<float>(presplit_floats(D, 2 * H));
   z = a.take<float>(n * 2 * H);
   for (int i = 0; i < slots; ++i) {
     cat1[i] = a.take<float>(n * 2 * H);
@@ -26,6 +29,9 @@ void Sage3Ctx::carve(Arena& a, int slots, bool backward) {
     w1catT = a.take<float>((size_t)2 * H * D);
     w2catT = a.take<float>((size_t)H * 2 * H);
     w3catT = a.take<float>((size_t)D * 2 * H);
+    s1T = a.take<float>(presplit_floats(D, 2 * H));
+    s2T = a.take<float>(presplit_floats(2 * H, H));
+    s3T = a.take<float>(presplit_floats(2 * H, D));
     gcat = a.take<float>(n * 2 * H);
     gz = a.take<float>(n * 2 * H);
     gv2 = a.take<float>(n * H);
@@ -66,7 +72,19 @@ int Sage3Ctx::pack(const gnode_sage3_params& p, bool backward, cudaStream_t s) {
     add(w1catT, p.w1l, H, D, 2 * H, 1);                // w1catT[c, r] = w1l[r, c]
     add(w1catT + H, p.w1r, H, D, 2 * H, 1);
   }
-  return pack_segments(sg, n, s);
+  GN_TRY(pack_segments(sg, n, s));
+  use_tc = current_engine() != GNODE_ENGINE_SIMT;
+  if (use_tc) {
+    GN_TRY(presplit_weights(w1cat, 2 * H, D, D, s1, s));
+    GN_TRY(presplit_weights(w2cat, H, 2 * H, 2 * H, s2, s));
+    GN_TRY(presplit_weights(w3cat, D, 2 * H, 2 * H, s3, s));
+    if (backward) {
+      GN_TRY(presplit_weights(w1catT, D, 2 * H, 2 * H, s1T, s));
+      GN_TRY(presplit_weights(w2catT, 2 * H, H, H, s2T, s));
+      GN_TRY(presplit_weights(w3catT, 2 * H, D, D, s3T, s));
+    }
+  }
+  return GNODE_OK;
 }
 
 int Sage3Ctx::zero_param_grads(cudaStream_t s) {
@@ -104,6 +122,7 @@ int Sage3Ctx::eval(const float* x, float* out, const float* base, float scale, i
   {  // Z = x @ w1cat^T
     GemmNT q{};
     q.A = x; q.lda = D; q.B = w1cat; q.ldb = D; q.C = z; q.ldc = H2; q.M = N; q.N = H2; q.K = D;
+    q.Bsplit = use_tc ? s1 : nullptr;
     GN_TRY(gemm_nt(q, s));
   }
   // h1 = relu(A(Z_l) + Z_r + b1) -> cat1[:, H:]
@@ -114,6 +133,7 @@ int Sage3Ctx::eval(const float* x, float* out, const float* base, float scale, i
     GemmNT q{};
     q.A = c1; q.lda = H2; q.B = w2cat; q.ldb = H2; q.C = c2 + H; q.ldc = H2; q.M = N; q.N = H; q.K = H2;
     q.bias = b2; q.relu = 1;
+    q.Bsplit = use_tc ? s2 : nullptr;
     GN_TRY(gemm_nt(q, s));
   }
   // A(h2) -> cat2[:, :H]
@@ -122,6 +142,7 @@ int Sage3Ctx::eval(const float* x, float* out, const float* base, float scale, i
     GemmNT q{};
     q.A = c2; q.lda = H2; q.B = w3cat; q.ldb = H2; q.C = out; q.ldc = D; q.M = N; q.N = D; q.K = H2;
     q.bias = b3; q.base = base; q.ldbase = D; q.scale = scale;
+    q.Bsplit = use_tc ? s3 : nullptr;
     GN_TRY(gemm_nt(q, s));
   }
   return GNODE_OK;
@@ -135,6 +156,7 @@ int Sage3Ctx::vjp(const float* x, int slot, const float* gk, float* gx, cudaStre
   {  // gcat = gk @ w3cat          [N, 2H]
     GemmNT q{};
     q.A = gk; q.lda = D; q.B = w3catT; q.ldb = D; q.C = gcat; q.ldc = H2; q.M = N; q.N = H2; q.K = D;
+    q.Bsplit = use_tc ? s3T : nullptr;
     GN_TRY(gemm_nt(q, s));
   }
   {  // dW3cat += gk^T @ cat2      [D, 2H]
@@ -149,6 +171,7 @@ int Sage3Ctx::vjp(const float* x, int slot, const float* gk, float* gx, cudaStre
   {  // gcat = g_v2 @ w2cat        [N, 2H]
     GemmNT q{};
     q.A = gv2; q.lda = H; q.B = w2catT; q.ldb = H; q.C = gcat; q.ldc = H2; q.M = N; q.N = H2; q.K = H;
+    q.Bsplit = use_tc ? s2T : nullptr;
     GN_TRY(gemm_nt(q, s));
   }
   {  // dW2cat += g_v2^T @ cat1    [H, 2H]
@@ -164,6 +187,7 @@ int Sage3Ctx::vjp(const float* x, int slot, const float* gk, float* gx, cudaStre
   {  // gx = gz @ w1cat            [N, D]
     GemmNT q{};
     q.A = gz; q.lda = H2; q.B = w1catT; q.ldb = H2; q.C = gx; q.ldc = D; q.M = N; q.N = D; q.K = H2;
+    q.Bsplit = use_tc ? s1T : nullptr;
     GN_TRY(gemm_nt(q, s));
   }
   {  // dW1cat += gz^T @ x         [2H, D]

@@ -360,3 +360,24 @@ def mlp_integrate(y0: torch.Tensor, params: Sequence[torch.Tensor], t, method: s
                                                _lib.ptr(ws), ws.numel(), _lib.stream_ptr(y0.device)),
                    "gnode_mlp_integrate_fixed")
     return sol, None
+
+
+# ----------------------------------------------------------------------------------------------
+# dense NT contraction (engine test surface; also the Linear layers of the secondary variants)
+# ----------------------------------------------------------------------------------------------
+def gemm_nt(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, act: str = "none",
+            base: Optional[torch.Tensor] = None, scale: float = 1.0) -> torch.Tensor:
+    """``base + scale * act(a @ w.T + bias)`` on the selected engine (no autograd)."""
+    a, w = _f32(a.detach(), "a"), _f32(w.detach(), "w")
+    m, k = a.shape
+    n = w.shape[0]
+    out = torch.empty((m, n), dtype=torch.float32, device=a.device)
+    L = _lib.lib()
+    ws = _ws(L.gnode_gemm_nt_workspace_bytes(n, k), a.device)
+    bias_c = _f32(bias.detach(), "bias") if bias is not None else None
+    base_c = _f32(base.detach(), "base") if base is not None else None
+    with torch.cuda.device(a.device):
+        _lib.check(L.gnode_gemm_nt(_lib.ptr(a), k, _lib.ptr(w), k, _lib.ptr(out), n, m, n, k, _lib.ptr(bias_c),
+                                   {"none": 0, "relu": 1, "tanh": 2}[act], _lib.ptr(base_c), n, float(scale),
+                                   _lib.ptr(ws), ws.numel(), _lib.stream_ptr(a.device)), "gnode_gemm_nt")
+    return out

@@ -189,7 +189,8 @@ def test_odeint_entry_point_signature(cuda):
     f.load_state_dict(fref.state_dict())
     f = f.to(cuda)
     t = torch.tensor([0.0, 0.3, 1.0])
-    gb = batch.to(cuda)
+    gb, _ = S.synthetic.warehouse_batch(2, seed=6)
+    gb = gb.to(cuda)
     for method in ("euler", "midpoint", "rk4", "dopri5", None):
         with torch.no_grad():
             want = odeint_ref(lambda tt, x: fref(tt, x, batch.edge_index), batch.x, t, rtol=1e-3, atol=1e-4, method=method)
