@@ -1,36 +1,47 @@
 // tcgen05 (5th-gen tensor core) engine for the dense contractions of the GNODE path, sm_100a only.
 //
-//   C[m, n] = epi( sum_k A[m, k] * B[n, k] )        A: fp32 activations [M, K] (row stride lda, any alignment)
-//                                                    B: fp32 weights, PRE-SPLIT into tf32 hi / lo planes
+//   C[m, n] = base[m, n] + scale * act( sum_k A[m, k] * B[n, k] + bias[n] )
+//     A: fp32 activations [M, K], row stride lda (rows need NOT be 16-byte aligned: D = 399)
+//     B: fp32 weights, pre-packed once per call into per-stage shared-memory images of tf32 hi/lo planes
 //
-// fp32-grade accuracy on the tensor pipe by the 3xTF32 split: a = a_hi + a_lo with a_hi = rna_tf32(a),
-// a_lo = rna_tf32(a - a_hi); the product uses a_lo*b_hi + a_hi*b_lo + a_hi*b_hi (the dropped a_lo*b_lo
-// term is < 2^-22 relative), accumulated in fp32 in tensor memory (TMEM).
+// fp32-grade accuracy on the tensor pipe by the 3xTF32 split: a = a_hi + a_lo, a_hi = rna_tf32(a),
+// a_lo = rna_tf32(a - a_hi); products a_lo*b_hi + a_hi*b_lo + a_hi*b_hi accumulate in fp32 in TMEM.
 //
-// One CTA = one 128 x BN output tile (BN <= 256, multiple of 16), 5 warps:
-//   warps 0-3  producers: coalesced global loads (lanes along K), hi/lo split in registers, scalar
-//              conflict-free st.shared into the UMMA K-major no-swizzle layout, fence.proxy.async,
-//              mbarrier arrive;  afterwards the same warps run the epilogue (tcgen05.ld of their TMEM
-//              lane quadrant -> smem transpose -> coalesced global stores with bias/act/scale/base).
-//   warp 4     TMEM alloc/dealloc; one elected lane issues tcgen05.mma.kind::tf32 (M=128, N=BN, K=8)
-//              and tcgen05.commit to release smem stages / publish the accumulator.
-// Two CTAs fit per SM (<= 100 KB smem, <= 256 TMEM columns each) so one tile's epilogue overlaps the
-// other's main loop.
+// Persistent kernel, one CTA per SM, ten warps:
+//   warp 0      TMA producer.  A arrives RAW through cp.async.bulk.tensor (2-D map; for rows that are not
+//               16-byte aligned the map views 4 consecutive rows as one "super-row" whose pitch is a
+//               multiple of 16 B, and four boxes per stage pick the four row phases).  B arrives as one
+//               cp.async.bulk of the pre-packed image, already in UMMA layout.  Both complete on an
+//               mbarrier transaction count -> deep memory-level parallelism with no register cost.
+//   warp 1      TMEM alloc; one lane issues tcgen05.mma.kind::tf32 (M=128, N=BN, K=8) and tcgen05.commit.
+//   warps 2-5   converters: raw smem -> registers -> hi/lo split -> conflict-free st.shared into the UMMA
+//               K-major no-swizzle layout -> fence.proxy.async -> mbarrier arrive.
+//   warps 6-9   epilogue: tcgen05.ld of their TMEM lane quadrant -> smem transpose -> coalesced global
+//               stores with bias / activation / scale / base.  The accumulator is double buffered in
+//               TMEM, so the epilogue of tile i overlaps the main loop of tile i+1.
 //
 // Every mbarrier wait is bounded: on timeout the kernel records a status word and finishes instead of
-// hanging (the host turns that into GNODE_ERR_CUDA).
+// hanging (gnode_tc_status() turns that into an error).
+#include <cuda.h>
+
 #include "common.cuh"
 
 namespace gnode {
+int gemm_nt_simt(const GemmNT& g, cudaStream_t s);
+
 namespace tc {
 
 constexpr int BM = 128;
-constexpr int BK = 16;               // K elements per stage: 4 chunks of 16 bytes, 2 MMA K-steps
+constexpr int BK = 16;                 // K elements per stage: 4 chunks of 16 bytes, 2 MMA K-steps
 constexpr int CHUNKS = BK / 4;
-constexpr int PROD_THREADS = 128;
-constexpr int THREADS = 160;
-constexpr int LBO_A = BM * 16 + 16;  // bytes between consecutive 16-byte K-chunks of the A tile (+16: bank spread)
-constexpr uint32_t SPIN_LIMIT = 1u << 24;
+constexpr int LBO_A = BM * 16 + 16;    // bytes between consecutive 16-byte K-chunks of the A planes (+16: bank spread)
+constexpr int RAW_BYTES = BM * BK * 4; // 8192
+constexpr int A_PLANE = CHUNKS * LBO_A;                 // 8256
+constexpr int B_OFF = RAW_BYTES + 2 * A_PLANE;          // 24704, 128-byte aligned
+constexpr int STAGING_BYTES = 4 * 32 * 33 * 4;          // 16896
+constexpr int THREADS = 320;
+constexpr int MAX_STAGES = 6;
+constexpr uint32_t SPIN_LIMIT = 1u << 22;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -39,6 +50,9 @@ __device__ __forceinline__ void mbar_init(uint32_t addr, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t addr) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(addr) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t addr, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(addr), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint32_t addr, uint32_t parity) {
   uint32_t ok;
@@ -77,12 +91,10 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
   d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
   return d;                // base_offset = 0, lbo_mode = 0, layout_type = SWIZZLE_NONE
 }
-
 // instruction descriptor: D = f32, A = B = tf32, both K-major, M = 128, N = bn
 __device__ __forceinline__ uint32_t make_idesc(int bn) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
-
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t"
@@ -96,52 +108,71 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t
 __device__ __forceinline__ void umma_commit(uint32_t bar_addr) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_addr) : "memory");
 }
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar)
+      : "memory");
+}
 
 struct Args {
-  const float* A; int64_t lda;
-  const float* Bhi; const float* Blo; int64_t ldb;  // pre-split weight planes, zero padded to [Npad16, Kpad16]
+  const float* Bimg;   // pre-packed weight images: [n_tiles][nkb][hi plane | lo plane], each plane CHUNKS * lbo_b bytes
   float* C; int64_t ldc;
   int64_t M; int N; int K;
-  int bn;        // N-tile width (multiple of 16, <= 256)
+  int lda;             // row stride of A in elements
+  int J;               // rows per TMA super-row: 1 (16-byte aligned rows) or 4
+  int bn;              // N-tile width (multiple of 16, <= 256)
+  int n_tiles;         // ceil(Npad16 / bn)
   int nstage;
+  int64_t m_tiles;
   const float* bias; int act;
   const float* base; int64_t ldbase;
   float scale;
   int* status;
 };
 
-__global__ void __launch_bounds__(THREADS) k_gemm_tc(const Args a) {
-  extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ __align__(8) uint64_t bar_full[4];
-  __shared__ __align__(8) uint64_t bar_empty[4];
-  __shared__ __align__(8) uint64_t bar_accum;
+__global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ CUtensorMap tmapA, const Args a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bar_tma[MAX_STAGES];    // TMA bytes landed (raw A + B image)
+  __shared__ __align__(8) uint64_t bar_op[MAX_STAGES];     // converters wrote the hi/lo A planes
+  __shared__ __align__(8) uint64_t bar_empty[MAX_STAGES];  // MMAs reading the stage retired
+  __shared__ __align__(8) uint64_t bar_acc_full[2];
+  __shared__ __align__(8) uint64_t bar_acc_empty[2];
   __shared__ uint32_t tmem_holder;
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
-  const int64_t m0 = (int64_t)blockIdx.x * BM;
-  const int n0 = blockIdx.y * a.bn;
-  const int npad = (a.N + 15) & ~15;
-  const int bn = (npad - n0 < a.bn) ? (npad - n0) : a.bn;   // this tile's MMA N (multiple of 16)
   const int nkb = (a.K + BK - 1) / BK;
-  const int NST = a.nstage;
+  const int NS = a.nstage;
   const uint32_t lbo_b = (uint32_t)a.bn * 16u + 16u;
-  const uint32_t a_plane = CHUNKS * LBO_A;                   // bytes of one A plane (hi or lo) per stage
   const uint32_t b_plane = CHUNKS * lbo_b;
-  const uint32_t stage_bytes = 2 * a_plane + 2 * b_plane;
+  const uint32_t stage_bytes = B_OFF + 2 * b_plane;
   const uint32_t smem_base = smem_u32(smem);
+  const uint32_t staging_off = (uint32_t)NS * stage_bytes;
+  const uint32_t acc_cols = ((uint32_t)a.bn + 31u) & ~31u;       // TMEM columns of one accumulator buffer
   uint32_t tmem_cols = 32;
-  while ((int)tmem_cols < a.bn) tmem_cols <<= 1;
+  while (tmem_cols < 2 * acc_cols) tmem_cols <<= 1;
+  const int64_t total_tiles = a.m_tiles * a.n_tiles;
 
   if (tid == 0) {
-    for (int s = 0; s < NST; ++s) {
-      mbar_init(smem_u32(&bar_full[s]), PROD_THREADS);
+    for (int s = 0; s < NS; ++s) {
+      mbar_init(smem_u32(&bar_tma[s]), 1);
+      mbar_init(smem_u32(&bar_op[s]), 128);
       mbar_init(smem_u32(&bar_empty[s]), 1);
     }
-    mbar_init(smem_u32(&bar_accum), 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(smem_u32(&bar_acc_full[b]), 1);
+      mbar_init(smem_u32(&bar_acc_empty[b]), 128);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 4) {
+  if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_holder)), "r"(tmem_cols));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
@@ -150,215 +181,303 @@ __global__ void __launch_bounds__(THREADS) k_gemm_tc(const Args a) {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = tmem_holder;
 
-  if (warp < 4) {
-    // =========================== producers ===========================
-    const int half = lane >> 4;   // which of the two rows of this warp instruction
-    const int kk = lane & 15;     // k inside the stage
-    const uint32_t koff = (uint32_t)(kk >> 2) * 1u;  // chunk index
-    bool ok = true;
-    for (int kb = 0; kb < nkb && ok; ++kb) {
-      const int s = kb % NST, it = kb / NST;
-      if (it > 0) ok = mbar_wait(smem_u32(&bar_empty[s]), (uint32_t)((it - 1) & 1), a.status, 1);
-      uint8_t* st = smem + (size_t)s * stage_bytes;
-      float* a_hi = reinterpret_cast<float*>(st);
-      float* a_lo = reinterpret_cast<float*>(st + a_plane);
-      float* b_hi = reinterpret_cast<float*>(st + 2 * a_plane);
-      float* b_lo = reinterpret_cast<float*>(st + 2 * a_plane + b_plane);
-      const int64_t gk = (int64_t)kb * BK + kk;
-      const bool kin = gk < a.K;
-      // ---- A: 128 rows x 16 k ; this warp covers rows 8q + warp + 4*half, q = 0..15 ----
-      float v[16];
-#pragma unroll
-      for (int q = 0; q < 16; ++q) {
-        const int row = 8 * q + warp + 4 * half;
-        const int64_t gm = m0 + row;
-        v[q] = (kin && gm < a.M) ? __ldg(a.A + gm * a.lda + gk) : 0.f;
-      }
-#pragma unroll
-      for (int q = 0; q < 16; ++q) {
-        const int row = 8 * q + warp + 4 * half;
-        const uint32_t hi = to_tf32(v[q]);
-        const uint32_t lo = to_tf32(v[q] - __uint_as_float(hi));
-        const uint32_t w = (koff * LBO_A + (uint32_t)row * 16u + (uint32_t)(kk & 3) * 4u) >> 2;
-        a_hi[w] = __uint_as_float(hi);
-        a_lo[w] = __uint_as_float(lo);
-      }
-      // ---- B: bn rows x 16 k from the pre-split planes (already tf32-exact, zero padded) ----
-      const int nq = bn >> 3;
-      for (int q0 = 0; q0 < nq; q0 += 8) {
-        float h[8], l[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int q = q0 + u;
-          const int row = 8 * q + warp + 4 * half;
-          const bool rin = q < nq;
-          const int64_t off = (int64_t)(n0 + row) * a.ldb + gk;
-          h[u] = rin ? __ldg(a.Bhi + off) : 0.f;
-          l[u] = rin ? __ldg(a.Blo + off) : 0.f;
-        }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int q = q0 + u;
-          if (q < nq) {
-            const int row = 8 * q + warp + 4 * half;
-            const uint32_t w = (koff * lbo_b + (uint32_t)row * 16u + (uint32_t)(kk & 3) * 4u) >> 2;
-            b_hi[w] = h[u];
-            b_lo[w] = l[u];
-          }
+  if (warp == 0) {
+    // =========================== TMA producer ===========================
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmapA)) : "memory");
+      uint32_t it = 0;
+      bool ok = true;
+      const uint32_t tx_bytes = RAW_BYTES + 2 * b_plane;
+      const int box_rows = BM / a.J;
+      for (int64_t t = blockIdx.x; t < total_tiles && ok; t += gridDim.x) {
+        const int64_t mt = t / a.n_tiles;
+        const int nt = (int)(t % a.n_tiles);
+        const int c1 = (int)(mt * box_rows);
+        for (int kb = 0; kb < nkb && ok; ++kb, ++it) {
+          const uint32_t s = it % NS, ph = (it / NS) & 1;
+          if (it >= (uint32_t)NS) ok = mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u, a.status, 1);
+          const uint32_t st = smem_base + s * stage_bytes;
+          const uint32_t bar = smem_u32(&bar_tma[s]);
+          mbar_expect_tx(bar, tx_bytes);
+          for (int j = 0; j < a.J; ++j)
+            tma_load_2d(st + (uint32_t)j * (RAW_BYTES / a.J), &tmapA, j * a.lda + kb * BK, c1, bar);
+          bulk_load_1d(st + B_OFF, a.Bimg + ((size_t)nt * nkb + kb) * (2 * b_plane / 4), 2 * b_plane, bar);
         }
       }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the MMA (async proxy)
-      mbar_arrive(smem_u32(&bar_full[s]));
     }
-
-    // =========================== epilogue ===========================
-    ok = ok && mbar_wait(smem_u32(&bar_accum), 0u, a.status, 3);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    float* stg = reinterpret_cast<float*>(smem) + warp * (32 * 33);     // all MMAs retired: stage memory is free
-    const uint32_t taddr_w = tmem_base + ((uint32_t)(32 * warp) << 16);
-    for (int c0 = 0; c0 < bn; c0 += 32) {
-      uint32_t r[32];
-      asm volatile(
-          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
-          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-            "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-            "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-            "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-          : "r"(taddr_w + (uint32_t)c0));
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  } else if (warp == 1) {
+    // =========================== MMA issuer ===========================
+    const uint32_t idesc = make_idesc(a.bn);
+    uint32_t it = 0, tc = 0;
+    bool ok = true;
+    for (int64_t t = blockIdx.x; t < total_tiles && ok; t += gridDim.x, ++tc) {
+      const uint32_t ab = tc & 1, aph = (tc >> 1) & 1;
+      if (tc >= 2) ok = mbar_wait(smem_u32(&bar_acc_empty[ab]), aph ^ 1u, a.status, 4);   // epilogue drained this buffer
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t tmem_d = tmem_base + ab * acc_cols;
+      for (int kb = 0; kb < nkb && ok; ++kb, ++it) {
+        const uint32_t s = it % NS, ph = (it / NS) & 1;
+        ok = mbar_wait(smem_u32(&bar_op[s]), ph, a.status, 2);
+        ok = ok && mbar_wait(smem_u32(&bar_tma[s]), ph, a.status, 2);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (lane == 0) {
+          const uint32_t st = smem_base + s * stage_bytes;
+          const uint32_t a_hi = st + RAW_BYTES, a_lo = a_hi + A_PLANE, b_hi = st + B_OFF, b_lo = b_hi + b_plane;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = __uint_as_float(r[j]);   // row = lane, col = j
-      __syncwarp();
-      const int col = n0 + c0 + lane;
-      const bool cin = (c0 + lane < bn) && (col < a.N);
-      const float bv = (cin && a.bias) ? __ldg(a.bias + col) : 0.f;
-      for (int rr = 0; rr < 32; ++rr) {
-        const int64_t gm = m0 + 32 * warp + rr;
-        if (gm < a.M && cin) {
-          float x = stg[rr * 33 + lane] + bv;
-          if (a.act == 1) x = fmaxf(x, 0.f);
-          else if (a.act == 2) x = tanhf(x);
-          x *= a.scale;
-          if (a.base) x += __ldg(a.base + gm * a.ldbase + col);
-          a.C[gm * a.ldc + col] = x;
+          for (int j = 0; j < BK / 8; ++j) {
+            const uint64_t dah = make_desc(a_hi + 2 * j * LBO_A, LBO_A);
+            const uint64_t dal = make_desc(a_lo + 2 * j * LBO_A, LBO_A);
+            const uint64_t dbh = make_desc(b_hi + 2 * j * lbo_b, lbo_b);
+            const uint64_t dbl = make_desc(b_lo + 2 * j * lbo_b, lbo_b);
+            umma_tf32(tmem_d, dal, dbh, idesc, (kb > 0 || j > 0) ? 1u : 0u);   // small terms first
+            umma_tf32(tmem_d, dah, dbl, idesc, 1u);
+            umma_tf32(tmem_d, dah, dbh, idesc, 1u);
+          }
+          umma_commit(smem_u32(&bar_empty[s]));                       // frees the stage once these MMAs retire
+          if (kb == nkb - 1) umma_commit(smem_u32(&bar_acc_full[ab])); // accumulator complete
         }
+        __syncwarp();
       }
-      __syncwarp();
+    }
+  } else if (warp < 6) {
+    // =========================== converters (raw -> tf32 hi/lo planes) ===========================
+    const int cw = warp - 2;
+    const int half = lane >> 4, kk = lane & 15;
+    const uint32_t kc_off = (uint32_t)(kk >> 2) * LBO_A + (uint32_t)(kk & 3) * 4u;
+    uint32_t it = 0;
+    bool ok = true;
+    for (int64_t t = blockIdx.x; t < total_tiles && ok; t += gridDim.x) {
+      for (int kb = 0; kb < nkb && ok; ++kb, ++it) {
+        const uint32_t s = it % NS, ph = (it / NS) & 1;
+        ok = mbar_wait(smem_u32(&bar_tma[s]), ph, a.status, 3);
+        uint8_t* st = smem + (size_t)s * stage_bytes;
+        const float* raw = reinterpret_cast<const float*>(st);
+        uint8_t* a_hi = st + RAW_BYTES;
+        uint8_t* a_lo = a_hi + A_PLANE;
+        const bool kin = (kb * BK + kk) < a.K;
+        float v[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+          const int row = 8 * q + cw + 4 * half;
+          const int ridx = (a.J == 4) ? ((row & 3) * 32 + (row >> 2)) : row;   // position of the row inside the raw boxes
+          v[q] = raw[ridx * BK + kk];
+        }
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+          const int row = 8 * q + cw + 4 * half;
+          const float x = kin ? v[q] : 0.f;
+          const uint32_t hi = to_tf32(x);
+          const uint32_t lo = to_tf32(x - __uint_as_float(hi));
+          const uint32_t off = kc_off + (uint32_t)row * 16u;
+          *reinterpret_cast<uint32_t*>(a_hi + off) = hi;
+          *reinterpret_cast<uint32_t*>(a_lo + off) = lo;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the MMA (async proxy)
+        mbar_arrive(smem_u32(&bar_op[s]));
+      }
     }
   } else {
-    // =========================== MMA issuer ===========================
-    const uint32_t idesc = make_idesc(bn);
+    // =========================== epilogue ===========================
+    const int qd = warp & 3;   // TMEM lane quadrant this warp may access
+    float* stg = reinterpret_cast<float*>(smem + staging_off) + qd * (32 * 33);
+    uint32_t tc = 0;
     bool ok = true;
-    for (int kb = 0; kb < nkb && ok; ++kb) {
-      const int s = kb % NST, it = kb / NST;
-      ok = mbar_wait(smem_u32(&bar_full[s]), (uint32_t)(it & 1), a.status, 2);
+    for (int64_t t = blockIdx.x; t < total_tiles && ok; t += gridDim.x, ++tc) {
+      const int64_t mt = t / a.n_tiles;
+      const int nt = (int)(t % a.n_tiles);
+      const int64_t m0 = mt * BM;
+      const int n0 = nt * a.bn;
+      const uint32_t ab = tc & 1, aph = (tc >> 1) & 1;
+      ok = mbar_wait(smem_u32(&bar_acc_full[ab]), aph, a.status, 5);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      if (lane == 0) {
-        const uint32_t sa = smem_base + (uint32_t)s * stage_bytes;
-        const uint32_t a_hi = sa, a_lo = sa + a_plane, b_hi = sa + 2 * a_plane, b_lo = sa + 2 * a_plane + b_plane;
+      const uint32_t taddr = tmem_base + ab * acc_cols + ((uint32_t)(32 * qd) << 16);
+      for (int c0 = 0; c0 < a.bn; c0 += 32) {
+        uint32_t r[32];
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+              "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+              "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+              "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+            : "r"(taddr + (uint32_t)c0));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-        for (int j = 0; j < BK / 8; ++j) {
-          const uint64_t dah = make_desc(a_hi + 2 * j * LBO_A, LBO_A);
-          const uint64_t dal = make_desc(a_lo + 2 * j * LBO_A, LBO_A);
-          const uint64_t dbh = make_desc(b_hi + 2 * j * lbo_b, lbo_b);
-          const uint64_t dbl = make_desc(b_lo + 2 * j * lbo_b, lbo_b);
-          umma_tf32(tmem_base, dal, dbh, idesc, (kb > 0 || j > 0) ? 1u : 0u);   // small terms first
-          umma_tf32(tmem_base, dah, dbl, idesc, 1u);
-          umma_tf32(tmem_base, dah, dbh, idesc, 1u);
+        for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = __uint_as_float(r[j]);   // row = lane, col = j
+        __syncwarp();
+        const int col = n0 + c0 + lane;
+        const bool cin = (c0 + lane < a.bn) && (col < a.N);
+        const float bv = (cin && a.bias) ? __ldg(a.bias + col) : 0.f;
+#pragma unroll 4
+        for (int rr = 0; rr < 32; ++rr) {
+          const int64_t gm = m0 + 32 * qd + rr;
+          if (gm < a.M && cin) {
+            float x = stg[rr * 33 + lane] + bv;
+            if (a.act == 1) x = fmaxf(x, 0.f);
+            else if (a.act == 2) x = tanhf(x);
+            x *= a.scale;
+            if (a.base) x += __ldg(a.base + gm * a.ldbase + col);
+            a.C[gm * a.ldc + col] = x;
+          }
         }
-        umma_commit(smem_u32(&bar_empty[s]));                 // frees the stage once these MMAs retire
-        if (kb == nkb - 1) umma_commit(smem_u32(&bar_accum)); // accumulator complete
+        __syncwarp();
       }
-      __syncwarp();
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      mbar_arrive(smem_u32(&bar_acc_empty[ab]));
     }
   }
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 4) {
+  if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols));
   }
 }
 
-// split a row-major weight matrix into tf32 hi / lo planes, zero padded to [rows_pad, cols_pad]
-__global__ void k_presplit(const float* __restrict__ W, int rows, int cols, int64_t ld, float* __restrict__ hi,
-                           float* __restrict__ lo, int rows_pad, int cols_pad) {
-  const int64_t total = (int64_t)rows_pad * cols_pad;
+// Pack a row-major weight matrix W [rows, cols] into per-(n-tile, k-block) stage images:
+//   image(nt, kb) = [hi plane | lo plane], plane = CHUNKS chunks of lbo_b bytes, element (n, k) of the tile at
+//   chunk (k%16)/4, byte n*16 + (k%4)*4.  Out-of-range rows / columns are zero.
+__global__ void k_pack_b(const float* __restrict__ W, int rows, int cols, int64_t ld, float* __restrict__ img, int bn,
+                         int n_tiles, int nkb) {
+  const int plane_f = CHUNKS * (bn * 16 + 16) / 4;
+  const int64_t total = (int64_t)n_tiles * nkb * 2 * plane_f;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int r = (int)(i / cols_pad), c = (int)(i % cols_pad);
-    const float v = (r < rows && c < cols) ? W[(int64_t)r * ld + c] : 0.f;
+    int64_t r = i;
+    const int w = (int)(r % plane_f); r /= plane_f;
+    const int plane = (int)(r % 2); r /= 2;
+    const int kb = (int)(r % nkb);
+    const int nt = (int)(r / nkb);
+    const int chunk_f = (bn * 16 + 16) / 4;
+    const int kc = w / chunk_f, rem = w % chunk_f;
+    const int nl = rem >> 2, e = rem & 3;
+    float v = 0.f;
+    const int n = nt * bn + nl, k = kb * BK + kc * 4 + e;
+    if (nl < bn && n < rows && k < cols) v = W[(int64_t)n * ld + k];
     const uint32_t h = to_tf32(v);
-    hi[i] = __uint_as_float(h);
-    lo[i] = __uint_as_float(to_tf32(v - __uint_as_float(h)));
+    img[i] = (plane == 0) ? __uint_as_float(h) : __uint_as_float(to_tf32(v - __uint_as_float(h)));
   }
 }
 
-}  // namespace tc
-
-size_t presplit_floats(int rows, int cols) {
-  const size_t rp = (size_t)((rows + 15) & ~15), cp = (size_t)((cols + 15) & ~15);
-  return 2 * rp * cp;
+inline int pick_bn(int N) {
+  const int npad = (N + 15) & ~15;
+  const int ntiles = (npad + 255) / 256;
+  return ((npad + ntiles - 1) / ntiles + 15) & ~15;
+}
+inline int pick_ntiles(int N) {
+  const int npad = (N + 15) & ~15;
+  const int bn = pick_bn(N);
+  return (npad + bn - 1) / bn;
 }
 
-int presplit_weights(const float* W, int rows, int cols, int64_t ld, float* planes, cudaStream_t s) {
-  const int rp = (rows + 15) & ~15, cp = (cols + 15) & ~15;
-  const int64_t total = (int64_t)rp * cp;
-  int64_t blocks = ceil_div64(total, 256);
-  if (blocks > kNumSMs * 4) blocks = kNumSMs * 4;
-  tc::k_presplit<<<(unsigned)blocks, 256, 0, s>>>(W, rows, cols, ld, planes, planes + total, rp, cp);
-  GN_LAUNCHED();
-  return GNODE_OK;
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
 }
 
-namespace {
 __device__ int g_tc_status_word = 0;   // barrier-timeout status of the tcgen05 kernels (0 = ok)
 int* status_ptr() {
   static int* p = nullptr;
   if (!p) cudaGetSymbolAddress(reinterpret_cast<void**>(&p), g_tc_status_word);
   return p;
 }
+
+}  // namespace tc
+
+size_t presplit_floats(int rows, int cols) {
+  const int bn = tc::pick_bn(rows), nt = tc::pick_ntiles(rows), nkb = (cols + tc::BK - 1) / tc::BK;
+  return (size_t)nt * nkb * 2 * (tc::CHUNKS * (bn * 16 + 16) / 4);
 }
 
+int presplit_weights(const float* W, int rows, int cols, int64_t ld, float* img, cudaStream_t s) {
+  const int bn = tc::pick_bn(rows), nt = tc::pick_ntiles(rows), nkb = (cols + tc::BK - 1) / tc::BK;
+  const int64_t total = (int64_t)presplit_floats(rows, cols);
+  int64_t blocks = ceil_div64(total, 256);
+  if (blocks > kNumSMs * 4) blocks = kNumSMs * 4;
+  tc::k_pack_b<<<(unsigned)blocks, 256, 0, s>>>(W, rows, cols, ld, img, bn, nt, nkb);
+  GN_LAUNCHED();
+  return GNODE_OK;
+}
+
+// The TMA view needs either 16-byte aligned rows (lda % 4 == 0) or dense rows (K == lda, super-row trick).
 bool gemm_nt_tc_supported(const GemmNT& g) {
-  return g.Bsplit != nullptr && g.M >= 1 && g.N >= 16 && g.K >= 1;
+  if (g.Bsplit == nullptr || g.M < 4 || g.N < 16 || g.K < 1) return false;
+  if ((reinterpret_cast<uintptr_t>(g.A) & 15) != 0) return false;
+  if (g.lda % 4 == 0) return true;
+  return g.K == g.lda && g.lda < (1 << 20);
 }
 
 int gemm_nt_tc(const GemmNT& g, cudaStream_t s) {
   if (g.M == 0 || g.N == 0) return GNODE_OK;
-  int* status_dev = status_ptr();
-  if (!status_dev) { set_error("gemm_nt_tc: cannot resolve the status symbol"); return GNODE_ERR_CUDA; }
-  const int npad = (g.N + 15) & ~15, kpad = (g.K + 15) & ~15;
-  const int ntiles = (npad + 255) / 256;
-  int bn = ((npad + ntiles - 1) / ntiles + 15) & ~15;
+  int* status_dev = tc::status_ptr();
+  tc::EncodeTiledFn enc = tc::encode_fn();
+  if (!status_dev || !enc) { set_error("gemm_nt_tc: driver entry point / status symbol unavailable"); return GNODE_ERR_CUDA; }
+  const int J = (g.lda % 4 == 0) ? 1 : 4;
+  const int64_t M_tc = (J == 4) ? (g.M / 4) * 4 : g.M;     // rows covered by whole super-rows
   tc::Args a;
-  a.A = g.A; a.lda = g.lda;
-  a.Bhi = g.Bsplit; a.Blo = g.Bsplit + (size_t)npad * kpad; a.ldb = kpad;
-  a.C = g.C; a.ldc = g.ldc; a.M = g.M; a.N = g.N; a.K = g.K; a.bn = bn;
+  a.Bimg = g.Bsplit; a.C = g.C; a.ldc = g.ldc; a.M = M_tc; a.N = g.N; a.K = g.K; a.lda = (int)g.lda; a.J = J;
+  a.bn = tc::pick_bn(g.N); a.n_tiles = tc::pick_ntiles(g.N);
+  a.m_tiles = ceil_div64(M_tc, tc::BM);
   a.bias = g.bias; a.act = g.relu; a.base = g.base; a.ldbase = g.ldbase; a.scale = g.scale;
   a.status = status_dev;
-  const size_t stage = 2 * (size_t)tc::CHUNKS * tc::LBO_A + 2 * (size_t)tc::CHUNKS * ((size_t)bn * 16 + 16);
-  int nstage = (int)((100 * 1024) / stage);
-  if (nstage > 4) nstage = 4;
-  if (nstage < 2) nstage = 2;
+  const size_t stage = tc::B_OFF + 2 * (size_t)tc::CHUNKS * ((size_t)a.bn * 16 + 16);
+  const size_t budget = 225 * 1024;
+  int nstage = (int)((budget - tc::STAGING_BYTES) / stage);
+  if (nstage > tc::MAX_STAGES) nstage = tc::MAX_STAGES;
+  if (nstage < 2) { set_error("gemm_nt_tc: tile does not fit in shared memory"); return GNODE_ERR_ARG; }
   a.nstage = nstage;
-  const size_t smem = stage * nstage;
-  static size_t attr_set = 0;
-  if (smem > attr_set) {
-    GN_CUDA(cudaFuncSetAttribute(tc::k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(110 * 1024)));
-    attr_set = 110 * 1024;
+  const size_t smem = stage * nstage + tc::STAGING_BYTES;
+
+  CUtensorMap tmap;
+  {
+    cuuint64_t gdim[2], gstride[1];
+    cuuint32_t box[2] = {(cuuint32_t)tc::BK, (cuuint32_t)(tc::BM / J)};
+    cuuint32_t estr[2] = {1, 1};
+    if (J == 1) {
+      gdim[0] = (cuuint64_t)g.K; gdim[1] = (cuuint64_t)M_tc; gstride[0] = (cuuint64_t)g.lda * 4;
+    } else {
+      gdim[0] = (cuuint64_t)g.lda * 4; gdim[1] = (cuuint64_t)(M_tc / 4); gstride[0] = (cuuint64_t)g.lda * 16;
+    }
+    CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(g.A), gdim, gstride, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("gemm_nt_tc: cuTensorMapEncodeTiled failed (%d)", (int)r); return GNODE_ERR_CUDA; }
   }
-  dim3 grid((unsigned)ceil_div64(g.M, tc::BM), (unsigned)ntiles, 1);
-  tc::k_gemm_tc<<<grid, tc::THREADS, smem, s>>>(a);
-  GN_LAUNCHED();
+  static bool attr_set = false;
+  if (!attr_set) {
+    GN_CUDA(cudaFuncSetAttribute(tc::k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(226 * 1024)));
+    attr_set = true;
+  }
+  if (M_tc > 0) {
+    const int64_t total = a.m_tiles * a.n_tiles;
+    const unsigned grid = (unsigned)(total < kNumSMs ? total : kNumSMs);
+    tc::k_gemm_tc<<<grid, tc::THREADS, smem, s>>>(tmap, a);
+    GN_LAUNCHED();
+  }
+  if (M_tc < g.M) {   // up to 3 trailing rows that do not fill a super-row: FFMA kernel
+    GemmNT tail = g;
+    tail.A = g.A + M_tc * g.lda; tail.C = g.C + M_tc * g.ldc; tail.M = g.M - M_tc;
+    if (g.base) tail.base = g.base + M_tc * g.ldbase;
+    tail.Bsplit = nullptr;
+    GN_TRY(gemm_nt_simt(tail, s));
+  }
   return GNODE_OK;
 }
 
 // reads and clears the tcgen05 status word (0 = ok); synchronises the stream
 int gemm_tc_status(cudaStream_t s, int* out) {
   *out = 0;
-  int* status_dev = status_ptr();
+  int* status_dev = tc::status_ptr();
   if (!status_dev) return GNODE_OK;
   GN_CUDA(cudaMemcpyAsync(out, status_dev, sizeof(int), cudaMemcpyDeviceToHost, s));
   GN_CUDA(cudaStreamSynchronize(s));
@@ -375,8 +494,9 @@ extern "C" int gnode_tc_status(gnode_stream_t stream) {
   int rc = gnode::gemm_tc_status(static_cast<cudaStream_t>(stream), &st);
   if (rc != GNODE_OK) return rc;
   if (st != 0) {
-    gnode::set_error("tcgen05 kernel barrier timeout (code %d: 1 = producer waiting for a free stage, 2 = MMA waiting "
-                     "for operands, 3 = epilogue waiting for the accumulator)", st);
+    gnode::set_error("tcgen05 kernel barrier timeout (code %d: 1 = TMA producer waiting for a free stage, 2 = MMA waiting "
+                     "for operands, 3 = converter waiting for TMA bytes, 4 = MMA waiting for a free accumulator, "
+                     "5 = epilogue waiting for the accumulator)", st);
     return GNODE_ERR_CUDA;
   }
   return GNODE_OK;

@@ -15,6 +15,8 @@ SHAPES = [(128, 128, 399), (1000, 128, 399), (300, 399, 128), (4096 + 37, 64, 12
 @pytest.mark.parametrize("engine", ["simt", "tc"])
 @pytest.mark.parametrize("m,n,k", SHAPES)
 def test_gemm_nt_plain(cuda, engine, m, n, k):
+    if engine == "tc" and m < 4:
+        pytest.skip("the tcgen05 engine takes >= 4 rows; AUTO falls back to FFMA below that")
     torch.manual_seed(m + n + k)
     a = torch.randn(m, k) * 3
     w = torch.randn(n, k) / k ** 0.5
