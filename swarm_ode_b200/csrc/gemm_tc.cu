@@ -10,7 +10,7 @@
 // Persistent kernel, one CTA per SM, ten warps:
 //   warp 0      TMA producer.  A arrives RAW through cp.async.bulk.tensor (2-D map; for rows that are not
 //               16-byte aligned the map views 4 consecutive rows as one "super-row" whose pitch is a
-//               multiple of 16 B, and four boxes per stage pick the four row phases).  B arrives as one
+//               multiple of 16 B, and four 16-byte-aligned boxes per stage pick the four row phases).  B arrives as one
 //               cp.async.bulk of the pre-packed image, already in UMMA layout.  Both complete on an
 //               mbarrier transaction count -> deep memory-level parallelism with no register cost.
 //   warp 1      TMEM alloc; one lane issues tcgen05.mma.kind::tf32 (M=128, N=BN, K=8) and tcgen05.commit.
@@ -35,9 +35,13 @@ constexpr int BM = 128;
 constexpr int BK = 16;                 // K elements per stage: 4 chunks of 16 bytes, 2 MMA K-steps
 constexpr int CHUNKS = BK / 4;
 constexpr int LBO_A = BM * 16 + 16;    // bytes between consecutive 16-byte K-chunks of the A planes (+16: bank spread)
-constexpr int RAW_BYTES = BM * BK * 4; // 8192
 constexpr int A_PLANE = CHUNKS * LBO_A;                 // 8256
-constexpr int B_OFF = RAW_BYTES + 2 * A_PLANE;          // 24704, 128-byte aligned
+// Raw A region of a stage.  Aligned rows (J = 1): one box of 128 rows x 16 floats.  Unaligned rows (J = 4):
+// TMA box starts must be 16-byte aligned in global memory, so each of the four row-phase boxes starts at the
+// aligned address below its first element and is 20 floats wide; the converter applies the 0..3 element shift.
+__host__ __device__ constexpr int raw_stride(int J) { return J == 4 ? 20 : 16; }       // floats per raw row
+__host__ __device__ constexpr int raw_bytes(int J) { return BM * raw_stride(J) * 4; }  // 8192 / 10240
+__host__ __device__ constexpr int b_off(int J) { return raw_bytes(J) + 2 * A_PLANE; }  // 24704 / 26752 (128-B aligned)
 constexpr int STAGING_BYTES = 4 * 32 * 33 * 4;          // 16896
 constexpr int THREADS = 320;
 constexpr int MAX_STAGES = 6;
@@ -138,7 +142,7 @@ struct Args {
 };
 
 __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ CUtensorMap tmapA, const Args a) {
-  extern __shared__ __align__(1024) uint8_t smem[];
+  extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t bar_tma[MAX_STAGES];    // TMA bytes landed (raw A + B image)
   __shared__ __align__(8) uint64_t bar_op[MAX_STAGES];     // converters wrote the hi/lo A planes
   __shared__ __align__(8) uint64_t bar_empty[MAX_STAGES];  // MMAs reading the stage retired
@@ -152,6 +156,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
   const int NS = a.nstage;
   const uint32_t lbo_b = (uint32_t)a.bn * 16u + 16u;
   const uint32_t b_plane = CHUNKS * lbo_b;
+  const uint32_t RAW_BYTES = raw_bytes(a.J), B_OFF = b_off(a.J);
+  const int RS = raw_stride(a.J);
   const uint32_t stage_bytes = B_OFF + 2 * b_plane;
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t staging_off = (uint32_t)NS * stage_bytes;
@@ -199,8 +205,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
           const uint32_t st = smem_base + s * stage_bytes;
           const uint32_t bar = smem_u32(&bar_tma[s]);
           mbar_expect_tx(bar, tx_bytes);
-          for (int j = 0; j < a.J; ++j)
-            tma_load_2d(st + (uint32_t)j * (RAW_BYTES / a.J), &tmapA, j * a.lda + kb * BK, c1, bar);
+          for (int j = 0; j < a.J; ++j)   // box start rounded down to a 16-byte boundary of the super-row
+            tma_load_2d(st + (uint32_t)j * (RAW_BYTES / a.J), &tmapA, (j * a.lda + kb * BK) & ~3, c1, bar);
           bulk_load_1d(st + B_OFF, a.Bimg + ((size_t)nt * nkb + kb) * (2 * b_plane / 4), 2 * b_plane, bar);
         }
       }
@@ -259,8 +265,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
 #pragma unroll
         for (int q = 0; q < 16; ++q) {
           const int row = 8 * q + cw + 4 * half;
-          const int ridx = (a.J == 4) ? ((row & 3) * 32 + (row >> 2)) : row;   // position of the row inside the raw boxes
-          v[q] = raw[ridx * BK + kk];
+          // position of the row inside the raw boxes, plus the element shift of its row phase
+          const int ridx = (a.J == 4) ? ((row & 3) * 32 + (row >> 2)) : row;
+          const int shift = (a.J == 4) ? (((row & 3) * a.lda) & 3) : 0;
+          v[q] = raw[ridx * RS + shift + kk];
         }
 #pragma unroll
         for (int q = 0; q < 16; ++q) {
@@ -430,7 +438,7 @@ int gemm_nt_tc(const GemmNT& g, cudaStream_t s) {
   a.m_tiles = ceil_div64(M_tc, tc::BM);
   a.bias = g.bias; a.act = g.relu; a.base = g.base; a.ldbase = g.ldbase; a.scale = g.scale;
   a.status = status_dev;
-  const size_t stage = tc::B_OFF + 2 * (size_t)tc::CHUNKS * ((size_t)a.bn * 16 + 16);
+  const size_t stage = tc::b_off(J) + 2 * (size_t)tc::CHUNKS * ((size_t)a.bn * 16 + 16);
   const size_t budget = 225 * 1024;
   int nstage = (int)((budget - tc::STAGING_BYTES) / stage);
   if (nstage > tc::MAX_STAGES) nstage = tc::MAX_STAGES;
@@ -441,7 +449,7 @@ int gemm_nt_tc(const GemmNT& g, cudaStream_t s) {
   CUtensorMap tmap;
   {
     cuuint64_t gdim[2], gstride[1];
-    cuuint32_t box[2] = {(cuuint32_t)tc::BK, (cuuint32_t)(tc::BM / J)};
+    cuuint32_t box[2] = {(cuuint32_t)tc::raw_stride(J), (cuuint32_t)(tc::BM / J)};
     cuuint32_t estr[2] = {1, 1};
     if (J == 1) {
       gdim[0] = (cuuint64_t)g.K; gdim[1] = (cuuint64_t)M_tc; gstride[0] = (cuuint64_t)g.lda * 4;
