@@ -7,15 +7,17 @@
 // fp32-grade accuracy on the tensor pipe by the 3xTF32 split: a = a_hi + a_lo, a_hi = rna_tf32(a),
 // a_lo = rna_tf32(a - a_hi); products a_lo*b_hi + a_hi*b_lo + a_hi*b_hi accumulate in fp32 in TMEM.
 //
-// Persistent kernel, one CTA per SM, ten warps:
-//   warp 0      TMA producer.  A arrives RAW through cp.async.bulk.tensor (2-D map; for rows that are not
-//               16-byte aligned the map views 4 consecutive rows as one "super-row" whose pitch is a
-//               multiple of 16 B, and four 16-byte-aligned boxes per stage pick the four row phases).  B arrives as one
-//               cp.async.bulk of the pre-packed image, already in UMMA layout.  Both complete on an
-//               mbarrier transaction count -> deep memory-level parallelism with no register cost.
-//   warp 1      TMEM alloc; one lane issues tcgen05.mma.kind::tf32 (M=128, N=BN, K=8) and tcgen05.commit.
-//   warps 2-5   converters: raw smem -> registers -> hi/lo split -> conflict-free st.shared into the UMMA
-//               K-major no-swizzle layout -> fence.proxy.async -> mbarrier arrive.
+// Persistent kernel, one CTA per SM, eleven warps, three decoupled shared-memory rings:
+//   warp 0      A producer: RAW fp32 tiles through cp.async.bulk.tensor into a DEEP ring (up to 10 stages,
+//               ~100 KB in flight per SM -- what Little's law asks for at HBM latency).  Rows that are not
+//               16-byte aligned are viewed as "super-rows" of 4 rows (pitch = multiple of 16 B); four
+//               16-byte-aligned boxes per stage pick the four row phases, the converter applies the shift.
+//   warp 10     B producer: one cp.async.bulk per K-block of the pre-packed weight image (already in UMMA
+//               layout) into its own ring.
+//   warps 2-5   converters: raw ring -> registers -> hi/lo split -> conflict-free st.shared into the UMMA
+//               K-major no-swizzle A-operand ring -> fence.proxy.async -> mbarrier arrive.
+//   warp 1      TMEM alloc; one lane issues tcgen05.mma.kind::tf32 (M=128, N=BN, K=8) and the tcgen05.commit
+//               that release the A-operand / B stages and publish the accumulator.
 //   warps 6-9   epilogue: tcgen05.ld of their TMEM lane quadrant -> smem transpose -> coalesced global
 //               stores with bias / activation / scale / base.  The accumulator is double buffered in
 //               TMEM, so the epilogue of tile i overlaps the main loop of tile i+1.
@@ -36,15 +38,15 @@ constexpr int BK = 16;                 // K elements per stage: 4 chunks of 16 b
 constexpr int CHUNKS = BK / 4;
 constexpr int LBO_A = BM * 16 + 16;    // bytes between consecutive 16-byte K-chunks of the A planes (+16: bank spread)
 constexpr int A_PLANE = CHUNKS * LBO_A;                 // 8256
-// Raw A region of a stage.  Aligned rows (J = 1): one box of 128 rows x 16 floats.  Unaligned rows (J = 4):
-// TMA box starts must be 16-byte aligned in global memory, so each of the four row-phase boxes starts at the
-// aligned address below its first element and is 20 floats wide; the converter applies the 0..3 element shift.
+constexpr int AOP_BYTES = 2 * A_PLANE;                  // hi + lo planes of one A-operand stage
+// Raw A stage.  Aligned rows (J = 1): one box of 128 rows x 16 floats.  Unaligned rows (J = 4): TMA box
+// starts must be 16-byte aligned in global memory, so each of the four row-phase boxes starts at the aligned
+// address below its first element and is 20 floats wide; the converter applies the 0..3 element shift.
 __host__ __device__ constexpr int raw_stride(int J) { return J == 4 ? 20 : 16; }       // floats per raw row
 __host__ __device__ constexpr int raw_bytes(int J) { return BM * raw_stride(J) * 4; }  // 8192 / 10240
-__host__ __device__ constexpr int b_off(int J) { return raw_bytes(J) + 2 * A_PLANE; }  // 24704 / 26752 (128-B aligned)
 constexpr int STAGING_BYTES = 4 * 32 * 33 * 4;          // 16896
-constexpr int THREADS = 320;
-constexpr int MAX_STAGES = 6;
+constexpr int THREADS = 352;
+constexpr int MAX_RAW = 10, MAX_AOP = 3, MAX_B = 4;
 constexpr uint32_t SPIN_LIMIT = 1u << 22;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -133,7 +135,7 @@ struct Args {
   int J;               // rows per TMA super-row: 1 (16-byte aligned rows) or 4
   int bn;              // N-tile width (multiple of 16, <= 256)
   int n_tiles;         // ceil(Npad16 / bn)
-  int nstage;
+  int n_raw, n_aop, n_b;  // ring depths
   int64_t m_tiles;
   const float* bias; int act;
   const float* base; int64_t ldbase;
@@ -141,41 +143,67 @@ struct Args {
   int* status;
 };
 
+template <int ACT, bool HAS_BASE>
+__device__ __forceinline__ void store_rows(const float* __restrict__ stg, int lane, float bv, float scale, float* crow,
+                                           int64_t ldc, const float* brow, int64_t ldbase, int rmax, bool cin) {
+#pragma unroll
+  for (int r0 = 0; r0 < 32; r0 += 8) {
+    float bs[8];
+    if (HAS_BASE) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) bs[u] = (cin && r0 + u < rmax) ? __ldg(brow + (int64_t)(r0 + u) * ldbase) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      float x = stg[(r0 + u) * 33 + lane] + bv;
+      if (ACT == 1) x = fmaxf(x, 0.f);
+      if (ACT == 2) x = tanhf(x);
+      x *= scale;
+      if (HAS_BASE) x += bs[u];
+      if (cin && r0 + u < rmax) crow[(int64_t)(r0 + u) * ldc] = x;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ CUtensorMap tmapA, const Args a) {
   extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ __align__(8) uint64_t bar_tma[MAX_STAGES];    // TMA bytes landed (raw A + B image)
-  __shared__ __align__(8) uint64_t bar_op[MAX_STAGES];     // converters wrote the hi/lo A planes
-  __shared__ __align__(8) uint64_t bar_empty[MAX_STAGES];  // MMAs reading the stage retired
+  __shared__ __align__(8) uint64_t bar_raw_full[MAX_RAW];
+  __shared__ __align__(8) uint64_t bar_raw_empty[MAX_RAW];
+  __shared__ __align__(8) uint64_t bar_aop_full[MAX_AOP];
+  __shared__ __align__(8) uint64_t bar_aop_empty[MAX_AOP];
+  __shared__ __align__(8) uint64_t bar_b_full[MAX_B];
+  __shared__ __align__(8) uint64_t bar_b_empty[MAX_B];
   __shared__ __align__(8) uint64_t bar_acc_full[2];
   __shared__ __align__(8) uint64_t bar_acc_empty[2];
   __shared__ uint32_t tmem_holder;
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
-  const int nkb = (a.K + BK - 1) / BK;
-  const int NS = a.nstage;
-  const uint32_t lbo_b = (uint32_t)a.bn * 16u + 16u;
+  // hoist every parameter the role loops need (keeps constant-bank loads out of the hot loops)
+  const int K = a.K, J = a.J, lda = a.lda, bn = a.bn, n_tiles = a.n_tiles;
+  const int NR = a.n_raw, NA = a.n_aop, NB = a.n_b;
+  int* const status = a.status;
+  const int nkb = (K + BK - 1) / BK;
+  const uint32_t lbo_b = (uint32_t)bn * 16u + 16u;
   const uint32_t b_plane = CHUNKS * lbo_b;
-  const uint32_t RAW_BYTES = raw_bytes(a.J), B_OFF = b_off(a.J);
-  const int RS = raw_stride(a.J);
-  const uint32_t stage_bytes = B_OFF + 2 * b_plane;
+  const uint32_t RAW_BYTES = raw_bytes(J);
+  const int RS = raw_stride(J);
   const uint32_t smem_base = smem_u32(smem);
-  const uint32_t staging_off = (uint32_t)NS * stage_bytes;
-  const uint32_t acc_cols = ((uint32_t)a.bn + 31u) & ~31u;       // TMEM columns of one accumulator buffer
+  const uint32_t raw_off = 0;
+  const uint32_t aop_off = raw_off + (uint32_t)NR * RAW_BYTES;
+  const uint32_t b_off = aop_off + (uint32_t)NA * AOP_BYTES;
+  const uint32_t staging_off = b_off + (uint32_t)NB * 2u * b_plane;
+  const uint32_t acc_cols = ((uint32_t)bn + 31u) & ~31u;       // TMEM columns of one accumulator buffer
   uint32_t tmem_cols = 32;
   while (tmem_cols < 2 * acc_cols) tmem_cols <<= 1;
-  const int64_t total_tiles = a.m_tiles * a.n_tiles;
+  const int64_t total_tiles = a.m_tiles * n_tiles;
+  const int64_t tile0 = blockIdx.x, tstep = gridDim.x;
 
   if (tid == 0) {
-    for (int s = 0; s < NS; ++s) {
-      mbar_init(smem_u32(&bar_tma[s]), 1);
-      mbar_init(smem_u32(&bar_op[s]), 128);
-      mbar_init(smem_u32(&bar_empty[s]), 1);
-    }
-    for (int b = 0; b < 2; ++b) {
-      mbar_init(smem_u32(&bar_acc_full[b]), 1);
-      mbar_init(smem_u32(&bar_acc_empty[b]), 128);
-    }
+    for (int s = 0; s < NR; ++s) { mbar_init(smem_u32(&bar_raw_full[s]), 1); mbar_init(smem_u32(&bar_raw_empty[s]), 128); }
+    for (int s = 0; s < NA; ++s) { mbar_init(smem_u32(&bar_aop_full[s]), 128); mbar_init(smem_u32(&bar_aop_empty[s]), 1); }
+    for (int s = 0; s < NB; ++s) { mbar_init(smem_u32(&bar_b_full[s]), 1); mbar_init(smem_u32(&bar_b_empty[s]), 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&bar_acc_full[b]), 1); mbar_init(smem_u32(&bar_acc_empty[b]), 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -188,47 +216,63 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
   const uint32_t tmem_base = tmem_holder;
 
   if (warp == 0) {
-    // =========================== TMA producer ===========================
+    // =========================== A producer (raw fp32 tiles, TMA) ===========================
     if (lane == 0) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmapA)) : "memory");
       uint32_t it = 0;
       bool ok = true;
-      const uint32_t tx_bytes = RAW_BYTES + 2 * b_plane;
-      const int box_rows = BM / a.J;
-      for (int64_t t = blockIdx.x; t < total_tiles && ok; t += gridDim.x) {
-        const int64_t mt = t / a.n_tiles;
-        const int nt = (int)(t % a.n_tiles);
-        const int c1 = (int)(mt * box_rows);
+      const int box_rows = BM / J;
+      const uint32_t box_bytes = RAW_BYTES / (uint32_t)J;
+      for (int64_t t = tile0; t < total_tiles && ok; t += tstep) {
+        const int c1 = (int)((t / n_tiles) * box_rows);
         for (int kb = 0; kb < nkb && ok; ++kb, ++it) {
-          const uint32_t s = it % NS, ph = (it / NS) & 1;
-          if (it >= (uint32_t)NS) ok = mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u, a.status, 1);
-          const uint32_t st = smem_base + s * stage_bytes;
-          const uint32_t bar = smem_u32(&bar_tma[s]);
-          mbar_expect_tx(bar, tx_bytes);
-          for (int j = 0; j < a.J; ++j)   // box start rounded down to a 16-byte boundary of the super-row
-            tma_load_2d(st + (uint32_t)j * (RAW_BYTES / a.J), &tmapA, (j * a.lda + kb * BK) & ~3, c1, bar);
-          bulk_load_1d(st + B_OFF, a.Bimg + ((size_t)nt * nkb + kb) * (2 * b_plane / 4), 2 * b_plane, bar);
+          const uint32_t s = it % NR, ph = (it / NR) & 1;
+          if (it >= (uint32_t)NR) ok = mbar_wait(smem_u32(&bar_raw_empty[s]), ph ^ 1u, status, 1);
+          const uint32_t dst = smem_base + raw_off + s * RAW_BYTES;
+          const uint32_t bar = smem_u32(&bar_raw_full[s]);
+          mbar_expect_tx(bar, RAW_BYTES);
+          for (int j = 0; j < J; ++j)   // box start rounded down to a 16-byte boundary of the super-row
+            tma_load_2d(dst + (uint32_t)j * box_bytes, &tmapA, (j * lda + kb * BK) & ~3, c1, bar);
+        }
+      }
+    }
+  } else if (warp == 10) {
+    // =========================== B producer (pre-packed weight images) ===========================
+    if (lane == 0) {
+      const float* Bimg = a.Bimg;
+      uint32_t it = 0;
+      bool ok = true;
+      const uint32_t img_bytes = 2 * b_plane;
+      for (int64_t t = tile0; t < total_tiles && ok; t += tstep) {
+        const int nt = (int)(t % n_tiles);
+        for (int kb = 0; kb < nkb && ok; ++kb, ++it) {
+          const uint32_t s = it % NB, ph = (it / NB) & 1;
+          if (it >= (uint32_t)NB) ok = mbar_wait(smem_u32(&bar_b_empty[s]), ph ^ 1u, status, 6);
+          const uint32_t bar = smem_u32(&bar_b_full[s]);
+          mbar_expect_tx(bar, img_bytes);
+          bulk_load_1d(smem_base + b_off + s * img_bytes, Bimg + ((size_t)nt * nkb + kb) * (img_bytes / 4), img_bytes, bar);
         }
       }
     }
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
-    const uint32_t idesc = make_idesc(a.bn);
+    const uint32_t idesc = make_idesc(bn);
     uint32_t it = 0, tc = 0;
     bool ok = true;
-    for (int64_t t = blockIdx.x; t < total_tiles && ok; t += gridDim.x, ++tc) {
+    for (int64_t t = tile0; t < total_tiles && ok; t += tstep, ++tc) {
       const uint32_t ab = tc & 1, aph = (tc >> 1) & 1;
-      if (tc >= 2) ok = mbar_wait(smem_u32(&bar_acc_empty[ab]), aph ^ 1u, a.status, 4);   // epilogue drained this buffer
+      if (tc >= 2) ok = mbar_wait(smem_u32(&bar_acc_empty[ab]), aph ^ 1u, status, 4);   // epilogue drained this buffer
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t tmem_d = tmem_base + ab * acc_cols;
       for (int kb = 0; kb < nkb && ok; ++kb, ++it) {
-        const uint32_t s = it % NS, ph = (it / NS) & 1;
-        ok = mbar_wait(smem_u32(&bar_op[s]), ph, a.status, 2);
-        ok = ok && mbar_wait(smem_u32(&bar_tma[s]), ph, a.status, 2);
+        const uint32_t sa = it % NA, pa = (it / NA) & 1;
+        const uint32_t sb = it % NB, pb = (it / NB) & 1;
+        ok = mbar_wait(smem_u32(&bar_b_full[sb]), pb, status, 2);
+        ok = ok && mbar_wait(smem_u32(&bar_aop_full[sa]), pa, status, 2);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (lane == 0) {
-          const uint32_t st = smem_base + s * stage_bytes;
-          const uint32_t a_hi = st + RAW_BYTES, a_lo = a_hi + A_PLANE, b_hi = st + B_OFF, b_lo = b_hi + b_plane;
+          const uint32_t a_hi = smem_base + aop_off + sa * AOP_BYTES, a_lo = a_hi + A_PLANE;
+          const uint32_t b_hi = smem_base + b_off + sb * 2u * b_plane, b_lo = b_hi + b_plane;
 #pragma unroll
           for (int j = 0; j < BK / 8; ++j) {
             const uint64_t dah = make_desc(a_hi + 2 * j * LBO_A, LBO_A);
@@ -239,7 +283,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
             umma_tf32(tmem_d, dah, dbl, idesc, 1u);
             umma_tf32(tmem_d, dah, dbh, idesc, 1u);
           }
-          umma_commit(smem_u32(&bar_empty[s]));                       // frees the stage once these MMAs retire
+          umma_commit(smem_u32(&bar_aop_empty[sa]));                   // stages are free once these MMAs retire
+          umma_commit(smem_u32(&bar_b_empty[sb]));
           if (kb == nkb - 1) umma_commit(smem_u32(&bar_acc_full[ab])); // accumulator complete
         }
         __syncwarp();
@@ -250,56 +295,66 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
     const int cw = warp - 2;
     const int half = lane >> 4, kk = lane & 15;
     const uint32_t kc_off = (uint32_t)(kk >> 2) * LBO_A + (uint32_t)(kk & 3) * 4u;
+    // per-thread constant source / destination offsets of its 16 rows
+    int src_off[16];
+    uint32_t dst_off[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      const int row = 8 * q + cw + 4 * half;
+      const int ridx = (J == 4) ? ((row & 3) * 32 + (row >> 2)) : row;   // position of the row inside the raw boxes
+      const int shift = (J == 4) ? (((row & 3) * lda) & 3) : 0;          // element shift of its row phase
+      src_off[q] = ridx * RS + shift + kk;
+      dst_off[q] = kc_off + (uint32_t)row * 16u;
+    }
     uint32_t it = 0;
     bool ok = true;
-    for (int64_t t = blockIdx.x; t < total_tiles && ok; t += gridDim.x) {
+    for (int64_t t = tile0; t < total_tiles && ok; t += tstep) {
       for (int kb = 0; kb < nkb && ok; ++kb, ++it) {
-        const uint32_t s = it % NS, ph = (it / NS) & 1;
-        ok = mbar_wait(smem_u32(&bar_tma[s]), ph, a.status, 3);
-        uint8_t* st = smem + (size_t)s * stage_bytes;
-        const float* raw = reinterpret_cast<const float*>(st);
-        uint8_t* a_hi = st + RAW_BYTES;
-        uint8_t* a_lo = a_hi + A_PLANE;
-        const bool kin = (kb * BK + kk) < a.K;
+        const uint32_t sr = it % NR, pr = (it / NR) & 1;
+        const uint32_t sa = it % NA, pa = (it / NA) & 1;
+        ok = mbar_wait(smem_u32(&bar_raw_full[sr]), pr, status, 3);
+        const float* raw = reinterpret_cast<const float*>(smem + raw_off + (size_t)sr * RAW_BYTES);
         float v[16];
 #pragma unroll
-        for (int q = 0; q < 16; ++q) {
-          const int row = 8 * q + cw + 4 * half;
-          // position of the row inside the raw boxes, plus the element shift of its row phase
-          const int ridx = (a.J == 4) ? ((row & 3) * 32 + (row >> 2)) : row;
-          const int shift = (a.J == 4) ? (((row & 3) * a.lda) & 3) : 0;
-          v[q] = raw[ridx * RS + shift + kk];
-        }
+        for (int q = 0; q < 16; ++q) v[q] = raw[src_off[q]];
+        const bool kin = (kb * BK + kk) < K;
+        if (it >= (uint32_t)NA) ok = ok && mbar_wait(smem_u32(&bar_aop_empty[sa]), pa ^ 1u, status, 7);
+        uint8_t* a_hi = smem + aop_off + (size_t)sa * AOP_BYTES;
+        uint8_t* a_lo = a_hi + A_PLANE;
 #pragma unroll
         for (int q = 0; q < 16; ++q) {
-          const int row = 8 * q + cw + 4 * half;
           const float x = kin ? v[q] : 0.f;
           const uint32_t hi = to_tf32(x);
           const uint32_t lo = to_tf32(x - __uint_as_float(hi));
-          const uint32_t off = kc_off + (uint32_t)row * 16u;
-          *reinterpret_cast<uint32_t*>(a_hi + off) = hi;
-          *reinterpret_cast<uint32_t*>(a_lo + off) = lo;
+          *reinterpret_cast<uint32_t*>(a_hi + dst_off[q]) = hi;
+          *reinterpret_cast<uint32_t*>(a_lo + dst_off[q]) = lo;
         }
+        mbar_arrive(smem_u32(&bar_raw_empty[sr]));                     // raw stage consumed (values are in registers)
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the MMA (async proxy)
-        mbar_arrive(smem_u32(&bar_op[s]));
+        mbar_arrive(smem_u32(&bar_aop_full[sa]));
       }
     }
   } else {
     // =========================== epilogue ===========================
     const int qd = warp & 3;   // TMEM lane quadrant this warp may access
     float* stg = reinterpret_cast<float*>(smem + staging_off) + qd * (32 * 33);
+    float* const Cp = a.C;
+    const float* const basep = a.base;
+    const float* const biasp = a.bias;
+    const int64_t ldc = a.ldc, ldbase = a.ldbase, M = a.M;
+    const int N = a.N, act = a.act;
+    const float scale = a.scale;
     uint32_t tc = 0;
     bool ok = true;
-    for (int64_t t = blockIdx.x; t < total_tiles && ok; t += gridDim.x, ++tc) {
-      const int64_t mt = t / a.n_tiles;
-      const int nt = (int)(t % a.n_tiles);
-      const int64_t m0 = mt * BM;
-      const int n0 = nt * a.bn;
+    for (int64_t t = tile0; t < total_tiles && ok; t += tstep, ++tc) {
+      const int64_t m0 = (t / n_tiles) * BM + 32 * qd;
+      const int n0 = (int)(t % n_tiles) * bn;
       const uint32_t ab = tc & 1, aph = (tc >> 1) & 1;
-      ok = mbar_wait(smem_u32(&bar_acc_full[ab]), aph, a.status, 5);
+      ok = mbar_wait(smem_u32(&bar_acc_full[ab]), aph, status, 5);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t taddr = tmem_base + ab * acc_cols + ((uint32_t)(32 * qd) << 16);
-      for (int c0 = 0; c0 < a.bn; c0 += 32) {
+      const int rmax = (M - m0 < 32) ? (int)(M - m0) : 32;   // valid rows of this warp's slab (may be <= 0)
+      for (int c0 = 0; c0 < bn; c0 += 32) {
         uint32_t r[32];
         asm volatile(
             "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -315,19 +370,18 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
         for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = __uint_as_float(r[j]);   // row = lane, col = j
         __syncwarp();
         const int col = n0 + c0 + lane;
-        const bool cin = (c0 + lane < a.bn) && (col < a.N);
-        const float bv = (cin && a.bias) ? __ldg(a.bias + col) : 0.f;
-#pragma unroll 4
-        for (int rr = 0; rr < 32; ++rr) {
-          const int64_t gm = m0 + 32 * qd + rr;
-          if (gm < a.M && cin) {
-            float x = stg[rr * 33 + lane] + bv;
-            if (a.act == 1) x = fmaxf(x, 0.f);
-            else if (a.act == 2) x = tanhf(x);
-            x *= a.scale;
-            if (a.base) x += __ldg(a.base + gm * a.ldbase + col);
-            a.C[gm * a.ldc + col] = x;
-          }
+        const bool cin = (c0 + lane < bn) && (col < N);
+        const float bv = (cin && biasp) ? __ldg(biasp + col) : 0.f;
+        float* crow = Cp + m0 * ldc + col;
+        const float* brow = basep ? basep + m0 * ldbase + col : nullptr;
+        if (basep) {
+          if (act == 0) store_rows<0, true>(stg, lane, bv, scale, crow, ldc, brow, ldbase, rmax, cin);
+          else if (act == 1) store_rows<1, true>(stg, lane, bv, scale, crow, ldc, brow, ldbase, rmax, cin);
+          else store_rows<2, true>(stg, lane, bv, scale, crow, ldc, brow, ldbase, rmax, cin);
+        } else {
+          if (act == 0) store_rows<0, false>(stg, lane, bv, scale, crow, ldc, brow, ldbase, rmax, cin);
+          else if (act == 1) store_rows<1, false>(stg, lane, bv, scale, crow, ldc, brow, ldbase, rmax, cin);
+          else store_rows<2, false>(stg, lane, bv, scale, crow, ldc, brow, ldbase, rmax, cin);
         }
         __syncwarp();
       }
@@ -438,13 +492,17 @@ int gemm_nt_tc(const GemmNT& g, cudaStream_t s) {
   a.m_tiles = ceil_div64(M_tc, tc::BM);
   a.bias = g.bias; a.act = g.relu; a.base = g.base; a.ldbase = g.ldbase; a.scale = g.scale;
   a.status = status_dev;
-  const size_t stage = tc::b_off(J) + 2 * (size_t)tc::CHUNKS * ((size_t)a.bn * 16 + 16);
-  const size_t budget = 225 * 1024;
-  int nstage = (int)((budget - tc::STAGING_BYTES) / stage);
-  if (nstage > tc::MAX_STAGES) nstage = tc::MAX_STAGES;
-  if (nstage < 2) { set_error("gemm_nt_tc: tile does not fit in shared memory"); return GNODE_ERR_ARG; }
-  a.nstage = nstage;
-  const size_t smem = stage * nstage + tc::STAGING_BYTES;
+  // shared-memory plan: A-operand ring (3) + B ring (4, or 3 for wide tiles) + staging, the rest is the raw ring
+  const size_t img = 2 * (size_t)tc::CHUNKS * ((size_t)a.bn * 16 + 16);
+  const size_t budget = 224 * 1024;
+  a.n_aop = tc::MAX_AOP;
+  a.n_b = (a.bn > 128) ? 3 : tc::MAX_B;
+  const size_t fixed = (size_t)a.n_aop * tc::AOP_BYTES + (size_t)a.n_b * img + tc::STAGING_BYTES;
+  int n_raw = (int)((budget - fixed) / tc::raw_bytes(J));
+  if (n_raw > tc::MAX_RAW) n_raw = tc::MAX_RAW;
+  if (n_raw < 2) { set_error("gemm_nt_tc: tile does not fit in shared memory"); return GNODE_ERR_ARG; }
+  a.n_raw = n_raw;
+  const size_t smem = fixed + (size_t)n_raw * tc::raw_bytes(J);
 
   CUtensorMap tmap;
   {
@@ -463,7 +521,7 @@ int gemm_nt_tc(const GemmNT& g, cudaStream_t s) {
   }
   static bool attr_set = false;
   if (!attr_set) {
-    GN_CUDA(cudaFuncSetAttribute(tc::k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(226 * 1024)));
+    GN_CUDA(cudaFuncSetAttribute(tc::k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(225 * 1024)));
     attr_set = true;
   }
   if (M_tc > 0) {
@@ -502,9 +560,10 @@ extern "C" int gnode_tc_status(gnode_stream_t stream) {
   int rc = gnode::gemm_tc_status(static_cast<cudaStream_t>(stream), &st);
   if (rc != GNODE_OK) return rc;
   if (st != 0) {
-    gnode::set_error("tcgen05 kernel barrier timeout (code %d: 1 = TMA producer waiting for a free stage, 2 = MMA waiting "
+    gnode::set_error("tcgen05 kernel barrier timeout (code %d: 1 = A producer waiting for a free raw stage, 2 = MMA waiting "
                      "for operands, 3 = converter waiting for TMA bytes, 4 = MMA waiting for a free accumulator, "
-                     "5 = epilogue waiting for the accumulator)", st);
+                     "5 = epilogue waiting for the accumulator, 6 = B producer waiting for a free stage, 7 = converter "
+                     "waiting for a free A-operand stage)", st);
     return GNODE_ERR_CUDA;
   }
   return GNODE_OK;
