@@ -45,7 +45,11 @@ constexpr int AOP_BYTES = 2 * A_PLANE;                  // hi + lo planes of one
 __host__ __device__ constexpr int raw_stride(int J) { return J == 4 ? 20 : 16; }       // floats per raw row
 __host__ __device__ constexpr int raw_bytes(int J) { return BM * raw_stride(J) * 4; }  // 8192 / 10240
 constexpr int STAGING_BYTES = 4 * 32 * 33 * 4;          // 16896
-constexpr int THREADS = 352;
+constexpr int CONV_WARPS = 8;                           // converter warps (2 per SM sub-partition)
+constexpr int CONV_THREADS = CONV_WARPS * 32;
+constexpr int WARP_EPI0 = 2 + CONV_WARPS;               // first epilogue warp (10: 10 % 4 == 2, quadrants 2,3,0,1)
+constexpr int WARP_BPROD = WARP_EPI0 + 4;               // B producer warp
+constexpr int THREADS = (WARP_BPROD + 1) * 32;          // 480
 constexpr int MAX_RAW = 10, MAX_AOP = 3, MAX_B = 4;
 constexpr uint32_t SPIN_LIMIT = 1u << 22;
 
@@ -200,8 +204,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
   const int64_t tile0 = blockIdx.x, tstep = gridDim.x;
 
   if (tid == 0) {
-    for (int s = 0; s < NR; ++s) { mbar_init(smem_u32(&bar_raw_full[s]), 1); mbar_init(smem_u32(&bar_raw_empty[s]), 128); }
-    for (int s = 0; s < NA; ++s) { mbar_init(smem_u32(&bar_aop_full[s]), 128); mbar_init(smem_u32(&bar_aop_empty[s]), 1); }
+    for (int s = 0; s < NR; ++s) { mbar_init(smem_u32(&bar_raw_full[s]), 1); mbar_init(smem_u32(&bar_raw_empty[s]), CONV_THREADS); }
+    for (int s = 0; s < NA; ++s) { mbar_init(smem_u32(&bar_aop_full[s]), CONV_THREADS); mbar_init(smem_u32(&bar_aop_empty[s]), 1); }
     for (int s = 0; s < NB; ++s) { mbar_init(smem_u32(&bar_b_full[s]), 1); mbar_init(smem_u32(&bar_b_empty[s]), 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&bar_acc_full[b]), 1); mbar_init(smem_u32(&bar_acc_empty[b]), 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -219,66 +223,67 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
     // =========================== A producer (raw fp32 tiles, TMA) ===========================
     if (lane == 0) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmapA)) : "memory");
-      uint32_t it = 0;
-      bool ok = true;
+      uint32_t s = 0, ph = 0;        // ring slot and phase bit (flips on wrap)
+      bool first_lap = true, ok = true;
       const int box_rows = BM / J;
       const uint32_t box_bytes = RAW_BYTES / (uint32_t)J;
       for (int64_t t = tile0; t < total_tiles && ok; t += tstep) {
         const int c1 = (int)((t / n_tiles) * box_rows);
-        for (int kb = 0; kb < nkb && ok; ++kb, ++it) {
-          const uint32_t s = it % NR, ph = (it / NR) & 1;
-          if (it >= (uint32_t)NR) ok = mbar_wait(smem_u32(&bar_raw_empty[s]), ph ^ 1u, status, 1);
+        for (int kb = 0; kb < nkb && ok; ++kb) {
+          if (!first_lap) ok = mbar_wait(smem_u32(&bar_raw_empty[s]), ph ^ 1u, status, 1);
           const uint32_t dst = smem_base + raw_off + s * RAW_BYTES;
           const uint32_t bar = smem_u32(&bar_raw_full[s]);
           mbar_expect_tx(bar, RAW_BYTES);
           for (int j = 0; j < J; ++j)   // box start rounded down to a 16-byte boundary of the super-row
             tma_load_2d(dst + (uint32_t)j * box_bytes, &tmapA, (j * lda + kb * BK) & ~3, c1, bar);
+          if (++s == (uint32_t)NR) { s = 0; ph ^= 1u; first_lap = false; }
         }
       }
     }
-  } else if (warp == 10) {
+  } else if (warp == WARP_BPROD) {
     // =========================== B producer (pre-packed weight images) ===========================
     if (lane == 0) {
       const float* Bimg = a.Bimg;
-      uint32_t it = 0;
-      bool ok = true;
+      uint32_t s = 0, ph = 0;
+      bool first_lap = true, ok = true;
       const uint32_t img_bytes = 2 * b_plane;
       for (int64_t t = tile0; t < total_tiles && ok; t += tstep) {
-        const int nt = (int)(t % n_tiles);
-        for (int kb = 0; kb < nkb && ok; ++kb, ++it) {
-          const uint32_t s = it % NB, ph = (it / NB) & 1;
-          if (it >= (uint32_t)NB) ok = mbar_wait(smem_u32(&bar_b_empty[s]), ph ^ 1u, status, 6);
+        const float* src = Bimg + (size_t)(t % n_tiles) * nkb * (img_bytes / 4);
+        for (int kb = 0; kb < nkb && ok; ++kb, src += img_bytes / 4) {
+          if (!first_lap) ok = mbar_wait(smem_u32(&bar_b_empty[s]), ph ^ 1u, status, 6);
           const uint32_t bar = smem_u32(&bar_b_full[s]);
           mbar_expect_tx(bar, img_bytes);
-          bulk_load_1d(smem_base + b_off + s * img_bytes, Bimg + ((size_t)nt * nkb + kb) * (img_bytes / 4), img_bytes, bar);
+          bulk_load_1d(smem_base + b_off + s * img_bytes, src, img_bytes, bar);
+          if (++s == (uint32_t)NB) { s = 0; ph ^= 1u; first_lap = false; }
         }
       }
     }
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
     const uint32_t idesc = make_idesc(bn);
-    uint32_t it = 0, tc = 0;
+    // descriptor templates: everything but the 14-bit start address; K-step j advances the address by 2 chunks
+    const uint64_t desc_a = make_desc(0, LBO_A), desc_b = make_desc(0, lbo_b);
+    const uint32_t step_a = (2 * LBO_A) >> 4, step_b = (2 * lbo_b) >> 4;
+    uint32_t sa = 0, pa = 0, sb = 0, pb = 0, tc = 0;
     bool ok = true;
     for (int64_t t = tile0; t < total_tiles && ok; t += tstep, ++tc) {
       const uint32_t ab = tc & 1, aph = (tc >> 1) & 1;
       if (tc >= 2) ok = mbar_wait(smem_u32(&bar_acc_empty[ab]), aph ^ 1u, status, 4);   // epilogue drained this buffer
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t tmem_d = tmem_base + ab * acc_cols;
-      for (int kb = 0; kb < nkb && ok; ++kb, ++it) {
-        const uint32_t sa = it % NA, pa = (it / NA) & 1;
-        const uint32_t sb = it % NB, pb = (it / NB) & 1;
+      for (int kb = 0; kb < nkb && ok; ++kb) {
         ok = mbar_wait(smem_u32(&bar_b_full[sb]), pb, status, 2);
         ok = ok && mbar_wait(smem_u32(&bar_aop_full[sa]), pa, status, 2);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (lane == 0) {
-          const uint32_t a_hi = smem_base + aop_off + sa * AOP_BYTES, a_lo = a_hi + A_PLANE;
-          const uint32_t b_hi = smem_base + b_off + sb * 2u * b_plane, b_lo = b_hi + b_plane;
+          const uint32_t a_hi = (smem_base + aop_off + sa * AOP_BYTES) >> 4, a_lo = a_hi + (A_PLANE >> 4);
+          const uint32_t b_hi = (smem_base + b_off + sb * 2u * b_plane) >> 4, b_lo = b_hi + (b_plane >> 4);
 #pragma unroll
           for (int j = 0; j < BK / 8; ++j) {
-            const uint64_t dah = make_desc(a_hi + 2 * j * LBO_A, LBO_A);
-            const uint64_t dal = make_desc(a_lo + 2 * j * LBO_A, LBO_A);
-            const uint64_t dbh = make_desc(b_hi + 2 * j * lbo_b, lbo_b);
-            const uint64_t dbl = make_desc(b_lo + 2 * j * lbo_b, lbo_b);
+            const uint64_t dah = desc_a | (uint64_t)(a_hi + j * step_a);
+            const uint64_t dal = desc_a | (uint64_t)(a_lo + j * step_a);
+            const uint64_t dbh = desc_b | (uint64_t)(b_hi + j * step_b);
+            const uint64_t dbl = desc_b | (uint64_t)(b_lo + j * step_b);
             umma_tf32(tmem_d, dal, dbh, idesc, (kb > 0 || j > 0) ? 1u : 0u);   // small terms first
             umma_tf32(tmem_d, dah, dbl, idesc, 1u);
             umma_tf32(tmem_d, dah, dbh, idesc, 1u);
@@ -288,50 +293,60 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
           if (kb == nkb - 1) umma_commit(smem_u32(&bar_acc_full[ab])); // accumulator complete
         }
         __syncwarp();
+        if (++sa == (uint32_t)NA) { sa = 0; pa ^= 1u; }
+        if (++sb == (uint32_t)NB) { sb = 0; pb ^= 1u; }
       }
     }
-  } else if (warp < 6) {
+  } else if (warp < WARP_EPI0) {
     // =========================== converters (raw -> tf32 hi/lo planes) ===========================
+    // 8 warps; a warp instruction covers two rows (r, r+4) x 16 k.  Warp cw owns row phase p = cw & 3 of the
+    // 8-row groups q in [8*(cw>>2), 8*(cw>>2)+8):  row = 8q + p + 4*half.
+    constexpr int QPW = 16 / (CONV_WARPS / 4);   // 8-row groups per warp
     const int cw = warp - 2;
+    const int p = cw & 3, q0 = (cw >> 2) * QPW;
     const int half = lane >> 4, kk = lane & 15;
     const uint32_t kc_off = (uint32_t)(kk >> 2) * LBO_A + (uint32_t)(kk & 3) * 4u;
-    // per-thread constant source / destination offsets of its 16 rows
-    int src_off[16];
-    uint32_t dst_off[16];
+    // per-thread constant source / destination offsets of its rows
+    int src_off[QPW];
+    uint32_t dst_off[QPW];
 #pragma unroll
-    for (int q = 0; q < 16; ++q) {
-      const int row = 8 * q + cw + 4 * half;
+    for (int q = 0; q < QPW; ++q) {
+      const int row = 8 * (q0 + q) + p + 4 * half;
       const int ridx = (J == 4) ? ((row & 3) * 32 + (row >> 2)) : row;   // position of the row inside the raw boxes
       const int shift = (J == 4) ? (((row & 3) * lda) & 3) : 0;          // element shift of its row phase
       src_off[q] = ridx * RS + shift + kk;
       dst_off[q] = kc_off + (uint32_t)row * 16u;
     }
-    uint32_t it = 0;
-    bool ok = true;
+    uint32_t sr = 0, pr = 0, sa = 0, pa = 0;
+    bool first_lap_a = true, ok = true;
     for (int64_t t = tile0; t < total_tiles && ok; t += tstep) {
-      for (int kb = 0; kb < nkb && ok; ++kb, ++it) {
-        const uint32_t sr = it % NR, pr = (it / NR) & 1;
-        const uint32_t sa = it % NA, pa = (it / NA) & 1;
+      for (int kb = 0; kb < nkb && ok; ++kb) {
         ok = mbar_wait(smem_u32(&bar_raw_full[sr]), pr, status, 3);
         const float* raw = reinterpret_cast<const float*>(smem + raw_off + (size_t)sr * RAW_BYTES);
-        float v[16];
+        float v[QPW];
 #pragma unroll
-        for (int q = 0; q < 16; ++q) v[q] = raw[src_off[q]];
-        const bool kin = (kb * BK + kk) < K;
-        if (it >= (uint32_t)NA) ok = ok && mbar_wait(smem_u32(&bar_aop_empty[sa]), pa ^ 1u, status, 7);
+        for (int q = 0; q < QPW; ++q) v[q] = raw[src_off[q]];
+        if (kb == nkb - 1 && (kb * BK + kk) >= K) {   // K tail: columns beyond K hold the next row's data (or TMA zero fill)
+#pragma unroll
+          for (int q = 0; q < QPW; ++q) v[q] = 0.f;
+        }
+        if (!first_lap_a) ok = ok && mbar_wait(smem_u32(&bar_aop_empty[sa]), pa ^ 1u, status, 7);
         uint8_t* a_hi = smem + aop_off + (size_t)sa * AOP_BYTES;
         uint8_t* a_lo = a_hi + A_PLANE;
 #pragma unroll
-        for (int q = 0; q < 16; ++q) {
-          const float x = kin ? v[q] : 0.f;
-          const uint32_t hi = to_tf32(x);
-          const uint32_t lo = to_tf32(x - __uint_as_float(hi));
-          *reinterpret_cast<uint32_t*>(a_hi + dst_off[q]) = hi;
-          *reinterpret_cast<uint32_t*>(a_lo + dst_off[q]) = lo;
+        for (int q = 0; q < QPW; ++q) {
+          // hi = x rounded to tf32 (round-half-away on the magnitude bits), lo = x - hi exactly; the tensor core
+          // reads the top 19 bits of lo.  (Finite inputs assumed: no NaN/Inf special-casing in the hot loop.)
+          const uint32_t hb = (__float_as_uint(v[q]) + 0x1000u) & 0xFFFFE000u;
+          const float lo = v[q] - __uint_as_float(hb);
+          *reinterpret_cast<uint32_t*>(a_hi + dst_off[q]) = hb;
+          *reinterpret_cast<float*>(a_lo + dst_off[q]) = lo;
         }
         mbar_arrive(smem_u32(&bar_raw_empty[sr]));                     // raw stage consumed (values are in registers)
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the MMA (async proxy)
         mbar_arrive(smem_u32(&bar_aop_full[sa]));
+        if (++sr == (uint32_t)NR) { sr = 0; pr ^= 1u; }
+        if (++sa == (uint32_t)NA) { sa = 0; pa ^= 1u; first_lap_a = false; }
       }
     }
   } else {
