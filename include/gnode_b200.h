@@ -161,16 +161,24 @@ int gnode_rhs_bwd(const gnode_graph* g, const gnode_sage3_params* p, const float
  * ---------------------------------------------------------------------------------------- */
 size_t gnode_integrate_fixed_workspace_bytes(int64_t n_nodes, int32_t node_dim, int32_t hidden_dim,
                                              int32_t method, int32_t backward);
+/* Bytes of the optional `save` area: per solver step the stage inputs and the per-stage layer
+ * intermediates (what autograd would keep on its tape).  0 for n_t < 2. */
+size_t gnode_integrate_fixed_save_bytes(int64_t n_nodes, int32_t node_dim, int32_t hidden_dim,
+                                        int32_t method, int32_t n_t);
+/* save: NULL for a plain forward; otherwise a device buffer of >= *_save_bytes() that the matching
+ * gnode_integrate_fixed_bwd call reads instead of recomputing every stage. */
 int gnode_integrate_fixed(const gnode_graph* g, const gnode_sage3_params* p, int32_t method,
                           const float* y0, const float* t, int32_t n_t, float* sol,
+                          void* save, size_t save_bytes,
                           void* workspace, size_t workspace_bytes, gnode_stream_t stream);
 /* Backprop through the solver (discretise-then-optimise, like autograd through torchdiffeq's
  * fixed-grid loop).  sol is the forward output; grad_sol: device [n_t, n_nodes, D] (cotangent of
- * every saved time point); grad_y0 overwritten; param grads accumulated (+=). Each step's stages
- * are recomputed from sol[j]. */
+ * every saved time point); grad_y0 overwritten; param grads accumulated (+=).  With save == NULL
+ * each step's stages are recomputed from sol[j]; with the forward's save area they are not. */
 int gnode_integrate_fixed_bwd(const gnode_graph* g, const gnode_sage3_params* p, int32_t method,
                               const float* sol, const float* t, int32_t n_t, const float* grad_sol,
                               float* grad_y0, const gnode_sage3_grads* grads,
+                              const void* save, size_t save_bytes,
                               void* workspace, size_t workspace_bytes, gnode_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------

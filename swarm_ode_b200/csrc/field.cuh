@@ -66,8 +66,14 @@ int check_graph(const gnode_graph* g, const char* who);
 int check_params(const gnode_sage3_params* p, const char* who);
 
 // ---- generic drivers (integrate.cu) ----
+// Optional per-step hook of integrate_fixed: called before step j; may re-point the field's intermediate slots
+// and returns the stage-input buffers xs[1..S-1] to use for this step (stage st then evaluates into slot st).
+struct StepSaver {
+  virtual ~StepSaver() {}
+  virtual float* const* begin_step(int j) = 0;
+};
 int integrate_fixed(Field& f, int method, const float* y0, const float* t, int n_t, float* sol,
-                    float* const* kbuf /* S-1 buffers */, float* xs, cudaStream_t s);
+                    float* const* kbuf /* S-1 buffers */, float* xs, cudaStream_t s, StepSaver* saver = nullptr);
 
 struct Dopri5Bufs {
   float* k[7];

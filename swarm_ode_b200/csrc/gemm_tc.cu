@@ -247,7 +247,19 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
       uint32_t s = 0, ph = 0;
       bool first_lap = true, ok = true;
       const uint32_t img_bytes = 2 * b_plane;
+      const float* const basep = a.base;
+      const int64_t ldbase = a.ldbase, M = a.M;
+      const bool base_pf = basep != nullptr && (reinterpret_cast<uint64_t>(basep) & 15) == 0;
       for (int64_t t = tile0; t < total_tiles && ok; t += tstep) {
+        if (base_pf && (t % n_tiles) == 0) {
+          // the epilogue of this tile reads base[m0 : m0+128, :]: one contiguous span -> warm it in L2 now,
+          // a whole main loop ahead of its use
+          const int64_t m0 = (t / n_tiles) * BM;
+          const int64_t rows = (M - m0 < BM) ? (M - m0) : BM;
+          const uint32_t bytes = (uint32_t)((rows * ldbase * 4) & ~15ll);
+          if (bytes > 0)
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<uint64_t>(basep + m0 * ldbase)), "r"(bytes) : "memory");
+        }
         const float* src = Bimg + (size_t)(t % n_tiles) * nkb * (img_bytes / 4);
         for (int kb = 0; kb < nkb && ok; ++kb, src += img_bytes / 4) {
           if (!first_lap) ok = mbar_wait(smem_u32(&bar_b_empty[s]), ph ^ 1u, status, 6);

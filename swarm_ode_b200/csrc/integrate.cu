@@ -101,7 +101,7 @@ static int stage_input(const Tableau& tb, int s_idx, const float* y, float* cons
 // Fixed grid: grid == t, solution[j+1] = y_j + step(y_j)
 // ------------------------------------------------------------------------------------------------
 int integrate_fixed(Field& f, int method, const float* y0, const float* t, int n_t, float* sol,
-                    float* const* kbuf, float* xs, cudaStream_t s) {
+                    float* const* kbuf, float* xs_shared, cudaStream_t s, StepSaver* saver) {
   const Tableau* tbp = tableau_for(method);
   if (!tbp || method == GNODE_DOPRI5) { set_error("integrate_fixed: bad method %d", method); return GNODE_ERR_ARG; }
   const Tableau& tb = *tbp;
@@ -112,13 +112,17 @@ int integrate_fixed(Field& f, int method, const float* y0, const float* t, int n
     const float* y = sol + (int64_t)j * n;
     float* y1 = sol + (int64_t)(j + 1) * n;
     const int S = tb.S;
+    // with a saver every stage keeps its input and its layer intermediates (slot = stage) for the backward pass
+    float* const* xs_step = saver ? saver->begin_step(j) : nullptr;
     for (int st = 0; st < S - 1; ++st) {
       const float* x = y;
+      float* xs = saver ? xs_step[st] : xs_shared;
       if (st > 0) { GN_TRY(stage_input(tb, st, y, kbuf, dt, xs, n, s)); x = xs; }
-      GN_TRY(f.eval(x, kbuf[st], nullptr, 1.f, 0, s));
+      GN_TRY(f.eval(x, kbuf[st], nullptr, 1.f, saver ? st : 0, s));
     }
     // last stage: y1 = (y + dt * sum_{j<S-1} c_j k_j) + dt * c_{S-1} * f(x_{S-1}) fused into the field's epilogue
     const float* x = y;
+    float* xs = saver ? xs_step[S - 1] : xs_shared;
     if (S > 1) { GN_TRY(stage_input(tb, S - 1, y, kbuf, dt, xs, n, s)); x = xs; }
     const float* base = y;
     if (S > 1) {
@@ -128,7 +132,7 @@ int integrate_fixed(Field& f, int method, const float* y0, const float* t, int n
       GN_TRY(lincomb(lc, s));
       base = y1;
     }
-    GN_TRY(f.eval(x, y1, base, (float)tb.c_sol[S - 1] * dt, 0, s));
+    GN_TRY(f.eval(x, y1, base, (float)tb.c_sol[S - 1] * dt, saver ? S - 1 : 0, s));
   }
   return GNODE_OK;
 }
@@ -308,7 +312,30 @@ void carve_fixed(Arena& a, Sage3Ctx& c, const Tableau& tb, bool backward, FixedW
   }
 }
 
+// Per-step save area of a forward pass that will be differentiated: stage inputs xs[1..S-1] ([N, D] each) and
+// the per-stage layer intermediates cat1 / cat2 ([N, 2H] each).  Lets the backward skip the stage recompute.
+struct Sage3Saver : StepSaver {
+  Sage3Ctx* c; int S; size_t n, nc; float* base; float* xs[kMaxStages];
+  size_t step_floats() const { return (size_t)(S - 1) * n + (size_t)S * 2 * nc; }
+  float* const* begin_step(int j) override {
+    float* p = base + (size_t)j * step_floats();
+    xs[0] = nullptr;
+    for (int st = 1; st < S; ++st) { xs[st] = p; p += n; }
+    for (int st = 0; st < S; ++st) { c->cat1[st] = p; p += nc; c->cat2[st] = p; p += nc; }
+    return xs;
+  }
+};
+
 }  // namespace
+
+extern "C" size_t gnode_integrate_fixed_save_bytes(int64_t n_nodes, int32_t node_dim, int32_t hidden_dim,
+                                                   int32_t method, int32_t n_t) {
+  const Tableau* tb = tableau_for(method);
+  if (!tb || method == GNODE_DOPRI5 || n_t < 2) return 0;
+  Sage3Saver sv{};
+  sv.S = tb->S; sv.n = (size_t)n_nodes * node_dim; sv.nc = (size_t)n_nodes * 2 * hidden_dim;
+  return sv.step_floats() * sizeof(float) * (size_t)(n_t - 1);
+}
 
 extern "C" size_t gnode_integrate_fixed_workspace_bytes(int64_t n_nodes, int32_t node_dim, int32_t hidden_dim,
                                                         int32_t method, int32_t backward) {
@@ -323,8 +350,9 @@ extern "C" size_t gnode_integrate_fixed_workspace_bytes(int64_t n_nodes, int32_t
 }
 
 extern "C" int gnode_integrate_fixed(const gnode_graph* g, const gnode_sage3_params* p, int32_t method,
-                                     const float* y0, const float* t, int32_t n_t, float* sol, void* workspace,
-                                     size_t workspace_bytes, gnode_stream_t stream) {
+                                     const float* y0, const float* t, int32_t n_t, float* sol, void* save,
+                                     size_t save_bytes, void* workspace, size_t workspace_bytes,
+                                     gnode_stream_t stream) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   GN_TRY(check_graph(g, "gnode_integrate_fixed"));
   GN_TRY(check_params(p, "gnode_integrate_fixed"));
@@ -340,13 +368,19 @@ extern "C" int gnode_integrate_fixed(const gnode_graph* g, const gnode_sage3_par
   carve_fixed(a, c, *tb, false, w);
   GN_ARENA_OK(a, "gnode_integrate_fixed");
   GN_TRY(c.pack(*p, false, s));
-  return integrate_fixed(c, method, y0, t, n_t, sol, w.kbuf, w.xs[0], s);
+  if (save == nullptr) return integrate_fixed(c, method, y0, t, n_t, sol, w.kbuf, w.xs[0], s);
+  GN_ARG(save_bytes >= gnode_integrate_fixed_save_bytes(c.N, c.D, c.H, method, n_t),
+         "gnode_integrate_fixed: save buffer too small (%zu bytes)", save_bytes);
+  Sage3Saver sv{};
+  sv.c = &c; sv.S = tb->S; sv.n = (size_t)c.N * c.D; sv.nc = (size_t)c.N * 2 * c.H; sv.base = static_cast<float*>(save);
+  return integrate_fixed(c, method, y0, t, n_t, sol, w.kbuf, w.xs[0], s, &sv);
 }
 
 extern "C" int gnode_integrate_fixed_bwd(const gnode_graph* g, const gnode_sage3_params* p, int32_t method,
                                          const float* sol, const float* t, int32_t n_t, const float* grad_sol,
-                                         float* grad_y0, const gnode_sage3_grads* grads, void* workspace,
-                                         size_t workspace_bytes, gnode_stream_t stream) {
+                                         float* grad_y0, const gnode_sage3_grads* grads, const void* save,
+                                         size_t save_bytes, void* workspace, size_t workspace_bytes,
+                                         gnode_stream_t stream) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   GN_TRY(check_graph(g, "gnode_integrate_fixed_bwd"));
   GN_TRY(check_params(p, "gnode_integrate_fixed_bwd"));
@@ -364,6 +398,11 @@ extern "C" int gnode_integrate_fixed_bwd(const gnode_graph* g, const gnode_sage3
   GN_TRY(c.pack(*p, true, s));
   GN_TRY(c.zero_param_grads(s));
   const int64_t n = c.numel();
+  Sage3Saver sv{};
+  sv.c = &c; sv.S = S; sv.n = (size_t)n; sv.nc = (size_t)c.N * 2 * c.H;
+  sv.base = static_cast<float*>(const_cast<void*>(save));
+  if (save) GN_ARG(save_bytes >= gnode_integrate_fixed_save_bytes(c.N, c.D, c.H, method, n_t),
+                   "gnode_integrate_fixed_bwd: save buffer too small (%zu bytes)", save_bytes);
 
   // gcur = cotangent of y_{j+1} (explicit part from grad_sol plus what flowed back from later steps)
   GN_CUDA(cudaMemcpyAsync(w.gcur, grad_sol + (int64_t)(n_t - 1) * n, sizeof(float) * n, cudaMemcpyDeviceToDevice, s));
@@ -373,14 +412,20 @@ extern "C" int gnode_integrate_fixed_bwd(const gnode_graph* g, const gnode_sage3
     // ---- recompute the stages of step j, keeping x_s and the layer intermediates per stage ----
     const float* xst[kMaxStages];
     xst[0] = y;
-    for (int st = 0; st < S; ++st) {
-      if (st > 0) {
-        GN_TRY(stage_input(tb, st, y, w.kbuf, dt, w.xs[st], n, s));
-        xst[st] = w.xs[st];
+    if (save) {
+      // the forward pass kept every stage input and the layer intermediates of this step
+      float* const* xs_saved = sv.begin_step(j);
+      for (int st = 1; st < S; ++st) xst[st] = xs_saved[st];
+    } else {
+      for (int st = 0; st < S; ++st) {
+        if (st > 0) {
+          GN_TRY(stage_input(tb, st, y, w.kbuf, dt, w.xs[st], n, s));
+          xst[st] = w.xs[st];
+        }
+        // k of the last stage is never needed again (y_{j+1} is already known), but its layer
+        // intermediates are: evaluate it too, into kbuf[S-1].
+        GN_TRY(c.eval(xst[st], w.kbuf[st], nullptr, 1.f, st, s));
       }
-      // k of the last stage is never needed again (y_{j+1} is already known), but its layer
-      // intermediates are: evaluate it too, into kbuf[S-1].
-      GN_TRY(c.eval(xst[st], w.kbuf[st], nullptr, 1.f, st, s));
     }
     // ---- reverse sweep over the stages; kbuf[s] is reused to hold g_x[s] ----
     for (int st = S - 1; st >= 0; --st) {

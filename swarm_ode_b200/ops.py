@@ -18,6 +18,10 @@ from .graph import CSRGraph
 
 _f32 = _lib.require_cuda_f32
 
+# A differentiable fixed-grid solve keeps its per-stage intermediates for the backward pass when they take at
+# most this fraction of the currently free device memory; otherwise the backward recomputes them.
+SAVE_FRACTION = 0.5
+
 
 def _ws(nbytes: int, device) -> torch.Tensor:
     return _lib.WORKSPACE.get(nbytes, device)
@@ -147,11 +151,20 @@ class _IntegrateFixedFn(torch.autograd.Function):
         L = _lib.lib()
         ws = _ws(L.gnode_integrate_fixed_workspace_bytes(N, D, H, method, 0), y0.device)
         tarr = _float_array(t_host)
+        # When a backward will follow, keep the per-stage intermediates (autograd's "tape") so the backward does
+        # not recompute every stage -- unless they would not fit comfortably in free device memory.
+        save = None
+        if any(ctx.needs_input_grad) and T >= 2:
+            nbytes = int(L.gnode_integrate_fixed_save_bytes(N, D, H, method, T))
+            free, _total = torch.cuda.mem_get_info(y0.device)
+            if 0 < nbytes <= SAVE_FRACTION * free:
+                save = torch.empty(nbytes, dtype=torch.uint8, device=y0.device)
         with torch.cuda.device(y0.device):
             _lib.check(L.gnode_integrate_fixed(graph.ref(), C.byref(p), method, _lib.ptr(y0), tarr, T, _lib.ptr(sol),
+                                               _lib.ptr(save), save.numel() if save is not None else 0,
                                                _lib.ptr(ws), ws.numel(), _lib.stream_ptr(y0.device)),
                        "gnode_integrate_fixed")
-        ctx.graph, ctx.method, ctx.t_host = graph, method, t_host
+        ctx.graph, ctx.method, ctx.t_host, ctx.save = graph, method, t_host, save
         ctx.save_for_backward(sol, *w)
         return sol
 
@@ -169,10 +182,13 @@ class _IntegrateFixedFn(torch.autograd.Function):
         ws = _ws(L.gnode_integrate_fixed_workspace_bytes(N, D, H, ctx.method, 1), sol.device)
         tarr = _float_array(ctx.t_host)
         with torch.cuda.device(sol.device):
+            save = ctx.save
             _lib.check(L.gnode_integrate_fixed_bwd(ctx.graph.ref(), C.byref(p), ctx.method, _lib.ptr(sol), tarr, T,
-                                                   _lib.ptr(gsol), _lib.ptr(gy0), C.byref(grads), _lib.ptr(ws),
+                                                   _lib.ptr(gsol), _lib.ptr(gy0), C.byref(grads), _lib.ptr(save),
+                                                   save.numel() if save is not None else 0, _lib.ptr(ws),
                                                    ws.numel(), _lib.stream_ptr(sol.device)),
                        "gnode_integrate_fixed_bwd")
+        ctx.save = None
         return (gy0, None, None, None, *gw)
 
 

@@ -76,6 +76,33 @@ def test_train_step_gradients(cuda, solver, T):
         assert rel_l2(p.grad, rp[name].grad) <= FIXED_TOL, name
 
 
+@pytest.mark.parametrize("solver,T", [("rk4", 2), ("midpoint", 4), ("euler", 3)])
+def test_saved_intermediates_equal_recompute(cuda, solver, T):
+    """The backward that reads the forward's save area must give the gradients of the recomputing backward."""
+    from swarm_ode_b200 import ops
+    batch, nxt = S.synthetic.warehouse_batch(6, seed=8)
+    D = batch.x.shape[1]
+    model, _ = _models(D, solver, cuda, conv3_scale=0.05)
+    gb = batch.to(cuda)
+    t = torch.linspace(0, 1, T).to(cuda)
+    grads = {}
+    for mode, frac in (("save", 0.5), ("recompute", 0.0)):
+        old = ops.SAVE_FRACTION
+        ops.SAVE_FRACTION = frac
+        try:
+            model.zero_grad(set_to_none=True)
+            gb.x.grad = None
+            gb.x.requires_grad_()
+            out = model(gb, t)
+            loss = (out["trajectories"][-1] ** 2).mean() + out["node_features"][1].sum() * 1e-3
+            loss.backward()
+            grads[mode] = [p.grad.clone() for p in model.parameters()] + [gb.x.grad.clone()]
+        finally:
+            ops.SAVE_FRACTION = old
+    for a, b in zip(grads["save"], grads["recompute"]):
+        assert torch.equal(a, b)
+
+
 def test_backward_wrt_initial_state_and_all_time_points(cuda):
     batch, _ = S.synthetic.warehouse_batch(3, seed=5)
     D = batch.x.shape[1]

@@ -48,7 +48,7 @@ def test_argument_validation_returns_error_codes_without_touching_cuda():
     assert rc == -1 and b"n_nodes" in L.gnode_last_error()
     rc = L.gnode_decoder_fwd(None, 10, 16, 99, None, None, None, None)
     assert rc == -1 and b"n_out" in L.gnode_last_error()
-    rc = L.gnode_integrate_fixed(None, None, 2, None, None, 0, None, None, 0, None)
+    rc = L.gnode_integrate_fixed(None, None, 2, None, None, 0, None, None, 0, None, 0, None)
     assert rc == -1 and b"graph is null" in L.gnode_last_error()
     with pytest.raises(S.GnodeError, match="status -1"):
         _lib.check(rc, "gnode_integrate_fixed")
