@@ -316,12 +316,14 @@ void carve_fixed(Arena& a, Sage3Ctx& c, const Tableau& tb, bool backward, FixedW
 // the per-stage layer intermediates cat1 / cat2 ([N, 2H] each).  Lets the backward skip the stage recompute.
 struct Sage3Saver : StepSaver {
   Sage3Ctx* c; int S; size_t n, nc; float* base; float* xs[kMaxStages];
-  size_t step_floats() const { return (size_t)(S - 1) * n + (size_t)S * 2 * nc; }
+  // every sub-buffer starts on a 256-byte boundary (TMA / 128-bit paths need aligned bases)
+  static size_t pad(size_t floats) { return (floats + 63) & ~(size_t)63; }
+  size_t step_floats() const { return (size_t)(S - 1) * pad(n) + (size_t)S * 2 * pad(nc); }
   float* const* begin_step(int j) override {
     float* p = base + (size_t)j * step_floats();
     xs[0] = nullptr;
-    for (int st = 1; st < S; ++st) { xs[st] = p; p += n; }
-    for (int st = 0; st < S; ++st) { c->cat1[st] = p; p += nc; c->cat2[st] = p; p += nc; }
+    for (int st = 1; st < S; ++st) { xs[st] = p; p += pad(n); }
+    for (int st = 0; st < S; ++st) { c->cat1[st] = p; p += pad(nc); c->cat2[st] = p; p += pad(nc); }
     return xs;
   }
 };
