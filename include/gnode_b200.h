@@ -116,6 +116,16 @@ int gnode_gemm_nt(const float* A, int64_t lda, const float* B, int64_t ldb, floa
                   int64_t ldbase, float scale, void* workspace, size_t workspace_bytes,
                   gnode_stream_t stream);
 
+/* Dense "TN" contraction (the weight gradients of those Linear layers, autograd of
+ * scripts/train_gde.py:493):   C[p, q] += scale * sum_r A[r, p] * B[r, q]
+ * A: [rows, p] row stride lda, B: [rows, q] row stride ldb, C: [p, q] row stride ldc (accumulated into).
+ * Deterministic (fixed-order reduction of per-CTA partials).  Engine AUTO/TC: tcgen05 3xTF32 when both
+ * operands are dense (lda == p, ldb == q) and one of them is at most 128 wide; otherwise fp32 FFMA. */
+size_t gnode_gemm_tn_workspace_bytes(int32_t p, int32_t q, int64_t rows);
+int gnode_gemm_tn(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc,
+                  int64_t rows, int32_t p, int32_t q, float scale, void* workspace, size_t workspace_bytes,
+                  gnode_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * One SAGEConv layer:  out = mean_{j in N(i)} x_j @ wl^T + bl + x_i @ wr^T   (optional ReLU)
  * wl, wr: [c_out, c_in] (PyG / nn.Linear layout), bl: [c_out].

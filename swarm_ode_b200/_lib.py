@@ -72,6 +72,9 @@ _SIGNATURES = {
     "gnode_gemm_nt_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
     "gnode_gemm_nt": (C.c_int, [_P, C.c_int64, _P, C.c_int64, _P, C.c_int64, C.c_int64, C.c_int32, C.c_int32, _P,
                                 C.c_int32, _P, C.c_int64, C.c_float, _P, C.c_size_t, _P]),
+    "gnode_gemm_tn_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int64]),
+    "gnode_gemm_tn": (C.c_int, [_P, C.c_int64, _P, C.c_int64, _P, C.c_int64, C.c_int64, C.c_int32, C.c_int32,
+                                C.c_float, _P, C.c_size_t, _P]),
     "gnode_sage_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int32, C.c_int32]),
     "gnode_sage_fwd": (C.c_int, [C.POINTER(GnodeGraph), _P, C.c_int32, C.c_int32, _P, _P, _P, C.c_int32, _P, _P,
                                  C.c_size_t, _P]),

@@ -19,6 +19,27 @@ int gemm_nt(const GemmNT& g, cudaStream_t s) {
   }
   return gemm_nt_simt(g, s);
 }
+
+int gemm_tn_simt(const GemmTN& g, float* partials, cudaStream_t s);
+size_t gemm_tn_simt_workspace_floats(int P, int Q, int64_t Nrows);
+bool gemm_tn_tc_supported(const GemmTN& g);
+int gemm_tn_tc(const GemmTN& g, float* partials, cudaStream_t s);
+size_t gemm_tn_tc_workspace_floats(int P, int Q);
+
+size_t gemm_tn_workspace_floats(int P, int Q, int64_t Nrows) {
+  const size_t a = gemm_tn_simt_workspace_floats(P, Q, Nrows), b = gemm_tn_tc_workspace_floats(P, Q);
+  return a > b ? a : b;
+}
+
+// weight gradients: tcgen05 when the engine allows and the operands are dense row slabs, else FFMA
+int gemm_tn(const GemmTN& g, float* partials, cudaStream_t s) {
+  if (g.P == 0 || g.Q == 0 || g.Nrows == 0) return GNODE_OK;
+  const int engine = current_engine();
+  const bool tc = engine != GNODE_ENGINE_SIMT && gemm_tn_tc_supported(g);
+  GN_PROF(s, 2.0 * g.P * g.Q * g.Nrows, 4.0 * ((double)g.Nrows * (g.P + g.Q) + (double)g.P * g.Q),
+          "gemm_tn[%s] P=%d Q=%d", tc ? "tcgen05" : "ffma", g.P, g.Q);
+  return tc ? gemm_tn_tc(g, partials, s) : gemm_tn_simt(g, partials, s);
+}
 }  // namespace gnode
 
 // ------------------------------------------------------------------------------------------------
@@ -48,4 +69,21 @@ extern "C" int gnode_gemm_nt(const float* A, int64_t lda, const float* B, int64_
     q.Bsplit = planes;
   }
   return gemm_nt(q, s);
+}
+
+extern "C" size_t gnode_gemm_tn_workspace_bytes(int32_t p, int32_t q, int64_t rows) {
+  return align_up(gemm_tn_workspace_floats(p, q, rows) * sizeof(float));
+}
+
+extern "C" int gnode_gemm_tn(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc,
+                             int64_t rows, int32_t p, int32_t q, float scale, void* workspace,
+                             size_t workspace_bytes, gnode_stream_t stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  GN_ARG(A && B && C && rows >= 0 && p > 0 && q > 0, "gnode_gemm_tn: bad argument");
+  Arena a(workspace, workspace_bytes);
+  float* partials = a.take<float>(gemm_tn_workspace_floats(p, q, rows));
+  GN_ARENA_OK(a, "gnode_gemm_tn");
+  GemmTN g{};
+  g.A = A; g.lda = lda; g.P = p; g.B = B; g.ldb = ldb; g.Q = q; g.Nrows = rows; g.C = C; g.ldc = ldc; g.scale = scale;
+  return gemm_tn(g, partials, s);
 }

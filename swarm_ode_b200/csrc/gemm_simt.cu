@@ -217,14 +217,12 @@ int gemm_nt_simt(const GemmNT& g, cudaStream_t s) {
   return GNODE_OK;
 }
 
-size_t gemm_tn_workspace_floats(int P, int Q, int64_t Nrows) {
+size_t gemm_tn_simt_workspace_floats(int P, int Q, int64_t Nrows) {
   return (size_t)tn_splits(P, Q, Nrows) * (size_t)P * (size_t)Q;
 }
 
-int gemm_tn(const GemmTN& g, float* partials, cudaStream_t s) {
-  if (g.P == 0 || g.Q == 0) return GNODE_OK;
-  GN_PROF(s, 2.0 * g.P * g.Q * g.Nrows, 4.0 * ((double)g.Nrows * (g.P + g.Q) + (double)g.P * g.Q),
-          "gemm_tn[ffma] P=%d Q=%d", g.P, g.Q);
+int gemm_tn_simt(const GemmTN& g, float* partials, cudaStream_t s) {
+  if (g.P == 0 || g.Q == 0 || g.Nrows == 0) return GNODE_OK;
   const int S = tn_splits(g.P, g.Q, g.Nrows);
   int64_t kchunk = ceil_div64(ceil_div64(g.Nrows, S), BK) * BK;
   if (kchunk < BK) kchunk = BK;

@@ -397,3 +397,20 @@ def gemm_nt(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = Non
                                    {"none": 0, "relu": 1, "tanh": 2}[act], _lib.ptr(base_c), n, float(scale),
                                    _lib.ptr(ws), ws.numel(), _lib.stream_ptr(a.device)), "gnode_gemm_nt")
     return out
+
+
+def gemm_tn(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None, scale: float = 1.0) -> torch.Tensor:
+    """``out += scale * a.T @ b`` (reduction over rows; the weight-gradient contraction) on the selected engine."""
+    a, b = _f32(a.detach(), "a"), _f32(b.detach(), "b")
+    rows, p = a.shape
+    q = b.shape[1]
+    if b.shape[0] != rows:
+        raise GnodeError("gemm_tn: a and b must have the same number of rows")
+    if out is None:
+        out = torch.zeros((p, q), dtype=torch.float32, device=a.device)
+    L = _lib.lib()
+    ws = _ws(L.gnode_gemm_tn_workspace_bytes(p, q, rows), a.device)
+    with torch.cuda.device(a.device):
+        _lib.check(L.gnode_gemm_tn(_lib.ptr(a), p, _lib.ptr(b), q, _lib.ptr(out), out.stride(0), rows, p, q, float(scale),
+                                   _lib.ptr(ws), ws.numel(), _lib.stream_ptr(a.device)), "gnode_gemm_tn")
+    return out

@@ -67,3 +67,36 @@ def test_tc_engine_matches_ffma_on_warehouse_magnitudes(cuda):
             S.set_engine(prev)
     print(errs)
     assert errs["tc"] <= 1e-5 and errs["simt"] <= 1e-6
+
+
+# rows, p, q -- the three weight-gradient shapes of a GraphODEFunc layer stack (D=399 / 435, 2H=128, H=64) plus
+# ragged row counts (tail rows go through the FFMA kernel), narrow padding (p, q < 128) and a wide N operand.
+TN_SHAPES = [(4096, 399, 128), (4096, 128, 399), (4096, 64, 128), (12345, 435, 128), (1003, 128, 435),
+             (64, 128, 64), (9, 16, 24), (8, 399, 128), (50000, 512, 96), (777, 32, 64), (2048, 128, 128)]
+
+
+@pytest.mark.parametrize("engine", ["simt", "tc"])
+@pytest.mark.parametrize("rows,p,q", TN_SHAPES)
+def test_gemm_tn(cuda, engine, rows, p, q):
+    torch.manual_seed(rows + p + q)
+    a = torch.randn(rows, p) * 2
+    b = torch.randn(rows, q)
+    c0 = torch.randn(p, q)
+    want = c0.double() + 0.5 * (a.double().t() @ b.double())
+    prev = S.set_engine(engine)
+    try:
+        got = S.ops.gemm_tn(a.to(cuda), b.to(cuda), out=c0.to(cuda).clone(), scale=0.5)
+        _lib.tc_check(cuda)
+    finally:
+        S.set_engine(prev)
+    err = rel_l2(got, want)
+    print(f"{engine} tn rows={rows} {p}x{q}: rel-L2 {err:.3e}")
+    assert err <= (1e-5 if engine == "tc" else 2e-6)
+
+
+def test_gemm_tn_deterministic(cuda):
+    torch.manual_seed(0)
+    a, b = torch.randn(30000, 399, device=cuda), torch.randn(30000, 128, device=cuda)
+    outs = [S.ops.gemm_tn(a, b) for _ in range(3)]
+    _lib.tc_check(cuda)
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
