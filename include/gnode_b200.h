@@ -64,6 +64,12 @@ const char* gnode_last_error(void);
 int gnode_abi_version(void);
 /* process-wide selection of the GEMM engine (default AUTO); returns the previous value */
 int gnode_set_engine(int engine);
+/* process-wide selection of how the fixed-grid integrators evaluate the RK stages (default 1); returns the previous
+ * value.  1 = folded: conv1 / conv3 are linear, so the stage inputs never materialise D-wide -- two D-wide
+ * contractions per STEP (csrc/fold.cu).  0 = direct: every stage evaluates the full field (the straightforward
+ * anchor).  Both agree to fp32 rounding.  A forward call with a save area and its backward call must use the same
+ * setting. */
+int gnode_set_fold(int fold);
 /* number of kernels this library has launched since load (all threads) */
 int64_t gnode_launch_count(void);
 /* Synchronises `stream` and reports whether a tcgen05 kernel hit one of its bounded barrier waits

@@ -5,7 +5,7 @@ thin C-ABI CUDA library (``libgnode_b200.so``, declared in ``include/gnode_b200.
 multi-backend dispatch, no CPU fallback: importing the package is cheap and GPU-free, but every
 compute entry point raises unless the extension is built and the tensors live on a CUDA device.
 """
-from ._lib import GnodeError, set_engine, launch_count, LIB_PATH  # noqa: F401
+from ._lib import GnodeError, set_engine, set_fold, launch_count, LIB_PATH  # noqa: F401
 from .data import (Batch, Data, GraphConverter, TrajectoryBatch, collate_trajectory_batches,  # noqa: F401
                    extract_positions_from_graph, spatial_edges_cuda)
 from .graph import CSRGraph, csr_for  # noqa: F401
@@ -14,7 +14,7 @@ from .odeint import odeint  # noqa: F401
 from . import ops, synthetic  # noqa: F401
 
 __all__ = [
-    "GnodeError", "set_engine", "launch_count", "LIB_PATH",
+    "GnodeError", "set_engine", "set_fold", "launch_count", "LIB_PATH",
     "Batch", "Data", "GraphConverter", "TrajectoryBatch", "collate_trajectory_batches",
     "extract_positions_from_graph", "spatial_edges_cuda",
     "CSRGraph", "csr_for",

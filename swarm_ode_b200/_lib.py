@@ -63,6 +63,7 @@ _SIGNATURES = {
     "gnode_last_error": (C.c_char_p, []),
     "gnode_abi_version": (C.c_int, []),
     "gnode_set_engine": (C.c_int, [C.c_int]),
+    "gnode_set_fold": (C.c_int, [C.c_int]),
     "gnode_launch_count": (C.c_int64, []),
     "gnode_tc_status": (C.c_int, [_P]),
     "gnode_prof_enable": (C.c_int, [C.c_int]),
@@ -192,6 +193,11 @@ def set_engine(name: str) -> str:
     code = {"auto": ENGINE_AUTO, "simt": ENGINE_SIMT, "tc": ENGINE_TC}[name]
     prev = lib().gnode_set_engine(code)
     return {ENGINE_AUTO: "auto", ENGINE_SIMT: "simt", ENGINE_TC: "tc"}.get(prev, "auto")
+
+
+def set_fold(on: bool) -> bool:
+    """Folded (True, default) or direct (False) evaluation of the RK stages; returns the previous setting."""
+    return bool(lib().gnode_set_fold(1 if on else 0))
 
 
 def launch_count() -> int:

@@ -90,11 +90,13 @@ constexpr int kNumSMs = 148;  // B200
 
 // ---- engine selection (gemm.cu) ----
 int current_engine();
+int current_fold();
 
 // ---- dense contractions (gemm_simt.cu / gemm_tc.cu) ----
 // C[m, n] = epi( sum_k A[m, k] * B[n, k] )          (both operands K-contiguous, "NT")
-//   epi(v) = base[m, n] + scale * act(v + bias[n])   with act (field `relu`) = 0 identity, 1 relu, 2 tanh;
-//   bias / base may be null.  lda/ldb/ldc/ldbase are row strides in elements.
+//   epi(v) = base_scale * base[m, n] + base2[m, n] + scale * act(v + bias_scale * bias[n])
+//   with act (field `relu`) = 0 identity, 1 relu, 2 tanh; bias / base / base2 may be null.
+//   lda/ldb/ldc/ldbase/ldbase2 are row strides in elements.
 struct GemmNT {
   const float* A; int64_t lda;
   const float* B; int64_t ldb;
@@ -104,6 +106,9 @@ struct GemmNT {
   int relu = 0;
   const float* base = nullptr; int64_t ldbase = 0;
   float scale = 1.0f;
+  float bias_scale = 1.0f;
+  float base_scale = 1.0f;
+  const float* base2 = nullptr; int64_t ldbase2 = 0;
   const float* Bsplit = nullptr;   // optional: B pre-split into tf32 hi/lo planes (presplit_weights) -> tcgen05 engine
 };
 int gemm_nt(const GemmNT& g, cudaStream_t s);

@@ -62,6 +62,33 @@ struct Sage3Ctx : Field {
   int unpack_grads(const gnode_sage3_grads& gr, cudaStream_t s);
 };
 
+// ---- folded fixed-grid integration (fold.cu): D-wide contractions once per step instead of once per stage ----
+struct FoldWs {
+  int S = 0;
+  float *M13 = nullptr, *M13T = nullptr, *c13 = nullptr;   // w1cat @ w3cat [2H, 2H], its transpose, w1cat @ b3 [2H]
+  float *sM13 = nullptr, *sM13T = nullptr;                 // tf32 hi/lo planes of the two
+  float *z0 = nullptr, *Cbuf = nullptr;                    // [N, 2H]
+  float* Vws[kMaxStages] = {};                             // workspace V_s (when nothing is saved)
+  float *cat1[kMaxStages] = {}, *cat2[kMaxStages] = {}, *V[kMaxStages] = {};   // stage slots of the current step
+  // backward
+  float *G3 = nullptr, *U = nullptr, *GZ = nullptr;        // [N, 2H]
+  float* gzs[kMaxStages] = {};                             // dL/dZ_s  [N, 2H]
+  float *gcur = nullptr, *gnext = nullptr;                 // [N, D] cotangent ping-pong
+  float *R = nullptr, *g1 = nullptr, *cs = nullptr, *partials = nullptr;
+
+  void carve(Arena& a, const Sage3Ctx& c, int S, bool backward);
+  static size_t save_floats_per_step(const Sage3Ctx& c, int S);
+  void bind_slots(Sage3Ctx& c, float* save, int j);
+  int prepare(Sage3Ctx& c, cudaStream_t s);
+  int forward_stages(Sage3Ctx& c, const Tableau& tb, const float* y, float dt, cudaStream_t s);
+  int combine_solution(Sage3Ctx& c, const Tableau& tb, float dt, cudaStream_t s);
+};
+int integrate_fixed_folded(Sage3Ctx& c, FoldWs& f, const Tableau& tb, const float* y0, const float* t, int n_t,
+                           float* sol, float* save, cudaStream_t s);
+int integrate_fixed_folded_bwd(Sage3Ctx& c, FoldWs& f, const Tableau& tb, const float* sol, const float* t, int n_t,
+                               const float* grad_sol, float* grad_y0, const float* save, cudaStream_t s);
+int current_fold();
+
 int check_graph(const gnode_graph* g, const char* who);
 int check_params(const gnode_sage3_params* p, const char* who);
 

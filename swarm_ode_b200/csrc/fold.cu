@@ -1,0 +1,345 @@
+// Folded fixed-grid Runge-Kutta integration of the GraphODEFunc field (scripts/train_gde.py:33-45 integrated by
+// torchdiffeq's fixed-grid solvers, :78-85) and its backward pass (loss.backward(), :493).
+//
+// conv1 and conv3 are linear maps around the nonlinear 2H-wide core of the field, and every stage input of an
+// explicit RK step is  x_s = y + dt * sum_{j<s} beta_sj k_j  with  k_j = cat2_j @ w3cat^T + b3.  Hence
+//
+//   Z_s  = x_s @ w1cat^T = Z_0 + V_s @ M13^T + (dt * sum_j beta_sj) * c13,      V_s = dt * sum_{j<s} beta_sj cat2_j
+//   y_1  = y + C @ w3cat^T + (dt * sum_s c_s) * b3,                             C   = dt * sum_s c_s cat2_s
+//   M13  = w1cat @ w3cat  [2H, 2H],   c13 = w1cat @ b3  [2H]        (recomputed from the weights on every call)
+//
+// so the D-wide state is touched by TWO dense contractions per step (Z_0 on the way in, y_1 on the way out) instead
+// of two per STAGE, and no D-wide stage buffer (x_s, k_s) ever exists.  The backward pass folds the same way:
+//
+//   gcat2_s = dt c_s (G @ w3cat) + U_s @ M13,      U_s = dt * sum_{i>s} beta_is gz_i          (gz_i = dL/dZ_i)
+//   dW3cat += G^T C + w1cat^T R,   dW1cat += GZ^T y + R @ w3cat^T + g1 (x) b3,   db3 += (dt sum c_s) colsum(G) + g1 @ w1cat
+//   grad_y  = G + GZ @ w1cat,      GZ = sum_s gz_s,  R = sum_s gz_s^T V_s,  g1 = sum_s (dt sum_j beta_sj) colsum(gz_s)
+//
+// i.e. per step two D-wide data contractions (G @ w3cat, GZ @ w1cat) and two D-wide weight-gradient contractions.
+// This is a re-association of the reference arithmetic (fp32 rounding order only; parity gate: rel-L2 <= 1e-4); the
+// unfolded path (gnode_set_fold(0)) stays available as the straightforward anchor.
+#include <cstring>
+
+#include "field.cuh"
+
+namespace gnode {
+
+namespace {
+
+// M13[z, c] = sum_d w1cat[z, d] w3cat[d, c];  M13T = transpose;  c13[z] = sum_d w1cat[z, d] b3[d]   (fp64 accumulate)
+__global__ void k_fold_weights(const float* __restrict__ w1cat, const float* __restrict__ w3cat, const float* __restrict__ b3,
+                               int H2, int D, float* __restrict__ M13, float* __restrict__ M13T, float* __restrict__ c13) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;   // cat2 feature (or H2 -> the bias column)
+  const int z = blockIdx.y;
+  if (c > H2) return;
+  double acc = 0.0;
+  const float* wz = w1cat + (size_t)z * D;
+  if (c < H2) {
+    for (int d = 0; d < D; ++d) acc += (double)wz[d] * (double)w3cat[(size_t)d * H2 + c];
+    M13[(size_t)z * H2 + c] = (float)acc;
+    M13T[(size_t)c * H2 + z] = (float)acc;
+  } else {
+    for (int d = 0; d < D; ++d) acc += (double)wz[d] * (double)b3[d];
+    c13[z] = (float)acc;
+  }
+}
+
+// small dense products applied once at the end of the backward pass (fp32, tiny):
+//   dW3cat[d, c] += sum_z w1cat[z, d] R[z, c]          dW1cat[z, d] += sum_c R[z, c] w3cat[d, c] + g1[z] b3[d]
+//   db3[d]       += sum_z g1[z] w1cat[z, d]
+__global__ void k_fold_param_grads(const float* __restrict__ w1cat, const float* __restrict__ w3cat, const float* __restrict__ b3,
+                                   const float* __restrict__ R, const float* __restrict__ g1, int H2, int D,
+                                   float* __restrict__ dW3cat, float* __restrict__ dW1cat, float* __restrict__ db3) {
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y;   // 0..H2-1: column c of dW3cat / row z of dW1cat;  H2: db3
+  if (d >= D) return;
+  if (j < H2) {
+    float a3 = 0.f, a1 = 0.f;
+    for (int q = 0; q < H2; ++q) {
+      a3 = fmaf(w1cat[(size_t)q * D + d], R[(size_t)q * H2 + j], a3);       // z = q, c = j
+      a1 = fmaf(R[(size_t)j * H2 + q], w3cat[(size_t)d * H2 + q], a1);       // z = j, c = q
+    }
+    dW3cat[(size_t)d * H2 + j] += a3;
+    dW1cat[(size_t)j * D + d] += a1 + g1[j] * b3[d];
+  } else {
+    float a = 0.f;
+    for (int q = 0; q < H2; ++q) a = fmaf(g1[q], w1cat[(size_t)q * D + d], a);
+    db3[d] += a;
+  }
+}
+
+size_t padf(size_t floats) { return (floats + 63) & ~(size_t)63; }
+
+}  // namespace
+
+void FoldWs::carve(Arena& a, const Sage3Ctx& c, int S_, bool backward) {
+  S = S_;
+  const size_t nh = (size_t)c.N * 2 * c.H, nd = (size_t)c.N * c.D;
+  const int H2 = 2 * c.H;
+  M13 = a.take<float>((size_t)H2 * H2);
+  M13T = a.take<float>((size_t)H2 * H2);
+  c13 = a.take<float>(H2);
+  sM13 = a.take<float>(presplit_floats(H2, H2));
+  sM13T = a.take<float>(presplit_floats(H2, H2));
+  z0 = a.take<float>(nh);
+  Cbuf = a.take<float>(nh);
+  for (int i = 1; i < S; ++i) Vws[i] = a.take<float>(nh);
+  if (backward) {
+    G3 = a.take<float>(nh);
+    U = a.take<float>(nh);
+    GZ = a.take<float>(nh);
+    for (int i = 0; i < S; ++i) gzs[i] = a.take<float>(nh);
+    gcur = a.take<float>(nd);
+    gnext = a.take<float>(nd);
+    R = a.take<float>((size_t)H2 * H2);
+    g1 = a.take<float>(H2);
+    cs = a.take<float>(H2);
+    size_t pf = gemm_tn_workspace_floats(c.D, H2, c.N);
+    const size_t cand[3] = {gemm_tn_workspace_floats(H2, c.D, c.N), gemm_tn_workspace_floats(H2, H2, c.N),
+                            gemm_tn_workspace_floats(c.H, H2, c.N)};
+    for (size_t v : cand) if (v > pf) pf = v;
+    partials = a.take<float>(pf);
+  }
+}
+
+size_t FoldWs::save_floats_per_step(const Sage3Ctx& c, int S_) {
+  return (size_t)(3 * S_ - 1) * padf((size_t)c.N * 2 * c.H);
+}
+
+// point the stage slots of step j at the save area (or at the workspace when save == null)
+void FoldWs::bind_slots(Sage3Ctx& c, float* save, int j) {
+  const size_t nh = padf((size_t)c.N * 2 * c.H);
+  if (save) {
+    float* p = save + (size_t)j * save_floats_per_step(c, S);
+    for (int st = 0; st < S; ++st) { cat1[st] = p; p += nh; cat2[st] = p; p += nh; }
+    V[0] = nullptr;
+    for (int st = 1; st < S; ++st) { V[st] = p; p += nh; }
+  } else {
+    for (int st = 0; st < S; ++st) { cat1[st] = c.cat1[st]; cat2[st] = c.cat2[st]; V[st] = Vws[st]; }
+  }
+}
+
+int FoldWs::prepare(Sage3Ctx& c, cudaStream_t s) {
+  const int H2 = 2 * c.H;
+  {
+    GN_PROF(s, 2.0 * H2 * (H2 + 1) * c.D, 0.0, "fold_weights");
+    dim3 grid((unsigned)ceil_div64(H2 + 1, 128), (unsigned)H2);
+    k_fold_weights<<<grid, 128, 0, s>>>(c.w1cat, c.w3cat, c.b3, H2, c.D, M13, M13T, c13);
+    GN_LAUNCHED();
+  }
+  if (c.use_tc) {
+    GN_TRY(presplit_weights(M13, H2, H2, H2, sM13, s));
+    GN_TRY(presplit_weights(M13T, H2, H2, H2, sM13T, s));
+  }
+  return GNODE_OK;
+}
+
+// Stages of one step: fills cat1[st], cat2[st] (and V[st] for st >= 1) from y.  Z_0 is left in z0.
+int FoldWs::forward_stages(Sage3Ctx& c, const Tableau& tb, const float* y, float dt, cudaStream_t s) {
+  const int H = c.H, H2 = 2 * c.H;
+  const int64_t N = c.N;
+  const int64_t nh = N * H2;
+  {  // Z_0 = y @ w1cat^T
+    GemmNT q{};
+    q.A = y; q.lda = c.D; q.B = c.w1cat; q.ldb = c.D; q.C = z0; q.ldc = H2; q.M = N; q.N = H2; q.K = c.D;
+    q.Bsplit = c.use_tc ? c.s1 : nullptr;
+    GN_TRY(gemm_nt(q, s));
+  }
+  for (int st = 0; st < S; ++st) {
+    const float* z = z0;
+    if (st > 0) {
+      // V_st = dt * sum_{j<st} beta[st][j] cat2_j ;  Z_st = Z_0 + V_st @ M13^T + (dt sum_j beta) c13
+      LinComb lc{};
+      lc.out = V[st]; lc.base = nullptr; lc.n = nh; lc.n_terms = 0;
+      double bsum = 0.0;
+      for (int j = 0; j < st; ++j) {
+        lc.in[lc.n_terms] = cat2[j]; lc.coef[lc.n_terms] = (float)tb.beta[st][j] * dt; ++lc.n_terms;
+        bsum += tb.beta[st][j];
+      }
+      GN_TRY(lincomb(lc, s));
+      GemmNT q{};
+      q.A = V[st]; q.lda = H2; q.B = M13; q.ldb = H2; q.C = c.z; q.ldc = H2; q.M = N; q.N = H2; q.K = H2;
+      q.bias = c13; q.bias_scale = (float)bsum * dt; q.base = z0; q.ldbase = H2;
+      q.Bsplit = c.use_tc ? sM13 : nullptr;
+      GN_TRY(gemm_nt(q, s));
+      z = c.z;
+    }
+    float* c1 = cat1[st];
+    float* c2 = cat2[st];
+    GN_TRY(agg_mean_fwd(c.g, z, H2, c1 + H, H2, H, z + H, H2, c.b1, 1, s));          // h1
+    GN_TRY(agg_mean_fwd(c.g, c1 + H, H2, c1, H2, H, nullptr, 0, nullptr, 0, s));     // A(h1)
+    {
+      GemmNT q{};
+      q.A = c1; q.lda = H2; q.B = c.w2cat; q.ldb = H2; q.C = c2 + H; q.ldc = H2; q.M = N; q.N = H; q.K = H2;
+      q.bias = c.b2; q.relu = 1;
+      q.Bsplit = c.use_tc ? c.s2 : nullptr;
+      GN_TRY(gemm_nt(q, s));                                                          // h2
+    }
+    GN_TRY(agg_mean_fwd(c.g, c2 + H, H2, c2, H2, H, nullptr, 0, nullptr, 0, s));     // A(h2)
+  }
+  return GNODE_OK;
+}
+
+// C = dt * sum_s c_sol[s] cat2_s   -> Cbuf
+int FoldWs::combine_solution(Sage3Ctx& c, const Tableau& tb, float dt, cudaStream_t s) {
+  LinComb lc{};
+  lc.out = Cbuf; lc.base = nullptr; lc.n = c.N * 2 * c.H; lc.n_terms = 0;
+  for (int st = 0; st < S; ++st) { lc.in[lc.n_terms] = cat2[st]; lc.coef[lc.n_terms] = (float)tb.c_sol[st] * dt; ++lc.n_terms; }
+  return lincomb(lc, s);
+}
+
+int integrate_fixed_folded(Sage3Ctx& c, FoldWs& f, const Tableau& tb, const float* y0, const float* t, int n_t,
+                           float* sol, float* save, cudaStream_t s) {
+  const int H2 = 2 * c.H;
+  const int64_t n = c.numel();
+  if (sol != y0) GN_CUDA(cudaMemcpyAsync(sol, y0, sizeof(float) * n, cudaMemcpyDeviceToDevice, s));
+  GN_TRY(f.prepare(c, s));
+  double csum = 0.0;
+  for (int st = 0; st < tb.S; ++st) csum += tb.c_sol[st];
+  for (int j = 0; j + 1 < n_t; ++j) {
+    const float dt = t[j + 1] - t[j];
+    const float* y = sol + (int64_t)j * n;
+    float* y1 = sol + (int64_t)(j + 1) * n;
+    f.bind_slots(c, save, j);
+    GN_TRY(f.forward_stages(c, tb, y, dt, s));
+    GN_TRY(f.combine_solution(c, tb, dt, s));
+    GemmNT q{};   // y_1 = y + C @ w3cat^T + (dt sum c) b3
+    q.A = f.Cbuf; q.lda = H2; q.B = c.w3cat; q.ldb = H2; q.C = y1; q.ldc = c.D; q.M = c.N; q.N = c.D; q.K = H2;
+    q.bias = c.b3; q.bias_scale = (float)csum * dt; q.base = y; q.ldbase = c.D;
+    q.Bsplit = c.use_tc ? c.s3 : nullptr;
+    GN_TRY(gemm_nt(q, s));
+  }
+  return GNODE_OK;
+}
+
+int integrate_fixed_folded_bwd(Sage3Ctx& c, FoldWs& f, const Tableau& tb, const float* sol, const float* t, int n_t,
+                               const float* grad_sol, float* grad_y0, const float* save, cudaStream_t s) {
+  const int S = tb.S, H = c.H, H2 = 2 * c.H;
+  const int64_t N = c.N, n = c.numel(), nh = N * H2;
+  GN_TRY(f.prepare(c, s));
+  GN_CUDA(cudaMemsetAsync(f.R, 0, sizeof(float) * H2 * H2, s));
+  GN_CUDA(cudaMemsetAsync(f.g1, 0, sizeof(float) * H2, s));
+  double csum = 0.0;
+  for (int st = 0; st < S; ++st) csum += tb.c_sol[st];
+
+  // G = cotangent of y_{j+1}: explicit part from grad_sol plus what flowed back from later steps
+  const float* G = grad_sol + (int64_t)(n_t - 1) * n;
+  float* gout = f.gcur;
+  for (int j = n_t - 2; j >= 0; --j) {
+    const float dt = t[j + 1] - t[j];
+    const float* y = sol + (int64_t)j * n;
+    f.bind_slots(c, const_cast<float*>(save), j);
+    if (!save) GN_TRY(f.forward_stages(c, tb, y, dt, s));          // recompute this step's stages
+    {  // G3 = G @ w3cat     [N, 2H]
+      GemmNT q{};
+      q.A = G; q.lda = c.D; q.B = c.w3catT; q.ldb = c.D; q.C = f.G3; q.ldc = H2; q.M = N; q.N = H2; q.K = c.D;
+      q.Bsplit = c.use_tc ? c.s3T : nullptr;
+      GN_TRY(gemm_nt(q, s));
+    }
+    for (int st = S - 1; st >= 0; --st) {
+      float* gz = f.gzs[st];
+      // U_st = dt * sum_{i>st} beta[i][st] gz_i
+      LinComb lu{};
+      lu.out = f.U; lu.base = nullptr; lu.n = nh; lu.n_terms = 0;
+      for (int i = st + 1; i < S; ++i)
+        if (tb.beta[i][st] != 0.0) { lu.in[lu.n_terms] = f.gzs[i]; lu.coef[lu.n_terms] = (float)tb.beta[i][st] * dt; ++lu.n_terms; }
+      const bool has_u = lu.n_terms > 0;
+      const float cs_dt = (float)tb.c_sol[st] * dt;
+      if (!has_u && cs_dt == 0.f) {   // the stage does not influence the output
+        GN_CUDA(cudaMemsetAsync(gz, 0, sizeof(float) * nh, s));
+        continue;
+      }
+      if (has_u) {
+        GN_TRY(lincomb(lu, s));
+        GemmNT q{};   // gcat = dt c_st G3 + U @ M13
+        q.A = f.U; q.lda = H2; q.B = f.M13T; q.ldb = H2; q.C = c.gcat; q.ldc = H2; q.M = N; q.N = H2; q.K = H2;
+        q.base = f.G3; q.ldbase = H2; q.base_scale = cs_dt;
+        q.Bsplit = c.use_tc ? f.sM13T : nullptr;
+        GN_TRY(gemm_nt(q, s));
+      } else {
+        LinComb lg{};
+        lg.out = c.gcat; lg.base = nullptr; lg.n = nh; lg.n_terms = 1; lg.in[0] = f.G3; lg.coef[0] = cs_dt;
+        GN_TRY(lincomb(lg, s));
+      }
+      const float* c1 = f.cat1[st];
+      const float* c2 = f.cat2[st];
+      // ---- conv3 -> conv2 ----   g_v2 = (A^T(gcat_l) + gcat_r) * [h2 > 0]
+      GN_TRY(agg_mean_bwd(c.g, c.gcat, H2, c.gv2, H, H, c.gcat + H, H2, c2 + H, H2, s));
+      {  // gcat = g_v2 @ w2cat   [N, 2H]
+        GemmNT q{};
+        q.A = c.gv2; q.lda = H; q.B = c.w2catT; q.ldb = H; q.C = c.gcat; q.ldc = H2; q.M = N; q.N = H2; q.K = H;
+        q.Bsplit = c.use_tc ? c.s2T : nullptr;
+        GN_TRY(gemm_nt(q, s));
+      }
+      {  // dW2cat += g_v2^T @ cat1
+        GemmTN q{};
+        q.A = c.gv2; q.lda = H; q.P = H; q.B = c1; q.ldb = H2; q.Q = H2; q.Nrows = N; q.C = c.dW2cat; q.ldc = H2;
+        GN_TRY(gemm_tn(q, f.partials, s));
+      }
+      GN_TRY(colsum_accum(c.gv2, H, N, H, c.db2, 1.f, c.colpart, s));
+      // ---- conv2 -> conv1 ----   g_u1 = (A^T(gcat_l) + gcat_r) * [h1 > 0] -> gz[:, H:] ; A^T(g_u1) -> gz[:, :H]
+      GN_TRY(agg_mean_bwd(c.g, c.gcat, H2, gz + H, H2, H, c.gcat + H, H2, c1 + H, H2, s));
+      GN_TRY(agg_mean_bwd(c.g, gz + H, H2, gz, H2, H, nullptr, 0, nullptr, 0, s));
+      // column sums of gz_st: db1 += cs[H:],  g1 += (dt sum_j beta[st][j]) cs
+      GN_CUDA(cudaMemsetAsync(f.cs, 0, sizeof(float) * H2, s));
+      GN_TRY(colsum_accum(gz, H2, N, H2, f.cs, 1.f, c.colpart, s));
+      {
+        LinComb l1{};
+        l1.out = c.db1; l1.base = c.db1; l1.n = H; l1.n_terms = 1; l1.in[0] = f.cs + H; l1.coef[0] = 1.f;
+        GN_TRY(lincomb(l1, s));
+      }
+      if (st > 0) {
+        double bsum = 0.0;
+        for (int jj = 0; jj < st; ++jj) bsum += tb.beta[st][jj];
+        const float w = (float)bsum * dt;
+        if (w != 0.f) {
+          LinComb l2{};
+          l2.out = f.g1; l2.base = f.g1; l2.n = H2; l2.n_terms = 1; l2.in[0] = f.cs; l2.coef[0] = w;
+          GN_TRY(lincomb(l2, s));
+        }
+        // R += gz_st^T @ V_st     [2H, 2H]
+        GemmTN q{};
+        q.A = gz; q.lda = H2; q.P = H2; q.B = f.V[st]; q.ldb = H2; q.Q = H2; q.Nrows = N; q.C = f.R; q.ldc = H2;
+        GN_TRY(gemm_tn(q, f.partials, s));
+      }
+    }
+    // ---- D-wide parameter gradients of this step ----
+    {
+      LinComb lz{};
+      lz.out = f.GZ; lz.base = nullptr; lz.n = nh; lz.n_terms = 0;
+      for (int st = 0; st < S; ++st) { lz.in[lz.n_terms] = f.gzs[st]; lz.coef[lz.n_terms] = 1.f; ++lz.n_terms; }
+      GN_TRY(lincomb(lz, s));
+    }
+    GN_TRY(f.combine_solution(c, tb, dt, s));
+    {  // dW3cat += G^T @ C     [D, 2H]
+      GemmTN q{};
+      q.A = G; q.lda = c.D; q.P = c.D; q.B = f.Cbuf; q.ldb = H2; q.Q = H2; q.Nrows = N; q.C = c.dW3cat; q.ldc = H2;
+      GN_TRY(gemm_tn(q, f.partials, s));
+    }
+    GN_TRY(colsum_accum(G, c.D, N, c.D, c.db3, (float)csum * dt, c.colpart, s));
+    {  // dW1cat += GZ^T @ y    [2H, D]
+      GemmTN q{};
+      q.A = f.GZ; q.lda = H2; q.P = H2; q.B = y; q.ldb = c.D; q.Q = c.D; q.Nrows = N; q.C = c.dW1cat; q.ldc = c.D;
+      GN_TRY(gemm_tn(q, f.partials, s));
+    }
+    {  // cotangent of y_j:  G + GZ @ w1cat + grad_sol[j]
+      GemmNT q{};
+      q.A = f.GZ; q.lda = H2; q.B = c.w1catT; q.ldb = H2; q.C = gout; q.ldc = c.D; q.M = N; q.N = c.D; q.K = H2;
+      q.base = G; q.ldbase = c.D; q.base2 = grad_sol + (int64_t)j * n; q.ldbase2 = c.D;
+      q.Bsplit = c.use_tc ? c.s1T : nullptr;
+      GN_TRY(gemm_nt(q, s));
+    }
+    G = gout;
+    gout = (gout == f.gcur) ? f.gnext : f.gcur;
+  }
+  GN_CUDA(cudaMemcpyAsync(grad_y0, G, sizeof(float) * n, cudaMemcpyDeviceToDevice, s));
+  {
+    GN_PROF(s, 4.0 * H2 * H2 * c.D, 0.0, "fold_param_grads");
+    dim3 grid((unsigned)ceil_div64(c.D, 128), (unsigned)(H2 + 1));
+    k_fold_param_grads<<<grid, 128, 0, s>>>(c.w1cat, c.w3cat, c.b3, f.R, f.g1, H2, c.D, c.dW3cat, c.dW1cat, c.db3);
+    GN_LAUNCHED();
+  }
+  return GNODE_OK;
+}
+
+}  // namespace gnode

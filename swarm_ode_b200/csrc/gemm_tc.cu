@@ -65,18 +65,26 @@ struct Args {
   const float* bias; int act;
   const float* base; int64_t ldbase;
   float scale;
+  float bias_scale, base_scale;
+  const float* base2; int64_t ldbase2;
   int* status;
 };
 
-template <int ACT, bool HAS_BASE>
+// HAS_BASE: 0 none, 1 base, 2 base + base2
+template <int ACT, int HAS_BASE>
 __device__ __forceinline__ void store_rows(const float* __restrict__ stg, int lane, float bv, float scale, float* crow,
-                                           int64_t ldc, const float* brow, int64_t ldbase, int rmax, bool cin) {
+                                           int64_t ldc, const float* brow, int64_t ldbase, float base_scale,
+                                           const float* b2row, int64_t ldbase2, int rmax, bool cin) {
 #pragma unroll
   for (int r0 = 0; r0 < 32; r0 += 8) {
     float bs[8];
-    if (HAS_BASE) {
+    if (HAS_BASE >= 1) {
 #pragma unroll
-      for (int u = 0; u < 8; ++u) bs[u] = (cin && r0 + u < rmax) ? __ldg(brow + (int64_t)(r0 + u) * ldbase) : 0.f;
+      for (int u = 0; u < 8; ++u) bs[u] = (cin && r0 + u < rmax) ? base_scale * __ldg(brow + (int64_t)(r0 + u) * ldbase) : 0.f;
+    }
+    if (HAS_BASE == 2) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) bs[u] += (cin && r0 + u < rmax) ? __ldg(b2row + (int64_t)(r0 + u) * ldbase2) : 0.f;
     }
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
@@ -84,7 +92,7 @@ __device__ __forceinline__ void store_rows(const float* __restrict__ stg, int la
       if (ACT == 1) x = fmaxf(x, 0.f);
       if (ACT == 2) x = tanhf(x);
       x *= scale;
-      if (HAS_BASE) x += bs[u];
+      if (HAS_BASE >= 1) x += bs[u];
       if (cin && r0 + u < rmax) crow[(int64_t)(r0 + u) * ldc] = x;
     }
   }
@@ -288,10 +296,11 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
     float* stg = reinterpret_cast<float*>(smem + staging_off) + qd * (32 * 33);
     float* const Cp = a.C;
     const float* const basep = a.base;
+    const float* const base2p = a.base2;
     const float* const biasp = a.bias;
-    const int64_t ldc = a.ldc, ldbase = a.ldbase, M = a.M;
+    const int64_t ldc = a.ldc, ldbase = a.ldbase, ldbase2 = a.ldbase2, M = a.M;
     const int N = a.N, act = a.act;
-    const float scale = a.scale;
+    const float scale = a.scale, bias_scale = a.bias_scale, base_scale = a.base_scale;
     uint32_t tc = 0;
     bool ok = true;
     for (int64_t t = tile0; t < total_tiles && ok; t += tstep, ++tc) {
@@ -319,18 +328,19 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
         __syncwarp();
         const int col = n0 + c0 + lane;
         const bool cin = (c0 + lane < bn) && (col < N);
-        const float bv = (cin && biasp) ? __ldg(biasp + col) : 0.f;
+        const float bv = (cin && biasp) ? bias_scale * __ldg(biasp + col) : 0.f;
         float* crow = Cp + m0 * ldc + col;
         const float* brow = basep ? basep + m0 * ldbase + col : nullptr;
-        if (basep) {
-          if (act == 0) store_rows<0, true>(stg, lane, bv, scale, crow, ldc, brow, ldbase, rmax, cin);
-          else if (act == 1) store_rows<1, true>(stg, lane, bv, scale, crow, ldc, brow, ldbase, rmax, cin);
-          else store_rows<2, true>(stg, lane, bv, scale, crow, ldc, brow, ldbase, rmax, cin);
+        const float* b2row = base2p ? base2p + m0 * ldbase2 + col : nullptr;
+#define GN_STORE(ACT_, HB_) store_rows<ACT_, HB_>(stg, lane, bv, scale, crow, ldc, brow, ldbase, base_scale, b2row, ldbase2, rmax, cin)
+        if (basep && base2p) {
+          if (act == 0) GN_STORE(0, 2); else if (act == 1) GN_STORE(1, 2); else GN_STORE(2, 2);
+        } else if (basep) {
+          if (act == 0) GN_STORE(0, 1); else if (act == 1) GN_STORE(1, 1); else GN_STORE(2, 1);
         } else {
-          if (act == 0) store_rows<0, false>(stg, lane, bv, scale, crow, ldc, brow, ldbase, rmax, cin);
-          else if (act == 1) store_rows<1, false>(stg, lane, bv, scale, crow, ldc, brow, ldbase, rmax, cin);
-          else store_rows<2, false>(stg, lane, bv, scale, crow, ldc, brow, ldbase, rmax, cin);
+          if (act == 0) GN_STORE(0, 0); else if (act == 1) GN_STORE(1, 0); else GN_STORE(2, 0);
         }
+#undef GN_STORE
         __syncwarp();
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -439,6 +449,8 @@ int gemm_nt_tc(const GemmNT& g, cudaStream_t s) {
   a.bn = tc::pick_bn(g.N); a.n_tiles = tc::pick_ntiles(g.N);
   a.m_tiles = ceil_div64(M_tc, tc::BM);
   a.bias = g.bias; a.act = g.relu; a.base = g.base; a.ldbase = g.ldbase; a.scale = g.scale;
+  a.bias_scale = g.bias_scale; a.base_scale = g.base_scale;
+  a.base2 = g.base ? g.base2 : nullptr; a.ldbase2 = g.ldbase2;
   a.status = status_dev;
   // shared-memory plan: A-operand ring (3) + B ring (4, or 3 for wide tiles) + staging, the rest is the raw ring
   const size_t img = 2 * (size_t)tc::CHUNKS * ((size_t)a.bn * 16 + 16);
@@ -482,6 +494,7 @@ int gemm_nt_tc(const GemmNT& g, cudaStream_t s) {
     GemmNT tail = g;
     tail.A = g.A + M_tc * g.lda; tail.C = g.C + M_tc * g.ldc; tail.M = g.M - M_tc;
     if (g.base) tail.base = g.base + M_tc * g.ldbase;
+    if (g.base2) tail.base2 = g.base2 + M_tc * g.ldbase2;
     tail.Bsplit = nullptr;
     GN_TRY(gemm_nt_simt(tail, s));
   }

@@ -334,6 +334,11 @@ extern "C" size_t gnode_integrate_fixed_save_bytes(int64_t n_nodes, int32_t node
                                                    int32_t method, int32_t n_t) {
   const Tableau* tb = tableau_for(method);
   if (!tb || method == GNODE_DOPRI5 || n_t < 2) return 0;
+  if (current_fold()) {
+    Sage3Ctx c;
+    c.N = n_nodes; c.D = node_dim; c.H = hidden_dim;
+    return FoldWs::save_floats_per_step(c, tb->S) * sizeof(float) * (size_t)(n_t - 1);
+  }
   Sage3Saver sv{};
   sv.S = tb->S; sv.n = (size_t)n_nodes * node_dim; sv.nc = (size_t)n_nodes * 2 * hidden_dim;
   return sv.step_floats() * sizeof(float) * (size_t)(n_t - 1);
@@ -346,6 +351,12 @@ extern "C" size_t gnode_integrate_fixed_workspace_bytes(int64_t n_nodes, int32_t
   Sage3Ctx c;
   c.N = n_nodes; c.D = node_dim; c.H = hidden_dim;
   Arena a(nullptr, 0);
+  if (current_fold()) {
+    FoldWs f;
+    c.carve(a, tb->S, backward != 0);
+    f.carve(a, c, tb->S, backward != 0);
+    return a.off;
+  }
   FixedWs w;
   carve_fixed(a, c, *tb, backward != 0, w);
   return a.off;
@@ -366,6 +377,16 @@ extern "C" int gnode_integrate_fixed(const gnode_graph* g, const gnode_sage3_par
   Sage3Ctx c;
   c.g = *g; c.N = g->n_nodes; c.D = p->node_dim; c.H = p->hidden_dim;
   Arena a(workspace, workspace_bytes);
+  if (current_fold()) {
+    FoldWs f;
+    c.carve(a, tb->S, false);
+    f.carve(a, c, tb->S, false);
+    GN_ARENA_OK(a, "gnode_integrate_fixed");
+    GN_TRY(c.pack(*p, false, s));
+    if (save) GN_ARG(save_bytes >= gnode_integrate_fixed_save_bytes(c.N, c.D, c.H, method, n_t),
+                     "gnode_integrate_fixed: save buffer too small (%zu bytes)", save_bytes);
+    return integrate_fixed_folded(c, f, *tb, y0, t, n_t, sol, static_cast<float*>(save), s);
+  }
   FixedWs w;
   carve_fixed(a, c, *tb, false, w);
   GN_ARENA_OK(a, "gnode_integrate_fixed");
@@ -394,6 +415,19 @@ extern "C" int gnode_integrate_fixed_bwd(const gnode_graph* g, const gnode_sage3
   Sage3Ctx c;
   c.g = *g; c.N = g->n_nodes; c.D = p->node_dim; c.H = p->hidden_dim;
   Arena a(workspace, workspace_bytes);
+  if (current_fold()) {
+    FoldWs f;
+    c.carve(a, S, true);
+    f.carve(a, c, S, true);
+    GN_ARENA_OK(a, "gnode_integrate_fixed_bwd");
+    GN_TRY(c.pack(*p, true, s));
+    GN_TRY(c.zero_param_grads(s));
+    if (save) GN_ARG(save_bytes >= gnode_integrate_fixed_save_bytes(c.N, c.D, c.H, method, n_t),
+                     "gnode_integrate_fixed_bwd: save buffer too small (%zu bytes)", save_bytes);
+    GN_TRY(integrate_fixed_folded_bwd(c, f, tb, sol, t, n_t, grad_sol, grad_y0, static_cast<const float*>(save), s));
+    if (grads) GN_TRY(c.unpack_grads(*grads, s));
+    return GNODE_OK;
+  }
   FixedWs w;
   carve_fixed(a, c, tb, true, w);
   GN_ARENA_OK(a, "gnode_integrate_fixed_bwd");

@@ -10,6 +10,7 @@ namespace {
 thread_local char g_err[1024] = "";
 std::atomic<int64_t> g_launches{0};
 std::atomic<int> g_engine{GNODE_ENGINE_AUTO};
+std::atomic<int> g_fold{1};
 }  // namespace
 
 void set_error(const char* fmt, ...) {
@@ -20,6 +21,7 @@ void set_error(const char* fmt, ...) {
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 int current_engine() { return g_engine.load(std::memory_order_relaxed); }
+int current_fold() { return g_fold.load(std::memory_order_relaxed); }
 }  // namespace gnode
 
 extern "C" const char* gnode_last_error(void) { return gnode::g_err; }
@@ -28,4 +30,5 @@ extern "C" int gnode_set_engine(int engine) {
   if (engine < GNODE_ENGINE_AUTO || engine > GNODE_ENGINE_TC) return -1;
   return gnode::g_engine.exchange(engine);
 }
+extern "C" int gnode_set_fold(int fold) { return gnode::g_fold.exchange(fold ? 1 : 0); }
 extern "C" int64_t gnode_launch_count(void) { return gnode::g_launches.load(std::memory_order_relaxed); }

@@ -41,7 +41,7 @@ void Sage3Ctx::carve(Arena& a, int slots, bool backward) {
     if (p2 > pf) pf = p2;
     if (p3 > pf) pf = p3;
     partials = a.take<float>(pf);
-    colpart = a.take<float>(colsum_workspace_floats(D > H ? D : H, N));
+    colpart = a.take<float>(colsum_workspace_floats(D > 2 * H ? D : 2 * H, N));
     dW1cat = a.take<float>((size_t)2 * H * D);
     dW2cat = a.take<float>((size_t)H * 2 * H);
     dW3cat = a.take<float>((size_t)D * 2 * H);

@@ -149,6 +149,8 @@ class _IntegrateFixedFn(torch.autograd.Function):
         T = len(t_host)
         sol = torch.empty((T, N, D), dtype=torch.float32, device=y0.device)
         L = _lib.lib()
+        fold = bool(L.gnode_set_fold(1))     # read the current setting (set-and-restore)
+        L.gnode_set_fold(1 if fold else 0)
         ws = _ws(L.gnode_integrate_fixed_workspace_bytes(N, D, H, method, 0), y0.device)
         tarr = _float_array(t_host)
         # When a backward will follow, keep the per-stage intermediates (autograd's "tape") so the backward does
@@ -165,6 +167,7 @@ class _IntegrateFixedFn(torch.autograd.Function):
                                                _lib.ptr(ws), ws.numel(), _lib.stream_ptr(y0.device)),
                        "gnode_integrate_fixed")
         ctx.graph, ctx.method, ctx.t_host, ctx.save = graph, method, t_host, save
+        ctx.fold = fold
         ctx.save_for_backward(sol, *w)
         return sol
 
@@ -179,15 +182,19 @@ class _IntegrateFixedFn(torch.autograd.Function):
         gw = [torch.zeros_like(t) for t in w]
         grads = _lib.GnodeSage3Grads(*[t.data_ptr() for t in gw])
         L = _lib.lib()
-        ws = _ws(L.gnode_integrate_fixed_workspace_bytes(N, D, H, ctx.method, 1), sol.device)
-        tarr = _float_array(ctx.t_host)
-        with torch.cuda.device(sol.device):
-            save = ctx.save
-            _lib.check(L.gnode_integrate_fixed_bwd(ctx.graph.ref(), C.byref(p), ctx.method, _lib.ptr(sol), tarr, T,
-                                                   _lib.ptr(gsol), _lib.ptr(gy0), C.byref(grads), _lib.ptr(save),
-                                                   save.numel() if save is not None else 0, _lib.ptr(ws),
-                                                   ws.numel(), _lib.stream_ptr(sol.device)),
-                       "gnode_integrate_fixed_bwd")
+        prev_fold = L.gnode_set_fold(1 if ctx.fold else 0)   # the save area's layout is the forward's
+        try:
+            ws = _ws(L.gnode_integrate_fixed_workspace_bytes(N, D, H, ctx.method, 1), sol.device)
+            tarr = _float_array(ctx.t_host)
+            with torch.cuda.device(sol.device):
+                save = ctx.save
+                _lib.check(L.gnode_integrate_fixed_bwd(ctx.graph.ref(), C.byref(p), ctx.method, _lib.ptr(sol), tarr, T,
+                                                       _lib.ptr(gsol), _lib.ptr(gy0), C.byref(grads), _lib.ptr(save),
+                                                       save.numel() if save is not None else 0, _lib.ptr(ws),
+                                                       ws.numel(), _lib.stream_ptr(sol.device)),
+                           "gnode_integrate_fixed_bwd")
+        finally:
+            L.gnode_set_fold(prev_fold)
         ctx.save = None
         return (gy0, None, None, None, *gw)
 

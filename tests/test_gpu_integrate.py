@@ -10,6 +10,15 @@ from tests._util import FIXED_TOL, rel_l2, to_ref_batch
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True, params=["folded", "direct"])
+def fold_mode(request, cuda):
+    """Every test runs with the folded RK stages (default: D-wide contractions once per step, csrc/fold.cu) and with
+    the direct evaluation of the field at every stage (the straightforward anchor)."""
+    prev = S.set_fold(request.param == "folded")
+    yield request.param
+    S.set_fold(prev)
+
+
 def _models(D, solver, cuda, conv3_scale=0.1, seed=1):
     model = S.GraphODE(D, 12, 7, hidden_dim=64, ode_solver=solver)
     S.synthetic.init_weights(model, seed=seed, conv3_scale=conv3_scale)
