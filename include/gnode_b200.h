@@ -109,6 +109,12 @@ int gnode_csr_build(const int64_t* edge_index, int64_t n_edges, int64_t n_nodes,
                     int32_t* rowptr, int32_t* col, int32_t* t_rowptr, int32_t* t_col,
                     void* workspace, size_t workspace_bytes, gnode_stream_t stream);
 
+/* Same, without synchronising: `error_flag` (device int32, caller-owned) is set to 1 when an index is out of range
+ * (such edges are skipped, the arrays stay memory-safe); the caller reads it whenever convenient. */
+int gnode_csr_build_async(const int64_t* edge_index, int64_t n_edges, int64_t n_nodes,
+                          int32_t* rowptr, int32_t* col, int32_t* t_rowptr, int32_t* t_col, int32_t* error_flag,
+                          void* workspace, size_t workspace_bytes, gnode_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * Dense "NT" contraction on the selected engine (the per-node Linear layers of SAGEConv /
  * ODEFunction; reference call sites scripts/train_gde.py:27-29, scripts/gnode.py:165-171):

@@ -70,6 +70,7 @@ _SIGNATURES = {
     "gnode_prof_read": (C.c_int, [C.POINTER(GnodeProfEntry), C.c_int]),
     "gnode_csr_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int64]),
     "gnode_csr_build": (C.c_int, [_P, C.c_int64, C.c_int64, _P, _P, _P, _P, _P, C.c_size_t, _P]),
+    "gnode_csr_build_async": (C.c_int, [_P, C.c_int64, C.c_int64, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
     "gnode_gemm_nt_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
     "gnode_gemm_nt": (C.c_int, [_P, C.c_int64, _P, C.c_int64, _P, C.c_int64, C.c_int64, C.c_int32, C.c_int32, _P,
                                 C.c_int32, _P, C.c_int64, C.c_float, _P, C.c_size_t, _P]),

@@ -49,16 +49,18 @@ __global__ void __launch_bounds__(256) k_agg_fwd(const int32_t* __restrict__ row
   const float denom = (float)((e - b) > 1 ? (e - b) : 1);
   for (int c = gl * VEC; c < C; c += lpr * VEC) {
     typename V::T acc = V::zero();
-    int p = b;
-    for (; p + 4 <= e; p += 4) {
-      const int j0 = col[p], j1 = col[p + 1], j2 = col[p + 2], j3 = col[p + 3];
-      const typename V::T v0 = V::ld(in + (int64_t)j0 * ld_in + c);
-      const typename V::T v1 = V::ld(in + (int64_t)j1 * ld_in + c);
-      const typename V::T v2 = V::ld(in + (int64_t)j2 * ld_in + c);
-      const typename V::T v3 = V::ld(in + (int64_t)j3 * ld_in + c);
-      acc = V::add(V::add(V::add(V::add(acc, v0), v1), v2), v3);
+    // batches of four neighbours, indices first, then all row loads in flight together (the tail batch is
+    // predicated instead of serialised: most rows of the warehouse graphs have 1-3 neighbours)
+    for (int p = b; p < e; p += 4) {
+      int j[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) j[k] = (p + k < e) ? col[p + k] : -1;
+      typename V::T v[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v[k] = (j[k] >= 0) ? V::ld(in + (int64_t)j[k] * ld_in + c) : V::zero();
+#pragma unroll
+      for (int k = 0; k < 4; ++k) if (j[k] >= 0) acc = V::add(acc, v[k]);
     }
-    for (; p < e; ++p) acc = V::add(acc, V::ld(in + (int64_t)col[p] * ld_in + c));
     acc = V::div(acc, denom);
     if (add) acc = V::add(acc, V::ld(add + row * ld_add + c));
     if (bias) acc = V::add(acc, V::ld(bias + c));
@@ -82,10 +84,18 @@ __global__ void __launch_bounds__(256) k_agg_bwd(const int32_t* __restrict__ row
   const int b = t_rowptr[row], e = t_rowptr[row + 1];
   for (int c = gl * VEC; c < C; c += lpr * VEC) {
     typename V::T acc = V::zero();
-    for (int p = b; p < e; ++p) {
-      const int i = t_col[p];
-      const int deg = rowptr[i + 1] - rowptr[i];  // >= 1 since edge (row -> i) exists
-      acc = V::add(acc, V::div(V::ld(gin + (int64_t)i * ld_gin + c), (float)deg));
+    for (int p = b; p < e; p += 4) {
+      int i[4], r0[4], r1[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) i[k] = (p + k < e) ? t_col[p + k] : -1;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { r0[k] = (i[k] >= 0) ? rowptr[i[k]] : 0; r1[k] = (i[k] >= 0) ? rowptr[i[k] + 1] : 1; }
+      typename V::T v[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v[k] = (i[k] >= 0) ? V::ld(gin + (int64_t)i[k] * ld_gin + c) : V::zero();
+#pragma unroll
+      for (int k = 0; k < 4; ++k)   // deg >= 1 since the edge (row -> i) exists
+        if (i[k] >= 0) acc = V::add(acc, V::div(v[k], (float)(r1[k] - r0[k])));
     }
     if (add) acc = V::add(acc, V::ld(add + row * ld_add + c));
     if (act) acc = V::mask(acc, V::ld(act + row * ld_act + c));

@@ -125,6 +125,9 @@ struct GemmTN {
   int64_t Nrows;
   float* C; int64_t ldc;     // accumulated: C += scale * result
   float scale = 1.0f;
+  // optional fused column sums (bias gradients):  colsumA[p] += colsumA_scale * sum_n A[n, p], same for B
+  float* colsumA = nullptr; float colsumA_scale = 1.0f;
+  float* colsumB = nullptr; float colsumB_scale = 1.0f;
 };
 size_t gemm_tn_workspace_floats(int P, int Q, int64_t Nrows);
 int gemm_tn(const GemmTN& g, float* partials, cudaStream_t s);

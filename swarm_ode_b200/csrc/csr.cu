@@ -209,10 +209,11 @@ extern "C" size_t gnode_csr_workspace_bytes(int64_t n_nodes, int64_t n_edges) {
   return a.off;
 }
 
-extern "C" int gnode_csr_build(const int64_t* edge_index, int64_t E, int64_t N, int32_t* rowptr,
-                               int32_t* col, int32_t* t_rowptr, int32_t* t_col, void* workspace,
-                               size_t workspace_bytes, gnode_stream_t stream) {
+extern "C" int gnode_csr_build_async(const int64_t* edge_index, int64_t E, int64_t N, int32_t* rowptr,
+                                     int32_t* col, int32_t* t_rowptr, int32_t* t_col, int32_t* error_flag,
+                                     void* workspace, size_t workspace_bytes, gnode_stream_t stream) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  GN_ARG(error_flag != nullptr, "gnode_csr_build_async: error_flag is null");
   GN_ARG(N > 0 && E >= 0, "gnode_csr_build: n_nodes must be > 0 and n_edges >= 0 (got %lld, %lld)",
          (long long)N, (long long)E);
   GN_ARG(N < (1ll << 31) - 1 && E < (1ll << 31) - 1, "gnode_csr_build: int32 CSR overflow");
@@ -224,11 +225,11 @@ extern "C" int gnode_csr_build(const int64_t* edge_index, int64_t E, int64_t N, 
   GN_PROF(s, 0.0, 16.0 * E + 8.0 * E + 8.0 * N, "csr_build");
   GN_CUDA(cudaMemsetAsync(w.cnt_in, 0, sizeof(int32_t) * (N + 1), s));
   GN_CUDA(cudaMemsetAsync(w.cnt_out, 0, sizeof(int32_t) * (N + 1), s));
-  GN_CUDA(cudaMemsetAsync(w.flag, 0, sizeof(int32_t), s));
+  GN_CUDA(cudaMemsetAsync(error_flag, 0, sizeof(int32_t), s));
   const int threads = 256;
   unsigned eblocks = (unsigned)(E > 0 ? (ceil_div64(E, threads) < 148 * 16 ? ceil_div64(E, threads) : 148 * 16) : 1);
   if (E > 0) {
-    k_count<<<eblocks, threads, 0, s>>>(edge_index, E, N, w.cnt_in, w.cnt_out, w.flag);
+    k_count<<<eblocks, threads, 0, s>>>(edge_index, E, N, w.cnt_in, w.cnt_out, error_flag);
     GN_LAUNCHED();
   }
   GN_TRY(scan_counts(w.cnt_in, N, rowptr, w.sums, s));
@@ -250,6 +251,19 @@ extern "C" int gnode_csr_build(const int64_t* edge_index, int64_t E, int64_t N, 
     k_sort_long<<<wb, threads, 0, s>>>(t_rowptr, w.t_col_u, t_col, N);
     GN_LAUNCHED();
   }
+  return GNODE_OK;
+}
+
+extern "C" int gnode_csr_build(const int64_t* edge_index, int64_t E, int64_t N, int32_t* rowptr,
+                               int32_t* col, int32_t* t_rowptr, int32_t* t_col, void* workspace,
+                               size_t workspace_bytes, gnode_stream_t stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  GN_ARG(N > 0 && E >= 0, "gnode_csr_build: n_nodes must be > 0 and n_edges >= 0 (got %lld, %lld)",
+         (long long)N, (long long)E);
+  Arena a(workspace, workspace_bytes);
+  CsrWs w = carve(a, N, E);
+  GN_ARENA_OK(a, "gnode_csr_build");
+  GN_TRY(gnode_csr_build_async(edge_index, E, N, rowptr, col, t_rowptr, t_col, w.flag, workspace, workspace_bytes, stream));
   int32_t flag = 0;
   GN_CUDA(cudaMemcpyAsync(&flag, w.flag, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
   GN_CUDA(cudaStreamSynchronize(s));

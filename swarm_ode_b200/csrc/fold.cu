@@ -274,32 +274,20 @@ int integrate_fixed_folded_bwd(Sage3Ctx& c, FoldWs& f, const Tableau& tb, const 
       {  // dW2cat += g_v2^T @ cat1
         GemmTN q{};
         q.A = c.gv2; q.lda = H; q.P = H; q.B = c1; q.ldb = H2; q.Q = H2; q.Nrows = N; q.C = c.dW2cat; q.ldc = H2;
+        q.colsumA = c.db2;                                          // db2 += colsum(g_v2), fused
         GN_TRY(gemm_tn(q, f.partials, s));
       }
-      GN_TRY(colsum_accum(c.gv2, H, N, H, c.db2, 1.f, c.colpart, s));
       // ---- conv2 -> conv1 ----   g_u1 = (A^T(gcat_l) + gcat_r) * [h1 > 0] -> gz[:, H:] ; A^T(g_u1) -> gz[:, :H]
       GN_TRY(agg_mean_bwd(c.g, c.gcat, H2, gz + H, H2, H, c.gcat + H, H2, c1 + H, H2, s));
       GN_TRY(agg_mean_bwd(c.g, gz + H, H2, gz, H2, H, nullptr, 0, nullptr, 0, s));
-      // column sums of gz_st: db1 += cs[H:],  g1 += (dt sum_j beta[st][j]) cs
-      GN_CUDA(cudaMemsetAsync(f.cs, 0, sizeof(float) * H2, s));
-      GN_TRY(colsum_accum(gz, H2, N, H2, f.cs, 1.f, c.colpart, s));
-      {
-        LinComb l1{};
-        l1.out = c.db1; l1.base = c.db1; l1.n = H; l1.n_terms = 1; l1.in[0] = f.cs + H; l1.coef[0] = 1.f;
-        GN_TRY(lincomb(l1, s));
-      }
       if (st > 0) {
+        // R += gz_st^T @ V_st  [2H, 2H];   g1 += (dt sum_j beta[st][j]) colsum(gz_st), fused into the same pass
         double bsum = 0.0;
         for (int jj = 0; jj < st; ++jj) bsum += tb.beta[st][jj];
         const float w = (float)bsum * dt;
-        if (w != 0.f) {
-          LinComb l2{};
-          l2.out = f.g1; l2.base = f.g1; l2.n = H2; l2.n_terms = 1; l2.in[0] = f.cs; l2.coef[0] = w;
-          GN_TRY(lincomb(l2, s));
-        }
-        // R += gz_st^T @ V_st     [2H, 2H]
         GemmTN q{};
         q.A = gz; q.lda = H2; q.P = H2; q.B = f.V[st]; q.ldb = H2; q.Q = H2; q.Nrows = N; q.C = f.R; q.ldc = H2;
+        if (w != 0.f) { q.colsumA = f.g1; q.colsumA_scale = w; }
         GN_TRY(gemm_tn(q, f.partials, s));
       }
     }
@@ -314,13 +302,18 @@ int integrate_fixed_folded_bwd(Sage3Ctx& c, FoldWs& f, const Tableau& tb, const 
     {  // dW3cat += G^T @ C     [D, 2H]
       GemmTN q{};
       q.A = G; q.lda = c.D; q.P = c.D; q.B = f.Cbuf; q.ldb = H2; q.Q = H2; q.Nrows = N; q.C = c.dW3cat; q.ldc = H2;
+      q.colsumA = c.db3; q.colsumA_scale = (float)csum * dt;       // db3 += (dt sum c_s) colsum(G), fused
       GN_TRY(gemm_tn(q, f.partials, s));
     }
-    GN_TRY(colsum_accum(G, c.D, N, c.D, c.db3, (float)csum * dt, c.colpart, s));
-    {  // dW1cat += GZ^T @ y    [2H, D]
+    {  // dW1cat += GZ^T @ y    [2H, D];   colsum(GZ) = sum_s colsum(gz_s): its right half is db1
+      GN_CUDA(cudaMemsetAsync(f.cs, 0, sizeof(float) * H2, s));
       GemmTN q{};
       q.A = f.GZ; q.lda = H2; q.P = H2; q.B = y; q.ldb = c.D; q.Q = c.D; q.Nrows = N; q.C = c.dW1cat; q.ldc = c.D;
+      q.colsumA = f.cs;
       GN_TRY(gemm_tn(q, f.partials, s));
+      LinComb l1{};
+      l1.out = c.db1; l1.base = c.db1; l1.n = H; l1.n_terms = 1; l1.in[0] = f.cs + H; l1.coef[0] = 1.f;
+      GN_TRY(lincomb(l1, s));
     }
     {  // cotangent of y_j:  G + GZ @ w1cat + grad_sol[j]
       GemmNT q{};

@@ -222,7 +222,9 @@ int gemm_nt_simt(const GemmNT& g, cudaStream_t s) {
 }
 
 size_t gemm_tn_simt_workspace_floats(int P, int Q, int64_t Nrows) {
-  return (size_t)tn_splits(P, Q, Nrows) * (size_t)P * (size_t)Q;
+  const size_t a = (size_t)tn_splits(P, Q, Nrows) * (size_t)P * (size_t)Q;
+  const size_t b = (size_t)colsum_blocks(Nrows) * (size_t)(P > Q ? P : Q);
+  return a > b ? a : b;
 }
 
 int gemm_tn_simt(const GemmTN& g, float* partials, cudaStream_t s) {
@@ -241,6 +243,8 @@ int gemm_tn_simt(const GemmTN& g, float* partials, cudaStream_t s) {
   const int64_t PQ = (int64_t)g.P * g.Q;
   k_reduce_partials<<<(unsigned)ceil_div64(PQ, 256), 256, 0, s>>>(partials, S, PQ, g.Q, g.C, g.ldc, g.scale);
   GN_LAUNCHED();
+  if (g.colsumA) GN_TRY(colsum_accum(g.A, g.lda, g.Nrows, g.P, g.colsumA, g.colsumA_scale, partials, s));
+  if (g.colsumB) GN_TRY(colsum_accum(g.B, g.ldb, g.Nrows, g.Q, g.colsumB, g.colsumB_scale, partials, s));
   return GNODE_OK;
 }
 

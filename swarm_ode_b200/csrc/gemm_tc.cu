@@ -70,31 +70,31 @@ struct Args {
   int* status;
 };
 
-// HAS_BASE: 0 none, 1 base, 2 base + base2
+// HAS_BASE: 0 none, 1 base, 2 base + base2.  All 32 (64) base loads of the chunk are issued before the first use,
+// so the epilogue pays the L2 / HBM latency once per 32 x 32 chunk instead of once per 8 rows.
 template <int ACT, int HAS_BASE>
 __device__ __forceinline__ void store_rows(const float* __restrict__ stg, int lane, float bv, float scale, float* crow,
                                            int64_t ldc, const float* brow, int64_t ldbase, float base_scale,
                                            const float* b2row, int64_t ldbase2, int rmax, bool cin) {
+  float bs[32];
+  if (HAS_BASE >= 1) {
 #pragma unroll
-  for (int r0 = 0; r0 < 32; r0 += 8) {
-    float bs[8];
-    if (HAS_BASE >= 1) {
+    for (int u = 0; u < 32; ++u) bs[u] = (cin && u < rmax) ? __ldg(brow + (int64_t)u * ldbase) : 0.f;
+  }
+  float b2[32];
+  if (HAS_BASE == 2) {
 #pragma unroll
-      for (int u = 0; u < 8; ++u) bs[u] = (cin && r0 + u < rmax) ? base_scale * __ldg(brow + (int64_t)(r0 + u) * ldbase) : 0.f;
-    }
-    if (HAS_BASE == 2) {
+    for (int u = 0; u < 32; ++u) b2[u] = (cin && u < rmax) ? __ldg(b2row + (int64_t)u * ldbase2) : 0.f;
+  }
 #pragma unroll
-      for (int u = 0; u < 8; ++u) bs[u] += (cin && r0 + u < rmax) ? __ldg(b2row + (int64_t)(r0 + u) * ldbase2) : 0.f;
-    }
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      float x = stg[(r0 + u) * 33 + lane] + bv;
-      if (ACT == 1) x = fmaxf(x, 0.f);
-      if (ACT == 2) x = tanhf(x);
-      x *= scale;
-      if (HAS_BASE >= 1) x += bs[u];
-      if (cin && r0 + u < rmax) crow[(int64_t)(r0 + u) * ldc] = x;
-    }
+  for (int u = 0; u < 32; ++u) {
+    float x = stg[u * 33 + lane] + bv;
+    if (ACT == 1) x = fmaxf(x, 0.f);
+    if (ACT == 2) x = tanhf(x);
+    x *= scale;
+    if (HAS_BASE >= 1) x += base_scale * bs[u];
+    if (HAS_BASE == 2) x += b2[u];
+    if (cin && u < rmax) crow[(int64_t)u * ldc] = x;
   }
 }
 
@@ -177,8 +177,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
       bool first_lap = true, ok = true;
       const uint32_t img_bytes = 2 * b_plane;
       const float* const basep = a.base;
-      const int64_t ldbase = a.ldbase, M = a.M;
+      const float* const base2p = a.base2;
+      const int64_t ldbase = a.ldbase, ldbase2 = a.ldbase2, M = a.M;
       const bool base_pf = basep != nullptr && (reinterpret_cast<uint64_t>(basep) & 15) == 0;
+      const bool base2_pf = base2p != nullptr && (reinterpret_cast<uint64_t>(base2p) & 15) == 0;
       for (int64_t t = tile0; t < total_tiles && ok; t += tstep) {
         if (base_pf && (t % n_tiles) == 0) {
           // the epilogue of this tile reads base[m0 : m0+128, :]: one contiguous span -> warm it in L2 now,
@@ -188,6 +190,13 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
           const uint32_t bytes = (uint32_t)((rows * ldbase * 4) & ~15ll);
           if (bytes > 0)
             asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<uint64_t>(basep + m0 * ldbase)), "r"(bytes) : "memory");
+        }
+        if (base2_pf && (t % n_tiles) == 0) {
+          const int64_t m0 = (t / n_tiles) * BM;
+          const int64_t rows = (M - m0 < BM) ? (M - m0) : BM;
+          const uint32_t bytes = (uint32_t)((rows * ldbase2 * 4) & ~15ll);
+          if (bytes > 0)
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<uint64_t>(base2p + m0 * ldbase2)), "r"(bytes) : "memory");
         }
         const float* src = Bimg + (size_t)(t % n_tiles) * nkb * (img_bytes / 4);
         for (int kb = 0; kb < nkb && ok; ++kb, src += img_bytes / 4) {

@@ -39,6 +39,8 @@ struct Args {
   int64_t n_kb;                // 8-row blocks in total
   int n_raw;                   // raw ring depth
   float* partials;             // [gridDim.x][wn][MW]
+  float* colpart_m;            // optional [gridDim.x][2][wm]: per-CTA, per-K-chunk column sums of the M operand
+  float* colpart_n;            // optional [gridDim.x][2][wn]
   int* status;
 };
 
@@ -160,6 +162,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tn_tc(const Args a) {
         valid |= 2u << q;
       } else { src[1 + q] = 0; pitch[1 + q] = 0; dst[1 + q] = 0; lo_off[1 + q] = 0; }
     }
+    float csum[1 + NT_TASKS];
+#pragma unroll
+    for (int q = 0; q < 1 + NT_TASKS; ++q) csum[q] = 0.f;
     uint32_t sr = 0, pr = 0, so = 0, po = 0;
     bool first_lap_o = true, ok = true;
     for (int i = 0; i < nkb && ok; ++i) {
@@ -186,6 +191,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tn_tc(const Args a) {
           h.w = (__float_as_uint(v[q][3]) + 0x1000u) & 0xFFFFE000u; l.w = v[q][3] - __uint_as_float(h.w);
           *reinterpret_cast<uint4*>(op + dst[q]) = h;
           *reinterpret_cast<float4*>(op + dst[q] + lo_off[q]) = l;
+          csum[q] += (v[q][0] + v[q][1]) + (v[q][2] + v[q][3]);   // fused column sums (bias gradients)
         }
       }
       mbar_arrive(smem_u32(&bar_raw_empty[sr]));
@@ -193,6 +199,13 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tn_tc(const Args a) {
       mbar_arrive(smem_u32(&bar_op_full[so]));
       if (++sr == (uint32_t)NR) { sr = 0; pr ^= 1u; }
       if (++so == (uint32_t)N_OP) { so = 0; po ^= 1u; first_lap_o = false; }
+    }
+    // per-CTA column sums: task (kc, column) -> partial [cta][kc][column]
+    if (a.colpart_m && (valid & 1u)) a.colpart_m[(size_t)blockIdx.x * 2 * wm + t] = csum[0];
+    if (a.colpart_n) {
+#pragma unroll
+      for (int q = 0; q < NT_TASKS; ++q)
+        if (valid & (2u << q)) a.colpart_n[(size_t)blockIdx.x * 2 * wn + t + q * CONV_THREADS] = csum[1 + q];
     }
     // =========================== epilogue (warps 2..5: TMEM lane quadrants 2, 3, 0, 1) ===========================
     if (warp < 6 && nkb > 0 && ok) {
@@ -228,10 +241,30 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tn_tc(const Args a) {
 }
 
 // C (+)= scale * sum_c partials[c][n][m]   with C[m, n] (n_major = 0) or C[n, m] (n_major = 1); m < wm
+// followed (same launch) by the column sums:  out_m[c] += scale_m * sum over [S][2] of colpart_m, same for n
 __global__ void k_reduce_tn(const float* __restrict__ partials, int S, int wn, int wm, float* __restrict__ C,
-                            int64_t ldc, int n_major, float scale) {
-  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (i >= (int64_t)wn * MW) return;
+                            int64_t ldc, int n_major, float scale, const float* __restrict__ colpart_m,
+                            float* __restrict__ out_m, float scale_m, const float* __restrict__ colpart_n,
+                            float* __restrict__ out_n, float scale_n) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= (int64_t)wn * MW) {
+    i -= (int64_t)wn * MW;
+    if (i < wm) {
+      if (out_m) {
+        float s = 0.f;
+        for (int r = 0; r < 2 * S; ++r) s += colpart_m[(size_t)r * wm + i];
+        out_m[i] += scale_m * s;
+      }
+    } else if (i - wm < wn) {
+      i -= wm;
+      if (out_n) {
+        float s = 0.f;
+        for (int r = 0; r < 2 * S; ++r) s += colpart_n[(size_t)r * wn + i];
+        out_n[i] += scale_n * s;
+      }
+    }
+    return;
+  }
   const int n = (int)(i / MW), m = (int)(i % MW);
   if (m >= wm) return;
   float s = 0.f;
@@ -270,9 +303,9 @@ namespace tc { int* status_ptr(); }
 bool gemm_tn_tc_supported(const GemmTN& g) { return tctn::plan_for(g).ok; }
 
 size_t gemm_tn_tc_workspace_floats(int P, int Q) {
-  // worst case over both operand roles: kNumSMs partials of [wn][128]
+  // worst case over both operand roles: kNumSMs partials of [wn][128], plus the column-sum partials [kNumSMs][2][P + Q]
   const int wn = (Q <= tctn::MW && (P > tctn::MW || Q >= P)) ? P : Q;
-  return (size_t)kNumSMs * (size_t)wn * tctn::MW;
+  return (size_t)kNumSMs * (size_t)wn * tctn::MW + (size_t)kNumSMs * 2 * (size_t)(P + Q);
 }
 
 int gemm_tn_simt(const GemmTN& g, float* partials, cudaStream_t s);
@@ -286,6 +319,13 @@ int gemm_tn_tc(const GemmTN& g, float* partials, cudaStream_t s) {
   a.Am = p.m_is_b ? g.B : g.A; a.wm = p.wm;
   a.Bn = p.m_is_b ? g.A : g.B; a.wn = p.wn;
   a.bn = p.bn; a.nt = p.nt; a.n_kb = p.n_kb; a.partials = partials; a.status = status_dev;
+  float* const out_m = p.m_is_b ? g.colsumB : g.colsumA;
+  float* const out_n = p.m_is_b ? g.colsumA : g.colsumB;
+  const float scale_m = p.m_is_b ? g.colsumB_scale : g.colsumA_scale;
+  const float scale_n = p.m_is_b ? g.colsumA_scale : g.colsumB_scale;
+  float* cp = partials + (size_t)p.grid * (size_t)p.wn * tctn::MW;
+  a.colpart_m = out_m ? cp : nullptr;
+  a.colpart_n = out_n ? cp + (size_t)p.grid * 2 * p.wm : nullptr;
   const size_t raw_stage = 32 * (size_t)(p.wm + p.wn);
   const size_t op_stage = 2 * (size_t)tctn::M_PLANE + 4 * ((size_t)p.nt * p.bn * 16 + 16);
   const size_t budget = 220 * 1024;
@@ -301,10 +341,11 @@ int gemm_tn_tc(const GemmTN& g, float* partials, cudaStream_t s) {
   }
   tctn::k_gemm_tn_tc<<<p.grid, tctn::THREADS, smem, s>>>(a);
   GN_LAUNCHED();
-  const int64_t cnt = (int64_t)p.wn * tctn::MW;
+  const int64_t cnt = (int64_t)p.wn * tctn::MW + p.wm + p.wn;
   // C is [P, Q]: with the M operand = B (q = m) the partial index n is p -> rows of C are n
   tctn::k_reduce_tn<<<(unsigned)ceil_div64(cnt, 256), 256, 0, s>>>(partials, p.grid, p.wn, p.wm, g.C, g.ldc,
-                                                                    p.m_is_b ? 1 : 0, g.scale);
+                                                                    p.m_is_b ? 1 : 0, g.scale, a.colpart_m, out_m, scale_m,
+                                                                    a.colpart_n, out_n, scale_n);
   GN_LAUNCHED();
   const int64_t done = p.n_kb * tctn::BKR;
   if (done < g.Nrows) {   // up to 7 trailing rows: FFMA kernel, accumulated on top

@@ -162,9 +162,9 @@ int Sage3Ctx::vjp(const float* x, int slot, const float* gk, float* gx, cudaStre
   {  // dW3cat += gk^T @ cat2      [D, 2H]
     GemmTN q{};
     q.A = gk; q.lda = D; q.P = D; q.B = c2; q.ldb = H2; q.Q = H2; q.Nrows = N; q.C = dW3cat; q.ldc = H2;
+    q.colsumA = db3;                                   // db3 += colsum(gk), fused into the same pass
     GN_TRY(gemm_tn(q, partials, s));
   }
-  GN_TRY(colsum_accum(gk, D, N, D, db3, 1.f, colpart, s));
   // g_v2 = (A^T(gcat_l) + gcat_r) * [h2 > 0]
   GN_TRY(agg_mean_bwd(g, gcat, H2, gv2, H, H, gcat + H, H2, c2 + H, H2, s));
   // ---- conv2 ----
@@ -177,9 +177,9 @@ int Sage3Ctx::vjp(const float* x, int slot, const float* gk, float* gx, cudaStre
   {  // dW2cat += g_v2^T @ cat1    [H, 2H]
     GemmTN q{};
     q.A = gv2; q.lda = H; q.P = H; q.B = c1; q.ldb = H2; q.Q = H2; q.Nrows = N; q.C = dW2cat; q.ldc = H2;
+    q.colsumA = db2;
     GN_TRY(gemm_tn(q, partials, s));
   }
-  GN_TRY(colsum_accum(gv2, H, N, H, db2, 1.f, colpart, s));
   // g_u1 = (A^T(gcat_l) + gcat_r) * [h1 > 0]  -> gz[:, H:] ;  A^T(g_u1) -> gz[:, :H]
   GN_TRY(agg_mean_bwd(g, gcat, H2, gz + H, H2, H, gcat + H, H2, c1 + H, H2, s));
   GN_TRY(agg_mean_bwd(g, gz + H, H2, gz, H2, H, nullptr, 0, nullptr, 0, s));

@@ -96,7 +96,13 @@ def masked_mse_train_step(model, optimizer, graphs, next_positions: torch.Tensor
     mask = graphs.is_current_agent
     target = next_positions.view(-1, 2)
     local_n = int(target.shape[0])
-    loss = torch.nn.functional.mse_loss(pred[mask], target)
+    # pred[mask] of the reference (scripts/train_gde.py:490) synchronises with the host to size its result; the number
+    # of masked nodes is known here (one target row each), so the same rows are gathered without a synchronisation
+    if hasattr(torch, "nonzero_static") and mask.is_cuda:
+        idx = torch.nonzero_static(mask, size=local_n).view(-1)
+        loss = torch.nn.functional.mse_loss(pred.index_select(0, idx), target)
+    else:
+        loss = torch.nn.functional.mse_loss(pred[mask], target)
     loss.backward()
     if is_dist():
         total_n = global_count(local_n, device=pred.device, group=group)

@@ -18,7 +18,7 @@ from . import _lib
 class CSRGraph:
     """int32 CSR (by destination) + transpose CSR (by source) living on one CUDA device."""
 
-    def __init__(self, edge_index: torch.Tensor, num_nodes: int):
+    def __init__(self, edge_index: torch.Tensor, num_nodes: int, validate: str = "sync"):
         if not edge_index.is_cuda:
             raise _lib.GnodeError("edge_index must live on a CUDA device; libgnode_b200 has no CPU path")
         if edge_index.dim() != 2 or edge_index.size(0) != 2:
@@ -36,22 +36,70 @@ class CSRGraph:
         L = _lib.lib()
         nbytes = L.gnode_csr_workspace_bytes(N, E)
         ws = _lib.WORKSPACE.get(nbytes, dev, "csr")
+        self._err_dev = torch.empty(1, dtype=torch.int32, device=dev)
+        self._err_host = None
+        self._err_event = None
         with torch.cuda.device(dev):
-            _lib.check(L.gnode_csr_build(_lib.ptr(edge_index), E, N, _lib.ptr(self.rowptr), _lib.ptr(self.col),
-                                         _lib.ptr(self.t_rowptr), _lib.ptr(self.t_col), _lib.ptr(ws), ws.numel(),
-                                         _lib.stream_ptr(dev)), "gnode_csr_build")
+            if validate == "sync":
+                _lib.check(L.gnode_csr_build(_lib.ptr(edge_index), E, N, _lib.ptr(self.rowptr), _lib.ptr(self.col),
+                                             _lib.ptr(self.t_rowptr), _lib.ptr(self.t_col), _lib.ptr(ws), ws.numel(),
+                                             _lib.stream_ptr(dev)), "gnode_csr_build")
+            else:
+                # no host synchronisation: out-of-range edges are skipped on the device and flagged; the flag travels
+                # to pinned host memory asynchronously and is looked at by poll() / validate()
+                _lib.check(L.gnode_csr_build_async(_lib.ptr(edge_index), E, N, _lib.ptr(self.rowptr), _lib.ptr(self.col),
+                                                   _lib.ptr(self.t_rowptr), _lib.ptr(self.t_col), _lib.ptr(self._err_dev),
+                                                   _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev)), "gnode_csr_build_async")
+                self._err_host = torch.empty(1, dtype=torch.int32, pin_memory=True)
+                self._err_host.copy_(self._err_dev, non_blocking=True)
+                self._err_event = torch.cuda.Event()
+                self._err_event.record(torch.cuda.current_stream(dev))
+                _PENDING.append(self)
         self.struct = _lib.GnodeGraph(N, E, self.rowptr.data_ptr(), self.col.data_ptr(), self.t_rowptr.data_ptr(),
                                       self.t_col.data_ptr())
 
     def ref(self):
         return C.byref(self.struct)
 
+    def poll(self, wait: bool = False) -> bool:
+        """Deferred index validation: returns True once the verdict is known; raises GnodeError for a bad edge list."""
+        if self._err_event is None:
+            return True
+        if wait:
+            self._err_event.synchronize()
+        elif not self._err_event.query():
+            return False
+        bad = int(self._err_host[0]) != 0
+        self._err_event = None
+        if bad:
+            raise _lib.GnodeError(f"gnode_csr_build: edge_index holds node ids outside [0, {self.num_nodes}) "
+                                  "(deferred check; the offending edges were skipped)")
+        return True
+
+    def validate(self) -> None:
+        self.poll(wait=True)
+
+
+_PENDING: list = []
+
+
+def poll_pending() -> None:
+    """Look (without blocking) at the deferred validations that have completed."""
+    keep = []
+    try:
+        for g in _PENDING:
+            if not g.poll():
+                keep.append(g)
+    finally:
+        _PENDING[:] = keep
+
 
 _CACHE: "OrderedDict[tuple, tuple]" = OrderedDict()  # key -> (keyed edge_index tensor, CSRGraph)
 _CACHE_MAX = 8
 
 
-def csr_for(edge_index: torch.Tensor, num_nodes: int, holder: Optional[object] = None) -> CSRGraph:
+def csr_for(edge_index: torch.Tensor, num_nodes: int, holder: Optional[object] = None,
+            validate: str = "sync") -> CSRGraph:
     """CSR of ``edge_index``; cached on ``holder`` (e.g. the batch object) and in a small LRU keyed by
     the tensor's storage, shape and version counter.  Every cache entry keeps the keyed tensor alive,
     so its address cannot be recycled for a different edge list while the entry exists."""
@@ -62,7 +110,9 @@ def csr_for(edge_index: torch.Tensor, num_nodes: int, holder: Optional[object] =
             return cached[1]
     entry = _CACHE.get(key)
     if entry is None or entry[0] is not edge_index and entry[0].data_ptr() != edge_index.data_ptr():
-        entry = (edge_index, CSRGraph(edge_index, num_nodes))
+        if validate != "sync":
+            poll_pending()
+        entry = (edge_index, CSRGraph(edge_index, num_nodes, validate=validate))
         _CACHE[key] = entry
         while len(_CACHE) > _CACHE_MAX:
             _CACHE.popitem(last=False)

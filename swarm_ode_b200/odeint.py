@@ -34,7 +34,7 @@ def odeint(func, y0: torch.Tensor, t: torch.Tensor, *, rtol: float = 1e-7, atol:
     if torch.is_tensor(t):
         if t.dim() != 1:
             raise ValueError("t must be one dimensional")
-        t_list = t.detach().to("cpu", torch.float64).tolist()
+        t_list = ops.time_grid_to_host(t, torch.float64)
         if any(b <= a for a, b in zip(t_list[:-1], t_list[1:])):
             raise ValueError("t must be strictly increasing")
     sink = options.get("_stats_sink")

@@ -199,10 +199,28 @@ class _IntegrateFixedFn(torch.autograd.Function):
         return (gy0, None, None, None, *gw)
 
 
+_T_CACHE: dict = {}
+
+
+def time_grid_to_host(t, dtype=torch.float32) -> Tuple[float, ...]:
+    """Host copy of a time grid.  A CUDA tensor costs one device->host synchronisation the first time it is seen;
+    the values are cached by (storage, version), so a training loop that reuses its ``time_span`` tensor pays once."""
+    if not torch.is_tensor(t):
+        return tuple(float(v) for v in t)
+    if not t.is_cuda:
+        return tuple(float(v) for v in t.detach().to(dtype).tolist())
+    key = (t.data_ptr(), t._version, tuple(t.shape), str(t.device), t.dtype, dtype)
+    hit = _T_CACHE.get(key)
+    if hit is None:
+        hit = tuple(float(v) for v in t.detach().to("cpu", dtype).tolist())
+        if len(_T_CACHE) > 64:
+            _T_CACHE.clear()
+        _T_CACHE[key] = hit
+    return hit
+
+
 def _t_to_host(t) -> Tuple[float, ...]:
-    if torch.is_tensor(t):
-        return tuple(float(v) for v in t.detach().to("cpu", torch.float32).tolist())
-    return tuple(float(v) for v in t)
+    return time_grid_to_host(t, torch.float32)
 
 
 def integrate_fixed(y0, graph: CSRGraph, params: Sequence[torch.Tensor], t, method: str) -> torch.Tensor:
@@ -258,7 +276,7 @@ def integrate_dopri5(y0, graph: CSRGraph, params: Sequence[torch.Tensor], t, rto
     if N != graph.num_nodes:
         raise GnodeError(f"y0 has {N} rows but the graph has {graph.num_nodes} nodes")
     p = _sage3_params(D, H, w)
-    t_host = [float(v) for v in (t.detach().to("cpu", torch.float64).tolist() if torch.is_tensor(t) else t)]
+    t_host = list(time_grid_to_host(t, torch.float64))
     T = len(t_host)
     tarr = (C.c_double * T)(*t_host)
     sol = torch.empty((T, N, D), dtype=torch.float32, device=y0.device)

@@ -155,3 +155,18 @@ def test_spatial_edges_non_integer_positions_bit_exact(cuda):
         want = conv.spatial_edges(pos[s]).numpy()
         assert int(counts[s]) == want.shape[1]
         assert np.array_equal(edges[s, :int(counts[s])].cpu().numpy().T, want)
+
+
+def test_deferred_csr_validation_flags_bad_edges(cuda):
+    """GraphODE builds its CSR without a host synchronisation; an out-of-range edge is skipped on the device and
+    reported by validate() (or by the non-blocking poll of a later call)."""
+    from swarm_ode_b200.graph import CSRGraph
+    ei = torch.tensor([[0, 1, 7], [1, 2, 0]], device=cuda)      # node 7 does not exist (n = 3)
+    with pytest.raises(S.GnodeError, match="outside"):
+        CSRGraph(ei, 3)                                          # synchronous validation (default)
+    g = CSRGraph(ei, 3, validate="deferred")
+    assert g.rowptr.tolist() == [0, 0, 1, 2]                    # the two valid edges survive
+    with pytest.raises(S.GnodeError, match="deferred"):
+        g.validate()
+    ok = CSRGraph(ei[:, :2], 3, validate="deferred")
+    ok.validate()
