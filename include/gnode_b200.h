@@ -195,7 +195,8 @@ int gnode_integrate_fixed(const gnode_graph* g, const gnode_sage3_params* p, int
                           void* workspace, size_t workspace_bytes, gnode_stream_t stream);
 /* Backprop through the solver (discretise-then-optimise, like autograd through torchdiffeq's
  * fixed-grid loop).  sol is the forward output; grad_sol: device [n_t, n_nodes, D] (cotangent of
- * every saved time point); grad_y0 overwritten; param grads accumulated (+=).  With save == NULL
+ * every saved time point); grad_y0 overwritten (NULL = not wanted: its D-wide contraction is skipped); param grads
+ * accumulated (+=).  With save == NULL
  * each step's stages are recomputed from sol[j]; with the forward's save area they are not. */
 int gnode_integrate_fixed_bwd(const gnode_graph* g, const gnode_sage3_params* p, int32_t method,
                               const float* sol, const float* t, int32_t n_t, const float* grad_sol,

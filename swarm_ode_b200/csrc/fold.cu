@@ -315,6 +315,7 @@ int integrate_fixed_folded_bwd(Sage3Ctx& c, FoldWs& f, const Tableau& tb, const 
       l1.out = c.db1; l1.base = c.db1; l1.n = H; l1.n_terms = 1; l1.in[0] = f.cs + H; l1.coef[0] = 1.f;
       GN_TRY(lincomb(l1, s));
     }
+    if (j == 0 && grad_y0 == nullptr) break;   // nobody asked for dL/dy_0: skip its D-wide contraction
     {  // cotangent of y_j:  G + GZ @ w1cat + grad_sol[j]
       GemmNT q{};
       q.A = f.GZ; q.lda = H2; q.B = c.w1catT; q.ldb = H2; q.C = gout; q.ldc = c.D; q.M = N; q.N = c.D; q.K = H2;
@@ -325,7 +326,7 @@ int integrate_fixed_folded_bwd(Sage3Ctx& c, FoldWs& f, const Tableau& tb, const 
     G = gout;
     gout = (gout == f.gcur) ? f.gnext : f.gcur;
   }
-  GN_CUDA(cudaMemcpyAsync(grad_y0, G, sizeof(float) * n, cudaMemcpyDeviceToDevice, s));
+  if (grad_y0) GN_CUDA(cudaMemcpyAsync(grad_y0, G, sizeof(float) * n, cudaMemcpyDeviceToDevice, s));
   {
     GN_PROF(s, 4.0 * H2 * H2 * c.D, 0.0, "fold_param_grads");
     dim3 grid((unsigned)ceil_div64(c.D, 128), (unsigned)(H2 + 1));

@@ -22,25 +22,25 @@ namespace gnode {
 namespace tctn {
 using namespace tc;
 
-constexpr int BKR = 8;                   // node rows per stage
+constexpr int BKR = 8;                   // node rows per K step (tf32 UMMA K = 8); a stage holds KS K steps
 constexpr int MW = 128;                  // M operand width after zero padding
-constexpr int LBO_M = MW * 16 + 16;      // bytes between the two K chunks of an M-operand plane
-constexpr int M_PLANE = 2 * LBO_M;       // 4128
+constexpr int LBO_M = MW * 16 + 16;      // bytes between consecutive 16-byte K chunks of an M-operand plane
 constexpr int CONV_WARPS = 8;
 constexpr int CONV_THREADS = CONV_WARPS * 32;
 constexpr int THREADS = (2 + CONV_WARPS) * 32;   // 320
 constexpr int MAX_RAW = 8, N_OP = 3;
-constexpr int NT_TASKS = 4;              // N-operand tasks per converter thread (2 * 512 / 256)
+constexpr int N_TASKS = 5;               // converter tasks per thread: 2 * KS * (wm + wn) <= N_TASKS * CONV_THREADS
 
 struct Args {
   const float* Am; int wm;     // M operand [rows, wm]
   const float* Bn; int wn;     // N operand [rows, wn]
   int bn, nt;                  // N tile width (multiple of 16, <= 256) and count; nt * bn >= wn
-  int64_t n_kb;                // 8-row blocks in total
+  int ks;                      // K steps (8 node rows each) per stage: 1 for wide operands, 2 / 4 for narrow ones
+  int64_t n_kb;                // stages (8 * ks row blocks) in total
   int n_raw;                   // raw ring depth
   float* partials;             // [gridDim.x][wn][MW]
-  float* colpart_m;            // optional [gridDim.x][2][wm]: per-CTA, per-K-chunk column sums of the M operand
-  float* colpart_n;            // optional [gridDim.x][2][wn]
+  float* colpart_m;            // optional [gridDim.x][2 * ks][wm]: per-CTA, per-K-chunk column sums of the M operand
+  float* colpart_n;            // optional [gridDim.x][2 * ks][wn]
   int* status;
 };
 
@@ -55,12 +55,13 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tn_tc(const Args a) {
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
-  const int wm = a.wm, wn = a.wn, bn = a.bn, nt = a.nt, NR = a.n_raw;
+  const int wm = a.wm, wn = a.wn, bn = a.bn, nt = a.nt, NR = a.n_raw, KS = a.ks;
   int* const status = a.status;
   const int wn_pad = nt * bn;
   const uint32_t lbo_n = (uint32_t)wn_pad * 16u + 16u;
-  const uint32_t n_plane = 2u * lbo_n;
-  const uint32_t raw_m_bytes = 32u * (uint32_t)wm, raw_n_bytes = 32u * (uint32_t)wn;
+  const uint32_t M_PLANE = 2u * (uint32_t)KS * LBO_M;
+  const uint32_t n_plane = 2u * (uint32_t)KS * lbo_n;
+  const uint32_t raw_m_bytes = 32u * (uint32_t)(KS * wm), raw_n_bytes = 32u * (uint32_t)(KS * wn);
   const uint32_t raw_stage = raw_m_bytes + raw_n_bytes;
   const uint32_t op_stage = 2u * M_PLANE + 2u * n_plane;
   const uint32_t smem_base = smem_u32(smem);
@@ -96,11 +97,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tn_tc(const Args a) {
   if (warp == 0) {
     // =========================== producer ===========================
     if (lane == 0) {
-      const float* pm = a.Am + kb0 * (int64_t)(BKR * wm);
-      const float* pn = a.Bn + kb0 * (int64_t)(BKR * wn);
+      const int rows_m = BKR * KS * wm, rows_n = BKR * KS * wn;   // floats per stage
+      const float* pm = a.Am + kb0 * (int64_t)rows_m;
+      const float* pn = a.Bn + kb0 * (int64_t)rows_n;
       uint32_t s = 0, ph = 0;
       bool first_lap = true, ok = true;
-      for (int i = 0; i < nkb && ok; ++i, pm += BKR * wm, pn += BKR * wn) {
+      for (int i = 0; i < nkb && ok; ++i, pm += rows_m, pn += rows_n) {
         if (!first_lap) ok = mbar_wait(smem_u32(&bar_raw_empty[s]), ph ^ 1u, status, 11);
         const uint32_t dst = smem_base + s * raw_stage;
         const uint32_t bar = smem_u32(&bar_raw_full[s]);
@@ -122,15 +124,18 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tn_tc(const Args a) {
       if (lane == 0) {
         const uint32_t m_hi = (smem_base + op_off + so * op_stage) >> 4, m_lo = m_hi + (M_PLANE >> 4);
         const uint32_t n_hi0 = m_hi + ((2u * M_PLANE) >> 4), n_lo0 = n_hi0 + (n_plane >> 4);
-        const uint64_t dmh = desc_m | (uint64_t)m_hi, dml = desc_m | (uint64_t)m_lo;
-        for (int j = 0; j < nt; ++j) {
-          const uint32_t toff = (uint32_t)(j * bn);              // 16 bytes per N row -> bn rows = bn * 16 bytes = bn "16-byte units"
-          const uint64_t dnh = desc_n | (uint64_t)(n_hi0 + toff);
-          const uint64_t dnl = desc_n | (uint64_t)(n_lo0 + toff);
-          const uint32_t d = tmem_base + (uint32_t)(j * bn);
-          umma_tf32(d, dml, dnh, idesc, i > 0 ? 1u : 0u);        // small terms first
-          umma_tf32(d, dmh, dnl, idesc, 1u);
-          umma_tf32(d, dmh, dnh, idesc, 1u);
+        for (int ks = 0; ks < KS; ++ks) {                          // K step ks uses chunks 2ks, 2ks + 1 of every plane
+          const uint32_t am = (uint32_t)ks * ((2u * LBO_M) >> 4), an = (uint32_t)ks * ((2u * lbo_n) >> 4);
+          const uint64_t dmh = desc_m | (uint64_t)(m_hi + am), dml = desc_m | (uint64_t)(m_lo + am);
+          for (int j = 0; j < nt; ++j) {
+            const uint32_t toff = (uint32_t)(j * bn) + an;         // 16 bytes per N row: bn rows = bn 16-byte units
+            const uint64_t dnh = desc_n | (uint64_t)(n_hi0 + toff);
+            const uint64_t dnl = desc_n | (uint64_t)(n_lo0 + toff);
+            const uint32_t d = tmem_base + (uint32_t)(j * bn);
+            umma_tf32(d, dml, dnh, idesc, (i > 0 || ks > 0) ? 1u : 0u);   // small terms first
+            umma_tf32(d, dmh, dnl, idesc, 1u);
+            umma_tf32(d, dmh, dnh, idesc, 1u);
+          }
         }
         umma_commit(smem_u32(&bar_op_empty[so]));
         if (i == nkb - 1) umma_commit(smem_u32(&bar_acc_full));
@@ -141,38 +146,41 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tn_tc(const Args a) {
   } else {
     // =========================== converters ===========================
     const int t = tid - 64;
-    // task 0: M operand, tasks 1..NT_TASKS: N operand.  src in floats from the stage base, dst in bytes from
-    // the operand-stage base (hi plane); the lo plane sits lo_off bytes further.
-    int src[1 + NT_TASKS], pitch[1 + NT_TASKS];
-    uint32_t dst[1 + NT_TASKS], lo_off[1 + NT_TASKS];
+    // Task tau = kc * (wm + wn) + column: K chunk kc (4 node rows) of one column of the M operand (column < wm) or of
+    // the N operand.  src in floats from the raw stage base, dst in bytes from the operand-stage base (hi plane);
+    // the lo plane sits lo_off bytes further.
+    int src[N_TASKS], pitch[N_TASKS];
+    uint32_t dst[N_TASKS], lo_off[N_TASKS];
     uint32_t valid = 0;
-    if (t < 2 * wm) {
-      const int kc = t / wm, m = t - kc * wm;
-      src[0] = 4 * kc * wm + m; pitch[0] = wm;
-      dst[0] = (uint32_t)kc * LBO_M + (uint32_t)m * 16u; lo_off[0] = M_PLANE;
-      valid |= 1u;
-    } else { src[0] = 0; pitch[0] = 0; dst[0] = 0; lo_off[0] = 0; }
+    const int wsum = wm + wn;
 #pragma unroll
-    for (int q = 0; q < NT_TASKS; ++q) {
+    for (int q = 0; q < N_TASKS; ++q) {
       const int task = t + q * CONV_THREADS;
-      if (task < 2 * wn) {
-        const int kc = task / wn, n = task - kc * wn;
-        src[1 + q] = BKR * wm + 4 * kc * wn + n; pitch[1 + q] = wn;
-        dst[1 + q] = 2u * M_PLANE + (uint32_t)kc * lbo_n + (uint32_t)n * 16u; lo_off[1 + q] = n_plane;
-        valid |= 2u << q;
-      } else { src[1 + q] = 0; pitch[1 + q] = 0; dst[1 + q] = 0; lo_off[1 + q] = 0; }
+      src[q] = 0; pitch[q] = 0; dst[q] = 0; lo_off[q] = 0;
+      if (task < 2 * KS * wsum) {
+        const int kc = task / wsum, col = task - kc * wsum;
+        if (col < wm) {
+          src[q] = 4 * kc * wm + col; pitch[q] = wm;
+          dst[q] = (uint32_t)kc * LBO_M + (uint32_t)col * 16u; lo_off[q] = M_PLANE;
+        } else {
+          const int n = col - wm;
+          src[q] = BKR * KS * wm + 4 * kc * wn + n; pitch[q] = wn;
+          dst[q] = 2u * M_PLANE + (uint32_t)kc * lbo_n + (uint32_t)n * 16u; lo_off[q] = n_plane;
+        }
+        valid |= 1u << q;
+      }
     }
-    float csum[1 + NT_TASKS];
+    float csum[N_TASKS];
 #pragma unroll
-    for (int q = 0; q < 1 + NT_TASKS; ++q) csum[q] = 0.f;
+    for (int q = 0; q < N_TASKS; ++q) csum[q] = 0.f;
     uint32_t sr = 0, pr = 0, so = 0, po = 0;
     bool first_lap_o = true, ok = true;
     for (int i = 0; i < nkb && ok; ++i) {
       ok = mbar_wait(smem_u32(&bar_raw_full[sr]), pr, status, 13);
       const float* raw = reinterpret_cast<const float*>(smem + (size_t)sr * raw_stage);
-      float v[1 + NT_TASKS][4];
+      float v[N_TASKS][4];
 #pragma unroll
-      for (int q = 0; q < 1 + NT_TASKS; ++q) {
+      for (int q = 0; q < N_TASKS; ++q) {
         if (valid & (1u << q)) {
 #pragma unroll
           for (int e = 0; e < 4; ++e) v[q][e] = raw[src[q] + e * pitch[q]];
@@ -181,7 +189,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tn_tc(const Args a) {
       if (!first_lap_o) ok = ok && mbar_wait(smem_u32(&bar_op_empty[so]), po ^ 1u, status, 14);
       uint8_t* op = smem + op_off + (size_t)so * op_stage;
 #pragma unroll
-      for (int q = 0; q < 1 + NT_TASKS; ++q) {
+      for (int q = 0; q < N_TASKS; ++q) {
         if (valid & (1u << q)) {
           uint4 h;
           float4 l;
@@ -200,12 +208,15 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tn_tc(const Args a) {
       if (++sr == (uint32_t)NR) { sr = 0; pr ^= 1u; }
       if (++so == (uint32_t)N_OP) { so = 0; po ^= 1u; first_lap_o = false; }
     }
-    // per-CTA column sums: task (kc, column) -> partial [cta][kc][column]
-    if (a.colpart_m && (valid & 1u)) a.colpart_m[(size_t)blockIdx.x * 2 * wm + t] = csum[0];
-    if (a.colpart_n) {
+    // per-CTA column sums: task (kc, column) -> partial [cta][kc][column] of its operand
 #pragma unroll
-      for (int q = 0; q < NT_TASKS; ++q)
-        if (valid & (2u << q)) a.colpart_n[(size_t)blockIdx.x * 2 * wn + t + q * CONV_THREADS] = csum[1 + q];
+    for (int q = 0; q < N_TASKS; ++q) {
+      if (valid & (1u << q)) {
+        const int task = t + q * CONV_THREADS;
+        const int kc = task / wsum, col = task - kc * wsum;
+        if (col < wm) { if (a.colpart_m) a.colpart_m[((size_t)blockIdx.x * 2 * KS + kc) * wm + col] = csum[q]; }
+        else if (a.colpart_n) a.colpart_n[((size_t)blockIdx.x * 2 * KS + kc) * wn + (col - wm)] = csum[q];
+      }
     }
     // =========================== epilogue (warps 2..5: TMEM lane quadrants 2, 3, 0, 1) ===========================
     if (warp < 6 && nkb > 0 && ok) {
@@ -245,21 +256,21 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tn_tc(const Args a) {
 __global__ void k_reduce_tn(const float* __restrict__ partials, int S, int wn, int wm, float* __restrict__ C,
                             int64_t ldc, int n_major, float scale, const float* __restrict__ colpart_m,
                             float* __restrict__ out_m, float scale_m, const float* __restrict__ colpart_n,
-                            float* __restrict__ out_n, float scale_n) {
+                            float* __restrict__ out_n, float scale_n, int ks) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= (int64_t)wn * MW) {
     i -= (int64_t)wn * MW;
     if (i < wm) {
       if (out_m) {
         float s = 0.f;
-        for (int r = 0; r < 2 * S; ++r) s += colpart_m[(size_t)r * wm + i];
+        for (int r = 0; r < 2 * ks * S; ++r) s += colpart_m[(size_t)r * wm + i];
         out_m[i] += scale_m * s;
       }
     } else if (i - wm < wn) {
       i -= wm;
       if (out_n) {
         float s = 0.f;
-        for (int r = 0; r < 2 * S; ++r) s += colpart_n[(size_t)r * wn + i];
+        for (int r = 0; r < 2 * ks * S; ++r) s += colpart_n[(size_t)r * wn + i];
         out_n[i] += scale_n * s;
       }
     }
@@ -274,7 +285,7 @@ __global__ void k_reduce_tn(const float* __restrict__ partials, int S, int wn, i
   *dst += scale * s;
 }
 
-struct Plan { bool ok; bool m_is_b; int wm, wn, bn, nt; int64_t n_kb; int grid; };
+struct Plan { bool ok; bool m_is_b; int wm, wn, bn, nt, ks; int64_t n_kb; int grid; };
 
 Plan plan_for(const GemmTN& g) {
   Plan p{};
@@ -290,7 +301,11 @@ Plan plan_for(const GemmTN& g) {
   p.nt = (npad + 255) / 256;
   p.bn = ((npad + p.nt - 1) / p.nt + 15) & ~15;
   if (p.nt * p.bn > 512) return p;
-  p.n_kb = g.Nrows / BKR;
+  // rows per stage: as many K steps as the converter task budget allows (narrow operands -> fewer, fatter stages)
+  p.ks = 1;
+  while (p.ks < 4 && 2 * (2 * p.ks) * (p.wm + p.wn) <= N_TASKS * CONV_THREADS && g.Nrows >= (int64_t)BKR * 2 * p.ks * kNumSMs)
+    p.ks *= 2;
+  p.n_kb = g.Nrows / (BKR * p.ks);
   p.grid = (int)(p.n_kb < kNumSMs ? p.n_kb : kNumSMs);
   p.ok = true;
   return p;
@@ -305,7 +320,7 @@ bool gemm_tn_tc_supported(const GemmTN& g) { return tctn::plan_for(g).ok; }
 size_t gemm_tn_tc_workspace_floats(int P, int Q) {
   // worst case over both operand roles: kNumSMs partials of [wn][128], plus the column-sum partials [kNumSMs][2][P + Q]
   const int wn = (Q <= tctn::MW && (P > tctn::MW || Q >= P)) ? P : Q;
-  return (size_t)kNumSMs * (size_t)wn * tctn::MW + (size_t)kNumSMs * 2 * (size_t)(P + Q);
+  return (size_t)kNumSMs * (size_t)wn * tctn::MW + (size_t)kNumSMs * 8 * (size_t)(P + Q);
 }
 
 int gemm_tn_simt(const GemmTN& g, float* partials, cudaStream_t s);
@@ -318,16 +333,16 @@ int gemm_tn_tc(const GemmTN& g, float* partials, cudaStream_t s) {
   tctn::Args a;
   a.Am = p.m_is_b ? g.B : g.A; a.wm = p.wm;
   a.Bn = p.m_is_b ? g.A : g.B; a.wn = p.wn;
-  a.bn = p.bn; a.nt = p.nt; a.n_kb = p.n_kb; a.partials = partials; a.status = status_dev;
+  a.bn = p.bn; a.nt = p.nt; a.ks = p.ks; a.n_kb = p.n_kb; a.partials = partials; a.status = status_dev;
   float* const out_m = p.m_is_b ? g.colsumB : g.colsumA;
   float* const out_n = p.m_is_b ? g.colsumA : g.colsumB;
   const float scale_m = p.m_is_b ? g.colsumB_scale : g.colsumA_scale;
   const float scale_n = p.m_is_b ? g.colsumA_scale : g.colsumB_scale;
   float* cp = partials + (size_t)p.grid * (size_t)p.wn * tctn::MW;
   a.colpart_m = out_m ? cp : nullptr;
-  a.colpart_n = out_n ? cp + (size_t)p.grid * 2 * p.wm : nullptr;
-  const size_t raw_stage = 32 * (size_t)(p.wm + p.wn);
-  const size_t op_stage = 2 * (size_t)tctn::M_PLANE + 4 * ((size_t)p.nt * p.bn * 16 + 16);
+  a.colpart_n = out_n ? cp + (size_t)p.grid * 2 * p.ks * p.wm : nullptr;
+  const size_t raw_stage = 32 * (size_t)p.ks * (size_t)(p.wm + p.wn);
+  const size_t op_stage = 4 * (size_t)p.ks * ((size_t)tctn::LBO_M + ((size_t)p.nt * p.bn * 16 + 16));
   const size_t budget = 220 * 1024;
   int n_raw = (int)((budget - tctn::N_OP * op_stage) / raw_stage);
   if (n_raw > tctn::MAX_RAW) n_raw = tctn::MAX_RAW;
@@ -345,10 +360,10 @@ int gemm_tn_tc(const GemmTN& g, float* partials, cudaStream_t s) {
   // C is [P, Q]: with the M operand = B (q = m) the partial index n is p -> rows of C are n
   tctn::k_reduce_tn<<<(unsigned)ceil_div64(cnt, 256), 256, 0, s>>>(partials, p.grid, p.wn, p.wm, g.C, g.ldc,
                                                                     p.m_is_b ? 1 : 0, g.scale, a.colpart_m, out_m, scale_m,
-                                                                    a.colpart_n, out_n, scale_n);
+                                                                    a.colpart_n, out_n, scale_n, p.ks);
   GN_LAUNCHED();
-  const int64_t done = p.n_kb * tctn::BKR;
-  if (done < g.Nrows) {   // up to 7 trailing rows: FFMA kernel, accumulated on top
+  const int64_t done = p.n_kb * tctn::BKR * p.ks;
+  if (done < g.Nrows) {   // trailing rows that do not fill a stage: FFMA kernel, accumulated on top
     GemmTN tail = g;
     tail.A = g.A + done * g.lda; tail.B = g.B + done * g.ldb; tail.Nrows = g.Nrows - done;
     GN_TRY(gemm_tn_simt(tail, partials, s));

@@ -409,7 +409,7 @@ extern "C" int gnode_integrate_fixed_bwd(const gnode_graph* g, const gnode_sage3
   GN_TRY(check_params(p, "gnode_integrate_fixed_bwd"));
   const Tableau* tbp = tableau_for(method);
   GN_ARG(tbp && method != GNODE_DOPRI5, "gnode_integrate_fixed_bwd: method %d is not a fixed-grid solver", method);
-  GN_ARG(sol && t && grad_sol && grad_y0 && n_t >= 1, "gnode_integrate_fixed_bwd: null pointer or empty time grid");
+  GN_ARG(sol && t && grad_sol && n_t >= 1, "gnode_integrate_fixed_bwd: null pointer or empty time grid");
   const Tableau& tb = *tbp;
   const int S = tb.S;
   Sage3Ctx c;
@@ -488,7 +488,7 @@ extern "C" int gnode_integrate_fixed_bwd(const gnode_graph* g, const gnode_sage3
     lc.in[lc.n_terms] = grad_sol + (int64_t)j * n; lc.coef[lc.n_terms] = 1.f; ++lc.n_terms;
     GN_TRY(lincomb(lc, s));
   }
-  GN_CUDA(cudaMemcpyAsync(grad_y0, w.gcur, sizeof(float) * n, cudaMemcpyDeviceToDevice, s));
+  if (grad_y0) GN_CUDA(cudaMemcpyAsync(grad_y0, w.gcur, sizeof(float) * n, cudaMemcpyDeviceToDevice, s));
   if (grads) GN_TRY(c.unpack_grads(*grads, s));
   return GNODE_OK;
 }

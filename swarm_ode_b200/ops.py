@@ -178,7 +178,7 @@ class _IntegrateFixedFn(torch.autograd.Function):
         T, N, D = sol.shape
         H = w[0].shape[0]
         p = _sage3_params(D, H, w)
-        gy0 = torch.empty((N, D), dtype=torch.float32, device=sol.device)
+        gy0 = torch.empty((N, D), dtype=torch.float32, device=sol.device) if ctx.needs_input_grad[0] else None
         gw = [torch.zeros_like(t) for t in w]
         grads = _lib.GnodeSage3Grads(*[t.data_ptr() for t in gw])
         L = _lib.lib()
