@@ -154,6 +154,17 @@ int gnode_sage_bwd(const gnode_graph* g, const float* x, const float* out, const
                    float* grad_x, float* grad_wl, float* grad_bl, float* grad_wr,
                    void* workspace, size_t workspace_bytes, gnode_stream_t stream);
 
+/* Bipartite SAGEConv forward, one HeteroConv relation (scripts/gnode.py:92-99,126-128; scripts/run_gnode.py:89-96):
+ *   out = post( accum + scale * ( mean_{j in N(i)} x_src[j] @ wl^T + bl + x_dst[i] @ wr^T ) ),   post = relu | id
+ * g: CSR whose first n_dst rows are the destination nodes and whose column ids index rows of x_src (build it with
+ * n_nodes >= max(n_src, n_dst)).  accum (may be NULL) / scale fold HeteroConv(aggr='mean') over the relations of one
+ * destination type -- and the ReLU after it -- into the relation calls.  out may alias accum. */
+size_t gnode_sage_bipartite_workspace_bytes(int64_t n_dst, int32_t c_in, int32_t c_out);
+int gnode_sage_bipartite_fwd(const gnode_graph* g, int64_t n_dst, const float* x_src, const float* x_dst,
+                             int32_t c_in, int32_t c_out, const float* wl, const float* bl, const float* wr,
+                             float scale, const float* accum, int32_t post_relu, float* out,
+                             void* workspace, size_t workspace_bytes, gnode_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * The GNODE vector field: three SAGE layers, ReLU between them (GraphODEFunc).
  * ---------------------------------------------------------------------------------------- */

@@ -14,7 +14,7 @@ Everything runs on CPU in plain PyTorch.
 from __future__ import annotations
 
 import math
-from typing import List, Optional
+from typing import Dict, List, Optional, Tuple
 
 import torch
 import torch.nn as nn
@@ -129,14 +129,94 @@ class _PygLinear(nn.Module):
 
 
 class SAGEConvRef(nn.Module):
-    """Parameter layout of PyG ``SAGEConv``: ``lin_l.{weight,bias}``, ``lin_r.weight``."""
+    """Parameter layout of PyG ``SAGEConv``: ``lin_l.{weight,bias}``, ``lin_r.weight``.
 
-    def __init__(self, in_channels: int, out_channels: int):
+    ``in_channels`` may be a pair ``(src, dst)`` and ``x`` a pair ``(x_src, x_dst)`` (bipartite message passing, the
+    form ``HeteroConv`` uses: scripts/gnode.py:92-97): ``lin_l`` acts on the mean of the SOURCE rows gathered per
+    destination, ``lin_r`` on the destination's own row [upstream PyG]."""
+
+    def __init__(self, in_channels, out_channels: int):
         super().__init__()
+        if isinstance(in_channels, int):
+            in_channels = (in_channels, in_channels)
         self.in_channels = in_channels
         self.out_channels = out_channels
-        self.lin_l = _PygLinear(in_channels, out_channels, bias=True)
-        self.lin_r = _PygLinear(in_channels, out_channels, bias=False)
+        self.lin_l = _PygLinear(in_channels[0], out_channels, bias=True)
+        self.lin_r = _PygLinear(in_channels[1], out_channels, bias=False)
 
-    def forward(self, x: torch.Tensor, edge_index: torch.Tensor) -> torch.Tensor:
-        return sage_conv_ref(x, edge_index, self.lin_l.weight, self.lin_l.bias, self.lin_r.weight)
+    def forward(self, x, edge_index: torch.Tensor) -> torch.Tensor:
+        if isinstance(x, torch.Tensor):
+            return sage_conv_ref(x, edge_index, self.lin_l.weight, self.lin_l.bias, self.lin_r.weight)
+        x_src, x_dst = x
+        src, dst = edge_index[0], edge_index[1]
+        agg = scatter_mean_ref(x_src.index_select(0, src), dst, x_dst.size(0))
+        out = torch.nn.functional.linear(agg, self.lin_l.weight, self.lin_l.bias)
+        return out + torch.nn.functional.linear(x_dst, self.lin_r.weight)
+
+
+class HeteroConvRef(nn.Module):
+    """``torch_geometric.nn.HeteroConv(convs, aggr='mean')`` [upstream]: for every edge type present in BOTH the
+    module dict and ``edge_index_dict`` (and whose node types are in ``x_dict``), run its conv on
+    ``(x_src, x_dst)`` (or ``x`` when src == dst); outputs of the same destination type are stacked and reduced with
+    ``mean``.  Destination types that receive nothing are absent from the result."""
+
+    def __init__(self, convs: Dict[Tuple[str, str, str], nn.Module], aggr: str = "mean"):
+        super().__init__()
+        assert aggr == "mean"
+        self.edge_types = list(convs.keys())
+        self.convs = nn.ModuleDict({"__".join(k): v for k, v in convs.items()})
+
+    def forward(self, x_dict, edge_index_dict):
+        outs: Dict[str, List[torch.Tensor]] = {}
+        for et in self.edge_types:
+            src, _rel, dst = et
+            if et not in edge_index_dict or src not in x_dict or dst not in x_dict:
+                continue
+            conv = self.convs["__".join(et)]
+            ei = edge_index_dict[et]
+            out = conv(x_dict[src], ei) if src == dst else conv((x_dict[src], x_dict[dst]), ei)
+            outs.setdefault(dst, []).append(out)
+        return {k: torch.stack(v, dim=0).mean(dim=0) for k, v in outs.items()}
+
+
+class _Store:
+    """Attribute bag of one node / edge type of ``RefHeteroData``."""
+
+    def __init__(self):
+        self.__dict__["_d"] = {}
+
+    def __getattr__(self, k):
+        try:
+            return self.__dict__["_d"][k]
+        except KeyError:
+            raise AttributeError(k)
+
+    def __setattr__(self, k, v):
+        self.__dict__["_d"][k] = v
+
+    @property
+    def num_nodes(self) -> int:
+        return int(self.__dict__["_d"]["x"].size(0))
+
+
+class RefHeteroData:
+    """Minimal stand-in for ``torch_geometric.data.HeteroData``: ``data['agv'].x``,
+    ``data['agv', 'targets', 'location'].edge_index``, ``data.edge_index_dict``."""
+
+    def __init__(self):
+        self._stores: Dict[object, _Store] = {}
+
+    def __getitem__(self, key):
+        if isinstance(key, list):
+            key = tuple(key)
+        if key not in self._stores:
+            self._stores[key] = _Store()
+        return self._stores[key]
+
+    @property
+    def edge_index_dict(self):
+        return {k: s.edge_index for k, s in self._stores.items() if isinstance(k, tuple) and "edge_index" in s.__dict__["_d"]}
+
+    @property
+    def node_types(self):
+        return [k for k in self._stores if isinstance(k, str)]

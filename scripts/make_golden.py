@@ -168,8 +168,78 @@ def golden_graph_ode(ref):
     print("graph_ode.npz:", len(out), "arrays")
 
 
+def reference_classes(rel_path, names):
+    """The reference's hetero scripts cannot be imported (module-level argparse / gym / rware code), so the class
+    definitions are taken from the file by name and executed with the stand-ins in scope.  Nothing is copied into the
+    repository: the source text is read from /root/reference at generation time."""
+    import ast
+    import torch.nn as nn
+    from oracle.pyg_ref import HeteroConvRef, SAGEConvRef
+    from oracle.torchdiffeq_ref import odeint_ref
+    path = os.path.join(REF, rel_path)
+    src = open(path).read()
+    tree = ast.parse(src)
+    ns = {"torch": torch, "nn": nn, "SAGEConv": SAGEConvRef, "HeteroConv": HeteroConvRef, "odeint": odeint_ref}
+    for node in tree.body:
+        if isinstance(node, ast.ClassDef) and node.name in names:
+            exec(compile(ast.Module(body=[node], type_ignores=[]), path, "exec"), ns)
+    return ns
+
+
+def hetero_case(seed=3, n_agv=6, n_pick=3, n_loc=20, dims=(11, 8, 5)):
+    from oracle.pyg_ref import RefHeteroData
+    g = torch.Generator().manual_seed(seed)
+    d = RefHeteroData()
+    d["agv"].x = torch.randn(n_agv, dims[0], generator=g)
+    d["picker"].x = torch.randn(n_pick, dims[1], generator=g)
+    d["location"].x = torch.randn(n_loc, dims[2], generator=g)
+    tgt = torch.randint(0, n_loc, (n_agv,), generator=g)
+    ar = torch.arange(n_agv)
+    d["agv", "targets", "location"].edge_index = torch.stack([ar, tgt])
+    d["location", "is targeted by", "agv"].edge_index = torch.stack([tgt, ar])
+    pairs = [(i, j) for i in range(n_agv) for j in range(n_agv) if i != j and (i + j) % 3 == 0]
+    d["agv", "communicates", "agv"].edge_index = torch.tensor(pairs).t().contiguous()
+    mg = torch.randint(0, n_pick, (n_loc,), generator=g)
+    d["picker", "manages", "location"].edge_index = torch.stack([mg, torch.arange(n_loc)])
+    coop = torch.randint(0, n_pick, (n_agv,), generator=g)
+    d["agv", "cooperates with", "picker"].edge_index = torch.stack([ar, coop])     # picker 'coop' may receive several AGVs
+    d["picker", "helps", "agv"].edge_index = torch.stack([coop[:4], ar[:4]])       # AGVs 4, 5 get no help edge
+    return d
+
+
+def golden_hetero():
+    out = {}
+    d = hetero_case()
+    for k in ("agv", "picker", "location"):
+        out[f"x/{k}"] = d[k].x.numpy()
+    for et, ei in d.edge_index_dict.items():
+        out["edge/" + "__".join(et)] = ei.numpy()
+    dims = {"agv": 11, "picker": 8, "location": 5}
+    for tag, rel, kwargs in (("joint", "scripts/gnode.py", dict(hidden_dim=32, num_layers=2, ode_hidden_dim=16)),
+                             ("typed", "scripts/run_gnode.py", dict(action_size=5, hidden_dim=32, num_layers=2, ode_hidden_dim=16))):
+        ns = reference_classes(rel, {"HeteroGraphODENetwork", "ODEFunction"})
+        torch.manual_seed(21)
+        model = ns["HeteroGraphODENetwork"](dims, **kwargs)
+        with torch.no_grad():
+            for p in model.parameters():      # damp the MLP field a little so that default-tolerance dopri5 stays cheap
+                p.mul_(0.7)
+            res = model(d, integration_time=1.0 if tag == "typed" else 0.5)
+        for k, v in model.state_dict().items():
+            out[f"{tag}/param/{k}"] = v.numpy()
+        for k, v in res.items():
+            out[f"{tag}/{k}"] = v.numpy()
+    np.savez_compressed(os.path.join(OUT, "hetero.npz"), **out)
+    print("hetero.npz:", len(out), "arrays")
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    ref = import_reference_train_gde()
-    golden_converter(ref)
-    golden_graph_ode(ref)
+    which = sys.argv[1:] or ["converter", "graph_ode", "hetero"]
+    if "converter" in which or "graph_ode" in which:
+        ref = import_reference_train_gde()
+        if "converter" in which:
+            golden_converter(ref)
+        if "graph_ode" in which:
+            golden_graph_ode(ref)
+    if "hetero" in which:
+        golden_hetero()

@@ -11,6 +11,7 @@ from .data import (Batch, Data, GraphConverter, TrajectoryBatch, collate_traject
 from .graph import CSRGraph, csr_for  # noqa: F401
 from .modules import GraphODE, GraphODEFunc, ODEFunction, SAGEConv, BoundGraphODEFunc  # noqa: F401
 from .odeint import odeint  # noqa: F401
+from .hetero import HeteroData, HeteroConv, HeteroGraphODENetwork  # noqa: F401
 from . import ops, synthetic  # noqa: F401
 
 __all__ = [
@@ -19,5 +20,6 @@ __all__ = [
     "extract_positions_from_graph", "spatial_edges_cuda",
     "CSRGraph", "csr_for",
     "GraphODE", "GraphODEFunc", "ODEFunction", "SAGEConv", "BoundGraphODEFunc",
+    "HeteroData", "HeteroConv", "HeteroGraphODENetwork",
     "odeint", "ops", "synthetic",
 ]

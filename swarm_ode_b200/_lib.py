@@ -82,6 +82,9 @@ _SIGNATURES = {
                                  C.c_size_t, _P]),
     "gnode_sage_bwd": (C.c_int, [C.POINTER(GnodeGraph), _P, _P, _P, C.c_int32, C.c_int32, _P, _P, C.c_int32, _P, _P,
                                  _P, _P, _P, C.c_size_t, _P]),
+    "gnode_sage_bipartite_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int32, C.c_int32]),
+    "gnode_sage_bipartite_fwd": (C.c_int, [C.POINTER(GnodeGraph), C.c_int64, _P, _P, C.c_int32, C.c_int32, _P, _P, _P,
+                                           C.c_float, _P, C.c_int32, _P, _P, C.c_size_t, _P]),
     "gnode_rhs_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int32, C.c_int32]),
     "gnode_rhs_fwd": (C.c_int, [C.POINTER(GnodeGraph), C.POINTER(GnodeSage3Params), _P, _P, _P, C.c_size_t, _P]),
     "gnode_rhs_bwd": (C.c_int, [C.POINTER(GnodeGraph), C.POINTER(GnodeSage3Params), _P, _P, _P,

@@ -94,8 +94,8 @@ int current_fold();
 
 // ---- dense contractions (gemm_simt.cu / gemm_tc.cu) ----
 // C[m, n] = epi( sum_k A[m, k] * B[n, k] )          (both operands K-contiguous, "NT")
-//   epi(v) = base_scale * base[m, n] + base2[m, n] + scale * act(v + bias_scale * bias[n])
-//   with act (field `relu`) = 0 identity, 1 relu, 2 tanh; bias / base / base2 may be null.
+//   epi(v) = post( base_scale * base[m, n] + base2[m, n] + scale * act(v + bias_scale * bias[n]) )
+//   with act (field `relu`) = 0 identity, 1 relu, 2 tanh; post = relu when post_relu; bias / base / base2 may be null.
 //   lda/ldb/ldc/ldbase/ldbase2 are row strides in elements.
 struct GemmNT {
   const float* A; int64_t lda;
@@ -109,6 +109,7 @@ struct GemmNT {
   float bias_scale = 1.0f;
   float base_scale = 1.0f;
   const float* base2 = nullptr; int64_t ldbase2 = 0;
+  int post_relu = 0;               // ReLU applied to the final value (after the base terms)
   const float* Bsplit = nullptr;   // optional: B pre-split into tf32 hi/lo planes (presplit_weights) -> tcgen05 engine
 };
 int gemm_nt(const GemmNT& g, cudaStream_t s);

@@ -29,6 +29,7 @@ struct SgemmArgs {
   float scale;
   float bias_scale, base_scale;
   const float* base2; int64_t ldbase2;
+  int post_relu;
 };
 
 template <bool TRANS>
@@ -148,6 +149,7 @@ __global__ void __launch_bounds__(THREADS) k_sgemm(const SgemmArgs a) {
       v *= a.scale;
       if (a.base) v += a.base_scale * __ldg(a.base + m * a.ldbase + n);
       if (a.base2) v += __ldg(a.base2 + m * a.ldbase2 + n);
+      if (a.post_relu) v = fmaxf(v, 0.f);
       C[m * a.ldc + n] = v;
     }
   }
@@ -215,6 +217,7 @@ int gemm_nt_simt(const GemmNT& g, cudaStream_t s) {
   a.M = g.M; a.N = g.N; a.K = g.K; a.kchunk = g.K > 0 ? g.K : 1; a.c_split_stride = 0;
   a.bias = g.bias; a.relu = g.relu; a.base = g.base; a.ldbase = g.ldbase; a.scale = g.scale;
   a.bias_scale = g.bias_scale; a.base_scale = g.base_scale; a.base2 = g.base2; a.ldbase2 = g.ldbase2;
+  a.post_relu = g.post_relu;
   dim3 grid((unsigned)ceil_div64(g.M, BM), (unsigned)ceil_div64(g.N, BN), 1);
   k_sgemm<false><<<grid, THREADS, 0, s>>>(a);
   GN_LAUNCHED();
@@ -236,7 +239,7 @@ int gemm_tn_simt(const GemmTN& g, float* partials, cudaStream_t s) {
   a.A = g.A; a.lda = g.lda; a.B = g.B; a.ldb = g.ldb; a.C = partials; a.ldc = g.Q;
   a.M = g.P; a.N = g.Q; a.K = g.Nrows; a.kchunk = kchunk; a.c_split_stride = (int64_t)g.P * g.Q;
   a.bias = nullptr; a.relu = 0; a.base = nullptr; a.ldbase = 0; a.scale = 1.f;
-  a.bias_scale = 1.f; a.base_scale = 1.f; a.base2 = nullptr; a.ldbase2 = 0;
+  a.bias_scale = 1.f; a.base_scale = 1.f; a.base2 = nullptr; a.ldbase2 = 0; a.post_relu = 0;
   dim3 grid((unsigned)ceil_div64(g.P, BM), (unsigned)ceil_div64(g.Q, BN), (unsigned)S);
   k_sgemm<true><<<grid, THREADS, 0, s>>>(a);
   GN_LAUNCHED();

@@ -67,6 +67,7 @@ struct Args {
   float scale;
   float bias_scale, base_scale;
   const float* base2; int64_t ldbase2;
+  int post_relu;
   int* status;
 };
 
@@ -75,7 +76,7 @@ struct Args {
 template <int ACT, int HAS_BASE>
 __device__ __forceinline__ void store_rows(const float* __restrict__ stg, int lane, float bv, float scale, float* crow,
                                            int64_t ldc, const float* brow, int64_t ldbase, float base_scale,
-                                           const float* b2row, int64_t ldbase2, int rmax, bool cin) {
+                                           const float* b2row, int64_t ldbase2, int rmax, bool cin, bool post_relu) {
   float bs[32];
   if (HAS_BASE >= 1) {
 #pragma unroll
@@ -94,6 +95,7 @@ __device__ __forceinline__ void store_rows(const float* __restrict__ stg, int la
     x *= scale;
     if (HAS_BASE >= 1) x += base_scale * bs[u];
     if (HAS_BASE == 2) x += b2[u];
+    if (post_relu) x = fmaxf(x, 0.f);
     if (cin && u < rmax) crow[(int64_t)u * ldc] = x;
   }
 }
@@ -310,6 +312,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
     const int64_t ldc = a.ldc, ldbase = a.ldbase, ldbase2 = a.ldbase2, M = a.M;
     const int N = a.N, act = a.act;
     const float scale = a.scale, bias_scale = a.bias_scale, base_scale = a.base_scale;
+    const bool post_relu = a.post_relu != 0;
     uint32_t tc = 0;
     bool ok = true;
     for (int64_t t = tile0; t < total_tiles && ok; t += tstep, ++tc) {
@@ -341,7 +344,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
         float* crow = Cp + m0 * ldc + col;
         const float* brow = basep ? basep + m0 * ldbase + col : nullptr;
         const float* b2row = base2p ? base2p + m0 * ldbase2 + col : nullptr;
-#define GN_STORE(ACT_, HB_) store_rows<ACT_, HB_>(stg, lane, bv, scale, crow, ldc, brow, ldbase, base_scale, b2row, ldbase2, rmax, cin)
+#define GN_STORE(ACT_, HB_) store_rows<ACT_, HB_>(stg, lane, bv, scale, crow, ldc, brow, ldbase, base_scale, b2row, ldbase2, rmax, cin, post_relu)
         if (basep && base2p) {
           if (act == 0) GN_STORE(0, 2); else if (act == 1) GN_STORE(1, 2); else GN_STORE(2, 2);
         } else if (basep) {
@@ -459,7 +462,7 @@ int gemm_nt_tc(const GemmNT& g, cudaStream_t s) {
   a.m_tiles = ceil_div64(M_tc, tc::BM);
   a.bias = g.bias; a.act = g.relu; a.base = g.base; a.ldbase = g.ldbase; a.scale = g.scale;
   a.bias_scale = g.bias_scale; a.base_scale = g.base_scale;
-  a.base2 = g.base ? g.base2 : nullptr; a.ldbase2 = g.ldbase2;
+  a.base2 = g.base ? g.base2 : nullptr; a.ldbase2 = g.ldbase2; a.post_relu = g.post_relu;
   a.status = status_dev;
   // shared-memory plan: A-operand ring (3) + B ring (4, or 3 for wide tiles) + staging, the rest is the raw ring
   const size_t img = 2 * (size_t)tc::CHUNKS * ((size_t)a.bn * 16 + 16);

@@ -118,3 +118,56 @@ extern "C" int gnode_sage_bwd(const gnode_graph* g, const float* x, const float*
   if (grad_bl) GN_TRY(colsum_accum(gm, co, N, co, grad_bl, 1.f, w.colpart, s));
   return GNODE_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Bipartite SAGEConv forward, the form HeteroConv runs per relation (scripts/gnode.py:92-99, 126-128):
+//   out = post( accum + scale * ( [mean_{j in N(i)} x_src[j] | x_dst[i]] @ [wl | wr]^T + bl ) )
+// `accum` / `scale` let the caller fold HeteroConv's mean over the relations of one destination type (and the ReLU
+// that follows it) into the last relation's epilogue.
+// ------------------------------------------------------------------------------------------------
+namespace gnode {
+namespace {
+struct BipWs { float *wcat, *cat, *planes; };
+void carve_bip(Arena& a, int64_t n_dst, int ci, int co, BipWs& w) {
+  w.wcat = a.take<float>((size_t)co * 2 * ci);
+  w.cat = a.take<float>((size_t)n_dst * 2 * ci);
+  w.planes = a.take<float>(presplit_floats(co, 2 * ci));
+}
+}  // namespace
+}  // namespace gnode
+
+extern "C" size_t gnode_sage_bipartite_workspace_bytes(int64_t n_dst, int32_t c_in, int32_t c_out) {
+  Arena a(nullptr, 0);
+  BipWs w;
+  carve_bip(a, n_dst, c_in, c_out, w);
+  return a.off;
+}
+
+extern "C" int gnode_sage_bipartite_fwd(const gnode_graph* g, int64_t n_dst, const float* x_src, const float* x_dst,
+                                        int32_t ci, int32_t co, const float* wl, const float* bl, const float* wr,
+                                        float scale, const float* accum, int32_t post_relu, float* out,
+                                        void* workspace, size_t workspace_bytes, gnode_stream_t stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  GN_ARG(g != nullptr && g->rowptr != nullptr && (g->n_edges == 0 || g->col != nullptr), "gnode_sage_bipartite_fwd: bad graph");
+  GN_ARG(n_dst > 0 && n_dst <= g->n_nodes, "gnode_sage_bipartite_fwd: n_dst must be in (0, graph rows]");
+  GN_ARG(ci > 0 && co > 0 && x_src && x_dst && wl && wr && out, "gnode_sage_bipartite_fwd: bad argument");
+  Arena a(workspace, workspace_bytes);
+  BipWs w;
+  carve_bip(a, n_dst, ci, co, w);
+  GN_ARENA_OK(a, "gnode_sage_bipartite_fwd");
+  gnode_graph gd = *g;
+  gd.n_nodes = n_dst;   // rows = destination nodes; column ids index x_src
+  PackSegHost sg[3] = {{w.wcat, wl, co, ci, ci, 2 * ci, 0, 0},
+                       {w.wcat + ci, wr, co, ci, ci, 2 * ci, 0, 0},
+                       {w.cat + ci, x_dst, (int)n_dst, ci, ci, 2 * ci, 0, 0}};
+  GN_TRY(pack_segments(sg, 3, s));
+  GN_TRY(agg_mean_fwd(gd, x_src, ci, w.cat, 2 * ci, ci, nullptr, 0, nullptr, 0, s));
+  GemmNT q{};
+  q.A = w.cat; q.lda = 2 * ci; q.B = w.wcat; q.ldb = 2 * ci; q.C = out; q.ldc = co; q.M = n_dst; q.N = co; q.K = 2 * ci;
+  q.bias = bl; q.scale = scale; q.base = accum; q.ldbase = co; q.post_relu = post_relu ? 1 : 0;
+  if (current_engine() != GNODE_ENGINE_SIMT) {
+    GN_TRY(presplit_weights(w.wcat, co, 2 * ci, 2 * ci, w.planes, s));
+    q.Bsplit = w.planes;
+  }
+  return gemm_nt(q, s);
+}

@@ -52,7 +52,8 @@ class SAGEConv(nn.Module):
     def __init__(self, in_channels: int, out_channels: int, aggr: str = "mean", normalize: bool = False,
                  root_weight: bool = True, project: bool = False, bias: bool = True):
         super().__init__()
-        if isinstance(in_channels, (tuple, list)):
+        self.bipartite = isinstance(in_channels, (tuple, list))   # used on (x_src, x_dst) pairs by HeteroConv
+        if self.bipartite:
             if in_channels[0] != in_channels[1]:
                 raise NotImplementedError("bipartite SAGEConv with different source/target widths")
             in_channels = in_channels[0]

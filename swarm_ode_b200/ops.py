@@ -23,6 +23,23 @@ _f32 = _lib.require_cuda_f32
 SAVE_FRACTION = 0.5
 
 
+_TOTAL_MEM: dict = {}
+
+
+def _save_fits(nbytes: int, device) -> bool:
+    """Keep the forward's intermediates when they take at most SAVE_FRACTION of the free device memory.  Small save
+    areas (< 1/16 of the device) skip the driver query: cudaMemGetInfo is a synchronous driver call per step."""
+    if SAVE_FRACTION <= 0.0:
+        return False
+    key = str(device)
+    if key not in _TOTAL_MEM:
+        _TOTAL_MEM[key] = torch.cuda.get_device_properties(device).total_memory
+    if SAVE_FRACTION >= 0.25 and nbytes <= _TOTAL_MEM[key] // 16:
+        return True
+    free, _total = torch.cuda.mem_get_info(device)
+    return nbytes <= SAVE_FRACTION * free
+
+
 def _ws(nbytes: int, device) -> torch.Tensor:
     return _lib.WORKSPACE.get(nbytes, device)
 
@@ -158,8 +175,7 @@ class _IntegrateFixedFn(torch.autograd.Function):
         save = None
         if any(ctx.needs_input_grad) and T >= 2:
             nbytes = int(L.gnode_integrate_fixed_save_bytes(N, D, H, method, T))
-            free, _total = torch.cuda.mem_get_info(y0.device)
-            if 0 < nbytes <= SAVE_FRACTION * free:
+            if nbytes > 0 and _save_fits(nbytes, y0.device):
                 save = torch.empty(nbytes, dtype=torch.uint8, device=y0.device)
         with torch.cuda.device(y0.device):
             _lib.check(L.gnode_integrate_fixed(graph.ref(), C.byref(p), method, _lib.ptr(y0), tarr, T, _lib.ptr(sol),

@@ -1,0 +1,106 @@
+"""HeteroGraphODENetwork (scripts/gnode.py:70-158 and scripts/run_gnode.py:67-151): golden vectors produced by the
+reference's own class definitions (scripts/make_golden.py executes them with SAGEConv / HeteroConv / odeint replaced by
+the oracle's restatements) against the oracle restatement (CPU, bit-exact) and the CUDA path (GPU, rel-L2 <= 1e-4)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import swarm_ode_b200 as S
+from oracle.gnode_ref import EDGE_TYPES, HeteroGraphODENetworkRef
+from oracle.pyg_ref import RefHeteroData
+from tests._util import FIXED_TOL, rel_l2
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "hetero.npz")
+DIMS = {"agv": 11, "picker": 8, "location": 5}
+CASES = {"joint": dict(action_size=None, t=0.5), "typed": dict(action_size=5, t=1.0)}
+KEYS = ["agv_q_values", "picker_q_values", "agv_embeddings", "picker_embeddings", "location_embeddings"]
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(GOLDEN)
+
+
+def _data(gold, cls):
+    d = cls()
+    for k in ("agv", "picker", "location"):
+        d[k].x = torch.from_numpy(gold[f"x/{k}"])
+    for et in EDGE_TYPES:
+        d[et].edge_index = torch.from_numpy(gold["edge/" + "__".join(et)])
+    return d
+
+
+def _model(gold, cls, tag):
+    m = cls(DIMS, action_size=CASES[tag]["action_size"], hidden_dim=32, num_layers=2, ode_hidden_dim=16)
+    sd = {k[len(tag) + 7:]: torch.from_numpy(gold[k]) for k in gold.files if k.startswith(f"{tag}/param/")}
+    m.load_state_dict(sd)     # the reference module's state_dict keys load unchanged
+    return m
+
+
+@pytest.mark.parametrize("tag", list(CASES))
+def test_oracle_matches_reference_class(gold, tag):
+    m = _model(gold, HeteroGraphODENetworkRef, tag)
+    with torch.no_grad():
+        out = m(_data(gold, RefHeteroData), integration_time=CASES[tag]["t"])
+    assert list(out) == KEYS
+    for k in KEYS:
+        assert np.array_equal(out[k].numpy(), gold[f"{tag}/{k}"]), k
+
+
+def test_hetero_conv_skips_absent_relations_cpu_semantics():
+    """A relation missing from edge_index_dict contributes nothing; a destination type without any relation is dropped."""
+    from oracle.pyg_ref import HeteroConvRef, SAGEConvRef
+    convs = {et: SAGEConvRef(4 if et[0] == et[2] else (4, 4), 4) for et in EDGE_TYPES}
+    hc = HeteroConvRef(convs)
+    x = {"agv": torch.randn(3, 4), "picker": torch.randn(2, 4), "location": torch.randn(5, 4)}
+    out = hc(x, {("agv", "communicates", "agv"): torch.tensor([[0], [1]])})
+    assert list(out) == ["agv"] and out["agv"].shape == (3, 4)
+
+
+def test_forward_only_module_raises_under_autograd():
+    m = S.HeteroGraphODENetwork(DIMS, hidden_dim=16, ode_hidden_dim=8)
+    with pytest.raises(S.GnodeError, match="forward-only"):
+        m(S.HeteroData())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("engine", ["simt", "auto"])
+@pytest.mark.parametrize("tag", list(CASES))
+def test_cuda_matches_reference_class(cuda, gold, tag, engine):
+    prev = S.set_engine(engine)
+    try:
+        m = _model(gold, S.HeteroGraphODENetwork, tag).to(cuda)
+        d = _data(gold, S.HeteroData).to(cuda)
+        with torch.no_grad():
+            out = m(d, integration_time=CASES[tag]["t"])
+        assert list(out) == KEYS
+        for k in KEYS:
+            want = torch.from_numpy(gold[f"{tag}/{k}"])
+            assert out[k].shape == want.shape
+            assert rel_l2(out[k], want) <= FIXED_TOL, (k, rel_l2(out[k], want))
+    finally:
+        S.set_engine(prev)
+
+
+@pytest.mark.gpu
+def test_cuda_hetero_conv_without_some_relations(cuda):
+    """Relations absent from edge_index_dict are skipped (PyG semantics): compare against the oracle."""
+    from oracle.pyg_ref import HeteroConvRef, SAGEConvRef
+    torch.manual_seed(0)
+    H = 16
+    convs = {et: S.SAGEConv(H if et[0] == et[2] else (H, H), H) for et in EDGE_TYPES}
+    hc = S.HeteroConv(convs)
+    ref = HeteroConvRef({et: SAGEConvRef(H if et[0] == et[2] else (H, H), H) for et in EDGE_TYPES})
+    ref.load_state_dict(hc.state_dict())
+    x = {"agv": torch.randn(7, H), "picker": torch.randn(3, H), "location": torch.randn(40, H)}
+    eid = {("agv", "targets", "location"): torch.stack([torch.arange(7), torch.randint(0, 40, (7,))]),
+           ("picker", "manages", "location"): torch.stack([torch.randint(0, 3, (40,)), torch.arange(40)]),
+           ("agv", "communicates", "agv"): torch.tensor([[0, 1, 2, 2], [1, 0, 0, 6]])}
+    with torch.no_grad():
+        want = ref(x, eid)
+        got = hc.to(cuda)({k: v.to(cuda) for k, v in x.items()}, {k: v.to(cuda) for k, v in eid.items()})
+    assert set(got) == set(want) == {"location", "agv"}
+    for k in want:
+        assert rel_l2(got[k], want[k]) <= 1e-5, k
