@@ -280,7 +280,15 @@ __global__ void k_reduce_tn(const float* __restrict__ partials, int S, int wn, i
   if (m >= wm) return;
   float s = 0.f;
   const size_t stride = (size_t)wn * MW;
-  for (int c = 0; c < S; ++c) s += partials[c * stride + i];
+  int c = 0;
+  for (; c + 8 <= S; c += 8) {   // eight independent loads in flight; the additions keep the fixed order
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = __ldg(partials + (size_t)(c + u) * stride + i);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) s += v[u];
+  }
+  for (; c < S; ++c) s += __ldg(partials + (size_t)c * stride + i);
   float* dst = n_major ? C + (int64_t)n * ldc + m : C + (int64_t)m * ldc + n;
   *dst += scale * s;
 }
