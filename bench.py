@@ -271,6 +271,8 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         b = S.Batch(x=host.x.to(dev, non_blocking=non_blocking), edge_index=host.edge_index.to(dev, non_blocking=non_blocking))
         b.batch = host.batch.to(dev, non_blocking=non_blocking)
         b.is_current_agent = host.is_current_agent.to(dev, non_blocking=non_blocking)
+        b.ptr = host.ptr.to(dev, non_blocking=non_blocking)          # graph offsets (PyG Batch.ptr)
+        b.num_graphs, b.max_graph_nodes = host.num_graphs, host.max_graph_nodes
         return b, nxt_host.to(dev, non_blocking=non_blocking)
 
     resident, nxt_res = to_device(False)
@@ -382,7 +384,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_ms = float(te) / args.steps
     e2e_value = units_per_step_rank * world / (e2e_ms * 1e-3)
-    h2d = sum(t.numel() * t.element_size() for t in (host.x, host.edge_index, host.batch, host.is_current_agent, nxt_host))
+    h2d = sum(t.numel() * t.element_size() for t in (host.x, host.edge_index, host.batch, host.is_current_agent, host.ptr, nxt_host))
 
     if rank != 0:
         return

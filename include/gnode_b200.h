@@ -99,7 +99,17 @@ typedef struct {
   const int32_t* col;      /* device [n_edges]    source node ids                                 */
   const int32_t* t_rowptr; /* device [n_nodes+1]  out-edges of node j                             */
   const int32_t* t_col;    /* device [n_edges]    destination node ids                            */
+  /* optional (NULL = absent): tiling of the rows into runs of WHOLE graphs of at most 128 rows, from
+   * gnode_tiles_build; lets the integrators run their per-stage chain graph-resident (csrc/chain_fwd.cu).
+   * tile_err: device int32 set to 1 if an edge is found to leave its tile (the batch was not a disjoint union). */
+  const int32_t* tiles;
+  int32_t* tile_err;
 } gnode_graph;
+
+/* tiles: device int32 [n_graphs + 2]; graph_ptr: device int64 [n_graphs + 1] node offsets of the graphs of a batch
+ * (PyG `Batch.ptr`).  tiles[0] = number of tiles (-1 if a graph has more than 128 nodes), tiles[1 + t] = first row of
+ * tile t.  Does not synchronise. */
+int gnode_tiles_build(const int64_t* graph_ptr, int64_t n_graphs, int32_t* tiles, gnode_stream_t stream);
 
 size_t gnode_csr_workspace_bytes(int64_t n_nodes, int64_t n_edges);
 /* edge_index: device int64 [2, n_edges] (row 0 = source j, row 1 = destination i), any order,

@@ -31,6 +31,8 @@ struct Field {
 // ---- GraphODEFunc: three SAGE layers (scripts/train_gde.py:20-45) ----
 struct Sage3Ctx : Field {
   gnode_graph g{};
+  const int32_t* g_tiles = nullptr;    // whole-graph row tiles (gnode_graph.tiles), null when the batch has none
+  int32_t* g_tile_err = nullptr;
   int D = 0, H = 0;
   int64_t N = 0;
   const float *b1 = nullptr, *b2 = nullptr, *b3 = nullptr;
@@ -88,6 +90,9 @@ int integrate_fixed_folded(Sage3Ctx& c, FoldWs& f, const Tableau& tb, const floa
 int integrate_fixed_folded_bwd(Sage3Ctx& c, FoldWs& f, const Tableau& tb, const float* sol, const float* t, int n_t,
                                const float* grad_sol, float* grad_y0, const float* save, cudaStream_t s);
 int current_fold();
+// graph-resident forward chain of the folded stages (chain_fwd.cu)
+bool chain_fwd_supported(const Sage3Ctx& c);
+int chain_fwd(Sage3Ctx& c, FoldWs& f, const Tableau& tb, float dt, cudaStream_t s);
 
 int check_graph(const gnode_graph* g, const char* who);
 int check_params(const gnode_sage3_params* p, const char* who);

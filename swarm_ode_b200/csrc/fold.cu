@@ -145,6 +145,7 @@ int FoldWs::forward_stages(Sage3Ctx& c, const Tableau& tb, const float* y, float
     q.Bsplit = c.use_tc ? c.s1 : nullptr;
     GN_TRY(gemm_nt(q, s));
   }
+  if (chain_fwd_supported(c)) return chain_fwd(c, *this, tb, dt, s);   // all stages of the step, graph-resident
   for (int st = 0; st < S; ++st) {
     const float* z = z0;
     if (st > 0) {

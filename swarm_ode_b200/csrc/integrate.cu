@@ -375,7 +375,7 @@ extern "C" int gnode_integrate_fixed(const gnode_graph* g, const gnode_sage3_par
   for (int j = 0; j + 1 < n_t; ++j)
     GN_ARG(t[j + 1] > t[j], "gnode_integrate_fixed: t must be strictly increasing");
   Sage3Ctx c;
-  c.g = *g; c.N = g->n_nodes; c.D = p->node_dim; c.H = p->hidden_dim;
+  c.g = *g; c.g_tiles = g->tiles; c.g_tile_err = g->tile_err; c.N = g->n_nodes; c.D = p->node_dim; c.H = p->hidden_dim;
   Arena a(workspace, workspace_bytes);
   if (current_fold()) {
     FoldWs f;
@@ -413,7 +413,7 @@ extern "C" int gnode_integrate_fixed_bwd(const gnode_graph* g, const gnode_sage3
   const Tableau& tb = *tbp;
   const int S = tb.S;
   Sage3Ctx c;
-  c.g = *g; c.N = g->n_nodes; c.D = p->node_dim; c.H = p->hidden_dim;
+  c.g = *g; c.g_tiles = g->tiles; c.g_tile_err = g->tile_err; c.N = g->n_nodes; c.D = p->node_dim; c.H = p->hidden_dim;
   Arena a(workspace, workspace_bytes);
   if (current_fold()) {
     FoldWs f;
@@ -518,7 +518,7 @@ extern "C" int gnode_integrate_dopri5(const gnode_graph* g, const gnode_sage3_pa
   for (int j = 0; j + 1 < n_t; ++j)
     GN_ARG(t[j + 1] > t[j], "gnode_integrate_dopri5: t must be strictly increasing");
   Sage3Ctx c;
-  c.g = *g; c.N = g->n_nodes; c.D = p->node_dim; c.H = p->hidden_dim;
+  c.g = *g; c.g_tiles = g->tiles; c.g_tile_err = g->tile_err; c.N = g->n_nodes; c.D = p->node_dim; c.H = p->hidden_dim;
   Arena a(workspace, workspace_bytes);
   c.carve(a, 1, false);
   const size_t n = (size_t)c.N * c.D;

@@ -238,7 +238,7 @@ extern "C" int gnode_rhs_fwd(const gnode_graph* g, const gnode_sage3_params* p, 
   GN_TRY(check_params(p, "gnode_rhs_fwd"));
   GN_ARG(x && dxdt, "gnode_rhs_fwd: null state pointer");
   Sage3Ctx c;
-  c.g = *g; c.N = g->n_nodes; c.D = p->node_dim; c.H = p->hidden_dim;
+  c.g = *g; c.g_tiles = g->tiles; c.g_tile_err = g->tile_err; c.N = g->n_nodes; c.D = p->node_dim; c.H = p->hidden_dim;
   Arena a(workspace, workspace_bytes);
   c.carve(a, 1, false);
   GN_ARENA_OK(a, "gnode_rhs_fwd");
@@ -254,7 +254,7 @@ extern "C" int gnode_rhs_bwd(const gnode_graph* g, const gnode_sage3_params* p, 
   GN_TRY(check_params(p, "gnode_rhs_bwd"));
   GN_ARG(x && grad_out && grad_x, "gnode_rhs_bwd: null pointer");
   Sage3Ctx c;
-  c.g = *g; c.N = g->n_nodes; c.D = p->node_dim; c.H = p->hidden_dim;
+  c.g = *g; c.g_tiles = g->tiles; c.g_tile_err = g->tile_err; c.N = g->n_nodes; c.D = p->node_dim; c.H = p->hidden_dim;
   Arena a(workspace, workspace_bytes);
   c.carve(a, 1, true);
   GN_ARENA_OK(a, "gnode_rhs_bwd");

@@ -84,6 +84,7 @@ class Batch(Data):
         if all(m is not None for m in masks) and masks:
             out.is_current_agent = torch.cat(masks, dim=0)
         out.num_graphs = len(sizes)
+        out.max_graph_nodes = max(sizes) if sizes else 0     # host-side fact: enables the graph-resident kernels
         return out
 
     def shard(self, rank: int, world_size: int) -> "Batch":
@@ -99,6 +100,8 @@ class Batch(Data):
         if getattr(self, "is_current_agent", None) is not None:
             out.is_current_agent = self.is_current_agent[n0:n1]
         out.num_graphs = hi - lo
+        if getattr(self, "max_graph_nodes", None) is not None:
+            out.max_graph_nodes = self.max_graph_nodes
         return out
 
 

@@ -18,7 +18,8 @@ from . import _lib
 class CSRGraph:
     """int32 CSR (by destination) + transpose CSR (by source) living on one CUDA device."""
 
-    def __init__(self, edge_index: torch.Tensor, num_nodes: int, validate: str = "sync"):
+    def __init__(self, edge_index: torch.Tensor, num_nodes: int, validate: str = "sync",
+                 graph_ptr: Optional[torch.Tensor] = None, max_graph_nodes: Optional[int] = None):
         if not edge_index.is_cuda:
             raise _lib.GnodeError("edge_index must live on a CUDA device; libgnode_b200 has no CPU path")
         if edge_index.dim() != 2 or edge_index.size(0) != 2:
@@ -55,8 +56,20 @@ class CSRGraph:
                 self._err_event = torch.cuda.Event()
                 self._err_event.record(torch.cuda.current_stream(dev))
                 _PENDING.append(self)
+        # Whole-graph row tiles (<= 128 rows): let the integrators keep a tile on chip across the stages of a step.
+        # Needs the batch's graph offsets and the host-known size of its largest graph.
+        self.tiles = None
+        self.tile_err = None
+        if (graph_ptr is not None and max_graph_nodes is not None and 0 < int(max_graph_nodes) <= 128
+                and graph_ptr.is_cuda and graph_ptr.numel() >= 2):
+            gp = graph_ptr.to(torch.int64).contiguous()
+            self.tiles = torch.empty(gp.numel() + 1, dtype=torch.int32, device=dev)
+            self.tile_err = torch.zeros(1, dtype=torch.int32, device=dev)
+            with torch.cuda.device(dev):
+                _lib.check(L.gnode_tiles_build(_lib.ptr(gp), gp.numel() - 1, _lib.ptr(self.tiles), _lib.stream_ptr(dev)),
+                           "gnode_tiles_build")
         self.struct = _lib.GnodeGraph(N, E, self.rowptr.data_ptr(), self.col.data_ptr(), self.t_rowptr.data_ptr(),
-                                      self.t_col.data_ptr())
+                                      self.t_col.data_ptr(), _lib.ptr(self.tiles), _lib.ptr(self.tile_err))
 
     def ref(self):
         return C.byref(self.struct)
@@ -78,6 +91,34 @@ class CSRGraph:
 
     def validate(self) -> None:
         self.poll(wait=True)
+        if self.tile_err is not None and int(self.tile_err.item()) != 0:
+            raise _lib.GnodeError("an edge leaves its whole-graph tile: batch.ptr does not describe a disjoint union "
+                                  "of the graphs in edge_index")
+
+    def schedule_tile_check(self) -> None:
+        """Called after the graph-resident kernels ran: ship the tile error flag to pinned memory without blocking;
+        a later poll_pending() raises if an edge was found outside its tile."""
+        if self.tile_err is None:
+            return
+        chk = _TileCheck(self)
+        _PENDING.append(chk)
+
+
+class _TileCheck:
+    def __init__(self, g: "CSRGraph"):
+        dev = g.device
+        self.host = torch.empty(1, dtype=torch.int32, pin_memory=True)
+        self.host.copy_(g.tile_err, non_blocking=True)
+        self.event = torch.cuda.Event()
+        self.event.record(torch.cuda.current_stream(dev))
+
+    def poll(self) -> bool:
+        if not self.event.query():
+            return False
+        if int(self.host[0]) != 0:
+            raise _lib.GnodeError("an edge leaves its whole-graph tile: batch.ptr does not describe a disjoint union of "
+                                  "the graphs in edge_index (deferred check; results of that call are invalid)")
+        return True
 
 
 _PENDING: list = []
@@ -99,7 +140,8 @@ _CACHE_MAX = 8
 
 
 def csr_for(edge_index: torch.Tensor, num_nodes: int, holder: Optional[object] = None,
-            validate: str = "sync") -> CSRGraph:
+            validate: str = "sync", graph_ptr: Optional[torch.Tensor] = None,
+            max_graph_nodes: Optional[int] = None) -> CSRGraph:
     """CSR of ``edge_index``; cached on ``holder`` (e.g. the batch object) and in a small LRU keyed by
     the tensor's storage, shape and version counter.  Every cache entry keeps the keyed tensor alive,
     so its address cannot be recycled for a different edge list while the entry exists."""
@@ -112,7 +154,8 @@ def csr_for(edge_index: torch.Tensor, num_nodes: int, holder: Optional[object] =
     if entry is None or entry[0] is not edge_index and entry[0].data_ptr() != edge_index.data_ptr():
         if validate != "sync":
             poll_pending()
-        entry = (edge_index, CSRGraph(edge_index, num_nodes, validate=validate))
+        entry = (edge_index, CSRGraph(edge_index, num_nodes, validate=validate, graph_ptr=graph_ptr,
+                                      max_graph_nodes=max_graph_nodes))
         _CACHE[key] = entry
         while len(_CACHE) > _CACHE_MAX:
             _CACHE.popitem(last=False)

@@ -139,7 +139,9 @@ class GraphODE(nn.Module):
         batch = batch_data.batch
         # deferred index validation: no host synchronisation in the training step (a bad edge list raises at the
         # next call; its edges are skipped on the device meanwhile)
-        graph = csr_for(edge_index, x0.size(0), holder=batch_data, validate="deferred")
+        graph = csr_for(edge_index, x0.size(0), holder=batch_data, validate="deferred",
+                        graph_ptr=getattr(batch_data, "ptr", None),
+                        max_graph_nodes=getattr(batch_data, "max_graph_nodes", None))
         solution = odeint(self.ode_func.bind(graph), x0, time_span, method=self.ode_solver, rtol=1e-3, atol=1e-4,
                           options={"_stats_sink": self, "allreduce": self.dopri5_allreduce})
         trajectories = ops.decode_positions(solution, self.position_decoder.weight, self.position_decoder.bias)

@@ -182,6 +182,7 @@ class _IntegrateFixedFn(torch.autograd.Function):
                                                _lib.ptr(save), save.numel() if save is not None else 0,
                                                _lib.ptr(ws), ws.numel(), _lib.stream_ptr(y0.device)),
                        "gnode_integrate_fixed")
+        graph.schedule_tile_check()
         ctx.graph, ctx.method, ctx.t_host, ctx.save = graph, method, t_host, save
         ctx.fold = fold
         ctx.save_for_backward(sol, *w)

@@ -152,6 +152,7 @@ def warehouse_batch(num_graphs: int, num_agvs: int = 12, num_pickers: int = 7, s
     mask[:, W - 1] = True
     batch.is_current_agent = mask.reshape(-1)
     batch.num_graphs = B
+    batch.max_graph_nodes = W * n
     # (x, y) of snapshot 1 == first n rows of the next step's window graph (reference quirk)
     nxt_src = pos[:, min(1, W - 1)]
     next_positions = torch.from_numpy(np.stack([nxt_src[..., 1], nxt_src[..., 0]], axis=-1).astype(np.float32))

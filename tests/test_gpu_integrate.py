@@ -299,3 +299,35 @@ def test_dopri5_two_rank_lockstep_reproduces_unsharded_decisions(cuda):
             assert abs(a - b) <= 1e-5 * max(abs(b), 1e-9)
     got = torch.cat([results[0][0], results[1][0]], dim=1)
     assert rel_l2(got, full) <= 1e-5
+
+
+@pytest.mark.parametrize("n_agv,n_pick,graphs", [(12, 7, 9), (4, 3, 23), (2, 1, 40), (19, 6, 5)])
+@pytest.mark.parametrize("solver", ["rk4", "euler"])
+def test_graph_resident_chain_equals_kernel_per_op_path(cuda, fold_mode, solver, n_agv, n_pick, graphs):
+    """With batch.ptr / max_graph_nodes present the folded stages run graph-resident (csrc/chain_fwd.cu): one CTA keeps
+    a tile of whole graphs on chip for all stages.  Same arithmetic as the kernel-per-op folded path up to fp32
+    summation order; graphs of 35 / 15 nodes pack several per tile, 125 nodes fill one."""
+    if fold_mode != "folded":
+        pytest.skip("the chain kernel belongs to the folded integrator")
+    batch, nxt = S.synthetic.warehouse_batch(graphs, num_agvs=n_agv, num_pickers=n_pick, seed=11)
+    D = batch.x.shape[1]
+    model = S.GraphODE(D, n_agv, n_pick, hidden_dim=64, ode_solver=solver)
+    S.synthetic.init_weights(model, seed=2, conv3_scale=0.05)
+    model = model.to(cuda)
+    t = torch.tensor([0.0, 0.5, 1.0], device=cuda)
+    outs = {}
+    for mode in ("chain", "per_op"):
+        gb = batch.to(cuda) if mode == "chain" else S.Batch(x=batch.x.to(cuda), edge_index=batch.edge_index.to(cuda))
+        if mode == "per_op":
+            gb.batch, gb.is_current_agent = batch.batch.to(cuda), batch.is_current_agent.to(cuda)
+        model.zero_grad(set_to_none=True)
+        out = model(gb, t)
+        loss = (out["trajectories"][-1] ** 2).mean()
+        loss.backward()
+        outs[mode] = (out["node_features"].detach().clone(), [p.grad.clone() for p in model.parameters()])
+        S.graph.csr_for(gb.edge_index, gb.x.shape[0], holder=gb).validate()
+    assert rel_l2(outs["chain"][0], outs["per_op"][0]) <= 2e-6
+    for a, b in zip(outs["chain"][1], outs["per_op"][1]):
+        assert rel_l2(a, b) <= 2e-5
+    from swarm_ode_b200 import _lib
+    _lib.tc_check(cuda)
