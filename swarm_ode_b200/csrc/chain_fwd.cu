@@ -38,6 +38,7 @@ constexpr int N_AOP = 3, N_B = 4;
 constexpr int WORKERS = 256, THREADS = 64 + WORKERS;
 constexpr int T_BYTES = TM * TP * 4;               // 67584
 constexpr int SMEM_BYTES = T_BYTES + N_AOP * AOP_BYTES + N_B * B1_IMG;   // 183168
+constexpr int NBR_REG = 4;                         // neighbour ids per row kept in registers
 constexpr int TMEM_COLS = 256;                     // acc1: cols 0..127, acc2: cols 128..191
 
 struct Args {
@@ -227,18 +228,40 @@ __global__ void __launch_bounds__(THREADS, 1) k_chain_fwd(const Args a) {
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
       const int r0 = a.tiles[1 + t];
       const int nr = a.tiles[2 + t] - r0;                 // 1..128 rows, whole graphs
-      // CSR slice of this thread's row (aggregation phases)
+      // CSR slice of this thread's row (aggregation phases); the first NBR_REG neighbour ids (tile-local) stay in
+      // registers for the three aggregations of every stage
       int nb_b = 0, nb_e = 0;
       if (arow < nr) { nb_b = a.rowptr[r0 + arow]; nb_e = a.rowptr[r0 + arow + 1]; }
       const float inv_deg = 1.0f / (float)((nb_e - nb_b) > 1 ? (nb_e - nb_b) : 1);
+      int nbr[NBR_REG];
+#pragma unroll
+      for (int q = 0; q < NBR_REG; ++q) {
+        int v = -1;
+        if (nb_b + q < nb_e) {
+          v = a.col[nb_b + q] - r0;
+          if (v < 0 || v >= nr) { *a.err = 1; v = -1; }       // neighbour outside the tile: not a disjoint-union batch
+        }
+        nbr[q] = v;
+      }
 
       // mean over the in-neighbours of T[.][src_col0 + ac0 .. +32) of this thread's row
       auto aggregate = [&](int src_col0, float4 (&acc)[8]) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int p = nb_b; p < nb_e; ++p) {
+#pragma unroll
+        for (int q = 0; q < NBR_REG; ++q) {
+          if (nbr[q] >= 0) {
+            const float4* src = reinterpret_cast<const float4*>(T + nbr[q] * TP + src_col0 + ac0);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 v = src[i];
+              acc[i].x += v.x; acc[i].y += v.y; acc[i].z += v.z; acc[i].w += v.w;
+            }
+          }
+        }
+        for (int p = nb_b + NBR_REG; p < nb_e; ++p) {          // rows with more than NBR_REG neighbours
           const int nb = a.col[p] - r0;
-          if (nb < 0 || nb >= nr) { *a.err = 1; continue; }   // neighbour outside the tile: not a disjoint-union batch
+          if (nb < 0 || nb >= nr) { *a.err = 1; continue; }
           const float4* src = reinterpret_cast<const float4*>(T + nb * TP + src_col0 + ac0);
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
@@ -259,25 +282,48 @@ __global__ void __launch_bounds__(THREADS, 1) k_chain_fwd(const Args a) {
 
       for (int st = 0; st < S; ++st) {
         // ---- tile input: Z_0 (stage 0) or V_st = sum_j coef * cat2_j (later stages; also written out) ----
-        for (int idx = wt; idx < TM * (W2H / 4); idx += WORKERS) {
-          const int r = idx >> 5, c4 = idx & 31;
-          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (r < nr) {
-            const size_t off = (size_t)(r0 + r) * W2H + 4 * c4;
-            if (st == 0) {
-              acc = __ldg(reinterpret_cast<const float4*>(a.z0 + off));
-            } else {
-              for (int j = 0; j < st; ++j) {
-                const float cf = a.coef[st][j];
-                if (cf != 0.f) {
-                  const float4 v = *reinterpret_cast<const float4*>(a.cat2[j] + off);   // written by this CTA: plain load
-                  acc.x = fmaf(cf, v.x, acc.x); acc.y = fmaf(cf, v.y, acc.y); acc.z = fmaf(cf, v.z, acc.z); acc.w = fmaf(cf, v.w, acc.w);
-                }
+        // Every thread owns 16 float4 slots of the tile; all their loads are issued before the first store (the
+        // compiler cannot hoist loads over the V stores by itself).
+        {
+          constexpr int SLOTS = TM * (W2H / 4) / WORKERS;   // 16
+          float4 acc[SLOTS];
+#pragma unroll
+          for (int u = 0; u < SLOTS; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (st == 0) {
+#pragma unroll
+            for (int u = 0; u < SLOTS; ++u) {
+              const int idx = wt + u * WORKERS, r = idx >> 5, c4 = idx & 31;
+              if (r < nr) acc[u] = __ldg(reinterpret_cast<const float4*>(a.z0 + (size_t)(r0 + r) * W2H + 4 * c4));
+            }
+          } else {
+            for (int j = 0; j < st; ++j) {
+              const float cf = a.coef[st][j];
+              if (cf == 0.f) continue;
+              const float* srcj = a.cat2[j];
+              float4 v[SLOTS];
+#pragma unroll
+              for (int u = 0; u < SLOTS; ++u) {
+                const int idx = wt + u * WORKERS, r = idx >> 5, c4 = idx & 31;
+                v[u] = (r < nr) ? *reinterpret_cast<const float4*>(srcj + (size_t)(r0 + r) * W2H + 4 * c4)   // written by this CTA: plain load
+                                : make_float4(0.f, 0.f, 0.f, 0.f);
               }
-              *reinterpret_cast<float4*>(a.V[st] + off) = acc;
+#pragma unroll
+              for (int u = 0; u < SLOTS; ++u) {
+                acc[u].x = fmaf(cf, v[u].x, acc[u].x); acc[u].y = fmaf(cf, v[u].y, acc[u].y);
+                acc[u].z = fmaf(cf, v[u].z, acc[u].z); acc[u].w = fmaf(cf, v[u].w, acc[u].w);
+              }
+            }
+#pragma unroll
+            for (int u = 0; u < SLOTS; ++u) {
+              const int idx = wt + u * WORKERS, r = idx >> 5, c4 = idx & 31;
+              if (r < nr) *reinterpret_cast<float4*>(a.V[st] + (size_t)(r0 + r) * W2H + 4 * c4) = acc[u];
             }
           }
-          *reinterpret_cast<float4*>(T + r * TP + 4 * c4) = acc;
+#pragma unroll
+          for (int u = 0; u < SLOTS; ++u) {
+            const int idx = wt + u * WORKERS, r = idx >> 5, c4 = idx & 31;
+            *reinterpret_cast<float4*>(T + r * TP + 4 * c4) = acc[u];
+          }
         }
         worker_sync();
         if (st > 0) {
@@ -286,29 +332,34 @@ __global__ void __launch_bounds__(THREADS, 1) k_chain_fwd(const Args a) {
           wait_bar(smem_u32(&bar_acc_full[0]), ph_acc[0], dead, status, 25);
           ph_acc[0] ^= 1u;
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          {
+            const float cs = a.c13_scale[st];
+            const int row = 32 * eq + lane;
+            const bool rin = row < nr;
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            uint32_t r[32];
-            const int c0 = 64 * ehf + 32 * h;
-            tmem_ld32((uint32_t)c0, r);
-            float* trow = T + (32 * eq + lane) * TP + c0;
+            for (int h = 0; h < 2; ++h) {
+              const int c0 = 64 * ehf + 32 * h;
+              // this lane's Z_0 row segment (32 floats = one 128-byte line) is requested before the TMEM load returns
+              float4 z[8];
+              const float4* zp = reinterpret_cast<const float4*>(a.z0 + (size_t)(r0 + (rin ? row : 0)) * W2H + c0);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) trow[j] = __uint_as_float(r[j]);
-          }
-          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-          worker_sync();
-          const float cs = a.c13_scale[st];
-          for (int idx = wt; idx < TM * (W2H / 4); idx += WORKERS) {
-            const int r = idx >> 5, c4 = idx & 31;
-            if (r < nr) {
-              const float4 z = __ldg(reinterpret_cast<const float4*>(a.z0 + (size_t)(r0 + r) * W2H + 4 * c4));
-              const float4 c = __ldg(reinterpret_cast<const float4*>(a.c13 + 4 * c4));
-              float4* tp = reinterpret_cast<float4*>(T + r * TP + 4 * c4);
-              float4 v = *tp;
-              v.x += z.x + cs * c.x; v.y += z.y + cs * c.y; v.z += z.z + cs * c.z; v.w += z.w + cs * c.w;
-              *tp = v;
+              for (int i = 0; i < 8; ++i) z[i] = rin ? __ldg(zp + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+              uint32_t r[32];
+              tmem_ld32((uint32_t)c0, r);
+              float* trow = T + row * TP + c0;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float4 c = __ldg(reinterpret_cast<const float4*>(a.c13 + c0) + i);
+                float4 o;
+                o.x = __uint_as_float(r[4 * i + 0]) + z[i].x + cs * c.x;
+                o.y = __uint_as_float(r[4 * i + 1]) + z[i].y + cs * c.y;
+                o.z = __uint_as_float(r[4 * i + 2]) + z[i].z + cs * c.z;
+                o.w = __uint_as_float(r[4 * i + 3]) + z[i].w + cs * c.w;
+                *reinterpret_cast<float4*>(trow + 4 * i) = o;
+              }
             }
           }
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
           worker_sync();
         }
         // ---- h1 = relu(A(Z_l) + Z_r + b1) -> right half (in place) ----

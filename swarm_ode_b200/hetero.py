@@ -89,12 +89,12 @@ class HeteroData:
 def _relation_graph(edge_index: torch.Tensor, n_src: int, n_dst: int, cache: Optional[dict], key) -> CSRGraph:
     """Destination-sorted CSR of one relation; rows = destination nodes, column ids = source rows."""
     if cache is not None and key in cache:
-        ck, g = cache[key]
+        ck, g, _keep = cache[key]
         if ck == (edge_index.data_ptr(), edge_index._version, tuple(edge_index.shape), n_src, n_dst):
             return g
     g = CSRGraph(edge_index, max(n_src, n_dst))
-    if cache is not None:
-        cache[key] = ((edge_index.data_ptr(), edge_index._version, tuple(edge_index.shape), n_src, n_dst), g)
+    if cache is not None:   # the entry keeps the keyed tensor alive, so its address cannot be recycled meanwhile
+        cache[key] = ((edge_index.data_ptr(), edge_index._version, tuple(edge_index.shape), n_src, n_dst), g, edge_index)
     return g
 
 

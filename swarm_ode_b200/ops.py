@@ -229,11 +229,13 @@ def time_grid_to_host(t, dtype=torch.float32) -> Tuple[float, ...]:
     key = (t.data_ptr(), t._version, tuple(t.shape), str(t.device), t.dtype, dtype)
     hit = _T_CACHE.get(key)
     if hit is None:
-        hit = tuple(float(v) for v in t.detach().to("cpu", dtype).tolist())
+        vals = tuple(float(v) for v in t.detach().to("cpu", dtype).tolist())
         if len(_T_CACHE) > 64:
             _T_CACHE.clear()
+        # the entry keeps the tensor alive: its address cannot be recycled for a different grid while it is cached
+        hit = (t.detach(), vals)
         _T_CACHE[key] = hit
-    return hit
+    return hit[1]
 
 
 def _t_to_host(t) -> Tuple[float, ...]:

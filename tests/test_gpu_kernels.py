@@ -170,3 +170,14 @@ def test_deferred_csr_validation_flags_bad_edges(cuda):
         g.validate()
     ok = CSRGraph(ei[:, :2], 3, validate="deferred")
     ok.validate()
+
+
+def test_time_grid_cache_survives_address_reuse(cuda):
+    """The host copy of a CUDA time grid is cached by storage address; a freed grid's address must not serve a new one."""
+    from swarm_ode_b200 import ops
+    seen = []
+    for k in range(20):
+        t = torch.tensor([0.0, 0.1 * (k + 1), 1.0 + k], device=cuda)
+        seen.append(ops.time_grid_to_host(t))
+        del t
+    assert seen == [(0.0, float(torch.tensor(0.1 * (k + 1), dtype=torch.float32)), 1.0 + k) for k in range(20)]
