@@ -28,16 +28,19 @@ using namespace tc;
 constexpr int TM = 128;                 // rows per tile = TMEM lanes
 constexpr int W2H = 128, WH = 64;       // 2H, H (this kernel is specialised for hidden_dim = 64)
 constexpr int TP = 132;                 // tile row pitch in floats (16-byte aligned rows)
-constexpr int BK = 16, CHUNKS = 4, NKB = W2H / BK;
+constexpr int BK = 8, CHUNKS = 2, NKB = W2H / BK;  // one tf32 K step per stage: small rings -> two CTAs per SM
 constexpr int LBO_A = TM * 16 + 16;
-constexpr int A_PLANE = CHUNKS * LBO_A;            // 8256
-constexpr int AOP_BYTES = 2 * A_PLANE;             // 16512
-constexpr int LBO_B1 = W2H * 16 + 16, B1_PLANE = CHUNKS * LBO_B1, B1_IMG = 2 * B1_PLANE;   // N = 128: 16512
-constexpr int LBO_B2 = WH * 16 + 16, B2_PLANE = CHUNKS * LBO_B2, B2_IMG = 2 * B2_PLANE;    // N = 64:   8320
-constexpr int N_AOP = 3, N_B = 4;
+constexpr int A_PLANE = CHUNKS * LBO_A;            // 4128
+constexpr int AOP_BYTES = 2 * A_PLANE;             // 8256
+// weight images come from presplit_weights (K blocks of 16: [hi plane: 4 chunks | lo plane: 4 chunks]); a stage of
+// this kernel takes chunks (2h, 2h+1) of both planes of K-block kb/2
+constexpr int LBO_B1 = W2H * 16 + 16, B1_PLANE16 = 4 * LBO_B1, B1_IMG16 = 2 * B1_PLANE16;   // N = 128
+constexpr int LBO_B2 = WH * 16 + 16, B2_PLANE16 = 4 * LBO_B2, B2_IMG16 = 2 * B2_PLANE16;    // N = 64
+constexpr int B_STAGE = 4 * LBO_B1;                // [hi: 2 chunks | lo: 2 chunks] of the wider image: 8256
+constexpr int N_AOP = 2, N_B = 2;
 constexpr int WORKERS = 256, THREADS = 64 + WORKERS;
 constexpr int T_BYTES = TM * TP * 4;               // 67584
-constexpr int SMEM_BYTES = T_BYTES + N_AOP * AOP_BYTES + N_B * B1_IMG;   // 183168
+constexpr int SMEM_BYTES = T_BYTES + N_AOP * AOP_BYTES + N_B * B_STAGE;   // 100608: two CTAs per SM
 constexpr int NBR_REG = 4;                         // neighbour ids per row kept in registers
 constexpr int TMEM_COLS = 256;                     // acc1: cols 0..127, acc2: cols 128..191
 
@@ -68,7 +71,7 @@ __device__ __forceinline__ void wait_bar(uint32_t addr, uint32_t parity, volatil
   if (status) atomicExch(status, code);
 }
 
-__global__ void __launch_bounds__(THREADS, 1) k_chain_fwd(const Args a) {
+__global__ void __launch_bounds__(THREADS, 2) k_chain_fwd(const Args a) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t bar_aop_full[N_AOP];
   __shared__ __align__(8) uint64_t bar_aop_empty[N_AOP];
@@ -113,13 +116,18 @@ __global__ void __launch_bounds__(THREADS, 1) k_chain_fwd(const Args a) {
       for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
         for (int st = 0; st < S; ++st) {
           for (int g = (st > 0 ? 0 : 1); g < 2; ++g) {           // g = 0: M13 (stage > 0 only), g = 1: w2cat
-            const float* src = g == 0 ? a.img13 : a.img2;
-            const uint32_t bytes = g == 0 ? B1_IMG : B2_IMG;
-            for (int kb = 0; kb < NKB; ++kb, src += bytes / 4) {
+            const uint8_t* img = reinterpret_cast<const uint8_t*>(g == 0 ? a.img13 : a.img2);
+            const uint32_t lbo_b = g == 0 ? LBO_B1 : LBO_B2;
+            const uint32_t plane16 = g == 0 ? B1_PLANE16 : B2_PLANE16, img16 = g == 0 ? B1_IMG16 : B2_IMG16;
+            const uint32_t half_bytes = 2 * lbo_b;                 // two K chunks of one plane
+            for (int kb = 0; kb < NKB; ++kb) {
               if (!first_lap) wait_bar(smem_u32(&bar_b_empty[s]), ph ^ 1u, dead, status, 21);
               const uint32_t bar = smem_u32(&bar_b_full[s]);
-              mbar_expect_tx(bar, bytes);
-              bulk_load_1d(smem_base + b_off + s * B1_IMG, src, bytes, bar);
+              const uint8_t* src = img + (size_t)(kb >> 1) * img16 + (size_t)(kb & 1) * half_bytes;
+              const uint32_t dst = smem_base + b_off + s * B_STAGE;
+              mbar_expect_tx(bar, 2 * half_bytes);
+              bulk_load_1d(dst, src, half_bytes, bar);                           // hi chunks
+              bulk_load_1d(dst + half_bytes, src + plane16, half_bytes, bar);    // lo chunks
               if (++s == (uint32_t)N_B) { s = 0; ph ^= 1u; first_lap = false; }
             }
           }
@@ -129,16 +137,13 @@ __global__ void __launch_bounds__(THREADS, 1) k_chain_fwd(const Args a) {
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
     const uint64_t desc_a = make_desc(0, LBO_A);
-    const uint32_t step_a = (2 * LBO_A) >> 4;
     uint32_t sa = 0, pa = 0, sb = 0, pb = 0;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
       for (int st = 0; st < S; ++st) {
         for (int g = (st > 0 ? 0 : 1); g < 2; ++g) {
           const uint32_t lbo_b = g == 0 ? LBO_B1 : LBO_B2;
-          const uint32_t b_plane = g == 0 ? B1_PLANE : B2_PLANE;
           const uint32_t idesc = make_idesc(g == 0 ? W2H : WH);
           const uint64_t desc_b = make_desc(0, lbo_b);
-          const uint32_t step_b = (2 * lbo_b) >> 4;
           const uint32_t tmem_d = tmem_base + (g == 0 ? 0u : (uint32_t)W2H);
           for (int kb = 0; kb < NKB; ++kb) {
             wait_bar(smem_u32(&bar_b_full[sb]), pb, dead, status, 22);
@@ -146,17 +151,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_chain_fwd(const Args a) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (lane == 0) {
               const uint32_t a_hi = (smem_base + aop_off + sa * AOP_BYTES) >> 4, a_lo = a_hi + (A_PLANE >> 4);
-              const uint32_t b_hi = (smem_base + b_off + sb * B1_IMG) >> 4, b_lo = b_hi + (b_plane >> 4);
-#pragma unroll
-              for (int j = 0; j < BK / 8; ++j) {
-                const uint64_t dah = desc_a | (uint64_t)(a_hi + j * step_a);
-                const uint64_t dal = desc_a | (uint64_t)(a_lo + j * step_a);
-                const uint64_t dbh = desc_b | (uint64_t)(b_hi + j * step_b);
-                const uint64_t dbl = desc_b | (uint64_t)(b_lo + j * step_b);
-                umma_tf32(tmem_d, dal, dbh, idesc, (kb > 0 || j > 0) ? 1u : 0u);   // small terms first
-                umma_tf32(tmem_d, dah, dbl, idesc, 1u);
-                umma_tf32(tmem_d, dah, dbh, idesc, 1u);
-              }
+              const uint32_t b_hi = (smem_base + b_off + sb * B_STAGE) >> 4, b_lo = b_hi + ((2 * lbo_b) >> 4);
+              const uint64_t dah = desc_a | (uint64_t)a_hi, dal = desc_a | (uint64_t)a_lo;
+              const uint64_t dbh = desc_b | (uint64_t)b_hi, dbl = desc_b | (uint64_t)b_lo;
+              umma_tf32(tmem_d, dal, dbh, idesc, kb > 0 ? 1u : 0u);   // small terms first
+              umma_tf32(tmem_d, dah, dbl, idesc, 1u);
+              umma_tf32(tmem_d, dah, dbh, idesc, 1u);
               umma_commit(smem_u32(&bar_aop_empty[sa]));
               umma_commit(smem_u32(&bar_b_empty[sb]));
               if (kb == NKB - 1) umma_commit(smem_u32(&bar_acc_full[g]));
@@ -172,14 +172,15 @@ __global__ void __launch_bounds__(THREADS, 1) k_chain_fwd(const Args a) {
     // =========================== workers ===========================
     const int wt = tid - 64;                       // 0..255
     const int cw = warp - 2;                       // 0..7
-    // converter mapping (same as gemm_tc.cu): a warp instruction covers rows (r, r+4) x 16 k
-    const int cp = cw & 3, cq0 = (cw >> 2) * 8, chalf = lane >> 4, ckk = lane & 15;
+    // converter mapping: a warp instruction covers 4 rows (two apart: conflict-free banks) x 8 k; warp cw owns rows
+    // [16 cw, 16 cw + 16), four instructions per K block
+    const int ckk = lane & 7, cr = lane >> 3;
     const uint32_t kc_off = (uint32_t)(ckk >> 2) * LBO_A + (uint32_t)(ckk & 3) * 4u;
-    int csrc[8];
-    uint32_t cdst[8];
+    int csrc[4];
+    uint32_t cdst[4];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const int row = 8 * (cq0 + q) + cp + 4 * chalf;
+    for (int q = 0; q < 4; ++q) {
+      const int row = 16 * cw + (q & 1) + 2 * cr + 8 * (q >> 1);
       csrc[q] = row * TP + ckk;
       cdst[q] = kc_off + (uint32_t)row * 16u;
     }
@@ -189,18 +190,20 @@ __global__ void __launch_bounds__(THREADS, 1) k_chain_fwd(const Args a) {
     // epilogue mapping: TMEM lane quadrant of this warp, column half
     const int eq = warp & 3, ehf = cw >> 2;
     // aggregation mapping: two threads per row, 32 of the 64 channels each
-    const int arow = wt >> 1, ac0 = (wt & 1) * 32;
+    // (threads 0..127 take channels 0..31 of rows 0..127, threads 128..255 channels 32..63: the eight lanes of a
+    // 128-bit shared-memory phase then touch eight different rows = eight different bank groups)
+    const int arow = wt & (TM - 1), ac0 = (wt >> 7) * 32;
 
     auto convert_tile = [&]() {
       for (int kb = 0; kb < NKB; ++kb) {
-        float v[8];
+        float v[4];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) v[q] = T[csrc[q] + kb * BK];
+        for (int q = 0; q < 4; ++q) v[q] = T[csrc[q] + kb * BK];
         if (!first_lap_a) wait_bar(smem_u32(&bar_aop_empty[sa]), pa ^ 1u, dead, status, 24);
         uint8_t* a_hi = smem + aop_off + (size_t)sa * AOP_BYTES;
         uint8_t* a_lo = a_hi + A_PLANE;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
+        for (int q = 0; q < 4; ++q) {
           const uint32_t hb = (__float_as_uint(v[q]) + 0x1000u) & 0xFFFFE000u;
           *reinterpret_cast<uint32_t*>(a_hi + cdst[q]) = hb;
           *reinterpret_cast<float*>(a_lo + cdst[q]) = v[q] - __uint_as_float(hb);
@@ -285,14 +288,16 @@ __global__ void __launch_bounds__(THREADS, 1) k_chain_fwd(const Args a) {
         // Every thread owns 16 float4 slots of the tile; all their loads are issued before the first store (the
         // compiler cannot hoist loads over the V stores by itself).
         {
-          constexpr int SLOTS = TM * (W2H / 4) / WORKERS;   // 16
+          constexpr int SLOTS = TM * (W2H / 4) / WORKERS / 2;   // 8 per half
+          for (int hf = 0; hf < 2; ++hf) {
+          const int ibase = wt + hf * SLOTS * WORKERS;
           float4 acc[SLOTS];
 #pragma unroll
           for (int u = 0; u < SLOTS; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
           if (st == 0) {
 #pragma unroll
             for (int u = 0; u < SLOTS; ++u) {
-              const int idx = wt + u * WORKERS, r = idx >> 5, c4 = idx & 31;
+              const int idx = ibase + u * WORKERS, r = idx >> 5, c4 = idx & 31;
               if (r < nr) acc[u] = __ldg(reinterpret_cast<const float4*>(a.z0 + (size_t)(r0 + r) * W2H + 4 * c4));
             }
           } else {
@@ -303,7 +308,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_chain_fwd(const Args a) {
               float4 v[SLOTS];
 #pragma unroll
               for (int u = 0; u < SLOTS; ++u) {
-                const int idx = wt + u * WORKERS, r = idx >> 5, c4 = idx & 31;
+                const int idx = ibase + u * WORKERS, r = idx >> 5, c4 = idx & 31;
                 v[u] = (r < nr) ? *reinterpret_cast<const float4*>(srcj + (size_t)(r0 + r) * W2H + 4 * c4)   // written by this CTA: plain load
                                 : make_float4(0.f, 0.f, 0.f, 0.f);
               }
@@ -315,14 +320,15 @@ __global__ void __launch_bounds__(THREADS, 1) k_chain_fwd(const Args a) {
             }
 #pragma unroll
             for (int u = 0; u < SLOTS; ++u) {
-              const int idx = wt + u * WORKERS, r = idx >> 5, c4 = idx & 31;
+              const int idx = ibase + u * WORKERS, r = idx >> 5, c4 = idx & 31;
               if (r < nr) *reinterpret_cast<float4*>(a.V[st] + (size_t)(r0 + r) * W2H + 4 * c4) = acc[u];
             }
           }
 #pragma unroll
           for (int u = 0; u < SLOTS; ++u) {
-            const int idx = wt + u * WORKERS, r = idx >> 5, c4 = idx & 31;
+            const int idx = ibase + u * WORKERS, r = idx >> 5, c4 = idx & 31;
             *reinterpret_cast<float4*>(T + r * TP + 4 * c4) = acc[u];
+          }
           }
         }
         worker_sync();
@@ -477,9 +483,10 @@ int chain_fwd(Sage3Ctx& c, FoldWs& f, const Tableau& tb, float dt, cudaStream_t 
   static bool attr_set = false;
   if (!attr_set) {
     GN_CUDA(cudaFuncSetAttribute(chain::k_chain_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, chain::SMEM_BYTES));
+    GN_CUDA(cudaFuncSetAttribute(chain::k_chain_fwd, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     attr_set = true;
   }
-  chain::k_chain_fwd<<<kNumSMs, chain::THREADS, chain::SMEM_BYTES, s>>>(a);
+  chain::k_chain_fwd<<<2 * kNumSMs, chain::THREADS, chain::SMEM_BYTES, s>>>(a);
   GN_LAUNCHED();
   return GNODE_OK;
 }

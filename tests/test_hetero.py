@@ -45,8 +45,8 @@ def test_oracle_matches_reference_class(gold, tag):
     with torch.no_grad():
         out = m(_data(gold, RefHeteroData), integration_time=CASES[tag]["t"])
     assert list(out) == KEYS
-    for k in KEYS:
-        assert np.array_equal(out[k].numpy(), gold[f"{tag}/{k}"]), k
+    for k in KEYS:   # bit for bit on the generating machine; fp32 rounding elsewhere
+        np.testing.assert_allclose(out[k].numpy(), gold[f"{tag}/{k}"], rtol=2e-5, atol=2e-6, err_msg=k)
 
 
 def test_hetero_conv_skips_absent_relations_cpu_semantics():
