@@ -280,6 +280,161 @@ int integrate_dopri5(Field& f, const float* y0, const double* t, int n_t, double
   return GNODE_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Adaptive dopri5 with folded stages (fold.cu): per attempted step the D-wide state is touched by three dense
+// contractions (Z_0 = y @ w1cat^T on the way in; y_1 and the error estimate on the way out) instead of two per stage;
+// the seven stages run 2H-wide (graph-resident when the batch carries whole-graph tiles).  The controller, the norms
+// and the dense output keep torchdiffeq's arithmetic; only the stage evaluations are re-associated.
+// ------------------------------------------------------------------------------------------------
+struct Dopri5FoldBufs {
+  float *ya, *yb, *k0, *k1, *xs, *err;   // [N, D] each
+  double* partials; double* dsum;
+};
+
+int integrate_dopri5_folded(Sage3Ctx& c, FoldWs& f, const float* y0, const double* t, int n_t, double rtol, double atol,
+                            float* sol, gnode_dopri5_stats* stats, const gnode_dopri5_trace* trace,
+                            gnode_allreduce_fn allreduce, void* allreduce_user, int64_t max_num_steps,
+                            const Dopri5FoldBufs& b, cudaStream_t s) {
+  const Tableau& tb = *tableau_for(GNODE_DOPRI5);
+  const int64_t n = c.numel();
+  const int H2 = 2 * c.H;
+  const int64_t nh = c.N * H2;
+  const float rtolf = (float)rtol, atolf = (float)atol;
+  gnode_dopri5_stats st{};
+  st.min_margin = INFINITY;
+  NormCtx nc{allreduce, allreduce_user, b.dsum, s, n};
+  float* ya = b.ya;
+  float* yb = b.yb;
+
+  if (sol != y0) GN_CUDA(cudaMemcpyAsync(sol, y0, sizeof(float) * n, cudaMemcpyDeviceToDevice, s));
+  GN_CUDA(cudaMemcpyAsync(ya, y0, sizeof(float) * n, cudaMemcpyDeviceToDevice, s));
+  GN_TRY(f.prepare(c, s));
+  f.bind_slots(c, nullptr, 0);
+
+  // k = scale_w * (W @ w3cat^T) + scale_b * b3   for a 2H-wide W; optional base
+  auto project = [&](const float* W, float* out, const float* base, float bias_scale) -> int {
+    GemmNT q{};
+    q.A = W; q.lda = H2; q.B = c.w3cat; q.ldb = H2; q.C = out; q.ldc = c.D; q.M = c.N; q.N = c.D; q.K = H2;
+    q.bias = c.b3; q.bias_scale = bias_scale; q.base = base; q.ldbase = c.D;
+    q.Bsplit = c.use_tc ? c.s3 : nullptr;
+    return gemm_nt(q, s);
+  };
+  auto combine = [&](const double* coef, float dtf, double* sum_out) -> int {   // Cbuf = dt * sum_j coef_j cat2_j
+    LinComb lc{};
+    lc.out = f.Cbuf; lc.base = nullptr; lc.n = nh; lc.n_terms = 0;
+    double sum = 0.0;
+    for (int j = 0; j < 7; ++j) {
+      sum += coef[j];
+      if (coef[j] != 0.0) { lc.in[lc.n_terms] = f.cat2[j]; lc.coef[lc.n_terms] = (float)coef[j] * dtf; ++lc.n_terms; }
+    }
+    *sum_out = sum;
+    return lincomb(lc, s);
+  };
+
+  // ---- _select_initial_step: two direct evaluations of the field (D-wide derivatives are needed for the norms) ----
+  GN_TRY(c.eval(ya, b.k0, nullptr, 1.f, 0, s));
+  st.nfe++;
+  double dt;
+  {
+    float d0, d1, d2;
+    GN_TRY(scaled_sumsq(ya, nullptr, ya, atolf, rtolf, n, b.partials, b.dsum, s));
+    GN_TRY(nc.finish(&d0));
+    GN_TRY(scaled_sumsq(b.k0, nullptr, ya, atolf, rtolf, n, b.partials, b.dsum, s));
+    GN_TRY(nc.finish(&d1));
+    float h0;
+    if (d0 < 1e-5f || d1 < 1e-5f) h0 = 1e-6f; else h0 = 0.01f * d0 / d1;
+    h0 = fabsf(h0);
+    LinComb lc{};
+    lc.out = b.xs; lc.base = ya; lc.in[0] = b.k0; lc.coef[0] = h0; lc.n_terms = 1; lc.n = n;
+    GN_TRY(lincomb(lc, s));
+    GN_TRY(c.eval(b.xs, b.k1, nullptr, 1.f, 0, s));
+    st.nfe++;
+    GN_TRY(scaled_sumsq(b.k1, b.k0, ya, atolf, rtolf, n, b.partials, b.dsum, s));
+    GN_TRY(nc.finish(&d2));
+    d2 = fabsf(d2 / h0);
+    float h1;
+    if (d1 <= 1e-15f && d2 <= 1e-15f) h1 = fmaxf(1e-6f, h0 * 1e-3f);
+    else h1 = powf(0.01f / fmaxf(d1, d2), 1.0f / 5.0f);
+    h1 = fabsf(h1);
+    dt = (double)fminf(100.f * h0, h1);
+  }
+  st.first_step = dt;
+
+  double t_cur = t[0];
+  int next_out = 1;
+  int64_t n_steps = 0;
+  while (next_out < n_t) {
+    if (!(t[next_out] > t_cur)) {
+      GN_CUDA(cudaMemcpyAsync(sol + (int64_t)next_out * n, ya, sizeof(float) * n, cudaMemcpyDeviceToDevice, s));
+      ++next_out;
+      continue;
+    }
+    if (n_steps >= max_num_steps) { set_error("dopri5: max_num_steps exceeded (%lld)", (long long)n_steps); return GNODE_ERR_SOLVER; }
+    const double t0 = t_cur, t1 = t0 + dt;
+    if (!(t0 + dt > t0)) { set_error("dopri5: underflow in dt %g", dt); return GNODE_ERR_SOLVER; }
+    const float dtf = (float)dt;
+    // seven stages, 2H-wide (stage 6's input is the 5th-order solution: beta[6] == c_sol, FSAL)
+    GN_TRY(f.forward_stages(c, tb, ya, dtf, s));
+    st.nfe += 6;
+    double csum;
+    GN_TRY(combine(tb.c_sol, dtf, &csum));
+    GN_TRY(project(f.Cbuf, yb, ya, (float)csum * dtf));                 // y1 = y0 + dt sum c_sol k
+    GN_TRY(combine(tb.c_err, dtf, &csum));
+    GN_TRY(project(f.Cbuf, b.err, nullptr, (float)csum * dtf));         // err = dt sum c_err k
+    LinComb le{};
+    le.n = n; le.n_terms = 1; le.in[0] = b.err; le.coef[0] = 1.f;
+    GN_TRY(error_sumsq(le, ya, yb, atolf, rtolf, b.partials, b.dsum, s));
+    float ratio;
+    GN_TRY(nc.finish(&ratio));
+    if (!std::isfinite(ratio)) { set_error("dopri5: non-finite values in state `y` (error ratio %g at t=%g, dt=%g)", (double)ratio, t0, dt); return GNODE_ERR_SOLVER; }
+    const bool accept = ratio <= 1.0f;
+    if (trace && trace->trace_cap > st.n_attempted) {
+      if (trace->error_ratio) trace->error_ratio[st.n_attempted] = ratio;
+      if (trace->dt) trace->dt[st.n_attempted] = dt;
+      if (trace->accepted) trace->accepted[st.n_attempted] = accept ? 1 : 0;
+    }
+    st.n_attempted++;
+    const double margin = std::fabs((double)ratio - 1.0);
+    if (margin < st.min_margin) st.min_margin = margin;
+    if (accept) {
+      st.n_accepted++;
+      if (next_out < n_t && t[next_out] <= t1) {
+        // dense output needs D-wide f0 = k_0, f1 = k_6 and dt * sum c_mid k: three projections, then the
+        // reference's quartic in the reference's operation order
+        GN_TRY(project(f.cat2[0], b.k0, nullptr, 1.f));
+        GN_TRY(project(f.cat2[6], b.k1, nullptr, 1.f));
+        GN_TRY(combine(tb.c_mid, dtf, &csum));
+        GN_TRY(project(f.Cbuf, b.xs, nullptr, (float)csum * dtf));
+        while (next_out < n_t && t[next_out] <= t1) {
+          const float x = (float)((t[next_out] - t0) / (t1 - t0));
+          LinComb lm{};
+          lm.n = n; lm.n_terms = 7;
+          for (int q = 0; q < 7; ++q) { lm.in[q] = b.k0; lm.coef[q] = 0.f; }
+          lm.in[1] = b.xs; lm.coef[1] = 1.f;      // comb_terms = dt * sum c_mid k  (the other terms add exact zeros)
+          lm.in[6] = b.k1;
+          GN_TRY(dopri_interp(lm, ya, yb, dtf, x, sol + (int64_t)next_out * n, s));
+          ++next_out;
+        }
+      }
+      float* tmp = ya; ya = yb; yb = tmp;
+      t_cur = t1;
+    }
+    double factor;
+    if (ratio == 0.f) {
+      factor = 10.0;
+    } else {
+      const double dfactor = (ratio < 1.f) ? 1.0 : 0.2;
+      factor = std::fmin(10.0, std::fmax(0.9 / std::pow((double)ratio, 0.2), dfactor));
+    }
+    dt = dt * factor;
+    ++n_steps;
+  }
+  st.last_dt = dt;
+  if (stats) *stats = st;
+  return GNODE_OK;
+}
+
 }  // namespace gnode
 
 using namespace gnode;
@@ -493,10 +648,28 @@ extern "C" int gnode_integrate_fixed_bwd(const gnode_graph* g, const gnode_sage3
   return GNODE_OK;
 }
 
+namespace {
+void carve_dopri5_fold(Arena& a, Sage3Ctx& c, FoldWs& f, Dopri5FoldBufs& b) {
+  c.carve(a, 7, false);
+  f.carve(a, c, 7, false);
+  const size_t n = (size_t)c.N * c.D;
+  b.ya = a.take<float>(n); b.yb = a.take<float>(n); b.k0 = a.take<float>(n);
+  b.k1 = a.take<float>(n); b.xs = a.take<float>(n); b.err = a.take<float>(n);
+  b.partials = a.take<double>((size_t)norm_blocks((int64_t)n));
+  b.dsum = a.take<double>(2);
+}
+}  // namespace
+
 extern "C" size_t gnode_integrate_dopri5_workspace_bytes(int64_t n_nodes, int32_t node_dim, int32_t hidden_dim) {
   Sage3Ctx c;
   c.N = n_nodes; c.D = node_dim; c.H = hidden_dim;
   Arena a(nullptr, 0);
+  if (current_fold()) {
+    FoldWs f;
+    Dopri5FoldBufs b{};
+    carve_dopri5_fold(a, c, f, b);
+    return a.off;
+  }
   c.carve(a, 1, false);
   const size_t n = (size_t)n_nodes * node_dim;
   for (int i = 0; i < 10; ++i) a.take<float>(n);
@@ -520,6 +693,16 @@ extern "C" int gnode_integrate_dopri5(const gnode_graph* g, const gnode_sage3_pa
   Sage3Ctx c;
   c.g = *g; c.g_tiles = g->tiles; c.g_tile_err = g->tile_err; c.N = g->n_nodes; c.D = p->node_dim; c.H = p->hidden_dim;
   Arena a(workspace, workspace_bytes);
+  if (max_num_steps <= 0) max_num_steps = (1ll << 31) - 1;
+  if (current_fold()) {
+    FoldWs f;
+    Dopri5FoldBufs fb{};
+    carve_dopri5_fold(a, c, f, fb);
+    GN_ARENA_OK(a, "gnode_integrate_dopri5");
+    GN_TRY(c.pack(*p, false, s));
+    return integrate_dopri5_folded(c, f, y0, t, n_t, rtol, atol, sol, stats, trace, allreduce, allreduce_user,
+                                   max_num_steps, fb, s);
+  }
   c.carve(a, 1, false);
   const size_t n = (size_t)c.N * c.D;
   Dopri5Bufs b{};

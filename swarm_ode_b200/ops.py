@@ -318,6 +318,7 @@ def integrate_dopri5(y0, graph: CSRGraph, params: Sequence[torch.Tensor], t, rto
                        "gnode_integrate_dopri5")
 
     stats = _run_dopri5(call, trace_cap)
+    graph.schedule_tile_check()
     return sol, stats
 
 
