@@ -64,9 +64,11 @@ __device__ __forceinline__ void worker_sync() { asm volatile("bar.sync 1, %0;" :
 
 // bounded wait that gives up immediately once any wait of this CTA has timed out
 __device__ __forceinline__ void wait_bar(uint32_t addr, uint32_t parity, volatile int* dead, int* status, int code) {
-  if (*dead) return;
-  for (uint32_t i = 0; i < SPIN_LIMIT; ++i)
+  if (mbar_try_wait(addr, parity)) return;            // fast path: no shared-memory flag read
+  for (uint32_t i = 0; i < SPIN_LIMIT; ++i) {
     if (mbar_try_wait(addr, parity)) return;
+    if ((i & 1023u) == 1023u && *dead) return;         // another wait of this CTA already timed out
+  }
   *dead = 1;
   if (status) atomicExch(status, code);
 }
