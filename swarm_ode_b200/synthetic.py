@@ -176,6 +176,7 @@ def dense_batch(num_graphs: int, num_agents: int = 256, node_dim_: int = 64, see
     out.ptr = torch.arange(B + 1, dtype=torch.long) * n
     out.is_current_agent = torch.ones(B * n, dtype=torch.bool)
     out.num_graphs = B
+    out.max_graph_nodes = n
     return out
 
 
@@ -201,6 +202,7 @@ def geometric_batch(num_graphs: int, num_agents: int, node_dim_: int = 128, thre
     out.ptr = torch.arange(B + 1, dtype=torch.long) * n
     out.is_current_agent = torch.ones(B * n, dtype=torch.bool)
     out.num_graphs = B
+    out.max_graph_nodes = n
     return out
 
 
