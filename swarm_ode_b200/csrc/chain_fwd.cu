@@ -50,6 +50,8 @@ struct Args {
   float* cat2[kMaxStages];
   float* V[kMaxStages];
   float coef[kMaxStages][kMaxStages];   // dt * beta[s][j]
+  float csol[kMaxStages];               // dt * c_sol[s]
+  float* Cout;                          // optional: C = sum_s csol[s] cat2_s, written after the last stage
   float c13_scale[kMaxStages];          // dt * sum_j beta[s][j]
   const float *c13, *b1, *b2;
   const float *img13, *img2;            // weight images of M13 [2H x 2H] and w2cat [H x 2H]
@@ -421,6 +423,42 @@ __global__ void __launch_bounds__(THREADS, 2) k_chain_fwd(const Args a) {
         }
         worker_sync();
         store_tile(a.cat2[st]);
+        if (st == S - 1 && a.Cout != nullptr) {
+          // C = sum_s csol[s] cat2_s: the last cat2 tile is still on chip, the earlier ones come back from L2
+          constexpr int SLOTS = TM * (W2H / 4) / WORKERS / 2;
+          for (int hf = 0; hf < 2; ++hf) {
+            const int ibase = wt + hf * SLOTS * WORKERS;
+            float4 acc[SLOTS];
+            const float cl = a.csol[st];
+#pragma unroll
+            for (int u = 0; u < SLOTS; ++u) {
+              const int idx = ibase + u * WORKERS, r = idx >> 5, c4 = idx & 31;
+              const float4 v = *reinterpret_cast<const float4*>(T + r * TP + 4 * c4);
+              acc[u] = make_float4(cl * v.x, cl * v.y, cl * v.z, cl * v.w);
+            }
+            for (int j = 0; j < st; ++j) {
+              const float cf = a.csol[j];
+              if (cf == 0.f) continue;
+              const float* srcj = a.cat2[j];
+              float4 v[SLOTS];
+#pragma unroll
+              for (int u = 0; u < SLOTS; ++u) {
+                const int idx = ibase + u * WORKERS, r = idx >> 5, c4 = idx & 31;
+                v[u] = (r < nr) ? *reinterpret_cast<const float4*>(srcj + (size_t)(r0 + r) * W2H + 4 * c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+              }
+#pragma unroll
+              for (int u = 0; u < SLOTS; ++u) {
+                acc[u].x = fmaf(cf, v[u].x, acc[u].x); acc[u].y = fmaf(cf, v[u].y, acc[u].y);
+                acc[u].z = fmaf(cf, v[u].z, acc[u].z); acc[u].w = fmaf(cf, v[u].w, acc[u].w);
+              }
+            }
+#pragma unroll
+            for (int u = 0; u < SLOTS; ++u) {
+              const int idx = ibase + u * WORKERS, r = idx >> 5, c4 = idx & 31;
+              if (r < nr) *reinterpret_cast<float4*>(a.Cout + (size_t)(r0 + r) * W2H + 4 * c4) = acc[u];
+            }
+          }
+        }
         worker_sync();      // the tile buffer is reused by the next stage; its cat2 rows are visible to this CTA
       }
     }
@@ -462,7 +500,7 @@ namespace tc { int* status_ptr(); }
 
 bool chain_fwd_supported(const Sage3Ctx& c) { return c.H == chain::WH && c.use_tc && c.g_tiles != nullptr; }
 
-int chain_fwd(Sage3Ctx& c, FoldWs& f, const Tableau& tb, float dt, cudaStream_t s) {
+int chain_fwd(Sage3Ctx& c, FoldWs& f, const Tableau& tb, float dt, float* Cout, cudaStream_t s) {
   int* status_dev = tc::status_ptr();
   if (!status_dev) { set_error("chain_fwd: status symbol unavailable"); return GNODE_ERR_CUDA; }
   chain::Args a{};
@@ -472,7 +510,9 @@ int chain_fwd(Sage3Ctx& c, FoldWs& f, const Tableau& tb, float dt, cudaStream_t 
     double bsum = 0.0;
     for (int j = 0; j < st; ++j) { a.coef[st][j] = (float)tb.beta[st][j] * dt; bsum += tb.beta[st][j]; }
     a.c13_scale[st] = (float)bsum * dt;
+    a.csol[st] = (float)tb.c_sol[st] * dt;
   }
+  a.Cout = Cout;
   a.c13 = f.c13; a.b1 = c.b1; a.b2 = c.b2;
   a.img13 = f.sM13; a.img2 = c.s2;
   a.rowptr = c.g.rowptr; a.col = c.g.col;

@@ -70,6 +70,7 @@ struct FoldWs {
   float *M13 = nullptr, *M13T = nullptr, *c13 = nullptr;   // w1cat @ w3cat [2H, 2H], its transpose, w1cat @ b3 [2H]
   float *sM13 = nullptr, *sM13T = nullptr;                 // tf32 hi/lo planes of the two
   float *z0 = nullptr, *Cbuf = nullptr;                    // [N, 2H]
+  float* Cslot = nullptr;                                  // C = dt sum_s c_s cat2_s of the current step (save area or Cbuf)
   float* Vws[kMaxStages] = {};                             // workspace V_s (when nothing is saved)
   float *cat1[kMaxStages] = {}, *cat2[kMaxStages] = {}, *V[kMaxStages] = {};   // stage slots of the current step
   // backward
@@ -82,8 +83,9 @@ struct FoldWs {
   static size_t save_floats_per_step(const Sage3Ctx& c, int S);
   void bind_slots(Sage3Ctx& c, float* save, int j);
   int prepare(Sage3Ctx& c, cudaStream_t s);
-  int forward_stages(Sage3Ctx& c, const Tableau& tb, const float* y, float dt, cudaStream_t s);
-  int combine_solution(Sage3Ctx& c, const Tableau& tb, float dt, cudaStream_t s);
+  // fills cat1 / cat2 / V of every stage from y; with Cout also C = dt sum_s c_sol[s] cat2_s
+  int forward_stages(Sage3Ctx& c, const Tableau& tb, const float* y, float dt, cudaStream_t s, float* Cout = nullptr);
+  int combine_solution(Sage3Ctx& c, const Tableau& tb, float dt, float* out, cudaStream_t s);
 };
 int integrate_fixed_folded(Sage3Ctx& c, FoldWs& f, const Tableau& tb, const float* y0, const float* t, int n_t,
                            float* sol, float* save, cudaStream_t s);
@@ -92,7 +94,7 @@ int integrate_fixed_folded_bwd(Sage3Ctx& c, FoldWs& f, const Tableau& tb, const 
 int current_fold();
 // graph-resident forward chain of the folded stages (chain_fwd.cu)
 bool chain_fwd_supported(const Sage3Ctx& c);
-int chain_fwd(Sage3Ctx& c, FoldWs& f, const Tableau& tb, float dt, cudaStream_t s);
+int chain_fwd(Sage3Ctx& c, FoldWs& f, const Tableau& tb, float dt, float* Cout, cudaStream_t s);
 
 int check_graph(const gnode_graph* g, const char* who);
 int check_params(const gnode_sage3_params* p, const char* who);

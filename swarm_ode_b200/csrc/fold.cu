@@ -103,7 +103,7 @@ void FoldWs::carve(Arena& a, const Sage3Ctx& c, int S_, bool backward) {
 }
 
 size_t FoldWs::save_floats_per_step(const Sage3Ctx& c, int S_) {
-  return (size_t)(3 * S_ - 1) * padf((size_t)c.N * 2 * c.H);
+  return (size_t)(3 * S_) * padf((size_t)c.N * 2 * c.H);   // cat1, cat2 per stage; V_1..V_{S-1}; C
 }
 
 // point the stage slots of step j at the save area (or at the workspace when save == null)
@@ -114,8 +114,10 @@ void FoldWs::bind_slots(Sage3Ctx& c, float* save, int j) {
     for (int st = 0; st < S; ++st) { cat1[st] = p; p += nh; cat2[st] = p; p += nh; }
     V[0] = nullptr;
     for (int st = 1; st < S; ++st) { V[st] = p; p += nh; }
+    Cslot = p;
   } else {
     for (int st = 0; st < S; ++st) { cat1[st] = c.cat1[st]; cat2[st] = c.cat2[st]; V[st] = Vws[st]; }
+    Cslot = Cbuf;
   }
 }
 
@@ -135,7 +137,7 @@ int FoldWs::prepare(Sage3Ctx& c, cudaStream_t s) {
 }
 
 // Stages of one step: fills cat1[st], cat2[st] (and V[st] for st >= 1) from y.  Z_0 is left in z0.
-int FoldWs::forward_stages(Sage3Ctx& c, const Tableau& tb, const float* y, float dt, cudaStream_t s) {
+int FoldWs::forward_stages(Sage3Ctx& c, const Tableau& tb, const float* y, float dt, cudaStream_t s, float* Cout) {
   const int H = c.H, H2 = 2 * c.H;
   const int64_t N = c.N;
   const int64_t nh = N * H2;
@@ -145,7 +147,7 @@ int FoldWs::forward_stages(Sage3Ctx& c, const Tableau& tb, const float* y, float
     q.Bsplit = c.use_tc ? c.s1 : nullptr;
     GN_TRY(gemm_nt(q, s));
   }
-  if (chain_fwd_supported(c)) return chain_fwd(c, *this, tb, dt, s);   // all stages of the step, graph-resident
+  if (chain_fwd_supported(c)) return chain_fwd(c, *this, tb, dt, Cout, s);   // all stages of the step, graph-resident
   for (int st = 0; st < S; ++st) {
     const float* z = z0;
     if (st > 0) {
@@ -178,13 +180,14 @@ int FoldWs::forward_stages(Sage3Ctx& c, const Tableau& tb, const float* y, float
     }
     GN_TRY(agg_mean_fwd(c.g, c2 + H, H2, c2, H2, H, nullptr, 0, nullptr, 0, s));     // A(h2)
   }
+  if (Cout) GN_TRY(combine_solution(c, tb, dt, Cout, s));
   return GNODE_OK;
 }
 
 // C = dt * sum_s c_sol[s] cat2_s   -> Cbuf
-int FoldWs::combine_solution(Sage3Ctx& c, const Tableau& tb, float dt, cudaStream_t s) {
+int FoldWs::combine_solution(Sage3Ctx& c, const Tableau& tb, float dt, float* out, cudaStream_t s) {
   LinComb lc{};
-  lc.out = Cbuf; lc.base = nullptr; lc.n = c.N * 2 * c.H; lc.n_terms = 0;
+  lc.out = out; lc.base = nullptr; lc.n = c.N * 2 * c.H; lc.n_terms = 0;
   for (int st = 0; st < S; ++st) { lc.in[lc.n_terms] = cat2[st]; lc.coef[lc.n_terms] = (float)tb.c_sol[st] * dt; ++lc.n_terms; }
   return lincomb(lc, s);
 }
@@ -202,10 +205,9 @@ int integrate_fixed_folded(Sage3Ctx& c, FoldWs& f, const Tableau& tb, const floa
     const float* y = sol + (int64_t)j * n;
     float* y1 = sol + (int64_t)(j + 1) * n;
     f.bind_slots(c, save, j);
-    GN_TRY(f.forward_stages(c, tb, y, dt, s));
-    GN_TRY(f.combine_solution(c, tb, dt, s));
+    GN_TRY(f.forward_stages(c, tb, y, dt, s, f.Cslot));
     GemmNT q{};   // y_1 = y + C @ w3cat^T + (dt sum c) b3
-    q.A = f.Cbuf; q.lda = H2; q.B = c.w3cat; q.ldb = H2; q.C = y1; q.ldc = c.D; q.M = c.N; q.N = c.D; q.K = H2;
+    q.A = f.Cslot; q.lda = H2; q.B = c.w3cat; q.ldb = H2; q.C = y1; q.ldc = c.D; q.M = c.N; q.N = c.D; q.K = H2;
     q.bias = c.b3; q.bias_scale = (float)csum * dt; q.base = y; q.ldbase = c.D;
     q.Bsplit = c.use_tc ? c.s3 : nullptr;
     GN_TRY(gemm_nt(q, s));
@@ -230,7 +232,7 @@ int integrate_fixed_folded_bwd(Sage3Ctx& c, FoldWs& f, const Tableau& tb, const 
     const float dt = t[j + 1] - t[j];
     const float* y = sol + (int64_t)j * n;
     f.bind_slots(c, const_cast<float*>(save), j);
-    if (!save) GN_TRY(f.forward_stages(c, tb, y, dt, s));          // recompute this step's stages
+    if (!save) GN_TRY(f.forward_stages(c, tb, y, dt, s, f.Cslot));  // recompute this step's stages (and C)
     {  // G3 = G @ w3cat     [N, 2H]
       GemmNT q{};
       q.A = G; q.lda = c.D; q.B = c.w3catT; q.ldb = c.D; q.C = f.G3; q.ldc = H2; q.M = N; q.N = H2; q.K = c.D;
@@ -299,10 +301,9 @@ int integrate_fixed_folded_bwd(Sage3Ctx& c, FoldWs& f, const Tableau& tb, const 
       for (int st = 0; st < S; ++st) { lz.in[lz.n_terms] = f.gzs[st]; lz.coef[lz.n_terms] = 1.f; ++lz.n_terms; }
       GN_TRY(lincomb(lz, s));
     }
-    GN_TRY(f.combine_solution(c, tb, dt, s));
-    {  // dW3cat += G^T @ C     [D, 2H]
+    {  // dW3cat += G^T @ C     [D, 2H]   (C kept by the forward pass)
       GemmTN q{};
-      q.A = G; q.lda = c.D; q.P = c.D; q.B = f.Cbuf; q.ldb = H2; q.Q = H2; q.Nrows = N; q.C = c.dW3cat; q.ldc = H2;
+      q.A = G; q.lda = c.D; q.P = c.D; q.B = f.Cslot; q.ldb = H2; q.Q = H2; q.Nrows = N; q.C = c.dW3cat; q.ldc = H2;
       q.colsumA = c.db3; q.colsumA_scale = (float)csum * dt;       // db3 += (dt sum c_s) colsum(G), fused
       GN_TRY(gemm_tn(q, f.partials, s));
     }

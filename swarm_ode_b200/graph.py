@@ -91,6 +91,8 @@ class CSRGraph:
 
     def validate(self) -> None:
         self.poll(wait=True)
+        # this call gives the verdict for the graph: drop its deferred checks so that they do not raise again later
+        _PENDING[:] = [c for c in _PENDING if not (isinstance(c, _TileCheck) and c.graph is self)]
         if self.tile_err is not None and int(self.tile_err.item()) != 0:
             raise _lib.GnodeError("an edge leaves its whole-graph tile: batch.ptr does not describe a disjoint union "
                                   "of the graphs in edge_index")
@@ -106,6 +108,7 @@ class CSRGraph:
 
 class _TileCheck:
     def __init__(self, g: "CSRGraph"):
+        self.graph = g
         dev = g.device
         self.host = torch.empty(1, dtype=torch.int32, pin_memory=True)
         self.host.copy_(g.tile_err, non_blocking=True)
@@ -125,14 +128,18 @@ _PENDING: list = []
 
 
 def poll_pending() -> None:
-    """Look (without blocking) at the deferred validations that have completed."""
-    keep = []
-    try:
-        for g in _PENDING:
+    """Look (without blocking) at the deferred validations that have completed; raises the first failure found (every
+    completed check leaves the list either way)."""
+    keep, first = [], None
+    for g in list(_PENDING):
+        try:
             if not g.poll():
                 keep.append(g)
-    finally:
-        _PENDING[:] = keep
+        except _lib.GnodeError as e:
+            first = first or e
+    _PENDING[:] = keep
+    if first is not None:
+        raise first
 
 
 _CACHE: "OrderedDict[tuple, tuple]" = OrderedDict()  # key -> (keyed edge_index tensor, CSRGraph)
