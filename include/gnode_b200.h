@@ -225,6 +225,18 @@ int gnode_integrate_fixed_bwd(const gnode_graph* g, const gnode_sage3_params* p,
                               const void* save, size_t save_bytes,
                               void* workspace, size_t workspace_bytes, gnode_stream_t stream);
 
+/* Backward of a ONE-STEP fixed-grid solve (n_t == 2, folded integrator) whose solution reaches the loss only through
+ * position_decoder at the last time point -- the training step of scripts/train_gde.py:486-493.  The cotangent of y_1
+ * is grad_traj_last [n_nodes, n_out] @ dec_w [n_out, D] (rank n_out <= 8): it is never formed, and neither are its two
+ * D-wide contractions.  Param grads accumulated (+=); dL/dy_0 is not produced. */
+size_t gnode_integrate_fixed_bwd_decoded_workspace_bytes(int64_t n_nodes, int32_t node_dim, int32_t hidden_dim,
+                                                         int32_t method, int32_t n_out);
+int gnode_integrate_fixed_bwd_decoded(const gnode_graph* g, const gnode_sage3_params* p, int32_t method,
+                                      const float* sol, const float* t, int32_t n_t,
+                                      const float* grad_traj_last, const float* dec_w, int32_t n_out,
+                                      const gnode_sage3_grads* grads, const void* save, size_t save_bytes,
+                                      void* workspace, size_t workspace_bytes, gnode_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * Adaptive Dormand-Prince 5(4), torchdiffeq semantics (global RMS error norm over the whole
  * state tensor, Hairer initial step, FSAL, quartic dense output, fp64 time / fp32 state).

@@ -206,6 +206,20 @@ int wgrad_blocks(int64_t M) {   // blocks stride over 256-row chunks
 }  // namespace
 }  // namespace gnode
 
+namespace gnode {
+// total[o * D + c] = sum_m g[m, o] * x[m, c],  total[n_out * D + o] = sum_m g[m, o]   (fixed-order reduction)
+// partials: decoder_wgrad_partial_floats(M, D, n_out) floats; total: n_out * D + n_out floats (overwritten).
+size_t decoder_wgrad_partial_floats(int64_t M, int D, int n_out) { return (size_t)wgrad_blocks(M) * ((size_t)n_out * D + n_out); }
+int decoder_wgrad(const float* x, const float* g, int64_t M, int D, int n_out, float* partials, float* total, cudaStream_t s) {
+  const int nb = wgrad_blocks(M);
+  const int64_t per = (int64_t)n_out * D + n_out;
+  k_decoder_wgrad<<<nb, DEC_THREADS, 0, s>>>(x, g, M, D, n_out, ceil_div64(M, kWgRows), partials);
+  GN_LAUNCHED();
+  GN_CUDA(cudaMemsetAsync(total, 0, sizeof(float) * per, s));
+  return reduce_partials_accum(partials, nb, per, total, 1.f, s);
+}
+}  // namespace gnode
+
 using namespace gnode;
 
 extern "C" size_t gnode_decoder_workspace_bytes(int64_t m, int32_t node_dim, int32_t n_out) {

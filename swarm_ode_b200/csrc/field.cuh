@@ -89,8 +89,17 @@ struct FoldWs {
 };
 int integrate_fixed_folded(Sage3Ctx& c, FoldWs& f, const Tableau& tb, const float* y0, const float* t, int n_t,
                            float* sol, float* save, cudaStream_t s);
+// Cotangent of the last time point given in factored form  G = g1 @ Wd  (g1 [N, n_out], Wd [n_out, D]): what the
+// position decoder hands back when the loss reaches the solution only through it (scripts/train_gde.py:486-490).
+struct LowRankG {
+  const float* g1; const float* Wd; int n_out;
+  float *WdW3, *X, *partials;     // scratch: [n_out, 2H], [n_out * 2H + n_out], decoder_wgrad_partial_floats(N, 2H, n_out)
+};
 int integrate_fixed_folded_bwd(Sage3Ctx& c, FoldWs& f, const Tableau& tb, const float* sol, const float* t, int n_t,
-                               const float* grad_sol, float* grad_y0, const float* save, cudaStream_t s);
+                               const float* grad_sol, float* grad_y0, const float* save, cudaStream_t s,
+                               const LowRankG* lr = nullptr);
+size_t decoder_wgrad_partial_floats(int64_t M, int D, int n_out);
+int decoder_wgrad(const float* x, const float* g, int64_t M, int D, int n_out, float* partials, float* total, cudaStream_t s);
 int current_fold();
 // graph-resident forward chain of the folded stages (chain_fwd.cu)
 bool chain_fwd_supported(const Sage3Ctx& c);

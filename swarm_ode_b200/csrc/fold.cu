@@ -70,6 +70,49 @@ __global__ void k_fold_param_grads(const float* __restrict__ w1cat, const float*
 
 size_t padf(size_t floats) { return (floats + 63) & ~(size_t)63; }
 
+// ---- factored cotangent G = g1 @ Wd (rank n_out <= 8) ----
+// WdW3[o, c] = sum_d Wd[o, d] w3cat[d, c]      (fp64 accumulate; n_out * 2H outputs)
+__global__ void k_lr_prep(const float* __restrict__ Wd, const float* __restrict__ w3cat, int n_out, int D, int H2,
+                          float* __restrict__ WdW3) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_out * H2) return;
+  const int o = i / H2, c = i % H2;
+  double acc = 0.0;
+  for (int d = 0; d < D; ++d) acc += (double)Wd[(size_t)o * D + d] * (double)w3cat[(size_t)d * H2 + c];
+  WdW3[i] = (float)acc;
+}
+// G3[n, c] = sum_o g1[n, o] WdW3[o, c]          (= (g1 @ Wd) @ w3cat, 2H-wide; one float4 per thread)
+__global__ void k_lr_g3(const float* __restrict__ g1, const float* __restrict__ WdW3, int64_t N, int n_out, int H2,
+                        float* __restrict__ G3) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;   // float4 index
+  const int q = H2 / 4;
+  if (i >= N * q) return;
+  const int64_t n = i / q;
+  const int c = (int)(i % q) * 4;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int o = 0; o < n_out; ++o) {
+    const float g = __ldg(g1 + n * n_out + o);
+    const float4 w = __ldg(reinterpret_cast<const float4*>(WdW3 + (size_t)o * H2 + c));
+    acc.x = fmaf(g, w.x, acc.x); acc.y = fmaf(g, w.y, acc.y); acc.z = fmaf(g, w.z, acc.z); acc.w = fmaf(g, w.w, acc.w);
+  }
+  *reinterpret_cast<float4*>(G3 + n * H2 + c) = acc;
+}
+// dW3cat[d, c] += sum_o Wd[o, d] X[o, c];   db3[d] += cs * sum_o Wd[o, d] X[n_out * H2 + o]     (X = g1^T [C | 1])
+__global__ void k_lr_finish(const float* __restrict__ Wd, const float* __restrict__ X, int n_out, int D, int H2, float cs,
+                            float* __restrict__ dW3cat, float* __restrict__ db3) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= D * (H2 + 1)) return;
+  const int d = i / (H2 + 1), c = i % (H2 + 1);
+  float acc = 0.f;
+  if (c < H2) {
+    for (int o = 0; o < n_out; ++o) acc = fmaf(Wd[(size_t)o * D + d], X[(size_t)o * H2 + c], acc);
+    dW3cat[(size_t)d * H2 + c] += acc;
+  } else {
+    for (int o = 0; o < n_out; ++o) acc = fmaf(Wd[(size_t)o * D + d], X[(size_t)n_out * H2 + o], acc);
+    db3[d] += cs * acc;
+  }
+}
+
 }  // namespace
 
 void FoldWs::carve(Arena& a, const Sage3Ctx& c, int S_, bool backward) {
@@ -216,7 +259,8 @@ int integrate_fixed_folded(Sage3Ctx& c, FoldWs& f, const Tableau& tb, const floa
 }
 
 int integrate_fixed_folded_bwd(Sage3Ctx& c, FoldWs& f, const Tableau& tb, const float* sol, const float* t, int n_t,
-                               const float* grad_sol, float* grad_y0, const float* save, cudaStream_t s) {
+                               const float* grad_sol, float* grad_y0, const float* save, cudaStream_t s,
+                               const LowRankG* lr) {
   const int S = tb.S, H = c.H, H2 = 2 * c.H;
   const int64_t N = c.N, n = c.numel(), nh = N * H2;
   GN_TRY(f.prepare(c, s));
@@ -226,14 +270,20 @@ int integrate_fixed_folded_bwd(Sage3Ctx& c, FoldWs& f, const Tableau& tb, const 
   for (int st = 0; st < S; ++st) csum += tb.c_sol[st];
 
   // G = cotangent of y_{j+1}: explicit part from grad_sol plus what flowed back from later steps
-  const float* G = grad_sol + (int64_t)(n_t - 1) * n;
+  const float* G = lr ? nullptr : grad_sol + (int64_t)(n_t - 1) * n;
   float* gout = f.gcur;
   for (int j = n_t - 2; j >= 0; --j) {
     const float dt = t[j + 1] - t[j];
     const float* y = sol + (int64_t)j * n;
     f.bind_slots(c, const_cast<float*>(save), j);
     if (!save) GN_TRY(f.forward_stages(c, tb, y, dt, s, f.Cslot));  // recompute this step's stages (and C)
-    {  // G3 = G @ w3cat     [N, 2H]
+    if (lr) {  // G = g1 @ Wd is never formed:  G3 = g1 @ (Wd @ w3cat)
+      GN_PROF(s, 2.0 * N * lr->n_out * H2, 4.0 * (double)N * (H2 + lr->n_out), "lowrank_G3");
+      k_lr_prep<<<(unsigned)ceil_div64((int64_t)lr->n_out * H2, 128), 128, 0, s>>>(lr->Wd, c.w3cat, lr->n_out, c.D, H2, lr->WdW3);
+      GN_LAUNCHED();
+      k_lr_g3<<<(unsigned)ceil_div64(N * (H2 / 4), 256), 256, 0, s>>>(lr->g1, lr->WdW3, N, lr->n_out, H2, f.G3);
+      GN_LAUNCHED();
+    } else {  // G3 = G @ w3cat     [N, 2H]
       GemmNT q{};
       q.A = G; q.lda = c.D; q.B = c.w3catT; q.ldb = c.D; q.C = f.G3; q.ldc = H2; q.M = N; q.N = H2; q.K = c.D;
       q.Bsplit = c.use_tc ? c.s3T : nullptr;
@@ -301,7 +351,13 @@ int integrate_fixed_folded_bwd(Sage3Ctx& c, FoldWs& f, const Tableau& tb, const 
       for (int st = 0; st < S; ++st) { lz.in[lz.n_terms] = f.gzs[st]; lz.coef[lz.n_terms] = 1.f; ++lz.n_terms; }
       GN_TRY(lincomb(lz, s));
     }
-    {  // dW3cat += G^T @ C     [D, 2H]   (C kept by the forward pass)
+    if (lr) {  // dW3cat += Wd^T (g1^T C),  db3 += (dt sum c_s) Wd^T colsum(g1): only rows with a cotangent are read
+      GN_PROF(s, 2.0 * N * lr->n_out * H2, 4.0 * (double)N * lr->n_out, "lowrank_dW3");
+      GN_TRY(decoder_wgrad(f.Cslot, lr->g1, N, H2, lr->n_out, lr->partials, lr->X, s));
+      k_lr_finish<<<(unsigned)ceil_div64((int64_t)c.D * (H2 + 1), 256), 256, 0, s>>>(lr->Wd, lr->X, lr->n_out, c.D, H2,
+                                                                                    (float)csum * dt, c.dW3cat, c.db3);
+      GN_LAUNCHED();
+    } else {  // dW3cat += G^T @ C     [D, 2H]   (C kept by the forward pass)
       GemmTN q{};
       q.A = G; q.lda = c.D; q.P = c.D; q.B = f.Cslot; q.ldb = H2; q.Q = H2; q.Nrows = N; q.C = c.dW3cat; q.ldc = H2;
       q.colsumA = c.db3; q.colsumA_scale = (float)csum * dt;       // db3 += (dt sum c_s) colsum(G), fused

@@ -717,3 +717,51 @@ extern "C" int gnode_integrate_dopri5(const gnode_graph* g, const gnode_sage3_pa
   if (max_num_steps <= 0) max_num_steps = (1ll << 31) - 1;
   return integrate_dopri5(c, y0, t, n_t, rtol, atol, sol, stats, trace, allreduce, allreduce_user, max_num_steps, b, s);
 }
+
+// Backward of a one-step fixed-grid solve whose solution reaches the loss only through position_decoder at the last
+// time point (the training step of scripts/train_gde.py:486-493): dL/dy_1 = grad_traj_last @ dec_w has rank n_out, so
+// neither it nor its two D-wide contractions are ever formed.
+extern "C" size_t gnode_integrate_fixed_bwd_decoded_workspace_bytes(int64_t n_nodes, int32_t node_dim, int32_t hidden_dim,
+                                                                    int32_t method, int32_t n_out) {
+  const size_t base = gnode_integrate_fixed_workspace_bytes(n_nodes, node_dim, hidden_dim, method, 1);
+  Arena a(nullptr, 0);
+  a.take<float>((size_t)n_out * 2 * hidden_dim);
+  a.take<float>((size_t)n_out * 2 * hidden_dim + n_out);
+  a.take<float>(decoder_wgrad_partial_floats(n_nodes, 2 * hidden_dim, n_out));
+  return base + a.off + 256;
+}
+
+extern "C" int gnode_integrate_fixed_bwd_decoded(const gnode_graph* g, const gnode_sage3_params* p, int32_t method,
+                                                 const float* sol, const float* t, int32_t n_t,
+                                                 const float* grad_traj_last, const float* dec_w, int32_t n_out,
+                                                 const gnode_sage3_grads* grads, const void* save, size_t save_bytes,
+                                                 void* workspace, size_t workspace_bytes, gnode_stream_t stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  GN_TRY(check_graph(g, "gnode_integrate_fixed_bwd_decoded"));
+  GN_TRY(check_params(p, "gnode_integrate_fixed_bwd_decoded"));
+  const Tableau* tbp = tableau_for(method);
+  GN_ARG(tbp && method != GNODE_DOPRI5, "gnode_integrate_fixed_bwd_decoded: method %d is not a fixed-grid solver", method);
+  GN_ARG(current_fold(), "gnode_integrate_fixed_bwd_decoded: needs the folded integrator (gnode_set_fold(1))");
+  GN_ARG(n_t == 2, "gnode_integrate_fixed_bwd_decoded: exactly one solver step (n_t == 2) is supported, got n_t = %d", n_t);
+  GN_ARG(sol && t && grad_traj_last && dec_w && n_out >= 1 && n_out <= 8, "gnode_integrate_fixed_bwd_decoded: bad argument");
+  const Tableau& tb = *tbp;
+  Sage3Ctx c;
+  c.g = *g; c.g_tiles = g->tiles; c.g_tile_err = g->tile_err; c.N = g->n_nodes; c.D = p->node_dim; c.H = p->hidden_dim;
+  Arena a(workspace, workspace_bytes);
+  FoldWs f;
+  c.carve(a, tb.S, true);
+  f.carve(a, c, tb.S, true);
+  LowRankG lr{};
+  lr.g1 = grad_traj_last; lr.Wd = dec_w; lr.n_out = n_out;
+  lr.WdW3 = a.take<float>((size_t)n_out * 2 * c.H);
+  lr.X = a.take<float>((size_t)n_out * 2 * c.H + n_out);
+  lr.partials = a.take<float>(decoder_wgrad_partial_floats(c.N, 2 * c.H, n_out));
+  GN_ARENA_OK(a, "gnode_integrate_fixed_bwd_decoded");
+  GN_TRY(c.pack(*p, true, s));
+  GN_TRY(c.zero_param_grads(s));
+  if (save) GN_ARG(save_bytes >= gnode_integrate_fixed_save_bytes(c.N, c.D, c.H, method, n_t),
+                   "gnode_integrate_fixed_bwd_decoded: save buffer too small (%zu bytes)", save_bytes);
+  GN_TRY(integrate_fixed_folded_bwd(c, f, tb, sol, t, n_t, nullptr, nullptr, static_cast<const float*>(save), s, &lr));
+  if (grads) GN_TRY(c.unpack_grads(*grads, s));
+  return GNODE_OK;
+}

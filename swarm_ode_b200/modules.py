@@ -142,6 +142,15 @@ class GraphODE(nn.Module):
         graph = csr_for(edge_index, x0.size(0), holder=batch_data, validate="deferred",
                         graph_ptr=getattr(batch_data, "ptr", None),
                         max_graph_nodes=getattr(batch_data, "max_graph_nodes", None))
+        if self.ode_solver in ("euler", "midpoint", "rk4") and self.position_decoder.out_features <= 8:
+            # solver + decoder as one autograd node: lets the backward pass use the factored cotangent of the
+            # reference's training loss (see ops._IntegrateDecodeFn)
+            if torch.is_tensor(time_span) and time_span.dim() != 1:
+                raise ValueError("t must be one dimensional")
+            solution, trajectories = ops.integrate_fixed_decode(x0, graph, self.ode_func.param_list(), time_span,
+                                                                self.ode_solver, self.position_decoder.weight,
+                                                                self.position_decoder.bias)
+            return {"trajectories": trajectories, "node_features": solution, "batch": batch}
         solution = odeint(self.ode_func.bind(graph), x0, time_span, method=self.ode_solver, rtol=1e-3, atol=1e-4,
                           options={"_stats_sink": self, "allreduce": self.dopri5_allreduce})
         trajectories = ops.decode_positions(solution, self.position_decoder.weight, self.position_decoder.bias)

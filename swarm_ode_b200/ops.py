@@ -153,9 +153,10 @@ def gnode_rhs(x, graph: CSRGraph, params: Sequence[torch.Tensor]) -> torch.Tenso
 # ----------------------------------------------------------------------------------------------
 # fixed-grid integration with backprop through the solver
 # ----------------------------------------------------------------------------------------------
-class _IntegrateFixedFn(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, y0, graph: CSRGraph, method: int, t_host: Tuple[float, ...], *w):
+def _fixed_forward(ctx, y0, graph: CSRGraph, method: int, t_host: Tuple[float, ...], w):
+    """Shared forward of the fixed-grid autograd nodes: runs the solve, keeps the save area on ``ctx``.
+    Returns ``(solution, contiguous parameter list)``; the caller does ``ctx.save_for_backward``."""
+    if True:
         y0 = _f32(y0, "y0")
         w = [_f32(t, "param") for t in w]
         N, D = y0.shape
@@ -173,7 +174,7 @@ class _IntegrateFixedFn(torch.autograd.Function):
         # When a backward will follow, keep the per-stage intermediates (autograd's "tape") so the backward does
         # not recompute every stage -- unless they would not fit comfortably in free device memory.
         save = None
-        if any(ctx.needs_input_grad) and T >= 2:
+        if any(ctx.needs_input_grad) and T >= 2:   # (also true when called from _IntegrateDecodeFn: same ctx)
             nbytes = int(L.gnode_integrate_fixed_save_bytes(N, D, H, method, T))
             if nbytes > 0 and _save_fits(nbytes, y0.device):
                 save = torch.empty(nbytes, dtype=torch.uint8, device=y0.device)
@@ -185,6 +186,13 @@ class _IntegrateFixedFn(torch.autograd.Function):
         graph.schedule_tile_check()
         ctx.graph, ctx.method, ctx.t_host, ctx.save = graph, method, t_host, save
         ctx.fold = fold
+        return sol, w
+
+
+class _IntegrateFixedFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, y0, graph: CSRGraph, method: int, t_host: Tuple[float, ...], *w):
+        sol, w = _fixed_forward(ctx, y0, graph, method, t_host, w)
         ctx.save_for_backward(sol, *w)
         return sol
 
@@ -363,6 +371,101 @@ class _DecoderFn(torch.autograd.Function):
 def decode_positions(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
     """``F.linear(x, weight, bias)`` for a tall-skinny decoder (n_out <= 8) over [..., D]."""
     return _DecoderFn.apply(x, weight, bias)
+
+
+# ----------------------------------------------------------------------------------------------
+# fixed-grid integration + position decoder as one autograd node (GraphODE.forward, scripts/train_gde.py:67-100)
+# ----------------------------------------------------------------------------------------------
+class _IntegrateDecodeFn(torch.autograd.Function):
+    """``solution = odeint(...)`` and ``trajectories = position_decoder(solution)`` in one node, so that the backward
+    pass can see HOW the solution reaches the loss.  When only ``trajectories`` carries a cotangent (the training
+    loss of scripts/train_gde.py:486-490), the solve has one step and dL/dy_0 is not wanted, the cotangent of the
+    solution is the rank-2 product ``g_traj[-1] @ W_dec`` and is handed to the integrator in factored form
+    (``gnode_integrate_fixed_bwd_decoded``); every other case takes the general path."""
+
+    @staticmethod
+    def forward(ctx, y0, graph: CSRGraph, method: int, t_host: Tuple[float, ...], dec_w, dec_b, *w):
+        ctx.set_materialize_grads(False)
+        sol, w = _fixed_forward(ctx, y0, graph, method, t_host, w)            # fills ctx.{graph,method,t_host,save,fold}
+        dec_w, dec_b = _f32(dec_w, "position_decoder.weight"), _f32(dec_b, "position_decoder.bias")
+        T, N, D = sol.shape
+        n_out = dec_w.shape[0]
+        traj = torch.empty((T, N, n_out), dtype=torch.float32, device=sol.device)
+        L = _lib.lib()
+        with torch.cuda.device(sol.device):
+            _lib.check(L.gnode_decoder_fwd(_lib.ptr(sol), T * N, D, n_out, _lib.ptr(dec_w), _lib.ptr(dec_b), _lib.ptr(traj),
+                                           _lib.stream_ptr(sol.device)), "gnode_decoder_fwd")
+        ctx.save_for_backward(sol, dec_w, *w)
+        return sol, traj
+
+    @staticmethod
+    def backward(ctx, g_sol, g_traj):
+        sol, dec_w, *w = ctx.saved_tensors
+        T, N, D = sol.shape
+        H = w[0].shape[0]
+        n_out = dec_w.shape[0]
+        dev = sol.device
+        L = _lib.lib()
+        need_y0 = ctx.needs_input_grad[0]
+        need_dw, need_db = ctx.needs_input_grad[4], ctx.needs_input_grad[5]
+        p = _sage3_params(D, H, w)
+        gw = [torch.zeros_like(t) for t in w]
+        grads = _lib.GnodeSage3Grads(*[t.data_ptr() for t in gw])
+        g_dec_w = torch.zeros_like(dec_w) if (need_dw and g_traj is not None) else None
+        g_dec_b = torch.zeros(n_out, dtype=torch.float32, device=dev) if (need_db and g_traj is not None) else None
+        tarr = _float_array(ctx.t_host)
+        if g_traj is not None:
+            g_traj = _f32(g_traj, "grad_trajectories")
+        fast = g_sol is None and g_traj is not None and T == 2 and ctx.fold and not need_y0 and n_out <= 8
+        prev_fold = L.gnode_set_fold(1 if ctx.fold else 0)
+        try:
+            with torch.cuda.device(dev):
+                save = ctx.save
+                sbytes = save.numel() if save is not None else 0
+                if fast:
+                    if g_dec_w is not None or g_dec_b is not None:      # decoder parameter gradients (no dL/dsolution)
+                        ws = _ws(L.gnode_decoder_workspace_bytes(T * N, D, n_out), dev)
+                        _lib.check(L.gnode_decoder_bwd(_lib.ptr(sol), _lib.ptr(g_traj), T * N, D, n_out, _lib.ptr(dec_w),
+                                                       None, _lib.ptr(g_dec_w), _lib.ptr(g_dec_b), _lib.ptr(ws), ws.numel(),
+                                                       _lib.stream_ptr(dev)), "gnode_decoder_bwd")
+                    ws = _ws(L.gnode_integrate_fixed_bwd_decoded_workspace_bytes(N, D, H, ctx.method, n_out), dev)
+                    g_last = g_traj[T - 1]                               # contiguous [N, n_out] slice
+                    _lib.check(L.gnode_integrate_fixed_bwd_decoded(ctx.graph.ref(), C.byref(p), ctx.method, _lib.ptr(sol),
+                                                                   tarr, T, _lib.ptr(g_last), _lib.ptr(dec_w), n_out,
+                                                                   C.byref(grads), _lib.ptr(save), sbytes, _lib.ptr(ws),
+                                                                   ws.numel(), _lib.stream_ptr(dev)),
+                               "gnode_integrate_fixed_bwd_decoded")
+                    gy0 = None
+                else:
+                    if g_traj is not None:
+                        gsol = torch.empty_like(sol)
+                        ws = _ws(L.gnode_decoder_workspace_bytes(T * N, D, n_out), dev)
+                        _lib.check(L.gnode_decoder_bwd(_lib.ptr(sol), _lib.ptr(g_traj), T * N, D, n_out, _lib.ptr(dec_w),
+                                                       _lib.ptr(gsol), _lib.ptr(g_dec_w), _lib.ptr(g_dec_b), _lib.ptr(ws),
+                                                       ws.numel(), _lib.stream_ptr(dev)), "gnode_decoder_bwd")
+                        if g_sol is not None:
+                            gsol.add_(_f32(g_sol, "grad_solution"))
+                    elif g_sol is not None:
+                        gsol = _f32(g_sol, "grad_solution")
+                    else:
+                        gsol = torch.zeros_like(sol)
+                    gy0 = torch.empty((N, D), dtype=torch.float32, device=dev) if need_y0 else None
+                    ws = _ws(L.gnode_integrate_fixed_workspace_bytes(N, D, H, ctx.method, 1), dev)
+                    _lib.check(L.gnode_integrate_fixed_bwd(ctx.graph.ref(), C.byref(p), ctx.method, _lib.ptr(sol), tarr, T,
+                                                           _lib.ptr(gsol), _lib.ptr(gy0), C.byref(grads), _lib.ptr(save),
+                                                           sbytes, _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev)),
+                               "gnode_integrate_fixed_bwd")
+        finally:
+            L.gnode_set_fold(prev_fold)
+        ctx.save = None
+        return (gy0, None, None, None, g_dec_w, g_dec_b, *gw)
+
+
+def integrate_fixed_decode(y0, graph: CSRGraph, params: Sequence[torch.Tensor], t, method: str, dec_w, dec_b):
+    """``(solution [T, N, D], trajectories [T, N, n_out])`` of GraphODE.forward on a fixed grid; differentiable."""
+    if method not in ("euler", "midpoint", "rk4"):
+        raise ValueError(f"not a fixed-grid method: {method}")
+    return _IntegrateDecodeFn.apply(y0, graph, METHODS[method], _t_to_host(t), dec_w, dec_b, *params)
 
 
 # ----------------------------------------------------------------------------------------------
