@@ -473,25 +473,43 @@ __global__ void __launch_bounds__(THREADS, 2) k_chain_fwd(const Args a) {
 
 // tiles[0] = number of tiles, tiles[1 + t] = first row of tile t, tiles[1 + n_tiles] = N.  Greedy packing of whole
 // graphs (graph_ptr: node offsets, n_graphs + 1 entries) into tiles of at most TM rows; a graph larger than TM rows
-// cannot be tiled: tiles[0] = -1.
-__global__ void k_tiles_build(const int64_t* __restrict__ graph_ptr, int64_t n_graphs, int32_t* __restrict__ tiles) {
-  if (blockIdx.x != 0 || threadIdx.x != 0) return;
-  int nt = 0;
-  int64_t start = graph_ptr[0];
-  tiles[1] = (int32_t)start;
-  bool bad = false;
-  for (int64_t g = 0; g < n_graphs; ++g) {
-    const int64_t b = graph_ptr[g], e = graph_ptr[g + 1];
-    if (e - b > TM) { bad = true; break; }
-    if (e - start > TM) {           // graph g does not fit: close the tile before it
-      ++nt;
-      tiles[1 + nt] = (int32_t)b;
-      start = b;
+// cannot be tiled: tiles[0] = -1.  One block: the offsets are staged in shared memory chunk by chunk (coalesced), one
+// thread walks the chunk (the packing is inherently sequential, ~10 cycles per graph out of shared memory) and the
+// block flushes the tile starts it produced.
+constexpr int TB_CHUNK = 4096;
+__global__ void __launch_bounds__(1024) k_tiles_build(const int64_t* __restrict__ graph_ptr, int64_t n_graphs,
+                                                      int32_t* __restrict__ tiles) {
+  __shared__ int32_t sp[TB_CHUNK + 1];
+  __shared__ int32_t st[TB_CHUNK + 1];
+  __shared__ int s_nt, s_new, s_start, s_bad;
+  if (threadIdx.x == 0) { s_nt = 0; s_start = (int)graph_ptr[0]; s_bad = 0; tiles[1] = (int32_t)graph_ptr[0]; }
+  __syncthreads();
+  for (int64_t g0 = 0; g0 < n_graphs; g0 += TB_CHUNK) {
+    const int cnt = (int)((n_graphs - g0 < TB_CHUNK) ? (n_graphs - g0) : TB_CHUNK);
+    for (int i = threadIdx.x; i <= cnt; i += blockDim.x) sp[i] = (int32_t)graph_ptr[g0 + i];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int start = s_start, made = 0;
+      for (int i = 0; i < cnt; ++i) {
+        const int b = sp[i], e = sp[i + 1];
+        if (e - b > TM) s_bad = 1;
+        if (e - start > TM) { st[made++] = b; start = b; }   // graph i does not fit: a new tile starts at it
+      }
+      s_start = start;
+      s_new = made;
     }
+    __syncthreads();
+    const int base = s_nt;
+    for (int i = threadIdx.x; i < s_new; i += blockDim.x) tiles[2 + base + i] = st[i];
+    __syncthreads();
+    if (threadIdx.x == 0) s_nt = base + s_new;
+    __syncthreads();
   }
-  ++nt;
-  tiles[1 + nt] = (int32_t)graph_ptr[n_graphs];
-  tiles[0] = bad ? -1 : nt;
+  if (threadIdx.x == 0) {
+    const int nt = s_nt + 1;
+    tiles[1 + nt] = (int32_t)graph_ptr[n_graphs];
+    tiles[0] = s_bad ? -1 : nt;
+  }
 }
 
 }  // namespace chain
@@ -541,7 +559,7 @@ using namespace gnode;
 extern "C" int gnode_tiles_build(const int64_t* graph_ptr, int64_t n_graphs, int32_t* tiles, gnode_stream_t stream) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   GN_ARG(graph_ptr && tiles && n_graphs > 0, "gnode_tiles_build: bad argument");
-  chain::k_tiles_build<<<1, 32, 0, s>>>(graph_ptr, n_graphs, tiles);
+  chain::k_tiles_build<<<1, 1024, 0, s>>>(graph_ptr, n_graphs, tiles);
   GN_LAUNCHED();
   return GNODE_OK;
 }

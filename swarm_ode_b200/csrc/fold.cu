@@ -27,20 +27,25 @@ namespace gnode {
 namespace {
 
 // M13[z, c] = sum_d w1cat[z, d] w3cat[d, c];  M13T = transpose;  c13[z] = sum_d w1cat[z, d] b3[d]   (fp64 accumulate)
+// Eight lanes share one output and split the D loop (d = l, l + 8, ...); fixed-order butterfly -> deterministic.
 __global__ void k_fold_weights(const float* __restrict__ w1cat, const float* __restrict__ w3cat, const float* __restrict__ b3,
                                int H2, int D, float* __restrict__ M13, float* __restrict__ M13T, float* __restrict__ c13) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;   // cat2 feature (or H2 -> the bias column)
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = gid >> 3, l = gid & 7;                   // cat2 feature (or H2 -> the bias column), lane of the split
   const int z = blockIdx.y;
-  if (c > H2) return;
   double acc = 0.0;
   const float* wz = w1cat + (size_t)z * D;
   if (c < H2) {
-    for (int d = 0; d < D; ++d) acc += (double)wz[d] * (double)w3cat[(size_t)d * H2 + c];
-    M13[(size_t)z * H2 + c] = (float)acc;
-    M13T[(size_t)c * H2 + z] = (float)acc;
-  } else {
-    for (int d = 0; d < D; ++d) acc += (double)wz[d] * (double)b3[d];
-    c13[z] = (float)acc;
+    for (int d = l; d < D; d += 8) acc += (double)wz[d] * (double)w3cat[(size_t)d * H2 + c];
+  } else if (c == H2) {
+    for (int d = l; d < D; d += 8) acc += (double)wz[d] * (double)b3[d];
+  }
+  acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+  if (l == 0) {
+    if (c < H2) { M13[(size_t)z * H2 + c] = (float)acc; M13T[(size_t)c * H2 + z] = (float)acc; }
+    else if (c == H2) c13[z] = (float)acc;
   }
 }
 
@@ -71,15 +76,17 @@ __global__ void k_fold_param_grads(const float* __restrict__ w1cat, const float*
 size_t padf(size_t floats) { return (floats + 63) & ~(size_t)63; }
 
 // ---- factored cotangent G = g1 @ Wd (rank n_out <= 8) ----
-// WdW3[o, c] = sum_d Wd[o, d] w3cat[d, c]      (fp64 accumulate; n_out * 2H outputs)
+// WdW3[o, c] = sum_d Wd[o, d] w3cat[d, c]      (fp64 accumulate; a warp per output, lanes split the D loop)
 __global__ void k_lr_prep(const float* __restrict__ Wd, const float* __restrict__ w3cat, int n_out, int D, int H2,
                           float* __restrict__ WdW3) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, l = threadIdx.x & 31;
   if (i >= n_out * H2) return;
   const int o = i / H2, c = i % H2;
   double acc = 0.0;
-  for (int d = 0; d < D; ++d) acc += (double)Wd[(size_t)o * D + d] * (double)w3cat[(size_t)d * H2 + c];
-  WdW3[i] = (float)acc;
+  for (int d = l; d < D; d += 32) acc += (double)Wd[(size_t)o * D + d] * (double)w3cat[(size_t)d * H2 + c];
+#pragma unroll
+  for (int sft = 1; sft < 32; sft <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, sft);
+  if (l == 0) WdW3[i] = (float)acc;
 }
 // G3[n, c] = sum_o g1[n, o] WdW3[o, c]          (= (g1 @ Wd) @ w3cat, 2H-wide; one float4 per thread)
 __global__ void k_lr_g3(const float* __restrict__ g1, const float* __restrict__ WdW3, int64_t N, int n_out, int H2,
@@ -168,8 +175,8 @@ int FoldWs::prepare(Sage3Ctx& c, cudaStream_t s) {
   const int H2 = 2 * c.H;
   {
     GN_PROF(s, 2.0 * H2 * (H2 + 1) * c.D, 0.0, "fold_weights");
-    dim3 grid((unsigned)ceil_div64(H2 + 1, 128), (unsigned)H2);
-    k_fold_weights<<<grid, 128, 0, s>>>(c.w1cat, c.w3cat, c.b3, H2, c.D, M13, M13T, c13);
+    dim3 grid((unsigned)ceil_div64((int64_t)(H2 + 1) * 8, 256), (unsigned)H2);
+    k_fold_weights<<<grid, 256, 0, s>>>(c.w1cat, c.w3cat, c.b3, H2, c.D, M13, M13T, c13);
     GN_LAUNCHED();
   }
   if (c.use_tc) {
@@ -279,7 +286,7 @@ int integrate_fixed_folded_bwd(Sage3Ctx& c, FoldWs& f, const Tableau& tb, const 
     if (!save) GN_TRY(f.forward_stages(c, tb, y, dt, s, f.Cslot));  // recompute this step's stages (and C)
     if (lr) {  // G = g1 @ Wd is never formed:  G3 = g1 @ (Wd @ w3cat)
       GN_PROF(s, 2.0 * N * lr->n_out * H2, 4.0 * (double)N * (H2 + lr->n_out), "lowrank_G3");
-      k_lr_prep<<<(unsigned)ceil_div64((int64_t)lr->n_out * H2, 128), 128, 0, s>>>(lr->Wd, c.w3cat, lr->n_out, c.D, H2, lr->WdW3);
+      k_lr_prep<<<(unsigned)ceil_div64((int64_t)lr->n_out * H2 * 32, 256), 256, 0, s>>>(lr->Wd, c.w3cat, lr->n_out, c.D, H2, lr->WdW3);
       GN_LAUNCHED();
       k_lr_g3<<<(unsigned)ceil_div64(N * (H2 / 4), 256), 256, 0, s>>>(lr->g1, lr->WdW3, N, lr->n_out, H2, f.G3);
       GN_LAUNCHED();

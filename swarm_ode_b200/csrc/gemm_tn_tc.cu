@@ -252,45 +252,51 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tn_tc(const Args a) {
 }
 
 // C (+)= scale * sum_c partials[c][n][m]   with C[m, n] (n_major = 0) or C[n, m] (n_major = 1); m < wm
-// followed (same launch) by the column sums:  out_m[c] += scale_m * sum over [S][2] of colpart_m, same for n
+// followed (same launch) by the column sums:  out_m[c] += scale_m * sum over [S][2 ks] of colpart_m, same for n.
+// Four threads share one output element: thread q sums partials c = q, q + 4, ... (independent loads in flight), the
+// four sums are combined in a fixed order -> deterministic.
 __global__ void k_reduce_tn(const float* __restrict__ partials, int S, int wn, int wm, float* __restrict__ C,
                             int64_t ldc, int n_major, float scale, const float* __restrict__ colpart_m,
                             float* __restrict__ out_m, float scale_m, const float* __restrict__ colpart_n,
                             float* __restrict__ out_n, float scale_n, int ks) {
-  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (i >= (int64_t)wn * MW) {
-    i -= (int64_t)wn * MW;
+  const int64_t gid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  int64_t i = gid >> 2;
+  const int q = (int)(gid & 3);
+  const int64_t n_mat = (int64_t)wn * MW;
+  float s = 0.f;
+  bool live = false;
+  float* dst = nullptr;
+  float sc = 0.f;
+  if (i < n_mat) {
+    const int n = (int)(i / MW), m = (int)(i % MW);
+    if (m < wm) {
+      live = true;
+      for (int c = q; c < S; c += 4) s += __ldg(partials + (size_t)c * n_mat + i);
+      dst = n_major ? C + (int64_t)n * ldc + m : C + (int64_t)m * ldc + n;
+      sc = scale;
+    }
+  } else {
+    i -= n_mat;
     if (i < wm) {
       if (out_m) {
-        float s = 0.f;
-        for (int r = 0; r < 2 * ks * S; ++r) s += colpart_m[(size_t)r * wm + i];
-        out_m[i] += scale_m * s;
+        live = true;
+        for (int r = q; r < 2 * ks * S; r += 4) s += __ldg(colpart_m + (size_t)r * wm + i);
+        dst = out_m + i; sc = scale_m;
       }
     } else if (i - wm < wn) {
       i -= wm;
       if (out_n) {
-        float s = 0.f;
-        for (int r = 0; r < 2 * ks * S; ++r) s += colpart_n[(size_t)r * wn + i];
-        out_n[i] += scale_n * s;
+        live = true;
+        for (int r = q; r < 2 * ks * S; r += 4) s += __ldg(colpart_n + (size_t)r * wn + i);
+        dst = out_n + i; sc = scale_n;
       }
     }
-    return;
   }
-  const int n = (int)(i / MW), m = (int)(i % MW);
-  if (m >= wm) return;
-  float s = 0.f;
-  const size_t stride = (size_t)wn * MW;
-  int c = 0;
-  for (; c + 8 <= S; c += 8) {   // eight independent loads in flight; the additions keep the fixed order
-    float v[8];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) v[u] = __ldg(partials + (size_t)(c + u) * stride + i);
-#pragma unroll
-    for (int u = 0; u < 8; ++u) s += v[u];
-  }
-  for (; c < S; ++c) s += __ldg(partials + (size_t)c * stride + i);
-  float* dst = n_major ? C + (int64_t)n * ldc + m : C + (int64_t)m * ldc + n;
-  *dst += scale * s;
+  // the four lanes of an element are adjacent: (s0 + s1) + (s2 + s3)
+  const float s1 = __shfl_xor_sync(0xffffffffu, s, 1);
+  const float pair = (q & 1) ? (s1 + s) : (s + s1);
+  const float other = __shfl_xor_sync(0xffffffffu, pair, 2);
+  if (live && q == 0) *dst += sc * (pair + other);
 }
 
 struct Plan { bool ok; bool m_is_b; int wm, wn, bn, nt, ks; int64_t n_kb; int grid; };
@@ -366,7 +372,7 @@ int gemm_tn_tc(const GemmTN& g, float* partials, cudaStream_t s) {
   GN_LAUNCHED();
   const int64_t cnt = (int64_t)p.wn * tctn::MW + p.wm + p.wn;
   // C is [P, Q]: with the M operand = B (q = m) the partial index n is p -> rows of C are n
-  tctn::k_reduce_tn<<<(unsigned)ceil_div64(cnt, 256), 256, 0, s>>>(partials, p.grid, p.wn, p.wm, g.C, g.ldc,
+  tctn::k_reduce_tn<<<(unsigned)ceil_div64(cnt * 4, 256), 256, 0, s>>>(partials, p.grid, p.wn, p.wm, g.C, g.ldc,
                                                                     p.m_is_b ? 1 : 0, g.scale, a.colpart_m, out_m, scale_m,
                                                                     a.colpart_n, out_n, scale_n, p.ks);
   GN_LAUNCHED();
