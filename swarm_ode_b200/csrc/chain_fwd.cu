@@ -8,53 +8,41 @@
 //
 // A batch is a disjoint union of small graphs (Batch.from_data_list, scripts/train_gde.py:367): no edge leaves its
 // graph, so a tile of <= 128 consecutive rows holding WHOLE graphs carries every neighbour row its mean
-// aggregations A(.) need.  One CTA owns a tile for ALL stages of the step: the [128 x 2H] fp32 tile lives in shared
-// memory, the two small contractions run on tcgen05 (3xTF32, accumulators in TMEM), the aggregations read shared
-// memory, and HBM only sees Z_0 once on the way in and V_s / cat1_s / cat2_s (what the backward pass needs) on the
-// way out; the cat2_j re-reads of later stages hit L2 (the same CTA wrote them microseconds earlier).
+// aggregations A(.) need.  One CTA owns a tile for ALL stages of the step.  The [128 x 2H] fp32 tile lives in shared
+// memory in the UMMA operand layout (chain_common.cuh): the two small contractions read it in place (tf32 leading
+// term + weight-residual term) and take the tile's own residual as a bf16 operand from tensor memory, so a
+// contraction costs ONE hand-off between the worker warps and the MMA warp.  The aggregations read shared memory,
+// and HBM only sees Z_0 once on the way in and V_s / cat1_s / cat2_s (what the backward pass needs) on the way out;
+// the cat2_j re-reads of later stages hit L2 (the same CTA wrote them microseconds earlier).
 //
-//   warp 0      weight-image producer: M13 / w2cat K-block images (pre-split tf32 hi/lo, UMMA layout) by 1-D bulk copy
-//   warp 1      TMEM alloc + MMA issue (kind::tf32, lo*hi + hi*lo + hi*hi per K step)
-//   warps 2-9   workers: tile loads / combinations, fp32 -> hi/lo operand conversion, TMEM epilogues, aggregations,
-//               tile stores; they advance in lockstep through named barrier 1.
-#include "common.cuh"
+//   warp 0      weight-image producer: one 1-D bulk copy per K block of 16 (M13 / w2cat images, L2 resident)
+//   warp 1      TMEM alloc + MMA issue
+//   warps 2-9   workers: tile loads / combinations, residual operand, TMEM epilogues, aggregations, tile stores; they
+//               advance in lockstep through named barrier 1.
+#include "chain_common.cuh"
 #include "field.cuh"
-#include "tc_common.cuh"
 
 namespace gnode {
 namespace chain {
-using namespace tc;
 
-constexpr int TM = 128;                 // rows per tile = TMEM lanes
-constexpr int W2H = 128, WH = 64;       // 2H, H (this kernel is specialised for hidden_dim = 64)
-constexpr int TP = 132;                 // tile row pitch in floats (16-byte aligned rows)
-constexpr int BK = 8, CHUNKS = 2, NKB = W2H / BK;  // one tf32 K step per stage: small rings -> two CTAs per SM
-constexpr int LBO_A = TM * 16 + 16;
-constexpr int A_PLANE = CHUNKS * LBO_A;            // 4128
-constexpr int AOP_BYTES = 2 * A_PLANE;             // 8256
-// weight images come from presplit_weights (K blocks of 16: [hi plane: 4 chunks | lo plane: 4 chunks]); a stage of
-// this kernel takes chunks (2h, 2h+1) of both planes of K-block kb/2
-constexpr int LBO_B1 = W2H * 16 + 16, B1_PLANE16 = 4 * LBO_B1, B1_IMG16 = 2 * B1_PLANE16;   // N = 128
-constexpr int LBO_B2 = WH * 16 + 16, B2_PLANE16 = 4 * LBO_B2, B2_IMG16 = 2 * B2_PLANE16;    // N = 64
-constexpr int B_STAGE = 4 * LBO_B1;                // [hi: 2 chunks | lo: 2 chunks] of the wider image: 8256
-constexpr int N_AOP = 2, N_B = 2;
-constexpr int WORKERS = 256, THREADS = 64 + WORKERS;
-constexpr int T_BYTES = TM * TP * 4;               // 67584
-constexpr int SMEM_BYTES = T_BYTES + N_AOP * AOP_BYTES + N_B * B_STAGE;   // 100608: two CTAs per SM
-constexpr int NBR_REG = 4;                         // neighbour ids per row kept in registers
-constexpr int TMEM_COLS = 256;                     // acc1: cols 0..127, acc2: cols 128..191
+#ifdef CHAIN_TRACE
+__device__ long long g_chain_trace[128];
+#define CT(i) do { if (blockIdx.x == 0 && wt == 0 && t == blockIdx.x + 2 * (int)gridDim.x) g_chain_trace[(i)] = clock64(); } while (0)
+#else
+#define CT(i) do { } while (0)
+#endif
 
 struct Args {
   const float* z0;
   float* cat1[kMaxStages];
   float* cat2[kMaxStages];
-  float* V[kMaxStages];
+  float* V[kMaxStages];                 // V[s] may be null: not written
   float coef[kMaxStages][kMaxStages];   // dt * beta[s][j]
   float csol[kMaxStages];               // dt * c_sol[s]
   float* Cout;                          // optional: C = sum_s csol[s] cat2_s, written after the last stage
   float c13_scale[kMaxStages];          // dt * sum_j beta[s][j]
   const float *c13, *b1, *b2;
-  const float *img13, *img2;            // weight images of M13 [2H x 2H] and w2cat [H x 2H]
+  const float *img13, *img2;            // chain-format weight images of M13 [2H x 2H] and w2cat [H x 2H]
   const int32_t *rowptr, *col;
   const int32_t* tiles;                 // [0] = number of tiles, [1 ..] = first row of every tile, then N
   int S;
@@ -62,26 +50,12 @@ struct Args {
   int* err;                             // set to 1 when a neighbour lies outside its tile
 };
 
-__device__ __forceinline__ void worker_sync() { asm volatile("bar.sync 1, %0;" ::"n"(WORKERS) : "memory"); }
-
-// bounded wait that gives up immediately once any wait of this CTA has timed out
-__device__ __forceinline__ void wait_bar(uint32_t addr, uint32_t parity, volatile int* dead, int* status, int code) {
-  if (mbar_try_wait(addr, parity)) return;            // fast path: no shared-memory flag read
-  for (uint32_t i = 0; i < SPIN_LIMIT; ++i) {
-    if (mbar_try_wait(addr, parity)) return;
-    if ((i & 1023u) == 1023u && *dead) return;         // another wait of this CTA already timed out
-  }
-  *dead = 1;
-  if (status) atomicExch(status, code);
-}
-
 __global__ void __launch_bounds__(THREADS, 2) k_chain_fwd(const Args a) {
   extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ __align__(8) uint64_t bar_aop_full[N_AOP];
-  __shared__ __align__(8) uint64_t bar_aop_empty[N_AOP];
   __shared__ __align__(8) uint64_t bar_b_full[N_B];
   __shared__ __align__(8) uint64_t bar_b_empty[N_B];
-  __shared__ __align__(8) uint64_t bar_acc_full[2];
+  __shared__ __align__(8) uint64_t bar_a_ready;
+  __shared__ __align__(8) uint64_t bar_acc_full;
   __shared__ uint32_t tmem_holder;
   __shared__ int dead_flag;
 
@@ -90,17 +64,16 @@ __global__ void __launch_bounds__(THREADS, 2) k_chain_fwd(const Args a) {
   const int S = a.S;
   int* const status = a.status;
   volatile int* dead = &dead_flag;
-  float* const T = reinterpret_cast<float*>(smem);
+  uint8_t* const T = smem;
   const uint32_t smem_base = smem_u32(smem);
-  const uint32_t aop_off = T_BYTES, b_off = T_BYTES + N_AOP * AOP_BYTES;
+  const uint32_t b_off = T_BYTES;
   const int n_tiles = a.tiles[0];
 
   if (tid == 0) {
     dead_flag = 0;
-    for (int s = 0; s < N_AOP; ++s) { mbar_init(smem_u32(&bar_aop_full[s]), WORKERS); mbar_init(smem_u32(&bar_aop_empty[s]), 1); }
     for (int s = 0; s < N_B; ++s) { mbar_init(smem_u32(&bar_b_full[s]), 1); mbar_init(smem_u32(&bar_b_empty[s]), 1); }
-    mbar_init(smem_u32(&bar_acc_full[0]), 1);
-    mbar_init(smem_u32(&bar_acc_full[1]), 1);
+    mbar_init(smem_u32(&bar_a_ready), WORKERS / 32);
+    mbar_init(smem_u32(&bar_acc_full), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -121,17 +94,12 @@ __global__ void __launch_bounds__(THREADS, 2) k_chain_fwd(const Args a) {
         for (int st = 0; st < S; ++st) {
           for (int g = (st > 0 ? 0 : 1); g < 2; ++g) {           // g = 0: M13 (stage > 0 only), g = 1: w2cat
             const uint8_t* img = reinterpret_cast<const uint8_t*>(g == 0 ? a.img13 : a.img2);
-            const uint32_t lbo_b = g == 0 ? LBO_B1 : LBO_B2;
-            const uint32_t plane16 = g == 0 ? B1_PLANE16 : B2_PLANE16, img16 = g == 0 ? B1_IMG16 : B2_IMG16;
-            const uint32_t half_bytes = 2 * lbo_b;                 // two K chunks of one plane
-            for (int kb = 0; kb < NKB; ++kb) {
+            const uint32_t bytes = g == 0 ? stage_bytes(W2H) : stage_bytes(WH);
+            for (int kb = 0; kb < W2H / KB16; ++kb) {
               if (!first_lap) wait_bar(smem_u32(&bar_b_empty[s]), ph ^ 1u, dead, status, 21);
               const uint32_t bar = smem_u32(&bar_b_full[s]);
-              const uint8_t* src = img + (size_t)(kb >> 1) * img16 + (size_t)(kb & 1) * half_bytes;
-              const uint32_t dst = smem_base + b_off + s * B_STAGE;
-              mbar_expect_tx(bar, 2 * half_bytes);
-              bulk_load_1d(dst, src, half_bytes, bar);                           // hi chunks
-              bulk_load_1d(dst + half_bytes, src + plane16, half_bytes, bar);    // lo chunks
+              mbar_expect_tx(bar, bytes);
+              bulk_load_1d(smem_base + b_off + s * B_STAGE, img + (size_t)kb * bytes, bytes, bar);
               if (++s == (uint32_t)N_B) { s = 0; ph ^= 1u; first_lap = false; }
             }
           }
@@ -140,33 +108,22 @@ __global__ void __launch_bounds__(THREADS, 2) k_chain_fwd(const Args a) {
     }
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
-    const uint64_t desc_a = make_desc(0, LBO_A);
-    uint32_t sa = 0, pa = 0, sb = 0, pb = 0;
+    uint32_t pa = 0, sb = 0, pb = 0;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
       for (int st = 0; st < S; ++st) {
         for (int g = (st > 0 ? 0 : 1); g < 2; ++g) {
-          const uint32_t lbo_b = g == 0 ? LBO_B1 : LBO_B2;
-          const uint32_t idesc = make_idesc(g == 0 ? W2H : WH);
-          const uint64_t desc_b = make_desc(0, lbo_b);
-          const uint32_t tmem_d = tmem_base + (g == 0 ? 0u : (uint32_t)W2H);
-          for (int kb = 0; kb < NKB; ++kb) {
+          const int n = g == 0 ? W2H : WH;
+          wait_bar(smem_u32(&bar_a_ready), pa, dead, status, 23);   // tile + residual operand ready
+          pa ^= 1u;
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          for (int kb = 0; kb < W2H / KB16; ++kb) {
             wait_bar(smem_u32(&bar_b_full[sb]), pb, dead, status, 22);
-            wait_bar(smem_u32(&bar_aop_full[sa]), pa, dead, status, 23);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (lane == 0) {
-              const uint32_t a_hi = (smem_base + aop_off + sa * AOP_BYTES) >> 4, a_lo = a_hi + (A_PLANE >> 4);
-              const uint32_t b_hi = (smem_base + b_off + sb * B_STAGE) >> 4, b_lo = b_hi + ((2 * lbo_b) >> 4);
-              const uint64_t dah = desc_a | (uint64_t)a_hi, dal = desc_a | (uint64_t)a_lo;
-              const uint64_t dbh = desc_b | (uint64_t)b_hi, dbl = desc_b | (uint64_t)b_lo;
-              umma_tf32(tmem_d, dal, dbh, idesc, kb > 0 ? 1u : 0u);   // small terms first
-              umma_tf32(tmem_d, dah, dbl, idesc, 1u);
-              umma_tf32(tmem_d, dah, dbh, idesc, 1u);
-              umma_commit(smem_u32(&bar_aop_empty[sa]));
+              issue_kblock(tmem_base + ACC_COL, tmem_base + ALO_COL, smem_base, smem_base + b_off + sb * B_STAGE, n, kb, kb == 0);
               umma_commit(smem_u32(&bar_b_empty[sb]));
-              if (kb == NKB - 1) umma_commit(smem_u32(&bar_acc_full[g]));
+              if (kb == W2H / KB16 - 1) umma_commit(smem_u32(&bar_acc_full));
             }
             __syncwarp();
-            if (++sa == (uint32_t)N_AOP) { sa = 0; pa ^= 1u; }
             if (++sb == (uint32_t)N_B) { sb = 0; pb ^= 1u; }
           }
         }
@@ -176,60 +133,21 @@ __global__ void __launch_bounds__(THREADS, 2) k_chain_fwd(const Args a) {
     // =========================== workers ===========================
     const int wt = tid - 64;                       // 0..255
     const int cw = warp - 2;                       // 0..7
-    // converter mapping: a warp instruction covers 4 rows (two apart: conflict-free banks) x 8 k; warp cw owns rows
-    // [16 cw, 16 cw + 16), four instructions per K block
-    const int ckk = lane & 7, cr = lane >> 3;
-    const uint32_t kc_off = (uint32_t)(ckk >> 2) * LBO_A + (uint32_t)(ckk & 3) * 4u;
-    int csrc[4];
-    uint32_t cdst[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int row = 16 * cw + (q & 1) + 2 * cr + 8 * (q >> 1);
-      csrc[q] = row * TP + ckk;
-      cdst[q] = kc_off + (uint32_t)row * 16u;
-    }
-    uint32_t sa = 0, pa = 0;
-    bool first_lap_a = true;
-    uint32_t ph_acc[2] = {0u, 0u};
-    // epilogue mapping: TMEM lane quadrant of this warp, column half
+    uint32_t ph_acc = 0u;
+    // TMEM mapping: lane quadrant of this warp, column half
     const int eq = warp & 3, ehf = cw >> 2;
-    // aggregation mapping: two threads per row, 32 of the 64 channels each
-    // (threads 0..127 take channels 0..31 of rows 0..127, threads 128..255 channels 32..63: the eight lanes of a
-    // 128-bit shared-memory phase then touch eight different rows = eight different bank groups)
-    const int arow = wt & (TM - 1), ac0 = (wt >> 7) * 32;
-
-    auto convert_tile = [&]() {
-      for (int kb = 0; kb < NKB; ++kb) {
-        float v[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) v[q] = T[csrc[q] + kb * BK];
-        if (!first_lap_a) wait_bar(smem_u32(&bar_aop_empty[sa]), pa ^ 1u, dead, status, 24);
-        uint8_t* a_hi = smem + aop_off + (size_t)sa * AOP_BYTES;
-        uint8_t* a_lo = a_hi + A_PLANE;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const uint32_t hb = (__float_as_uint(v[q]) + 0x1000u) & 0xFFFFE000u;
-          *reinterpret_cast<uint32_t*>(a_hi + cdst[q]) = hb;
-          *reinterpret_cast<float*>(a_lo + cdst[q]) = v[q] - __uint_as_float(hb);
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_arrive(smem_u32(&bar_aop_full[sa]));
-        if (++sa == (uint32_t)N_AOP) { sa = 0; pa ^= 1u; first_lap_a = false; }
-      }
-    };
-    // 32 TMEM columns starting at `col` of this warp's lane quadrant -> r[]
-    auto tmem_ld32 = [&](uint32_t col, uint32_t (&r)[32]) {
-      const uint32_t taddr = tmem_base + ((uint32_t)(32 * eq) << 16) + col;
-      asm volatile(
-          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
-          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-            "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-            "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-            "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-          : "r"(taddr));
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    const int erow = 32 * eq + lane;
+    // aggregation mapping: two threads per row, 32 of the 64 channels (8 chunks) each
+    const int arow = wt & (TM - 1), ach = (wt >> 7) * 8;
+    auto Tp = [&](int chunk, int row) { return reinterpret_cast<float4*>(T + (size_t)chunk * LBO_T + row * 16); };
+    // residual operand of the whole tile (K = 128) -> tensor memory, then hand the contraction to the MMA warp
+    auto hand_off = [&]() {
+      residual_to_tmem(T, tmem_base, eq, lane, 16 * ehf, 0);
+      residual_to_tmem(T, tmem_base, eq, lane, 16 * ehf + 8, 0);
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&bar_a_ready));
     };
 
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
@@ -251,17 +169,16 @@ __global__ void __launch_bounds__(THREADS, 2) k_chain_fwd(const Args a) {
         nbr[q] = v;
       }
 
-      // mean over the in-neighbours of T[.][src_col0 + ac0 .. +32) of this thread's row
-      auto aggregate = [&](int src_col0, float4 (&acc)[8]) {
+      // mean over the in-neighbours of chunks [c0, c0 + 8) of this thread's row
+      auto aggregate = [&](int c0, float4 (&acc)[8]) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int q = 0; q < NBR_REG; ++q) {
           if (nbr[q] >= 0) {
-            const float4* src = reinterpret_cast<const float4*>(T + nbr[q] * TP + src_col0 + ac0);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              const float4 v = src[i];
+              const float4 v = *Tp(c0 + i, nbr[q]);
               acc[i].x += v.x; acc[i].y += v.y; acc[i].z += v.z; acc[i].w += v.w;
             }
           }
@@ -269,10 +186,9 @@ __global__ void __launch_bounds__(THREADS, 2) k_chain_fwd(const Args a) {
         for (int p = nb_b + NBR_REG; p < nb_e; ++p) {          // rows with more than NBR_REG neighbours
           const int nb = a.col[p] - r0;
           if (nb < 0 || nb >= nr) { *a.err = 1; continue; }
-          const float4* src = reinterpret_cast<const float4*>(T + nb * TP + src_col0 + ac0);
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const float4 v = src[i];
+            const float4 v = *Tp(c0 + i, nb);
             acc[i].x += v.x; acc[i].y += v.y; acc[i].z += v.z; acc[i].w += v.w;
           }
         }
@@ -281,151 +197,173 @@ __global__ void __launch_bounds__(THREADS, 2) k_chain_fwd(const Args a) {
       };
       // coalesced tile store: rows < nr of T -> dst[(r0 + r) * 2H + c]
       auto store_tile = [&](float* dst) {
-        for (int idx = wt; idx < TM * (W2H / 4); idx += WORKERS) {
+#pragma unroll 4
+        for (int idx = wt; idx < TM * NCHUNK; idx += WORKERS) {
           const int r = idx >> 5, c4 = idx & 31;
-          if (r < nr) *reinterpret_cast<float4*>(dst + (size_t)(r0 + r) * W2H + 4 * c4) = *reinterpret_cast<const float4*>(T + r * TP + 4 * c4);
+          if (r < nr) *reinterpret_cast<float4*>(dst + (size_t)(r0 + r) * W2H + 4 * c4) = *Tp(c4, r);
         }
       };
 
       for (int st = 0; st < S; ++st) {
-        // ---- tile input: Z_0 (stage 0) or V_st = sum_j coef * cat2_j (later stages; also written out) ----
-        // Every thread owns 16 float4 slots of the tile; all their loads are issued before the first store (the
-        // compiler cannot hoist loads over the V stores by itself).
+        CT(16 * st + 0);
+        // ---- tile input: Z_0 (stage 0) or V_st = sum_j coef * cat2_j, in place (cat2_{st-1} is still on chip; also
+        // written out for the backward pass) ----
         {
-          constexpr int SLOTS = TM * (W2H / 4) / WORKERS / 2;   // 8 per half
+          constexpr int SLOTS = TM * NCHUNK / WORKERS / 2;   // 8 per half
           for (int hf = 0; hf < 2; ++hf) {
-          const int ibase = wt + hf * SLOTS * WORKERS;
-          float4 acc[SLOTS];
-#pragma unroll
-          for (int u = 0; u < SLOTS; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (st == 0) {
-#pragma unroll
-            for (int u = 0; u < SLOTS; ++u) {
-              const int idx = ibase + u * WORKERS, r = idx >> 5, c4 = idx & 31;
-              if (r < nr) acc[u] = __ldg(reinterpret_cast<const float4*>(a.z0 + (size_t)(r0 + r) * W2H + 4 * c4));
-            }
-          } else {
-            for (int j = 0; j < st; ++j) {
-              const float cf = a.coef[st][j];
-              if (cf == 0.f) continue;
-              const float* srcj = a.cat2[j];
-              float4 v[SLOTS];
+            const int ibase = wt + hf * SLOTS * WORKERS;
+            float4 acc[SLOTS];
+            if (st == 0) {
 #pragma unroll
               for (int u = 0; u < SLOTS; ++u) {
                 const int idx = ibase + u * WORKERS, r = idx >> 5, c4 = idx & 31;
-                v[u] = (r < nr) ? *reinterpret_cast<const float4*>(srcj + (size_t)(r0 + r) * W2H + 4 * c4)   // written by this CTA: plain load
-                                : make_float4(0.f, 0.f, 0.f, 0.f);
+                acc[u] = (r < nr) ? __ldg(reinterpret_cast<const float4*>(a.z0 + (size_t)(r0 + r) * W2H + 4 * c4))
+                                  : make_float4(0.f, 0.f, 0.f, 0.f);
               }
+            } else {
+              const float cl = a.coef[st][st - 1];
 #pragma unroll
               for (int u = 0; u < SLOTS; ++u) {
-                acc[u].x = fmaf(cf, v[u].x, acc[u].x); acc[u].y = fmaf(cf, v[u].y, acc[u].y);
-                acc[u].z = fmaf(cf, v[u].z, acc[u].z); acc[u].w = fmaf(cf, v[u].w, acc[u].w);
+                const int idx = ibase + u * WORKERS, r = idx >> 5, c4 = idx & 31;
+                const float4 v = *Tp(c4, r);
+                acc[u] = (r < nr) ? make_float4(cl * v.x, cl * v.y, cl * v.z, cl * v.w) : make_float4(0.f, 0.f, 0.f, 0.f);
+              }
+              for (int j = 0; j < st - 1; ++j) {
+                const float cf = a.coef[st][j];
+                if (cf == 0.f) continue;
+                const float* srcj = a.cat2[j];
+                float4 v[SLOTS];
+#pragma unroll
+                for (int u = 0; u < SLOTS; ++u) {
+                  const int idx = ibase + u * WORKERS, r = idx >> 5, c4 = idx & 31;
+                  v[u] = (r < nr) ? *reinterpret_cast<const float4*>(srcj + (size_t)(r0 + r) * W2H + 4 * c4)   // written by this CTA: plain load
+                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int u = 0; u < SLOTS; ++u) {
+                  acc[u].x = fmaf(cf, v[u].x, acc[u].x); acc[u].y = fmaf(cf, v[u].y, acc[u].y);
+                  acc[u].z = fmaf(cf, v[u].z, acc[u].z); acc[u].w = fmaf(cf, v[u].w, acc[u].w);
+                }
+              }
+              if (a.V[st] != nullptr) {
+#pragma unroll
+                for (int u = 0; u < SLOTS; ++u) {
+                  const int idx = ibase + u * WORKERS, r = idx >> 5, c4 = idx & 31;
+                  if (r < nr) *reinterpret_cast<float4*>(a.V[st] + (size_t)(r0 + r) * W2H + 4 * c4) = acc[u];
+                }
               }
             }
 #pragma unroll
             for (int u = 0; u < SLOTS; ++u) {
               const int idx = ibase + u * WORKERS, r = idx >> 5, c4 = idx & 31;
-              if (r < nr) *reinterpret_cast<float4*>(a.V[st] + (size_t)(r0 + r) * W2H + 4 * c4) = acc[u];
+              *Tp(c4, r) = acc[u];
             }
           }
-#pragma unroll
-          for (int u = 0; u < SLOTS; ++u) {
-            const int idx = ibase + u * WORKERS, r = idx >> 5, c4 = idx & 31;
-            *reinterpret_cast<float4*>(T + r * TP + 4 * c4) = acc[u];
-          }
-          }
         }
-        worker_sync();
+        worker_sync_w();
+        CT(16 * st + 1);
         if (st > 0) {
           // ---- Z_st = Z_0 + V_st @ M13^T + scale * c13 ----
-          convert_tile();
-          wait_bar(smem_u32(&bar_acc_full[0]), ph_acc[0], dead, status, 25);
-          ph_acc[0] ^= 1u;
+          hand_off();
+          CT(16 * st + 2);
+          const float cs = a.c13_scale[st];
+          const bool rin = erow < nr;
+          const float4* zp = reinterpret_cast<const float4*>(a.z0 + (size_t)(r0 + (rin ? erow : 0)) * W2H + 64 * ehf);
+          // this lane's Z_0 row segment (32 floats = one 128-byte line) is requested before the accumulator is ready
+          float4 z[2][8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) z[0][i] = __ldg(zp + i);
+          wait_bar(smem_u32(&bar_acc_full), ph_acc, dead, status, 25);
+          ph_acc ^= 1u;
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          {
-            const float cs = a.c13_scale[st];
-            const int row = 32 * eq + lane;
-            const bool rin = row < nr;
+          CT(16 * st + 3);
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const int c0 = 64 * ehf + 32 * h;
-              // this lane's Z_0 row segment (32 floats = one 128-byte line) is requested before the TMEM load returns
-              float4 z[8];
-              const float4* zp = reinterpret_cast<const float4*>(a.z0 + (size_t)(r0 + (rin ? row : 0)) * W2H + c0);
+          for (int i = 0; i < 8; ++i) z[1][i] = __ldg(zp + 8 + i);
 #pragma unroll
-              for (int i = 0; i < 8; ++i) z[i] = rin ? __ldg(zp + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-              uint32_t r[32];
-              tmem_ld32((uint32_t)c0, r);
-              float* trow = T + row * TP + c0;
+          for (int h = 0; h < 2; ++h) {
+            const int c0 = 64 * ehf + 32 * h;
+            uint32_t r[32];
+            tmem_ld32(tmem_base, eq, (uint32_t)(ACC_COL + c0), r);
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const float4 c = __ldg(reinterpret_cast<const float4*>(a.c13 + c0) + i);
-                float4 o;
-                o.x = __uint_as_float(r[4 * i + 0]) + z[i].x + cs * c.x;
-                o.y = __uint_as_float(r[4 * i + 1]) + z[i].y + cs * c.y;
-                o.z = __uint_as_float(r[4 * i + 2]) + z[i].z + cs * c.z;
-                o.w = __uint_as_float(r[4 * i + 3]) + z[i].w + cs * c.w;
-                *reinterpret_cast<float4*>(trow + 4 * i) = o;
-              }
+            for (int i = 0; i < 8; ++i) {
+              const float4 c = __ldg(reinterpret_cast<const float4*>(a.c13 + c0) + i);
+              float4 o;
+              o.x = __uint_as_float(r[4 * i + 0]) + z[h][i].x + cs * c.x;
+              o.y = __uint_as_float(r[4 * i + 1]) + z[h][i].y + cs * c.y;
+              o.z = __uint_as_float(r[4 * i + 2]) + z[h][i].z + cs * c.z;
+              o.w = __uint_as_float(r[4 * i + 3]) + z[h][i].w + cs * c.w;
+              *Tp(c0 / 4 + i, erow) = o;
             }
           }
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-          worker_sync();
+          worker_sync_w();
         }
+        CT(16 * st + 4);
         // ---- h1 = relu(A(Z_l) + Z_r + b1) -> right half (in place) ----
         if (arow < nr) {
           float4 acc[8];
-          aggregate(0, acc);
-          float4* own = reinterpret_cast<float4*>(T + arow * TP + WH + ac0);
-          const float4* bb = reinterpret_cast<const float4*>(a.b1 + ac0);
+          aggregate(ach, acc);
+          const float4* bb = reinterpret_cast<const float4*>(a.b1 + 4 * ach);
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const float4 z = own[i], b = __ldg(bb + i);
+            float4* own = Tp(16 + ach + i, arow);
+            const float4 z = *own, b = __ldg(bb + i);
             float4 h;
             h.x = fmaxf(acc[i].x + z.x + b.x, 0.f); h.y = fmaxf(acc[i].y + z.y + b.y, 0.f);
             h.z = fmaxf(acc[i].z + z.z + b.z, 0.f); h.w = fmaxf(acc[i].w + z.w + b.w, 0.f);
-            own[i] = h;
+            *own = h;
           }
         }
-        worker_sync();
+        worker_sync_w();
+        CT(16 * st + 5);
         // ---- A(h1) -> left half: the tile is now cat1 ----
         if (arow < nr) {
           float4 acc[8];
-          aggregate(WH, acc);
-          float4* dstp = reinterpret_cast<float4*>(T + arow * TP + ac0);
+          aggregate(16 + ach, acc);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) dstp[i] = acc[i];
+          for (int i = 0; i < 8; ++i) *Tp(ach + i, arow) = acc[i];
         }
-        worker_sync();
+        worker_sync_w();
+        CT(16 * st + 6);
+        // ---- h2 = relu(cat1 @ w2cat^T + b2) -> right half; cat1 goes out while the contraction runs ----
+        hand_off();
+        CT(16 * st + 7);
         store_tile(a.cat1[st]);
-        // ---- h2 = relu(cat1 @ w2cat^T + b2) -> right half ----
-        convert_tile();
-        wait_bar(smem_u32(&bar_acc_full[1]), ph_acc[1], dead, status, 26);
-        ph_acc[1] ^= 1u;
+        CT(16 * st + 8);
+        wait_bar(smem_u32(&bar_acc_full), ph_acc, dead, status, 26);
+        ph_acc ^= 1u;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         {
           uint32_t r[32];
-          const int c0 = 32 * ehf;
-          tmem_ld32((uint32_t)(W2H + c0), r);
-          float* trow = T + (32 * eq + lane) * TP + WH + c0;
+          tmem_ld32(tmem_base, eq, (uint32_t)(ACC_COL + 32 * ehf), r);
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          worker_sync();                       // every thread has finished reading the tile for the cat1 store
+          CT(16 * st + 9);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) trow[j] = fmaxf(__uint_as_float(r[j]) + __ldg(a.b2 + c0 + j), 0.f);
+          for (int i = 0; i < 8; ++i) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(a.b2 + 32 * ehf) + i);
+            float4 h;
+            h.x = fmaxf(__uint_as_float(r[4 * i + 0]) + b.x, 0.f); h.y = fmaxf(__uint_as_float(r[4 * i + 1]) + b.y, 0.f);
+            h.z = fmaxf(__uint_as_float(r[4 * i + 2]) + b.z, 0.f); h.w = fmaxf(__uint_as_float(r[4 * i + 3]) + b.w, 0.f);
+            *Tp(16 + 8 * ehf + i, erow) = h;
+          }
         }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        worker_sync();
+        worker_sync_w();
+        CT(16 * st + 10);
         // ---- A(h2) -> left half: the tile is now cat2 ----
         if (arow < nr) {
           float4 acc[8];
-          aggregate(WH, acc);
-          float4* dstp = reinterpret_cast<float4*>(T + arow * TP + ac0);
+          aggregate(16 + ach, acc);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) dstp[i] = acc[i];
+          for (int i = 0; i < 8; ++i) *Tp(ach + i, arow) = acc[i];
         }
-        worker_sync();
+        worker_sync_w();
+        CT(16 * st + 11);
         store_tile(a.cat2[st]);
+        CT(16 * st + 12);
         if (st == S - 1 && a.Cout != nullptr) {
           // C = sum_s csol[s] cat2_s: the last cat2 tile is still on chip, the earlier ones come back from L2
-          constexpr int SLOTS = TM * (W2H / 4) / WORKERS / 2;
+          constexpr int SLOTS = TM * NCHUNK / WORKERS / 2;
           for (int hf = 0; hf < 2; ++hf) {
             const int ibase = wt + hf * SLOTS * WORKERS;
             float4 acc[SLOTS];
@@ -433,7 +371,7 @@ __global__ void __launch_bounds__(THREADS, 2) k_chain_fwd(const Args a) {
 #pragma unroll
             for (int u = 0; u < SLOTS; ++u) {
               const int idx = ibase + u * WORKERS, r = idx >> 5, c4 = idx & 31;
-              const float4 v = *reinterpret_cast<const float4*>(T + r * TP + 4 * c4);
+              const float4 v = *Tp(c4, r);
               acc[u] = make_float4(cl * v.x, cl * v.y, cl * v.z, cl * v.w);
             }
             for (int j = 0; j < st; ++j) {
@@ -459,7 +397,8 @@ __global__ void __launch_bounds__(THREADS, 2) k_chain_fwd(const Args a) {
             }
           }
         }
-        worker_sync();      // the tile buffer is reused by the next stage; its cat2 rows are visible to this CTA
+        worker_sync();      // the tile buffer is modified by the next stage; its cat2 rows are visible to this CTA
+        CT(16 * st + 13);
       }
     }
   }
@@ -469,6 +408,47 @@ __global__ void __launch_bounds__(THREADS, 2) k_chain_fwd(const Args a) {
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS));
   }
+}
+
+// chain-format weight image (chain_common.cuh): one 16-byte unit per thread
+__global__ void k_pack_image(const float* __restrict__ W, int n, int k, int64_t ld, uint4* __restrict__ img) {
+  const int units_per_chunk = n + 1, units_per_stage = 10 * units_per_chunk;
+  const int64_t total = (int64_t)(k / KB16) * units_per_stage;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int kb = (int)(i / units_per_stage), u = (int)(i % units_per_stage);
+    const int chunk = u / units_per_chunk, row = u % units_per_chunk;
+    uint4 out = make_uint4(0u, 0u, 0u, 0u);
+    if (row < n) {
+      const float* src = W + (size_t)row * ld + kb * KB16;
+      if (chunk < 8) {
+        const int c = chunk & 3;
+        uint32_t v[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float w = src[4 * c + e];
+          const uint32_t hb = (__float_as_uint(w) + 0x1000u) & 0xFFFFE000u;
+          v[e] = chunk < 4 ? hb : __float_as_uint(w - __uint_as_float(hb));
+        }
+        out = make_uint4(v[0], v[1], v[2], v[3]);
+      } else {
+        const int c = chunk - 8;
+        uint32_t v[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(v[e]) : "f"(src[8 * c + 2 * e + 1]), "f"(src[8 * c + 2 * e]));
+        }
+        out = make_uint4(v[0], v[1], v[2], v[3]);
+      }
+    }
+    img[i] = out;
+  }
+}
+
+int pack_image(const float* W, int n, int k, int64_t ld, float* img, cudaStream_t s) {
+  const int64_t total = (int64_t)(k / KB16) * 10 * (n + 1);
+  k_pack_image<<<(unsigned)ceil_div64(total, 256), 256, 0, s>>>(W, n, k, ld, reinterpret_cast<uint4*>(img));
+  GN_LAUNCHED();
+  return GNODE_OK;
 }
 
 // tiles[0] = number of tiles, tiles[1 + t] = first row of tile t, tiles[1 + n_tiles] = N.  Greedy packing of whole
@@ -516,7 +496,10 @@ __global__ void __launch_bounds__(1024) k_tiles_build(const int64_t* __restrict_
 
 namespace tc { int* status_ptr(); }
 
-bool chain_fwd_supported(const Sage3Ctx& c) { return c.H == chain::WH && c.use_tc && c.g_tiles != nullptr; }
+size_t chain_image_floats(int n, int k) { return chain::image_floats(n, k); }
+int chain_pack_image(const float* W, int n, int k, int64_t ld, float* img, cudaStream_t s) { return chain::pack_image(W, n, k, ld, img, s); }
+bool chain_shape_ok(int H) { return H == chain::WH; }
+bool chain_fwd_supported(const Sage3Ctx& c) { return c.H == chain::WH && c.use_tc && c.g_tiles != nullptr && c.ci2 != nullptr; }
 
 int chain_fwd(Sage3Ctx& c, FoldWs& f, const Tableau& tb, float dt, float* Cout, cudaStream_t s) {
   int* status_dev = tc::status_ptr();
@@ -532,7 +515,7 @@ int chain_fwd(Sage3Ctx& c, FoldWs& f, const Tableau& tb, float dt, float* Cout, 
   }
   a.Cout = Cout;
   a.c13 = f.c13; a.b1 = c.b1; a.b2 = c.b2;
-  a.img13 = f.sM13; a.img2 = c.s2;
+  a.img13 = f.ci13; a.img2 = c.ci2;
   a.rowptr = c.g.rowptr; a.col = c.g.col;
   a.tiles = c.g_tiles;
   a.S = tb.S;
@@ -554,6 +537,12 @@ int chain_fwd(Sage3Ctx& c, FoldWs& f, const Tableau& tb, float dt, float* Cout, 
 }  // namespace gnode
 
 using namespace gnode;
+
+#ifdef CHAIN_TRACE
+extern "C" int gnode_chain_trace(long long* out128) {
+  return (int)cudaMemcpyFromSymbol(out128, chain::g_chain_trace, sizeof(long long) * 128);
+}
+#endif
 
 // tiles: device int32 [n_graphs + 2].  graph_ptr: device int64 [n_graphs + 1] node offsets of the graphs of the batch.
 extern "C" int gnode_tiles_build(const int64_t* graph_ptr, int64_t n_graphs, int32_t* tiles, gnode_stream_t stream) {

@@ -42,6 +42,7 @@ struct Sage3Ctx : Field {
   float *w1catT = nullptr, *w2catT = nullptr, *w3catT = nullptr;
   // tf32 hi/lo planes of the six packed matrices for the tcgen05 engine (null -> FFMA engine)
   float *s1 = nullptr, *s2 = nullptr, *s3 = nullptr, *s1T = nullptr, *s2T = nullptr, *s3T = nullptr;
+  float *ci2 = nullptr, *ci2T = nullptr;   // chain-kernel images (chain_common.cuh) of w2cat [H x 2H] and w2catT [2H x H]
   bool use_tc = false;
   float* z = nullptr;                  // [N, 2H]  x @ w1cat^T
   int n_slots = 1;
@@ -69,6 +70,7 @@ struct FoldWs {
   int S = 0;
   float *M13 = nullptr, *M13T = nullptr, *c13 = nullptr;   // w1cat @ w3cat [2H, 2H], its transpose, w1cat @ b3 [2H]
   float *sM13 = nullptr, *sM13T = nullptr;                 // tf32 hi/lo planes of the two
+  float *ci13 = nullptr, *ci13T = nullptr;                 // chain-kernel images of the two
   float *z0 = nullptr, *Cbuf = nullptr;                    // [N, 2H]
   float* Cslot = nullptr;                                  // C = dt sum_s c_s cat2_s of the current step (save area or Cbuf)
   float* Vws[kMaxStages] = {};                             // workspace V_s (when nothing is saved)
@@ -102,6 +104,9 @@ size_t decoder_wgrad_partial_floats(int64_t M, int D, int n_out);
 int decoder_wgrad(const float* x, const float* g, int64_t M, int D, int n_out, float* partials, float* total, cudaStream_t s);
 int current_fold();
 // graph-resident forward chain of the folded stages (chain_fwd.cu)
+size_t chain_image_floats(int n, int k);
+int chain_pack_image(const float* W, int n, int k, int64_t ld, float* img, cudaStream_t s);
+bool chain_shape_ok(int H);
 bool chain_fwd_supported(const Sage3Ctx& c);
 int chain_fwd(Sage3Ctx& c, FoldWs& f, const Tableau& tb, float dt, float* Cout, cudaStream_t s);
 

@@ -131,6 +131,10 @@ void FoldWs::carve(Arena& a, const Sage3Ctx& c, int S_, bool backward) {
   c13 = a.take<float>(H2);
   sM13 = a.take<float>(presplit_floats(H2, H2));
   sM13T = a.take<float>(presplit_floats(H2, H2));
+  if (chain_shape_ok(c.H)) {
+    ci13 = a.take<float>(chain_image_floats(H2, H2));
+    ci13T = a.take<float>(chain_image_floats(H2, H2));
+  }
   z0 = a.take<float>(nh);
   Cbuf = a.take<float>(nh);
   for (int i = 1; i < S; ++i) Vws[i] = a.take<float>(nh);
@@ -182,6 +186,10 @@ int FoldWs::prepare(Sage3Ctx& c, cudaStream_t s) {
   if (c.use_tc) {
     GN_TRY(presplit_weights(M13, H2, H2, H2, sM13, s));
     GN_TRY(presplit_weights(M13T, H2, H2, H2, sM13T, s));
+    if (chain_shape_ok(c.H)) {
+      GN_TRY(chain_pack_image(M13, H2, H2, H2, ci13, s));
+      GN_TRY(chain_pack_image(M13T, H2, H2, H2, ci13T, s));
+    }
   }
   return GNODE_OK;
 }

@@ -20,6 +20,7 @@ void Sage3Ctx::carve(Arena& a, int slots, bool backward) {
   s1 = a.take<float>(presplit_floats(2 * H, D));
   s2 = a.take<float>(presplit_floats(H, 2 * H));
   s3 = a.take<float>(presplit_floats(D, 2 * H));
+  if (chain_shape_ok(H)) ci2 = a.take<float>(chain_image_floats(H, 2 * H));
   z = a.take<float>(n * 2 * H);
   for (int i = 0; i < slots; ++i) {
     cat1[i] = a.take<float>(n * 2 * H);
@@ -32,6 +33,7 @@ void Sage3Ctx::carve(Arena& a, int slots, bool backward) {
     s1T = a.take<float>(presplit_floats(D, 2 * H));
     s2T = a.take<float>(presplit_floats(2 * H, H));
     s3T = a.take<float>(presplit_floats(2 * H, D));
+    if (chain_shape_ok(H)) ci2T = a.take<float>(chain_image_floats(2 * H, H));
     gcat = a.take<float>(n * 2 * H);
     gz = a.take<float>(n * 2 * H);
     gv2 = a.take<float>(n * H);
@@ -78,6 +80,10 @@ int Sage3Ctx::pack(const gnode_sage3_params& p, bool backward, cudaStream_t s) {
     GN_TRY(presplit_weights(w1cat, 2 * H, D, D, s1, s));
     GN_TRY(presplit_weights(w2cat, H, 2 * H, 2 * H, s2, s));
     GN_TRY(presplit_weights(w3cat, D, 2 * H, 2 * H, s3, s));
+    if (chain_shape_ok(H)) {
+      GN_TRY(chain_pack_image(w2cat, H, 2 * H, 2 * H, ci2, s));
+      if (backward) GN_TRY(chain_pack_image(w2catT, 2 * H, H, H, ci2T, s));
+    }
     if (backward) {
       GN_TRY(presplit_weights(w1catT, D, 2 * H, 2 * H, s1T, s));
       GN_TRY(presplit_weights(w2catT, 2 * H, H, H, s2T, s));
