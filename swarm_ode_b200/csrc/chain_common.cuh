@@ -24,9 +24,13 @@ using namespace tc;
 
 constexpr int TM = 128;                       // rows per tile = TMEM lanes
 constexpr int W2H = 128, WH = 64;             // 2H, H (the chain kernels are specialised for hidden_dim = 64)
-constexpr int LBO_T = TM * 16 + 16;           // 2064: distance of the 16-byte column chunks of the tile
 constexpr int NCHUNK = W2H / 4;               // 32
-constexpr int T_BYTES = NCHUNK * LBO_T;       // 66048
+// The tile keeps only TR = round_up(max rows of the CTA's tiles, 8) rows per chunk: chunk pitch lbo_t = 16 TR + 16.
+// The MMA still reads 128 rows per chunk (rows >= TR alias the following chunks: garbage in accumulator lanes that
+// nobody reads).  95-node graphs (12 AGVs + 7 pickers x 5 snapshots) need 49.7 KB instead of 66 KB, which buys a third
+// slot of the weight ring.
+__host__ __device__ constexpr int lbo_t_of(int tr) { return tr * 16 + 16; }
+__host__ __device__ constexpr int t_bytes_of(int tr) { return NCHUNK * lbo_t_of(tr); }
 constexpr int KB16 = 16;                      // K per pipeline stage of the weight stream
 constexpr int WORKERS = 256, THREADS = 64 + WORKERS;
 constexpr int NBR_REG = 4;                    // neighbour ids per row kept in registers
@@ -36,8 +40,12 @@ constexpr int TMEM_COLS = 256;
 __host__ __device__ constexpr int lbo_b(int n) { return n * 16 + 16; }
 __host__ __device__ constexpr int stage_bytes(int n) { return 10 * lbo_b(n); }     // hi 4 + lo 4 + bf16 2 chunks
 constexpr int B_STAGE = stage_bytes(W2H);     // 20640: ring slot (the N = 64 image uses half of it)
-constexpr int N_B = 2;
-constexpr int SMEM_BYTES = T_BYTES + N_B * B_STAGE;   // 107328: two CTAs per SM
+constexpr int MAX_SLOTS = 4;
+constexpr int SMEM_BYTES = t_bytes_of(96) + 3 * B_STAGE;   // 111584: two CTAs per SM; 2 slots for 128-row tiles, 3 for <= 96 rows
+__host__ __device__ constexpr int ring_slots(int tr) {
+  return (SMEM_BYTES - t_bytes_of(tr)) / B_STAGE > MAX_SLOTS ? MAX_SLOTS : (SMEM_BYTES - t_bytes_of(tr)) / B_STAGE;
+}
+static_assert(ring_slots(128) >= 2, "ring too small");
 
 inline size_t image_floats(int n, int k) { return (size_t)(k / KB16) * stage_bytes(n) / 4; }
 // img <- chain-format image of row-major W [n x k] (row stride ld); n % 8 == 0, k % 16 == 0
@@ -78,14 +86,14 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, u
 }
 
 // One K = 16 block of the three-term product: tile chunks [4 kb, 4 kb + 4) x weight stage at `bstage`.
-__device__ __forceinline__ void issue_kblock(uint32_t tmem_acc, uint32_t tmem_alo, uint32_t tile_addr, uint32_t bstage, int n,
-                                             int kb, bool first) {
+__device__ __forceinline__ void issue_kblock(uint32_t tmem_acc, uint32_t tmem_alo, uint32_t tile_addr, uint32_t lbo_t,
+                                             uint32_t bstage, int n, int kb, bool first) {
   const uint32_t lb = (uint32_t)lbo_b(n);
-  const uint64_t dT = make_desc(0, LBO_T), dB = make_desc(0, lb);
+  const uint64_t dT = make_desc(0, lbo_t), dB = make_desc(0, lb);
   const uint32_t idf = make_idesc(n), idb = make_idesc_bf16(n);
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
-    const uint64_t da = dT | (uint64_t)(((tile_addr + (uint32_t)(4 * kb + 2 * h) * LBO_T) >> 4) & 0x3FFF);
+    const uint64_t da = dT | (uint64_t)(((tile_addr + (uint32_t)(4 * kb + 2 * h) * lbo_t) >> 4) & 0x3FFF);
     const uint64_t dlo = dB | (uint64_t)(((bstage + (uint32_t)(4 + 2 * h) * lb) >> 4) & 0x3FFF);
     const uint64_t dhi = dB | (uint64_t)(((bstage + (uint32_t)(2 * h) * lb) >> 4) & 0x3FFF);
     umma_tf32(tmem_acc, da, dlo, idf, (first && h == 0) ? 0u : 1u);    // small term first
@@ -128,12 +136,16 @@ __device__ __forceinline__ uint32_t residual_pair(float x, float y) {
 
 // Residual operand of the tile -> tensor memory.  Thread (row = 32 eq + lane, part): chunks [c_first, c_first + 8) of
 // its row = 32 k values = 16 TMEM columns starting at ALO_COL + 2 (c_first - c_base).
-__device__ __forceinline__ void residual_to_tmem(const uint8_t* tile, uint32_t tmem_base, int eq, int lane, int c_first, int c_base) {
+// Rows >= tr do not exist in the tile: zeros (warp-uniform skip when the whole quadrant is out of range).
+__device__ __forceinline__ void residual_to_tmem(const uint8_t* tile, int lbo_t, int tr, uint32_t tmem_base, int eq, int lane,
+                                                 int c_first, int c_base) {
+  if (32 * eq >= tr) return;
   const int row = 32 * eq + lane;
   uint32_t p[16];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    const float4 x = *reinterpret_cast<const float4*>(tile + (size_t)(c_first + i) * LBO_T + row * 16);
+    const float4 x = row < tr ? *reinterpret_cast<const float4*>(tile + (size_t)(c_first + i) * lbo_t + row * 16)
+                              : make_float4(0.f, 0.f, 0.f, 0.f);
     p[2 * i] = residual_pair(x.x, x.y);
     p[2 * i + 1] = residual_pair(x.z, x.w);
   }

@@ -12,7 +12,7 @@
 // memory in the UMMA operand layout (chain_common.cuh): the two small contractions read it in place (tf32 leading
 // term + weight-residual term) and take the tile's own residual as a bf16 operand from tensor memory, so a
 // contraction costs ONE hand-off between the worker warps and the MMA warp.  The aggregations read shared memory,
-// and HBM only sees Z_0 once on the way in and V_s / cat1_s / cat2_s (what the backward pass needs) on the way out;
+// and HBM only sees Z_0 once on the way in and cat1_s / cat2_s / C (what the backward pass needs) on the way out;
 // the cat2_j re-reads of later stages hit L2 (the same CTA wrote them microseconds earlier).
 //
 //   warp 0      weight-image producer: one 1-D bulk copy per K block of 16 (M13 / w2cat images, L2 resident)
@@ -36,7 +36,6 @@ struct Args {
   const float* z0;
   float* cat1[kMaxStages];
   float* cat2[kMaxStages];
-  float* V[kMaxStages];                 // V[s] may be null: not written
   float coef[kMaxStages][kMaxStages];   // dt * beta[s][j]
   float csol[kMaxStages];               // dt * c_sol[s]
   float* Cout;                          // optional: C = sum_s csol[s] cat2_s, written after the last stage
@@ -50,40 +49,23 @@ struct Args {
   int* err;                             // set to 1 when a neighbour lies outside its tile
 };
 
-__global__ void __launch_bounds__(THREADS, 2) k_chain_fwd(const Args a) {
-  extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ __align__(8) uint64_t bar_b_full[N_B];
-  __shared__ __align__(8) uint64_t bar_b_empty[N_B];
-  __shared__ __align__(8) uint64_t bar_a_ready;
-  __shared__ __align__(8) uint64_t bar_acc_full;
-  __shared__ uint32_t tmem_holder;
-  __shared__ int dead_flag;
-
+template <int TR>
+__device__ __forceinline__ void chain_fwd_body(const Args& a, uint8_t* smem, uint64_t* bar_b_full, uint64_t* bar_b_empty,
+                                               uint64_t* bar_a_ready_p, uint64_t* bar_acc_full_p, uint32_t tmem_base,
+                                               int* dead_flag_p) {
+  constexpr int lbo_t = lbo_t_of(TR);
+  constexpr uint32_t b_off = (uint32_t)t_bytes_of(TR);
+  constexpr uint32_t n_slots = (uint32_t)ring_slots(TR);
+  uint64_t& bar_a_ready = *bar_a_ready_p;
+  uint64_t& bar_acc_full = *bar_acc_full_p;
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
   const int S = a.S;
   int* const status = a.status;
-  volatile int* dead = &dead_flag;
+  volatile int* dead = dead_flag_p;
   uint8_t* const T = smem;
   const uint32_t smem_base = smem_u32(smem);
-  const uint32_t b_off = T_BYTES;
   const int n_tiles = a.tiles[0];
-
-  if (tid == 0) {
-    dead_flag = 0;
-    for (int s = 0; s < N_B; ++s) { mbar_init(smem_u32(&bar_b_full[s]), 1); mbar_init(smem_u32(&bar_b_empty[s]), 1); }
-    mbar_init(smem_u32(&bar_a_ready), WORKERS / 32);
-    mbar_init(smem_u32(&bar_acc_full), 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_holder)), "r"((uint32_t)TMEM_COLS));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem_base = tmem_holder;
 
   if (warp == 0) {
     // =========================== weight-image producer ===========================
@@ -100,7 +82,7 @@ __global__ void __launch_bounds__(THREADS, 2) k_chain_fwd(const Args a) {
               const uint32_t bar = smem_u32(&bar_b_full[s]);
               mbar_expect_tx(bar, bytes);
               bulk_load_1d(smem_base + b_off + s * B_STAGE, img + (size_t)kb * bytes, bytes, bar);
-              if (++s == (uint32_t)N_B) { s = 0; ph ^= 1u; first_lap = false; }
+              if (++s == n_slots) { s = 0; ph ^= 1u; first_lap = false; }
             }
           }
         }
@@ -119,12 +101,12 @@ __global__ void __launch_bounds__(THREADS, 2) k_chain_fwd(const Args a) {
           for (int kb = 0; kb < W2H / KB16; ++kb) {
             wait_bar(smem_u32(&bar_b_full[sb]), pb, dead, status, 22);
             if (lane == 0) {
-              issue_kblock(tmem_base + ACC_COL, tmem_base + ALO_COL, smem_base, smem_base + b_off + sb * B_STAGE, n, kb, kb == 0);
+              issue_kblock(tmem_base + ACC_COL, tmem_base + ALO_COL, smem_base, (uint32_t)lbo_t, smem_base + b_off + sb * B_STAGE, n, kb, kb == 0);
               umma_commit(smem_u32(&bar_b_empty[sb]));
               if (kb == W2H / KB16 - 1) umma_commit(smem_u32(&bar_acc_full));
             }
             __syncwarp();
-            if (++sb == (uint32_t)N_B) { sb = 0; pb ^= 1u; }
+            if (++sb == n_slots) { sb = 0; pb ^= 1u; }
           }
         }
       }
@@ -139,11 +121,12 @@ __global__ void __launch_bounds__(THREADS, 2) k_chain_fwd(const Args a) {
     const int erow = 32 * eq + lane;
     // aggregation mapping: two threads per row, 32 of the 64 channels (8 chunks) each
     const int arow = wt & (TM - 1), ach = (wt >> 7) * 8;
-    auto Tp = [&](int chunk, int row) { return reinterpret_cast<float4*>(T + (size_t)chunk * LBO_T + row * 16); };
+    auto Tp = [&](int chunk, int row) { return reinterpret_cast<float4*>(T + (size_t)chunk * lbo_t + row * 16); };
+    constexpr int n_slots_t = TR * NCHUNK;                // float4 slots of the tile (tile-linear mapping: idx -> row idx >> 5, chunk idx & 31)
     // residual operand of the whole tile (K = 128) -> tensor memory, then hand the contraction to the MMA warp
     auto hand_off = [&]() {
-      residual_to_tmem(T, tmem_base, eq, lane, 16 * ehf, 0);
-      residual_to_tmem(T, tmem_base, eq, lane, 16 * ehf + 8, 0);
+      residual_to_tmem(T, lbo_t, TR, tmem_base, eq, lane, 16 * ehf, 0);
+      residual_to_tmem(T, lbo_t, TR, tmem_base, eq, lane, 16 * ehf + 8, 0);
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
@@ -198,16 +181,15 @@ __global__ void __launch_bounds__(THREADS, 2) k_chain_fwd(const Args a) {
       // coalesced tile store: rows < nr of T -> dst[(r0 + r) * 2H + c]
       auto store_tile = [&](float* dst) {
 #pragma unroll 4
-        for (int idx = wt; idx < TM * NCHUNK; idx += WORKERS) {
+        for (int idx = wt; idx < nr * NCHUNK; idx += WORKERS) {
           const int r = idx >> 5, c4 = idx & 31;
-          if (r < nr) *reinterpret_cast<float4*>(dst + (size_t)(r0 + r) * W2H + 4 * c4) = *Tp(c4, r);
+          *reinterpret_cast<float4*>(dst + (size_t)(r0 + r) * W2H + 4 * c4) = *Tp(c4, r);
         }
       };
 
       for (int st = 0; st < S; ++st) {
         CT(16 * st + 0);
-        // ---- tile input: Z_0 (stage 0) or V_st = sum_j coef * cat2_j, in place (cat2_{st-1} is still on chip; also
-        // written out for the backward pass) ----
+        // ---- tile input: Z_0 (stage 0) or V_st = sum_j coef * cat2_j, in place (cat2_{st-1} is still on chip) ----
         {
           constexpr int SLOTS = TM * NCHUNK / WORKERS / 2;   // 8 per half
           for (int hf = 0; hf < 2; ++hf) {
@@ -225,8 +207,8 @@ __global__ void __launch_bounds__(THREADS, 2) k_chain_fwd(const Args a) {
 #pragma unroll
               for (int u = 0; u < SLOTS; ++u) {
                 const int idx = ibase + u * WORKERS, r = idx >> 5, c4 = idx & 31;
-                const float4 v = *Tp(c4, r);
-                acc[u] = (r < nr) ? make_float4(cl * v.x, cl * v.y, cl * v.z, cl * v.w) : make_float4(0.f, 0.f, 0.f, 0.f);
+                acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (r < nr) { const float4 v = *Tp(c4, r); acc[u] = make_float4(cl * v.x, cl * v.y, cl * v.z, cl * v.w); }
               }
               for (int j = 0; j < st - 1; ++j) {
                 const float cf = a.coef[st][j];
@@ -245,18 +227,11 @@ __global__ void __launch_bounds__(THREADS, 2) k_chain_fwd(const Args a) {
                   acc[u].z = fmaf(cf, v[u].z, acc[u].z); acc[u].w = fmaf(cf, v[u].w, acc[u].w);
                 }
               }
-              if (a.V[st] != nullptr) {
-#pragma unroll
-                for (int u = 0; u < SLOTS; ++u) {
-                  const int idx = ibase + u * WORKERS, r = idx >> 5, c4 = idx & 31;
-                  if (r < nr) *reinterpret_cast<float4*>(a.V[st] + (size_t)(r0 + r) * W2H + 4 * c4) = acc[u];
-                }
-              }
             }
 #pragma unroll
             for (int u = 0; u < SLOTS; ++u) {
               const int idx = ibase + u * WORKERS, r = idx >> 5, c4 = idx & 31;
-              *Tp(c4, r) = acc[u];
+              if (idx < n_slots_t) *Tp(c4, r) = acc[u];
             }
           }
         }
@@ -267,18 +242,17 @@ __global__ void __launch_bounds__(THREADS, 2) k_chain_fwd(const Args a) {
           hand_off();
           CT(16 * st + 2);
           const float cs = a.c13_scale[st];
-          const bool rin = erow < nr;
+                    const bool rin = erow < nr;   // eact: this warp's lane quadrant holds tile rows
           const float4* zp = reinterpret_cast<const float4*>(a.z0 + (size_t)(r0 + (rin ? erow : 0)) * W2H + 64 * ehf);
           // this lane's Z_0 row segment (32 floats = one 128-byte line) is requested before the accumulator is ready
-          float4 z[2][8];
+          float4 z[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) z[0][i] = __ldg(zp + i);
+          for (int i = 0; i < 8; ++i) z[i] = rin ? __ldg(zp + i) : make_float4(0.f, 0.f, 0.f, 0.f);
           wait_bar(smem_u32(&bar_acc_full), ph_acc, dead, status, 25);
           ph_acc ^= 1u;
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           CT(16 * st + 3);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) z[1][i] = __ldg(zp + 8 + i);
+          // (every warp runs the epilogue, also one whose lane quadrant holds no tile rows: skipping it measured 20 % slower)
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             const int c0 = 64 * ehf + 32 * h;
@@ -288,11 +262,16 @@ __global__ void __launch_bounds__(THREADS, 2) k_chain_fwd(const Args a) {
             for (int i = 0; i < 8; ++i) {
               const float4 c = __ldg(reinterpret_cast<const float4*>(a.c13 + c0) + i);
               float4 o;
-              o.x = __uint_as_float(r[4 * i + 0]) + z[h][i].x + cs * c.x;
-              o.y = __uint_as_float(r[4 * i + 1]) + z[h][i].y + cs * c.y;
-              o.z = __uint_as_float(r[4 * i + 2]) + z[h][i].z + cs * c.z;
-              o.w = __uint_as_float(r[4 * i + 3]) + z[h][i].w + cs * c.w;
-              *Tp(c0 / 4 + i, erow) = o;
+              o.x = __uint_as_float(r[4 * i + 0]) + z[i].x + cs * c.x;
+              o.y = __uint_as_float(r[4 * i + 1]) + z[i].y + cs * c.y;
+              o.z = __uint_as_float(r[4 * i + 2]) + z[i].z + cs * c.z;
+              o.w = __uint_as_float(r[4 * i + 3]) + z[i].w + cs * c.w;
+              if (erow < TR) *Tp(c0 / 4 + i, erow) = o;
+              asm volatile("" ::: "memory");      // keep the c13 loads from being hoisted (register pressure)
+            }
+            if (h == 0) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) z[i] = rin ? __ldg(zp + 8 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
           }
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -345,7 +324,7 @@ __global__ void __launch_bounds__(THREADS, 2) k_chain_fwd(const Args a) {
             float4 h;
             h.x = fmaxf(__uint_as_float(r[4 * i + 0]) + b.x, 0.f); h.y = fmaxf(__uint_as_float(r[4 * i + 1]) + b.y, 0.f);
             h.z = fmaxf(__uint_as_float(r[4 * i + 2]) + b.z, 0.f); h.w = fmaxf(__uint_as_float(r[4 * i + 3]) + b.w, 0.f);
-            *Tp(16 + 8 * ehf + i, erow) = h;
+            if (erow < TR) *Tp(16 + 8 * ehf + i, erow) = h;
           }
         }
         worker_sync_w();
@@ -371,8 +350,8 @@ __global__ void __launch_bounds__(THREADS, 2) k_chain_fwd(const Args a) {
 #pragma unroll
             for (int u = 0; u < SLOTS; ++u) {
               const int idx = ibase + u * WORKERS, r = idx >> 5, c4 = idx & 31;
-              const float4 v = *Tp(c4, r);
-              acc[u] = make_float4(cl * v.x, cl * v.y, cl * v.z, cl * v.w);
+              acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (r < nr) { const float4 v = *Tp(c4, r); acc[u] = make_float4(cl * v.x, cl * v.y, cl * v.z, cl * v.w); }
             }
             for (int j = 0; j < st; ++j) {
               const float cf = a.csol[j];
@@ -402,6 +381,47 @@ __global__ void __launch_bounds__(THREADS, 2) k_chain_fwd(const Args a) {
       }
     }
   }
+
+}
+
+__global__ void __launch_bounds__(THREADS, 2) k_chain_fwd(const Args a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bar_b_full[MAX_SLOTS];
+  __shared__ __align__(8) uint64_t bar_b_empty[MAX_SLOTS];
+  __shared__ int s_tr;
+  __shared__ __align__(8) uint64_t bar_a_ready;
+  __shared__ __align__(8) uint64_t bar_acc_full;
+  __shared__ uint32_t tmem_holder;
+  __shared__ int dead_flag;
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int n_tiles = a.tiles[0];
+
+  if (tid == 0) {
+    dead_flag = 0;
+    int mr = 8;                                                  // most rows of any tile of this CTA
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) { const int nr = a.tiles[2 + t] - a.tiles[1 + t]; mr = nr > mr ? nr : mr; }
+    s_tr = (mr + 7) & ~7;
+    for (int s = 0; s < MAX_SLOTS; ++s) { mbar_init(smem_u32(&bar_b_full[s]), 1); mbar_init(smem_u32(&bar_b_empty[s]), 1); }
+    mbar_init(smem_u32(&bar_a_ready), WORKERS / 32);
+    mbar_init(smem_u32(&bar_acc_full), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_holder)), "r"((uint32_t)TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_holder;
+  // rows kept per chunk: compile-time variants so that the tile addressing folds into immediates
+#ifndef CHAIN_TR_SMALL
+#define CHAIN_TR_SMALL 96
+#endif
+  if (s_tr <= CHAIN_TR_SMALL) chain_fwd_body<CHAIN_TR_SMALL>(a, smem, bar_b_full, bar_b_empty, &bar_a_ready, &bar_acc_full, tmem_base, &dead_flag);
+  else chain_fwd_body<128>(a, smem, bar_b_full, bar_b_empty, &bar_a_ready, &bar_acc_full, tmem_base, &dead_flag);
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -507,7 +527,7 @@ int chain_fwd(Sage3Ctx& c, FoldWs& f, const Tableau& tb, float dt, float* Cout, 
   chain::Args a{};
   a.z0 = f.z0;
   for (int st = 0; st < tb.S; ++st) {
-    a.cat1[st] = f.cat1[st]; a.cat2[st] = f.cat2[st]; a.V[st] = f.V[st];
+    a.cat1[st] = f.cat1[st]; a.cat2[st] = f.cat2[st];
     double bsum = 0.0;
     for (int j = 0; j < st; ++j) { a.coef[st][j] = (float)tb.beta[st][j] * dt; bsum += tb.beta[st][j]; }
     a.c13_scale[st] = (float)bsum * dt;
@@ -521,7 +541,7 @@ int chain_fwd(Sage3Ctx& c, FoldWs& f, const Tableau& tb, float dt, float* Cout, 
   a.S = tb.S;
   a.status = status_dev;
   a.err = c.g_tile_err;
-  GN_PROF(s, (double)c.N * tb.S * (2.0 * 128 * 128 + 2.0 * 128 * 64), 4.0 * (double)c.N * 128 * (1 + 3.0 * tb.S - 1),
+  GN_PROF(s, (double)c.N * tb.S * (2.0 * 128 * 128 + 2.0 * 128 * 64), 4.0 * (double)c.N * 128 * (2 + 2.0 * tb.S),
           "chain_fwd S=%d", tb.S);
   static bool attr_set = false;
   if (!attr_set) {

@@ -73,8 +73,8 @@ struct FoldWs {
   float *ci13 = nullptr, *ci13T = nullptr;                 // chain-kernel images of the two
   float *z0 = nullptr, *Cbuf = nullptr;                    // [N, 2H]
   float* Cslot = nullptr;                                  // C = dt sum_s c_s cat2_s of the current step (save area or Cbuf)
-  float* Vws[kMaxStages] = {};                             // workspace V_s (when nothing is saved)
-  float *cat1[kMaxStages] = {}, *cat2[kMaxStages] = {}, *V[kMaxStages] = {};   // stage slots of the current step
+  float* Vbuf = nullptr;                                   // [N, 2H] V_s of the kernel-per-op path
+  float *cat1[kMaxStages] = {}, *cat2[kMaxStages] = {};   // stage slots of the current step
   // backward
   float *G3 = nullptr, *U = nullptr, *GZ = nullptr;        // [N, 2H]
   float* gzs[kMaxStages] = {};                             // dL/dZ_s  [N, 2H]
@@ -85,7 +85,7 @@ struct FoldWs {
   static size_t save_floats_per_step(const Sage3Ctx& c, int S);
   void bind_slots(Sage3Ctx& c, float* save, int j);
   int prepare(Sage3Ctx& c, cudaStream_t s);
-  // fills cat1 / cat2 / V of every stage from y; with Cout also C = dt sum_s c_sol[s] cat2_s
+  // fills cat1 / cat2 of every stage from y; with Cout also C = dt sum_s c_sol[s] cat2_s
   int forward_stages(Sage3Ctx& c, const Tableau& tb, const float* y, float dt, cudaStream_t s, float* Cout = nullptr);
   int combine_solution(Sage3Ctx& c, const Tableau& tb, float dt, float* out, cudaStream_t s);
 };

@@ -137,7 +137,7 @@ void FoldWs::carve(Arena& a, const Sage3Ctx& c, int S_, bool backward) {
   }
   z0 = a.take<float>(nh);
   Cbuf = a.take<float>(nh);
-  for (int i = 1; i < S; ++i) Vws[i] = a.take<float>(nh);
+  Vbuf = a.take<float>(nh);
   if (backward) {
     G3 = a.take<float>(nh);
     U = a.take<float>(nh);
@@ -157,7 +157,7 @@ void FoldWs::carve(Arena& a, const Sage3Ctx& c, int S_, bool backward) {
 }
 
 size_t FoldWs::save_floats_per_step(const Sage3Ctx& c, int S_) {
-  return (size_t)(3 * S_) * padf((size_t)c.N * 2 * c.H);   // cat1, cat2 per stage; V_1..V_{S-1}; C
+  return (size_t)(2 * S_ + 1) * padf((size_t)c.N * 2 * c.H);   // cat1, cat2 per stage; C
 }
 
 // point the stage slots of step j at the save area (or at the workspace when save == null)
@@ -166,11 +166,9 @@ void FoldWs::bind_slots(Sage3Ctx& c, float* save, int j) {
   if (save) {
     float* p = save + (size_t)j * save_floats_per_step(c, S);
     for (int st = 0; st < S; ++st) { cat1[st] = p; p += nh; cat2[st] = p; p += nh; }
-    V[0] = nullptr;
-    for (int st = 1; st < S; ++st) { V[st] = p; p += nh; }
     Cslot = p;
   } else {
-    for (int st = 0; st < S; ++st) { cat1[st] = c.cat1[st]; cat2[st] = c.cat2[st]; V[st] = Vws[st]; }
+    for (int st = 0; st < S; ++st) { cat1[st] = c.cat1[st]; cat2[st] = c.cat2[st]; }
     Cslot = Cbuf;
   }
 }
@@ -194,7 +192,7 @@ int FoldWs::prepare(Sage3Ctx& c, cudaStream_t s) {
   return GNODE_OK;
 }
 
-// Stages of one step: fills cat1[st], cat2[st] (and V[st] for st >= 1) from y.  Z_0 is left in z0.
+// Stages of one step: fills cat1[st], cat2[st] from y.  Z_0 is left in z0.
 int FoldWs::forward_stages(Sage3Ctx& c, const Tableau& tb, const float* y, float dt, cudaStream_t s, float* Cout) {
   const int H = c.H, H2 = 2 * c.H;
   const int64_t N = c.N;
@@ -211,7 +209,7 @@ int FoldWs::forward_stages(Sage3Ctx& c, const Tableau& tb, const float* y, float
     if (st > 0) {
       // V_st = dt * sum_{j<st} beta[st][j] cat2_j ;  Z_st = Z_0 + V_st @ M13^T + (dt sum_j beta) c13
       LinComb lc{};
-      lc.out = V[st]; lc.base = nullptr; lc.n = nh; lc.n_terms = 0;
+      lc.out = Vbuf; lc.base = nullptr; lc.n = nh; lc.n_terms = 0;
       double bsum = 0.0;
       for (int j = 0; j < st; ++j) {
         lc.in[lc.n_terms] = cat2[j]; lc.coef[lc.n_terms] = (float)tb.beta[st][j] * dt; ++lc.n_terms;
@@ -219,7 +217,7 @@ int FoldWs::forward_stages(Sage3Ctx& c, const Tableau& tb, const float* y, float
       }
       GN_TRY(lincomb(lc, s));
       GemmNT q{};
-      q.A = V[st]; q.lda = H2; q.B = M13; q.ldb = H2; q.C = c.z; q.ldc = H2; q.M = N; q.N = H2; q.K = H2;
+      q.A = Vbuf; q.lda = H2; q.B = M13; q.ldb = H2; q.C = c.z; q.ldc = H2; q.M = N; q.N = H2; q.K = H2;
       q.bias = c13; q.bias_scale = (float)bsum * dt; q.base = z0; q.ldbase = H2;
       q.Bsplit = c.use_tc ? sM13 : nullptr;
       GN_TRY(gemm_nt(q, s));
@@ -319,6 +317,14 @@ int integrate_fixed_folded_bwd(Sage3Ctx& c, FoldWs& f, const Tableau& tb, const 
       }
       if (has_u) {
         GN_TRY(lincomb(lu, s));
+        {
+          // R += U_st^T @ cat2_st  [2H, 2H]  (= sum_s gz_s^T V_s regrouped by cat2_j, so that V_s need not be kept);
+          // g1 += colsum(U_st)  (= sum_s (dt sum_j beta_sj) colsum(gz_s)), fused into the same pass
+          GemmTN q{};
+          q.A = f.U; q.lda = H2; q.P = H2; q.B = f.cat2[st]; q.ldb = H2; q.Q = H2; q.Nrows = N; q.C = f.R; q.ldc = H2;
+          q.colsumA = f.g1;
+          GN_TRY(gemm_tn(q, f.partials, s));
+        }
         GemmNT q{};   // gcat = dt c_st G3 + U @ M13
         q.A = f.U; q.lda = H2; q.B = f.M13T; q.ldb = H2; q.C = c.gcat; q.ldc = H2; q.M = N; q.N = H2; q.K = H2;
         q.base = f.G3; q.ldbase = H2; q.base_scale = cs_dt;
@@ -348,16 +354,6 @@ int integrate_fixed_folded_bwd(Sage3Ctx& c, FoldWs& f, const Tableau& tb, const 
       // ---- conv2 -> conv1 ----   g_u1 = (A^T(gcat_l) + gcat_r) * [h1 > 0] -> gz[:, H:] ; A^T(g_u1) -> gz[:, :H]
       GN_TRY(agg_mean_bwd(c.g, c.gcat, H2, gz + H, H2, H, c.gcat + H, H2, c1 + H, H2, s));
       GN_TRY(agg_mean_bwd(c.g, gz + H, H2, gz, H2, H, nullptr, 0, nullptr, 0, s));
-      if (st > 0) {
-        // R += gz_st^T @ V_st  [2H, 2H];   g1 += (dt sum_j beta[st][j]) colsum(gz_st), fused into the same pass
-        double bsum = 0.0;
-        for (int jj = 0; jj < st; ++jj) bsum += tb.beta[st][jj];
-        const float w = (float)bsum * dt;
-        GemmTN q{};
-        q.A = gz; q.lda = H2; q.P = H2; q.B = f.V[st]; q.ldb = H2; q.Q = H2; q.Nrows = N; q.C = f.R; q.ldc = H2;
-        if (w != 0.f) { q.colsumA = f.g1; q.colsumA_scale = w; }
-        GN_TRY(gemm_tn(q, f.partials, s));
-      }
     }
     // ---- D-wide parameter gradients of this step ----
     {
