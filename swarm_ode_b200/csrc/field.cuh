@@ -78,6 +78,8 @@ struct FoldWs {
   // backward
   float *G3 = nullptr, *U = nullptr, *GZ = nullptr;        // [N, 2H]
   float* gzs[kMaxStages] = {};                             // dL/dZ_s  [N, 2H]
+  float* Us[kMaxStages] = {};                              // U_s of every stage (backward chain kernel), one contiguous stack
+  float* gv2s[kMaxStages] = {};                            // g_v2 of every stage [N, H] (backward chain kernel), contiguous
   float *gcur = nullptr, *gnext = nullptr;                 // [N, D] cotangent ping-pong
   float *R = nullptr, *g1 = nullptr, *cs = nullptr, *partials = nullptr;
 
@@ -109,6 +111,8 @@ int chain_pack_image(const float* W, int n, int k, int64_t ld, float* img, cudaS
 bool chain_shape_ok(int H);
 bool chain_fwd_supported(const Sage3Ctx& c);
 int chain_fwd(Sage3Ctx& c, FoldWs& f, const Tableau& tb, float dt, float* Cout, cudaStream_t s);
+bool chain_bwd_supported(const Sage3Ctx& c, const FoldWs& f);
+int chain_bwd(Sage3Ctx& c, FoldWs& f, const Tableau& tb, float dt, bool* has_u, cudaStream_t s);
 
 int check_graph(const gnode_graph* g, const char* who);
 int check_params(const gnode_sage3_params* p, const char* who);

@@ -143,14 +143,19 @@ void FoldWs::carve(Arena& a, const Sage3Ctx& c, int S_, bool backward) {
     U = a.take<float>(nh);
     GZ = a.take<float>(nh);
     for (int i = 0; i < S; ++i) gzs[i] = a.take<float>(nh);
+    if (chain_shape_ok(c.H)) {
+      float* us = a.take<float>(nh * S);
+      float* gv = a.take<float>(nh / 2 * S);
+      for (int i = 0; i < S; ++i) { Us[i] = us ? us + (size_t)i * nh : nullptr; gv2s[i] = gv ? gv + (size_t)i * (nh / 2) : nullptr; }
+    }
     gcur = a.take<float>(nd);
     gnext = a.take<float>(nd);
     R = a.take<float>((size_t)H2 * H2);
     g1 = a.take<float>(H2);
     cs = a.take<float>(H2);
     size_t pf = gemm_tn_workspace_floats(c.D, H2, c.N);
-    const size_t cand[3] = {gemm_tn_workspace_floats(H2, c.D, c.N), gemm_tn_workspace_floats(H2, H2, c.N),
-                            gemm_tn_workspace_floats(c.H, H2, c.N)};
+    const size_t cand[3] = {gemm_tn_workspace_floats(H2, c.D, c.N), gemm_tn_workspace_floats(H2, H2, c.N * S),
+                            gemm_tn_workspace_floats(c.H, H2, c.N * S)};
     for (size_t v : cand) if (v > pf) pf = v;
     partials = a.take<float>(pf);
   }
@@ -165,8 +170,8 @@ void FoldWs::bind_slots(Sage3Ctx& c, float* save, int j) {
   const size_t nh = padf((size_t)c.N * 2 * c.H);
   if (save) {
     float* p = save + (size_t)j * save_floats_per_step(c, S);
-    for (int st = 0; st < S; ++st) { cat1[st] = p; p += nh; cat2[st] = p; p += nh; }
-    Cslot = p;
+    for (int st = 0; st < S; ++st) { cat1[st] = p + (size_t)st * nh; cat2[st] = p + (size_t)(S + st) * nh; }   // two contiguous stacks
+    Cslot = p + (size_t)2 * S * nh;
   } else {
     for (int st = 0; st < S; ++st) { cat1[st] = c.cat1[st]; cat2[st] = c.cat2[st]; }
     Cslot = Cbuf;
@@ -302,65 +307,92 @@ int integrate_fixed_folded_bwd(Sage3Ctx& c, FoldWs& f, const Tableau& tb, const 
       q.Bsplit = c.use_tc ? c.s3T : nullptr;
       GN_TRY(gemm_nt(q, s));
     }
-    for (int st = S - 1; st >= 0; --st) {
-      float* gz = f.gzs[st];
-      // U_st = dt * sum_{i>st} beta[i][st] gz_i
-      LinComb lu{};
-      lu.out = f.U; lu.base = nullptr; lu.n = nh; lu.n_terms = 0;
-      for (int i = st + 1; i < S; ++i)
-        if (tb.beta[i][st] != 0.0) { lu.in[lu.n_terms] = f.gzs[i]; lu.coef[lu.n_terms] = (float)tb.beta[i][st] * dt; ++lu.n_terms; }
-      const bool has_u = lu.n_terms > 0;
-      const float cs_dt = (float)tb.c_sol[st] * dt;
-      if (!has_u && cs_dt == 0.f) {   // the stage does not influence the output
-        GN_CUDA(cudaMemsetAsync(gz, 0, sizeof(float) * nh, s));
-        continue;
+    if (chain_bwd_supported(c, f)) {
+      // all stages of this step in one graph-resident kernel (chain_bwd.cu), then the weight-gradient contractions
+      // over its outputs: dW2cat += g_v2_s^T cat1_s (db2 += colsum g_v2_s), R += U_s^T cat2_s (g1 += colsum U_s)
+      bool has_u[kMaxStages];
+      GN_TRY(chain_bwd(c, f, tb, dt, has_u, s));
+      // stages stacked along the row dimension: one contraction per operand pair when the slots are contiguous
+      bool stacked = true;
+      int n_u = 0;
+      for (int st = 0; st < S; ++st) {
+        if (st > 0 && (f.cat1[st] != f.cat1[st - 1] + nh || f.cat2[st] != f.cat2[st - 1] + nh)) stacked = false;
+        if (has_u[st]) { if (st != n_u) stacked = false; ++n_u; }
       }
-      if (has_u) {
-        GN_TRY(lincomb(lu, s));
-        {
-          // R += U_st^T @ cat2_st  [2H, 2H]  (= sum_s gz_s^T V_s regrouped by cat2_j, so that V_s need not be kept);
-          // g1 += colsum(U_st)  (= sum_s (dt sum_j beta_sj) colsum(gz_s)), fused into the same pass
-          GemmTN q{};
-          q.A = f.U; q.lda = H2; q.P = H2; q.B = f.cat2[st]; q.ldb = H2; q.Q = H2; q.Nrows = N; q.C = f.R; q.ldc = H2;
-          q.colsumA = f.g1;
-          GN_TRY(gemm_tn(q, f.partials, s));
-        }
-        GemmNT q{};   // gcat = dt c_st G3 + U @ M13
-        q.A = f.U; q.lda = H2; q.B = f.M13T; q.ldb = H2; q.C = c.gcat; q.ldc = H2; q.M = N; q.N = H2; q.K = H2;
-        q.base = f.G3; q.ldbase = H2; q.base_scale = cs_dt;
-        q.Bsplit = c.use_tc ? f.sM13T : nullptr;
-        GN_TRY(gemm_nt(q, s));
-      } else {
-        LinComb lg{};
-        lg.out = c.gcat; lg.base = nullptr; lg.n = nh; lg.n_terms = 1; lg.in[0] = f.G3; lg.coef[0] = cs_dt;
-        GN_TRY(lincomb(lg, s));
-      }
-      const float* c1 = f.cat1[st];
-      const float* c2 = f.cat2[st];
-      // ---- conv3 -> conv2 ----   g_v2 = (A^T(gcat_l) + gcat_r) * [h2 > 0]
-      GN_TRY(agg_mean_bwd(c.g, c.gcat, H2, c.gv2, H, H, c.gcat + H, H2, c2 + H, H2, s));
-      {  // gcat = g_v2 @ w2cat   [N, 2H]
-        GemmNT q{};
-        q.A = c.gv2; q.lda = H; q.B = c.w2catT; q.ldb = H; q.C = c.gcat; q.ldc = H2; q.M = N; q.N = H2; q.K = H;
-        q.Bsplit = c.use_tc ? c.s2T : nullptr;
-        GN_TRY(gemm_nt(q, s));
-      }
-      {  // dW2cat += g_v2^T @ cat1
+      for (int st = 0; st < (stacked ? 1 : S); ++st) {
         GemmTN q{};
-        q.A = c.gv2; q.lda = H; q.P = H; q.B = c1; q.ldb = H2; q.Q = H2; q.Nrows = N; q.C = c.dW2cat; q.ldc = H2;
-        q.colsumA = c.db2;                                          // db2 += colsum(g_v2), fused
+        q.A = f.gv2s[st]; q.lda = H; q.P = H; q.B = f.cat1[st]; q.ldb = H2; q.Q = H2; q.Nrows = stacked ? N * S : N;
+        q.C = c.dW2cat; q.ldc = H2; q.colsumA = c.db2;
         GN_TRY(gemm_tn(q, f.partials, s));
       }
-      // ---- conv2 -> conv1 ----   g_u1 = (A^T(gcat_l) + gcat_r) * [h1 > 0] -> gz[:, H:] ; A^T(g_u1) -> gz[:, :H]
-      GN_TRY(agg_mean_bwd(c.g, c.gcat, H2, gz + H, H2, H, c.gcat + H, H2, c1 + H, H2, s));
-      GN_TRY(agg_mean_bwd(c.g, gz + H, H2, gz, H2, H, nullptr, 0, nullptr, 0, s));
-    }
-    // ---- D-wide parameter gradients of this step ----
-    {
-      LinComb lz{};
-      lz.out = f.GZ; lz.base = nullptr; lz.n = nh; lz.n_terms = 0;
-      for (int st = 0; st < S; ++st) { lz.in[lz.n_terms] = f.gzs[st]; lz.coef[lz.n_terms] = 1.f; ++lz.n_terms; }
-      GN_TRY(lincomb(lz, s));
+      for (int st = 0; st < (stacked ? (n_u > 0 ? 1 : 0) : S); ++st) {
+        if (!stacked && !has_u[st]) continue;
+        GemmTN q{};
+        q.A = f.Us[st]; q.lda = H2; q.P = H2; q.B = f.cat2[st]; q.ldb = H2; q.Q = H2; q.Nrows = stacked ? N * n_u : N;
+        q.C = f.R; q.ldc = H2; q.colsumA = f.g1;
+        GN_TRY(gemm_tn(q, f.partials, s));
+      }
+    } else {
+    for (int st = S - 1; st >= 0; --st) {
+        float* gz = f.gzs[st];
+        // U_st = dt * sum_{i>st} beta[i][st] gz_i
+        LinComb lu{};
+        lu.out = f.U; lu.base = nullptr; lu.n = nh; lu.n_terms = 0;
+        for (int i = st + 1; i < S; ++i)
+          if (tb.beta[i][st] != 0.0) { lu.in[lu.n_terms] = f.gzs[i]; lu.coef[lu.n_terms] = (float)tb.beta[i][st] * dt; ++lu.n_terms; }
+        const bool has_u = lu.n_terms > 0;
+        const float cs_dt = (float)tb.c_sol[st] * dt;
+        if (!has_u && cs_dt == 0.f) {   // the stage does not influence the output
+          GN_CUDA(cudaMemsetAsync(gz, 0, sizeof(float) * nh, s));
+          continue;
+        }
+        if (has_u) {
+          GN_TRY(lincomb(lu, s));
+          {
+            // R += U_st^T @ cat2_st  [2H, 2H]  (= sum_s gz_s^T V_s regrouped by cat2_j, so that V_s need not be kept);
+            // g1 += colsum(U_st)  (= sum_s (dt sum_j beta_sj) colsum(gz_s)), fused into the same pass
+            GemmTN q{};
+            q.A = f.U; q.lda = H2; q.P = H2; q.B = f.cat2[st]; q.ldb = H2; q.Q = H2; q.Nrows = N; q.C = f.R; q.ldc = H2;
+            q.colsumA = f.g1;
+            GN_TRY(gemm_tn(q, f.partials, s));
+          }
+          GemmNT q{};   // gcat = dt c_st G3 + U @ M13
+          q.A = f.U; q.lda = H2; q.B = f.M13T; q.ldb = H2; q.C = c.gcat; q.ldc = H2; q.M = N; q.N = H2; q.K = H2;
+          q.base = f.G3; q.ldbase = H2; q.base_scale = cs_dt;
+          q.Bsplit = c.use_tc ? f.sM13T : nullptr;
+          GN_TRY(gemm_nt(q, s));
+        } else {
+          LinComb lg{};
+          lg.out = c.gcat; lg.base = nullptr; lg.n = nh; lg.n_terms = 1; lg.in[0] = f.G3; lg.coef[0] = cs_dt;
+          GN_TRY(lincomb(lg, s));
+        }
+        const float* c1 = f.cat1[st];
+        const float* c2 = f.cat2[st];
+        // ---- conv3 -> conv2 ----   g_v2 = (A^T(gcat_l) + gcat_r) * [h2 > 0]
+        GN_TRY(agg_mean_bwd(c.g, c.gcat, H2, c.gv2, H, H, c.gcat + H, H2, c2 + H, H2, s));
+        {  // gcat = g_v2 @ w2cat   [N, 2H]
+          GemmNT q{};
+          q.A = c.gv2; q.lda = H; q.B = c.w2catT; q.ldb = H; q.C = c.gcat; q.ldc = H2; q.M = N; q.N = H2; q.K = H;
+          q.Bsplit = c.use_tc ? c.s2T : nullptr;
+          GN_TRY(gemm_nt(q, s));
+        }
+        {  // dW2cat += g_v2^T @ cat1
+          GemmTN q{};
+          q.A = c.gv2; q.lda = H; q.P = H; q.B = c1; q.ldb = H2; q.Q = H2; q.Nrows = N; q.C = c.dW2cat; q.ldc = H2;
+          q.colsumA = c.db2;                                          // db2 += colsum(g_v2), fused
+          GN_TRY(gemm_tn(q, f.partials, s));
+        }
+        // ---- conv2 -> conv1 ----   g_u1 = (A^T(gcat_l) + gcat_r) * [h1 > 0] -> gz[:, H:] ; A^T(g_u1) -> gz[:, :H]
+        GN_TRY(agg_mean_bwd(c.g, c.gcat, H2, gz + H, H2, H, c.gcat + H, H2, c1 + H, H2, s));
+        GN_TRY(agg_mean_bwd(c.g, gz + H, H2, gz, H2, H, nullptr, 0, nullptr, 0, s));
+      }
+      // ---- D-wide parameter gradients of this step ----
+      {
+        LinComb lz{};
+        lz.out = f.GZ; lz.base = nullptr; lz.n = nh; lz.n_terms = 0;
+        for (int st = 0; st < S; ++st) { lz.in[lz.n_terms] = f.gzs[st]; lz.coef[lz.n_terms] = 1.f; ++lz.n_terms; }
+        GN_TRY(lincomb(lz, s));
+      }
     }
     if (lr) {  // dW3cat += Wd^T (g1^T C),  db3 += (dt sum c_s) Wd^T colsum(g1): only rows with a cotangent are read
       GN_PROF(s, 2.0 * N * lr->n_out * H2, 4.0 * (double)N * lr->n_out, "lowrank_dW3");

@@ -22,10 +22,8 @@ void Sage3Ctx::carve(Arena& a, int slots, bool backward) {
   s3 = a.take<float>(presplit_floats(D, 2 * H));
   if (chain_shape_ok(H)) ci2 = a.take<float>(chain_image_floats(H, 2 * H));
   z = a.take<float>(n * 2 * H);
-  for (int i = 0; i < slots; ++i) {
-    cat1[i] = a.take<float>(n * 2 * H);
-    cat2[i] = a.take<float>(n * 2 * H);
-  }
+  for (int i = 0; i < slots; ++i) cat1[i] = a.take<float>(n * 2 * H);   // two stacks (stage-major): the backward pass
+  for (int i = 0; i < slots; ++i) cat2[i] = a.take<float>(n * 2 * H);   // contracts over all stages at once
   if (backward) {
     w1catT = a.take<float>((size_t)2 * H * D);
     w2catT = a.take<float>((size_t)H * 2 * H);
