@@ -18,13 +18,15 @@ for _ in range(3):
     masked_mse_train_step(model, opt, b, nx, t)
 torch.cuda.synchronize()
 lib = C.CDLL(_lib.LIB_PATH)
-buf = (C.c_longlong * 128)()
-rc = lib.gnode_chain_trace(buf)
-v = list(buf)
-print("rc", rc)
-for st in range(4):
+for fn in ("gnode_chain_trace", "gnode_chain_trace_b"):
+  buf = (C.c_longlong * 128)()
+  rc = getattr(lib, fn)(buf)
+  v = list(buf)
+  print(fn, "rc", rc)
+  base0 = min(x for x in v if x)
+  for st in (range(4) if fn == "gnode_chain_trace" else range(3, -1, -1)):
     row = v[16 * st:16 * st + 16]
-    base = v[0]
+    base = base0
     print("stage", st, " ".join(f"{(x - base) / 1.965e3:7.2f}" if x else "    -  " for x in row[:14]))
     d = [f"{(row[i + 1] - row[i]) / 1.965e3:6.2f}" if row[i] and row[i + 1] else "   -  " for i in range(13)]
     print("   delta us:", " ".join(d))

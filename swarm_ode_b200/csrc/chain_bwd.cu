@@ -9,7 +9,7 @@
 // A^T is the transpose of the mean aggregation: A^T(g)[j] = sum_{i : j -> i} g[i] / max(deg_in(i), 1).  No edge leaves
 // its graph, so a tile of whole graphs (the same tiles as the forward chain) carries every row these sums touch.  One
 // CTA owns a tile for ALL stages, last to first: gz_{s+1} is still on chip when U_s is formed, the other gz_i come back
-// from L2.  HBM sees G3 and the ReLU masks (right halves of cat1_s / cat2_s) on the way in and gz_s, U_s, g_v2_s on the
+// from L2.  HBM sees G3 and the ReLU sign bits (8 bytes per row and layer, kept by the forward chain) on the way in and gz_s, U_s, g_v2_s on the
 // way out (operands of the weight-gradient contractions that follow: dW2cat += g_v2_s^T cat1_s, R += U_s^T cat2_s),
 // plus GZ = sum_s gz_s after the last stage.  Structure, tile layout and the three-term tensor-core product are those
 // of chain_fwd.cu (chain_common.cuh).
@@ -19,10 +19,16 @@
 namespace gnode {
 namespace chain {
 
+#ifdef CHAIN_TRACE
+__device__ long long g_chain_trace_b[128];
+#define CTB(i) do { if (blockIdx.x == 0 && wt == 0 && t == blockIdx.x + 2 * (int)gridDim.x) g_chain_trace_b[(i)] = clock64(); } while (0)
+#else
+#define CTB(i) do { } while (0)
+#endif
+
 struct BwdArgs {
   const float* G3;                      // [N, 2H]
-  const float* cat1[kMaxStages];        // masks: right halves
-  const float* cat2[kMaxStages];
+  const uint32_t* mask[kMaxStages];     // [N, 4] sign bits of h1 (words 0, 1) and h2 (words 2, 3), written by chain_fwd
   const float* gz[kMaxStages];          // out [N, 2H] (written through gz_out, read back as a source)
   float* gz_out[kMaxStages];
   float* U[kMaxStages];                 // out [N, 2H] (stages with has_u)
@@ -169,13 +175,10 @@ __device__ __forceinline__ void chain_bwd_body(const BwdArgs& a, uint8_t* smem, 
           }
         }
       };
-      // right half <- (A^T(left half) + right half) * [act > 0], act = right half of a forward activation tile
-      auto relu_back = [&](const float* act) {
+      // right half <- (A^T(left half) + right half) * [h > 0]; which = 0: h1, 1: h2 (sign bits kept by the forward chain)
+      auto relu_back = [&](const uint32_t* mask, int which) {
         if (arow < nr) {
-          const float4* ap = reinterpret_cast<const float4*>(act + (size_t)(r0 + arow) * W2H + WH + 4 * ach);
-          float4 m[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) m[i] = __ldg(ap + i);
+          const uint32_t m = __ldg(mask + (size_t)(r0 + arow) * 4 + 2 * which + (ach >> 3));
           float4 acc[8];
           aggregate_t(ach, acc);
 #pragma unroll
@@ -183,8 +186,8 @@ __device__ __forceinline__ void chain_bwd_body(const BwdArgs& a, uint8_t* smem, 
             float4* own = Tp(16 + ach + i, arow);
             const float4 g = *own;
             float4 o;
-            o.x = m[i].x > 0.f ? acc[i].x + g.x : 0.f; o.y = m[i].y > 0.f ? acc[i].y + g.y : 0.f;
-            o.z = m[i].z > 0.f ? acc[i].z + g.z : 0.f; o.w = m[i].w > 0.f ? acc[i].w + g.w : 0.f;
+            o.x = (m >> (4 * i)) & 1u ? acc[i].x + g.x : 0.f; o.y = (m >> (4 * i + 1)) & 1u ? acc[i].y + g.y : 0.f;
+            o.z = (m >> (4 * i + 2)) & 1u ? acc[i].z + g.z : 0.f; o.w = (m >> (4 * i + 3)) & 1u ? acc[i].w + g.w : 0.f;
             *own = o;
           }
         }
@@ -224,7 +227,7 @@ __device__ __forceinline__ void chain_bwd_body(const BwdArgs& a, uint8_t* smem, 
 #pragma unroll
             for (int u = 0; u < SLOTS; ++u) {
               const int idx = ibase + u * WORKERS, r = idx >> 5, c4 = idx & 31;
-              if (r < nr) *reinterpret_cast<float4*>(out + (size_t)(r0 + r) * W2H + 4 * c4) = acc[u];
+              if (r < nr) __stcs(reinterpret_cast<float4*>(out + (size_t)(r0 + r) * W2H + 4 * c4), acc[u]);
             }
           }
 #pragma unroll
@@ -237,14 +240,17 @@ __device__ __forceinline__ void chain_bwd_body(const BwdArgs& a, uint8_t* smem, 
 
       for (int st = S - 1; st >= 0; --st) {
         const float csd = a.cs_dt[st];
+        CTB(16 * st + 0);
         if (a.has_u[st]) {
           // ---- U_st = sum_{i>st} cu * gz_i, in place (gz_{st+1} is still on chip); kept for R += U_st^T cat2_st ----
           combine(0, st, a.cu[st][st + 1], st + 2, S, a.U[st]);
           worker_sync_w();
+          CTB(16 * st + 1);
           // ---- gcat2 = dt c_st G3 + U_st @ M13 ----
           residual_to_tmem(T, lbo_t, TR, tmem_base, eq, lane, 16 * ehf, 0);
           residual_to_tmem(T, lbo_t, TR, tmem_base, eq, lane, 16 * ehf + 8, 0);
           arrive_a();
+          CTB(16 * st + 2);
           const bool rin = erow < nr && csd != 0.f;
           const float4* gp = reinterpret_cast<const float4*>(a.G3 + (size_t)(r0 + (erow < nr ? erow : 0)) * W2H + 64 * ehf);
           float4 z[8];
@@ -253,6 +259,7 @@ __device__ __forceinline__ void chain_bwd_body(const BwdArgs& a, uint8_t* smem, 
           wait_bar(smem_u32(&bar_acc_full), ph_acc, dead, status, 35);
           ph_acc ^= 1u;
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          CTB(16 * st + 3);
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             uint32_t r[32];
@@ -276,20 +283,25 @@ __device__ __forceinline__ void chain_bwd_body(const BwdArgs& a, uint8_t* smem, 
           combine(1, st, 0.f, 0, 1, nullptr);
           worker_sync_w();
         }
+        CTB(16 * st + 4);
         // ---- g_v2 = (A^T(gcat2_l) + gcat2_r) * [h2 > 0] -> right half ----
-        relu_back(a.cat2[st]);
+        relu_back(a.mask[st], 1);
         worker_sync_w();
+        CTB(16 * st + 5);
         // ---- gcat1 = g_v2 @ w2cat (K = 64: the right half is the operand); g_v2 goes out while the contraction runs ----
         residual_to_tmem(T, lbo_t, TR, tmem_base, eq, lane, 16 + 8 * ehf, 16);
         arrive_a();
+        CTB(16 * st + 6);
         for (int idx = wt; idx < nr * (NCHUNK / 2); idx += WORKERS) {
           const int r = idx >> 4, c4 = idx & 15;
-          *reinterpret_cast<float4*>(a.gv2[st] + (size_t)(r0 + r) * WH + 4 * c4) = *Tp(16 + c4, r);
+          __stcs(reinterpret_cast<float4*>(a.gv2[st] + (size_t)(r0 + r) * WH + 4 * c4), *Tp(16 + c4, r));
         }
+        CTB(16 * st + 7);
         wait_bar(smem_u32(&bar_acc_full), ph_acc, dead, status, 36);
         ph_acc ^= 1u;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         worker_sync();                         // every thread has finished reading the tile for the g_v2 store
+        CTB(16 * st + 8);
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           uint32_t r[32];
@@ -303,9 +315,11 @@ __device__ __forceinline__ void chain_bwd_body(const BwdArgs& a, uint8_t* smem, 
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         worker_sync_w();
+        CTB(16 * st + 9);
         // ---- g_u1 = (A^T(gcat1_l) + gcat1_r) * [h1 > 0] -> right half ----
-        relu_back(a.cat1[st]);
+        relu_back(a.mask[st], 0);
         worker_sync_w();
+        CTB(16 * st + 10);
         // ---- A^T(g_u1) -> left half: the tile is now gz_st ----
         if (arow < nr) {
           float4 acc[8];
@@ -314,6 +328,7 @@ __device__ __forceinline__ void chain_bwd_body(const BwdArgs& a, uint8_t* smem, 
           for (int i = 0; i < 8; ++i) *Tp(ach + i, arow) = acc[i];
         }
         worker_sync_w();
+        CTB(16 * st + 11);
         for (int idx = wt; idx < nr * NCHUNK; idx += WORKERS) {
           const int r = idx >> 5, c4 = idx & 31;
           *reinterpret_cast<float4*>(a.gz_out[st] + (size_t)(r0 + r) * W2H + 4 * c4) = *Tp(c4, r);
@@ -323,7 +338,9 @@ __device__ __forceinline__ void chain_bwd_body(const BwdArgs& a, uint8_t* smem, 
           worker_sync();
           combine(2, 0, 1.f, 1, S, a.GZ);
         }
+        CTB(16 * st + 12);
         worker_sync();      // the tile buffer is modified by the next stage / tile
+        CTB(16 * st + 13);
       }
     }
   }
@@ -375,9 +392,14 @@ __global__ void __launch_bounds__(THREADS, 2) k_chain_bwd(const BwdArgs a) {
 }  // namespace chain
 
 namespace tc { int* status_ptr(); }
+#ifdef CHAIN_TRACE
+extern "C" int gnode_chain_trace_b(long long* out128) {
+  return (int)cudaMemcpyFromSymbol(out128, chain::g_chain_trace_b, sizeof(long long) * 128);
+}
+#endif
 
 bool chain_bwd_supported(const Sage3Ctx& c, const FoldWs& f) {
-  return chain_fwd_supported(c) && c.ci2T != nullptr && f.ci13T != nullptr && f.Us[0] != nullptr && f.gv2s[0] != nullptr &&
+  return chain_fwd_supported(c) && c.ci2T != nullptr && f.ci13T != nullptr && f.Us[0] != nullptr && f.gv2s[0] != nullptr && f.mask[0] != nullptr &&
          c.g.t_rowptr != nullptr && c.g.t_col != nullptr;
 }
 
@@ -390,7 +412,7 @@ int chain_bwd(Sage3Ctx& c, FoldWs& f, const Tableau& tb, float dt, bool* has_u, 
   a.G3 = f.G3; a.GZ = f.GZ;
   int n_u = 0;
   for (int st = 0; st < tb.S; ++st) {
-    a.cat1[st] = f.cat1[st]; a.cat2[st] = f.cat2[st];
+    a.mask[st] = f.mask[st];
     a.gz[st] = f.gzs[st]; a.gz_out[st] = f.gzs[st]; a.U[st] = f.Us[st]; a.gv2[st] = f.gv2s[st];
     a.cs_dt[st] = (float)tb.c_sol[st] * dt;
     a.has_u[st] = 0;
@@ -408,7 +430,7 @@ int chain_bwd(Sage3Ctx& c, FoldWs& f, const Tableau& tb, float dt, bool* has_u, 
   a.status = status_dev;
   a.err = c.g_tile_err;
   GN_PROF(s, (double)c.N * (n_u * 2.0 * 128 * 128 + tb.S * 2.0 * 128 * 64),
-          4.0 * (double)c.N * (128.0 * (tb.S + n_u + 1 + 1) + 64.0 * 3 * tb.S), "chain_bwd S=%d", tb.S);
+          4.0 * (double)c.N * (128.0 * (tb.S + n_u + 1 + 1) + 64.0 * tb.S + 4.0 * tb.S), "chain_bwd S=%d", tb.S);
   static bool attr_set = false;
   if (!attr_set) {
     GN_CUDA(cudaFuncSetAttribute(chain::k_chain_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, chain::SMEM_BYTES));

@@ -103,6 +103,9 @@ __device__ __forceinline__ void issue_kblock(uint32_t tmem_acc, uint32_t tmem_al
   umma_bf16_ts(tmem_acc, tmem_alo + (uint32_t)(8 * kb), dbf, idb, 1u);
 }
 
+// L2 prefetch of the 128-byte line at p (no register cost: hides the HBM latency of a load issued a stage later)
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 // 32 TMEM columns starting at `col` of lane quadrant `eq` -> r[]
 __device__ __forceinline__ void tmem_ld32(uint32_t tmem_base, int eq, uint32_t col, uint32_t (&r)[32]) {
   const uint32_t taddr = tmem_base + ((uint32_t)(32 * eq) << 16) + col;

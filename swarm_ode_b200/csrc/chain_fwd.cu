@@ -38,6 +38,7 @@ struct Args {
   float* cat2[kMaxStages];
   float coef[kMaxStages][kMaxStages];   // dt * beta[s][j]
   float csol[kMaxStages];               // dt * c_sol[s]
+  uint32_t* mask[kMaxStages];           // optional [N, 4]: sign bits of h1 (words 0, 1) and h2 (words 2, 3) for the backward chain
   float* Cout;                          // optional: C = sum_s csol[s] cat2_s, written after the last stage
   float c13_scale[kMaxStages];          // dt * sum_j beta[s][j]
   const float *c13, *b1, *b2;
@@ -179,16 +180,22 @@ __device__ __forceinline__ void chain_fwd_body(const Args& a, uint8_t* smem, uin
         for (int i = 0; i < 8; ++i) { acc[i].x *= inv_deg; acc[i].y *= inv_deg; acc[i].z *= inv_deg; acc[i].w *= inv_deg; }
       };
       // coalesced tile store: rows < nr of T -> dst[(r0 + r) * 2H + c]
-      auto store_tile = [&](float* dst) {
+      // (streaming = evict-first in L2: for outputs that this kernel does not read back)
+      auto store_tile = [&](float* dst, bool streaming) {
 #pragma unroll 4
         for (int idx = wt; idx < nr * NCHUNK; idx += WORKERS) {
           const int r = idx >> 5, c4 = idx & 31;
-          *reinterpret_cast<float4*>(dst + (size_t)(r0 + r) * W2H + 4 * c4) = *Tp(c4, r);
+          float4* gp = reinterpret_cast<float4*>(dst + (size_t)(r0 + r) * W2H + 4 * c4);
+          if (streaming) __stcs(gp, *Tp(c4, r)); else *gp = *Tp(c4, r);
         }
       };
 
       for (int st = 0; st < S; ++st) {
         CT(16 * st + 0);
+        if (st + 1 < S && erow < nr) {   // Z_0 comes back in the epilogue of the next stage: keep its lines in L2
+          const float* zl = a.z0 + (size_t)(r0 + erow) * W2H + 64 * ehf;
+          prefetch_l2(zl); prefetch_l2(zl + 32);
+        }
         // ---- tile input: Z_0 (stage 0) or V_st = sum_j coef * cat2_j, in place (cat2_{st-1} is still on chip) ----
         {
           constexpr int SLOTS = TM * NCHUNK / WORKERS / 2;   // 8 per half
@@ -283,6 +290,7 @@ __device__ __forceinline__ void chain_fwd_body(const Args& a, uint8_t* smem, uin
           float4 acc[8];
           aggregate(ach, acc);
           const float4* bb = reinterpret_cast<const float4*>(a.b1 + 4 * ach);
+          uint32_t mbits = 0u;
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             float4* own = Tp(16 + ach + i, arow);
@@ -291,7 +299,10 @@ __device__ __forceinline__ void chain_fwd_body(const Args& a, uint8_t* smem, uin
             h.x = fmaxf(acc[i].x + z.x + b.x, 0.f); h.y = fmaxf(acc[i].y + z.y + b.y, 0.f);
             h.z = fmaxf(acc[i].z + z.z + b.z, 0.f); h.w = fmaxf(acc[i].w + z.w + b.w, 0.f);
             *own = h;
+            mbits |= (h.x > 0.f ? 1u : 0u) << (4 * i) | (h.y > 0.f ? 2u : 0u) << (4 * i) | (h.z > 0.f ? 4u : 0u) << (4 * i) |
+                     (h.w > 0.f ? 8u : 0u) << (4 * i);
           }
+          if (a.mask[st] != nullptr) a.mask[st][(size_t)(r0 + arow) * 4 + (ach >> 3)] = mbits;
         }
         worker_sync_w();
         CT(16 * st + 5);
@@ -307,7 +318,7 @@ __device__ __forceinline__ void chain_fwd_body(const Args& a, uint8_t* smem, uin
         // ---- h2 = relu(cat1 @ w2cat^T + b2) -> right half; cat1 goes out while the contraction runs ----
         hand_off();
         CT(16 * st + 7);
-        store_tile(a.cat1[st]);
+        store_tile(a.cat1[st], true);
         CT(16 * st + 8);
         wait_bar(smem_u32(&bar_acc_full), ph_acc, dead, status, 26);
         ph_acc ^= 1u;
@@ -318,6 +329,7 @@ __device__ __forceinline__ void chain_fwd_body(const Args& a, uint8_t* smem, uin
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
           worker_sync();                       // every thread has finished reading the tile for the cat1 store
           CT(16 * st + 9);
+          uint32_t mbits = 0u;
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const float4 b = __ldg(reinterpret_cast<const float4*>(a.b2 + 32 * ehf) + i);
@@ -325,7 +337,10 @@ __device__ __forceinline__ void chain_fwd_body(const Args& a, uint8_t* smem, uin
             h.x = fmaxf(__uint_as_float(r[4 * i + 0]) + b.x, 0.f); h.y = fmaxf(__uint_as_float(r[4 * i + 1]) + b.y, 0.f);
             h.z = fmaxf(__uint_as_float(r[4 * i + 2]) + b.z, 0.f); h.w = fmaxf(__uint_as_float(r[4 * i + 3]) + b.w, 0.f);
             if (erow < TR) *Tp(16 + 8 * ehf + i, erow) = h;
+            mbits |= (h.x > 0.f ? 1u : 0u) << (4 * i) | (h.y > 0.f ? 2u : 0u) << (4 * i) | (h.z > 0.f ? 4u : 0u) << (4 * i) |
+                     (h.w > 0.f ? 8u : 0u) << (4 * i);
           }
+          if (a.mask[st] != nullptr && erow < nr) a.mask[st][(size_t)(r0 + erow) * 4 + 2 + ehf] = mbits;
         }
         worker_sync_w();
         CT(16 * st + 10);
@@ -338,7 +353,7 @@ __device__ __forceinline__ void chain_fwd_body(const Args& a, uint8_t* smem, uin
         }
         worker_sync_w();
         CT(16 * st + 11);
-        store_tile(a.cat2[st]);
+        store_tile(a.cat2[st], st == S - 1 && a.Cout == nullptr);
         CT(16 * st + 12);
         if (st == S - 1 && a.Cout != nullptr) {
           // C = sum_s csol[s] cat2_s: the last cat2 tile is still on chip, the earlier ones come back from L2
@@ -372,7 +387,7 @@ __device__ __forceinline__ void chain_fwd_body(const Args& a, uint8_t* smem, uin
 #pragma unroll
             for (int u = 0; u < SLOTS; ++u) {
               const int idx = ibase + u * WORKERS, r = idx >> 5, c4 = idx & 31;
-              if (r < nr) *reinterpret_cast<float4*>(a.Cout + (size_t)(r0 + r) * W2H + 4 * c4) = acc[u];
+              if (r < nr) __stcs(reinterpret_cast<float4*>(a.Cout + (size_t)(r0 + r) * W2H + 4 * c4), acc[u]);
             }
           }
         }
@@ -527,7 +542,7 @@ int chain_fwd(Sage3Ctx& c, FoldWs& f, const Tableau& tb, float dt, float* Cout, 
   chain::Args a{};
   a.z0 = f.z0;
   for (int st = 0; st < tb.S; ++st) {
-    a.cat1[st] = f.cat1[st]; a.cat2[st] = f.cat2[st];
+    a.cat1[st] = f.cat1[st]; a.cat2[st] = f.cat2[st]; a.mask[st] = f.mask[st];
     double bsum = 0.0;
     for (int j = 0; j < st; ++j) { a.coef[st][j] = (float)tb.beta[st][j] * dt; bsum += tb.beta[st][j]; }
     a.c13_scale[st] = (float)bsum * dt;

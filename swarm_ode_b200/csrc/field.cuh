@@ -75,6 +75,8 @@ struct FoldWs {
   float* Cslot = nullptr;                                  // C = dt sum_s c_s cat2_s of the current step (save area or Cbuf)
   float* Vbuf = nullptr;                                   // [N, 2H] V_s of the kernel-per-op path
   float *cat1[kMaxStages] = {}, *cat2[kMaxStages] = {};   // stage slots of the current step
+  uint32_t* mask[kMaxStages] = {};                         // [N, 4] ReLU sign bits per stage (chain kernels), same slots
+  uint32_t* maskws = nullptr;                              // workspace copy (when nothing is saved)
   // backward
   float *G3 = nullptr, *U = nullptr, *GZ = nullptr;        // [N, 2H]
   float* gzs[kMaxStages] = {};                             // dL/dZ_s  [N, 2H]

@@ -138,6 +138,7 @@ void FoldWs::carve(Arena& a, const Sage3Ctx& c, int S_, bool backward) {
   z0 = a.take<float>(nh);
   Cbuf = a.take<float>(nh);
   Vbuf = a.take<float>(nh);
+  if (chain_shape_ok(c.H)) maskws = a.take<uint32_t>((size_t)S * padf((size_t)c.N * 4));
   if (backward) {
     G3 = a.take<float>(nh);
     U = a.take<float>(nh);
@@ -162,7 +163,8 @@ void FoldWs::carve(Arena& a, const Sage3Ctx& c, int S_, bool backward) {
 }
 
 size_t FoldWs::save_floats_per_step(const Sage3Ctx& c, int S_) {
-  return (size_t)(2 * S_ + 1) * padf((size_t)c.N * 2 * c.H);   // cat1, cat2 per stage; C
+  return (size_t)(2 * S_ + 1) * padf((size_t)c.N * 2 * c.H) +   // cat1, cat2 per stage; C
+         (chain_shape_ok(c.H) ? (size_t)S_ * padf((size_t)c.N * 4) : 0);   // ReLU sign bits per stage
 }
 
 // point the stage slots of step j at the save area (or at the workspace when save == null)
@@ -172,7 +174,10 @@ void FoldWs::bind_slots(Sage3Ctx& c, float* save, int j) {
     float* p = save + (size_t)j * save_floats_per_step(c, S);
     for (int st = 0; st < S; ++st) { cat1[st] = p + (size_t)st * nh; cat2[st] = p + (size_t)(S + st) * nh; }   // two contiguous stacks
     Cslot = p + (size_t)2 * S * nh;
+    uint32_t* mp = reinterpret_cast<uint32_t*>(p + (size_t)(2 * S + 1) * nh);
+    for (int st = 0; st < S; ++st) mask[st] = chain_shape_ok(c.H) ? mp + (size_t)st * padf((size_t)c.N * 4) : nullptr;
   } else {
+    for (int st = 0; st < S; ++st) mask[st] = maskws ? maskws + (size_t)st * padf((size_t)c.N * 4) : nullptr;
     for (int st = 0; st < S; ++st) { cat1[st] = c.cat1[st]; cat2[st] = c.cat2[st]; }
     Cslot = Cbuf;
   }
