@@ -527,6 +527,65 @@ __global__ void __launch_bounds__(1024) k_tiles_build(const int64_t* __restrict_
   }
 }
 
+// Parallel form of the same greedy packing for batches whose offsets fit in shared memory.  The packing is a chain
+// 0 -> nxt(0) -> nxt(nxt(0)) ... with nxt(g) = first graph that no longer fits into a tile starting at g (binary
+// search over the offsets, one per graph).  The orbit of 0 is marked by pointer doubling (log2 rounds: graphs already
+// marked mark their 2^k-th successor), a block-wide prefix count turns marks into tile indices.
+constexpr int TBP_MAX = 16384;           // graphs: 13 bytes of shared memory each
+__global__ void __launch_bounds__(1024) k_tiles_build_par(const int64_t* __restrict__ graph_ptr, int n, int32_t* __restrict__ tiles) {
+  extern __shared__ __align__(16) uint8_t tb_smem[];
+  int32_t* sp = reinterpret_cast<int32_t*>(tb_smem);          // [n + 1] offsets
+  int32_t* ja = sp + (n + 1);                                 // [n] jump (double buffered)
+  int32_t* jb = ja + n;
+  uint8_t* mk = reinterpret_cast<uint8_t*>(jb + n);           // [n] marks
+  __shared__ int s_bad, s_warp[32];
+  const int tid = threadIdx.x;
+  if (tid == 0) s_bad = 0;
+  for (int i = tid; i <= n; i += 1024) sp[i] = (int32_t)graph_ptr[i];
+  __syncthreads();
+  for (int g = tid; g < n; g += 1024) {
+    if (sp[g + 1] - sp[g] > TM) s_bad = 1;
+    // largest h in (g, n] with sp[h] - sp[g] <= TM: graphs g .. h-1 share the tile
+    int lo = g + 1, hi = n;
+    const int lim = sp[g] + TM;
+    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (sp[mid] <= lim) lo = mid; else hi = mid - 1; }
+    ja[g] = lo;                                               // == n: the tile runs to the end of the batch
+    mk[g] = g == 0;
+  }
+  __syncthreads();
+  int32_t *jc = ja, *jn = jb;
+  for (int span = 1; span < n; span <<= 1) {
+    for (int g = tid; g < n; g += 1024) {
+      const int j = jc[g];
+      if (j < n && mk[g]) mk[j] = 1;
+      jn[g] = j < n ? jc[j] : n;
+    }
+    __syncthreads();
+    int32_t* t = jc; jc = jn; jn = t;
+  }
+  // tile index of a marked graph = number of marked graphs before it
+  const int per = (n + 1023) / 1024, g0 = tid * per, g1 = min(n, g0 + per);
+  int cnt = 0;
+  for (int g = g0; g < g1; ++g) cnt += mk[g];
+  int incl = cnt;
+  for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if ((tid & 31) >= o) incl += v; }
+  if ((tid & 31) == 31) s_warp[tid >> 5] = incl;
+  __syncthreads();
+  if (tid < 32) {
+    int w = s_warp[tid];
+    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, w, o); if (tid >= o) w += v; }
+    s_warp[tid] = w;
+  }
+  __syncthreads();
+  int idx = incl - cnt + ((tid >> 5) > 0 ? s_warp[(tid >> 5) - 1] : 0);
+  for (int g = g0; g < g1; ++g) if (mk[g]) tiles[1 + idx++] = sp[g];
+  if (tid == 0) {
+    const int nt = s_warp[31];
+    tiles[1 + nt] = sp[n];
+    tiles[0] = s_bad ? -1 : nt;
+  }
+}
+
 }  // namespace chain
 
 namespace tc { int* status_ptr(); }
@@ -583,7 +642,17 @@ extern "C" int gnode_chain_trace(long long* out128) {
 extern "C" int gnode_tiles_build(const int64_t* graph_ptr, int64_t n_graphs, int32_t* tiles, gnode_stream_t stream) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   GN_ARG(graph_ptr && tiles && n_graphs > 0, "gnode_tiles_build: bad argument");
-  chain::k_tiles_build<<<1, 1024, 0, s>>>(graph_ptr, n_graphs, tiles);
+  if (n_graphs <= chain::TBP_MAX) {
+    const size_t smem = (size_t)(n_graphs + 1) * 4 + (size_t)n_graphs * 9 + 16;
+    static bool attr_set = false;
+    if (!attr_set) {
+      GN_CUDA(cudaFuncSetAttribute(chain::k_tiles_build_par, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)(chain::TBP_MAX + 1) * 4 + (size_t)chain::TBP_MAX * 9 + 16)));
+      attr_set = true;
+    }
+    chain::k_tiles_build_par<<<1, 1024, smem, s>>>(graph_ptr, (int)n_graphs, tiles);
+  } else {
+    chain::k_tiles_build<<<1, 1024, 0, s>>>(graph_ptr, n_graphs, tiles);
+  }
   GN_LAUNCHED();
   return GNODE_OK;
 }

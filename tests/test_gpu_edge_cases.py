@@ -131,3 +131,30 @@ def test_edge_leaving_its_graph_is_reported(cuda):
         model(gb2, torch.tensor([0.0, 1.0], device=cuda))
     with pytest.raises(S.GnodeError, match="tile"):
         S.graph.csr_for(gb2.edge_index, 140, holder=gb2).validate()
+
+
+def _greedy_tiles(ptr, tm=128):
+    """Python statement of the packing: whole graphs, at most tm rows per tile, a new tile when the next graph does not fit."""
+    starts, start = [int(ptr[0])], int(ptr[0])
+    for g in range(len(ptr) - 1):
+        b, e = int(ptr[g]), int(ptr[g + 1])
+        if e - start > tm:
+            starts.append(b)
+            start = b
+    return starts + [int(ptr[-1])]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n_graphs,lo,hi", [(1, 95, 95), (7, 1, 128), (4096, 95, 95), (3000, 1, 128), (16384, 1, 40), (20000, 3, 90)])
+def test_tiles_build_matches_greedy_packing(cuda, n_graphs, lo, hi):
+    """gnode_tiles_build (parallel pointer-doubling form up to 16384 graphs, sequential form above) == greedy packing."""
+    g = torch.Generator().manual_seed(n_graphs)
+    sizes = torch.randint(lo, hi + 1, (n_graphs,), generator=g)
+    ptr = torch.cat([torch.zeros(1, dtype=torch.long), sizes.cumsum(0)])
+    N = int(ptr[-1])
+    ei = torch.zeros((2, 0), dtype=torch.long, device=cuda)
+    csr = S.graph.CSRGraph(ei, N, graph_ptr=ptr.to(cuda), max_graph_nodes=int(sizes.max()))
+    t = csr.tiles.cpu().tolist()
+    want = _greedy_tiles(ptr.tolist())
+    assert t[0] == len(want) - 1
+    assert t[1:1 + len(want)] == want
