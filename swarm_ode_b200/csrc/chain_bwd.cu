@@ -251,11 +251,14 @@ __device__ __forceinline__ void chain_bwd_body(const BwdArgs& a, uint8_t* smem, 
           residual_to_tmem(T, lbo_t, TR, tmem_base, eq, lane, 16 * ehf + 8, 0);
           arrive_a();
           CTB(16 * st + 2);
-          const bool rin = erow < nr && csd != 0.f;
-          const float4* gp = reinterpret_cast<const float4*>(a.G3 + (size_t)(r0 + (erow < nr ? erow : 0)) * W2H + 64 * ehf);
-          float4 z[8];
+          // G3 comes back in the tile-linear mapping (coalesced), first half requested before the accumulator is ready
+          constexpr int ZS = 8;
+          float4 z[ZS];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) z[i] = rin ? __ldg(gp + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int u = 0; u < ZS; ++u) {
+            const int idx = wt + u * WORKERS, r = idx >> 5, c4 = idx & 31;
+            z[u] = (r < nr && csd != 0.f) ? __ldg(reinterpret_cast<const float4*>(a.G3 + (size_t)(r0 + r) * W2H + 4 * c4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
           wait_bar(smem_u32(&bar_acc_full), ph_acc, dead, status, 35);
           ph_acc ^= 1u;
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -266,17 +269,29 @@ __device__ __forceinline__ void chain_bwd_body(const BwdArgs& a, uint8_t* smem, 
             tmem_ld32(tmem_base, eq, (uint32_t)(ACC_COL + 64 * ehf + 32 * h), r);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              float4 o;
-              o.x = fmaf(csd, z[i].x, __uint_as_float(r[4 * i + 0])); o.y = fmaf(csd, z[i].y, __uint_as_float(r[4 * i + 1]));
-              o.z = fmaf(csd, z[i].z, __uint_as_float(r[4 * i + 2])); o.w = fmaf(csd, z[i].w, __uint_as_float(r[4 * i + 3]));
-              if (erow < TR) *Tp(16 * ehf + 8 * h + i, erow) = o;
-            }
-            if (h == 0) {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) z[i] = rin ? __ldg(gp + 8 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+              if (erow < TR)
+                *Tp(16 * ehf + 8 * h + i, erow) = make_float4(__uint_as_float(r[4 * i + 0]), __uint_as_float(r[4 * i + 1]),
+                                                              __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
             }
           }
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          float4 z2[ZS];
+#pragma unroll
+          for (int u = 0; u < ZS; ++u) {
+            const int idx = wt + (ZS + u) * WORKERS, r = idx >> 5, c4 = idx & 31;
+            z2[u] = (r < nr && csd != 0.f) ? __ldg(reinterpret_cast<const float4*>(a.G3 + (size_t)(r0 + r) * W2H + 4 * c4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+          worker_sync();
+#pragma unroll
+          for (int u = 0; u < ZS; ++u) {
+            const int idx = wt + u * WORKERS, r = idx >> 5, c4 = idx & 31;
+            if (r < nr) { float4* tp = Tp(c4, r); float4 v = *tp; v.x = fmaf(csd, z[u].x, v.x); v.y = fmaf(csd, z[u].y, v.y); v.z = fmaf(csd, z[u].z, v.z); v.w = fmaf(csd, z[u].w, v.w); *tp = v; }
+          }
+#pragma unroll
+          for (int u = 0; u < ZS; ++u) {
+            const int idx = wt + (ZS + u) * WORKERS, r = idx >> 5, c4 = idx & 31;
+            if (r < nr) { float4* tp = Tp(c4, r); float4 v = *tp; v.x = fmaf(csd, z2[u].x, v.x); v.y = fmaf(csd, z2[u].y, v.y); v.z = fmaf(csd, z2[u].z, v.z); v.w = fmaf(csd, z2[u].w, v.w); *tp = v; }
+          }
           worker_sync_w();
         } else {
           // ---- no later stage feeds on this one: gcat2 = dt c_st G3 ----

@@ -249,17 +249,21 @@ __device__ __forceinline__ void chain_fwd_body(const Args& a, uint8_t* smem, uin
           hand_off();
           CT(16 * st + 2);
           const float cs = a.c13_scale[st];
-                    const bool rin = erow < nr;   // eact: this warp's lane quadrant holds tile rows
-          const float4* zp = reinterpret_cast<const float4*>(a.z0 + (size_t)(r0 + (rin ? erow : 0)) * W2H + 64 * ehf);
-          // this lane's Z_0 row segment (32 floats = one 128-byte line) is requested before the accumulator is ready
-          float4 z[8];
+          // Z_0 comes back in the tile-linear mapping (coalesced: a warp reads one 512-byte row; a row-per-lane load
+          // would touch 32 lines per instruction).  Its first half is requested before the accumulator is ready.
+          constexpr int ZS = 8;
+          float4 z[ZS];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) z[i] = rin ? __ldg(zp + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int u = 0; u < ZS; ++u) {
+            const int idx = wt + u * WORKERS, r = idx >> 5, c4 = idx & 31;
+            z[u] = (r < nr) ? __ldg(reinterpret_cast<const float4*>(a.z0 + (size_t)(r0 + r) * W2H + 4 * c4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
           wait_bar(smem_u32(&bar_acc_full), ph_acc, dead, status, 25);
           ph_acc ^= 1u;
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           CT(16 * st + 3);
-          // (every warp runs the epilogue, also one whose lane quadrant holds no tile rows: skipping it measured 20 % slower)
+          // accumulator + scale * c13 -> tile, lane = row
+          // (every warp runs this, also one whose lane quadrant holds no tile rows: skipping it measured 20 % slower)
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             const int c0 = 64 * ehf + 32 * h;
@@ -269,19 +273,30 @@ __device__ __forceinline__ void chain_fwd_body(const Args& a, uint8_t* smem, uin
             for (int i = 0; i < 8; ++i) {
               const float4 c = __ldg(reinterpret_cast<const float4*>(a.c13 + c0) + i);
               float4 o;
-              o.x = __uint_as_float(r[4 * i + 0]) + z[i].x + cs * c.x;
-              o.y = __uint_as_float(r[4 * i + 1]) + z[i].y + cs * c.y;
-              o.z = __uint_as_float(r[4 * i + 2]) + z[i].z + cs * c.z;
-              o.w = __uint_as_float(r[4 * i + 3]) + z[i].w + cs * c.w;
+              o.x = fmaf(cs, c.x, __uint_as_float(r[4 * i + 0])); o.y = fmaf(cs, c.y, __uint_as_float(r[4 * i + 1]));
+              o.z = fmaf(cs, c.z, __uint_as_float(r[4 * i + 2])); o.w = fmaf(cs, c.w, __uint_as_float(r[4 * i + 3]));
               if (erow < TR) *Tp(c0 / 4 + i, erow) = o;
-              asm volatile("" ::: "memory");      // keep the c13 loads from being hoisted (register pressure)
-            }
-            if (h == 0) {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) z[i] = rin ? __ldg(zp + 8 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
           }
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          // second half of Z_0 on its way while the workers meet
+          float4 z2[ZS];
+#pragma unroll
+          for (int u = 0; u < ZS; ++u) {
+            const int idx = wt + (ZS + u) * WORKERS, r = idx >> 5, c4 = idx & 31;
+            z2[u] = (r < nr) ? __ldg(reinterpret_cast<const float4*>(a.z0 + (size_t)(r0 + r) * W2H + 4 * c4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+          worker_sync();
+#pragma unroll
+          for (int u = 0; u < ZS; ++u) {
+            const int idx = wt + u * WORKERS, r = idx >> 5, c4 = idx & 31;
+            if (r < nr) { float4* tp = Tp(c4, r); float4 v = *tp; v.x += z[u].x; v.y += z[u].y; v.z += z[u].z; v.w += z[u].w; *tp = v; }
+          }
+#pragma unroll
+          for (int u = 0; u < ZS; ++u) {
+            const int idx = wt + (ZS + u) * WORKERS, r = idx >> 5, c4 = idx & 31;
+            if (r < nr) { float4* tp = Tp(c4, r); float4 v = *tp; v.x += z2[u].x; v.y += z2[u].y; v.z += z2[u].z; v.w += z2[u].w; *tp = v; }
+          }
           worker_sync_w();
         }
         CT(16 * st + 4);
