@@ -198,7 +198,7 @@ def run_reference(args, rank: int, world: int):
         "e2e": {"value": value, "unit": "agent-state-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def cpu_baseline(args, D: int):
@@ -433,11 +433,30 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         "kernels": kernels,
         "cpu_baseline": cpu,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_JSON_FD = None
+
+
+def emit(line: dict):
+    """The ONE JSON line of the contract, on the process's original stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
 
 
 def main():
+    global _JSON_FD
     args = parse()
+    # Libraries (NCCL prints its version banner on stdout) must not add lines to stdout: everything but the JSON line
+    # goes to stderr.
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

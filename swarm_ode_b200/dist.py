@@ -105,11 +105,19 @@ def masked_mse_train_step(model, optimizer, graphs, next_positions: torch.Tensor
         loss = torch.nn.functional.mse_loss(pred[mask], target)
     loss.backward()
     if is_dist():
-        total_n = global_count(local_n, device=pred.device, group=group)
-        w = local_n / max(total_n, 1)
-        allreduce_gradients(model.parameters(), w, group=group)
-        gl = loss.detach() * w
-        dist.all_reduce(gl, op=dist.ReduceOp.SUM, group=group)
+        # ONE collective per step and no host synchronisation: every rank contributes local_n * [grads, loss] and local_n
+        # itself; dividing the sum by the global count reproduces the masked mean of the unsharded batch
+        params = [p for p in model.parameters() if p.grad is not None]
+        tail = torch.stack([loss.detach().reshape(()), torch.ones((), device=pred.device, dtype=loss.dtype)])
+        flat = torch.cat([p.grad.reshape(-1) for p in params] + [tail]).mul_(float(local_n))
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        flat.div_(flat[-1].clamp_min(1.0))
+        off = 0
+        for p in params:
+            n = p.grad.numel()
+            p.grad.copy_(flat[off:off + n].view_as(p.grad))
+            off += n
+        gl = flat[-2].clone()
     else:
         gl = loss.detach()
     torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm=max_norm)

@@ -69,6 +69,24 @@ def _worker(rank, world, port, tmp):
         D.allreduce_gradients(model.parameters(), local_n / total_n)
         for p, q in zip(model.parameters(), ref.parameters()):
             assert torch.allclose(p.grad, q.grad, rtol=1e-5, atol=1e-6), (p.grad, q.grad)
+        # the whole training step (one sync-free collective): same gradients and the global masked-mean loss
+
+        class _Toy(torch.nn.Module):
+            def __init__(self, lin):
+                super().__init__()
+                self.lin = lin
+
+            def forward(self, graphs, time_span):
+                y = self.lin(graphs.x)
+                return {"trajectories": torch.stack([torch.zeros_like(y), y])}
+
+        toy = _Toy(torch.nn.Linear(5, 2))
+        toy.lin.load_state_dict(ref.state_dict())
+        opt = torch.optim.SGD(toy.parameters(), lr=0.0)
+        gl = D.masked_mse_train_step(toy, opt, mine, tgt, torch.tensor([0.0, 1.0]), max_norm=1e9)
+        assert torch.allclose(gl, loss_ref.detach(), rtol=1e-5, atol=1e-7), (gl, loss_ref)
+        for p, q in zip(toy.lin.parameters(), ref.parameters()):
+            assert torch.allclose(p.grad, q.grad, rtol=1e-5, atol=1e-6), (p.grad, q.grad)
         # dopri5 norm hook: (sum of squares, element count) summed over ranks
         hook = D.dopri5_norm_allreduce()
         s, c = hook(float(rank + 1), 10.0 * (rank + 1))
