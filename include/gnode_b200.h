@@ -272,6 +272,18 @@ int gnode_integrate_dopri5(const gnode_graph* g, const gnode_sage3_params* p, co
                            int64_t max_num_steps, void* workspace, size_t workspace_bytes,
                            gnode_stream_t stream);
 
+/* Backward through gnode_integrate_dopri5 -- loss.backward() through torchdiffeq's odeint (no adjoint), as in
+ * scripts/train_gde.py:493 with GraphODE(ode_solver='dopri5').  tau[0 .. n_accepted] are the accepted step times of the
+ * forward pass (tau[0] = t[0]; rebuilt from its trace: tau[k+1] = tau[k] + dt of the k-th accepted attempt).  Step sizes
+ * are constants of the differentiation (torchdiffeq's step-size controller runs under no_grad).  grad_sol: [n_t, N, D];
+ * grad_y0 overwritten (may be NULL); parameter gradients accumulated (+=) into grads.  Folded integrator only. */
+size_t gnode_integrate_dopri5_bwd_workspace_bytes(int64_t n_nodes, int32_t node_dim, int32_t hidden_dim,
+                                                  int32_t n_accepted);
+int gnode_integrate_dopri5_bwd(const gnode_graph* g, const gnode_sage3_params* p, const float* y0,
+                               const double* tau, int32_t n_accepted, const double* t, int32_t n_t,
+                               const float* grad_sol, float* grad_y0, const gnode_sage3_grads* grads,
+                               void* workspace, size_t workspace_bytes, gnode_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * position_decoder = Linear(D, 2) applied to every row of the solution.
  *   x: [m, D] (m = n_t * n_nodes), w: [n_out, D], b: [n_out], out: [m, n_out]; n_out <= 8.

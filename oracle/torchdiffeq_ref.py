@@ -206,7 +206,7 @@ def _optimal_step_size(last_step, error_ratio, safety, ifactor, dfactor, order):
     return last_step * factor
 
 
-def _integrate_dopri5(func, y0, t, rtol, atol, st, first_step=None, max_num_steps=2 ** 31 - 1):
+def _integrate_dopri5(func, y0, t, rtol, atol, st, first_step=None, max_num_steps=2 ** 31 - 1, imposed_dts=None):
     tdtype = torch.promote_types(torch.float64, y0.dtype)
     rtol_t = torch.as_tensor(rtol, dtype=tdtype)
     atol_t = torch.as_tensor(atol, dtype=tdtype)
@@ -223,8 +223,12 @@ def _integrate_dopri5(func, y0, t, rtol, atol, st, first_step=None, max_num_step
 
     t = t.to(tdtype)
     f0 = func(t[0], y0); st.nfe += 1
+    # Step sizes are constants of the differentiation: torchdiffeq computes the next step under @torch.no_grad()
+    # (misc._optimal_step_size); the initial step is detached here as well (its derivative would only move the step
+    # boundaries: an O(local error) effect), so that autograd through this restatement is exactly "backprop through the
+    # accepted steps", which is what libgnode_b200's gnode_integrate_dopri5_bwd computes.
     if first_step is None:
-        dt = _select_initial_step(func, t[0], y0, order - 1, rtol_t, atol_t, f0, st)
+        dt = _select_initial_step(func, t[0], y0, order - 1, rtol_t, atol_t, f0, st).detach()
     else:
         dt = torch.as_tensor(first_step, dtype=tdtype)
     st.first_step = float(dt)
@@ -256,8 +260,14 @@ def _integrate_dopri5(func, y0, t, rtol, atol, st, first_step=None, max_num_step
                 y1, f1, s_t0, s_t1 = yb, fb, ta, tb
             else:
                 s_t0, s_t1 = ta, ta
-            dt = _optimal_step_size(dt, error_ratio, safety, ifactor, dfactor, order)
+            dt = _optimal_step_size(dt, error_ratio.detach(), safety, ifactor, dfactor, order).detach()
             n_steps += 1
+            if imposed_dts is not None:
+                # test hook: replay a given sequence of attempted steps (the controller above is then only bookkeeping),
+                # to compare two implementations on the SAME discretisation when a decision is rounding-level close
+                assert len(imposed_dts) > st.n_attempted or not next_t > s_t1, "imposed step sequence too short"
+                if len(imposed_dts) > st.n_attempted:
+                    dt = torch.as_tensor(imposed_dts[st.n_attempted], dtype=tdtype)
         sol.append(_interp_evaluate(interp, s_t0, s_t1, next_t))
     return torch.stack(sol, dim=0)
 
@@ -282,5 +292,7 @@ def odeint_ref(func: Callable, y0: torch.Tensor, t: torch.Tensor, *, rtol: float
         return _integrate_fixed(func, y0, t, method, st)
     if method == "dopri5":
         opts = options or {}
-        return _integrate_dopri5(func, y0, t, rtol, atol, st, first_step=opts.get("first_step"))
+        dts = opts.get("imposed_dts")
+        return _integrate_dopri5(func, y0, t, rtol, atol, st, first_step=opts.get("first_step") if dts is None else dts[0],
+                                 imposed_dts=dts)
     raise ValueError(f"Invalid method \"{method}\"")

@@ -56,13 +56,15 @@ class GraphODERef(nn.Module):
         self.ode_func = GraphODEFuncRef(node_dim=node_dim, hidden_dim=hidden_dim)
         self.position_decoder = nn.Linear(node_dim, 2)
         self.last_stats: Optional[SolverStats] = None
+        self.solver_options: Optional[dict] = None     # test hook, forwarded to odeint_ref(options=...)
 
     def forward(self, batch_data, time_span: torch.Tensor) -> Dict[str, torch.Tensor]:
         x0 = batch_data.x
         edge_index = batch_data.edge_index
         stats = SolverStats()
         solution = odeint_ref(lambda t, x: self.ode_func(t, x, edge_index), x0, time_span,
-                              method=self.ode_solver, rtol=1e-3, atol=1e-4, stats=stats)
+                              method=self.ode_solver, rtol=1e-3, atol=1e-4, stats=stats,
+                              options=self.solver_options)
         self.last_stats = stats
         trajectories = torch.stack([self.position_decoder(solution[i]) for i in range(solution.size(0))], dim=0)
         return {"trajectories": trajectories, "node_features": solution, "batch": batch_data.batch}

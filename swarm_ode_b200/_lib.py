@@ -106,6 +106,10 @@ _SIGNATURES = {
                                          C.POINTER(C.c_double), C.c_int32, C.c_double, C.c_double, _P,
                                          C.POINTER(GnodeDopri5Stats), C.POINTER(GnodeDopri5Trace), ALLREDUCE_FN, _P,
                                          C.c_int64, _P, C.c_size_t, _P]),
+    "gnode_integrate_dopri5_bwd_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int32, C.c_int32, C.c_int32]),
+    "gnode_integrate_dopri5_bwd": (C.c_int, [C.POINTER(GnodeGraph), C.POINTER(GnodeSage3Params), _P,
+                                             C.POINTER(C.c_double), C.c_int32, C.POINTER(C.c_double), C.c_int32, _P, _P,
+                                             C.POINTER(GnodeSage3Grads), _P, C.c_size_t, _P]),
     "gnode_decoder_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int32, C.c_int32]),
     "gnode_decoder_fwd": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int32, _P, _P, _P, _P]),
     "gnode_decoder_bwd": (C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, C.c_size_t, _P]),

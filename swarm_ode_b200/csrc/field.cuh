@@ -104,6 +104,9 @@ struct LowRankG {
 int integrate_fixed_folded_bwd(Sage3Ctx& c, FoldWs& f, const Tableau& tb, const float* sol, const float* t, int n_t,
                                const float* grad_sol, float* grad_y0, const float* save, cudaStream_t s,
                                const LowRankG* lr = nullptr);
+// backward through dopri5 over the accepted steps tau[0 .. n_acc] of the forward pass (fold.cu)
+int integrate_dopri5_folded_bwd(Sage3Ctx& c, FoldWs& f, const float* y0, const double* tau, int n_acc, const double* t,
+                                int n_t, const float* grad_sol, float* grad_y0, float* ys, cudaStream_t s);
 size_t decoder_wgrad_partial_floats(int64_t M, int D, int n_out);
 int decoder_wgrad(const float* x, const float* g, int64_t M, int D, int n_out, float* partials, float* total, cudaStream_t s);
 int current_fold();

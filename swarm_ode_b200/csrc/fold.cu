@@ -281,6 +281,141 @@ int integrate_fixed_folded(Sage3Ctx& c, FoldWs& f, const Tableau& tb, const floa
   return GNODE_OK;
 }
 
+// Backward of ONE folded step whose stage slots (f.cat1 / f.cat2 / sign bits) and C (f.Cslot, combined with tb.c_sol) are
+// in place: accumulates the parameter gradients (dW*, db*, R, g1) for the cotangent G of
+//     y_out = y + dt * sum_s tb.c_sol[s] k_s
+// and leaves GZ = sum_s dL/dZ_s in f.GZ.  tb.c_sol may be any weight vector (dense-output weights for dopri5).
+// G may be given in factored form (lr).
+static int fold_step_bwd(Sage3Ctx& c, FoldWs& f, const Tableau& tb, float dt, const float* y, const float* G,
+                         const LowRankG* lr, cudaStream_t s) {
+  const int S = tb.S, H = c.H, H2 = 2 * c.H;
+  const int64_t N = c.N, nh = N * H2;
+  double csum = 0.0;
+  for (int st = 0; st < S; ++st) csum += tb.c_sol[st];
+  if (lr) {  // G = g1 @ Wd is never formed:  G3 = g1 @ (Wd @ w3cat)
+    GN_PROF(s, 2.0 * N * lr->n_out * H2, 4.0 * (double)N * (H2 + lr->n_out), "lowrank_G3");
+    k_lr_prep<<<(unsigned)ceil_div64((int64_t)lr->n_out * H2 * 32, 256), 256, 0, s>>>(lr->Wd, c.w3cat, lr->n_out, c.D, H2, lr->WdW3);
+    GN_LAUNCHED();
+    k_lr_g3<<<(unsigned)ceil_div64(N * (H2 / 4), 256), 256, 0, s>>>(lr->g1, lr->WdW3, N, lr->n_out, H2, f.G3);
+    GN_LAUNCHED();
+  } else {  // G3 = G @ w3cat     [N, 2H]
+    GemmNT q{};
+    q.A = G; q.lda = c.D; q.B = c.w3catT; q.ldb = c.D; q.C = f.G3; q.ldc = H2; q.M = N; q.N = H2; q.K = c.D;
+    q.Bsplit = c.use_tc ? c.s3T : nullptr;
+    GN_TRY(gemm_nt(q, s));
+  }
+  if (chain_bwd_supported(c, f)) {
+    // all stages of this step in one graph-resident kernel (chain_bwd.cu), then the weight-gradient contractions
+    // over its outputs: dW2cat += g_v2_s^T cat1_s (db2 += colsum g_v2_s), R += U_s^T cat2_s (g1 += colsum U_s)
+    bool has_u[kMaxStages];
+    GN_TRY(chain_bwd(c, f, tb, dt, has_u, s));
+    // stages stacked along the row dimension: one contraction per operand pair when the slots are contiguous
+    bool stacked = true;
+    int n_u = 0;
+    for (int st = 0; st < S; ++st) {
+      if (st > 0 && (f.cat1[st] != f.cat1[st - 1] + nh || f.cat2[st] != f.cat2[st - 1] + nh)) stacked = false;
+      if (has_u[st]) { if (st != n_u) stacked = false; ++n_u; }
+    }
+    for (int st = 0; st < (stacked ? 1 : S); ++st) {
+      GemmTN q{};
+      q.A = f.gv2s[st]; q.lda = H; q.P = H; q.B = f.cat1[st]; q.ldb = H2; q.Q = H2; q.Nrows = stacked ? N * S : N;
+      q.C = c.dW2cat; q.ldc = H2; q.colsumA = c.db2;
+      GN_TRY(gemm_tn(q, f.partials, s));
+    }
+    for (int st = 0; st < (stacked ? (n_u > 0 ? 1 : 0) : S); ++st) {
+      if (!stacked && !has_u[st]) continue;
+      GemmTN q{};
+      q.A = f.Us[st]; q.lda = H2; q.P = H2; q.B = f.cat2[st]; q.ldb = H2; q.Q = H2; q.Nrows = stacked ? N * n_u : N;
+      q.C = f.R; q.ldc = H2; q.colsumA = f.g1;
+      GN_TRY(gemm_tn(q, f.partials, s));
+    }
+  } else {
+  for (int st = S - 1; st >= 0; --st) {
+      float* gz = f.gzs[st];
+      // U_st = dt * sum_{i>st} beta[i][st] gz_i
+      LinComb lu{};
+      lu.out = f.U; lu.base = nullptr; lu.n = nh; lu.n_terms = 0;
+      for (int i = st + 1; i < S; ++i)
+        if (tb.beta[i][st] != 0.0) { lu.in[lu.n_terms] = f.gzs[i]; lu.coef[lu.n_terms] = (float)tb.beta[i][st] * dt; ++lu.n_terms; }
+      const bool has_u = lu.n_terms > 0;
+      const float cs_dt = (float)tb.c_sol[st] * dt;
+      if (!has_u && cs_dt == 0.f) {   // the stage does not influence the output
+        GN_CUDA(cudaMemsetAsync(gz, 0, sizeof(float) * nh, s));
+        continue;
+      }
+      if (has_u) {
+        GN_TRY(lincomb(lu, s));
+        {
+          // R += U_st^T @ cat2_st  [2H, 2H]  (= sum_s gz_s^T V_s regrouped by cat2_j, so that V_s need not be kept);
+          // g1 += colsum(U_st)  (= sum_s (dt sum_j beta_sj) colsum(gz_s)), fused into the same pass
+          GemmTN q{};
+          q.A = f.U; q.lda = H2; q.P = H2; q.B = f.cat2[st]; q.ldb = H2; q.Q = H2; q.Nrows = N; q.C = f.R; q.ldc = H2;
+          q.colsumA = f.g1;
+          GN_TRY(gemm_tn(q, f.partials, s));
+        }
+        GemmNT q{};   // gcat = dt c_st G3 + U @ M13
+        q.A = f.U; q.lda = H2; q.B = f.M13T; q.ldb = H2; q.C = c.gcat; q.ldc = H2; q.M = N; q.N = H2; q.K = H2;
+        q.base = f.G3; q.ldbase = H2; q.base_scale = cs_dt;
+        q.Bsplit = c.use_tc ? f.sM13T : nullptr;
+        GN_TRY(gemm_nt(q, s));
+      } else {
+        LinComb lg{};
+        lg.out = c.gcat; lg.base = nullptr; lg.n = nh; lg.n_terms = 1; lg.in[0] = f.G3; lg.coef[0] = cs_dt;
+        GN_TRY(lincomb(lg, s));
+      }
+      const float* c1 = f.cat1[st];
+      const float* c2 = f.cat2[st];
+      // ---- conv3 -> conv2 ----   g_v2 = (A^T(gcat_l) + gcat_r) * [h2 > 0]
+      GN_TRY(agg_mean_bwd(c.g, c.gcat, H2, c.gv2, H, H, c.gcat + H, H2, c2 + H, H2, s));
+      {  // gcat = g_v2 @ w2cat   [N, 2H]
+        GemmNT q{};
+        q.A = c.gv2; q.lda = H; q.B = c.w2catT; q.ldb = H; q.C = c.gcat; q.ldc = H2; q.M = N; q.N = H2; q.K = H;
+        q.Bsplit = c.use_tc ? c.s2T : nullptr;
+        GN_TRY(gemm_nt(q, s));
+      }
+      {  // dW2cat += g_v2^T @ cat1
+        GemmTN q{};
+        q.A = c.gv2; q.lda = H; q.P = H; q.B = c1; q.ldb = H2; q.Q = H2; q.Nrows = N; q.C = c.dW2cat; q.ldc = H2;
+        q.colsumA = c.db2;                                          // db2 += colsum(g_v2), fused
+        GN_TRY(gemm_tn(q, f.partials, s));
+      }
+      // ---- conv2 -> conv1 ----   g_u1 = (A^T(gcat_l) + gcat_r) * [h1 > 0] -> gz[:, H:] ; A^T(g_u1) -> gz[:, :H]
+      GN_TRY(agg_mean_bwd(c.g, c.gcat, H2, gz + H, H2, H, c.gcat + H, H2, c1 + H, H2, s));
+      GN_TRY(agg_mean_bwd(c.g, gz + H, H2, gz, H2, H, nullptr, 0, nullptr, 0, s));
+    }
+    // ---- D-wide parameter gradients of this step ----
+    {
+      LinComb lz{};
+      lz.out = f.GZ; lz.base = nullptr; lz.n = nh; lz.n_terms = 0;
+      for (int st = 0; st < S; ++st) { lz.in[lz.n_terms] = f.gzs[st]; lz.coef[lz.n_terms] = 1.f; ++lz.n_terms; }
+      GN_TRY(lincomb(lz, s));
+    }
+  }
+  if (lr) {  // dW3cat += Wd^T (g1^T C),  db3 += (dt sum c_s) Wd^T colsum(g1): only rows with a cotangent are read
+    GN_PROF(s, 2.0 * N * lr->n_out * H2, 4.0 * (double)N * lr->n_out, "lowrank_dW3");
+    GN_TRY(decoder_wgrad(f.Cslot, lr->g1, N, H2, lr->n_out, lr->partials, lr->X, s));
+    k_lr_finish<<<(unsigned)ceil_div64((int64_t)c.D * (H2 + 1), 256), 256, 0, s>>>(lr->Wd, lr->X, lr->n_out, c.D, H2,
+                                                                                  (float)csum * dt, c.dW3cat, c.db3);
+    GN_LAUNCHED();
+  } else {  // dW3cat += G^T @ C     [D, 2H]   (C kept by the forward pass)
+    GemmTN q{};
+    q.A = G; q.lda = c.D; q.P = c.D; q.B = f.Cslot; q.ldb = H2; q.Q = H2; q.Nrows = N; q.C = c.dW3cat; q.ldc = H2;
+    q.colsumA = c.db3; q.colsumA_scale = (float)csum * dt;       // db3 += (dt sum c_s) colsum(G), fused
+    GN_TRY(gemm_tn(q, f.partials, s));
+  }
+  {  // dW1cat += GZ^T @ y    [2H, D];   colsum(GZ) = sum_s colsum(gz_s): its right half is db1
+    GN_CUDA(cudaMemsetAsync(f.cs, 0, sizeof(float) * H2, s));
+    GemmTN q{};
+    q.A = f.GZ; q.lda = H2; q.P = H2; q.B = y; q.ldb = c.D; q.Q = c.D; q.Nrows = N; q.C = c.dW1cat; q.ldc = c.D;
+    q.colsumA = f.cs;
+    GN_TRY(gemm_tn(q, f.partials, s));
+    LinComb l1{};
+    l1.out = c.db1; l1.base = c.db1; l1.n = H; l1.n_terms = 1; l1.in[0] = f.cs + H; l1.coef[0] = 1.f;
+    GN_TRY(lincomb(l1, s));
+  }
+  return GNODE_OK;
+}
+
 int integrate_fixed_folded_bwd(Sage3Ctx& c, FoldWs& f, const Tableau& tb, const float* sol, const float* t, int n_t,
                                const float* grad_sol, float* grad_y0, const float* save, cudaStream_t s,
                                const LowRankG* lr) {
@@ -289,8 +424,6 @@ int integrate_fixed_folded_bwd(Sage3Ctx& c, FoldWs& f, const Tableau& tb, const 
   GN_TRY(f.prepare(c, s));
   GN_CUDA(cudaMemsetAsync(f.R, 0, sizeof(float) * H2 * H2, s));
   GN_CUDA(cudaMemsetAsync(f.g1, 0, sizeof(float) * H2, s));
-  double csum = 0.0;
-  for (int st = 0; st < S; ++st) csum += tb.c_sol[st];
 
   // G = cotangent of y_{j+1}: explicit part from grad_sol plus what flowed back from later steps
   const float* G = lr ? nullptr : grad_sol + (int64_t)(n_t - 1) * n;
@@ -300,127 +433,7 @@ int integrate_fixed_folded_bwd(Sage3Ctx& c, FoldWs& f, const Tableau& tb, const 
     const float* y = sol + (int64_t)j * n;
     f.bind_slots(c, const_cast<float*>(save), j);
     if (!save) GN_TRY(f.forward_stages(c, tb, y, dt, s, f.Cslot));  // recompute this step's stages (and C)
-    if (lr) {  // G = g1 @ Wd is never formed:  G3 = g1 @ (Wd @ w3cat)
-      GN_PROF(s, 2.0 * N * lr->n_out * H2, 4.0 * (double)N * (H2 + lr->n_out), "lowrank_G3");
-      k_lr_prep<<<(unsigned)ceil_div64((int64_t)lr->n_out * H2 * 32, 256), 256, 0, s>>>(lr->Wd, c.w3cat, lr->n_out, c.D, H2, lr->WdW3);
-      GN_LAUNCHED();
-      k_lr_g3<<<(unsigned)ceil_div64(N * (H2 / 4), 256), 256, 0, s>>>(lr->g1, lr->WdW3, N, lr->n_out, H2, f.G3);
-      GN_LAUNCHED();
-    } else {  // G3 = G @ w3cat     [N, 2H]
-      GemmNT q{};
-      q.A = G; q.lda = c.D; q.B = c.w3catT; q.ldb = c.D; q.C = f.G3; q.ldc = H2; q.M = N; q.N = H2; q.K = c.D;
-      q.Bsplit = c.use_tc ? c.s3T : nullptr;
-      GN_TRY(gemm_nt(q, s));
-    }
-    if (chain_bwd_supported(c, f)) {
-      // all stages of this step in one graph-resident kernel (chain_bwd.cu), then the weight-gradient contractions
-      // over its outputs: dW2cat += g_v2_s^T cat1_s (db2 += colsum g_v2_s), R += U_s^T cat2_s (g1 += colsum U_s)
-      bool has_u[kMaxStages];
-      GN_TRY(chain_bwd(c, f, tb, dt, has_u, s));
-      // stages stacked along the row dimension: one contraction per operand pair when the slots are contiguous
-      bool stacked = true;
-      int n_u = 0;
-      for (int st = 0; st < S; ++st) {
-        if (st > 0 && (f.cat1[st] != f.cat1[st - 1] + nh || f.cat2[st] != f.cat2[st - 1] + nh)) stacked = false;
-        if (has_u[st]) { if (st != n_u) stacked = false; ++n_u; }
-      }
-      for (int st = 0; st < (stacked ? 1 : S); ++st) {
-        GemmTN q{};
-        q.A = f.gv2s[st]; q.lda = H; q.P = H; q.B = f.cat1[st]; q.ldb = H2; q.Q = H2; q.Nrows = stacked ? N * S : N;
-        q.C = c.dW2cat; q.ldc = H2; q.colsumA = c.db2;
-        GN_TRY(gemm_tn(q, f.partials, s));
-      }
-      for (int st = 0; st < (stacked ? (n_u > 0 ? 1 : 0) : S); ++st) {
-        if (!stacked && !has_u[st]) continue;
-        GemmTN q{};
-        q.A = f.Us[st]; q.lda = H2; q.P = H2; q.B = f.cat2[st]; q.ldb = H2; q.Q = H2; q.Nrows = stacked ? N * n_u : N;
-        q.C = f.R; q.ldc = H2; q.colsumA = f.g1;
-        GN_TRY(gemm_tn(q, f.partials, s));
-      }
-    } else {
-    for (int st = S - 1; st >= 0; --st) {
-        float* gz = f.gzs[st];
-        // U_st = dt * sum_{i>st} beta[i][st] gz_i
-        LinComb lu{};
-        lu.out = f.U; lu.base = nullptr; lu.n = nh; lu.n_terms = 0;
-        for (int i = st + 1; i < S; ++i)
-          if (tb.beta[i][st] != 0.0) { lu.in[lu.n_terms] = f.gzs[i]; lu.coef[lu.n_terms] = (float)tb.beta[i][st] * dt; ++lu.n_terms; }
-        const bool has_u = lu.n_terms > 0;
-        const float cs_dt = (float)tb.c_sol[st] * dt;
-        if (!has_u && cs_dt == 0.f) {   // the stage does not influence the output
-          GN_CUDA(cudaMemsetAsync(gz, 0, sizeof(float) * nh, s));
-          continue;
-        }
-        if (has_u) {
-          GN_TRY(lincomb(lu, s));
-          {
-            // R += U_st^T @ cat2_st  [2H, 2H]  (= sum_s gz_s^T V_s regrouped by cat2_j, so that V_s need not be kept);
-            // g1 += colsum(U_st)  (= sum_s (dt sum_j beta_sj) colsum(gz_s)), fused into the same pass
-            GemmTN q{};
-            q.A = f.U; q.lda = H2; q.P = H2; q.B = f.cat2[st]; q.ldb = H2; q.Q = H2; q.Nrows = N; q.C = f.R; q.ldc = H2;
-            q.colsumA = f.g1;
-            GN_TRY(gemm_tn(q, f.partials, s));
-          }
-          GemmNT q{};   // gcat = dt c_st G3 + U @ M13
-          q.A = f.U; q.lda = H2; q.B = f.M13T; q.ldb = H2; q.C = c.gcat; q.ldc = H2; q.M = N; q.N = H2; q.K = H2;
-          q.base = f.G3; q.ldbase = H2; q.base_scale = cs_dt;
-          q.Bsplit = c.use_tc ? f.sM13T : nullptr;
-          GN_TRY(gemm_nt(q, s));
-        } else {
-          LinComb lg{};
-          lg.out = c.gcat; lg.base = nullptr; lg.n = nh; lg.n_terms = 1; lg.in[0] = f.G3; lg.coef[0] = cs_dt;
-          GN_TRY(lincomb(lg, s));
-        }
-        const float* c1 = f.cat1[st];
-        const float* c2 = f.cat2[st];
-        // ---- conv3 -> conv2 ----   g_v2 = (A^T(gcat_l) + gcat_r) * [h2 > 0]
-        GN_TRY(agg_mean_bwd(c.g, c.gcat, H2, c.gv2, H, H, c.gcat + H, H2, c2 + H, H2, s));
-        {  // gcat = g_v2 @ w2cat   [N, 2H]
-          GemmNT q{};
-          q.A = c.gv2; q.lda = H; q.B = c.w2catT; q.ldb = H; q.C = c.gcat; q.ldc = H2; q.M = N; q.N = H2; q.K = H;
-          q.Bsplit = c.use_tc ? c.s2T : nullptr;
-          GN_TRY(gemm_nt(q, s));
-        }
-        {  // dW2cat += g_v2^T @ cat1
-          GemmTN q{};
-          q.A = c.gv2; q.lda = H; q.P = H; q.B = c1; q.ldb = H2; q.Q = H2; q.Nrows = N; q.C = c.dW2cat; q.ldc = H2;
-          q.colsumA = c.db2;                                          // db2 += colsum(g_v2), fused
-          GN_TRY(gemm_tn(q, f.partials, s));
-        }
-        // ---- conv2 -> conv1 ----   g_u1 = (A^T(gcat_l) + gcat_r) * [h1 > 0] -> gz[:, H:] ; A^T(g_u1) -> gz[:, :H]
-        GN_TRY(agg_mean_bwd(c.g, c.gcat, H2, gz + H, H2, H, c.gcat + H, H2, c1 + H, H2, s));
-        GN_TRY(agg_mean_bwd(c.g, gz + H, H2, gz, H2, H, nullptr, 0, nullptr, 0, s));
-      }
-      // ---- D-wide parameter gradients of this step ----
-      {
-        LinComb lz{};
-        lz.out = f.GZ; lz.base = nullptr; lz.n = nh; lz.n_terms = 0;
-        for (int st = 0; st < S; ++st) { lz.in[lz.n_terms] = f.gzs[st]; lz.coef[lz.n_terms] = 1.f; ++lz.n_terms; }
-        GN_TRY(lincomb(lz, s));
-      }
-    }
-    if (lr) {  // dW3cat += Wd^T (g1^T C),  db3 += (dt sum c_s) Wd^T colsum(g1): only rows with a cotangent are read
-      GN_PROF(s, 2.0 * N * lr->n_out * H2, 4.0 * (double)N * lr->n_out, "lowrank_dW3");
-      GN_TRY(decoder_wgrad(f.Cslot, lr->g1, N, H2, lr->n_out, lr->partials, lr->X, s));
-      k_lr_finish<<<(unsigned)ceil_div64((int64_t)c.D * (H2 + 1), 256), 256, 0, s>>>(lr->Wd, lr->X, lr->n_out, c.D, H2,
-                                                                                    (float)csum * dt, c.dW3cat, c.db3);
-      GN_LAUNCHED();
-    } else {  // dW3cat += G^T @ C     [D, 2H]   (C kept by the forward pass)
-      GemmTN q{};
-      q.A = G; q.lda = c.D; q.P = c.D; q.B = f.Cslot; q.ldb = H2; q.Q = H2; q.Nrows = N; q.C = c.dW3cat; q.ldc = H2;
-      q.colsumA = c.db3; q.colsumA_scale = (float)csum * dt;       // db3 += (dt sum c_s) colsum(G), fused
-      GN_TRY(gemm_tn(q, f.partials, s));
-    }
-    {  // dW1cat += GZ^T @ y    [2H, D];   colsum(GZ) = sum_s colsum(gz_s): its right half is db1
-      GN_CUDA(cudaMemsetAsync(f.cs, 0, sizeof(float) * H2, s));
-      GemmTN q{};
-      q.A = f.GZ; q.lda = H2; q.P = H2; q.B = y; q.ldb = c.D; q.Q = c.D; q.Nrows = N; q.C = c.dW1cat; q.ldc = c.D;
-      q.colsumA = f.cs;
-      GN_TRY(gemm_tn(q, f.partials, s));
-      LinComb l1{};
-      l1.out = c.db1; l1.base = c.db1; l1.n = H; l1.n_terms = 1; l1.in[0] = f.cs + H; l1.coef[0] = 1.f;
-      GN_TRY(lincomb(l1, s));
-    }
+    GN_TRY(fold_step_bwd(c, f, tb, dt, y, G, lr, s));
     if (j == 0 && grad_y0 == nullptr) break;   // nobody asked for dL/dy_0: skip its D-wide contraction
     {  // cotangent of y_j:  G + GZ @ w1cat + grad_sol[j]
       GemmNT q{};
@@ -433,6 +446,118 @@ int integrate_fixed_folded_bwd(Sage3Ctx& c, FoldWs& f, const Tableau& tb, const 
     gout = (gout == f.gcur) ? f.gnext : f.gcur;
   }
   if (grad_y0) GN_CUDA(cudaMemcpyAsync(grad_y0, G, sizeof(float) * n, cudaMemcpyDeviceToDevice, s));
+  {
+    GN_PROF(s, 4.0 * H2 * H2 * c.D, 0.0, "fold_param_grads");
+    dim3 grid((unsigned)ceil_div64(c.D, 128), (unsigned)(H2 + 1));
+    k_fold_param_grads<<<grid, 128, 0, s>>>(c.w1cat, c.w3cat, c.b3, f.R, f.g1, H2, c.D, c.dW3cat, c.dW1cat, c.db3);
+    GN_LAUNCHED();
+  }
+  return GNODE_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Backward through dopri5 (backprop through the solver, like the reference's loss.backward() through
+// torchdiffeq's odeint; step sizes are constants of the differentiation, as under torchdiffeq's
+// @torch.no_grad() step-size controller).
+//
+// The forward pass chose the accepted steps tau_0 < tau_1 < ... (trace of gnode_integrate_dopri5).  With those fixed,
+// the solve is a fixed-grid integration with the 7-stage Dormand-Prince tableau, and every requested output time in
+// (tau_k, tau_{k+1}] is the dense-output quartic of step k, which is itself a stage combination
+//     y(x) = y_k + dt sum_s w_s(x) k_s,      x = (t - tau_k) / dt
+//     w_s(x) = x d_s0 + x^2 (d_s6 - 4 d_s0 - 5 c_s + 16 m_s) + x^3 (5 d_s0 - 3 d_s6 + 14 c_s - 32 m_s)
+//            + x^4 (2 d_s6 - 2 d_s0 - 8 c_s + 16 m_s)                      (c = c_sol, m = c_mid, d = Kronecker delta)
+// (oracle/torchdiffeq_ref.py:_interp_fit_dopri5 expanded; w(1) = c_sol).  So the backward of step k is fold_step_bwd
+// once per cotangent source: the cotangent of y_{k+1} with weights c_sol, and every output inside the step with
+// weights w(x).  States y_k are replayed first (deterministic kernels: bitwise the forward's), the stages of a step are
+// recomputed when its backward runs.
+void dopri5_dense_weights(const Tableau& tb, double x, double* w) {
+  const double x2 = x * x, x3 = x2 * x, x4 = x3 * x;
+  for (int s = 0; s < 7; ++s) {
+    const double d0 = s == 0 ? 1.0 : 0.0, d6 = s == 6 ? 1.0 : 0.0, cs = tb.c_sol[s], ms = tb.c_mid[s];
+    w[s] = x * d0 + x2 * (d6 - 4.0 * d0 - 5.0 * cs + 16.0 * ms) + x3 * (5.0 * d0 - 3.0 * d6 + 14.0 * cs - 32.0 * ms) +
+           x4 * (2.0 * d6 - 2.0 * d0 - 8.0 * cs + 16.0 * ms);
+  }
+}
+
+int integrate_dopri5_folded_bwd(Sage3Ctx& c, FoldWs& f, const float* y0, const double* tau, int n_acc, const double* t,
+                                int n_t, const float* grad_sol, float* grad_y0, float* ys /* [n_acc + 1, N, D] */,
+                                cudaStream_t s) {
+  const Tableau& tb = *tableau_for(GNODE_DOPRI5);
+  const int H2 = 2 * c.H;
+  const int64_t N = c.N, n = c.numel();
+  GN_TRY(f.prepare(c, s));
+  GN_CUDA(cudaMemsetAsync(f.R, 0, sizeof(float) * H2 * H2, s));
+  GN_CUDA(cudaMemsetAsync(f.g1, 0, sizeof(float) * H2, s));
+  f.bind_slots(c, nullptr, 0);
+  double csum = 0.0;
+  for (int st = 0; st < tb.S; ++st) csum += tb.c_sol[st];
+
+  // ---- replay the accepted steps: ys[k] = y(tau_k) ----
+  GN_CUDA(cudaMemcpyAsync(ys, y0, sizeof(float) * n, cudaMemcpyDeviceToDevice, s));
+  for (int k = 0; k + 1 < n_acc; ++k) {            // the last state is never a step input
+    const float dt = (float)(tau[k + 1] - tau[k]);
+    const float* y = ys + (int64_t)k * n;
+    GN_TRY(f.forward_stages(c, tb, y, dt, s, f.Cslot));
+    GemmNT q{};   // y_{k+1} = y_k + C @ w3cat^T + (dt sum c) b3
+    q.A = f.Cslot; q.lda = H2; q.B = c.w3cat; q.ldb = H2; q.C = ys + (int64_t)(k + 1) * n; q.ldc = c.D; q.M = N; q.N = c.D; q.K = H2;
+    q.bias = c.b3; q.bias_scale = (float)csum * dt; q.base = y; q.ldbase = c.D;
+    q.Bsplit = c.use_tc ? c.s3 : nullptr;
+    GN_TRY(gemm_nt(q, s));
+  }
+
+  // ---- backward over the steps, last to first ----
+  const float* Gnext = nullptr;      // cotangent of y_{k+1} flowing back from later steps
+  float* gout = f.gcur;
+  int out_hi = n_t - 1;              // outputs still to be assigned to a step (descending)
+  for (int k = n_acc - 1; k >= 0; --k) {
+    const double t0 = tau[k], t1 = tau[k + 1];
+    const float dt = (float)(t1 - t0);
+    const float* y = ys + (int64_t)k * n;
+    // outputs of this step: t0 < t_i <= t1 (the forward interpolates an output in the first step that reaches it)
+    int out_lo = out_hi;
+    while (out_lo >= 1 && t[out_lo] > t0) --out_lo;
+    const int n_out_here = out_hi - out_lo;        // outputs out_lo + 1 .. out_hi
+    const int n_src = n_out_here + (Gnext ? 1 : 0);
+    if (n_src == 0) continue;                       // nothing depends on this step (cannot happen before the last output)
+    bool stages_ready = false, first = true;
+    for (int q = 0; q < n_src; ++q) {
+      Tableau tw = tb;
+      const float* G;
+      if (q < n_out_here) {
+        const int i = out_lo + 1 + q;
+        dopri5_dense_weights(tb, (t[i] - t0) / (t1 - t0), tw.c_sol);
+        G = grad_sol + (int64_t)i * n;
+      } else {
+        G = Gnext;
+      }
+      if (!stages_ready) {
+        GN_TRY(f.forward_stages(c, tw, y, dt, s, f.Cslot));     // stages of this step and C for the first source
+        stages_ready = true;
+      } else {
+        GN_TRY(f.combine_solution(c, tw, dt, f.Cslot, s));      // same stages, this source's weights
+      }
+      GN_TRY(fold_step_bwd(c, f, tw, dt, y, G, nullptr, s));
+      {  // cotangent of y_k  (+)=  G + GZ @ w1cat
+        GemmNT g{};
+        g.A = f.GZ; g.lda = H2; g.B = c.w1catT; g.ldb = H2; g.C = gout; g.ldc = c.D; g.M = N; g.N = c.D; g.K = H2;
+        g.base = G; g.ldbase = c.D;
+        if (!first) { g.base2 = gout; g.ldbase2 = c.D; }
+        g.Bsplit = c.use_tc ? c.s1T : nullptr;
+        GN_TRY(gemm_nt(g, s));
+      }
+      first = false;
+    }
+    out_hi = out_lo;
+    Gnext = gout;
+    gout = (gout == f.gcur) ? f.gnext : f.gcur;
+  }
+  if (grad_y0) {
+    // dL/dy_0 = what flowed back through the steps + the cotangent of the output at t[0] (sol[0] = y0)
+    LinComb lc{};
+    lc.out = grad_y0; lc.base = grad_sol; lc.n = n; lc.n_terms = 0;
+    if (Gnext) { lc.in[0] = Gnext; lc.coef[0] = 1.f; lc.n_terms = 1; }
+    GN_TRY(lincomb(lc, s));
+  }
   {
     GN_PROF(s, 4.0 * H2 * H2 * c.D, 0.0, "fold_param_grads");
     dim3 grid((unsigned)ceil_div64(c.D, 128), (unsigned)(H2 + 1));

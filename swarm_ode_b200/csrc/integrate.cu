@@ -718,6 +718,47 @@ extern "C" int gnode_integrate_dopri5(const gnode_graph* g, const gnode_sage3_pa
   return integrate_dopri5(c, y0, t, n_t, rtol, atol, sol, stats, trace, allreduce, allreduce_user, max_num_steps, b, s);
 }
 
+// Backward through dopri5 over the accepted steps of the forward pass (fold.cu:integrate_dopri5_folded_bwd).
+extern "C" size_t gnode_integrate_dopri5_bwd_workspace_bytes(int64_t n_nodes, int32_t node_dim, int32_t hidden_dim,
+                                                             int32_t n_accepted) {
+  Sage3Ctx c;
+  c.N = n_nodes; c.D = node_dim; c.H = hidden_dim;
+  Arena a(nullptr, 0);
+  FoldWs f;
+  c.carve(a, 7, true);
+  f.carve(a, c, 7, true);
+  a.take<float>((size_t)(n_accepted > 0 ? n_accepted : 1) * (size_t)n_nodes * node_dim);
+  return a.off;
+}
+
+extern "C" int gnode_integrate_dopri5_bwd(const gnode_graph* g, const gnode_sage3_params* p, const float* y0,
+                                          const double* tau, int32_t n_accepted, const double* t, int32_t n_t,
+                                          const float* grad_sol, float* grad_y0, const gnode_sage3_grads* grads,
+                                          void* workspace, size_t workspace_bytes, gnode_stream_t stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  GN_TRY(check_graph(g, "gnode_integrate_dopri5_bwd"));
+  GN_TRY(check_params(p, "gnode_integrate_dopri5_bwd"));
+  GN_ARG(y0 && tau && t && grad_sol && n_t >= 1 && n_accepted >= 0, "gnode_integrate_dopri5_bwd: bad argument");
+  GN_ARG(current_fold(), "gnode_integrate_dopri5_bwd: needs the folded integrator (gnode_set_fold(1))");
+  for (int k = 0; k < n_accepted; ++k)
+    GN_ARG(tau[k + 1] > tau[k], "gnode_integrate_dopri5_bwd: accepted step times must be strictly increasing");
+  GN_ARG(n_t == 1 || (n_accepted >= 1 && tau[0] == t[0] && tau[n_accepted] >= t[n_t - 1]),
+         "gnode_integrate_dopri5_bwd: the accepted steps do not cover the time grid");
+  Sage3Ctx c;
+  c.g = *g; c.g_tiles = g->tiles; c.g_tile_err = g->tile_err; c.N = g->n_nodes; c.D = p->node_dim; c.H = p->hidden_dim;
+  Arena a(workspace, workspace_bytes);
+  FoldWs f;
+  c.carve(a, 7, true);
+  f.carve(a, c, 7, true);
+  float* ys = a.take<float>((size_t)(n_accepted > 0 ? n_accepted : 1) * (size_t)c.N * c.D);
+  GN_ARENA_OK(a, "gnode_integrate_dopri5_bwd");
+  GN_TRY(c.pack(*p, true, s));
+  GN_TRY(c.zero_param_grads(s));
+  GN_TRY(integrate_dopri5_folded_bwd(c, f, y0, tau, n_accepted, t, n_t, grad_sol, grad_y0, ys, s));
+  if (grads) GN_TRY(c.unpack_grads(*grads, s));
+  return GNODE_OK;
+}
+
 // Backward of a one-step fixed-grid solve whose solution reaches the loss only through position_decoder at the last
 // time point (the training step of scripts/train_gde.py:486-493): dL/dy_1 = grad_traj_last @ dec_w has rank n_out, so
 // neither it nor its two D-wide contractions are ever formed.

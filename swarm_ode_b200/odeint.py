@@ -44,13 +44,10 @@ def odeint(func, y0: torch.Tensor, t: torch.Tensor, *, rtol: float = 1e-7, atol:
         params = func.func.param_list()
         if method in _FIXED:
             return ops.integrate_fixed(y0, graph, params, t, method)
-        needs_grad = torch.is_grad_enabled() and (y0.requires_grad or any(p.requires_grad for p in params))
         sol, stats = ops.integrate_dopri5(y0, graph, params, t, rtol, atol, allreduce=options.get("allreduce"),
                                           max_num_steps=int(options.get("max_num_steps", 0)))
         if sink is not None:
             sink.last_stats = stats
-        if needs_grad:
-            sol = _NoBackward.apply(sol, y0, *params)
         return sol
 
     if isinstance(func, ODEFunction):
@@ -65,17 +62,3 @@ def odeint(func, y0: torch.Tensor, t: torch.Tensor, *, rtol: float = 1e-7, atol:
     raise GnodeError(
         f"odeint: unsupported vector field {type(func).__name__}. Pass GraphODEFunc.bind(edge_index) or an "
         "ODEFunction; arbitrary Python callables would need an eager fallback, which this package does not have.")
-
-
-class _NoBackward(torch.autograd.Function):
-    """Keeps the dopri5 solution attached to the graph so that an attempted backward fails loudly
-    instead of silently producing no gradient."""
-
-    @staticmethod
-    def forward(ctx, sol, *inputs):
-        return sol.view_as(sol)
-
-    @staticmethod
-    def backward(ctx, *grads):
-        raise GnodeError("backward through the adaptive dopri5 solve is not implemented; train with a fixed-grid "
-                         "solver ('euler' / 'midpoint' / 'rk4', the reference's training configuration)")

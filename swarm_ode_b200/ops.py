@@ -288,22 +288,13 @@ def _run_dopri5(call: Callable, trace_cap: int):
                        accepted=[bool(acc[i]) for i in range(n)])
 
 
-def integrate_dopri5(y0, graph: CSRGraph, params: Sequence[torch.Tensor], t, rtol: float, atol: float,
-                     allreduce: Optional[Callable[[float, float], Tuple[float, float]]] = None,
-                     max_num_steps: int = 0, trace_cap: int = 4096):
-    """Adaptive Dormand-Prince integration of the GraphODEFunc field.  Returns ``(solution, Dopri5Stats)``.
-
-    ``allreduce(sumsq, count) -> (sumsq, count)`` (optional) sums the error-norm pieces over
-    data-parallel ranks so that all ranks take the step-size decisions of the unsharded batch.
-    """
-    y0 = _f32(y0.detach(), "y0")
-    w = [_f32(p.detach(), "param") for p in params]
+def _dopri5_forward(y0, graph: CSRGraph, w: Sequence[torch.Tensor], t_host: Sequence[float], rtol: float, atol: float,
+                    allreduce, max_num_steps: int, trace_cap: int):
     N, D = y0.shape
     H = w[0].shape[0]
     if N != graph.num_nodes:
         raise GnodeError(f"y0 has {N} rows but the graph has {graph.num_nodes} nodes")
     p = _sage3_params(D, H, w)
-    t_host = list(time_grid_to_host(t, torch.float64))
     T = len(t_host)
     tarr = (C.c_double * T)(*t_host)
     sol = torch.empty((T, N, D), dtype=torch.float32, device=y0.device)
@@ -328,6 +319,77 @@ def integrate_dopri5(y0, graph: CSRGraph, params: Sequence[torch.Tensor], t, rto
     stats = _run_dopri5(call, trace_cap)
     graph.schedule_tile_check()
     return sol, stats
+
+
+class _IntegrateDopri5Fn(torch.autograd.Function):
+    """Adaptive solve with backprop through the solver (the reference differentiates torchdiffeq's odeint with plain
+    autograd, scripts/train_gde.py:493).  The forward's accepted steps are replayed as a fixed grid with the Dormand-Prince
+    tableau; step sizes are constants of the differentiation (``gnode_integrate_dopri5_bwd``)."""
+
+    @staticmethod
+    def forward(ctx, y0, graph: CSRGraph, t_host, rtol, atol, allreduce, max_num_steps, trace_cap, holder, *w):
+        y0c = _f32(y0.detach(), "y0")
+        wc = [_f32(p.detach(), "param") for p in w]
+        sol, stats = _dopri5_forward(y0c, graph, wc, t_host, rtol, atol, allreduce, max_num_steps, trace_cap)
+        holder.append(stats)
+        tau = None
+        if stats.n_attempted <= len(stats.dts):
+            tau = [float(t_host[0])]
+            for dt, acc in zip(stats.dts, stats.accepted):
+                if acc:
+                    tau.append(tau[-1] + dt)            # the solver's own double-precision t1 = t0 + dt
+        ctx.graph, ctx.t_host, ctx.tau = graph, tuple(t_host), tau
+        ctx.save_for_backward(y0c, *wc)
+        return sol
+
+    @staticmethod
+    def backward(ctx, gsol):
+        y0, *w = ctx.saved_tensors
+        if ctx.tau is None:
+            raise GnodeError("dopri5 backward: the forward pass attempted more steps than its trace holds; raise trace_cap")
+        gsol = _f32(gsol, "grad_solution")
+        N, D = y0.shape
+        H = w[0].shape[0]
+        p = _sage3_params(D, H, w)
+        T, K = len(ctx.t_host), len(ctx.tau) - 1
+        gy0 = torch.empty((N, D), dtype=torch.float32, device=y0.device) if ctx.needs_input_grad[0] else None
+        gw = [torch.zeros_like(t) for t in w]
+        grads = _lib.GnodeSage3Grads(*[t.data_ptr() for t in gw])
+        L = _lib.lib()
+        prev_fold = L.gnode_set_fold(1)                  # the replay runs on the folded integrator
+        try:
+            ws = _ws(L.gnode_integrate_dopri5_bwd_workspace_bytes(N, D, H, K), y0.device)
+            tau = (C.c_double * (K + 1))(*ctx.tau)
+            tarr = (C.c_double * T)(*ctx.t_host)
+            with torch.cuda.device(y0.device):
+                _lib.check(L.gnode_integrate_dopri5_bwd(ctx.graph.ref(), C.byref(p), _lib.ptr(y0), tau, K, tarr, T,
+                                                        _lib.ptr(gsol), _lib.ptr(gy0), C.byref(grads), _lib.ptr(ws),
+                                                        ws.numel(), _lib.stream_ptr(y0.device)),
+                           "gnode_integrate_dopri5_bwd")
+        finally:
+            L.gnode_set_fold(prev_fold)
+        ctx.graph.schedule_tile_check()
+        return (gy0, None, None, None, None, None, None, None, None, *gw)
+
+
+def integrate_dopri5(y0, graph: CSRGraph, params: Sequence[torch.Tensor], t, rtol: float, atol: float,
+                     allreduce: Optional[Callable[[float, float], Tuple[float, float]]] = None,
+                     max_num_steps: int = 0, trace_cap: int = 4096):
+    """Adaptive Dormand-Prince integration of the GraphODEFunc field.  Returns ``(solution, Dopri5Stats)``.
+    Differentiable with respect to ``y0`` and the parameters (backprop through the solver).
+
+    ``allreduce(sumsq, count) -> (sumsq, count)`` (optional) sums the error-norm pieces over
+    data-parallel ranks so that all ranks take the step-size decisions of the unsharded batch.
+    """
+    t_host = list(time_grid_to_host(t, torch.float64))
+    if torch.is_grad_enabled() and (y0.requires_grad or any(p.requires_grad for p in params)):
+        holder: list = []
+        sol = _IntegrateDopri5Fn.apply(y0, graph, t_host, float(rtol), float(atol), allreduce, int(max_num_steps),
+                                       int(trace_cap), holder, *params)
+        return sol, holder[0]
+    y0 = _f32(y0.detach(), "y0")
+    w = [_f32(p.detach(), "param") for p in params]
+    return _dopri5_forward(y0, graph, w, t_host, rtol, atol, allreduce, max_num_steps, trace_cap)
 
 
 # ----------------------------------------------------------------------------------------------
