@@ -308,6 +308,10 @@ typedef struct {
   const float *w2, *b2; /* [H,h], [H] */
 } gnode_mlp_params;
 
+typedef struct {
+  float *w0, *b0, *w1, *b1, *w2, *b2; /* same shapes as gnode_mlp_params; any pointer may be NULL */
+} gnode_mlp_grads;
+
 size_t gnode_mlp_ode_workspace_bytes(int64_t m, int32_t dim, int32_t hidden_dim, int32_t method);
 int gnode_mlp_rhs_fwd(const gnode_mlp_params* p, const float* x, int64_t m, float* dxdt,
                       void* workspace, size_t workspace_bytes, gnode_stream_t stream);
@@ -319,6 +323,22 @@ int gnode_mlp_integrate_dopri5(const gnode_mlp_params* p, const float* y0, int64
                                gnode_dopri5_stats* stats, const gnode_dopri5_trace* trace,
                                int64_t max_num_steps, void* workspace, size_t workspace_bytes,
                                gnode_stream_t stream);
+
+/* Backward of the MLP field and of its solves -- loss.backward() through ODEFunction / odeint in the Q-network
+ * training of scripts/gnode.py:136-137,160-174 and scripts/run_gnode.py:134-135 (plain autograd, no adjoint).
+ * Parameter gradients are accumulated (+=); grad_x / grad_y0 are overwritten (may be NULL).  The dopri5 form replays
+ * the accepted steps tau[0 .. n_accepted] of the forward pass like gnode_integrate_dopri5_bwd. */
+size_t gnode_mlp_bwd_workspace_bytes(int64_t m, int32_t dim, int32_t hidden_dim, int32_t method, int32_t n_accepted);
+int gnode_mlp_rhs_bwd(const gnode_mlp_params* p, const float* x, const float* grad_out, int64_t m, float* grad_x,
+                      const gnode_mlp_grads* grads, void* workspace, size_t workspace_bytes, gnode_stream_t stream);
+int gnode_mlp_integrate_fixed_bwd(const gnode_mlp_params* p, int32_t method, const float* sol, int64_t m,
+                                  const float* t, int32_t n_t, const float* grad_sol, float* grad_y0,
+                                  const gnode_mlp_grads* grads, void* workspace, size_t workspace_bytes,
+                                  gnode_stream_t stream);
+int gnode_mlp_integrate_dopri5_bwd(const gnode_mlp_params* p, const float* y0, int64_t m, const double* tau,
+                                   int32_t n_accepted, const double* t, int32_t n_t, const float* grad_sol,
+                                   float* grad_y0, const gnode_mlp_grads* grads, void* workspace,
+                                   size_t workspace_bytes, gnode_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Spatial edges of GraphConverter, batched over independent snapshots, bit-exact:

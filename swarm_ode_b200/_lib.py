@@ -50,6 +50,10 @@ class GnodeMlpParams(C.Structure):
         (n, C.c_void_p) for n in ("w0", "b0", "w1", "b1", "w2", "b2")]
 
 
+class GnodeMlpGrads(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("w0", "b0", "w1", "b1", "w2", "b2")]
+
+
 class GnodeProfEntry(C.Structure):
     _fields_ = [("name", C.c_char * 64), ("launches", C.c_int64), ("ms", C.c_double), ("flops", C.c_double),
                 ("bytes", C.c_double)]
@@ -120,6 +124,14 @@ _SIGNATURES = {
     "gnode_mlp_integrate_dopri5": (C.c_int, [C.POINTER(GnodeMlpParams), _P, C.c_int64, C.POINTER(C.c_double),
                                              C.c_int32, C.c_double, C.c_double, _P, C.POINTER(GnodeDopri5Stats),
                                              C.POINTER(GnodeDopri5Trace), C.c_int64, _P, C.c_size_t, _P]),
+    "gnode_mlp_bwd_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    "gnode_mlp_rhs_bwd": (C.c_int, [C.POINTER(GnodeMlpParams), _P, _P, C.c_int64, _P, C.POINTER(GnodeMlpGrads), _P,
+                                    C.c_size_t, _P]),
+    "gnode_mlp_integrate_fixed_bwd": (C.c_int, [C.POINTER(GnodeMlpParams), C.c_int32, _P, C.c_int64, C.POINTER(C.c_float),
+                                                C.c_int32, _P, _P, C.POINTER(GnodeMlpGrads), _P, C.c_size_t, _P]),
+    "gnode_mlp_integrate_dopri5_bwd": (C.c_int, [C.POINTER(GnodeMlpParams), _P, C.c_int64, C.POINTER(C.c_double), C.c_int32,
+                                                 C.POINTER(C.c_double), C.c_int32, _P, _P, C.POINTER(GnodeMlpGrads), _P,
+                                                 C.c_size_t, _P]),
     "gnode_spatial_edges": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_float, _P, _P, _P]),
 }
 

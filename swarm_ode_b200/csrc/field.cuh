@@ -25,6 +25,12 @@ struct Field {
   // out = scale * f(x) (+ base if base != null).  `slot` selects where intermediates are kept for a
   // later vjp (0 when nothing needs to be kept).  out may alias base.
   virtual int eval(const float* x, float* out, const float* base, float scale, int slot, cudaStream_t s) = 0;
+  // gx = J_f(x)^T gk using the intermediates that eval(..., slot) kept; parameter gradients accumulate inside the field
+  virtual int vjp(const float* x, int slot, const float* gk, float* gx, cudaStream_t s) {
+    (void)x; (void)slot; (void)gk; (void)gx; (void)s;
+    set_error("this vector field has no backward");
+    return GNODE_ERR_ARG;
+  }
   int64_t numel() const { return rows() * (int64_t)dim(); }
 };
 
@@ -61,7 +67,7 @@ struct Sage3Ctx : Field {
   int pack(const gnode_sage3_params& p, bool backward, cudaStream_t s);
   int zero_param_grads(cudaStream_t s);
   // grad_x = J_f(x)^T gk using the intermediates kept in `slot`; parameter gradients accumulate into dW*/db*
-  int vjp(const float* x, int slot, const float* gk, float* gx, cudaStream_t s);
+  int vjp(const float* x, int slot, const float* gk, float* gx, cudaStream_t s) override;
   int unpack_grads(const gnode_sage3_grads& gr, cudaStream_t s);
 };
 
@@ -131,6 +137,23 @@ struct StepSaver {
 };
 int integrate_fixed(Field& f, int method, const float* y0, const float* t, int n_t, float* sol,
                     float* const* kbuf /* S-1 buffers */, float* xs, cudaStream_t s, StepSaver* saver = nullptr);
+
+// Backprop through explicit RK steps of a generic field in direct form (integrate.cu).  A cotangent source is a tensor
+// G together with the stage weights of the output it belongs to:  y_out = y + dt sum_s w[s] k_s  (c_sol for the step's
+// own result, dense-output weights for a dopri5 output inside the step).
+struct RkBwdSrc { const float* G; double w[kMaxStages]; };
+struct RkBwdBufs { float* kbuf[kMaxStages]; float* xs[kMaxStages]; float* gk; };
+// gout = sum_q G_q + sum_s J_s^T g_k[s] (+ extra); gout may alias a source.  Stage s is evaluated into slot s.
+int rk_step_bwd(Field& f, const Tableau& tb, const float* y, float dt, const RkBwdSrc* src, int n_src,
+                const RkBwdBufs& b, const float* const* xs_saved, const float* extra, float* gout, cudaStream_t s);
+// fixed grid: grad_sol [n_t, rows, dim]; gcur scratch [rows, dim]; grad_y0 may be null
+int integrate_fixed_bwd_generic(Field& f, const Tableau& tb, const float* sol, const float* t, int n_t, const float* grad_sol,
+                                float* grad_y0, const RkBwdBufs& b, float* gcur, cudaStream_t s);
+// dopri5 over the accepted steps tau[0 .. n_acc]; ys scratch [n_acc, rows, dim]; gping / gpong scratch [rows, dim]
+int integrate_dopri5_bwd_generic(Field& f, const float* y0, const double* tau, int n_acc, const double* t, int n_t,
+                                 const float* grad_sol, float* grad_y0, const RkBwdBufs& b, float* ys, float* gping,
+                                 float* gpong, cudaStream_t s);
+void dopri5_dense_weights(const Tableau& tb, double x, double* w);
 
 struct Dopri5Bufs {
   float* k[7];

@@ -648,6 +648,140 @@ extern "C" int gnode_integrate_fixed_bwd(const gnode_graph* g, const gnode_sage3
   return GNODE_OK;
 }
 
+namespace gnode {
+
+int rk_step_bwd(Field& f, const Tableau& tb, const float* y, float dt, const RkBwdSrc* src, int n_src,
+                const RkBwdBufs& b, const float* const* xs_saved, const float* extra, float* gout, cudaStream_t s) {
+  const int S = tb.S;
+  const int64_t n = f.numel();
+  // ---- the stages of the step: stage inputs x_s and the field's intermediates per slot ----
+  const float* xst[kMaxStages];
+  xst[0] = y;
+  if (xs_saved) {
+    for (int st = 1; st < S; ++st) xst[st] = xs_saved[st];
+  } else {
+    for (int st = 0; st < S; ++st) {
+      if (st > 0) {
+        GN_TRY(stage_input(tb, st, y, b.kbuf, dt, b.xs[st], n, s));
+        xst[st] = b.xs[st];
+      }
+      GN_TRY(f.eval(xst[st], b.kbuf[st], nullptr, 1.f, st, s));
+    }
+  }
+  // ---- reverse sweep; kbuf[s] is reused to hold g_x[s] ----
+  for (int st = S - 1; st >= 0; --st) {
+    // g_k[st] = dt * sum_q w_q[st] G_q + dt * sum_{i > st} beta[i][st] g_x[i]
+    bool any = false;
+    LinComb lc{};
+    lc.out = b.gk; lc.base = nullptr; lc.n = n; lc.n_terms = 0;
+    auto flush = [&]() -> int {
+      if (lc.n_terms == 0) return GNODE_OK;
+      GN_TRY(lincomb(lc, s));
+      lc.base = b.gk; lc.n_terms = 0;
+      return GNODE_OK;
+    };
+    for (int q = 0; q < n_src; ++q) {
+      const float cf = (float)src[q].w[st] * dt;
+      if (cf == 0.f) continue;
+      if (lc.n_terms == kMaxTerms) GN_TRY(flush());
+      lc.in[lc.n_terms] = src[q].G; lc.coef[lc.n_terms] = cf; ++lc.n_terms; any = true;
+    }
+    for (int i = st + 1; i < S; ++i) {
+      const float cf = (float)tb.beta[i][st] * dt;
+      if (cf == 0.f) continue;
+      if (lc.n_terms == kMaxTerms) GN_TRY(flush());
+      lc.in[lc.n_terms] = b.kbuf[i]; lc.coef[lc.n_terms] = cf; ++lc.n_terms; any = true;
+    }
+    if (!any) {   // the stage does not influence any output
+      GN_CUDA(cudaMemsetAsync(b.kbuf[st], 0, sizeof(float) * n, s));
+      continue;
+    }
+    GN_TRY(flush());
+    GN_TRY(f.vjp(xst[st], st, b.gk, b.kbuf[st], s));
+  }
+  // gout = sum_q G_q + sum_s g_x[s] (+ extra)
+  LinComb lc{};
+  lc.out = gout; lc.base = nullptr; lc.n = n; lc.n_terms = 0;
+  auto add = [&](const float* p) -> int {
+    if (lc.n_terms == kMaxTerms) { GN_TRY(lincomb(lc, s)); lc.base = gout; lc.n_terms = 0; }
+    lc.in[lc.n_terms] = p; lc.coef[lc.n_terms] = 1.f; ++lc.n_terms;
+    return GNODE_OK;
+  };
+  for (int q = 0; q < n_src; ++q) GN_TRY(add(src[q].G));        // sources first: gout may alias one of them
+  for (int st = 0; st < S; ++st) GN_TRY(add(b.kbuf[st]));
+  if (extra) GN_TRY(add(extra));
+  GN_TRY(lincomb(lc, s));
+  return GNODE_OK;
+}
+
+int integrate_fixed_bwd_generic(Field& f, const Tableau& tb, const float* sol, const float* t, int n_t, const float* grad_sol,
+                                float* grad_y0, const RkBwdBufs& b, float* gcur, cudaStream_t s) {
+  const int64_t n = f.numel();
+  GN_CUDA(cudaMemcpyAsync(gcur, grad_sol + (int64_t)(n_t - 1) * n, sizeof(float) * n, cudaMemcpyDeviceToDevice, s));
+  for (int j = n_t - 2; j >= 0; --j) {
+    RkBwdSrc src{};
+    src.G = gcur;
+    for (int st = 0; st < tb.S; ++st) src.w[st] = tb.c_sol[st];
+    GN_TRY(rk_step_bwd(f, tb, sol + (int64_t)j * n, t[j + 1] - t[j], &src, 1, b, nullptr, grad_sol + (int64_t)j * n, gcur, s));
+  }
+  if (grad_y0) GN_CUDA(cudaMemcpyAsync(grad_y0, gcur, sizeof(float) * n, cudaMemcpyDeviceToDevice, s));
+  return GNODE_OK;
+}
+
+int integrate_dopri5_bwd_generic(Field& f, const float* y0, const double* tau, int n_acc, const double* t, int n_t,
+                                 const float* grad_sol, float* grad_y0, const RkBwdBufs& b, float* ys, float* gping,
+                                 float* gpong, cudaStream_t s) {
+  const Tableau& tb = *tableau_for(GNODE_DOPRI5);
+  const int64_t n = f.numel();
+  // ---- replay the accepted steps (see fold.cu:integrate_dopri5_folded_bwd for the scheme) ----
+  GN_CUDA(cudaMemcpyAsync(ys, y0, sizeof(float) * n, cudaMemcpyDeviceToDevice, s));
+  for (int k = 0; k + 1 < n_acc; ++k) {
+    const float dt = (float)(tau[k + 1] - tau[k]);
+    const float* y = ys + (int64_t)k * n;
+    for (int st = 0; st < tb.S - 1; ++st) {          // stage 6 is f(y_{k+1}): not needed for y_{k+1} itself
+      const float* x = y;
+      if (st > 0) { GN_TRY(stage_input(tb, st, y, b.kbuf, dt, b.xs[st], n, s)); x = b.xs[st]; }
+      GN_TRY(f.eval(x, b.kbuf[st], nullptr, 1.f, st, s));
+    }
+    GN_TRY(stage_input(tb, tb.S - 1, y, b.kbuf, dt, ys + (int64_t)(k + 1) * n, n, s));   // beta[6] == c_sol
+  }
+  const float* Gnext = nullptr;
+  float* gout = gping;
+  int out_hi = n_t - 1;
+  for (int k = n_acc - 1; k >= 0; --k) {
+    const double t0 = tau[k], t1 = tau[k + 1];
+    int out_lo = out_hi;
+    while (out_lo >= 1 && t[out_lo] > t0) --out_lo;
+    RkBwdSrc src[kMaxTerms];
+    int n_src = 0;
+    for (int i = out_lo + 1; i <= out_hi; ++i) {
+      if (n_src == kMaxTerms - 1) { set_error("dopri5 backward: more than %d outputs inside one accepted step", kMaxTerms - 1); return GNODE_ERR_SOLVER; }
+      src[n_src].G = grad_sol + (int64_t)i * n;
+      dopri5_dense_weights(tb, (t[i] - t0) / (t1 - t0), src[n_src].w);
+      ++n_src;
+    }
+    if (Gnext) {
+      src[n_src].G = Gnext;
+      for (int st = 0; st < tb.S; ++st) src[n_src].w[st] = tb.c_sol[st];
+      ++n_src;
+    }
+    out_hi = out_lo;
+    if (n_src == 0) continue;
+    GN_TRY(rk_step_bwd(f, tb, ys + (int64_t)k * n, (float)(t1 - t0), src, n_src, b, nullptr, nullptr, gout, s));
+    Gnext = gout;
+    gout = (gout == gping) ? gpong : gping;
+  }
+  if (grad_y0) {
+    LinComb lc{};
+    lc.out = grad_y0; lc.base = grad_sol; lc.n = n; lc.n_terms = 0;
+    if (Gnext) { lc.in[0] = Gnext; lc.coef[0] = 1.f; lc.n_terms = 1; }
+    GN_TRY(lincomb(lc, s));
+  }
+  return GNODE_OK;
+}
+
+}  // namespace gnode
+
 namespace {
 void carve_dopri5_fold(Arena& a, Sage3Ctx& c, FoldWs& f, Dopri5FoldBufs& b) {
   c.carve(a, 7, false);

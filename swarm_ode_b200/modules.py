@@ -176,6 +176,4 @@ class ODEFunction(nn.Module):
                 self.net[4].weight, self.net[4].bias]
 
     def forward(self, t, x: torch.Tensor) -> torch.Tensor:
-        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
-            raise GnodeError("ODEFunction: the native MLP field is forward-only; wrap the call in torch.no_grad()")
         return ops.mlp_rhs(x, self.param_list())

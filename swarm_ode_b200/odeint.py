@@ -51,8 +51,6 @@ def odeint(func, y0: torch.Tensor, t: torch.Tensor, *, rtol: float = 1e-7, atol:
         return sol
 
     if isinstance(func, ODEFunction):
-        if torch.is_grad_enabled() and (y0.requires_grad or any(p.requires_grad for p in func.parameters())):
-            raise GnodeError("odeint(ODEFunction): the native MLP field is forward-only; use torch.no_grad()")
         sol, stats = ops.mlp_integrate(y0, func.param_list(), t, method, rtol=rtol, atol=atol,
                                        max_num_steps=int(options.get("max_num_steps", 0)))
         if sink is not None:

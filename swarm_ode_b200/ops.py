@@ -531,7 +531,7 @@ def integrate_fixed_decode(y0, graph: CSRGraph, params: Sequence[torch.Tensor], 
 
 
 # ----------------------------------------------------------------------------------------------
-# MLP vector field (ODEFunction), forward only
+# MLP vector field (ODEFunction): forward, and backprop through the field / the solver
 # ----------------------------------------------------------------------------------------------
 def _mlp_params(w: Sequence[torch.Tensor]):
     w0, b0, w1, b1, w2, b2 = w
@@ -541,9 +541,7 @@ def _mlp_params(w: Sequence[torch.Tensor]):
     return _lib.GnodeMlpParams(H, h, *[t.data_ptr() for t in w]), H, h
 
 
-def mlp_rhs(x: torch.Tensor, params: Sequence[torch.Tensor]) -> torch.Tensor:
-    x = _f32(x.detach(), "x")
-    w = [_f32(p.detach(), "param") for p in params]
+def _mlp_rhs_forward(x, w):
     p, H, h = _mlp_params(w)
     M = x.shape[0]
     out = torch.empty_like(x)
@@ -555,11 +553,39 @@ def mlp_rhs(x: torch.Tensor, params: Sequence[torch.Tensor]) -> torch.Tensor:
     return out
 
 
-def mlp_integrate(y0: torch.Tensor, params: Sequence[torch.Tensor], t, method: str, rtol: float = 1e-7,
-                  atol: float = 1e-9, max_num_steps: int = 0, trace_cap: int = 4096):
-    """Integrate the MLP field; returns ``(solution [T, M, H], Dopri5Stats | None)``."""
-    y0 = _f32(y0.detach(), "y0")
-    w = [_f32(p.detach(), "param") for p in params]
+class _MlpRhsFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, *w):
+        xc = _f32(x.detach(), "x")
+        wc = [_f32(p.detach(), "param") for p in w]
+        ctx.save_for_backward(xc, *wc)
+        return _mlp_rhs_forward(xc, wc)
+
+    @staticmethod
+    def backward(ctx, g):
+        x, *w = ctx.saved_tensors
+        g = _f32(g, "grad_out")
+        p, H, h = _mlp_params(w)
+        M = x.shape[0]
+        gx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        gw = [torch.zeros_like(t) for t in w]
+        grads = _lib.GnodeMlpGrads(*[t.data_ptr() for t in gw])
+        L = _lib.lib()
+        ws = _ws(L.gnode_mlp_bwd_workspace_bytes(M, H, h, 0, 1), x.device)
+        with torch.cuda.device(x.device):
+            _lib.check(L.gnode_mlp_rhs_bwd(C.byref(p), _lib.ptr(x), _lib.ptr(g), M, _lib.ptr(gx), C.byref(grads),
+                                           _lib.ptr(ws), ws.numel(), _lib.stream_ptr(x.device)), "gnode_mlp_rhs_bwd")
+        return (gx, *gw)
+
+
+def mlp_rhs(x: torch.Tensor, params: Sequence[torch.Tensor]) -> torch.Tensor:
+    """One evaluation of the MLP field; differentiable."""
+    if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in params)):
+        return _MlpRhsFn.apply(x, *params)
+    return _mlp_rhs_forward(_f32(x.detach(), "x"), [_f32(p.detach(), "param") for p in params])
+
+
+def _mlp_integrate_forward(y0, w, t, method: str, rtol, atol, max_num_steps, trace_cap):
     p, H, h = _mlp_params(w)
     M = y0.shape[0]
     L = _lib.lib()
@@ -577,7 +603,7 @@ def mlp_integrate(y0: torch.Tensor, params: Sequence[torch.Tensor], t, method: s
                                                         _lib.ptr(sol), st, tr, int(max_num_steps), _lib.ptr(ws),
                                                         ws.numel(), _lib.stream_ptr(y0.device)),
                            "gnode_mlp_integrate_dopri5")
-        return sol, _run_dopri5(call, trace_cap)
+        return sol, _run_dopri5(call, trace_cap), t_host
     t_host = _t_to_host(t)
     T = len(t_host)
     sol = torch.empty((T, M, H), dtype=torch.float32, device=y0.device)
@@ -585,7 +611,72 @@ def mlp_integrate(y0: torch.Tensor, params: Sequence[torch.Tensor], t, method: s
         _lib.check(L.gnode_mlp_integrate_fixed(C.byref(p), m, _lib.ptr(y0), M, _float_array(t_host), T, _lib.ptr(sol),
                                                _lib.ptr(ws), ws.numel(), _lib.stream_ptr(y0.device)),
                    "gnode_mlp_integrate_fixed")
-    return sol, None
+    return sol, None, t_host
+
+
+class _MlpIntegrateFn(torch.autograd.Function):
+    """``odeint(ODEFunction, y0, t)`` with backprop through the solver (fixed grid, or dopri5 replayed over its accepted
+    steps with step sizes as constants -- see _IntegrateDopri5Fn)."""
+
+    @staticmethod
+    def forward(ctx, y0, t, method, rtol, atol, max_num_steps, trace_cap, holder, *w):
+        y0c = _f32(y0.detach(), "y0")
+        wc = [_f32(p.detach(), "param") for p in w]
+        sol, stats, t_host = _mlp_integrate_forward(y0c, wc, t, method, rtol, atol, max_num_steps, trace_cap)
+        holder.append(stats)
+        ctx.method, ctx.t_host, ctx.tau = method, tuple(t_host), None
+        if method == "dopri5" and stats.n_attempted <= len(stats.dts):
+            tau = [float(t_host[0])]
+            for dt, acc in zip(stats.dts, stats.accepted):
+                if acc:
+                    tau.append(tau[-1] + dt)
+            ctx.tau = tau
+        ctx.save_for_backward(y0c, sol, *wc)
+        return sol
+
+    @staticmethod
+    def backward(ctx, gsol):
+        y0, sol, *w = ctx.saved_tensors
+        gsol = _f32(gsol, "grad_solution")
+        p, H, h = _mlp_params(w)
+        M, T = y0.shape[0], len(ctx.t_host)
+        gy0 = torch.empty_like(y0) if ctx.needs_input_grad[0] else None
+        gw = [torch.zeros_like(t) for t in w]
+        grads = _lib.GnodeMlpGrads(*[t.data_ptr() for t in gw])
+        L = _lib.lib()
+        m = METHODS[ctx.method]
+        with torch.cuda.device(y0.device):
+            if ctx.method == "dopri5":
+                if ctx.tau is None:
+                    raise GnodeError("dopri5 backward: the forward pass attempted more steps than its trace holds; raise trace_cap")
+                K = len(ctx.tau) - 1
+                ws = _ws(L.gnode_mlp_bwd_workspace_bytes(M, H, h, m, K), y0.device)
+                tau = (C.c_double * (K + 1))(*ctx.tau)
+                tarr = (C.c_double * T)(*ctx.t_host)
+                _lib.check(L.gnode_mlp_integrate_dopri5_bwd(C.byref(p), _lib.ptr(y0), M, tau, K, tarr, T, _lib.ptr(gsol),
+                                                            _lib.ptr(gy0), C.byref(grads), _lib.ptr(ws), ws.numel(),
+                                                            _lib.stream_ptr(y0.device)), "gnode_mlp_integrate_dopri5_bwd")
+            else:
+                ws = _ws(L.gnode_mlp_bwd_workspace_bytes(M, H, h, m, 1), y0.device)
+                _lib.check(L.gnode_mlp_integrate_fixed_bwd(C.byref(p), m, _lib.ptr(sol), M, _float_array(ctx.t_host), T,
+                                                           _lib.ptr(gsol), _lib.ptr(gy0), C.byref(grads), _lib.ptr(ws),
+                                                           ws.numel(), _lib.stream_ptr(y0.device)),
+                           "gnode_mlp_integrate_fixed_bwd")
+        return (gy0, None, None, None, None, None, None, None, *gw)
+
+
+def mlp_integrate(y0: torch.Tensor, params: Sequence[torch.Tensor], t, method: str, rtol: float = 1e-7,
+                  atol: float = 1e-9, max_num_steps: int = 0, trace_cap: int = 4096):
+    """Integrate the MLP field; returns ``(solution [T, M, H], Dopri5Stats | None)``.  Differentiable with respect to
+    ``y0`` and the parameters."""
+    if torch.is_grad_enabled() and (y0.requires_grad or any(p.requires_grad for p in params)):
+        holder: list = []
+        sol = _MlpIntegrateFn.apply(y0, t, method, float(rtol), float(atol), int(max_num_steps), int(trace_cap), holder,
+                                    *params)
+        return sol, holder[0]
+    sol, stats, _ = _mlp_integrate_forward(_f32(y0.detach(), "y0"), [_f32(p.detach(), "param") for p in params], t, method,
+                                           rtol, atol, max_num_steps, trace_cap)
+    return sol, stats
 
 
 # ----------------------------------------------------------------------------------------------
