@@ -324,6 +324,24 @@ int gnode_mlp_integrate_dopri5(const gnode_mlp_params* p, const float* y0, int64
                                int64_t max_num_steps, void* workspace, size_t workspace_bytes,
                                gnode_stream_t stream);
 
+/* Backward of the bipartite SAGEConv relation of HeteroConv (scripts/gnode.py:92-99,126-128) and of the Linear
+ * embeddings / action heads (:84-90,104-115): what loss.backward() runs when the Q-network is trained.
+ *   gs = scale * grad_out * [out > 0]  (mask only when `out` is given: the ReLU folded into the last relation)
+ *   grad_wl += gs^T mean_j x_src, grad_bl += colsum(gs), grad_wr += gs^T x_dst          (accumulated, may be NULL)
+ *   grad_x_dst = gs @ wr, grad_x_src = A^T(gs @ wl)                                      (overwritten, may be NULL) */
+size_t gnode_sage_bipartite_bwd_workspace_bytes(int64_t n_dst, int32_t c_in, int32_t c_out);
+int gnode_sage_bipartite_bwd(const gnode_graph* g, int64_t n_src, int64_t n_dst, const float* x_src,
+                             const float* x_dst, int32_t c_in, int32_t c_out, const float* wl, const float* wr,
+                             const float* grad_out, const float* out, float scale, float* grad_x_src,
+                             float* grad_x_dst, float* grad_wl, float* grad_bl, float* grad_wr,
+                             void* workspace, size_t workspace_bytes, gnode_stream_t stream);
+/* out = act(x @ w^T + b): grad_x = gm @ w (overwritten), grad_w += gm^T x, grad_b += colsum(gm),
+ * gm = grad_out * [out > 0] when `out` is given (ReLU), else grad_out.  x [m, c_in], w [c_out, c_in]. */
+size_t gnode_linear_bwd_workspace_bytes(int64_t m, int32_t c_in, int32_t c_out);
+int gnode_linear_bwd(const float* x, const float* w, const float* out, const float* grad_out, int64_t m,
+                     int32_t c_in, int32_t c_out, float* grad_x, float* grad_w, float* grad_b, void* workspace,
+                     size_t workspace_bytes, gnode_stream_t stream);
+
 /* Backward of the MLP field and of its solves -- loss.backward() through ODEFunction / odeint in the Q-network
  * training of scripts/gnode.py:136-137,160-174 and scripts/run_gnode.py:134-135 (plain autograd, no adjoint).
  * Parameter gradients are accumulated (+=); grad_x / grad_y0 are overwritten (may be NULL).  The dopri5 form replays

@@ -65,6 +65,7 @@ class HeteroGraphODENetworkRef(nn.Module):
             self.ode_func_picker = ODEFunctionRef(hidden_dim, ode_hidden_dim)
         self.agv_action_head = nn.Sequential(nn.Linear(hidden_dim, hidden_dim // 2), nn.ReLU(), nn.Linear(hidden_dim // 2, out))
         self.picker_action_head = nn.Sequential(nn.Linear(hidden_dim, hidden_dim // 2), nn.ReLU(), nn.Linear(hidden_dim // 2, out))
+        self.solver_options: Optional[dict] = None     # test hook, forwarded to the adaptive odeint_ref(options=...)
 
     def forward(self, hetero_data, integration_time: float = 1.0):
         x_dict = {"agv": self.agv_embedding(hetero_data["agv"].x),
@@ -76,7 +77,7 @@ class HeteroGraphODENetworkRef(nn.Module):
         t = torch.tensor([0.0, integration_time], dtype=torch.float32)
         if self.action_size is None:
             allx = torch.cat([x_dict["agv"], x_dict["picker"], x_dict["location"]], dim=0)
-            ev = odeint_ref(self.ode_func, allx, t)[-1]
+            ev = odeint_ref(self.ode_func, allx, t, options=self.solver_options)[-1]
             na, npk = hetero_data["agv"].num_nodes, hetero_data["picker"].num_nodes
             agv, picker, loc = ev[:na], ev[na:na + npk], ev[na + npk:]
         else:

@@ -171,3 +171,143 @@ extern "C" int gnode_sage_bipartite_fwd(const gnode_graph* g, int64_t n_dst, con
   }
   return gemm_nt(q, s);
 }
+
+// ------------------------------------------------------------------------------------------------
+// Backward of the bipartite layer: with gs = scale * grad_out * [out > 0] (mask only when `out` is given),
+//   grad_wl += gs^T A(x_src)    grad_bl += colsum(gs)    grad_wr += gs^T x_dst
+//   grad_x_dst = gs @ wr        grad_x_src = A^T(gs @ wl)                       (both overwritten, may be NULL)
+// The Q-network of scripts/gnode.py / scripts/run_gnode.py is trained through these layers (loss.backward()).
+// ------------------------------------------------------------------------------------------------
+namespace gnode {
+namespace {
+struct BipBwdWs { float *wcat, *wcatT, *cat, *gm, *gcat, *dwcat, *partials; };
+void carve_bip_bwd(Arena& a, int64_t n_dst, int ci, int co, BipBwdWs& w) {
+  w.wcat = a.take<float>((size_t)co * 2 * ci);
+  w.wcatT = a.take<float>((size_t)co * 2 * ci);
+  w.cat = a.take<float>((size_t)n_dst * 2 * ci);
+  w.gm = a.take<float>((size_t)n_dst * co);
+  w.gcat = a.take<float>((size_t)n_dst * 2 * ci);
+  w.dwcat = a.take<float>((size_t)co * 2 * ci);
+  w.partials = a.take<float>(gemm_tn_workspace_floats(co, 2 * ci, n_dst));
+}
+}  // namespace
+}  // namespace gnode
+
+extern "C" size_t gnode_sage_bipartite_bwd_workspace_bytes(int64_t n_dst, int32_t c_in, int32_t c_out) {
+  Arena a(nullptr, 0);
+  BipBwdWs w;
+  carve_bip_bwd(a, n_dst, c_in, c_out, w);
+  return a.off;
+}
+
+extern "C" int gnode_sage_bipartite_bwd(const gnode_graph* g, int64_t n_src, int64_t n_dst, const float* x_src,
+                                        const float* x_dst, int32_t ci, int32_t co, const float* wl, const float* wr,
+                                        const float* grad_out, const float* out, float scale, float* grad_x_src,
+                                        float* grad_x_dst, float* grad_wl, float* grad_bl, float* grad_wr,
+                                        void* workspace, size_t workspace_bytes, gnode_stream_t stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  GN_ARG(g != nullptr && g->rowptr != nullptr && g->t_rowptr != nullptr && (g->n_edges == 0 || (g->col && g->t_col)),
+         "gnode_sage_bipartite_bwd: bad graph");
+  GN_ARG(n_dst > 0 && n_dst <= g->n_nodes && n_src > 0 && n_src <= g->n_nodes, "gnode_sage_bipartite_bwd: n_src / n_dst out of range");
+  GN_ARG(ci > 0 && co > 0 && x_src && x_dst && wl && wr && grad_out, "gnode_sage_bipartite_bwd: bad argument");
+  Arena a(workspace, workspace_bytes);
+  BipBwdWs w;
+  carve_bip_bwd(a, n_dst, ci, co, w);
+  GN_ARENA_OK(a, "gnode_sage_bipartite_bwd");
+  gnode_graph gd = *g;
+  gd.n_nodes = n_dst;
+  const float* gm = grad_out;
+  if (out) {
+    GN_TRY(relu_mask(grad_out, out, w.gm, n_dst * (int64_t)co, s));
+    gm = w.gm;
+  }
+  // cat = [A(x_src) | x_dst], wcat = [wl | wr], wcatT = wcat^T
+  PackSegHost sg[5] = {{w.wcat, wl, co, ci, ci, 2 * ci, 0, 0},
+                       {w.wcat + ci, wr, co, ci, ci, 2 * ci, 0, 0},
+                       {w.cat + ci, x_dst, (int)n_dst, ci, ci, 2 * ci, 0, 0},
+                       {w.wcatT, wl, co, ci, ci, co, 1, 0},
+                       {w.wcatT + (size_t)ci * co, wr, co, ci, ci, co, 1, 0}};
+  GN_TRY(pack_segments(sg, 5, s));
+  GN_TRY(agg_mean_fwd(gd, x_src, ci, w.cat, 2 * ci, ci, nullptr, 0, nullptr, 0, s));
+  if (grad_wl || grad_wr || grad_bl) {
+    GN_CUDA(cudaMemsetAsync(w.dwcat, 0, sizeof(float) * co * 2 * ci, s));
+    GemmTN q{};
+    q.A = gm; q.lda = co; q.P = co; q.B = w.cat; q.ldb = 2 * ci; q.Q = 2 * ci; q.Nrows = n_dst; q.C = w.dwcat; q.ldc = 2 * ci;
+    q.scale = scale;
+    if (grad_bl) { q.colsumA = grad_bl; q.colsumA_scale = scale; }
+    GN_TRY(gemm_tn(q, w.partials, s));
+    PackSegHost so[2];
+    int n = 0;
+    if (grad_wl) so[n++] = PackSegHost{grad_wl, w.dwcat, co, ci, 2 * ci, ci, 0, 1};
+    if (grad_wr) so[n++] = PackSegHost{grad_wr, w.dwcat + ci, co, ci, 2 * ci, ci, 0, 1};
+    if (n) GN_TRY(pack_segments(so, n, s));
+  }
+  if (grad_x_src || grad_x_dst) {
+    GemmNT q{};   // gcat = scale * gm @ wcat      [n_dst, 2 ci]
+    q.A = gm; q.lda = co; q.B = w.wcatT; q.ldb = co; q.C = w.gcat; q.ldc = 2 * ci; q.M = n_dst; q.N = 2 * ci; q.K = co;
+    q.scale = scale;
+    GN_TRY(gemm_nt(q, s));
+    if (grad_x_dst) {
+      PackSegHost so[1] = {{grad_x_dst, w.gcat + ci, (int)n_dst, ci, 2 * ci, ci, 0, 0}};
+      GN_TRY(pack_segments(so, 1, s));
+    }
+    if (grad_x_src) {
+      gnode_graph gs = *g;
+      gs.n_nodes = n_src;      // rows of the transposed CSR = source nodes
+      GN_TRY(agg_mean_bwd(gs, w.gcat, 2 * ci, grad_x_src, ci, ci, nullptr, 0, nullptr, 0, s));
+    }
+  }
+  return GNODE_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Backward of a Linear layer run through the NT contraction:  out = act(x @ w^T + b), act in {identity, relu}.
+//   grad_x = gm @ w (overwritten, may be NULL), grad_w += gm^T x, grad_b += colsum(gm), gm = grad_out * [out > 0] if out.
+// (embeddings and action heads of HeteroGraphODENetwork, scripts/gnode.py:84-90,104-115)
+// ------------------------------------------------------------------------------------------------
+extern "C" size_t gnode_linear_bwd_workspace_bytes(int64_t m, int32_t c_in, int32_t c_out) {
+  Arena a(nullptr, 0);
+  a.take<float>((size_t)m * c_out);
+  a.take<float>((size_t)c_in * c_out);
+  a.take<float>(gemm_tn_workspace_floats(c_out, c_in, m));
+  return a.off;
+}
+
+extern "C" int gnode_linear_bwd(const float* x, const float* w, const float* out, const float* grad_out, int64_t m,
+                                int32_t ci, int32_t co, float* grad_x, float* grad_w, float* grad_b, void* workspace,
+                                size_t workspace_bytes, gnode_stream_t stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  GN_ARG(x && w && grad_out && m > 0 && ci > 0 && co > 0, "gnode_linear_bwd: bad argument");
+  Arena a(workspace, workspace_bytes);
+  float* gmb = a.take<float>((size_t)m * co);
+  float* wT = a.take<float>((size_t)ci * co);
+  float* partials = a.take<float>(gemm_tn_workspace_floats(co, ci, m));
+  GN_ARENA_OK(a, "gnode_linear_bwd");
+  const float* gm = grad_out;
+  if (out) {
+    GN_TRY(relu_mask(grad_out, out, gmb, m * (int64_t)co, s));
+    gm = gmb;
+  }
+  if (grad_w || grad_b) {
+    GemmTN q{};
+    q.A = gm; q.lda = co; q.P = co; q.B = x; q.ldb = ci; q.Q = ci; q.Nrows = m; q.C = grad_w; q.ldc = ci;
+    if (grad_b) q.colsumA = grad_b;
+    if (grad_w) {
+      GN_TRY(gemm_tn(q, partials, s));
+    } else {
+      // bias only: column sums through the same engine into a scratch product
+      float* scratch = wT;
+      GN_CUDA(cudaMemsetAsync(scratch, 0, sizeof(float) * ci * co, s));
+      q.C = scratch;
+      GN_TRY(gemm_tn(q, partials, s));
+    }
+  }
+  if (grad_x) {
+    PackSegHost sg[1] = {{wT, w, co, ci, ci, co, 1, 0}};      // wT[c, r] = w[r, c]   [ci, co]
+    GN_TRY(pack_segments(sg, 1, s));
+    GemmNT q{};
+    q.A = gm; q.lda = co; q.B = wT; q.ldb = co; q.C = grad_x; q.ldc = ci; q.M = m; q.N = ci; q.K = co;
+    GN_TRY(gemm_nt(q, s));
+  }
+  return GNODE_OK;
+}

@@ -9,7 +9,8 @@
 Every FLOP runs in ``libgnode_b200.so``: the embeddings and action heads through the dense NT contraction, each
 relation through ``gnode_sage_bipartite_fwd`` (HeteroConv's mean over relations and the ReLU after it are folded into
 the relation calls), the MLP field through the native integrators.  The reference uses this network as an RL
-Q-function; here it is forward-only: calling it with autograd enabled on parameters raises (no silent fallback).
+Q-function and trains it with loss.backward(): every piece is an autograd node whose backward runs in the library too
+(``gnode_linear_bwd``, ``gnode_sage_bipartite_bwd``, the MLP solver backward of ops.mlp_integrate).
 """
 from __future__ import annotations
 
@@ -105,6 +106,11 @@ def sage_bipartite(graph: CSRGraph, x_src: torch.Tensor, x_dst: torch.Tensor, co
     x_src = _lib.require_cuda_f32(x_src.detach(), "x_src")
     x_dst = _lib.require_cuda_f32(x_dst.detach(), "x_dst")
     wl, bl, wr = (_lib.require_cuda_f32(t.detach(), "param") for t in (conv.lin_l.weight, conv.lin_l.bias, conv.lin_r.weight))
+    return _sage_bipartite_raw(graph, x_src, x_dst, wl, bl, wr, scale, accum, post_relu, out)
+
+
+def _sage_bipartite_raw(graph: CSRGraph, x_src, x_dst, wl, bl, wr, scale: float = 1.0, accum=None, post_relu: bool = False,
+                        out=None) -> torch.Tensor:
     n_dst, ci = x_dst.shape
     co = wl.shape[0]
     if x_src.shape[1] != ci or wl.shape[1] != ci or wr.shape[1] != ci:
@@ -141,7 +147,17 @@ class HeteroConv(nn.Module):
             if et in edge_index_dict and src in x_dict and dst in x_dict:
                 active.setdefault(dst, []).append(et)
         out: Dict[str, torch.Tensor] = {}
+        needs_grad = torch.is_grad_enabled() and (any(p.requires_grad for p in self.parameters()) or
+                                                  any(v.requires_grad for v in x_dict.values()))
         for dst, ets in active.items():
+            if needs_grad:
+                graphs, rest = [], []
+                for et in ets:
+                    conv = self.convs["__".join(et)]
+                    graphs.append(_relation_graph(edge_index_dict[et], x_dict[et[0]].size(0), x_dict[dst].size(0), cache, et))
+                    rest += [x_dict[et[0]], conv.lin_l.weight, conv.lin_l.bias, conv.lin_r.weight]
+                out[dst] = _RelationGroupFn.apply(graphs, relu, x_dict[dst], *rest)
+                continue
             acc = None
             for i, et in enumerate(ets):
                 src = et[0]
@@ -153,8 +169,86 @@ class HeteroConv(nn.Module):
         return out
 
 
+class _LinearFn(torch.autograd.Function):
+    """``act(x @ w.T + b)`` with the backward in the library (gnode_linear_bwd)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, act: str):
+        xc = _lib.require_cuda_f32(x.detach(), "x")
+        wc = _lib.require_cuda_f32(w.detach(), "weight")
+        bc = _lib.require_cuda_f32(b.detach(), "bias")
+        out = ops.gemm_nt(xc, wc, bias=bc, act=act)
+        ctx.act = act
+        ctx.save_for_backward(xc, wc, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, w, out = ctx.saved_tensors
+        g = _lib.require_cuda_f32(g.contiguous(), "grad_out")
+        m, ci = x.shape
+        co = w.shape[0]
+        gx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        gw = torch.zeros_like(w)
+        gb = torch.zeros(co, dtype=torch.float32, device=x.device)
+        L = _lib.lib()
+        ws = _lib.WORKSPACE.get(L.gnode_linear_bwd_workspace_bytes(m, ci, co), x.device)
+        with torch.cuda.device(x.device):
+            _lib.check(L.gnode_linear_bwd(_lib.ptr(x), _lib.ptr(w), _lib.ptr(out if ctx.act == "relu" else None), _lib.ptr(g),
+                                          m, ci, co, _lib.ptr(gx), _lib.ptr(gw), _lib.ptr(gb), _lib.ptr(ws), ws.numel(),
+                                          _lib.stream_ptr(x.device)), "gnode_linear_bwd")
+        return gx, gw, gb, None
+
+
 def _linear(x: torch.Tensor, lin: nn.Linear, act: str = "none") -> torch.Tensor:
+    if torch.is_grad_enabled() and (x.requires_grad or lin.weight.requires_grad or lin.bias.requires_grad):
+        return _LinearFn.apply(x, lin.weight, lin.bias, act)
     return ops.gemm_nt(x, lin.weight, bias=lin.bias, act=act)
+
+
+class _RelationGroupFn(torch.autograd.Function):
+    """All relations of one destination type of a HeteroConv layer: ``relu?(mean_r conv_r((x_src_r, x_dst), edges_r))``.
+    Inputs after the fixed ones: x_dst, then per relation (x_src, lin_l.weight, lin_l.bias, lin_r.weight)."""
+
+    @staticmethod
+    def forward(ctx, graphs, relu: bool, x_dst, *rest):
+        R = len(graphs)
+        xd = _lib.require_cuda_f32(x_dst.detach(), "x_dst")
+        tens = [_lib.require_cuda_f32(t.detach(), "relation input") for t in rest]
+        acc = None
+        for r in range(R):
+            xs, wl, bl, wr = tens[4 * r:4 * r + 4]
+            acc = _sage_bipartite_raw(graphs[r], xs, xd, wl, bl, wr, scale=1.0 / R, accum=acc,
+                                      post_relu=relu and r == R - 1, out=acc)
+        ctx.graphs, ctx.relu = graphs, relu
+        ctx.save_for_backward(xd, acc, *tens)
+        return acc
+
+    @staticmethod
+    def backward(ctx, g):
+        xd, out, *tens = ctx.saved_tensors
+        R = len(ctx.graphs)
+        g = _lib.require_cuda_f32(g.contiguous(), "grad_out")
+        n_dst, ci = xd.shape
+        co = out.shape[1]
+        L = _lib.lib()
+        ws = _lib.WORKSPACE.get(L.gnode_sage_bipartite_bwd_workspace_bytes(n_dst, ci, co), xd.device)
+        gxd_total = None
+        grads = []
+        with torch.cuda.device(xd.device):
+            for r in range(R):
+                xs, wl, bl, wr = tens[4 * r:4 * r + 4]
+                gxs = torch.empty_like(xs)
+                gxd = torch.empty_like(xd)
+                gwl, gbl, gwr = torch.zeros_like(wl), torch.zeros_like(bl), torch.zeros_like(wr)
+                _lib.check(L.gnode_sage_bipartite_bwd(ctx.graphs[r].ref(), xs.shape[0], n_dst, _lib.ptr(xs), _lib.ptr(xd), ci, co,
+                                                      _lib.ptr(wl), _lib.ptr(wr), _lib.ptr(g),
+                                                      _lib.ptr(out if ctx.relu else None), 1.0 / R, _lib.ptr(gxs),
+                                                      _lib.ptr(gxd), _lib.ptr(gwl), _lib.ptr(gbl), _lib.ptr(gwr), _lib.ptr(ws),
+                                                      ws.numel(), _lib.stream_ptr(xd.device)), "gnode_sage_bipartite_bwd")
+                gxd_total = gxd if gxd_total is None else gxd_total.add_(gxd)
+                grads += [gxs, gwl, gbl, gwr]
+        return (None, None, gxd_total, *grads)
 
 
 class HeteroGraphODENetwork(nn.Module):
@@ -190,9 +284,6 @@ class HeteroGraphODENetwork(nn.Module):
         return _linear(_linear(x, head[0], "relu"), head[2])
 
     def forward(self, hetero_data, integration_time: float = 1.0) -> Dict[str, torch.Tensor]:
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            raise GnodeError("HeteroGraphODENetwork: the native hetero path is forward-only; wrap the call in "
-                             "torch.no_grad() (training the Q-network through it is not implemented)")
         x_dict = {"agv": _linear(hetero_data["agv"].x, self.agv_embedding),
                   "picker": _linear(hetero_data["picker"].x, self.picker_embedding),
                   "location": _linear(hetero_data["location"].x, self.location_embedding)}

@@ -59,10 +59,43 @@ def test_hetero_conv_skips_absent_relations_cpu_semantics():
     assert list(out) == ["agv"] and out["agv"].shape == (3, 4)
 
 
-def test_forward_only_module_raises_under_autograd():
-    m = S.HeteroGraphODENetwork(DIMS, hidden_dim=16, ode_hidden_dim=8)
-    with pytest.raises(S.GnodeError, match="forward-only"):
-        m(S.HeteroData())
+def test_cpu_tensors_raise_no_fallback(gold):
+    m = _model(gold, S.HeteroGraphODENetwork, "typed")
+    with pytest.raises(S.GnodeError):
+        m(_data(gold, S.HeteroData))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag", list(CASES))
+def test_cuda_training_gradients_match_autograd_through_the_oracle(cuda, gold, tag):
+    """The reference trains this Q-network with loss.backward() (scripts/gnode.py / scripts/run_gnode.py learners): every
+    parameter gradient of a Q-value loss, through the action heads, the ODE solve (dopri5 for the joint form, euler for
+    the typed form), both HeteroConv layers and the embeddings, against autograd through the oracle (which replays the
+    GPU run's adaptive steps, see tests/test_gpu_integrate.py)."""
+    m = _model(gold, S.HeteroGraphODENetwork, tag).to(cuda)
+    d = _data(gold, S.HeteroData).to(cuda)
+    out = m(d, integration_time=CASES[tag]["t"])
+    loss = out["agv_q_values"].pow(2).mean() + 0.5 * out["picker_q_values"].pow(2).mean() + 0.1 * out["location_embeddings"].pow(2).mean()
+    loss.backward()
+    ref = _model(gold, HeteroGraphODENetworkRef, tag)
+    if tag == "joint":
+        ref.solver_options = {"imposed_dts": list(m.last_stats.dts)}
+    o2 = ref(_data(gold, RefHeteroData), integration_time=CASES[tag]["t"])
+    l2 = o2["agv_q_values"].pow(2).mean() + 0.5 * o2["picker_q_values"].pow(2).mean() + 0.1 * o2["location_embeddings"].pow(2).mean()
+    l2.backward()
+    assert abs(float(loss) - float(l2)) <= 1e-4 * abs(float(l2))
+    rp = dict(ref.named_parameters())
+    worst = 0.0
+    for name, p in m.named_parameters():
+        q = rp[name]
+        if q.grad is None:
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, name
+            continue
+        assert p.grad is not None, name
+        e = rel_l2(p.grad, q.grad)
+        worst = max(worst, e)
+        assert e <= FIXED_TOL, (name, e)
+    print(f"hetero {tag}: worst parameter-gradient rel-L2 {worst:.2e}")
 
 
 @pytest.mark.gpu
