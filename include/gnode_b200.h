@@ -324,6 +324,21 @@ int gnode_mlp_integrate_dopri5(const gnode_mlp_params* p, const float* y0, int64
                                int64_t max_num_steps, void* workspace, size_t workspace_bytes,
                                gnode_stream_t stream);
 
+/* Whole-episode graph construction on the device: all T window graphs of one episode as their disjoint
+ * union -- one GraphConverter applied step by step (scripts/train_gde.py:116-184 via :308-314) followed by
+ * Batch.from_data_list (:367), bit for bit.  obs: device f32 [n_steps, n_agents, node_dim] (rows < num_agvs are AGVs:
+ * position columns (3, 4), pickers (0, 1)).  Outputs (device): x [nodes, node_dim]; edge_index int64 [2, edge_capacity]
+ * (row 0 = sources, row 1 = targets; the first edge_offsets[n_steps] columns are valid); batch int64 [nodes];
+ * is_current_agent uint8/bool [nodes]; ptr int64 [n_steps + 1]; edge_offsets int64 [n_steps + 1] (first edge of every
+ * graph).  nodes = gnode_window_graphs_nodes(...), edge_capacity >= gnode_window_graphs_edge_capacity(...). */
+int64_t gnode_window_graphs_nodes(int64_t n_steps, int32_t n_agents, int32_t window);
+int64_t gnode_window_graphs_edge_capacity(int64_t n_steps, int32_t n_agents, int32_t window);
+size_t gnode_window_graphs_workspace_bytes(int64_t n_steps, int32_t n_agents);
+int gnode_window_graphs(const float* obs, int64_t n_steps, int32_t n_agents, int32_t node_dim, int32_t num_agvs,
+                        float threshold, int32_t window, float* x, int64_t* edge_index, int64_t edge_capacity,
+                        int64_t* batch, uint8_t* is_current_agent, int64_t* ptr, int64_t* edge_offsets,
+                        void* workspace, size_t workspace_bytes, gnode_stream_t stream);
+
 /* Backward of the bipartite SAGEConv relation of HeteroConv (scripts/gnode.py:92-99,126-128) and of the Linear
  * embeddings / action heads (:84-90,104-115): what loss.backward() runs when the Q-network is trained.
  *   gs = scale * grad_out * [out > 0]  (mask only when `out` is given: the ReLU folded into the last relation)

@@ -207,6 +207,42 @@ def spatial_edges_cuda(pos: torch.Tensor, threshold: float):
     return counts, edges
 
 
+def build_episode_batch(observations: torch.Tensor, num_agvs: int, num_pickers: int, distance_threshold: float = 3.0,
+                        temporal_window: int = 5) -> "Batch":
+    """All window graphs of ONE episode, built on the GPU, as the ``Batch`` the reference gets from a fresh
+    ``GraphConverter`` fed step by step (scripts/train_gde.py:308-314) and ``Batch.from_data_list`` (:367) -- bit for bit.
+
+    observations: CUDA float32 ``[n_steps, num_agvs + num_pickers, D]`` (zero-padded rows, as collect_data.py writes them).
+    The O(n^2) Python pair loop per step and the per-batch host collation disappear; one small device->host read (the
+    total edge count) sizes the returned ``edge_index``."""
+    obs = _lib.require_cuda_f32(observations, "observations")
+    if obs.dim() != 3 or obs.shape[1] != num_agvs + num_pickers:
+        raise _lib.GnodeError(f"observations must be [n_steps, {num_agvs + num_pickers}, D] (got {list(obs.shape)})")
+    T, n, D = obs.shape
+    dev = obs.device
+    L = _lib.lib()
+    N = int(L.gnode_window_graphs_nodes(T, n, temporal_window))
+    cap = int(L.gnode_window_graphs_edge_capacity(T, n, temporal_window))
+    x = torch.empty((N, D), dtype=torch.float32, device=dev)
+    ei = torch.empty((2, cap), dtype=torch.int64, device=dev)
+    batch = torch.empty(N, dtype=torch.int64, device=dev)
+    cur = torch.empty(N, dtype=torch.bool, device=dev)
+    ptr = torch.empty(T + 1, dtype=torch.int64, device=dev)
+    eoff = torch.empty(T + 1, dtype=torch.int64, device=dev)
+    ws = _lib.WORKSPACE.get(L.gnode_window_graphs_workspace_bytes(T, n), dev)
+    with torch.cuda.device(dev):
+        _lib.check(L.gnode_window_graphs(_lib.ptr(obs), T, n, D, int(num_agvs), float(distance_threshold), int(temporal_window),
+                                         _lib.ptr(x), _lib.ptr(ei), cap, _lib.ptr(batch), _lib.ptr(cur), _lib.ptr(ptr),
+                                         _lib.ptr(eoff), _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev)), "gnode_window_graphs")
+    E = int(eoff[-1])
+    out = Batch(x=x, edge_index=ei[:, :E].contiguous(), is_current_agent=cur)
+    out.batch, out.ptr = batch, ptr
+    out.num_graphs = T
+    out.max_graph_nodes = min(T, temporal_window) * n
+    out.edge_ptr = eoff
+    return out
+
+
 # ----------------------------------------------------------------------------------------------
 # Batching (scripts/train_gde.py:273-276, 336-375)
 # ----------------------------------------------------------------------------------------------

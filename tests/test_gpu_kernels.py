@@ -181,3 +181,22 @@ def test_time_grid_cache_survives_address_reuse(cuda):
         seen.append(ops.time_grid_to_host(t))
         del t
     assert seen == [(0.0, float(torch.tensor(0.1 * (k + 1), dtype=torch.float32)), 1.0 + k) for k in range(20)]
+
+
+@pytest.mark.parametrize("T,n_agv,n_pick,thr,W", [(1, 3, 2, 3.0, 5), (3, 12, 7, 5.0, 5), (23, 12, 7, 5.0, 5), (40, 19, 9, 3.0, 5),
+                                                    (12, 4, 0, 100.0, 3), (9, 1, 0, 5.0, 5), (17, 6, 5, 0.5, 1)])
+def test_build_episode_batch_equals_sequential_graph_converter(cuda, T, n_agv, n_pick, thr, W):
+    """all window graphs of an episode built on the device == GraphConverter step by step (scripts/
+    train_gde.py:116-184, itself golden-checked against the reference's code) + Batch.from_data_list, bit for bit."""
+    g = torch.Generator().manual_seed(T * 131 + n_agv)
+    n, D = n_agv + n_pick, 11
+    obs = torch.randn(T, n, D, generator=g)
+    obs[:, :, :5] = torch.randint(0, 12, (T, n, 5), generator=g).float()       # integer grid coordinates, many ties
+    conv = S.GraphConverter(n_agv, n_pick, distance_threshold=thr, temporal_window=W)
+    want = S.Batch.from_data_list([conv._build_graph_from_observation(obs[t].numpy()) for t in range(T)])
+    got = S.build_episode_batch(obs.to(cuda), n_agv, n_pick, distance_threshold=thr, temporal_window=W)
+    assert torch.equal(got.x.cpu(), want.x)
+    assert got.edge_index.dtype == torch.int64 and torch.equal(got.edge_index.cpu(), want.edge_index)
+    assert torch.equal(got.batch.cpu(), want.batch) and torch.equal(got.ptr.cpu(), want.ptr)
+    assert torch.equal(got.is_current_agent.cpu(), want.is_current_agent)
+    assert got.num_graphs == want.num_graphs and got.max_graph_nodes == want.max_graph_nodes
