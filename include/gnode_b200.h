@@ -324,6 +324,15 @@ int gnode_mlp_integrate_dopri5(const gnode_mlp_params* p, const float* y0, int64
                                int64_t max_num_steps, void* workspace, size_t workspace_bytes,
                                gnode_stream_t stream);
 
+/* The D-wide projections of the folded integrator on their own (parity tests of the engine, csrc/gemm_k128.cu):
+ *   C[m, n] = base_scale * base + base2 + scale * (A[m, :128] . B[n, :128] + bias_scale * bias[n])
+ * A: [m, 128] dense rows (16-byte aligned); B: [n, 128]; C / base / base2: row strides ldc / ldbase / ldbase2, any
+ * alignment; bias, base, base2 may be NULL (base2 needs base). */
+size_t gnode_gemm_k128_workspace_bytes(int32_t n);
+int gnode_gemm_k128(const float* A, const float* B, float* C, int64_t ldc, int64_t m, int32_t n, const float* bias,
+                    float bias_scale, const float* base, int64_t ldbase, float base_scale, const float* base2,
+                    int64_t ldbase2, float scale, void* workspace, size_t workspace_bytes, gnode_stream_t stream);
+
 /* Whole-episode graph construction on the device: all T window graphs of one episode as their disjoint
  * union -- one GraphConverter applied step by step (scripts/train_gde.py:116-184 via :308-314) followed by
  * Batch.from_data_list (:367), bit for bit.  obs: device f32 [n_steps, n_agents, node_dim] (rows < num_agvs are AGVs:

@@ -124,6 +124,9 @@ _SIGNATURES = {
     "gnode_mlp_integrate_dopri5": (C.c_int, [C.POINTER(GnodeMlpParams), _P, C.c_int64, C.POINTER(C.c_double),
                                              C.c_int32, C.c_double, C.c_double, _P, C.POINTER(GnodeDopri5Stats),
                                              C.POINTER(GnodeDopri5Trace), C.c_int64, _P, C.c_size_t, _P]),
+    "gnode_gemm_k128_workspace_bytes": (C.c_size_t, [C.c_int32]),
+    "gnode_gemm_k128": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int64, C.c_int32, _P, C.c_float, _P, C.c_int64, C.c_float, _P,
+                                  C.c_int64, C.c_float, _P, C.c_size_t, _P]),
     "gnode_window_graphs_nodes": (C.c_int64, [C.c_int64, C.c_int32, C.c_int32]),
     "gnode_window_graphs_edge_capacity": (C.c_int64, [C.c_int64, C.c_int32, C.c_int32]),
     "gnode_window_graphs_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int32]),

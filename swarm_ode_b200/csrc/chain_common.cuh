@@ -141,7 +141,7 @@ __device__ __forceinline__ uint32_t residual_pair(float x, float y) {
 // its row = 32 k values = 16 TMEM columns starting at ALO_COL + 2 (c_first - c_base).
 // Rows >= tr do not exist in the tile: zeros (warp-uniform skip when the whole quadrant is out of range).
 __device__ __forceinline__ void residual_to_tmem(const uint8_t* tile, int lbo_t, int tr, uint32_t tmem_base, int eq, int lane,
-                                                 int c_first, int c_base) {
+                                                 int c_first, int c_base, int alo_col = ALO_COL) {
   if (32 * eq >= tr) return;
   const int row = 32 * eq + lane;
   uint32_t p[16];
@@ -152,7 +152,7 @@ __device__ __forceinline__ void residual_to_tmem(const uint8_t* tile, int lbo_t,
     p[2 * i] = residual_pair(x.x, x.y);
     p[2 * i + 1] = residual_pair(x.z, x.w);
   }
-  tmem_st16(tmem_base + ((uint32_t)(32 * eq) << 16) + (uint32_t)(ALO_COL + 2 * (c_first - c_base)), p);
+  tmem_st16(tmem_base + ((uint32_t)(32 * eq) << 16) + (uint32_t)(alo_col + 2 * (c_first - c_base)), p);
 }
 
 }  // namespace chain

@@ -111,12 +111,16 @@ struct GemmNT {
   const float* base2 = nullptr; int64_t ldbase2 = 0;
   int post_relu = 0;               // ReLU applied to the final value (after the base terms)
   const float* Bsplit = nullptr;   // optional: B pre-split into tf32 hi/lo planes (presplit_weights) -> tcgen05 engine
+  const float* Bchain = nullptr;   // optional: chunked chain-format image of B (gemm_k128_pack) -> K = 128 wide-output engine
 };
 int gemm_nt(const GemmNT& g, cudaStream_t s);
 // tf32 hi/lo planes of a row-major weight matrix, zero padded to multiples of 16 (gemm_tc.cu)
 size_t presplit_floats(int rows, int cols);
 int presplit_weights(const float* W, int rows, int cols, int64_t ld, float* planes, cudaStream_t s);
 int gemm_tc_status(cudaStream_t s, int* out);
+// K = 128, wide unaligned output (gemm_k128.cu): chunked weight image of a row-major [n x 128] matrix
+size_t gemm_k128_image_floats(int n);
+int gemm_k128_pack(const float* W, int n, int64_t ld, float* img, cudaStream_t s);
 
 // C[p, q] (+)= scale * sum_n A[n, p] * B[n, q]        (reduction over rows, "TN": weight gradients)
 // Deterministic: split over row chunks into `partials` (workspace), reduced in fixed order.

@@ -49,6 +49,7 @@ struct Sage3Ctx : Field {
   // tf32 hi/lo planes of the six packed matrices for the tcgen05 engine (null -> FFMA engine)
   float *s1 = nullptr, *s2 = nullptr, *s3 = nullptr, *s1T = nullptr, *s2T = nullptr, *s3T = nullptr;
   float *ci2 = nullptr, *ci2T = nullptr;   // chain-kernel images (chain_common.cuh) of w2cat [H x 2H] and w2catT [2H x H]
+  float *ck3 = nullptr, *ck1T = nullptr;   // chunked images (gemm_k128.cu) of w3cat [D x 2H] and w1catT [D x 2H]
   bool use_tc = false;
   float* z = nullptr;                  // [N, 2H]  x @ w1cat^T
   int n_slots = 1;

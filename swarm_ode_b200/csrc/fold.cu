@@ -275,7 +275,7 @@ int integrate_fixed_folded(Sage3Ctx& c, FoldWs& f, const Tableau& tb, const floa
     GemmNT q{};   // y_1 = y + C @ w3cat^T + (dt sum c) b3
     q.A = f.Cslot; q.lda = H2; q.B = c.w3cat; q.ldb = H2; q.C = y1; q.ldc = c.D; q.M = c.N; q.N = c.D; q.K = H2;
     q.bias = c.b3; q.bias_scale = (float)csum * dt; q.base = y; q.ldbase = c.D;
-    q.Bsplit = c.use_tc ? c.s3 : nullptr;
+    q.Bsplit = c.use_tc ? c.s3 : nullptr; q.Bchain = c.use_tc ? c.ck3 : nullptr;
     GN_TRY(gemm_nt(q, s));
   }
   return GNODE_OK;
@@ -439,7 +439,7 @@ int integrate_fixed_folded_bwd(Sage3Ctx& c, FoldWs& f, const Tableau& tb, const 
       GemmNT q{};
       q.A = f.GZ; q.lda = H2; q.B = c.w1catT; q.ldb = H2; q.C = gout; q.ldc = c.D; q.M = N; q.N = c.D; q.K = H2;
       q.base = G; q.ldbase = c.D; q.base2 = grad_sol + (int64_t)j * n; q.ldbase2 = c.D;
-      q.Bsplit = c.use_tc ? c.s1T : nullptr;
+      q.Bsplit = c.use_tc ? c.s1T : nullptr; q.Bchain = c.use_tc ? c.ck1T : nullptr;
       GN_TRY(gemm_nt(q, s));
     }
     G = gout;
@@ -501,7 +501,7 @@ int integrate_dopri5_folded_bwd(Sage3Ctx& c, FoldWs& f, const float* y0, const d
     GemmNT q{};   // y_{k+1} = y_k + C @ w3cat^T + (dt sum c) b3
     q.A = f.Cslot; q.lda = H2; q.B = c.w3cat; q.ldb = H2; q.C = ys + (int64_t)(k + 1) * n; q.ldc = c.D; q.M = N; q.N = c.D; q.K = H2;
     q.bias = c.b3; q.bias_scale = (float)csum * dt; q.base = y; q.ldbase = c.D;
-    q.Bsplit = c.use_tc ? c.s3 : nullptr;
+    q.Bsplit = c.use_tc ? c.s3 : nullptr; q.Bchain = c.use_tc ? c.ck3 : nullptr;
     GN_TRY(gemm_nt(q, s));
   }
 
@@ -542,7 +542,7 @@ int integrate_dopri5_folded_bwd(Sage3Ctx& c, FoldWs& f, const float* y0, const d
         g.A = f.GZ; g.lda = H2; g.B = c.w1catT; g.ldb = H2; g.C = gout; g.ldc = c.D; g.M = N; g.N = c.D; g.K = H2;
         g.base = G; g.ldbase = c.D;
         if (!first) { g.base2 = gout; g.ldbase2 = c.D; }
-        g.Bsplit = c.use_tc ? c.s1T : nullptr;
+        g.Bsplit = c.use_tc ? c.s1T : nullptr; g.Bchain = c.use_tc ? c.ck1T : nullptr;
         GN_TRY(gemm_nt(g, s));
       }
       first = false;

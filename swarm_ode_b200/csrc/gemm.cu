@@ -1,4 +1,6 @@
 // Engine dispatch for the dense contractions: tcgen05 (3xTF32, gemm_tc.cu) or fp32 FFMA (gemm_simt.cu).
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace gnode {
@@ -6,12 +8,21 @@ int gemm_nt_simt(const GemmNT& g, cudaStream_t s);
 bool gemm_nt_tc_supported(const GemmNT& g);
 int gemm_nt_tc(const GemmNT& g, cudaStream_t s);
 
+bool gemm_k128_supported(const GemmNT& g);
+int gemm_k128(const GemmNT& g, cudaStream_t s);
+
 int gemm_nt(const GemmNT& g, cudaStream_t s) {
   const int engine = current_engine();
+  // The wide-output engine (gemm_k128.cu) measures the same as the general one on the D = 399 projections (both are bound by
+  // the DRAM locality of 160-byte row pieces at a 1596-byte pitch); it is opt-in (GNODE_WIDE_ENGINE=1) so
+  // that the default arithmetic stays the one the dopri5 step-count tests were recorded with.
+  static const bool wide_on = [] { const char* e = std::getenv("GNODE_WIDE_ENGINE"); return e && e[0] == '1'; }();
+  const bool wide = wide_on && engine != GNODE_ENGINE_SIMT && gemm_k128_supported(g);
   const bool tc = engine != GNODE_ENGINE_SIMT && gemm_nt_tc_supported(g);
   GN_PROF(s, 2.0 * g.M * g.N * g.K, 4.0 * ((double)g.M * g.K + (double)g.N * g.K + (double)g.M * g.N * (g.base ? 2 : 1)),
-          "gemm_nt[%s] N=%d K=%d", tc ? "tcgen05" : "ffma", g.N, g.K);
+          "gemm_nt[%s] N=%d K=%d", wide ? "k128" : (tc ? "tcgen05" : "ffma"), g.N, g.K);
   if (engine == GNODE_ENGINE_SIMT) return gemm_nt_simt(g, s);
+  if (wide) return gemm_k128(g, s);
   if (gemm_nt_tc_supported(g)) return gemm_nt_tc(g, s);
   if (engine == GNODE_ENGINE_TC) {
     set_error("gemm_nt: shape M=%lld N=%d K=%d not supported by the tcgen05 engine", (long long)g.M, g.N, g.K);
@@ -86,4 +97,24 @@ extern "C" int gnode_gemm_tn(const float* A, int64_t lda, const float* B, int64_
   GemmTN g{};
   g.A = A; g.lda = lda; g.P = p; g.B = B; g.ldb = ldb; g.Q = q; g.Nrows = rows; g.C = C; g.ldc = ldc; g.scale = scale;
   return gemm_tn(g, partials, s);
+}
+
+// The K = 128 wide-output engine on its own (gemm_k128.cu; parity tests).  B: row-major [n, 128].
+extern "C" size_t gnode_gemm_k128_workspace_bytes(int32_t n) { return align_up(gemm_k128_image_floats(n) * sizeof(float)); }
+
+extern "C" int gnode_gemm_k128(const float* A, const float* B, float* C, int64_t ldc, int64_t m, int32_t n, const float* bias,
+                               float bias_scale, const float* base, int64_t ldbase, float base_scale, const float* base2,
+                               int64_t ldbase2, float scale, void* workspace, size_t workspace_bytes, gnode_stream_t stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  GN_ARG(A && B && C && m > 0 && n >= 16, "gnode_gemm_k128: bad argument");
+  Arena a(workspace, workspace_bytes);
+  float* img = a.take<float>(gemm_k128_image_floats(n));
+  GN_ARENA_OK(a, "gnode_gemm_k128");
+  GN_TRY(gemm_k128_pack(B, n, 128, img, s));
+  GemmNT q{};
+  q.A = A; q.lda = 128; q.B = B; q.ldb = 128; q.C = C; q.ldc = ldc; q.M = m; q.N = n; q.K = 128;
+  q.bias = bias; q.bias_scale = bias_scale; q.base = base; q.ldbase = ldbase; q.base_scale = base_scale;
+  q.base2 = base2; q.ldbase2 = ldbase2; q.scale = scale; q.Bchain = img;
+  GN_ARG(gemm_k128_supported(q), "gnode_gemm_k128: operand A must be 16-byte aligned");
+  return gemm_k128(q, s);
 }

@@ -21,6 +21,7 @@ void Sage3Ctx::carve(Arena& a, int slots, bool backward) {
   s2 = a.take<float>(presplit_floats(H, 2 * H));
   s3 = a.take<float>(presplit_floats(D, 2 * H));
   if (chain_shape_ok(H)) ci2 = a.take<float>(chain_image_floats(H, 2 * H));
+  if (chain_shape_ok(H)) ck3 = a.take<float>(gemm_k128_image_floats(D));
   z = a.take<float>(n * 2 * H);
   for (int i = 0; i < slots; ++i) cat1[i] = a.take<float>(n * 2 * H);   // two stacks (stage-major): the backward pass
   for (int i = 0; i < slots; ++i) cat2[i] = a.take<float>(n * 2 * H);   // contracts over all stages at once
@@ -32,6 +33,7 @@ void Sage3Ctx::carve(Arena& a, int slots, bool backward) {
     s2T = a.take<float>(presplit_floats(2 * H, H));
     s3T = a.take<float>(presplit_floats(2 * H, D));
     if (chain_shape_ok(H)) ci2T = a.take<float>(chain_image_floats(2 * H, H));
+    if (chain_shape_ok(H)) ck1T = a.take<float>(gemm_k128_image_floats(D));
     gcat = a.take<float>(n * 2 * H);
     gz = a.take<float>(n * 2 * H);
     gv2 = a.take<float>(n * H);
@@ -80,7 +82,11 @@ int Sage3Ctx::pack(const gnode_sage3_params& p, bool backward, cudaStream_t s) {
     GN_TRY(presplit_weights(w3cat, D, 2 * H, 2 * H, s3, s));
     if (chain_shape_ok(H)) {
       GN_TRY(chain_pack_image(w2cat, H, 2 * H, 2 * H, ci2, s));
-      if (backward) GN_TRY(chain_pack_image(w2catT, 2 * H, H, H, ci2T, s));
+      GN_TRY(gemm_k128_pack(w3cat, D, 2 * H, ck3, s));
+      if (backward) {
+        GN_TRY(chain_pack_image(w2catT, 2 * H, H, H, ci2T, s));
+        GN_TRY(gemm_k128_pack(w1catT, D, 2 * H, ck1T, s));
+      }
     }
     if (backward) {
       GN_TRY(presplit_weights(w1catT, D, 2 * H, 2 * H, s1T, s));
@@ -146,7 +152,7 @@ int Sage3Ctx::eval(const float* x, float* out, const float* base, float scale, i
     GemmNT q{};
     q.A = c2; q.lda = H2; q.B = w3cat; q.ldb = H2; q.C = out; q.ldc = D; q.M = N; q.N = D; q.K = H2;
     q.bias = b3; q.base = base; q.ldbase = D; q.scale = scale;
-    q.Bsplit = use_tc ? s3 : nullptr;
+    q.Bsplit = use_tc ? s3 : nullptr; q.Bchain = use_tc ? ck3 : nullptr;
     GN_TRY(gemm_nt(q, s));
   }
   return GNODE_OK;
@@ -191,7 +197,7 @@ int Sage3Ctx::vjp(const float* x, int slot, const float* gk, float* gx, cudaStre
   {  // gx = gz @ w1cat            [N, D]
     GemmNT q{};
     q.A = gz; q.lda = H2; q.B = w1catT; q.ldb = H2; q.C = gx; q.ldc = D; q.M = N; q.N = D; q.K = H2;
-    q.Bsplit = use_tc ? s1T : nullptr;
+    q.Bsplit = use_tc ? s1T : nullptr; q.Bchain = use_tc ? ck1T : nullptr;
     GN_TRY(gemm_nt(q, s));
   }
   {  // dW1cat += gz^T @ x         [2H, D]

@@ -715,3 +715,24 @@ def gemm_tn(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None
         _lib.check(L.gnode_gemm_tn(_lib.ptr(a), p, _lib.ptr(b), q, _lib.ptr(out), out.stride(0), rows, p, q, float(scale),
                                    _lib.ptr(ws), ws.numel(), _lib.stream_ptr(a.device)), "gnode_gemm_tn")
     return out
+
+
+def gemm_k128(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, bias_scale: float = 1.0,
+              base: Optional[torch.Tensor] = None, base_scale: float = 1.0, base2: Optional[torch.Tensor] = None,
+              scale: float = 1.0) -> torch.Tensor:
+    """``base_scale * base + base2 + scale * (a @ w.T + bias_scale * bias)`` for a 128-wide reduction on the wide-output
+    tcgen05 engine (csrc/gemm_k128.cu); no autograd.  Test surface of the D-wide projections of the integrator."""
+    a, w = _f32(a.detach(), "a"), _f32(w.detach(), "w")
+    m, k = a.shape
+    n = w.shape[0]
+    if k != 128 or w.shape[1] != 128:
+        raise GnodeError("gemm_k128: the reduction width must be 128")
+    out = torch.empty((m, n), dtype=torch.float32, device=a.device)
+    L = _lib.lib()
+    ws = _ws(L.gnode_gemm_k128_workspace_bytes(n), a.device)
+    opt = [None if t is None else _f32(t.detach(), "operand") for t in (bias, base, base2)]
+    with torch.cuda.device(a.device):
+        _lib.check(L.gnode_gemm_k128(_lib.ptr(a), _lib.ptr(w), _lib.ptr(out), n, m, n, _lib.ptr(opt[0]), float(bias_scale),
+                                     _lib.ptr(opt[1]), n, float(base_scale), _lib.ptr(opt[2]), n, float(scale), _lib.ptr(ws),
+                                     ws.numel(), _lib.stream_ptr(a.device)), "gnode_gemm_k128")
+    return out

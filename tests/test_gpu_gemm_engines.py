@@ -100,3 +100,31 @@ def test_gemm_tn_deterministic(cuda):
     outs = [S.ops.gemm_tn(a, b) for _ in range(3)]
     _lib.tc_check(cuda)
     assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+
+
+@pytest.mark.parametrize("m,n", [(1, 16), (125, 343), (128, 399), (129, 80), (1000, 81), (3000, 400), (257, 435), (40000, 399)])
+@pytest.mark.parametrize("terms", ["plain", "bias+base", "all"])
+def test_k128_wide_output_engine(cuda, m, n, terms):
+    """csrc/gemm_k128.cu: C = base_scale * base + base2 + scale * (A @ W^T + bias_scale * bias), K = 128, any N >= 16, any
+    row count, rows of C / base only 4-byte aligned -- against float64, fp32-grade accuracy (three-term tensor-core product)."""
+    g = torch.Generator().manual_seed(m * 7 + n)
+    # poison the device heap first: the engine must not depend on fresh (zero) memory
+    junk = torch.full((8 << 20,), float("nan"), device=cuda)
+    del junk
+    a = torch.randn(m, 128, generator=g) * 3.0
+    w = torch.randn(n, 128, generator=g) * 0.3
+    bias = torch.randn(n, generator=g) if terms != "plain" else None
+    base = torch.randn(m, n, generator=g) * 5.0 if terms != "plain" else None
+    base2 = torch.randn(m, n, generator=g) if terms == "all" else None
+    scale, bs, bsc = (0.37, 1.7, 0.5) if terms == "all" else (1.0, 1.0, 1.0)
+    want = scale * (a.double() @ w.double().T + (bs * bias.double() if bias is not None else 0.0))
+    if base is not None:
+        want = want + bsc * base.double()
+    if base2 is not None:
+        want = want + base2.double()
+    dev = lambda t: None if t is None else t.to(cuda)
+    got = S.ops.gemm_k128(dev(a), dev(w), bias=dev(bias), bias_scale=bs, base=dev(base), base_scale=bsc, base2=dev(base2), scale=scale)
+    assert torch.isfinite(got).all()
+    assert rel_l2(got, want) <= 5e-6, rel_l2(got, want)
+    from swarm_ode_b200 import _lib
+    _lib.tc_check(cuda)
