@@ -99,17 +99,22 @@ typedef struct {
   const int32_t* col;      /* device [n_edges]    source node ids                                 */
   const int32_t* t_rowptr; /* device [n_nodes+1]  out-edges of node j                             */
   const int32_t* t_col;    /* device [n_edges]    destination node ids                            */
-  /* optional (NULL = absent): tiling of the rows into runs of WHOLE graphs of at most 128 rows, from
-   * gnode_tiles_build; lets the integrators run their per-stage chain graph-resident (csrc/chain_fwd.cu).
-   * tile_err: device int32 set to 1 if an edge is found to leave its tile (the batch was not a disjoint union). */
+  /* optional (NULL = absent): tiling of the rows into runs of WHOLE graphs of at most tile_rows rows, from
+   * gnode_tiles_build[_rows]; lets the integrators run their per-stage chain graph-resident (csrc/chain_fwd.cu,
+   * chain_bwd.cu).  tile_err: device int32 set to 1 if an edge is found to leave its tile (the batch was not a
+   * disjoint union).  tile_rows: the row limit the tiles were built with (0 = 128; 129 .. 256 for batches whose
+   * graphs have up to 256 nodes). */
   const int32_t* tiles;
   int32_t* tile_err;
+  int32_t tile_rows;
 } gnode_graph;
 
 /* tiles: device int32 [n_graphs + 2]; graph_ptr: device int64 [n_graphs + 1] node offsets of the graphs of a batch
  * (PyG `Batch.ptr`).  tiles[0] = number of tiles (-1 if a graph has more than 128 nodes), tiles[1 + t] = first row of
  * tile t.  Does not synchronise. */
-int gnode_tiles_build(const int64_t* graph_ptr, int64_t n_graphs, int32_t* tiles, gnode_stream_t stream);
+int gnode_tiles_build(const int64_t* graph_ptr, int64_t n_graphs, int32_t* tiles, gnode_stream_t stream);   /* 128 rows */
+int gnode_tiles_build_rows(const int64_t* graph_ptr, int64_t n_graphs, int32_t max_rows, int32_t* tiles,
+                           gnode_stream_t stream);
 
 size_t gnode_csr_workspace_bytes(int64_t n_nodes, int64_t n_edges);
 /* edge_index: device int64 [2, n_edges] (row 0 = source j, row 1 = destination i), any order,

@@ -23,7 +23,8 @@ METHODS = {"euler": GNODE_EULER, "midpoint": GNODE_MIDPOINT, "rk4": GNODE_RK4_38
 
 class GnodeGraph(C.Structure):
     _fields_ = [("n_nodes", C.c_int64), ("n_edges", C.c_int64), ("rowptr", C.c_void_p), ("col", C.c_void_p),
-                ("t_rowptr", C.c_void_p), ("t_col", C.c_void_p), ("tiles", C.c_void_p), ("tile_err", C.c_void_p)]
+                ("t_rowptr", C.c_void_p), ("t_col", C.c_void_p), ("tiles", C.c_void_p), ("tile_err", C.c_void_p),
+                ("tile_rows", C.c_int32)]
 
 
 class GnodeSage3Params(C.Structure):
@@ -76,6 +77,7 @@ _SIGNATURES = {
     "gnode_csr_build": (C.c_int, [_P, C.c_int64, C.c_int64, _P, _P, _P, _P, _P, C.c_size_t, _P]),
     "gnode_csr_build_async": (C.c_int, [_P, C.c_int64, C.c_int64, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
     "gnode_tiles_build": (C.c_int, [_P, C.c_int64, _P, _P]),
+    "gnode_tiles_build_rows": (C.c_int, [_P, C.c_int64, C.c_int32, _P, _P]),
     "gnode_gemm_nt_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
     "gnode_gemm_nt": (C.c_int, [_P, C.c_int64, _P, C.c_int64, _P, C.c_int64, C.c_int64, C.c_int32, C.c_int32, _P,
                                 C.c_int32, _P, C.c_int64, C.c_float, _P, C.c_size_t, _P]),

@@ -13,6 +13,8 @@
 // way out (operands of the weight-gradient contractions that follow: dW2cat += g_v2_s^T cat1_s, R += U_s^T cat2_s),
 // plus GZ = sum_s gz_s after the last stage.  Structure, tile layout and the three-term tensor-core product are those
 // of chain_fwd.cu (chain_common.cuh).
+#include <cstdlib>
+
 #include "chain_common.cuh"
 #include "field.cuh"
 
@@ -414,7 +416,9 @@ extern "C" int gnode_chain_trace_b(long long* out128) {
 #endif
 
 bool chain_bwd_supported(const Sage3Ctx& c, const FoldWs& f) {
-  return chain_fwd_supported(c) && c.ci2T != nullptr && f.ci13T != nullptr && f.Us[0] != nullptr && f.gv2s[0] != nullptr && f.mask[0] != nullptr &&
+  static const bool off = [] { const char* e = std::getenv("GNODE_NO_CHAIN_BWD"); return e && e[0] == '1'; }();
+  if (off) return false;
+  return chain_fwd_supported(c) && (c.g.tile_rows <= chain::TM) && c.ci2T != nullptr && f.ci13T != nullptr && f.Us[0] != nullptr && f.gv2s[0] != nullptr && f.mask[0] != nullptr &&
          c.g.t_rowptr != nullptr && c.g.t_col != nullptr;
 }
 

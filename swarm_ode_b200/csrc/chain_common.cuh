@@ -42,10 +42,15 @@ __host__ __device__ constexpr int stage_bytes(int n) { return 10 * lbo_b(n); }  
 constexpr int B_STAGE = stage_bytes(W2H);     // 20640: ring slot (the N = 64 image uses half of it)
 constexpr int MAX_SLOTS = 4;
 constexpr int SMEM_BYTES = t_bytes_of(96) + 3 * B_STAGE;   // 111584: two CTAs per SM; 2 slots for 128-row tiles, 3 for <= 96 rows
+// Tiles of more than 128 rows (graphs of 129 .. 256 nodes) are processed as two 128-row blocks: up to TR_MID rows still
+// leave room for one ring slot next to a second CTA; beyond that one CTA per SM with the full tile and two slots.
+constexpr int TR_MID = 144, TR_BIG = 256;
+constexpr int SMEM_BYTES_BIG = t_bytes_of(TR_BIG) + 2 * B_STAGE;   // 172864
+__host__ __device__ constexpr int smem_bytes_of(int tr) { return tr <= TR_MID ? SMEM_BYTES : SMEM_BYTES_BIG; }
 __host__ __device__ constexpr int ring_slots(int tr) {
-  return (SMEM_BYTES - t_bytes_of(tr)) / B_STAGE > MAX_SLOTS ? MAX_SLOTS : (SMEM_BYTES - t_bytes_of(tr)) / B_STAGE;
+  return (smem_bytes_of(tr) - t_bytes_of(tr)) / B_STAGE > MAX_SLOTS ? MAX_SLOTS : (smem_bytes_of(tr) - t_bytes_of(tr)) / B_STAGE;
 }
-static_assert(ring_slots(128) >= 2, "ring too small");
+static_assert(ring_slots(128) >= 2 && ring_slots(TR_MID) >= 1 && ring_slots(TR_BIG) >= 2, "ring too small");
 
 inline size_t image_floats(int n, int k) { return (size_t)(k / KB16) * stage_bytes(n) / 4; }
 // img <- chain-format image of row-major W [n x k] (row stride ld); n % 8 == 0, k % 16 == 0
@@ -140,10 +145,11 @@ __device__ __forceinline__ uint32_t residual_pair(float x, float y) {
 // Residual operand of the tile -> tensor memory.  Thread (row = 32 eq + lane, part): chunks [c_first, c_first + 8) of
 // its row = 32 k values = 16 TMEM columns starting at ALO_COL + 2 (c_first - c_base).
 // Rows >= tr do not exist in the tile: zeros (warp-uniform skip when the whole quadrant is out of range).
+// row_off: first row of the 128-row block whose residual is taken (tiles of two blocks).
 __device__ __forceinline__ void residual_to_tmem(const uint8_t* tile, int lbo_t, int tr, uint32_t tmem_base, int eq, int lane,
-                                                 int c_first, int c_base, int alo_col = ALO_COL) {
-  if (32 * eq >= tr) return;
-  const int row = 32 * eq + lane;
+                                                 int c_first, int c_base, int alo_col = ALO_COL, int row_off = 0) {
+  if (row_off + 32 * eq >= tr) return;
+  const int row = row_off + 32 * eq + lane;
   uint32_t p[16];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {

@@ -46,11 +46,16 @@ struct Args {
   const int32_t *rowptr, *col;
   const int32_t* tiles;                 // [0] = number of tiles, [1 ..] = first row of every tile, then N
   int S;
+  int tile_rows;                        // most rows a tile may hold (gnode_graph.tile_rows): selects the kernel variant
   int* status;                          // barrier-timeout word shared with the other tcgen05 kernels
   int* err;                             // set to 1 when a neighbour lies outside its tile
 };
 
-template <int TR>
+// TR = rows kept per chunk of the tile; NB = 128-row blocks per tile (1: tiles of <= 128 rows; 2: tiles of <= 256 rows, e.g.
+// the 140-node graphs of 19 AGVs + 9 pickers).  With NB = 2 the two contractions of a stage run block after block through
+// the same accumulator / residual columns of tensor memory (the weight images are streamed once per block), every other
+// phase covers all rows of the tile.
+template <int TR, int NB>
 __device__ __forceinline__ void chain_fwd_body(const Args& a, uint8_t* smem, uint64_t* bar_b_full, uint64_t* bar_b_empty,
                                                uint64_t* bar_a_ready_p, uint64_t* bar_acc_full_p, uint32_t tmem_base,
                                                int* dead_flag_p) {
@@ -67,6 +72,7 @@ __device__ __forceinline__ void chain_fwd_body(const Args& a, uint8_t* smem, uin
   uint8_t* const T = smem;
   const uint32_t smem_base = smem_u32(smem);
   const int n_tiles = a.tiles[0];
+  auto blocks_of = [&](int t) { return (NB == 2 && a.tiles[2 + t] - a.tiles[1 + t] > TM) ? 2 : 1; };
 
   if (warp == 0) {
     // =========================== weight-image producer ===========================
@@ -74,16 +80,19 @@ __device__ __forceinline__ void chain_fwd_body(const Args& a, uint8_t* smem, uin
       uint32_t s = 0, ph = 0;
       bool first_lap = true;
       for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const int nblk = blocks_of(t);
         for (int st = 0; st < S; ++st) {
           for (int g = (st > 0 ? 0 : 1); g < 2; ++g) {           // g = 0: M13 (stage > 0 only), g = 1: w2cat
             const uint8_t* img = reinterpret_cast<const uint8_t*>(g == 0 ? a.img13 : a.img2);
             const uint32_t bytes = g == 0 ? stage_bytes(W2H) : stage_bytes(WH);
-            for (int kb = 0; kb < W2H / KB16; ++kb) {
-              if (!first_lap) wait_bar(smem_u32(&bar_b_empty[s]), ph ^ 1u, dead, status, 21);
-              const uint32_t bar = smem_u32(&bar_b_full[s]);
-              mbar_expect_tx(bar, bytes);
-              bulk_load_1d(smem_base + b_off + s * B_STAGE, img + (size_t)kb * bytes, bytes, bar);
-              if (++s == n_slots) { s = 0; ph ^= 1u; first_lap = false; }
+            for (int b = 0; b < nblk; ++b) {
+              for (int kb = 0; kb < W2H / KB16; ++kb) {
+                if (!first_lap) wait_bar(smem_u32(&bar_b_empty[s]), ph ^ 1u, dead, status, 21);
+                const uint32_t bar = smem_u32(&bar_b_full[s]);
+                mbar_expect_tx(bar, bytes);
+                bulk_load_1d(smem_base + b_off + s * B_STAGE, img + (size_t)kb * bytes, bytes, bar);
+                if (++s == n_slots) { s = 0; ph ^= 1u; first_lap = false; }
+              }
             }
           }
         }
@@ -93,21 +102,25 @@ __device__ __forceinline__ void chain_fwd_body(const Args& a, uint8_t* smem, uin
     // =========================== MMA issuer ===========================
     uint32_t pa = 0, sb = 0, pb = 0;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+      const int nblk = blocks_of(t);
       for (int st = 0; st < S; ++st) {
         for (int g = (st > 0 ? 0 : 1); g < 2; ++g) {
           const int n = g == 0 ? W2H : WH;
-          wait_bar(smem_u32(&bar_a_ready), pa, dead, status, 23);   // tile + residual operand ready
-          pa ^= 1u;
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          for (int kb = 0; kb < W2H / KB16; ++kb) {
-            wait_bar(smem_u32(&bar_b_full[sb]), pb, dead, status, 22);
-            if (lane == 0) {
-              issue_kblock(tmem_base + ACC_COL, tmem_base + ALO_COL, smem_base, (uint32_t)lbo_t, smem_base + b_off + sb * B_STAGE, n, kb, kb == 0);
-              umma_commit(smem_u32(&bar_b_empty[sb]));
-              if (kb == W2H / KB16 - 1) umma_commit(smem_u32(&bar_acc_full));
+          for (int b = 0; b < nblk; ++b) {
+            wait_bar(smem_u32(&bar_a_ready), pa, dead, status, 23);   // tile + residual operand of this block ready
+            pa ^= 1u;
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            for (int kb = 0; kb < W2H / KB16; ++kb) {
+              wait_bar(smem_u32(&bar_b_full[sb]), pb, dead, status, 22);
+              if (lane == 0) {
+                issue_kblock(tmem_base + ACC_COL, tmem_base + ALO_COL, smem_base + (uint32_t)(b * TM * 16), (uint32_t)lbo_t,
+                             smem_base + b_off + sb * B_STAGE, n, kb, kb == 0);
+                umma_commit(smem_u32(&bar_b_empty[sb]));
+                if (kb == W2H / KB16 - 1) umma_commit(smem_u32(&bar_acc_full));
+              }
+              __syncwarp();
+              if (++sb == n_slots) { sb = 0; pb ^= 1u; }
             }
-            __syncwarp();
-            if (++sb == n_slots) { sb = 0; pb ^= 1u; }
           }
         }
       }
@@ -119,15 +132,16 @@ __device__ __forceinline__ void chain_fwd_body(const Args& a, uint8_t* smem, uin
     uint32_t ph_acc = 0u;
     // TMEM mapping: lane quadrant of this warp, column half
     const int eq = warp & 3, ehf = cw >> 2;
-    const int erow = 32 * eq + lane;
-    // aggregation mapping: two threads per row, 32 of the 64 channels (8 chunks) each
-    const int arow = wt & (TM - 1), ach = (wt >> 7) * 8;
+    const int elane = 32 * eq + lane;              // row of a 128-row block this thread owns in the TMEM mapping
+    // aggregation mapping: two threads per row of a block, 32 of the 64 channels (8 chunks) each
+    const int alane = wt & (TM - 1), ach = (wt >> 7) * 8;
     auto Tp = [&](int chunk, int row) { return reinterpret_cast<float4*>(T + (size_t)chunk * lbo_t + row * 16); };
-    constexpr int n_slots_t = TR * NCHUNK;                // float4 slots of the tile (tile-linear mapping: idx -> row idx >> 5, chunk idx & 31)
-    // residual operand of the whole tile (K = 128) -> tensor memory, then hand the contraction to the MMA warp
-    auto hand_off = [&]() {
-      residual_to_tmem(T, lbo_t, TR, tmem_base, eq, lane, 16 * ehf, 0);
-      residual_to_tmem(T, lbo_t, TR, tmem_base, eq, lane, 16 * ehf + 8, 0);
+    constexpr int n_slots_t = TR * NCHUNK;         // float4 slots of the tile (tile-linear mapping: idx -> row idx >> 5, chunk idx & 31)
+    constexpr int SLOTS = TM * NCHUNK / WORKERS / 2;   // 8 slots per thread and half block
+    // residual operand of one block (K = 128) -> tensor memory, then hand the contraction to the MMA warp
+    auto hand_off = [&](int b) {
+      residual_to_tmem(T, lbo_t, TR, tmem_base, eq, lane, 16 * ehf, 0, ALO_COL, b * TM);
+      residual_to_tmem(T, lbo_t, TR, tmem_base, eq, lane, 16 * ehf + 8, 0, ALO_COL, b * TM);
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
@@ -136,11 +150,12 @@ __device__ __forceinline__ void chain_fwd_body(const Args& a, uint8_t* smem, uin
 
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
       const int r0 = a.tiles[1 + t];
-      const int nr = a.tiles[2 + t] - r0;                 // 1..128 rows, whole graphs
-      // CSR slice of this thread's row (aggregation phases); the first NBR_REG neighbour ids (tile-local) stay in
-      // registers for the three aggregations of every stage
+      const int nr = a.tiles[2 + t] - r0;                 // rows of the tile: whole graphs
+      const int nblk = (NB == 2 && nr > TM) ? 2 : 1;
+      // CSR slice of this thread's row of block 0 (aggregation phases); its first NBR_REG neighbour ids (tile-local) stay
+      // in registers for the three aggregations of every stage.  Rows of block 1 walk their slice in global memory.
       int nb_b = 0, nb_e = 0;
-      if (arow < nr) { nb_b = a.rowptr[r0 + arow]; nb_e = a.rowptr[r0 + arow + 1]; }
+      if (alane < nr) { nb_b = a.rowptr[r0 + alane]; nb_e = a.rowptr[r0 + alane + 1]; }
       const float inv_deg = 1.0f / (float)((nb_e - nb_b) > 1 ? (nb_e - nb_b) : 1);
       int nbr[NBR_REG];
 #pragma unroll
@@ -153,21 +168,28 @@ __device__ __forceinline__ void chain_fwd_body(const Args& a, uint8_t* smem, uin
         nbr[q] = v;
       }
 
-      // mean over the in-neighbours of chunks [c0, c0 + 8) of this thread's row
-      auto aggregate = [&](int c0, float4 (&acc)[8]) {
+      // mean over the in-neighbours of chunks [c0, c0 + 8) of row 128 b + alane
+      auto aggregate = [&](int b, int c0, float4 (&acc)[8]) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        int pb_ = nb_b + NBR_REG, pe_ = nb_e;
+        float w = inv_deg;
+        if (b == 0) {
 #pragma unroll
-        for (int q = 0; q < NBR_REG; ++q) {
-          if (nbr[q] >= 0) {
+          for (int q = 0; q < NBR_REG; ++q) {
+            if (nbr[q] >= 0) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float4 v = *Tp(c0 + i, nbr[q]);
-              acc[i].x += v.x; acc[i].y += v.y; acc[i].z += v.z; acc[i].w += v.w;
+              for (int i = 0; i < 8; ++i) {
+                const float4 v = *Tp(c0 + i, nbr[q]);
+                acc[i].x += v.x; acc[i].y += v.y; acc[i].z += v.z; acc[i].w += v.w;
+              }
             }
           }
+        } else {
+          pb_ = a.rowptr[r0 + TM + alane]; pe_ = a.rowptr[r0 + TM + alane + 1];
+          w = 1.0f / (float)((pe_ - pb_) > 1 ? (pe_ - pb_) : 1);
         }
-        for (int p = nb_b + NBR_REG; p < nb_e; ++p) {          // rows with more than NBR_REG neighbours
+        for (int p = pb_; p < pe_; ++p) {          // block 0: neighbours beyond NBR_REG; block 1: all of them
           const int nb = a.col[p] - r0;
           if (nb < 0 || nb >= nr) { *a.err = 1; continue; }
 #pragma unroll
@@ -177,7 +199,7 @@ __device__ __forceinline__ void chain_fwd_body(const Args& a, uint8_t* smem, uin
           }
         }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { acc[i].x *= inv_deg; acc[i].y *= inv_deg; acc[i].z *= inv_deg; acc[i].w *= inv_deg; }
+        for (int i = 0; i < 8; ++i) { acc[i].x *= w; acc[i].y *= w; acc[i].z *= w; acc[i].w *= w; }
       };
       // coalesced tile store: rows < nr of T -> dst[(r0 + r) * 2H + c]
       // (streaming = evict-first in L2: for outputs that this kernel does not read back)
@@ -192,179 +214,195 @@ __device__ __forceinline__ void chain_fwd_body(const Args& a, uint8_t* smem, uin
 
       for (int st = 0; st < S; ++st) {
         CT(16 * st + 0);
-        if (st + 1 < S && erow < nr) {   // Z_0 comes back in the epilogue of the next stage: keep its lines in L2
-          const float* zl = a.z0 + (size_t)(r0 + erow) * W2H + 64 * ehf;
-          prefetch_l2(zl); prefetch_l2(zl + 32);
+        if (st + 1 < S) {   // Z_0 comes back in the epilogue of the next stage: keep its lines in L2
+          for (int b = 0; b < nblk; ++b) {
+            if (b * TM + elane < nr) {
+              const float* zl = a.z0 + (size_t)(r0 + b * TM + elane) * W2H + 64 * ehf;
+              prefetch_l2(zl); prefetch_l2(zl + 32);
+            }
+          }
         }
         // ---- tile input: Z_0 (stage 0) or V_st = sum_j coef * cat2_j, in place (cat2_{st-1} is still on chip) ----
-        {
-          constexpr int SLOTS = TM * NCHUNK / WORKERS / 2;   // 8 per half
-          for (int hf = 0; hf < 2; ++hf) {
-            const int ibase = wt + hf * SLOTS * WORKERS;
-            float4 acc[SLOTS];
-            if (st == 0) {
-#pragma unroll
-              for (int u = 0; u < SLOTS; ++u) {
-                const int idx = ibase + u * WORKERS, r = idx >> 5, c4 = idx & 31;
-                acc[u] = (r < nr) ? __ldg(reinterpret_cast<const float4*>(a.z0 + (size_t)(r0 + r) * W2H + 4 * c4))
-                                  : make_float4(0.f, 0.f, 0.f, 0.f);
-              }
-            } else {
-              const float cl = a.coef[st][st - 1];
-#pragma unroll
-              for (int u = 0; u < SLOTS; ++u) {
-                const int idx = ibase + u * WORKERS, r = idx >> 5, c4 = idx & 31;
-                acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (r < nr) { const float4 v = *Tp(c4, r); acc[u] = make_float4(cl * v.x, cl * v.y, cl * v.z, cl * v.w); }
-              }
-              for (int j = 0; j < st - 1; ++j) {
-                const float cf = a.coef[st][j];
-                if (cf == 0.f) continue;
-                const float* srcj = a.cat2[j];
-                float4 v[SLOTS];
-#pragma unroll
-                for (int u = 0; u < SLOTS; ++u) {
-                  const int idx = ibase + u * WORKERS, r = idx >> 5, c4 = idx & 31;
-                  v[u] = (r < nr) ? *reinterpret_cast<const float4*>(srcj + (size_t)(r0 + r) * W2H + 4 * c4)   // written by this CTA: plain load
-                                  : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-#pragma unroll
-                for (int u = 0; u < SLOTS; ++u) {
-                  acc[u].x = fmaf(cf, v[u].x, acc[u].x); acc[u].y = fmaf(cf, v[u].y, acc[u].y);
-                  acc[u].z = fmaf(cf, v[u].z, acc[u].z); acc[u].w = fmaf(cf, v[u].w, acc[u].w);
-                }
-              }
-            }
+        for (int hf = 0; hf < 2 * nblk; ++hf) {
+          const int ibase = wt + hf * SLOTS * WORKERS;
+          float4 acc[SLOTS];
+          if (st == 0) {
 #pragma unroll
             for (int u = 0; u < SLOTS; ++u) {
               const int idx = ibase + u * WORKERS, r = idx >> 5, c4 = idx & 31;
-              if (idx < n_slots_t) *Tp(c4, r) = acc[u];
+              acc[u] = (r < nr) ? __ldg(reinterpret_cast<const float4*>(a.z0 + (size_t)(r0 + r) * W2H + 4 * c4))
+                                : make_float4(0.f, 0.f, 0.f, 0.f);
             }
+          } else {
+            const float cl = a.coef[st][st - 1];
+#pragma unroll
+            for (int u = 0; u < SLOTS; ++u) {
+              const int idx = ibase + u * WORKERS, r = idx >> 5, c4 = idx & 31;
+              acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (r < nr) { const float4 v = *Tp(c4, r); acc[u] = make_float4(cl * v.x, cl * v.y, cl * v.z, cl * v.w); }
+            }
+            for (int j = 0; j < st - 1; ++j) {
+              const float cf = a.coef[st][j];
+              if (cf == 0.f) continue;
+              const float* srcj = a.cat2[j];
+              float4 v[SLOTS];
+#pragma unroll
+              for (int u = 0; u < SLOTS; ++u) {
+                const int idx = ibase + u * WORKERS, r = idx >> 5, c4 = idx & 31;
+                v[u] = (r < nr) ? *reinterpret_cast<const float4*>(srcj + (size_t)(r0 + r) * W2H + 4 * c4)   // written by this CTA: plain load
+                                : make_float4(0.f, 0.f, 0.f, 0.f);
+              }
+#pragma unroll
+              for (int u = 0; u < SLOTS; ++u) {
+                acc[u].x = fmaf(cf, v[u].x, acc[u].x); acc[u].y = fmaf(cf, v[u].y, acc[u].y);
+                acc[u].z = fmaf(cf, v[u].z, acc[u].z); acc[u].w = fmaf(cf, v[u].w, acc[u].w);
+              }
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < SLOTS; ++u) {
+            const int idx = ibase + u * WORKERS, r = idx >> 5, c4 = idx & 31;
+            if (idx < n_slots_t) *Tp(c4, r) = acc[u];
           }
         }
         worker_sync_w();
         CT(16 * st + 1);
         if (st > 0) {
-          // ---- Z_st = Z_0 + V_st @ M13^T + scale * c13 ----
-          hand_off();
-          CT(16 * st + 2);
+          // ---- Z_st = Z_0 + V_st @ M13^T + scale * c13, block after block ----
           const float cs = a.c13_scale[st];
-          // Z_0 comes back in the tile-linear mapping (coalesced: a warp reads one 512-byte row; a row-per-lane load
-          // would touch 32 lines per instruction).  Its first half is requested before the accumulator is ready.
-          constexpr int ZS = 8;
-          float4 z[ZS];
+          for (int b = 0; b < nblk; ++b) {
+            hand_off(b);
+            CT(16 * st + 2);
+            // Z_0 comes back in the tile-linear mapping (coalesced: a warp reads one 512-byte row; a row-per-lane load
+            // would touch 32 lines per instruction).  Its first half is requested before the accumulator is ready.
+            const int zbase = wt + b * 2 * SLOTS * WORKERS;
+            float4 z[SLOTS];
 #pragma unroll
-          for (int u = 0; u < ZS; ++u) {
-            const int idx = wt + u * WORKERS, r = idx >> 5, c4 = idx & 31;
-            z[u] = (r < nr) ? __ldg(reinterpret_cast<const float4*>(a.z0 + (size_t)(r0 + r) * W2H + 4 * c4)) : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-          wait_bar(smem_u32(&bar_acc_full), ph_acc, dead, status, 25);
-          ph_acc ^= 1u;
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          CT(16 * st + 3);
-          // accumulator + scale * c13 -> tile, lane = row
-          // (every warp runs this, also one whose lane quadrant holds no tile rows: skipping it measured 20 % slower)
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int c0 = 64 * ehf + 32 * h;
-            uint32_t r[32];
-            tmem_ld32(tmem_base, eq, (uint32_t)(ACC_COL + c0), r);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float4 c = __ldg(reinterpret_cast<const float4*>(a.c13 + c0) + i);
-              float4 o;
-              o.x = fmaf(cs, c.x, __uint_as_float(r[4 * i + 0])); o.y = fmaf(cs, c.y, __uint_as_float(r[4 * i + 1]));
-              o.z = fmaf(cs, c.z, __uint_as_float(r[4 * i + 2])); o.w = fmaf(cs, c.w, __uint_as_float(r[4 * i + 3]));
-              if (erow < TR) *Tp(c0 / 4 + i, erow) = o;
+            for (int u = 0; u < SLOTS; ++u) {
+              const int idx = zbase + u * WORKERS, r = idx >> 5, c4 = idx & 31;
+              z[u] = (r < nr) ? __ldg(reinterpret_cast<const float4*>(a.z0 + (size_t)(r0 + r) * W2H + 4 * c4)) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
-          }
-          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-          // second half of Z_0 on its way while the workers meet
-          float4 z2[ZS];
+            wait_bar(smem_u32(&bar_acc_full), ph_acc, dead, status, 25);
+            ph_acc ^= 1u;
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            CT(16 * st + 3);
+            // accumulator + scale * c13 -> tile, lane = row
+            // (every warp runs this, also one whose lane quadrant holds no tile rows: skipping it measured 20 % slower)
+            const int erow = b * TM + elane;
 #pragma unroll
-          for (int u = 0; u < ZS; ++u) {
-            const int idx = wt + (ZS + u) * WORKERS, r = idx >> 5, c4 = idx & 31;
-            z2[u] = (r < nr) ? __ldg(reinterpret_cast<const float4*>(a.z0 + (size_t)(r0 + r) * W2H + 4 * c4)) : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-          worker_sync();
+            for (int h = 0; h < 2; ++h) {
+              const int c0 = 64 * ehf + 32 * h;
+              uint32_t r[32];
+              tmem_ld32(tmem_base, eq, (uint32_t)(ACC_COL + c0), r);
 #pragma unroll
-          for (int u = 0; u < ZS; ++u) {
-            const int idx = wt + u * WORKERS, r = idx >> 5, c4 = idx & 31;
-            if (r < nr) { float4* tp = Tp(c4, r); float4 v = *tp; v.x += z[u].x; v.y += z[u].y; v.z += z[u].z; v.w += z[u].w; *tp = v; }
-          }
+              for (int i = 0; i < 8; ++i) {
+                const float4 c = __ldg(reinterpret_cast<const float4*>(a.c13 + c0) + i);
+                float4 o;
+                o.x = fmaf(cs, c.x, __uint_as_float(r[4 * i + 0])); o.y = fmaf(cs, c.y, __uint_as_float(r[4 * i + 1]));
+                o.z = fmaf(cs, c.z, __uint_as_float(r[4 * i + 2])); o.w = fmaf(cs, c.w, __uint_as_float(r[4 * i + 3]));
+                if (erow < TR) *Tp(c0 / 4 + i, erow) = o;
+              }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            // second half of Z_0 on its way while the workers meet
+            float4 z2[SLOTS];
 #pragma unroll
-          for (int u = 0; u < ZS; ++u) {
-            const int idx = wt + (ZS + u) * WORKERS, r = idx >> 5, c4 = idx & 31;
-            if (r < nr) { float4* tp = Tp(c4, r); float4 v = *tp; v.x += z2[u].x; v.y += z2[u].y; v.z += z2[u].z; v.w += z2[u].w; *tp = v; }
+            for (int u = 0; u < SLOTS; ++u) {
+              const int idx = zbase + (SLOTS + u) * WORKERS, r = idx >> 5, c4 = idx & 31;
+              z2[u] = (r < nr) ? __ldg(reinterpret_cast<const float4*>(a.z0 + (size_t)(r0 + r) * W2H + 4 * c4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            worker_sync();
+#pragma unroll
+            for (int u = 0; u < SLOTS; ++u) {
+              const int idx = zbase + u * WORKERS, r = idx >> 5, c4 = idx & 31;
+              if (r < nr) { float4* tp = Tp(c4, r); float4 v = *tp; v.x += z[u].x; v.y += z[u].y; v.z += z[u].z; v.w += z[u].w; *tp = v; }
+            }
+#pragma unroll
+            for (int u = 0; u < SLOTS; ++u) {
+              const int idx = zbase + (SLOTS + u) * WORKERS, r = idx >> 5, c4 = idx & 31;
+              if (r < nr) { float4* tp = Tp(c4, r); float4 v = *tp; v.x += z2[u].x; v.y += z2[u].y; v.z += z2[u].z; v.w += z2[u].w; *tp = v; }
+            }
+            worker_sync_w();
           }
-          worker_sync_w();
         }
         CT(16 * st + 4);
         // ---- h1 = relu(A(Z_l) + Z_r + b1) -> right half (in place) ----
-        if (arow < nr) {
-          float4 acc[8];
-          aggregate(ach, acc);
-          const float4* bb = reinterpret_cast<const float4*>(a.b1 + 4 * ach);
-          uint32_t mbits = 0u;
+        for (int b = 0; b < nblk; ++b) {
+          const int arow = b * TM + alane;
+          if (arow < nr) {
+            float4 acc[8];
+            aggregate(b, ach, acc);
+            const float4* bb = reinterpret_cast<const float4*>(a.b1 + 4 * ach);
+            uint32_t mbits = 0u;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            float4* own = Tp(16 + ach + i, arow);
-            const float4 z = *own, b = __ldg(bb + i);
-            float4 h;
-            h.x = fmaxf(acc[i].x + z.x + b.x, 0.f); h.y = fmaxf(acc[i].y + z.y + b.y, 0.f);
-            h.z = fmaxf(acc[i].z + z.z + b.z, 0.f); h.w = fmaxf(acc[i].w + z.w + b.w, 0.f);
-            *own = h;
-            mbits |= (h.x > 0.f ? 1u : 0u) << (4 * i) | (h.y > 0.f ? 2u : 0u) << (4 * i) | (h.z > 0.f ? 4u : 0u) << (4 * i) |
-                     (h.w > 0.f ? 8u : 0u) << (4 * i);
+            for (int i = 0; i < 8; ++i) {
+              float4* own = Tp(16 + ach + i, arow);
+              const float4 z = *own, bv = __ldg(bb + i);
+              float4 h;
+              h.x = fmaxf(acc[i].x + z.x + bv.x, 0.f); h.y = fmaxf(acc[i].y + z.y + bv.y, 0.f);
+              h.z = fmaxf(acc[i].z + z.z + bv.z, 0.f); h.w = fmaxf(acc[i].w + z.w + bv.w, 0.f);
+              *own = h;
+              mbits |= (h.x > 0.f ? 1u : 0u) << (4 * i) | (h.y > 0.f ? 2u : 0u) << (4 * i) | (h.z > 0.f ? 4u : 0u) << (4 * i) |
+                       (h.w > 0.f ? 8u : 0u) << (4 * i);
+            }
+            if (a.mask[st] != nullptr) a.mask[st][(size_t)(r0 + arow) * 4 + (ach >> 3)] = mbits;
           }
-          if (a.mask[st] != nullptr) a.mask[st][(size_t)(r0 + arow) * 4 + (ach >> 3)] = mbits;
         }
         worker_sync_w();
         CT(16 * st + 5);
         // ---- A(h1) -> left half: the tile is now cat1 ----
-        if (arow < nr) {
-          float4 acc[8];
-          aggregate(16 + ach, acc);
+        for (int b = 0; b < nblk; ++b) {
+          const int arow = b * TM + alane;
+          if (arow < nr) {
+            float4 acc[8];
+            aggregate(b, 16 + ach, acc);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) *Tp(ach + i, arow) = acc[i];
+            for (int i = 0; i < 8; ++i) *Tp(ach + i, arow) = acc[i];
+          }
         }
         worker_sync_w();
         CT(16 * st + 6);
-        // ---- h2 = relu(cat1 @ w2cat^T + b2) -> right half; cat1 goes out while the contraction runs ----
-        hand_off();
-        CT(16 * st + 7);
-        store_tile(a.cat1[st], true);
-        CT(16 * st + 8);
-        wait_bar(smem_u32(&bar_acc_full), ph_acc, dead, status, 26);
-        ph_acc ^= 1u;
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        {
+        // ---- h2 = relu(cat1 @ w2cat^T + b2) -> right half, block after block; cat1 goes out while the first contraction
+        // runs ----
+        for (int b = 0; b < nblk; ++b) {
+          hand_off(b);
+          CT(16 * st + 7);
+          if (b == 0) store_tile(a.cat1[st], true);
+          CT(16 * st + 8);
+          wait_bar(smem_u32(&bar_acc_full), ph_acc, dead, status, 26);
+          ph_acc ^= 1u;
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           uint32_t r[32];
           tmem_ld32(tmem_base, eq, (uint32_t)(ACC_COL + 32 * ehf), r);
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-          worker_sync();                       // every thread has finished reading the tile for the cat1 store
+          if (b == 0) worker_sync();           // every thread has finished reading the tile for the cat1 store
           CT(16 * st + 9);
+          const int erow = b * TM + elane;
           uint32_t mbits = 0u;
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const float4 b = __ldg(reinterpret_cast<const float4*>(a.b2 + 32 * ehf) + i);
+            const float4 bv = __ldg(reinterpret_cast<const float4*>(a.b2 + 32 * ehf) + i);
             float4 h;
-            h.x = fmaxf(__uint_as_float(r[4 * i + 0]) + b.x, 0.f); h.y = fmaxf(__uint_as_float(r[4 * i + 1]) + b.y, 0.f);
-            h.z = fmaxf(__uint_as_float(r[4 * i + 2]) + b.z, 0.f); h.w = fmaxf(__uint_as_float(r[4 * i + 3]) + b.w, 0.f);
+            h.x = fmaxf(__uint_as_float(r[4 * i + 0]) + bv.x, 0.f); h.y = fmaxf(__uint_as_float(r[4 * i + 1]) + bv.y, 0.f);
+            h.z = fmaxf(__uint_as_float(r[4 * i + 2]) + bv.z, 0.f); h.w = fmaxf(__uint_as_float(r[4 * i + 3]) + bv.w, 0.f);
             if (erow < TR) *Tp(16 + 8 * ehf + i, erow) = h;
             mbits |= (h.x > 0.f ? 1u : 0u) << (4 * i) | (h.y > 0.f ? 2u : 0u) << (4 * i) | (h.z > 0.f ? 4u : 0u) << (4 * i) |
                      (h.w > 0.f ? 8u : 0u) << (4 * i);
           }
           if (a.mask[st] != nullptr && erow < nr) a.mask[st][(size_t)(r0 + erow) * 4 + 2 + ehf] = mbits;
+          if (NB == 2 && b + 1 < nblk) worker_sync_w();   // block 1's operand rows must not change under its residual pass
         }
         worker_sync_w();
         CT(16 * st + 10);
         // ---- A(h2) -> left half: the tile is now cat2 ----
-        if (arow < nr) {
-          float4 acc[8];
-          aggregate(16 + ach, acc);
+        for (int b = 0; b < nblk; ++b) {
+          const int arow = b * TM + alane;
+          if (arow < nr) {
+            float4 acc[8];
+            aggregate(b, 16 + ach, acc);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) *Tp(ach + i, arow) = acc[i];
+            for (int i = 0; i < 8; ++i) *Tp(ach + i, arow) = acc[i];
+          }
         }
         worker_sync_w();
         CT(16 * st + 11);
@@ -372,8 +410,7 @@ __device__ __forceinline__ void chain_fwd_body(const Args& a, uint8_t* smem, uin
         CT(16 * st + 12);
         if (st == S - 1 && a.Cout != nullptr) {
           // C = sum_s csol[s] cat2_s: the last cat2 tile is still on chip, the earlier ones come back from L2
-          constexpr int SLOTS = TM * NCHUNK / WORKERS / 2;
-          for (int hf = 0; hf < 2; ++hf) {
+          for (int hf = 0; hf < 2 * nblk; ++hf) {
             const int ibase = wt + hf * SLOTS * WORKERS;
             float4 acc[SLOTS];
             const float cl = a.csol[st];
@@ -450,8 +487,15 @@ __global__ void __launch_bounds__(THREADS, 2) k_chain_fwd(const Args a) {
 #ifndef CHAIN_TR_SMALL
 #define CHAIN_TR_SMALL 96
 #endif
-  if (s_tr <= CHAIN_TR_SMALL) chain_fwd_body<CHAIN_TR_SMALL>(a, smem, bar_b_full, bar_b_empty, &bar_a_ready, &bar_acc_full, tmem_base, &dead_flag);
-  else chain_fwd_body<128>(a, smem, bar_b_full, bar_b_empty, &bar_a_ready, &bar_acc_full, tmem_base, &dead_flag);
+  // (the host launches with the shared memory of the variant the batch's largest graph needs: a.tile_rows)
+  if (a.tile_rows <= TM) {
+    if (s_tr <= CHAIN_TR_SMALL) chain_fwd_body<CHAIN_TR_SMALL, 1>(a, smem, bar_b_full, bar_b_empty, &bar_a_ready, &bar_acc_full, tmem_base, &dead_flag);
+    else chain_fwd_body<128, 1>(a, smem, bar_b_full, bar_b_empty, &bar_a_ready, &bar_acc_full, tmem_base, &dead_flag);
+  } else if (a.tile_rows <= TR_MID) {
+    chain_fwd_body<TR_MID, 2>(a, smem, bar_b_full, bar_b_empty, &bar_a_ready, &bar_acc_full, tmem_base, &dead_flag);
+  } else {
+    chain_fwd_body<TR_BIG, 2>(a, smem, bar_b_full, bar_b_empty, &bar_a_ready, &bar_acc_full, tmem_base, &dead_flag);
+  }
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -508,7 +552,7 @@ int pack_image(const float* W, int n, int k, int64_t ld, float* img, cudaStream_
 // block flushes the tile starts it produced.
 constexpr int TB_CHUNK = 4096;
 __global__ void __launch_bounds__(1024) k_tiles_build(const int64_t* __restrict__ graph_ptr, int64_t n_graphs,
-                                                      int32_t* __restrict__ tiles) {
+                                                      int32_t* __restrict__ tiles, int max_rows) {
   __shared__ int32_t sp[TB_CHUNK + 1];
   __shared__ int32_t st[TB_CHUNK + 1];
   __shared__ int s_nt, s_new, s_start, s_bad;
@@ -522,8 +566,8 @@ __global__ void __launch_bounds__(1024) k_tiles_build(const int64_t* __restrict_
       int start = s_start, made = 0;
       for (int i = 0; i < cnt; ++i) {
         const int b = sp[i], e = sp[i + 1];
-        if (e - b > TM) s_bad = 1;
-        if (e - start > TM) { st[made++] = b; start = b; }   // graph i does not fit: a new tile starts at it
+        if (e - b > max_rows) s_bad = 1;
+        if (e - start > max_rows) { st[made++] = b; start = b; }   // graph i does not fit: a new tile starts at it
       }
       s_start = start;
       s_new = made;
@@ -547,7 +591,8 @@ __global__ void __launch_bounds__(1024) k_tiles_build(const int64_t* __restrict_
 // search over the offsets, one per graph).  The orbit of 0 is marked by pointer doubling (log2 rounds: graphs already
 // marked mark their 2^k-th successor), a block-wide prefix count turns marks into tile indices.
 constexpr int TBP_MAX = 16384;           // graphs: 13 bytes of shared memory each
-__global__ void __launch_bounds__(1024) k_tiles_build_par(const int64_t* __restrict__ graph_ptr, int n, int32_t* __restrict__ tiles) {
+__global__ void __launch_bounds__(1024) k_tiles_build_par(const int64_t* __restrict__ graph_ptr, int n, int32_t* __restrict__ tiles,
+                                                          int max_rows) {
   extern __shared__ __align__(16) uint8_t tb_smem[];
   int32_t* sp = reinterpret_cast<int32_t*>(tb_smem);          // [n + 1] offsets
   int32_t* ja = sp + (n + 1);                                 // [n] jump (double buffered)
@@ -559,10 +604,10 @@ __global__ void __launch_bounds__(1024) k_tiles_build_par(const int64_t* __restr
   for (int i = tid; i <= n; i += 1024) sp[i] = (int32_t)graph_ptr[i];
   __syncthreads();
   for (int g = tid; g < n; g += 1024) {
-    if (sp[g + 1] - sp[g] > TM) s_bad = 1;
-    // largest h in (g, n] with sp[h] - sp[g] <= TM: graphs g .. h-1 share the tile
+    if (sp[g + 1] - sp[g] > max_rows) s_bad = 1;
+    // largest h in (g, n] with sp[h] - sp[g] <= max_rows: graphs g .. h-1 share the tile
     int lo = g + 1, hi = n;
-    const int lim = sp[g] + TM;
+    const int lim = sp[g] + max_rows;
     while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (sp[mid] <= lim) lo = mid; else hi = mid - 1; }
     ja[g] = lo;                                               // == n: the tile runs to the end of the batch
     mk[g] = g == 0;
@@ -628,17 +673,19 @@ int chain_fwd(Sage3Ctx& c, FoldWs& f, const Tableau& tb, float dt, float* Cout, 
   a.rowptr = c.g.rowptr; a.col = c.g.col;
   a.tiles = c.g_tiles;
   a.S = tb.S;
+  a.tile_rows = c.g.tile_rows > 0 ? c.g.tile_rows : chain::TM;
   a.status = status_dev;
   a.err = c.g_tile_err;
   GN_PROF(s, (double)c.N * tb.S * (2.0 * 128 * 128 + 2.0 * 128 * 64), 4.0 * (double)c.N * 128 * (2 + 2.0 * tb.S),
           "chain_fwd S=%d", tb.S);
   static bool attr_set = false;
   if (!attr_set) {
-    GN_CUDA(cudaFuncSetAttribute(chain::k_chain_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, chain::SMEM_BYTES));
+    GN_CUDA(cudaFuncSetAttribute(chain::k_chain_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, chain::SMEM_BYTES_BIG));
     GN_CUDA(cudaFuncSetAttribute(chain::k_chain_fwd, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     attr_set = true;
   }
-  chain::k_chain_fwd<<<2 * kNumSMs, chain::THREADS, chain::SMEM_BYTES, s>>>(a);
+  const bool big = a.tile_rows > chain::TR_MID;       // tiles of 145 .. 256 rows: one CTA per SM
+  chain::k_chain_fwd<<<(big ? 1 : 2) * kNumSMs, chain::THREADS, chain::smem_bytes_of(a.tile_rows), s>>>(a);
   GN_LAUNCHED();
   return GNODE_OK;
 }
@@ -654,9 +701,12 @@ extern "C" int gnode_chain_trace(long long* out128) {
 #endif
 
 // tiles: device int32 [n_graphs + 2].  graph_ptr: device int64 [n_graphs + 1] node offsets of the graphs of the batch.
-extern "C" int gnode_tiles_build(const int64_t* graph_ptr, int64_t n_graphs, int32_t* tiles, gnode_stream_t stream) {
+// max_rows: most rows a tile may hold (128, or up to 256 for batches with graphs of 129 .. 256 nodes).
+extern "C" int gnode_tiles_build_rows(const int64_t* graph_ptr, int64_t n_graphs, int32_t max_rows, int32_t* tiles,
+                                      gnode_stream_t stream) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   GN_ARG(graph_ptr && tiles && n_graphs > 0, "gnode_tiles_build: bad argument");
+  GN_ARG(max_rows >= 1 && max_rows <= chain::TR_BIG, "gnode_tiles_build: max_rows must be in [1, %d]", chain::TR_BIG);
   if (n_graphs <= chain::TBP_MAX) {
     const size_t smem = (size_t)(n_graphs + 1) * 4 + (size_t)n_graphs * 9 + 16;
     static bool attr_set = false;
@@ -664,10 +714,14 @@ extern "C" int gnode_tiles_build(const int64_t* graph_ptr, int64_t n_graphs, int
       GN_CUDA(cudaFuncSetAttribute(chain::k_tiles_build_par, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)(chain::TBP_MAX + 1) * 4 + (size_t)chain::TBP_MAX * 9 + 16)));
       attr_set = true;
     }
-    chain::k_tiles_build_par<<<1, 1024, smem, s>>>(graph_ptr, (int)n_graphs, tiles);
+    chain::k_tiles_build_par<<<1, 1024, smem, s>>>(graph_ptr, (int)n_graphs, tiles, max_rows);
   } else {
-    chain::k_tiles_build<<<1, 1024, 0, s>>>(graph_ptr, n_graphs, tiles);
+    chain::k_tiles_build<<<1, 1024, 0, s>>>(graph_ptr, n_graphs, tiles, max_rows);
   }
   GN_LAUNCHED();
   return GNODE_OK;
+}
+
+extern "C" int gnode_tiles_build(const int64_t* graph_ptr, int64_t n_graphs, int32_t* tiles, gnode_stream_t stream) {
+  return gnode_tiles_build_rows(graph_ptr, n_graphs, chain::TM, tiles, stream);
 }

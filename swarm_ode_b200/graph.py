@@ -56,20 +56,24 @@ class CSRGraph:
                 self._err_event = torch.cuda.Event()
                 self._err_event.record(torch.cuda.current_stream(dev))
                 _PENDING.append(self)
-        # Whole-graph row tiles (<= 128 rows): let the integrators keep a tile on chip across the stages of a step.
-        # Needs the batch's graph offsets and the host-known size of its largest graph.
+        # Whole-graph row tiles: let the integrators keep a tile on chip across the stages of a step.  Needs the batch's
+        # graph offsets and the host-known size of its largest graph: tiles hold at most 128 rows, or -- for batches with
+        # graphs of 129 .. 256 nodes -- 144 / 256 rows, processed as two 128-row blocks by the chain kernels.
         self.tiles = None
         self.tile_err = None
-        if (graph_ptr is not None and max_graph_nodes is not None and 0 < int(max_graph_nodes) <= 128
+        self.tile_rows = 0
+        if (graph_ptr is not None and max_graph_nodes is not None and 0 < int(max_graph_nodes) <= 256
                 and graph_ptr.is_cuda and graph_ptr.numel() >= 2):
+            m = int(max_graph_nodes)
+            self.tile_rows = 128 if m <= 128 else (144 if m <= 144 else 256)
             gp = graph_ptr.to(torch.int64).contiguous()
             self.tiles = torch.empty(gp.numel() + 1, dtype=torch.int32, device=dev)
             self.tile_err = torch.zeros(1, dtype=torch.int32, device=dev)
             with torch.cuda.device(dev):
-                _lib.check(L.gnode_tiles_build(_lib.ptr(gp), gp.numel() - 1, _lib.ptr(self.tiles), _lib.stream_ptr(dev)),
-                           "gnode_tiles_build")
+                _lib.check(L.gnode_tiles_build_rows(_lib.ptr(gp), gp.numel() - 1, self.tile_rows, _lib.ptr(self.tiles),
+                                                    _lib.stream_ptr(dev)), "gnode_tiles_build_rows")
         self.struct = _lib.GnodeGraph(N, E, self.rowptr.data_ptr(), self.col.data_ptr(), self.t_rowptr.data_ptr(),
-                                      self.t_col.data_ptr(), _lib.ptr(self.tiles), _lib.ptr(self.tile_err))
+                                      self.t_col.data_ptr(), _lib.ptr(self.tiles), _lib.ptr(self.tile_err), self.tile_rows)
 
     def ref(self):
         return C.byref(self.struct)

@@ -367,12 +367,15 @@ def test_dopri5_two_rank_lockstep_reproduces_unsharded_decisions(cuda):
     assert rel_l2(got, full) <= 1e-5
 
 
-@pytest.mark.parametrize("n_agv,n_pick,graphs", [(12, 7, 9), (4, 3, 23), (2, 1, 40), (19, 6, 5)])
+@pytest.mark.parametrize("n_agv,n_pick,graphs", [(12, 7, 9), (4, 3, 23), (2, 1, 40), (19, 6, 5), (19, 9, 7), (19, 9, 300), (30, 11, 4),
+                                                 (40, 11, 3), (26, 0, 5)])
 @pytest.mark.parametrize("solver", ["rk4", "euler"])
 def test_graph_resident_chain_equals_kernel_per_op_path(cuda, fold_mode, solver, n_agv, n_pick, graphs):
     """With batch.ptr / max_graph_nodes present the folded stages run graph-resident (csrc/chain_fwd.cu): one CTA keeps
     a tile of whole graphs on chip for all stages.  Same arithmetic as the kernel-per-op folded path up to fp32
-    summation order; graphs of 35 / 15 nodes pack several per tile, 125 nodes fill one."""
+    summation order; graphs of 35 / 15 nodes pack several per tile, 125 nodes fill one; graphs of 140 (19 AGVs + 9 pickers:
+    BASELINE configs[2]), 205 and 255 nodes run as tiles of two 128-row blocks (144-row and 256-row variants), 130-node
+    graphs (26 agents) likewise."""
     if fold_mode != "folded":
         pytest.skip("the chain kernel belongs to the folded integrator")
     batch, nxt = S.synthetic.warehouse_batch(graphs, num_agvs=n_agv, num_pickers=n_pick, seed=11)
