@@ -43,11 +43,13 @@ struct BwdArgs {
   const int32_t *rowptr, *t_rowptr, *t_col;
   const int32_t* tiles;
   int S;
+  int tile_rows;
   int* status;
   int* err;
 };
 
-template <int TR>
+// TR / NB as in chain_fwd.cu: rows kept per chunk, 128-row blocks per tile.
+template <int TR, int NB>
 __device__ __forceinline__ void chain_bwd_body(const BwdArgs& a, uint8_t* smem, float* s_inv, uint64_t* bar_b_full,
                                                uint64_t* bar_b_empty, uint64_t* bar_a_ready_p, uint64_t* bar_acc_full_p,
                                                uint32_t tmem_base, int* dead_flag_p) {
@@ -64,6 +66,7 @@ __device__ __forceinline__ void chain_bwd_body(const BwdArgs& a, uint8_t* smem, 
   uint8_t* const T = smem;
   const uint32_t smem_base = smem_u32(smem);
   const int n_tiles = a.tiles[0];
+  auto blocks_of = [&](int t) { return (NB == 2 && a.tiles[2 + t] - a.tiles[1 + t] > TM) ? 2 : 1; };
 
   if (warp == 0) {
     // =========================== weight-image producer ===========================
@@ -71,12 +74,14 @@ __device__ __forceinline__ void chain_bwd_body(const BwdArgs& a, uint8_t* smem, 
       uint32_t s = 0, ph = 0;
       bool first_lap = true;
       for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const int nblk = blocks_of(t);
         for (int st = S - 1; st >= 0; --st) {
           for (int g = (a.has_u[st] ? 0 : 1); g < 2; ++g) {       // g = 0: M13^T (K = 128), g = 1: w2cat^T (K = 64)
             const uint8_t* img = reinterpret_cast<const uint8_t*>(g == 0 ? a.img13T : a.img2T);
             const int nkb = g == 0 ? W2H / KB16 : WH / KB16;
             constexpr uint32_t bytes = stage_bytes(W2H);
-            for (int kb = 0; kb < nkb; ++kb) {
+            for (int kbb = 0; kbb < nkb * nblk; ++kbb) {
+              const int kb = kbb % nkb;
               if (!first_lap) wait_bar(smem_u32(&bar_b_empty[s]), ph ^ 1u, dead, status, 31);
               const uint32_t bar = smem_u32(&bar_b_full[s]);
               mbar_expect_tx(bar, bytes);
@@ -91,10 +96,12 @@ __device__ __forceinline__ void chain_bwd_body(const BwdArgs& a, uint8_t* smem, 
     // =========================== MMA issuer ===========================
     uint32_t pa = 0, sb = 0, pb = 0;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+      const int nblk = blocks_of(t);
       for (int st = S - 1; st >= 0; --st) {
         for (int g = (a.has_u[st] ? 0 : 1); g < 2; ++g) {
+         for (int b = 0; b < nblk; ++b) {
           const int nkb = g == 0 ? W2H / KB16 : WH / KB16;
-          const uint32_t a_addr = smem_base + (g == 0 ? 0u : (uint32_t)(16 * lbo_t));     // g = 1: right half of the tile
+          const uint32_t a_addr = smem_base + (g == 0 ? 0u : (uint32_t)(16 * lbo_t)) + (uint32_t)(b * TM * 16);   // g = 1: right half of the tile
           wait_bar(smem_u32(&bar_a_ready), pa, dead, status, 33);
           pa ^= 1u;
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -108,6 +115,7 @@ __device__ __forceinline__ void chain_bwd_body(const BwdArgs& a, uint8_t* smem, 
             __syncwarp();
             if (++sb == n_slots) { sb = 0; pb ^= 1u; }
           }
+         }
         }
       }
     }
@@ -117,8 +125,8 @@ __device__ __forceinline__ void chain_bwd_body(const BwdArgs& a, uint8_t* smem, 
     const int cw = warp - 2;                       // 0..7
     uint32_t ph_acc = 0u;
     const int eq = warp & 3, ehf = cw >> 2;        // TMEM mapping: lane quadrant of this warp, column half
-    const int erow = 32 * eq + lane;
-    const int arow = wt & (TM - 1), ach = (wt >> 7) * 8;   // aggregation mapping: two threads per row, 8 chunks each
+    const int elane = 32 * eq + lane;              // row of a 128-row block in the TMEM mapping
+    const int alane = wt & (TM - 1), ach = (wt >> 7) * 8;  // aggregation mapping: two threads per row of a block, 8 chunks each
     auto Tp = [&](int chunk, int row) { return reinterpret_cast<float4*>(T + (size_t)chunk * lbo_t + row * 16); };
     constexpr int n_slots_t = TR * NCHUNK;
     auto arrive_a = [&]() {
@@ -132,8 +140,9 @@ __device__ __forceinline__ void chain_bwd_body(const BwdArgs& a, uint8_t* smem, 
       const int r0 = a.tiles[1 + t];
       const int nr = a.tiles[2 + t] - r0;
       // out-neighbours of this thread's row (transposed CSR), tile-local, and 1 / in-degree of every row of the tile
+      const int nblk = (NB == 2 && nr > TM) ? 2 : 1;
       int nb_b = 0, nb_e = 0;
-      if (arow < nr) { nb_b = a.t_rowptr[r0 + arow]; nb_e = a.t_rowptr[r0 + arow + 1]; }
+      if (alane < nr) { nb_b = a.t_rowptr[r0 + alane]; nb_e = a.t_rowptr[r0 + alane + 1]; }
       int nbr[NBR_REG];
 #pragma unroll
       for (int q = 0; q < NBR_REG; ++q) {
@@ -144,28 +153,33 @@ __device__ __forceinline__ void chain_bwd_body(const BwdArgs& a, uint8_t* smem, 
         }
         nbr[q] = v;
       }
-      if (wt < TM) {
+      for (int rr = wt; rr < NB * TM; rr += WORKERS) {
         float w = 0.f;
-        if (wt < nr) { const int d = a.rowptr[r0 + wt + 1] - a.rowptr[r0 + wt]; w = 1.0f / (float)(d > 1 ? d : 1); }
-        s_inv[wt] = w;
+        if (rr < nr) { const int d = a.rowptr[r0 + rr + 1] - a.rowptr[r0 + rr]; w = 1.0f / (float)(d > 1 ? d : 1); }
+        s_inv[rr] = w;
       }
-      // A^T over chunks [c0, c0 + 8) of this thread's row
-      auto aggregate_t = [&](int c0, float4 (&acc)[8]) {
+      // A^T over chunks [c0, c0 + 8) of row 128 b + alane (block 1 walks its slice of the transposed CSR in global memory)
+      auto aggregate_t = [&](int b, int c0, float4 (&acc)[8]) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        int pb_ = nb_b + NBR_REG, pe_ = nb_e;
+        if (b == 0) {
 #pragma unroll
-        for (int q = 0; q < NBR_REG; ++q) {
-          if (nbr[q] >= 0) {
-            const float w = s_inv[nbr[q]];
+          for (int q = 0; q < NBR_REG; ++q) {
+            if (nbr[q] >= 0) {
+              const float w = s_inv[nbr[q]];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float4 v = *Tp(c0 + i, nbr[q]);
-              acc[i].x = fmaf(w, v.x, acc[i].x); acc[i].y = fmaf(w, v.y, acc[i].y);
-              acc[i].z = fmaf(w, v.z, acc[i].z); acc[i].w = fmaf(w, v.w, acc[i].w);
+              for (int i = 0; i < 8; ++i) {
+                const float4 v = *Tp(c0 + i, nbr[q]);
+                acc[i].x = fmaf(w, v.x, acc[i].x); acc[i].y = fmaf(w, v.y, acc[i].y);
+                acc[i].z = fmaf(w, v.z, acc[i].z); acc[i].w = fmaf(w, v.w, acc[i].w);
+              }
             }
           }
+        } else {
+          pb_ = a.t_rowptr[r0 + TM + alane]; pe_ = a.t_rowptr[r0 + TM + alane + 1];
         }
-        for (int p = nb_b + NBR_REG; p < nb_e; ++p) {
+        for (int p = pb_; p < pe_; ++p) {
           const int nb = a.t_col[p] - r0;
           if (nb < 0 || nb >= nr) { *a.err = 1; continue; }
           const float w = s_inv[nb];
@@ -179,10 +193,12 @@ __device__ __forceinline__ void chain_bwd_body(const BwdArgs& a, uint8_t* smem, 
       };
       // right half <- (A^T(left half) + right half) * [h > 0]; which = 0: h1, 1: h2 (sign bits kept by the forward chain)
       auto relu_back = [&](const uint32_t* mask, int which) {
+       for (int b = 0; b < nblk; ++b) {
+        const int arow = b * TM + alane;
         if (arow < nr) {
           const uint32_t m = __ldg(mask + (size_t)(r0 + arow) * 4 + 2 * which + (ach >> 3));
           float4 acc[8];
-          aggregate_t(ach, acc);
+          aggregate_t(b, ach, acc);
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             float4* own = Tp(16 + ach + i, arow);
@@ -193,14 +209,15 @@ __device__ __forceinline__ void chain_bwd_body(const BwdArgs& a, uint8_t* smem, 
             *own = o;
           }
         }
+       }
       };
       // tile-linear combination (rows < nr; zeros elsewhere), optionally also written to `out`:
       //   mode 0:  T <- c_self * T + sum_{i in [i0, i1)} cu[st_][i] * gz_i        (U_st)
       //   mode 1:  T <- cs_dt[st_] * G3
       //   mode 2:  T <- c_self * T + sum_{i in [i0, i1)} gz_i                       (GZ)
       auto combine = [&](int mode, int st_, float c_self, int i0, int i1, float* out) {
-        constexpr int SLOTS = TM * NCHUNK / WORKERS / 2;   // 8 per half
-        for (int hf = 0; hf < 2; ++hf) {
+        constexpr int SLOTS = TM * NCHUNK / WORKERS / 2;   // 8 per half block
+        for (int hf = 0; hf < 2 * nblk; ++hf) {
           const int ibase = wt + hf * SLOTS * WORKERS;
           float4 acc[SLOTS];
 #pragma unroll
@@ -248,23 +265,87 @@ __device__ __forceinline__ void chain_bwd_body(const BwdArgs& a, uint8_t* smem, 
           combine(0, st, a.cu[st][st + 1], st + 2, S, a.U[st]);
           worker_sync_w();
           CTB(16 * st + 1);
-          // ---- gcat2 = dt c_st G3 + U_st @ M13 ----
-          residual_to_tmem(T, lbo_t, TR, tmem_base, eq, lane, 16 * ehf, 0);
-          residual_to_tmem(T, lbo_t, TR, tmem_base, eq, lane, 16 * ehf + 8, 0);
-          arrive_a();
-          CTB(16 * st + 2);
-          // G3 comes back in the tile-linear mapping (coalesced), first half requested before the accumulator is ready
-          constexpr int ZS = 8;
-          float4 z[ZS];
+          // ---- gcat2 = dt c_st G3 + U_st @ M13, block after block ----
+          for (int b = 0; b < nblk; ++b) {
+            residual_to_tmem(T, lbo_t, TR, tmem_base, eq, lane, 16 * ehf, 0, ALO_COL, b * TM);
+            residual_to_tmem(T, lbo_t, TR, tmem_base, eq, lane, 16 * ehf + 8, 0, ALO_COL, b * TM);
+            arrive_a();
+            CTB(16 * st + 2);
+            // G3 comes back in the tile-linear mapping (coalesced), first half requested before the accumulator is ready
+            constexpr int ZS = 8;
+            const int zbase = wt + b * 2 * ZS * WORKERS;
+            float4 z[ZS];
 #pragma unroll
-          for (int u = 0; u < ZS; ++u) {
-            const int idx = wt + u * WORKERS, r = idx >> 5, c4 = idx & 31;
-            z[u] = (r < nr && csd != 0.f) ? __ldg(reinterpret_cast<const float4*>(a.G3 + (size_t)(r0 + r) * W2H + 4 * c4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int u = 0; u < ZS; ++u) {
+              const int idx = zbase + u * WORKERS, r = idx >> 5, c4 = idx & 31;
+              z[u] = (r < nr && csd != 0.f) ? __ldg(reinterpret_cast<const float4*>(a.G3 + (size_t)(r0 + r) * W2H + 4 * c4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            wait_bar(smem_u32(&bar_acc_full), ph_acc, dead, status, 35);
+            ph_acc ^= 1u;
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            CTB(16 * st + 3);
+            const int erow = b * TM + elane;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              uint32_t r[32];
+              tmem_ld32(tmem_base, eq, (uint32_t)(ACC_COL + 64 * ehf + 32 * h), r);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                if (erow < TR)
+                  *Tp(16 * ehf + 8 * h + i, erow) = make_float4(__uint_as_float(r[4 * i + 0]), __uint_as_float(r[4 * i + 1]),
+                                                                __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
+              }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            float4 z2[ZS];
+#pragma unroll
+            for (int u = 0; u < ZS; ++u) {
+              const int idx = zbase + (ZS + u) * WORKERS, r = idx >> 5, c4 = idx & 31;
+              z2[u] = (r < nr && csd != 0.f) ? __ldg(reinterpret_cast<const float4*>(a.G3 + (size_t)(r0 + r) * W2H + 4 * c4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            worker_sync();
+#pragma unroll
+            for (int u = 0; u < ZS; ++u) {
+              const int idx = zbase + u * WORKERS, r = idx >> 5, c4 = idx & 31;
+              if (r < nr) { float4* tp = Tp(c4, r); float4 v = *tp; v.x = fmaf(csd, z[u].x, v.x); v.y = fmaf(csd, z[u].y, v.y); v.z = fmaf(csd, z[u].z, v.z); v.w = fmaf(csd, z[u].w, v.w); *tp = v; }
+            }
+#pragma unroll
+            for (int u = 0; u < ZS; ++u) {
+              const int idx = zbase + (ZS + u) * WORKERS, r = idx >> 5, c4 = idx & 31;
+              if (r < nr) { float4* tp = Tp(c4, r); float4 v = *tp; v.x = fmaf(csd, z2[u].x, v.x); v.y = fmaf(csd, z2[u].y, v.y); v.z = fmaf(csd, z2[u].z, v.z); v.w = fmaf(csd, z2[u].w, v.w); *tp = v; }
+            }
+            worker_sync_w();
           }
-          wait_bar(smem_u32(&bar_acc_full), ph_acc, dead, status, 35);
+        } else {
+          // ---- no later stage feeds on this one: gcat2 = dt c_st G3 ----
+          combine(1, st, 0.f, 0, 1, nullptr);
+          worker_sync_w();
+        }
+        CTB(16 * st + 4);
+        // ---- g_v2 = (A^T(gcat2_l) + gcat2_r) * [h2 > 0] -> right half ----
+        relu_back(a.mask[st], 1);
+        worker_sync_w();
+        CTB(16 * st + 5);
+        // ---- gcat1 = g_v2 @ w2cat (K = 64: the right half is the operand); g_v2 goes out while the contraction runs ----
+        for (int b = 0; b < nblk; ++b) {
+          residual_to_tmem(T, lbo_t, TR, tmem_base, eq, lane, 16 + 8 * ehf, 16, ALO_COL, b * TM);
+          arrive_a();
+          CTB(16 * st + 6);
+          if (b == 0) {
+            for (int idx = wt; idx < nr * (NCHUNK / 2); idx += WORKERS) {
+              const int r = idx >> 4, c4 = idx & 15;
+              __stcs(reinterpret_cast<float4*>(a.gv2[st] + (size_t)(r0 + r) * WH + 4 * c4), *Tp(16 + c4, r));
+            }
+          }
+          CTB(16 * st + 7);
+          wait_bar(smem_u32(&bar_acc_full), ph_acc, dead, status, 36);
           ph_acc ^= 1u;
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          CTB(16 * st + 3);
+          // every thread has finished reading the tile for the g_v2 store; the epilogue of a block writes both halves of
+          // its OWN rows only (its operand rows, whose contraction has completed), never the other block's operand rows
+          worker_sync();
+          CTB(16 * st + 8);
+          const int erow = b * TM + elane;
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             uint32_t r[32];
@@ -277,72 +358,22 @@ __device__ __forceinline__ void chain_bwd_body(const BwdArgs& a, uint8_t* smem, 
             }
           }
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-          float4 z2[ZS];
-#pragma unroll
-          for (int u = 0; u < ZS; ++u) {
-            const int idx = wt + (ZS + u) * WORKERS, r = idx >> 5, c4 = idx & 31;
-            z2[u] = (r < nr && csd != 0.f) ? __ldg(reinterpret_cast<const float4*>(a.G3 + (size_t)(r0 + r) * W2H + 4 * c4)) : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-          worker_sync();
-#pragma unroll
-          for (int u = 0; u < ZS; ++u) {
-            const int idx = wt + u * WORKERS, r = idx >> 5, c4 = idx & 31;
-            if (r < nr) { float4* tp = Tp(c4, r); float4 v = *tp; v.x = fmaf(csd, z[u].x, v.x); v.y = fmaf(csd, z[u].y, v.y); v.z = fmaf(csd, z[u].z, v.z); v.w = fmaf(csd, z[u].w, v.w); *tp = v; }
-          }
-#pragma unroll
-          for (int u = 0; u < ZS; ++u) {
-            const int idx = wt + (ZS + u) * WORKERS, r = idx >> 5, c4 = idx & 31;
-            if (r < nr) { float4* tp = Tp(c4, r); float4 v = *tp; v.x = fmaf(csd, z2[u].x, v.x); v.y = fmaf(csd, z2[u].y, v.y); v.z = fmaf(csd, z2[u].z, v.z); v.w = fmaf(csd, z2[u].w, v.w); *tp = v; }
-          }
-          worker_sync_w();
-        } else {
-          // ---- no later stage feeds on this one: gcat2 = dt c_st G3 ----
-          combine(1, st, 0.f, 0, 1, nullptr);
           worker_sync_w();
         }
-        CTB(16 * st + 4);
-        // ---- g_v2 = (A^T(gcat2_l) + gcat2_r) * [h2 > 0] -> right half ----
-        relu_back(a.mask[st], 1);
-        worker_sync_w();
-        CTB(16 * st + 5);
-        // ---- gcat1 = g_v2 @ w2cat (K = 64: the right half is the operand); g_v2 goes out while the contraction runs ----
-        residual_to_tmem(T, lbo_t, TR, tmem_base, eq, lane, 16 + 8 * ehf, 16);
-        arrive_a();
-        CTB(16 * st + 6);
-        for (int idx = wt; idx < nr * (NCHUNK / 2); idx += WORKERS) {
-          const int r = idx >> 4, c4 = idx & 15;
-          __stcs(reinterpret_cast<float4*>(a.gv2[st] + (size_t)(r0 + r) * WH + 4 * c4), *Tp(16 + c4, r));
-        }
-        CTB(16 * st + 7);
-        wait_bar(smem_u32(&bar_acc_full), ph_acc, dead, status, 36);
-        ph_acc ^= 1u;
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        worker_sync();                         // every thread has finished reading the tile for the g_v2 store
-        CTB(16 * st + 8);
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          uint32_t r[32];
-          tmem_ld32(tmem_base, eq, (uint32_t)(ACC_COL + 64 * ehf + 32 * h), r);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            if (erow < TR)
-              *Tp(16 * ehf + 8 * h + i, erow) = make_float4(__uint_as_float(r[4 * i + 0]), __uint_as_float(r[4 * i + 1]),
-                                                            __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
-          }
-        }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        worker_sync_w();
         CTB(16 * st + 9);
         // ---- g_u1 = (A^T(gcat1_l) + gcat1_r) * [h1 > 0] -> right half ----
         relu_back(a.mask[st], 0);
         worker_sync_w();
         CTB(16 * st + 10);
         // ---- A^T(g_u1) -> left half: the tile is now gz_st ----
-        if (arow < nr) {
-          float4 acc[8];
-          aggregate_t(16 + ach, acc);
+        for (int b = 0; b < nblk; ++b) {
+          const int arow = b * TM + alane;
+          if (arow < nr) {
+            float4 acc[8];
+            aggregate_t(b, 16 + ach, acc);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) *Tp(ach + i, arow) = acc[i];
+            for (int i = 0; i < 8; ++i) *Tp(ach + i, arow) = acc[i];
+          }
         }
         worker_sync_w();
         CTB(16 * st + 11);
@@ -372,7 +403,7 @@ __global__ void __launch_bounds__(THREADS, 2) k_chain_bwd(const BwdArgs a) {
   __shared__ __align__(8) uint64_t bar_acc_full;
   __shared__ uint32_t tmem_holder;
   __shared__ int dead_flag;
-  __shared__ float s_inv[TM];
+  __shared__ float s_inv[2 * TM];
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -396,8 +427,14 @@ __global__ void __launch_bounds__(THREADS, 2) k_chain_bwd(const BwdArgs a) {
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = tmem_holder;
-  if (s_tr <= 96) chain_bwd_body<96>(a, smem, s_inv, bar_b_full, bar_b_empty, &bar_a_ready, &bar_acc_full, tmem_base, &dead_flag);
-  else chain_bwd_body<128>(a, smem, s_inv, bar_b_full, bar_b_empty, &bar_a_ready, &bar_acc_full, tmem_base, &dead_flag);
+  if (a.tile_rows <= TM) {
+    if (s_tr <= 96) chain_bwd_body<96, 1>(a, smem, s_inv, bar_b_full, bar_b_empty, &bar_a_ready, &bar_acc_full, tmem_base, &dead_flag);
+    else chain_bwd_body<128, 1>(a, smem, s_inv, bar_b_full, bar_b_empty, &bar_a_ready, &bar_acc_full, tmem_base, &dead_flag);
+  } else if (a.tile_rows <= TR_MID) {
+    chain_bwd_body<TR_MID, 2>(a, smem, s_inv, bar_b_full, bar_b_empty, &bar_a_ready, &bar_acc_full, tmem_base, &dead_flag);
+  } else {
+    chain_bwd_body<TR_BIG, 2>(a, smem, s_inv, bar_b_full, bar_b_empty, &bar_a_ready, &bar_acc_full, tmem_base, &dead_flag);
+  }
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -418,7 +455,7 @@ extern "C" int gnode_chain_trace_b(long long* out128) {
 bool chain_bwd_supported(const Sage3Ctx& c, const FoldWs& f) {
   static const bool off = [] { const char* e = std::getenv("GNODE_NO_CHAIN_BWD"); return e && e[0] == '1'; }();
   if (off) return false;
-  return chain_fwd_supported(c) && (c.g.tile_rows <= chain::TM) && c.ci2T != nullptr && f.ci13T != nullptr && f.Us[0] != nullptr && f.gv2s[0] != nullptr && f.mask[0] != nullptr &&
+  return chain_fwd_supported(c) && c.ci2T != nullptr && f.ci13T != nullptr && f.Us[0] != nullptr && f.gv2s[0] != nullptr && f.mask[0] != nullptr &&
          c.g.t_rowptr != nullptr && c.g.t_col != nullptr;
 }
 
@@ -446,17 +483,19 @@ int chain_bwd(Sage3Ctx& c, FoldWs& f, const Tableau& tb, float dt, bool* has_u, 
   a.rowptr = c.g.rowptr; a.t_rowptr = c.g.t_rowptr; a.t_col = c.g.t_col;
   a.tiles = c.g_tiles;
   a.S = tb.S;
+  a.tile_rows = c.g.tile_rows > 0 ? c.g.tile_rows : chain::TM;
   a.status = status_dev;
   a.err = c.g_tile_err;
   GN_PROF(s, (double)c.N * (n_u * 2.0 * 128 * 128 + tb.S * 2.0 * 128 * 64),
           4.0 * (double)c.N * (128.0 * (tb.S + n_u + 1 + 1) + 64.0 * tb.S + 4.0 * tb.S), "chain_bwd S=%d", tb.S);
   static bool attr_set = false;
   if (!attr_set) {
-    GN_CUDA(cudaFuncSetAttribute(chain::k_chain_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, chain::SMEM_BYTES));
+    GN_CUDA(cudaFuncSetAttribute(chain::k_chain_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, chain::SMEM_BYTES_BIG));
     GN_CUDA(cudaFuncSetAttribute(chain::k_chain_bwd, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     attr_set = true;
   }
-  chain::k_chain_bwd<<<2 * kNumSMs, chain::THREADS, chain::SMEM_BYTES, s>>>(a);
+  const bool big = a.tile_rows > chain::TR_MID;       // tiles of 145 .. 256 rows: one CTA per SM
+  chain::k_chain_bwd<<<(big ? 1 : 2) * kNumSMs, chain::THREADS, chain::smem_bytes_of(a.tile_rows), s>>>(a);
   GN_LAUNCHED();
   return GNODE_OK;
 }

@@ -76,10 +76,18 @@ def test_hidden_widths(cuda, solver, H):
     _run(batch, batch.x.shape[1], H, solver, cuda, torch.tensor([0.0, 0.5, 1.0]))
 
 
-def test_graphs_larger_than_a_tile_use_the_per_op_path(cuda):
-    """200-node dense graphs (config-4 shape, scaled): no whole-graph tiling (max_graph_nodes > 128), in-degree 199."""
+def test_dense_200_node_graphs_run_as_two_block_tiles(cuda):
+    """200-node dense graphs (config-4 shape, scaled): one graph per 256-row tile, processed by the chain kernels as two
+    128-row blocks; in-degree 199 (every neighbour beyond the four kept in registers is walked in the CSR)."""
     batch = S.synthetic.dense_batch(3, num_agents=200, node_dim_=64, seed=2)
-    assert batch.max_graph_nodes == 200 if hasattr(batch, "max_graph_nodes") else True
+    assert batch.max_graph_nodes == 200
+    _run(batch, 64, 64, "rk4", cuda, torch.tensor([0.0, 0.25]), conv3_scale=0.02)
+
+
+def test_graphs_larger_than_256_nodes_use_the_per_op_path(cuda):
+    """300-node dense graphs: no whole-graph tiling (max_graph_nodes > 256), kernel-per-op folded stages."""
+    batch = S.synthetic.dense_batch(2, num_agents=300, node_dim_=64, seed=4)
+    assert batch.max_graph_nodes == 300
     _run(batch, 64, 64, "rk4", cuda, torch.tensor([0.0, 0.25]), conv3_scale=0.02)
 
 
@@ -145,7 +153,8 @@ def _greedy_tiles(ptr, tm=128):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("n_graphs,lo,hi", [(1, 95, 95), (7, 1, 128), (4096, 95, 95), (3000, 1, 128), (16384, 1, 40), (20000, 3, 90)])
+@pytest.mark.parametrize("n_graphs,lo,hi", [(1, 95, 95), (7, 1, 128), (4096, 95, 95), (3000, 1, 128), (16384, 1, 40), (20000, 3, 90),
+                                            (500, 129, 144), (700, 1, 256), (20000, 100, 256)])
 def test_tiles_build_matches_greedy_packing(cuda, n_graphs, lo, hi):
     """gnode_tiles_build (parallel pointer-doubling form up to 16384 graphs, sequential form above) == greedy packing."""
     g = torch.Generator().manual_seed(n_graphs)
@@ -155,6 +164,8 @@ def test_tiles_build_matches_greedy_packing(cuda, n_graphs, lo, hi):
     ei = torch.zeros((2, 0), dtype=torch.long, device=cuda)
     csr = S.graph.CSRGraph(ei, N, graph_ptr=ptr.to(cuda), max_graph_nodes=int(sizes.max()))
     t = csr.tiles.cpu().tolist()
-    want = _greedy_tiles(ptr.tolist())
+    m = int(sizes.max())
+    assert csr.tile_rows == (128 if m <= 128 else (144 if m <= 144 else 256))
+    want = _greedy_tiles(ptr.tolist(), tm=csr.tile_rows)
     assert t[0] == len(want) - 1
     assert t[1:1 + len(want)] == want
