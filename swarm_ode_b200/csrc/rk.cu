@@ -94,33 +94,70 @@ __device__ __forceinline__ void block_reduce_store(double v, double* partials) {
 }
 
 // sum_i ( (a_i - b_i) / (atol + rtol * |y_i|) )^2         (b may be null)
+// VEC = 4: 128-bit loads over the first n & ~3 elements (16-byte aligned operands), scalar tail; the per-element
+// arithmetic (and its roundings) is the scalar one, the double-precision sum is order-insensitive at this level.
+__device__ __forceinline__ double sq_scaled(float a, float bsub, float y, float atol, float rtol) {
+  const float scale = __fadd_rn(atol, __fmul_rn(fabsf(y), rtol));
+  const float q = __fdiv_rn(__fsub_rn(a, bsub), scale);
+  return (double)__fmul_rn(q, q);
+}
+template <int VEC>
 __global__ void __launch_bounds__(EW_THREADS) k_scaled_sumsq(const float* __restrict__ a, const float* __restrict__ b,
                                                               const float* __restrict__ y, float atol, float rtol,
                                                               int64_t n, double* __restrict__ partials) {
   double acc = 0.0;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += stride) {
-    const float scale = __fadd_rn(atol, __fmul_rn(fabsf(__ldg(y + i)), rtol));
-    float v = __ldg(a + i);
-    if (b) v = __fsub_rn(v, __ldg(b + i));
-    const float q = __fdiv_rn(v, scale);
-    acc += (double)__fmul_rn(q, q);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x, tid0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  int64_t done = 0;
+  if (VEC == 4) {
+    const int64_t n4 = n >> 2;
+    for (int64_t i = tid0; i < n4; i += stride) {
+      const float4 va = __ldg(reinterpret_cast<const float4*>(a) + i), vy = __ldg(reinterpret_cast<const float4*>(y) + i);
+      const float4 vb = b ? __ldg(reinterpret_cast<const float4*>(b) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      // a - 0 == a exactly, so the b == null case keeps the reference's arithmetic
+      acc += sq_scaled(va.x, vb.x, vy.x, atol, rtol); acc += sq_scaled(va.y, vb.y, vy.y, atol, rtol);
+      acc += sq_scaled(va.z, vb.z, vy.z, atol, rtol); acc += sq_scaled(va.w, vb.w, vy.w, atol, rtol);
+    }
+    done = n4 << 2;
   }
+  for (int64_t i = done + tid0; i < n; i += stride) acc += sq_scaled(__ldg(a + i), b ? __ldg(b + i) : 0.f, __ldg(y + i), atol, rtol);
   block_reduce_store(acc, partials);
 }
 
 // dopri5 error ratio:  err_i = sum_j k_j,i * ce_j ;  tol_i = atol + rtol * max(|y0_i|, |y1_i|)
+__device__ __forceinline__ double sq_err(float err, float y0, float y1, float atol, float rtol) {
+  const float tol = __fadd_rn(atol, __fmul_rn(rtol, fmaxf(fabsf(y0), fabsf(y1))));
+  const float q = __fdiv_rn(err, tol);
+  return (double)__fmul_rn(q, q);
+}
+template <int VEC>
 __global__ void __launch_bounds__(EW_THREADS) k_error_sumsq(const LinComb lc /* in/coef = k_j, dt*c_err_j; base/out unused */,
                                                              const float* __restrict__ y0, const float* __restrict__ y1,
                                                              float atol, float rtol, double* __restrict__ partials) {
   double acc = 0.0;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < lc.n; i += stride) {
-    const float err = comb_terms(lc, i);
-    const float tol = __fadd_rn(atol, __fmul_rn(rtol, fmaxf(fabsf(__ldg(y0 + i)), fabsf(__ldg(y1 + i)))));
-    const float q = __fdiv_rn(err, tol);
-    acc += (double)__fmul_rn(q, q);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x, tid0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  int64_t done = 0;
+  if (VEC == 4) {
+    const int64_t n4 = lc.n >> 2;
+    for (int64_t i = tid0; i < n4; i += stride) {
+      float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
+      bool first = true;
+#pragma unroll
+      for (int j = 0; j < kMaxTerms; ++j) {
+        if (j < lc.n_terms) {       // same products and partial sums as comb_terms, four elements at a time
+          const float4 k = __ldg(reinterpret_cast<const float4*>(lc.in[j]) + i);
+          const float c = lc.coef[j];
+          const float4 p = make_float4(__fmul_rn(k.x, c), __fmul_rn(k.y, c), __fmul_rn(k.z, c), __fmul_rn(k.w, c));
+          e = first ? p : make_float4(__fadd_rn(e.x, p.x), __fadd_rn(e.y, p.y), __fadd_rn(e.z, p.z), __fadd_rn(e.w, p.w));
+          first = false;
+        }
+      }
+      const float4 a0 = __ldg(reinterpret_cast<const float4*>(y0) + i), a1 = __ldg(reinterpret_cast<const float4*>(y1) + i);
+      acc += sq_err(e.x, a0.x, a1.x, atol, rtol); acc += sq_err(e.y, a0.y, a1.y, atol, rtol);
+      acc += sq_err(e.z, a0.z, a1.z, atol, rtol); acc += sq_err(e.w, a0.w, a1.w, atol, rtol);
+    }
+    done = n4 << 2;
   }
+  for (int64_t i = done + tid0; i < lc.n; i += stride) acc += sq_err(comb_terms(lc, i), __ldg(y0 + i), __ldg(y1 + i), atol, rtol);
   block_reduce_store(acc, partials);
 }
 
@@ -244,7 +281,8 @@ int scaled_sumsq(const float* a, const float* b, const float* y, float atol, flo
                  double* partials, double* out, cudaStream_t s) {
   GN_PROF(s, 6.0 * n, 4.0 * (double)n * (b ? 3 : 2), "scaled_sumsq");
   const int nb = norm_blocks(n);
-  k_scaled_sumsq<<<nb, EW_THREADS, 0, s>>>(a, b, y, atol, rtol, n, partials);
+  if (aligned16(a) && aligned16(y) && (!b || aligned16(b))) k_scaled_sumsq<4><<<nb, EW_THREADS, 0, s>>>(a, b, y, atol, rtol, n, partials);
+  else k_scaled_sumsq<1><<<nb, EW_THREADS, 0, s>>>(a, b, y, atol, rtol, n, partials);
   GN_LAUNCHED();
   k_sum_partials<<<1, 32, 0, s>>>(partials, nb, out);
   GN_LAUNCHED();
@@ -255,7 +293,10 @@ int error_sumsq(const LinComb& lc, const float* y0, const float* y1, float atol,
                 double* partials, double* out, cudaStream_t s) {
   GN_PROF(s, 20.0 * lc.n, 4.0 * (double)lc.n * (lc.n_terms + 2), "dopri5_error_norm");
   const int nb = norm_blocks(lc.n);
-  k_error_sumsq<<<nb, EW_THREADS, 0, s>>>(lc, y0, y1, atol, rtol, partials);
+  bool al = aligned16(y0) && aligned16(y1);
+  for (int j = 0; j < lc.n_terms; ++j) al = al && aligned16(lc.in[j]);
+  if (al) k_error_sumsq<4><<<nb, EW_THREADS, 0, s>>>(lc, y0, y1, atol, rtol, partials);
+  else k_error_sumsq<1><<<nb, EW_THREADS, 0, s>>>(lc, y0, y1, atol, rtol, partials);
   GN_LAUNCHED();
   k_sum_partials<<<1, 32, 0, s>>>(partials, nb, out);
   GN_LAUNCHED();
