@@ -153,7 +153,7 @@ __device__ __forceinline__ void chain_fwd_body(const Args& a, uint8_t* smem, uin
       const int nr = a.tiles[2 + t] - r0;                 // rows of the tile: whole graphs
       const int nblk = (NB == 2 && nr > TM) ? 2 : 1;
       // CSR slice of this thread's row of block 0 (aggregation phases); its first NBR_REG neighbour ids (tile-local) stay
-      // in registers for the three aggregations of every stage.  Rows of block 1 walk their slice in global memory.
+      // in registers for the three aggregations of every stage.
       int nb_b = 0, nb_e = 0;
       if (alane < nr) { nb_b = a.rowptr[r0 + alane]; nb_e = a.rowptr[r0 + alane + 1]; }
       const float inv_deg = 1.0f / (float)((nb_e - nb_b) > 1 ? (nb_e - nb_b) : 1);
@@ -167,29 +167,42 @@ __device__ __forceinline__ void chain_fwd_body(const Args& a, uint8_t* smem, uin
         }
         nbr[q] = v;
       }
+      // the same for this thread's row of block 1 (two-block tiles only)
+      int nb1_b = 0, nb1_e = 0;
+      int nbr1[NBR_REG];
+#pragma unroll
+      for (int q = 0; q < NBR_REG; ++q) nbr1[q] = -1;
+      if (NB == 2 && TM + alane < nr) {
+        nb1_b = a.rowptr[r0 + TM + alane]; nb1_e = a.rowptr[r0 + TM + alane + 1];
+#pragma unroll
+        for (int q = 0; q < NBR_REG; ++q) {
+          if (nb1_b + q < nb1_e) {
+            int v = a.col[nb1_b + q] - r0;
+            if (v < 0 || v >= nr) { *a.err = 1; v = -1; }
+            nbr1[q] = v;
+          }
+        }
+      }
+      const float inv_deg1 = 1.0f / (float)((nb1_e - nb1_b) > 1 ? (nb1_e - nb1_b) : 1);
 
       // mean over the in-neighbours of chunks [c0, c0 + 8) of row 128 b + alane
       auto aggregate = [&](int b, int c0, float4 (&acc)[8]) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        int pb_ = nb_b + NBR_REG, pe_ = nb_e;
-        float w = inv_deg;
-        if (b == 0) {
+        const int pb_ = (b == 0 ? nb_b : nb1_b) + NBR_REG, pe_ = b == 0 ? nb_e : nb1_e;
+        const float w = b == 0 ? inv_deg : inv_deg1;
 #pragma unroll
-          for (int q = 0; q < NBR_REG; ++q) {
-            if (nbr[q] >= 0) {
+        for (int q = 0; q < NBR_REG; ++q) {
+          const int nq = b == 0 ? nbr[q] : nbr1[q];
+          if (nq >= 0) {
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const float4 v = *Tp(c0 + i, nbr[q]);
-                acc[i].x += v.x; acc[i].y += v.y; acc[i].z += v.z; acc[i].w += v.w;
-              }
+            for (int i = 0; i < 8; ++i) {
+              const float4 v = *Tp(c0 + i, nq);
+              acc[i].x += v.x; acc[i].y += v.y; acc[i].z += v.z; acc[i].w += v.w;
             }
           }
-        } else {
-          pb_ = a.rowptr[r0 + TM + alane]; pe_ = a.rowptr[r0 + TM + alane + 1];
-          w = 1.0f / (float)((pe_ - pb_) > 1 ? (pe_ - pb_) : 1);
         }
-        for (int p = pb_; p < pe_; ++p) {          // block 0: neighbours beyond NBR_REG; block 1: all of them
+        for (int p = pb_; p < pe_; ++p) {          // neighbours beyond the NBR_REG kept in registers
           const int nb = a.col[p] - r0;
           if (nb < 0 || nb >= nr) { *a.err = 1; continue; }
 #pragma unroll
