@@ -27,7 +27,10 @@ for trial in range(int(sys.argv[2]) if len(sys.argv) > 2 else 24):
     t = torch.tensor([0.0, 0.4, 1.0], device=cuda)
     outs = {}
     for mode in ("chain", "per_op"):
-        gb = batch.to(cuda) if mode == "chain" else S.Batch(x=batch.x.to(cuda), edge_index=batch.edge_index.to(cuda))
+        # (Data.to moves in place and csr_for caches by the edge tensor's storage: the per-op run needs its own copy of the
+        # edge list, or it would silently get the tiled graph of the chain run)
+        S.graph.clear_cache()
+        gb = batch.to(cuda) if mode == "chain" else S.Batch(x=batch.x.to(cuda), edge_index=batch.edge_index.to(cuda).clone())
         if mode == "per_op":
             gb.batch, gb.is_current_agent = batch.batch.to(cuda), batch.is_current_agent.to(cuda)
         model.zero_grad(set_to_none=True)

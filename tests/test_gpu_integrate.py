@@ -386,7 +386,10 @@ def test_graph_resident_chain_equals_kernel_per_op_path(cuda, fold_mode, solver,
     t = torch.tensor([0.0, 0.5, 1.0], device=cuda)
     outs = {}
     for mode in ("chain", "per_op"):
-        gb = batch.to(cuda) if mode == "chain" else S.Batch(x=batch.x.to(cuda), edge_index=batch.edge_index.to(cuda))
+        # (Data.to moves in place and csr_for caches by the edge tensor's storage: the per-op run needs its own copy of the
+        # edge list, or it would silently get the tiled graph of the chain run)
+        S.graph.clear_cache()
+        gb = batch.to(cuda) if mode == "chain" else S.Batch(x=batch.x.to(cuda), edge_index=batch.edge_index.to(cuda).clone())
         if mode == "per_op":
             gb.batch, gb.is_current_agent = batch.batch.to(cuda), batch.is_current_agent.to(cuda)
         model.zero_grad(set_to_none=True)
@@ -395,8 +398,9 @@ def test_graph_resident_chain_equals_kernel_per_op_path(cuda, fold_mode, solver,
         loss.backward()
         outs[mode] = (out["node_features"].detach().clone(), [p.grad.clone() for p in model.parameters()])
         S.graph.csr_for(gb.edge_index, gb.x.shape[0], holder=gb).validate()
-    assert rel_l2(outs["chain"][0], outs["per_op"][0]) <= 2e-6
+    e_sol = rel_l2(outs["chain"][0], outs["per_op"][0])
+    assert 0.0 < e_sol <= 5e-6, e_sol        # > 0: the two runs really took different kernels
     for a, b in zip(outs["chain"][1], outs["per_op"][1]):
-        assert rel_l2(a, b) <= 2e-5
+        assert rel_l2(a, b) <= 1e-4
     from swarm_ode_b200 import _lib
     _lib.tc_check(cuda)
