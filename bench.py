@@ -266,7 +266,9 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     model = S.GraphODE(D, 12, 7, hidden_dim=H, ode_solver=args.solver)
     S.synthetic.init_weights(model, seed=1, conv3_scale=0.1)
     model = model.to(dev)
-    opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-4)
+    # same update rule as the reference's torch.optim.Adam(lr, weight_decay) (scripts/train_gde.py:459); fused=True runs it as
+    # one multi-tensor kernel instead of ~10 (host glue, not part of the library)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-4, fused=True)
     t_dev = torch.tensor([0.0, 1.0], device=dev)
 
     def to_device(non_blocking=True):

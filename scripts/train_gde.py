@@ -77,7 +77,7 @@ def main():
     if world > 1:   # identical initial weights on every rank
         for p in model.parameters():
             dist.broadcast(p.data, src=0)
-    opt = torch.optim.Adam(model.parameters(), lr=args.lr, weight_decay=args.weight_decay)
+    opt = torch.optim.Adam(model.parameters(), lr=args.lr, weight_decay=args.weight_decay, fused=True)
     save_dir = os.path.join(args.save_dir, time.strftime("%Y%m%d_%H%M%S"))
     if rank == 0:
         os.makedirs(save_dir, exist_ok=True)
