@@ -112,6 +112,7 @@ struct GemmNT {
   int post_relu = 0;               // ReLU applied to the final value (after the base terms)
   const float* Bsplit = nullptr;   // optional: B pre-split into tf32 hi/lo planes (presplit_weights) -> tcgen05 engine
   const float* Bchain = nullptr;   // optional: chunked chain-format image of B (gemm_k128_pack) -> K = 128 wide-output engine
+  int rows_engine = 0;             // the caller accepts the row-major K = 128 engine (three-term truncated product) when it fits
 };
 int gemm_nt(const GemmNT& g, cudaStream_t s);
 // tf32 hi/lo planes of a row-major weight matrix, zero padded to multiples of 16 (gemm_tc.cu)

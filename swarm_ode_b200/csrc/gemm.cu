@@ -10,6 +10,13 @@ int gemm_nt_tc(const GemmNT& g, cudaStream_t s);
 
 bool gemm_k128_supported(const GemmNT& g);
 int gemm_k128(const GemmNT& g, cudaStream_t s);
+bool gemm_k128_rows_supported(const GemmNT& g);
+int gemm_k128_rows(const GemmNT& g, cudaStream_t s);
+
+static bool rows_engine_on() {   // GNODE_ROWS_ENGINE=0 falls back to the general engine (A/B runs)
+  static const bool on = [] { const char* e = std::getenv("GNODE_ROWS_ENGINE"); return !(e && e[0] == '0'); }();
+  return on;
+}
 
 int gemm_nt(const GemmNT& g, cudaStream_t s) {
   const int engine = current_engine();
@@ -18,10 +25,14 @@ int gemm_nt(const GemmNT& g, cudaStream_t s) {
   // that the default arithmetic stays the one the dopri5 step-count tests were recorded with.
   static const bool wide_on = [] { const char* e = std::getenv("GNODE_WIDE_ENGINE"); return e && e[0] == '1'; }();
   const bool wide = wide_on && engine != GNODE_ENGINE_SIMT && gemm_k128_supported(g);
+  // The row-major variant (dense D-wide rows moved as contiguous spans) is taken where the caller allows it: the y_1
+  // projection of the fixed-grid solvers.
+  const bool rows = g.rows_engine && rows_engine_on() && engine != GNODE_ENGINE_SIMT && gemm_k128_rows_supported(g);
   const bool tc = engine != GNODE_ENGINE_SIMT && gemm_nt_tc_supported(g);
   GN_PROF(s, 2.0 * g.M * g.N * g.K, 4.0 * ((double)g.M * g.K + (double)g.N * g.K + (double)g.M * g.N * (g.base ? 2 : 1)),
-          "gemm_nt[%s] N=%d K=%d", wide ? "k128" : (tc ? "tcgen05" : "ffma"), g.N, g.K);
+          "gemm_nt[%s] N=%d K=%d", rows ? "k128 rows" : wide ? "k128" : (tc ? "tcgen05" : "ffma"), g.N, g.K);
   if (engine == GNODE_ENGINE_SIMT) return gemm_nt_simt(g, s);
+  if (rows) return gemm_k128_rows(g, s);
   if (wide) return gemm_k128(g, s);
   if (gemm_nt_tc_supported(g)) return gemm_nt_tc(g, s);
   if (engine == GNODE_ENGINE_TC) {
@@ -116,5 +127,6 @@ extern "C" int gnode_gemm_k128(const float* A, const float* B, float* C, int64_t
   q.bias = bias; q.bias_scale = bias_scale; q.base = base; q.ldbase = ldbase; q.base_scale = base_scale;
   q.base2 = base2; q.ldbase2 = ldbase2; q.scale = scale; q.Bchain = img;
   GN_ARG(gemm_k128_supported(q), "gnode_gemm_k128: operand A must be 16-byte aligned");
+  if (rows_engine_on() && gemm_k128_rows_supported(q)) return gemm_k128_rows(q, s);   // dense rows, one base term
   return gemm_k128(q, s);
 }

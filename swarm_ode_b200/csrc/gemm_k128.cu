@@ -19,6 +19,8 @@
 //     per thread in flight, requested before the transposition.
 //
 //   warp 0 weight-image producer, warp 1 TMEM alloc + MMA issue, warps 2-9 workers.  Two CTAs per SM.
+#include <cstdlib>
+
 #include "chain_common.cuh"
 
 namespace gnode {
@@ -280,10 +282,284 @@ __global__ void k_pack_k128(const float* __restrict__ W, int n, int64_t ld, uint
 
 }  // namespace k128
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// ROW-MAJOR variant for C = base_scale * base + scale * (A B^T + bias_scale * bias) with DENSE rows (ldc = ldbase = N):
+// the y_1 = y + C w3cat^T + b3 projection of every folded step.
+//
+// Copy probes (scripts/dev/probe_l2prefetch.cu, probe_pitch.cu, probe_spanpipe.cu) show what bounds the chunked kernels
+// above: writing a [M x 399] matrix in row PIECES (any width below the row) runs at 2.2 TB/s read+write, because every
+// piece ends inside a 32-byte sector of a 1596-byte-pitch row, while moving the same matrix as contiguous spans through
+// shared memory with cp.async.bulk runs at 4.8 - 6.5 TB/s.  So here all N <= 400 accumulator columns of a 128-row block
+// stay in tensor memory (5 chunks of 80 columns, single buffered, one CTA per SM) and the epilogue is row major:
+//
+//   warp 10  pulls the base rows of the block into a ring of four 16-row SPAN slots (one 1-D bulk copy of 16 N floats
+//            each: contiguous and 16-byte aligned for any N),
+//   warps 2-9 (two per TMEM lane quadrant, lane = row) read their 32 rows x 200 columns of the accumulator and update
+//            the span in place (pitch N words: conflict free for odd N),
+//   warp 11  pushes the finished span back with one bulk store.
+//
+// The A tile of the next block is fetched with cp.async under the epilogue; the main loop of the next block (40 weight
+// stages, ~5 us) is the only serial part.  A ragged last group (< 16 rows) is updated directly in global memory.
+namespace k128r {
+using namespace chain;
+#ifdef K128_TRACE
+__device__ long long g_k128r_trace[128];
+#define RT(i) do { if (blockIdx.x == 0 && ehf == 0 && lane == 0 && it == 2) g_k128r_trace[8 * eq + (i)] = clock64(); } while (0)
+#else
+#define RT(i) do { } while (0)
+#endif
+using k128::NCH; using k128::NKB; using k128::KSTAGE;
+
+constexpr int RING = 4;
+constexpr int GR = 16, NSLOT = 4, MAXN = 400;
+static_assert(NSLOT == 4 && TM / GR == 2 * NSLOT, "the span pipeline is written for two rounds of four 16-row slots per block");
+constexpr int T_OFF = 0, B_OFF = t_bytes_of(TM), S_OFF = B_OFF + RING * KSTAGE;     // 66048, 117888
+constexpr int BIAS_OFF = S_OFF + NSLOT * GR * MAXN * 4;                               // 220288
+constexpr int SMEM = BIAS_OFF + MAXN * 4;                                             // 221888: one CTA per SM
+constexpr int ALO = 448, TMEM_ALL = 512;
+constexpr int WARP_LOAD = 10, WARP_STORE = 11, NTHREADS = 12 * 32;
+static_assert(S_OFF % 16 == 0 && SMEM <= 232448, "span slots must be 16-byte aligned and fit");
+
+__device__ __forceinline__ void bulk_store_1d(void* dst, uint32_t src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1) k_gemm_k128_rows(const k128::Args a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bar_b_full[RING];
+  __shared__ __align__(8) uint64_t bar_b_empty[RING];
+  __shared__ __align__(8) uint64_t bar_a_ready, bar_acc_full;
+  __shared__ __align__(8) uint64_t bar_full[NSLOT], bar_done[NSLOT], bar_free[NSLOT];
+  __shared__ uint32_t tmem_holder;
+  __shared__ int dead_flag;
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  int* const status = a.status;
+  volatile int* dead = &dead_flag;
+  uint8_t* const T = smem + T_OFF;
+  const uint32_t smem_base = smem_u32(smem);
+  const int64_t M = a.M;
+  const int N = a.N;
+  const int64_t m_tiles = (M + TM - 1) / TM;
+  const int n_chunks = a.n_chunks;
+  constexpr int lbo_t = lbo_t_of(TM);
+  const uint32_t slot_bytes = (uint32_t)(GR * N * 4);
+
+  if (tid == 0) {
+    dead_flag = 0;
+    for (int s = 0; s < RING; ++s) { mbar_init(smem_u32(&bar_b_full[s]), 1); mbar_init(smem_u32(&bar_b_empty[s]), 1); }
+    mbar_init(smem_u32(&bar_a_ready), WORKERS / 32);
+    mbar_init(smem_u32(&bar_acc_full), 1);
+    for (int s = 0; s < NSLOT; ++s) { mbar_init(smem_u32(&bar_full[s]), 1); mbar_init(smem_u32(&bar_done[s]), 2); mbar_init(smem_u32(&bar_free[s]), 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_holder)), "r"((uint32_t)TMEM_ALL));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  {
+    float* biasS = reinterpret_cast<float*>(smem + BIAS_OFF);
+    for (int i = tid; i < MAXN; i += NTHREADS) biasS[i] = (a.bias && i < N) ? a.scale * a.bias_scale * __ldg(a.bias + i) : 0.f;
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_holder;
+
+  if (warp == 0) {
+    // =========================== weight-image producer ===========================
+    if (lane == 0) {
+      uint32_t s = 0, ph = 0;
+      bool first_lap = true;
+      const uint8_t* img = reinterpret_cast<const uint8_t*>(a.img);
+      for (int64_t t = blockIdx.x; t < m_tiles; t += gridDim.x) {
+        for (int c = 0; c < n_chunks; ++c) {
+          for (int kb = 0; kb < NKB; ++kb) {
+            if (!first_lap) wait_bar(smem_u32(&bar_b_empty[s]), ph ^ 1u, dead, status, 51);
+            const uint32_t bar = smem_u32(&bar_b_full[s]);
+            mbar_expect_tx(bar, KSTAGE);
+            bulk_load_1d(smem_base + B_OFF + s * KSTAGE, img + ((size_t)c * NKB + kb) * KSTAGE, KSTAGE, bar);
+            if (++s == (uint32_t)RING) { s = 0; ph ^= 1u; first_lap = false; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =========================== MMA issuer ===========================
+    uint32_t sb = 0, pb = 0, it = 0;
+    for (int64_t t = blockIdx.x; t < m_tiles; t += gridDim.x, ++it) {
+      // A tile + residual operand in place; the workers arrive after draining the previous block's accumulators
+      wait_bar(smem_u32(&bar_a_ready), it & 1u, dead, status, 53);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      for (int c = 0; c < n_chunks; ++c) {
+        for (int kb = 0; kb < NKB; ++kb) {
+          wait_bar(smem_u32(&bar_b_full[sb]), pb, dead, status, 52);
+          if (lane == 0) {
+            issue_kblock(tmem_base + (uint32_t)(NCH * c), tmem_base + ALO, smem_base + T_OFF, (uint32_t)lbo_t,
+                         smem_base + B_OFF + sb * KSTAGE, NCH, kb, kb == 0);
+            umma_commit(smem_u32(&bar_b_empty[sb]));
+            if (c == n_chunks - 1 && kb == NKB - 1) umma_commit(smem_u32(&bar_acc_full));
+          }
+          __syncwarp();
+          if (++sb == (uint32_t)RING) { sb = 0; pb ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == WARP_LOAD) {
+    // =========================== base spans -> slots ===========================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int64_t t = blockIdx.x; t < m_tiles; t += gridDim.x, ++it) {
+        for (int g = 0; g < TM / GR; ++g) {
+          const uint32_t s = (uint32_t)g % NSLOT, lap = 2u * it + (uint32_t)g / NSLOT;
+          if (lap > 0) wait_bar(smem_u32(&bar_free[s]), (lap - 1) & 1u, dead, status, 54);
+          const int64_t r0 = t * TM + (int64_t)g * GR;
+          const bool whole = r0 + GR <= M;
+          const uint32_t bar = smem_u32(&bar_full[s]);
+          mbar_expect_tx(bar, whole ? slot_bytes : 0u);
+          if (whole) bulk_load_1d(smem_base + S_OFF + s * slot_bytes, a.base + r0 * N, slot_bytes, bar);
+        }
+      }
+    }
+  } else if (warp == WARP_STORE) {
+    // =========================== finished spans -> C ===========================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int64_t t = blockIdx.x; t < m_tiles; t += gridDim.x, ++it) {
+        for (int round = 0; round < TM / GR / NSLOT; ++round) {
+          // the four slots of a round: push each as soon as its rows are final, then free them in order as soon as the
+          // stores have READ them (about a microsecond) -- the loader is waiting for the slots.  (Freeing a slot one
+          // store late serialised the four quadrants of a block: traced at 40 us per block instead of 28.)
+          const uint32_t lap = 2u * it + (uint32_t)round;
+#pragma unroll
+          for (int s = 0; s < NSLOT; ++s) {
+            wait_bar(smem_u32(&bar_done[s]), lap & 1u, dead, status, 55);
+            const int64_t r0 = t * TM + (int64_t)(round * NSLOT + s) * GR;
+            if (r0 + GR <= M) bulk_store_1d(a.C + r0 * N, smem_base + S_OFF + s * slot_bytes, slot_bytes);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+          asm volatile("cp.async.bulk.wait_group.read 3;" ::: "memory"); mbar_arrive(smem_u32(&bar_free[0]));
+          asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory"); mbar_arrive(smem_u32(&bar_free[1]));
+          asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); mbar_arrive(smem_u32(&bar_free[2]));
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); mbar_arrive(smem_u32(&bar_free[3]));
+        }
+      }
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+  } else {
+    // =========================== workers ===========================
+    const int wt = tid - 64;
+    const int cw = warp - 2;
+    const int eq = warp & 3, ehf = cw >> 2;            // TMEM lane quadrant; which half of the columns
+    const float scale = a.scale, base_scale = a.base_scale;
+    const float* const biasS = reinterpret_cast<const float*>(smem + BIAS_OFF);
+    const uint32_t s0 = (uint32_t)(2 * eq) % NSLOT;
+    float* const my_row = reinterpret_cast<float*>(smem + S_OFF) + (size_t)(s0 * GR + lane) * N;   // slots s0, s0+1 are adjacent
+    const int c_lo = ehf ? 224 : 0, c_hi = ehf ? N : (N < 224 ? N : 224);
+
+    auto fetch_tile = [&](int64_t t_) {
+      const int64_t m0_ = t_ * TM;
+      const int nr_ = (int)((M - m0_ < TM) ? (M - m0_) : TM);
+#pragma unroll 4
+      for (int idx = wt; idx < TM * NCHUNK; idx += WORKERS) {
+        const int r = idx >> 5, c4 = idx & 31;
+        const uint32_t dst = smem_base + T_OFF + (uint32_t)c4 * lbo_t + (uint32_t)r * 16u;
+        if (r < nr_) {
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(a.A + (size_t)(m0_ + r) * W2H + 4 * c4) : "memory");
+        } else {
+          *reinterpret_cast<float4*>(T + (size_t)c4 * lbo_t + r * 16) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    auto publish_tile = [&]() {
+      asm volatile("cp.async.wait_all;" ::: "memory");
+      worker_sync_w();                                   // every granule landed; every worker is past its TMEM reads
+      residual_to_tmem(T, lbo_t, TM, tmem_base, eq, lane, 16 * ehf, 0, ALO);
+      residual_to_tmem(T, lbo_t, TM, tmem_base, eq, lane, 16 * ehf + 8, 0, ALO);
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&bar_a_ready));
+    };
+
+    if ((int64_t)blockIdx.x < m_tiles) { fetch_tile(blockIdx.x); publish_tile(); }
+    uint32_t it = 0;
+    for (int64_t t = blockIdx.x; t < m_tiles; t += gridDim.x, ++it) {
+      const int64_t m0 = t * TM;
+      RT(0);
+      wait_bar(smem_u32(&bar_acc_full), it & 1u, dead, status, 56);
+      RT(1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const bool more = t + gridDim.x < m_tiles;
+      // the MMAs of this block are complete: the tile is free for the next block's rows.  Quadrants 0 / 1 have their
+      // spans waiting and update them first (their stores start 2 us earlier); quadrants 2 / 3 wait for slots anyway.
+      if (more && eq >= 2) fetch_tile(t + gridDim.x);
+      RT(2);
+      // ---- my 32 rows x my half of the columns ----
+      const uint32_t lap = 2u * it + (uint32_t)(eq >> 1);
+      wait_bar(smem_u32(&bar_full[s0]), lap & 1u, dead, status, 57);
+      wait_bar(smem_u32(&bar_full[s0 + 1]), lap & 1u, dead, status, 57);
+      RT(3);
+      const int64_t grow = m0 + 32 * eq + lane;
+      const bool valid = grow < M;
+      const bool whole = m0 + 32 * eq + (lane & 16) + GR <= M;    // my 16-row group went through the slot
+      const float* brow = a.base + grow * a.ldbase;
+      float* crow = a.C + grow * a.ldc;
+      for (int c0 = c_lo; c0 < c_hi; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base, eq, (uint32_t)c0, r);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (whole) {
+          if (c0 + 32 <= N) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b4 = *reinterpret_cast<const float4*>(biasS + c0 + j);   // same address in every lane: broadcast
+              my_row[c0 + j] = base_scale * my_row[c0 + j] + scale * __uint_as_float(r[j]) + b4.x;
+              my_row[c0 + j + 1] = base_scale * my_row[c0 + j + 1] + scale * __uint_as_float(r[j + 1]) + b4.y;
+              my_row[c0 + j + 2] = base_scale * my_row[c0 + j + 2] + scale * __uint_as_float(r[j + 2]) + b4.z;
+              my_row[c0 + j + 3] = base_scale * my_row[c0 + j + 3] + scale * __uint_as_float(r[j + 3]) + b4.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (c0 + j < N) my_row[c0 + j] = base_scale * my_row[c0 + j] + scale * __uint_as_float(r[j]) + biasS[c0 + j];
+          }
+        } else if (valid) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (c0 + j < N) crow[c0 + j] = base_scale * __ldg(brow + c0 + j) + scale * __uint_as_float(r[j]) + biasS[c0 + j];
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(smem_u32(&bar_done[s0])); mbar_arrive(smem_u32(&bar_done[s0 + 1])); }
+      RT(4);
+      if (more && eq < 2) fetch_tile(t + gridDim.x);
+      if (more) publish_tile();
+      RT(5);
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_ALL));
+  }
+}
+
+}  // namespace k128r
+
 namespace tc { int* status_ptr(); }
 #ifdef K128_TRACE
 extern "C" int gnode_k128_trace(long long* out128) {
   return (int)cudaMemcpyFromSymbol(out128, k128::g_k128_trace, sizeof(long long) * 128);
+}
+extern "C" int gnode_k128r_trace(long long* out128) {
+  return (int)cudaMemcpyFromSymbol(out128, k128r::g_k128r_trace, sizeof(long long) * 128);
 }
 #endif
 
@@ -302,10 +578,13 @@ bool gemm_k128_supported(const GemmNT& g) {
          g.N >= 16 && (reinterpret_cast<uintptr_t>(g.A) & 15) == 0;
 }
 
-int gemm_k128(const GemmNT& g, cudaStream_t s) {
-  int* status_dev = tc::status_ptr();
-  if (!status_dev) { set_error("gemm_k128: status symbol unavailable"); return GNODE_ERR_CUDA; }
-  k128::Args a{};
+// dense rows on both sides, one base term, N <= 400: the row-major kernel
+bool gemm_k128_rows_supported(const GemmNT& g) {
+  return gemm_k128_supported(g) && g.base != nullptr && g.base2 == nullptr && g.N <= k128r::MAXN && g.ldc == g.N &&
+         g.ldbase == g.N && (reinterpret_cast<uintptr_t>(g.base) & 15) == 0 && (reinterpret_cast<uintptr_t>(g.C) & 15) == 0;
+}
+
+static void k128_args(const GemmNT& g, int* status_dev, k128::Args& a) {
   a.A = g.A; a.img = g.Bchain; a.C = g.C; a.ldc = g.ldc; a.M = g.M; a.N = g.N;
   a.n_chunks = (g.N + k128::NCH - 1) / k128::NCH;
   a.bias = g.bias; a.bias_scale = g.bias_scale;
@@ -313,6 +592,30 @@ int gemm_k128(const GemmNT& g, cudaStream_t s) {
   a.base2 = g.base ? g.base2 : nullptr; a.ldbase2 = g.ldbase2;
   a.scale = g.scale;
   a.status = status_dev;
+}
+
+int gemm_k128_rows(const GemmNT& g, cudaStream_t s) {
+  int* status_dev = tc::status_ptr();
+  if (!status_dev) { set_error("gemm_k128_rows: status symbol unavailable"); return GNODE_ERR_CUDA; }
+  k128::Args a{};
+  k128_args(g, status_dev, a);
+  static bool attr_set = false;
+  if (!attr_set) {
+    GN_CUDA(cudaFuncSetAttribute(k128r::k_gemm_k128_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, k128r::SMEM));
+    attr_set = true;
+  }
+  const int64_t m_tiles = (g.M + chain::TM - 1) / chain::TM;
+  const unsigned grid = (unsigned)(m_tiles < kNumSMs ? m_tiles : kNumSMs);
+  k128r::k_gemm_k128_rows<<<grid, k128r::NTHREADS, k128r::SMEM, s>>>(a);
+  GN_LAUNCHED();
+  return GNODE_OK;
+}
+
+int gemm_k128(const GemmNT& g, cudaStream_t s) {
+  int* status_dev = tc::status_ptr();
+  if (!status_dev) { set_error("gemm_k128: status symbol unavailable"); return GNODE_ERR_CUDA; }
+  k128::Args a{};
+  k128_args(g, status_dev, a);
   static bool attr_set = false;
   if (!attr_set) {
     GN_CUDA(cudaFuncSetAttribute(k128::k_gemm_k128, cudaFuncAttributeMaxDynamicSharedMemorySize, k128::SMEM));

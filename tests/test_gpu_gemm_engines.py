@@ -128,3 +128,27 @@ def test_k128_wide_output_engine(cuda, m, n, terms):
     assert rel_l2(got, want) <= 5e-6, rel_l2(got, want)
     from swarm_ode_b200 import _lib
     _lib.tc_check(cuda)
+
+
+@pytest.mark.parametrize("m,n", [(16, 399), (100, 399), (128 * 148 + 5, 399), (128 * 148 * 3 + 16 * 3 + 9, 399), (5000, 321), (5000, 64)])
+def test_k128_row_major_engine(cuda, m, n):
+    """Row-major variant (k_gemm_k128_rows: dense rows, one base term, N <= 400 -- the y_1 projection): whole 16-row spans
+    through shared memory, a ragged last group updated in global memory, several blocks per CTA; element-wise against float64."""
+    g = torch.Generator().manual_seed(m + n)
+    junk = torch.full((8 << 20,), float("nan"), device=cuda)
+    del junk
+    a = torch.randn(m, 128, generator=g) * 2.0
+    w = torch.randn(n, 128, generator=g) * 0.2
+    base = torch.randn(m, n, generator=g) * 4.0
+    bias = torch.randn(n, generator=g)
+    for kw, want in (
+        (dict(base_scale=1.0, scale=0.25), base.double() + 0.25 * (a.double() @ w.double().T)),
+        (dict(bias=bias.to(cuda), bias_scale=0.6, base_scale=-0.5, scale=1.5),
+         -0.5 * base.double() + 1.5 * (a.double() @ w.double().T + 0.6 * bias.double())),
+    ):
+        got = S.ops.gemm_k128(a.to(cuda), w.to(cuda), base=base.to(cuda), **kw)
+        _lib.tc_check(cuda)
+        assert torch.isfinite(got).all()
+        assert rel_l2(got, want) <= 5e-6, rel_l2(got, want)
+        err = (got.double().cpu() - want).abs().max().item()
+        assert err <= 2e-4, err          # no misplaced row / column anywhere (values are O(10))
