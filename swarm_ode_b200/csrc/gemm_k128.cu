@@ -51,6 +51,7 @@ struct Args {
   const float* base2; int64_t ldbase2;
   float scale;
   int* status;
+  int dev_flags;   // K128_TRACE builds: bit 0 = weight producer fetches half of every stage (timing experiment)
 };
 
 __global__ void __launch_bounds__(THREADS, 2) k_gemm_k128(const Args a) {
@@ -311,10 +312,11 @@ __device__ long long g_k128r_trace[128];
 #endif
 using k128::NCH; using k128::NKB; using k128::KSTAGE;
 
-constexpr int RING = 4;
+constexpr int KPS = 2;                    // K blocks per ring slot / bulk copy
+constexpr int RING = 2;                   // ring slots of KPS stages
 constexpr int GR = 16, NSLOT = 4, MAXN = 400;
 static_assert(NSLOT == 4 && TM / GR == 2 * NSLOT, "the span pipeline is written for two rounds of four 16-row slots per block");
-constexpr int T_OFF = 0, B_OFF = t_bytes_of(TM), S_OFF = B_OFF + RING * KSTAGE;     // 66048, 117888
+constexpr int T_OFF = 0, B_OFF = t_bytes_of(TM), S_OFF = B_OFF + RING * KPS * KSTAGE;     // 66048, 117888
 constexpr int BIAS_OFF = S_OFF + NSLOT * GR * MAXN * 4;                               // 220288
 constexpr int SMEM = BIAS_OFF + MAXN * 4;                                             // 221888: one CTA per SM
 constexpr int ALO = 448, TMEM_ALL = 512;
@@ -376,11 +378,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_k128_rows(const k128::Args
       const uint8_t* img = reinterpret_cast<const uint8_t*>(a.img);
       for (int64_t t = blockIdx.x; t < m_tiles; t += gridDim.x) {
         for (int c = 0; c < n_chunks; ++c) {
-          for (int kb = 0; kb < NKB; ++kb) {
+          for (int kb = 0; kb < NKB; kb += KPS) {     // one bulk copy per KPS K blocks (they are adjacent in the image)
             if (!first_lap) wait_bar(smem_u32(&bar_b_empty[s]), ph ^ 1u, dead, status, 51);
             const uint32_t bar = smem_u32(&bar_b_full[s]);
-            mbar_expect_tx(bar, KSTAGE);
-            bulk_load_1d(smem_base + B_OFF + s * KSTAGE, img + ((size_t)c * NKB + kb) * KSTAGE, KSTAGE, bar);
+            mbar_expect_tx(bar, KPS * KSTAGE);
+            bulk_load_1d(smem_base + B_OFF + s * (KPS * KSTAGE), img + ((size_t)c * NKB + kb) * KSTAGE, KPS * KSTAGE, bar);
             if (++s == (uint32_t)RING) { s = 0; ph ^= 1u; first_lap = false; }
           }
         }
@@ -394,13 +396,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_k128_rows(const k128::Args
       wait_bar(smem_u32(&bar_a_ready), it & 1u, dead, status, 53);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       for (int c = 0; c < n_chunks; ++c) {
-        for (int kb = 0; kb < NKB; ++kb) {
+        for (int kb = 0; kb < NKB; kb += KPS) {
           wait_bar(smem_u32(&bar_b_full[sb]), pb, dead, status, 52);
           if (lane == 0) {
-            issue_kblock(tmem_base + (uint32_t)(NCH * c), tmem_base + ALO, smem_base + T_OFF, (uint32_t)lbo_t,
-                         smem_base + B_OFF + sb * KSTAGE, NCH, kb, kb == 0);
+#pragma unroll
+            for (int j = 0; j < KPS; ++j)
+              issue_kblock(tmem_base + (uint32_t)(NCH * c), tmem_base + ALO, smem_base + T_OFF, (uint32_t)lbo_t,
+                           smem_base + B_OFF + (sb * KPS + j) * KSTAGE, NCH, kb + j, kb + j == 0);
             umma_commit(smem_u32(&bar_b_empty[sb]));
-            if (c == n_chunks - 1 && kb == NKB - 1) umma_commit(smem_u32(&bar_acc_full));
+            if (c == n_chunks - 1 && kb + KPS == NKB) umma_commit(smem_u32(&bar_acc_full));
           }
           __syncwarp();
           if (++sb == (uint32_t)RING) { sb = 0; pb ^= 1u; }
@@ -592,6 +596,10 @@ static void k128_args(const GemmNT& g, int* status_dev, k128::Args& a) {
   a.base2 = g.base ? g.base2 : nullptr; a.ldbase2 = g.ldbase2;
   a.scale = g.scale;
   a.status = status_dev;
+  a.dev_flags = 0;
+#ifdef K128_TRACE
+  { const char* e = std::getenv("K128_DEV_FLAGS"); a.dev_flags = e ? atoi(e) : 0; }
+#endif
 }
 
 int gemm_k128_rows(const GemmNT& g, cudaStream_t s) {
@@ -605,7 +613,10 @@ int gemm_k128_rows(const GemmNT& g, cudaStream_t s) {
     attr_set = true;
   }
   const int64_t m_tiles = (g.M + chain::TM - 1) / chain::TM;
-  const unsigned grid = (unsigned)(m_tiles < kNumSMs ? m_tiles : kNumSMs);
+  unsigned grid = (unsigned)(m_tiles < kNumSMs ? m_tiles : kNumSMs);
+#ifdef K128_TRACE
+  { const char* e = std::getenv("K128_GRID"); if (e && atoi(e) > 0 && (unsigned)atoi(e) < grid) grid = (unsigned)atoi(e); }
+#endif
   k128r::k_gemm_k128_rows<<<grid, k128r::NTHREADS, k128r::SMEM, s>>>(a);
   GN_LAUNCHED();
   return GNODE_OK;
