@@ -39,17 +39,18 @@ constexpr int TMEM_COLS = 256;
 
 __host__ __device__ constexpr int lbo_b(int n) { return n * 16 + 16; }
 __host__ __device__ constexpr int stage_bytes(int n) { return 10 * lbo_b(n); }     // hi 4 + lo 4 + bf16 2 chunks
-constexpr int B_STAGE = stage_bytes(W2H);     // 20640: ring slot (the N = 64 image uses half of it)
+constexpr int B_STAGE = 2 * stage_bytes(WH);  // 20800: ring slot = one K block of an N = 128 image (20640) or TWO of an N = 64 image
 constexpr int MAX_SLOTS = 4;
-constexpr int SMEM_BYTES = t_bytes_of(96) + 3 * B_STAGE;   // 111584: two CTAs per SM; 2 slots for 128-row tiles, 3 for <= 96 rows
+constexpr int SMEM_BYTES = t_bytes_of(96) + 3 * B_STAGE;   // 112064: two CTAs per SM; 2 slots for 128-row tiles, 3 for <= 96 rows
 // Tiles of more than 128 rows (graphs of 129 .. 256 nodes) are processed as two 128-row blocks: up to TR_MID rows still
 // leave room for one ring slot next to a second CTA; beyond that one CTA per SM with the full tile and two slots.
 constexpr int TR_MID = 144, TR_BIG = 256;
-constexpr int SMEM_BYTES_BIG = t_bytes_of(TR_BIG) + 2 * B_STAGE;   // 172864
+constexpr int SMEM_BYTES_BIG = t_bytes_of(TR_BIG) + 2 * B_STAGE;   // 173184
 __host__ __device__ constexpr int smem_bytes_of(int tr) { return tr <= TR_MID ? SMEM_BYTES : SMEM_BYTES_BIG; }
 __host__ __device__ constexpr int ring_slots(int tr) {
   return (smem_bytes_of(tr) - t_bytes_of(tr)) / B_STAGE > MAX_SLOTS ? MAX_SLOTS : (smem_bytes_of(tr) - t_bytes_of(tr)) / B_STAGE;
 }
+static_assert(B_STAGE >= stage_bytes(W2H), "slot too small");
 static_assert(ring_slots(128) >= 2 && ring_slots(TR_MID) >= 1 && ring_slots(TR_BIG) >= 2, "ring too small");
 
 inline size_t image_floats(int n, int k) { return (size_t)(k / KB16) * stage_bytes(n) / 4; }

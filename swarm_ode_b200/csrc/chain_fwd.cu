@@ -84,9 +84,12 @@ __device__ __forceinline__ void chain_fwd_body(const Args& a, uint8_t* smem, uin
         for (int st = 0; st < S; ++st) {
           for (int g = (st > 0 ? 0 : 1); g < 2; ++g) {           // g = 0: M13 (stage > 0 only), g = 1: w2cat
             const uint8_t* img = reinterpret_cast<const uint8_t*>(g == 0 ? a.img13 : a.img2);
-            const uint32_t bytes = g == 0 ? stage_bytes(W2H) : stage_bytes(WH);
+            // a ring slot / bulk copy carries one K block of the N = 128 image or two of the N = 64 image (the bulk copies
+            // of an SM complete one after the other with ~0.2 us of fixed cost each: fewer, larger copies)
+            const int kps = g == 0 ? 1 : 2;
+            const uint32_t bytes = g == 0 ? stage_bytes(W2H) : 2 * stage_bytes(WH);
             for (int b = 0; b < nblk; ++b) {
-              for (int kb = 0; kb < W2H / KB16; ++kb) {
+              for (int kb = 0; kb < W2H / KB16 / kps; ++kb) {
                 if (!first_lap) wait_bar(smem_u32(&bar_b_empty[s]), ph ^ 1u, dead, status, 21);
                 const uint32_t bar = smem_u32(&bar_b_full[s]);
                 mbar_expect_tx(bar, bytes);
@@ -110,13 +113,15 @@ __device__ __forceinline__ void chain_fwd_body(const Args& a, uint8_t* smem, uin
             wait_bar(smem_u32(&bar_a_ready), pa, dead, status, 23);   // tile + residual operand of this block ready
             pa ^= 1u;
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            for (int kb = 0; kb < W2H / KB16; ++kb) {
+            const int kps = g == 0 ? 1 : 2;               // K blocks per ring slot
+            for (int kb = 0; kb < W2H / KB16; kb += kps) {
               wait_bar(smem_u32(&bar_b_full[sb]), pb, dead, status, 22);
               if (lane == 0) {
-                issue_kblock(tmem_base + ACC_COL, tmem_base + ALO_COL, smem_base + (uint32_t)(b * TM * 16), (uint32_t)lbo_t,
-                             smem_base + b_off + sb * B_STAGE, n, kb, kb == 0);
+                for (int j = 0; j < kps; ++j)
+                  issue_kblock(tmem_base + ACC_COL, tmem_base + ALO_COL, smem_base + (uint32_t)(b * TM * 16), (uint32_t)lbo_t,
+                               smem_base + b_off + sb * B_STAGE + (uint32_t)(j * stage_bytes(WH)), n, kb + j, kb + j == 0);
                 umma_commit(smem_u32(&bar_b_empty[sb]));
-                if (kb == W2H / KB16 - 1) umma_commit(smem_u32(&bar_acc_full));
+                if (kb + kps == W2H / KB16) umma_commit(smem_u32(&bar_acc_full));
               }
               __syncwarp();
               if (++sb == n_slots) { sb = 0; pb ^= 1u; }
