@@ -332,7 +332,9 @@ int gnode_mlp_integrate_dopri5(const gnode_mlp_params* p, const float* y0, int64
 /* The D-wide projections of the folded integrator on their own (parity tests of the engine, csrc/gemm_k128.cu):
  *   C[m, n] = base_scale * base + base2 + scale * (A[m, :128] . B[n, :128] + bias_scale * bias[n])
  * A: [m, 128] dense rows (16-byte aligned); B: [n, 128]; C / base / base2: row strides ldc / ldbase / ldbase2, any
- * alignment; bias, base, base2 may be NULL (base2 needs base). */
+ * alignment; bias, base, base2 may be NULL (base2 needs base).  With dense rows (ldc == ldbase == n <= 400), one base
+ * term and 16-byte aligned C / base the row-major kernel runs (k_gemm_k128_rows: the y_1 projection of the fixed-grid
+ * solvers), otherwise the column-chunked one. */
 size_t gnode_gemm_k128_workspace_bytes(int32_t n);
 int gnode_gemm_k128(const float* A, const float* B, float* C, int64_t ldc, int64_t m, int32_t n, const float* bias,
                     float bias_scale, const float* base, int64_t ldbase, float base_scale, const float* base2,

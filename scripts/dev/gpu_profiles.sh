@@ -9,7 +9,7 @@ $CMD > gpurun_out/plain.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock
 echo "launch list rc=$?"
 P="python scripts/dev/step_prof.py 4096 rk4"
 $P > gpurun_out/plain2.log 2>&1 || exit 1
-for spec in "k_chain_fwd:10:chainfwd" "k_chain_bwd:10:chainbwd" "k_gemm_tc:22:y1" "k_gemm_tn_tc:41:tn64"; do
+for spec in "k_chain_fwd:10:chainfwd" "k_chain_bwd:10:chainbwd" "k_gemm_k128_rows:10:y1rows" "k_gemm_tc:10:z0"; do
   IFS=: read K S NAME <<< "$spec"
   ncu --set full --clock-control none --import-source on -k regex:$K -s $S -c 1 -o gpurun_out/${TAG}_full_$NAME $P > gpurun_out/ncu_$NAME.log 2>&1
   echo "ncu $NAME rc=$?"
