@@ -51,7 +51,13 @@ constexpr int CONV_THREADS = CONV_WARPS * 32;
 constexpr int WARP_EPI0 = 2 + CONV_WARPS;               // first epilogue warp (10: 10 % 4 == 2, quadrants 2,3,0,1)
 constexpr int WARP_BPROD = WARP_EPI0 + 4;               // B producer warp
 constexpr int THREADS = (WARP_BPROD + 1) * 32;          // 480
-constexpr int MAX_RAW = 10, MAX_AOP = 3, MAX_B = 4;
+constexpr int MAX_RAW = 10, MAX_AOP = 4, MAX_B = 4;
+#ifdef TC_TRACE
+__device__ long long g_tc_trace[16];
+#define TW(idx, stmt) do { const long long t0_ = clock64(); stmt; if (blockIdx.x == 0 && lane == 0) g_tc_trace[idx] += clock64() - t0_; } while (0)
+#else
+#define TW(idx, stmt) do { stmt; } while (0)
+#endif
 struct Args {
   const float* Bimg;   // pre-packed weight images: [n_tiles][nkb][hi plane | lo plane], each plane CHUNKS * lbo_b bytes
   float* C; int64_t ldc;
@@ -105,13 +111,15 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
   __shared__ __align__(8) uint64_t bar_raw_full[MAX_RAW];
   __shared__ __align__(8) uint64_t bar_raw_empty[MAX_RAW];
   __shared__ __align__(8) uint64_t bar_aop_full[MAX_AOP];
-  __shared__ __align__(8) uint64_t bar_aop_empty[MAX_AOP];
   __shared__ __align__(8) uint64_t bar_b_full[MAX_B];
   __shared__ __align__(8) uint64_t bar_b_empty[MAX_B];
   __shared__ __align__(8) uint64_t bar_acc_full[2];
   __shared__ __align__(8) uint64_t bar_acc_empty[2];
   __shared__ uint32_t tmem_holder;
 
+#ifdef TC_TRACE
+  const long long t_kernel0 = clock64();
+#endif
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
   // hoist every parameter the role loops need (keeps constant-bank loads out of the hot loops)
@@ -135,8 +143,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
   const int64_t tile0 = blockIdx.x, tstep = gridDim.x;
 
   if (tid == 0) {
-    for (int s = 0; s < NR; ++s) { mbar_init(smem_u32(&bar_raw_full[s]), 1); mbar_init(smem_u32(&bar_raw_empty[s]), CONV_THREADS); }
-    for (int s = 0; s < NA; ++s) { mbar_init(smem_u32(&bar_aop_full[s]), CONV_THREADS); mbar_init(smem_u32(&bar_aop_empty[s]), 1); }
+    // converter barriers count WARPS (lane 0 arrives after __syncwarp): 256 per-thread arrivals on one barrier word are
+    // 256 serialised shared-memory atomics per K block and barrier
+    for (int s = 0; s < NR; ++s) { mbar_init(smem_u32(&bar_raw_full[s]), 1); mbar_init(smem_u32(&bar_raw_empty[s]), CONV_WARPS); }
+    for (int s = 0; s < NA; ++s) { mbar_init(smem_u32(&bar_aop_full[s]), CONV_WARPS); }
     for (int s = 0; s < NB; ++s) { mbar_init(smem_u32(&bar_b_full[s]), 1); mbar_init(smem_u32(&bar_b_empty[s]), 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&bar_acc_full[b]), 1); mbar_init(smem_u32(&bar_acc_empty[b]), 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -161,7 +171,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
       for (int64_t t = tile0; t < total_tiles && ok; t += tstep) {
         const int c1 = (int)((t / n_tiles) * box_rows);
         for (int kb = 0; kb < nkb && ok; ++kb) {
-          if (!first_lap) ok = mbar_wait(smem_u32(&bar_raw_empty[s]), ph ^ 1u, status, 1);
+          if (!first_lap) TW(7, ok = mbar_wait(smem_u32(&bar_raw_empty[s]), ph ^ 1u, status, 1));
           const uint32_t dst = smem_base + raw_off + s * RAW_BYTES;
           const uint32_t bar = smem_u32(&bar_raw_full[s]);
           mbar_expect_tx(bar, RAW_BYTES);
@@ -202,7 +212,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
         }
         const float* src = Bimg + (size_t)(t % n_tiles) * nkb * (img_bytes / 4);
         for (int kb = 0; kb < nkb && ok; ++kb, src += img_bytes / 4) {
-          if (!first_lap) ok = mbar_wait(smem_u32(&bar_b_empty[s]), ph ^ 1u, status, 6);
+          if (!first_lap) TW(9, ok = mbar_wait(smem_u32(&bar_b_empty[s]), ph ^ 1u, status, 6));
           const uint32_t bar = smem_u32(&bar_b_full[s]);
           mbar_expect_tx(bar, img_bytes);
           bulk_load_1d(smem_base + b_off + s * img_bytes, src, img_bytes, bar);
@@ -220,16 +230,19 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
     bool ok = true;
     for (int64_t t = tile0; t < total_tiles && ok; t += tstep, ++tc) {
       const uint32_t ab = tc & 1, aph = (tc >> 1) & 1;
-      if (tc >= 2) ok = mbar_wait(smem_u32(&bar_acc_empty[ab]), aph ^ 1u, status, 4);   // epilogue drained this buffer
+      if (tc >= 2) TW(2, ok = mbar_wait(smem_u32(&bar_acc_empty[ab]), aph ^ 1u, status, 4));   // epilogue drained this buffer
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t tmem_d = tmem_base + ab * acc_cols;
       for (int kb = 0; kb < nkb && ok; ++kb) {
-        ok = mbar_wait(smem_u32(&bar_b_full[sb]), pb, status, 2);
-        ok = ok && mbar_wait(smem_u32(&bar_aop_full[sa]), pa, status, 2);
+        TW(0, ok = mbar_wait(smem_u32(&bar_b_full[sb]), pb, status, 2));
+        TW(1, ok = ok && mbar_wait(smem_u32(&bar_aop_full[sa]), pa, status, 2));
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (lane == 0) {
           const uint32_t a_hi = (smem_base + aop_off + sa * AOP_BYTES) >> 4, a_lo = a_hi + (A_PLANE >> 4);
           const uint32_t b_hi = (smem_base + b_off + sb * 2u * b_plane) >> 4, b_lo = b_hi + (b_plane >> 4);
+#ifdef TC_TRACE
+          const long long tm0 = clock64();
+#endif
 #pragma unroll
           for (int j = 0; j < BK / 8; ++j) {
             const uint64_t dah = desc_a | (uint64_t)(a_hi + j * step_a);
@@ -240,9 +253,16 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
             umma_tf32(tmem_d, dah, dbl, idesc, 1u);
             umma_tf32(tmem_d, dah, dbh, idesc, 1u);
           }
-          umma_commit(smem_u32(&bar_aop_empty[sa]));                   // stages are free once these MMAs retire
+#ifdef TC_TRACE
+          const long long tm1 = clock64();
+#endif
+          // ONE commit releases the A-operand stage and the weight stage (same ring depth, same slot index; the
+          // converters and the B producer both wait on bar_b_empty)
           umma_commit(smem_u32(&bar_b_empty[sb]));
           if (kb == nkb - 1) umma_commit(smem_u32(&bar_acc_full[ab])); // accumulator complete
+#ifdef TC_TRACE
+          if (blockIdx.x == 0) { g_tc_trace[10] += tm1 - tm0; g_tc_trace[11] += clock64() - tm1; }
+#endif
         }
         __syncwarp();
         if (++sa == (uint32_t)NA) { sa = 0; pa ^= 1u; }
@@ -273,7 +293,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
     bool first_lap_a = true, ok = true;
     for (int64_t t = tile0; t < total_tiles && ok; t += tstep) {
       for (int kb = 0; kb < nkb && ok; ++kb) {
-        ok = mbar_wait(smem_u32(&bar_raw_full[sr]), pr, status, 3);
+        if (cw == 0) TW(4, ok = mbar_wait(smem_u32(&bar_raw_full[sr]), pr, status, 3)); else ok = mbar_wait(smem_u32(&bar_raw_full[sr]), pr, status, 3);
         const float* raw = reinterpret_cast<const float*>(smem + raw_off + (size_t)sr * RAW_BYTES);
         float v[QPW];
 #pragma unroll
@@ -282,7 +302,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
 #pragma unroll
           for (int q = 0; q < QPW; ++q) v[q] = 0.f;
         }
-        if (!first_lap_a) ok = ok && mbar_wait(smem_u32(&bar_aop_empty[sa]), pa ^ 1u, status, 7);
+        if (!first_lap_a) { if (cw == 0) TW(5, ok = ok && mbar_wait(smem_u32(&bar_b_empty[sa]), pa ^ 1u, status, 7)); else ok = ok && mbar_wait(smem_u32(&bar_b_empty[sa]), pa ^ 1u, status, 7); }
         uint8_t* a_hi = smem + aop_off + (size_t)sa * AOP_BYTES;
         uint8_t* a_lo = a_hi + A_PLANE;
 #pragma unroll
@@ -294,9 +314,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
           *reinterpret_cast<uint32_t*>(a_hi + dst_off[q]) = hb;
           *reinterpret_cast<float*>(a_lo + dst_off[q]) = lo;
         }
-        mbar_arrive(smem_u32(&bar_raw_empty[sr]));                     // raw stage consumed (values are in registers)
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the MMA (async proxy)
-        mbar_arrive(smem_u32(&bar_aop_full[sa]));
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(smem_u32(&bar_raw_empty[sr]));                   // raw stage consumed (values are in registers)
+          mbar_arrive(smem_u32(&bar_aop_full[sa]));
+        }
         if (++sr == (uint32_t)NR) { sr = 0; pr ^= 1u; }
         if (++sa == (uint32_t)NA) { sa = 0; pa ^= 1u; first_lap_a = false; }
       }
@@ -319,7 +342,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
       const int64_t m0 = (t / n_tiles) * BM + 32 * qd;
       const int n0 = (int)(t % n_tiles) * bn;
       const uint32_t ab = tc & 1, aph = (tc >> 1) & 1;
-      ok = mbar_wait(smem_u32(&bar_acc_full[ab]), aph, status, 5);
+      if (qd == 0) TW(8, ok = mbar_wait(smem_u32(&bar_acc_full[ab]), aph, status, 5)); else ok = mbar_wait(smem_u32(&bar_acc_full[ab]), aph, status, 5);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t taddr = tmem_base + ab * acc_cols + ((uint32_t)(32 * qd) << 16);
       const int rmax = (M - m0 < 32) ? (int)(M - m0) : 32;   // valid rows of this warp's slab (may be <= 0)
@@ -360,6 +383,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
     }
   }
 
+#ifdef TC_TRACE
+  if (blockIdx.x == 0 && tid == 0) g_tc_trace[15] += clock64() - t_kernel0;
+#endif
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 1) {
@@ -467,8 +493,8 @@ int gemm_nt_tc(const GemmNT& g, cudaStream_t s) {
   // shared-memory plan: A-operand ring (3) + B ring (4, or 3 for wide tiles) + staging, the rest is the raw ring
   const size_t img = 2 * (size_t)tc::CHUNKS * ((size_t)a.bn * 16 + 16);
   const size_t budget = 224 * 1024;
-  a.n_aop = tc::MAX_AOP;
   a.n_b = (a.bn > 128) ? 3 : tc::MAX_B;
+  a.n_aop = a.n_b;      // one ring index and one release barrier for the A-operand stage and the weight stage
   const size_t fixed = (size_t)a.n_aop * tc::AOP_BYTES + (size_t)a.n_b * img + tc::STAGING_BYTES;
   int n_raw = (int)((budget - fixed) / tc::raw_bytes(J));
   if (n_raw > tc::MAX_RAW) n_raw = tc::MAX_RAW;
@@ -541,3 +567,11 @@ extern "C" int gnode_tc_status(gnode_stream_t stream) {
   }
   return GNODE_OK;
 }
+
+#ifdef TC_TRACE
+extern "C" int gnode_tc_trace(long long* out16, int reset) {
+  int rc = (int)cudaMemcpyFromSymbol(out16, gnode::tc::g_tc_trace, sizeof(long long) * 16);
+  if (reset) { long long z[16] = {0}; rc |= (int)cudaMemcpyToSymbol(gnode::tc::g_tc_trace, z, sizeof(z)); }
+  return rc;
+}
+#endif
