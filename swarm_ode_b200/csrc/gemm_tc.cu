@@ -234,7 +234,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t tmem_d = tmem_base + ab * acc_cols;
       for (int kb = 0; kb < nkb && ok; ++kb) {
-        TW(1, ok = mbar_wait(smem_u32(&bar_aop_full[sa]), pa, status, 2));   // A operand AND weights of this K block in place
+        TW(0, ok = mbar_wait(smem_u32(&bar_b_full[sb]), pb, status, 2));
+        TW(1, ok = ok && mbar_wait(smem_u32(&bar_aop_full[sa]), pa, status, 2));
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (lane == 0) {
           const uint32_t a_hi = (smem_base + aop_off + sa * AOP_BYTES) >> 4, a_lo = a_hi + (A_PLANE >> 4);
@@ -317,12 +318,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
         __syncwarp();
         if (lane == 0) {
           mbar_arrive(smem_u32(&bar_raw_empty[sr]));                   // raw stage consumed (values are in registers)
-          // converter warp 0 also vouches for the weight stage of this K block (same slot, same lap), so that the MMA
-          // warp -- the serial bottleneck of the kernel -- waits on ONE barrier per K block instead of two
-          if (cw == 0) ok = ok && mbar_wait(smem_u32(&bar_b_full[sa]), pa, status, 2);
           mbar_arrive(smem_u32(&bar_aop_full[sa]));
         }
-        ok = __shfl_sync(0xffffffffu, (int)ok, 0) != 0;
         if (++sr == (uint32_t)NR) { sr = 0; pr ^= 1u; }
         if (++sa == (uint32_t)NA) { sa = 0; pa ^= 1u; first_lap_a = false; }
       }
