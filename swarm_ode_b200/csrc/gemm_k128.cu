@@ -323,6 +323,41 @@ constexpr int ALO = 448, TMEM_ALL = 512;
 constexpr int WARP_LOAD = 10, WARP_STORE = 11, NTHREADS = 12 * 32;
 static_assert(S_OFF % 16 == 0 && SMEM <= 232448, "span slots must be 16-byte aligned and fit");
 
+// 8 TMEM columns starting at `col` of lane quadrant `eq` -> r[]
+__device__ __forceinline__ void tmem_ld8(uint32_t tmem_base, int eq, uint32_t col, uint32_t (&r)[8]) {
+  const uint32_t taddr = tmem_base + ((uint32_t)(32 * eq) << 16) + col;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+}
+
+// W accumulator columns [c0, c0 + W) of this thread's row: span slot in place (whole 16-row group) or global memory
+template <int W>
+__device__ __forceinline__ void span_update(float* my_row, const float* biasS, int c0, const uint32_t (&r)[W], int N,
+                                            float base_scale, float scale, bool whole, bool valid, const float* brow,
+                                            float* crow) {
+  if (whole) {
+    if (c0 + W <= N) {
+#pragma unroll
+      for (int j = 0; j < W; j += 4) {
+        const float4 b4 = *reinterpret_cast<const float4*>(biasS + c0 + j);   // same address in every lane: broadcast
+        my_row[c0 + j] = base_scale * my_row[c0 + j] + scale * __uint_as_float(r[j]) + b4.x;
+        my_row[c0 + j + 1] = base_scale * my_row[c0 + j + 1] + scale * __uint_as_float(r[j + 1]) + b4.y;
+        my_row[c0 + j + 2] = base_scale * my_row[c0 + j + 2] + scale * __uint_as_float(r[j + 2]) + b4.z;
+        my_row[c0 + j + 3] = base_scale * my_row[c0 + j + 3] + scale * __uint_as_float(r[j + 3]) + b4.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < W; ++j)
+        if (c0 + j < N) my_row[c0 + j] = base_scale * my_row[c0 + j] + scale * __uint_as_float(r[j]) + biasS[c0 + j];
+    }
+  } else if (valid) {
+#pragma unroll
+    for (int j = 0; j < W; ++j)
+      if (c0 + j < N) crow[c0 + j] = base_scale * __ldg(brow + c0 + j) + scale * __uint_as_float(r[j]) + biasS[c0 + j];
+  }
+}
+
 __device__ __forceinline__ void bulk_store_1d(void* dst, uint32_t src, uint32_t bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
 }
@@ -331,7 +366,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_k128_rows(const k128::Args
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t bar_b_full[RING];
   __shared__ __align__(8) uint64_t bar_b_empty[RING];
-  __shared__ __align__(8) uint64_t bar_a_ready, bar_acc_full;
+  __shared__ __align__(8) uint64_t bar_a_ready, bar_chunk_full[MAXN / NCH];   // accumulator chunk c complete
   __shared__ __align__(8) uint64_t bar_full[NSLOT], bar_done[NSLOT], bar_free[NSLOT];
   __shared__ uint32_t tmem_holder;
   __shared__ int dead_flag;
@@ -353,7 +388,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_k128_rows(const k128::Args
     dead_flag = 0;
     for (int s = 0; s < RING; ++s) { mbar_init(smem_u32(&bar_b_full[s]), 1); mbar_init(smem_u32(&bar_b_empty[s]), 1); }
     mbar_init(smem_u32(&bar_a_ready), WORKERS / 32);
-    mbar_init(smem_u32(&bar_acc_full), 1);
+    for (int c = 0; c < MAXN / NCH; ++c) mbar_init(smem_u32(&bar_chunk_full[c]), 1);
     for (int s = 0; s < NSLOT; ++s) { mbar_init(smem_u32(&bar_full[s]), 1); mbar_init(smem_u32(&bar_done[s]), 2); mbar_init(smem_u32(&bar_free[s]), 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -404,7 +439,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_k128_rows(const k128::Args
               issue_kblock(tmem_base + (uint32_t)(NCH * c), tmem_base + ALO, smem_base + T_OFF, (uint32_t)lbo_t,
                            smem_base + B_OFF + (sb * KPS + j) * KSTAGE, NCH, kb + j, kb + j == 0);
             umma_commit(smem_u32(&bar_b_empty[sb]));
-            if (c == n_chunks - 1 && kb + KPS == NKB) umma_commit(smem_u32(&bar_acc_full));
+            if (kb + KPS == NKB) umma_commit(smem_u32(&bar_chunk_full[c]));
           }
           __syncwarp();
           if (++sb == (uint32_t)RING) { sb = 0; pb ^= 1u; }
@@ -461,7 +496,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_k128_rows(const k128::Args
     const float* const biasS = reinterpret_cast<const float*>(smem + BIAS_OFF);
     const uint32_t s0 = (uint32_t)(2 * eq) % NSLOT;
     float* const my_row = reinterpret_cast<float*>(smem + S_OFF) + (size_t)(s0 * GR + lane) * N;   // slots s0, s0+1 are adjacent
-    const int c_lo = ehf ? 224 : 0, c_hi = ehf ? N : (N < 224 ? N : 224);
 
     auto fetch_tile = [&](int64_t t_) {
       const int64_t m0_ = t_ * TM;
@@ -494,15 +528,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_k128_rows(const k128::Args
     for (int64_t t = blockIdx.x; t < m_tiles; t += gridDim.x, ++it) {
       const int64_t m0 = t * TM;
       RT(0);
-      wait_bar(smem_u32(&bar_acc_full), it & 1u, dead, status, 56);
-      RT(1);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const bool more = t + gridDim.x < m_tiles;
-      // the MMAs of this block are complete: the tile is free for the next block's rows.  Quadrants 0 / 1 have their
-      // spans waiting and update them first (their stores start 2 us earlier); quadrants 2 / 3 wait for slots anyway.
-      if (more && eq >= 2) fetch_tile(t + gridDim.x);
+      const uint32_t par = it & 1u;
+      // Quadrants 0 / 1 have their spans waiting (prefetched under the main loop) and update them chunk by chunk as the
+      // accumulator chunks complete -- four fifths of their update runs under the MMAs.  Quadrants 2 / 3 get their slots
+      // only after the first round has been stored: they start the next block's A tile first (the tile is free once the
+      // last chunk is complete).
+      if (eq >= 2) {
+        wait_bar(smem_u32(&bar_chunk_full[n_chunks - 1]), par, dead, status, 56);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        RT(1);
+        if (more) fetch_tile(t + gridDim.x);
+      }
       RT(2);
-      // ---- my 32 rows x my half of the columns ----
       const uint32_t lap = 2u * it + (uint32_t)(eq >> 1);
       wait_bar(smem_u32(&bar_full[s0]), lap & 1u, dead, status, 57);
       wait_bar(smem_u32(&bar_full[s0 + 1]), lap & 1u, dead, status, 57);
@@ -512,29 +550,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_k128_rows(const k128::Args
       const bool whole = m0 + 32 * eq + (lane & 16) + GR <= M;    // my 16-row group went through the slot
       const float* brow = a.base + grow * a.ldbase;
       float* crow = a.C + grow * a.ldc;
-      for (int c0 = c_lo; c0 < c_hi; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld32(tmem_base, eq, (uint32_t)c0, r);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (whole) {
-          if (c0 + 32 <= N) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 b4 = *reinterpret_cast<const float4*>(biasS + c0 + j);   // same address in every lane: broadcast
-              my_row[c0 + j] = base_scale * my_row[c0 + j] + scale * __uint_as_float(r[j]) + b4.x;
-              my_row[c0 + j + 1] = base_scale * my_row[c0 + j + 1] + scale * __uint_as_float(r[j + 1]) + b4.y;
-              my_row[c0 + j + 2] = base_scale * my_row[c0 + j + 2] + scale * __uint_as_float(r[j + 2]) + b4.z;
-              my_row[c0 + j + 3] = base_scale * my_row[c0 + j + 3] + scale * __uint_as_float(r[j + 3]) + b4.w;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (c0 + j < N) my_row[c0 + j] = base_scale * my_row[c0 + j] + scale * __uint_as_float(r[j]) + biasS[c0 + j];
-          }
-        } else if (valid) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (c0 + j < N) crow[c0 + j] = base_scale * __ldg(brow + c0 + j) + scale * __uint_as_float(r[j]) + biasS[c0 + j];
+      for (int c = 0; c < n_chunks; ++c) {
+        if (eq < 2) {
+          wait_bar(smem_u32(&bar_chunk_full[c]), par, dead, status, 56);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          if (c == n_chunks - 1) RT(1);
+        }
+        const int c0 = NCH * c + (NCH / 2) * ehf;       // my 40 columns of the chunk
+        {
+          uint32_t r[32];
+          tmem_ld32(tmem_base, eq, (uint32_t)c0, r);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          span_update<32>(my_row, biasS, c0, r, N, base_scale, scale, whole, valid, brow, crow);
+        }
+        {
+          uint32_t r[8];
+          tmem_ld8(tmem_base, eq, (uint32_t)(c0 + 32), r);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          span_update<8>(my_row, biasS, c0 + 32, r, N, base_scale, scale, whole, valid, brow, crow);
         }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
