@@ -502,6 +502,7 @@ int integrate_dopri5_folded_bwd(Sage3Ctx& c, FoldWs& f, const float* y0, const d
     q.A = f.Cslot; q.lda = H2; q.B = c.w3cat; q.ldb = H2; q.C = ys + (int64_t)(k + 1) * n; q.ldc = c.D; q.M = N; q.N = c.D; q.K = H2;
     q.bias = c.b3; q.bias_scale = (float)csum * dt; q.base = y; q.ldbase = c.D;
     q.Bsplit = c.use_tc ? c.s3 : nullptr; q.Bchain = c.use_tc ? c.ck3 : nullptr;
+    q.rows_engine = 1;   // the replay takes no step-size decisions: the row-major engine may compute it
     GN_TRY(gemm_nt(q, s));
   }
 
