@@ -84,8 +84,9 @@ __device__ __forceinline__ void chain_fwd_body(const Args& a, uint8_t* smem, uin
         for (int st = 0; st < S; ++st) {
           for (int g = (st > 0 ? 0 : 1); g < 2; ++g) {           // g = 0: M13 (stage > 0 only), g = 1: w2cat
             const uint8_t* img = reinterpret_cast<const uint8_t*>(g == 0 ? a.img13 : a.img2);
-            // a ring slot / bulk copy carries one K block of the N = 128 image or two of the N = 64 image (the bulk copies
-            // of an SM complete one after the other with ~0.2 us of fixed cost each: fewer, larger copies)
+            // a ring slot / bulk copy carries one K block of the N = 128 image or two of the N = 64 image: a ring stage
+            // costs ~0.2 us of fixed time (copy completion, barrier wait, commit) on top of its MMAs ("what
+            // is next" (i)), so fewer, fatter stages
             const int kps = g == 0 ? 1 : 2;
             const uint32_t bytes = g == 0 ? stage_bytes(W2H) : 2 * stage_bytes(WH);
             for (int b = 0; b < nblk; ++b) {
