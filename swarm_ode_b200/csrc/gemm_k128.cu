@@ -300,8 +300,11 @@ __global__ void k_pack_k128(const float* __restrict__ W, int n, int64_t ld, uint
 //            the span in place (pitch N words: conflict free for odd N),
 //   warp 11  pushes the finished span back with one bulk store.
 //
-// The A tile of the next block is fetched with cp.async under the epilogue; the main loop of the next block (40 weight
-// stages, ~5 us) is the only serial part.  A ragged last group (< 16 rows) is updated directly in global memory.
+// The A tile of the next block is fetched with cp.async under the epilogue.  The main loop (5 chunks x 4 double stages of
+// the weight image, ~11.6 us per block) commits one barrier per accumulator chunk, so the two quadrants whose spans were
+// prefetched update them chunk by chunk under the MMAs; the other two follow when the first round has been stored (block
+// period 20.7 us, traced).  TMEM is full, so the main loop of block i+1 cannot overlap the epilogue of block i.  A ragged
+// last group (< 16 rows) is updated directly in global memory.
 namespace k128r {
 using namespace chain;
 #ifdef K128_TRACE
