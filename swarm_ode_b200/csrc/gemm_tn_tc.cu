@@ -253,50 +253,52 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tn_tc(const Args a) {
 
 // C (+)= scale * sum_c partials[c][n][m]   with C[m, n] (n_major = 0) or C[n, m] (n_major = 1); m < wm
 // followed (same launch) by the column sums:  out_m[c] += scale_m * sum over [S][2 ks] of colpart_m, same for n.
-// Four threads share one output element: thread q sums partials c = q, q + 4, ... (independent loads in flight), the
-// four sums are combined in a fixed order -> deterministic.
-__global__ void k_reduce_tn(const float* __restrict__ partials, int S, int wn, int wm, float* __restrict__ C,
-                            int64_t ldc, int n_major, float scale, const float* __restrict__ colpart_m,
-                            float* __restrict__ out_m, float scale_m, const float* __restrict__ colpart_n,
-                            float* __restrict__ out_n, float scale_n, int ks) {
-  const int64_t gid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  int64_t i = gid >> 2;
-  const int q = (int)(gid & 3);
+// A block of 256 threads owns 64 consecutive output elements; its four 64-thread groups each sum a contiguous quarter of
+// the partials (coalesced 256-byte rows, four independent loads in flight), the four sums are combined through shared memory
+// in a fixed order -> deterministic.
+__global__ void __launch_bounds__(256) k_reduce_tn(const float* __restrict__ partials, int S, int wn, int wm, float* __restrict__ C,
+                                                   int64_t ldc, int n_major, float scale, const float* __restrict__ colpart_m,
+                                                   float* __restrict__ out_m, float scale_m, const float* __restrict__ colpart_n,
+                                                   float* __restrict__ out_n, float scale_n, int ks) {
+  __shared__ float part[4][64];
+  const int e = threadIdx.x & 63, q = threadIdx.x >> 6;
+  int64_t i = blockIdx.x * 64LL + e;
   const int64_t n_mat = (int64_t)wn * MW;
-  float s = 0.f;
-  bool live = false;
+  const float* src = nullptr;     // partial r of this element at src[r * stride]
+  int64_t stride = 0;
+  int count = 0;
   float* dst = nullptr;
   float sc = 0.f;
   if (i < n_mat) {
     const int n = (int)(i / MW), m = (int)(i % MW);
     if (m < wm) {
-      live = true;
-      for (int c = q; c < S; c += 4) s += __ldg(partials + (size_t)c * n_mat + i);
+      src = partials + i; stride = n_mat; count = S;
       dst = n_major ? C + (int64_t)n * ldc + m : C + (int64_t)m * ldc + n;
       sc = scale;
     }
   } else {
     i -= n_mat;
     if (i < wm) {
-      if (out_m) {
-        live = true;
-        for (int r = q; r < 2 * ks * S; r += 4) s += __ldg(colpart_m + (size_t)r * wm + i);
-        dst = out_m + i; sc = scale_m;
-      }
+      if (out_m) { src = colpart_m + i; stride = wm; count = 2 * ks * S; dst = out_m + i; sc = scale_m; }
     } else if (i - wm < wn) {
       i -= wm;
-      if (out_n) {
-        live = true;
-        for (int r = q; r < 2 * ks * S; r += 4) s += __ldg(colpart_n + (size_t)r * wn + i);
-        dst = out_n + i; sc = scale_n;
-      }
+      if (out_n) { src = colpart_n + i; stride = wn; count = 2 * ks * S; dst = out_n + i; sc = scale_n; }
     }
   }
-  // the four lanes of an element are adjacent: (s0 + s1) + (s2 + s3)
-  const float s1 = __shfl_xor_sync(0xffffffffu, s, 1);
-  const float pair = (q & 1) ? (s1 + s) : (s + s1);
-  const float other = __shfl_xor_sync(0xffffffffu, pair, 2);
-  if (live && q == 0) *dst += sc * (pair + other);
+  const int per = (count + 3) / 4;
+  const int r0 = q * per, r1 = (r0 + per < count) ? r0 + per : count;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int r = r0;
+  for (; r + 4 <= r1; r += 4) {
+    s0 += __ldg(src + (size_t)r * stride);
+    s1 += __ldg(src + (size_t)(r + 1) * stride);
+    s2 += __ldg(src + (size_t)(r + 2) * stride);
+    s3 += __ldg(src + (size_t)(r + 3) * stride);
+  }
+  for (; r < r1; ++r) s0 += __ldg(src + (size_t)r * stride);
+  part[q][e] = (s0 + s1) + (s2 + s3);
+  __syncthreads();
+  if (q == 0 && dst) *dst += sc * ((part[0][e] + part[1][e]) + (part[2][e] + part[3][e]));
 }
 
 struct Plan { bool ok; bool m_is_b; int wm, wn, bn, nt, ks; int64_t n_kb; int grid; };
