@@ -75,6 +75,11 @@ int64_t gnode_launch_count(void);
 /* Synchronises `stream` and reports whether a tcgen05 kernel hit one of its bounded barrier waits
  * since the last call (GNODE_OK = healthy).  For tests / debugging; the hot path never calls it. */
 int gnode_tc_status(gnode_stream_t stream);
+/* Non-blocking form: enqueues on `stream` a copy of the status word (0 = healthy, otherwise the code of the barrier
+ * that expired) into `host_word` (pinned host memory).  The Python layer ships it next to the deferred tile check of
+ * every integrate call and raises from graph.poll_pending(); bench.py and scripts/train_gde.py call the blocking form
+ * after their timed region / once per epoch. */
+int gnode_tc_status_async(int32_t* host_word, gnode_stream_t stream);
 
 /* Per-kernel-class timing (CUDA events on the launching stream) for roofline reporting.  Each entry
  * carries the ALGORITHMIC flops / bytes of the launches it covers (computed from the shapes). */

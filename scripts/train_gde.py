@@ -120,6 +120,10 @@ def main():
         if world > 1:
             dist.all_reduce(vtot); dist.all_reduce(vn)
         val_loss = float(vtot / vn.clamp_min(1.0))
+        # once per epoch: the deferred device-side verdicts (edge-list / tile checks) and the tcgen05 barrier status word;
+        # raises GnodeError instead of training on with invalid results
+        S.graph.poll_pending()
+        S._lib.tc_check(dev)
         if rank == 0:
             if val_loss < best:
                 best = val_loss

@@ -71,6 +71,7 @@ _SIGNATURES = {
     "gnode_set_fold": (C.c_int, [C.c_int]),
     "gnode_launch_count": (C.c_int64, []),
     "gnode_tc_status": (C.c_int, [_P]),
+    "gnode_tc_status_async": (C.c_int, [_P, _P]),
     "gnode_prof_enable": (C.c_int, [C.c_int]),
     "gnode_prof_read": (C.c_int, [C.POINTER(GnodeProfEntry), C.c_int]),
     "gnode_csr_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int64]),
@@ -261,4 +262,5 @@ def prof_read():
 def tc_check(device=None) -> None:
     """Synchronise and raise if a tcgen05 kernel reported a barrier timeout (tests / debugging)."""
     dev = device if device is not None else torch.cuda.current_device()
-    check(lib().gnode_tc_status(stream_ptr(dev)), "gnode_tc_status")
+    with torch.cuda.device(dev):
+        check(lib().gnode_tc_status(stream_ptr(dev)), "gnode_tc_status")

@@ -409,6 +409,10 @@ __global__ void __launch_bounds__(THREADS, 2) k_chain_bwd(const BwdArgs a) {
   const int warp = tid >> 5;
   const int n_tiles = a.tiles[0];
 
+  // tiles[0] < 0: a graph of the batch exceeds the tile capacity the caller announced (max_graph_nodes understated).
+  // No tile is processed; flag it so that the deferred check raises instead of returning uninitialised results.
+  if (n_tiles < 0 && blockIdx.x == 0 && tid == 0 && a.err != nullptr) *a.err = 2;
+
   if (tid == 0) {
     dead_flag = 0;
     int mr = 8;
@@ -488,11 +492,9 @@ int chain_bwd(Sage3Ctx& c, FoldWs& f, const Tableau& tb, float dt, bool* has_u, 
   a.err = c.g_tile_err;
   GN_PROF(s, (double)c.N * (n_u * 2.0 * 128 * 128 + tb.S * 2.0 * 128 * 64),
           4.0 * (double)c.N * (128.0 * (tb.S + n_u + 1 + 1) + 64.0 * tb.S + 4.0 * tb.S), "chain_bwd S=%d", tb.S);
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (first_use_on_device(reinterpret_cast<const void*>(&chain::k_chain_bwd))) {
     GN_CUDA(cudaFuncSetAttribute(chain::k_chain_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, chain::SMEM_BYTES_BIG));
     GN_CUDA(cudaFuncSetAttribute(chain::k_chain_bwd, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    attr_set = true;
   }
   const bool big = a.tile_rows > chain::TR_MID;       // tiles of 145 .. 256 rows: one CTA per SM
   chain::k_chain_bwd<<<(big ? 1 : 2) * kNumSMs, chain::THREADS, chain::smem_bytes_of(a.tile_rows), s>>>(a);

@@ -66,11 +66,14 @@ __device__ __forceinline__ void worker_sync_w() {
 
 // bounded wait that gives up immediately once any wait of this CTA has timed out
 __device__ __forceinline__ void wait_bar(uint32_t addr, uint32_t parity, volatile int* dead, int* status, int code) {
-  if (mbar_try_wait(addr, parity)) return;            // fast path: no shared-memory flag read
-  for (uint32_t i = 0; i < SPIN_LIMIT; ++i) {
+  for (uint32_t i = 0; i < FAST_POLLS; ++i)            // fast path: no shared-memory flag read, no clock read
     if (mbar_try_wait(addr, parity)) return;
-    if ((i & 1023u) == 1023u && *dead) return;         // another wait of this CTA already timed out
-  }
+  const uint64_t t0 = globaltimer_ns();
+  do {
+    for (uint32_t i = 0; i < 256; ++i)
+      if (mbar_try_wait(addr, parity)) return;
+    if (*dead) return;                                 // another wait of this CTA already timed out
+  } while (globaltimer_ns() - t0 < WAIT_LIMIT_NS);
   *dead = 1;
   if (status) atomicExch(status, code);
 }

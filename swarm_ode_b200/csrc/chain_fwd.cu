@@ -484,6 +484,10 @@ __global__ void __launch_bounds__(THREADS, 2) k_chain_fwd(const Args a) {
   const int warp = tid >> 5, lane = tid & 31;
   const int n_tiles = a.tiles[0];
 
+  // tiles[0] < 0: a graph of the batch exceeds the tile capacity the caller announced (max_graph_nodes understated).
+  // No tile is processed; flag it so that the deferred check raises instead of returning uninitialised results.
+  if (n_tiles < 0 && blockIdx.x == 0 && tid == 0 && a.err != nullptr) *a.err = 2;
+
   if (tid == 0) {
     dead_flag = 0;
     int mr = 8;                                                  // most rows of any tile of this CTA
@@ -697,11 +701,9 @@ int chain_fwd(Sage3Ctx& c, FoldWs& f, const Tableau& tb, float dt, float* Cout, 
   a.err = c.g_tile_err;
   GN_PROF(s, (double)c.N * tb.S * (2.0 * 128 * 128 + 2.0 * 128 * 64), 4.0 * (double)c.N * 128 * (2 + 2.0 * tb.S),
           "chain_fwd S=%d", tb.S);
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (first_use_on_device(reinterpret_cast<const void*>(&chain::k_chain_fwd))) {
     GN_CUDA(cudaFuncSetAttribute(chain::k_chain_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, chain::SMEM_BYTES_BIG));
     GN_CUDA(cudaFuncSetAttribute(chain::k_chain_fwd, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    attr_set = true;
   }
   const bool big = a.tile_rows > chain::TR_MID;       // tiles of 145 .. 256 rows: one CTA per SM
   chain::k_chain_fwd<<<(big ? 1 : 2) * kNumSMs, chain::THREADS, chain::smem_bytes_of(a.tile_rows), s>>>(a);
@@ -728,10 +730,8 @@ extern "C" int gnode_tiles_build_rows(const int64_t* graph_ptr, int64_t n_graphs
   GN_ARG(max_rows >= 1 && max_rows <= chain::TR_BIG, "gnode_tiles_build: max_rows must be in [1, %d]", chain::TR_BIG);
   if (n_graphs <= chain::TBP_MAX) {
     const size_t smem = (size_t)(n_graphs + 1) * 4 + (size_t)n_graphs * 9 + 16;
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (first_use_on_device(reinterpret_cast<const void*>(&chain::k_tiles_build_par))) {
       GN_CUDA(cudaFuncSetAttribute(chain::k_tiles_build_par, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)(chain::TBP_MAX + 1) * 4 + (size_t)chain::TBP_MAX * 9 + 16)));
-      attr_set = true;
     }
     chain::k_tiles_build_par<<<1, 1024, smem, s>>>(graph_ptr, (int)n_graphs, tiles, max_rows);
   } else {

@@ -21,6 +21,7 @@ namespace gnode {
 
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
+bool first_use_on_device(const void* key);   // runtime.cu: per-device one-time setup guard
 
 #define GN_CUDA(expr)                                                                     \
   do {                                                                                    \

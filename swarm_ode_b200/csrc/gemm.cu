@@ -9,7 +9,6 @@ bool gemm_nt_tc_supported(const GemmNT& g);
 int gemm_nt_tc(const GemmNT& g, cudaStream_t s);
 
 bool gemm_k128_supported(const GemmNT& g);
-int gemm_k128(const GemmNT& g, cudaStream_t s);
 bool gemm_k128_rows_supported(const GemmNT& g);
 int gemm_k128_rows(const GemmNT& g, cudaStream_t s);
 
@@ -20,20 +19,14 @@ static bool rows_engine_on() {   // GNODE_ROWS_ENGINE=0 falls back to the genera
 
 int gemm_nt(const GemmNT& g, cudaStream_t s) {
   const int engine = current_engine();
-  // The wide-output engine (gemm_k128.cu) measures the same as the general one on the D = 399 projections (both are bound by
-  // the DRAM locality of 160-byte row pieces at a 1596-byte pitch); it is opt-in (GNODE_WIDE_ENGINE=1) so
-  // that the default arithmetic stays the one the dopri5 step-count tests were recorded with.
-  static const bool wide_on = [] { const char* e = std::getenv("GNODE_WIDE_ENGINE"); return e && e[0] == '1'; }();
-  const bool wide = wide_on && engine != GNODE_ENGINE_SIMT && gemm_k128_supported(g);
   // The row-major variant (dense D-wide rows moved as contiguous spans) is taken where the caller allows it: the y_1
   // projection of the fixed-grid solvers.
   const bool rows = g.rows_engine && rows_engine_on() && engine != GNODE_ENGINE_SIMT && gemm_k128_rows_supported(g);
   const bool tc = engine != GNODE_ENGINE_SIMT && gemm_nt_tc_supported(g);
   GN_PROF(s, 2.0 * g.M * g.N * g.K, 4.0 * ((double)g.M * g.K + (double)g.N * g.K + (double)g.M * g.N * (g.base ? 2 : 1)),
-          "gemm_nt[%s] N=%d K=%d", rows ? "k128 rows" : wide ? "k128" : (tc ? "tcgen05" : "ffma"), g.N, g.K);
+          "gemm_nt[%s] N=%d K=%d", rows ? "k128 rows" : (tc ? "tcgen05" : "ffma"), g.N, g.K);
   if (engine == GNODE_ENGINE_SIMT) return gemm_nt_simt(g, s);
   if (rows) return gemm_k128_rows(g, s);
-  if (wide) return gemm_k128(g, s);
   if (gemm_nt_tc_supported(g)) return gemm_nt_tc(g, s);
   if (engine == GNODE_ENGINE_TC) {
     set_error("gemm_nt: shape M=%lld N=%d K=%d not supported by the tcgen05 engine", (long long)g.M, g.N, g.K);
@@ -111,7 +104,9 @@ extern "C" int gnode_gemm_tn(const float* A, int64_t lda, const float* B, int64_
 }
 
 // The K = 128 wide-output engine on its own (gemm_k128.cu; parity tests).  B: row-major [n, 128].
-extern "C" size_t gnode_gemm_k128_workspace_bytes(int32_t n) { return align_up(gemm_k128_image_floats(n) * sizeof(float)); }
+extern "C" size_t gnode_gemm_k128_workspace_bytes(int32_t n) {
+  return align_up(gemm_k128_image_floats(n) * sizeof(float)) + align_up(presplit_floats(n, 128) * sizeof(float));
+}
 
 extern "C" int gnode_gemm_k128(const float* A, const float* B, float* C, int64_t ldc, int64_t m, int32_t n, const float* bias,
                                float bias_scale, const float* base, int64_t ldbase, float base_scale, const float* base2,
@@ -128,5 +123,10 @@ extern "C" int gnode_gemm_k128(const float* A, const float* B, float* C, int64_t
   q.base2 = base2; q.ldbase2 = ldbase2; q.scale = scale; q.Bchain = img;
   GN_ARG(gemm_k128_supported(q), "gnode_gemm_k128: operand A must be 16-byte aligned");
   if (rows_engine_on() && gemm_k128_rows_supported(q)) return gemm_k128_rows(q, s);   // dense rows, one base term
-  return gemm_k128(q, s);
+  // every other shape (two base terms, strided rows, N > 400): the general tcgen05 engine
+  float* planes = a.take<float>(presplit_floats(n, 128));
+  GN_ARENA_OK(a, "gnode_gemm_k128");
+  GN_TRY(presplit_weights(B, n, 128, 128, planes, s));
+  q.Bsplit = planes; q.Bchain = nullptr;
+  return gemm_nt(q, s);
 }

@@ -1,24 +1,15 @@
 // NT contraction with a 2H = 128 wide reduction and a WIDE, arbitrarily aligned output (sm_100a, tcgen05):
 //
-//   C[m, n] = base_scale * base[m, n] + base2[m, n] + scale * ( sum_k A[m, k] B[n, k] + bias_scale * bias[n] )
+//   C[m, n] = base_scale * base[m, n] + scale * ( sum_k A[m, k] B[n, k] + bias_scale * bias[n] )
 //
-// This is the shape of every D-wide projection of the folded integrator (fold.cu): y_1 = y + C @ w3cat^T + b3, the
-// dopri5 error / dense-output projections, dL/dy = G + GZ @ w1cat.  N = D (399: rows 4-byte aligned only), K = 128, so
-// the kernel is all epilogue: 1.44 GB of base + output traffic against 0.2 GB of operand.  The general engine
-// (gemm_tc.cu) runs such a tile with four epilogue warps and one 32 x 32 chunk of base loads in flight each (16 KB per
-// SM) and is latency bound at 1.8 TB/s.  Here a CTA owns a 128-row block and every worker warp moves output:
-//
-//   * the A tile [128 x 128] is loaded once, coalesced, into the UMMA operand layout and is read in place by
-//     tcgen05.mma.kind::tf32; the three-term product of the chain kernels (chain_common.cuh: tile residual as a bf16
-//     operand in tensor memory, weight images streamed per K block of 16) gives fp32-grade accuracy without a
-//     converted copy;
-//   * the output is produced in chunks of 80 columns; the accumulator is double buffered in tensor memory so that the
-//     MMAs of chunk c+1 run under the epilogue of chunk c;
-//   * the epilogue of a chunk transposes 40 columns at a time through shared memory (lane = row out of TMEM, then
-//     lane = column), so that global loads of base and stores of C are coalesced along a row, 20 independent elements
-//     per thread in flight, requested before the transposition.
-//
-//   warp 0 weight-image producer, warp 1 TMEM alloc + MMA issue, warps 2-9 workers.  Two CTAs per SM.
+// This is the shape of the D-wide projections of the folded integrator (fold.cu): y_1 = y + C @ w3cat^T + b3.  N = D
+// (399: rows 4-byte aligned only), K = 128, so the kernel is all epilogue: 1.44 GB of base + output traffic against
+// 0.2 GB of operand.  The A tile [128 x 128] is loaded once, coalesced, into the UMMA operand layout and read in place by
+// tcgen05.mma.kind::tf32; the three-term product of the chain kernels (chain_common.cuh: tile residual as a bf16
+// operand in tensor memory, weight images streamed per K block of 16) gives fp32-grade accuracy without a converted
+// copy.  (A column-chunked predecessor of the row-major kernel below -- 80-column accumulator chunks, transposed
+// epilogue -- measured the same as the general engine of gemm_tc.cu and was removed in round 2; shapes the row-major
+// kernel does not take go to gemm_tc.cu.)
 #include <cstdlib>
 
 #include "chain_common.cuh"
@@ -28,19 +19,8 @@ namespace k128 {
 using namespace chain;
 
 constexpr int NCH = 80;                               // output columns per accumulator chunk
-constexpr int HALF = NCH / 2;                         // columns per transposition pass
-constexpr int STG_PITCH = TM + 1;                     // staging [col][row] pitch (odd: conflict-free both ways)
-constexpr int STG_BYTES = HALF * STG_PITCH * 4;       // 20640
 constexpr int KSTAGE = stage_bytes(NCH);              // 12960 bytes per K block of 16
 constexpr int NKB = W2H / KB16;                       // 8
-constexpr int RING = 2;
-constexpr int T_OFF = 0, B_OFF = t_bytes_of(TM), S_OFF = B_OFF + RING * KSTAGE;
-constexpr int SMEM = S_OFF + STG_BYTES;               // 66048 + 25920 + 20640 = 112608: two CTAs per SM
-constexpr int ACC0 = 0, ACC1 = 80, ALO = 160;         // TMEM columns: two accumulators, residual operand (64)
-
-#ifdef K128_TRACE
-__device__ long long g_k128_trace[128];
-#endif
 
 struct Args {
   const float* A; const float* img;                   // A [M, 128] dense rows; chunked weight image
@@ -53,199 +33,6 @@ struct Args {
   int* status;
   int dev_flags;   // K128_TRACE builds: bit 0 = weight producer fetches half of every stage (timing experiment)
 };
-
-__global__ void __launch_bounds__(THREADS, 2) k_gemm_k128(const Args a) {
-  extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ __align__(8) uint64_t bar_b_full[RING];
-  __shared__ __align__(8) uint64_t bar_b_empty[RING];
-  __shared__ __align__(8) uint64_t bar_a_ready;
-  __shared__ __align__(8) uint64_t bar_acc_full[2];
-  __shared__ __align__(8) uint64_t bar_acc_empty[2];
-  __shared__ uint32_t tmem_holder;
-  __shared__ int dead_flag;
-
-  const int tid = threadIdx.x;
-  const int warp = tid >> 5, lane = tid & 31;
-  int* const status = a.status;
-  volatile int* dead = &dead_flag;
-  uint8_t* const T = smem + T_OFF;
-  const uint32_t smem_base = smem_u32(smem);
-  const int64_t m_tiles = (a.M + TM - 1) / TM;
-  const int n_chunks = a.n_chunks;
-  constexpr int lbo_t = lbo_t_of(TM);
-
-  if (tid == 0) {
-    dead_flag = 0;
-    for (int s = 0; s < RING; ++s) { mbar_init(smem_u32(&bar_b_full[s]), 1); mbar_init(smem_u32(&bar_b_empty[s]), 1); }
-    mbar_init(smem_u32(&bar_a_ready), WORKERS / 32);
-    for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(&bar_acc_full[s]), 1); mbar_init(smem_u32(&bar_acc_empty[s]), WORKERS / 32); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_holder)), "r"((uint32_t)TMEM_COLS));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem_base = tmem_holder;
-
-  if (warp == 0) {
-    // =========================== weight-image producer ===========================
-    if (lane == 0) {
-      uint32_t s = 0, ph = 0;
-      bool first_lap = true;
-      const uint8_t* img = reinterpret_cast<const uint8_t*>(a.img);
-      for (int64_t t = blockIdx.x; t < m_tiles; t += gridDim.x) {
-        for (int c = 0; c < n_chunks; ++c) {
-          for (int kb = 0; kb < NKB; ++kb) {
-            if (!first_lap) wait_bar(smem_u32(&bar_b_empty[s]), ph ^ 1u, dead, status, 41);
-            const uint32_t bar = smem_u32(&bar_b_full[s]);
-            mbar_expect_tx(bar, KSTAGE);
-            bulk_load_1d(smem_base + B_OFF + s * KSTAGE, img + ((size_t)c * NKB + kb) * KSTAGE, KSTAGE, bar);
-            if (++s == (uint32_t)RING) { s = 0; ph ^= 1u; first_lap = false; }
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // =========================== MMA issuer ===========================
-    uint32_t pa = 0, sb = 0, pb = 0, use[2] = {0u, 0u};
-    for (int64_t t = blockIdx.x; t < m_tiles; t += gridDim.x) {
-      wait_bar(smem_u32(&bar_a_ready), pa, dead, status, 43);        // A tile + residual operand in place
-      pa ^= 1u;
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      for (int c = 0; c < n_chunks; ++c) {
-        const int ab = c & 1;
-        if (use[ab] > 0) wait_bar(smem_u32(&bar_acc_empty[ab]), (use[ab] - 1) & 1u, dead, status, 44);   // epilogue drained it
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        ++use[ab];
-        for (int kb = 0; kb < NKB; ++kb) {
-          wait_bar(smem_u32(&bar_b_full[sb]), pb, dead, status, 42);
-          if (lane == 0) {
-            issue_kblock(tmem_base + (ab ? ACC1 : ACC0), tmem_base + ALO, smem_base + T_OFF, (uint32_t)lbo_t,
-                         smem_base + B_OFF + sb * KSTAGE, NCH, kb, kb == 0);
-            umma_commit(smem_u32(&bar_b_empty[sb]));
-            if (kb == NKB - 1) umma_commit(smem_u32(&bar_acc_full[ab]));
-          }
-          __syncwarp();
-          if (++sb == (uint32_t)RING) { sb = 0; pb ^= 1u; }
-        }
-      }
-    }
-  } else {
-    // =========================== workers ===========================
-    const int wt = tid - 64;
-    const int cw = warp - 2;
-    const int eq = warp & 3, ehf = cw >> 2;            // TMEM lane quadrant, which 20 of the 40 columns of a pass
-    const int erow = 32 * eq + lane;
-    float* const stg = reinterpret_cast<float*>(smem + S_OFF);
-    uint32_t use[2] = {0u, 0u};
-    const int N = a.N;
-    const float scale = a.scale, bias_scale = a.bias_scale, base_scale = a.base_scale;
-    for (int64_t t = blockIdx.x; t < m_tiles; t += gridDim.x) {
-      const int64_t m0 = t * TM;
-      const int nr = (int)((a.M - m0 < TM) ? (a.M - m0) : TM);
-#ifdef K128_TRACE
-      if (blockIdx.x == 0 && wt == 0 && t == blockIdx.x + 2 * (int64_t)gridDim.x) g_k128_trace[0] = clock64();
-#endif
-      // ---- A tile: coalesced rows -> operand layout (rows >= nr: zeros) ----
-#pragma unroll 4
-      for (int idx = wt; idx < TM * NCHUNK; idx += WORKERS) {
-        const int r = idx >> 5, c4 = idx & 31;
-        const float4 v = (r < nr) ? __ldg(reinterpret_cast<const float4*>(a.A + (size_t)(m0 + r) * W2H + 4 * c4)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        *reinterpret_cast<float4*>(T + (size_t)c4 * lbo_t + r * 16) = v;
-      }
-      worker_sync_w();
-#ifdef K128_TRACE
-      if (blockIdx.x == 0 && wt == 0 && t == blockIdx.x + 2 * (int64_t)gridDim.x) g_k128_trace[1] = clock64();
-#endif
-      residual_to_tmem(T, lbo_t, TM, tmem_base, eq, lane, 16 * ehf, 0, ALO);
-      residual_to_tmem(T, lbo_t, TM, tmem_base, eq, lane, 16 * ehf + 8, 0, ALO);
-      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&bar_a_ready));
-
-      // base values of this thread's (row, column) elements of a pass: 20 per thread, requested ONE PASS AHEAD so that
-      // the HBM latency runs under the previous pass (two passes = 40 KB per CTA in flight)
-      constexpr int EPT = TM * HALF / WORKERS;
-      const int total = nr * HALF;
-      auto load_base = [&](int c_, int hp_, float (&bs_)[EPT]) {
-        const int n0_ = c_ * NCH + hp_ * HALF;
-#pragma unroll
-        for (int u = 0; u < EPT; ++u) {
-          const int idx = wt + u * WORKERS, row = idx / HALF, col = n0_ + idx % HALF;
-          bs_[u] = (idx < total && col < N && a.base) ? __ldg(a.base + (size_t)(m0 + row) * a.ldbase + col) : 0.f;
-        }
-      };
-#ifdef K128_TRACE
-#define KT(i) do { if (blockIdx.x == 0 && wt == 0 && t == blockIdx.x + 2 * (int64_t)gridDim.x) g_k128_trace[(i)] = clock64(); } while (0)
-#else
-#define KT(i) do { } while (0)
-#endif
-      KT(2);
-      for (int c = 0; c < n_chunks; ++c) {
-        const int ab = c & 1;
-        KT(3 + 8 * c);
-        wait_bar(smem_u32(&bar_acc_full[ab]), use[ab] & 1u, dead, status, 45);
-        ++use[ab];
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t acc = (uint32_t)(ab ? ACC1 : ACC0);
-#pragma unroll
-        for (int hp = 0; hp < 2; ++hp) {
-          const int n0 = c * NCH + hp * HALF;
-          float bs[EPT];
-          load_base(c, hp, bs);
-          KT(4 + 8 * c + 4 * hp + 0);
-          // ---- TMEM (lane = row) -> staging[col][row]: this warp's 20 columns of the pass ----
-          {
-            const uint32_t taddr = tmem_base + ((uint32_t)(32 * eq) << 16) + acc + (uint32_t)(HALF * hp + 20 * ehf);
-            uint32_t r[20];
-            asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-                         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-                           "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-                         : "r"(taddr));
-            asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
-                         : "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19])
-                         : "r"(taddr + 16u));
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-            for (int j = 0; j < 20; ++j) stg[(20 * ehf + j) * STG_PITCH + erow] = __uint_as_float(r[j]);
-          }
-          if (hp == 1) {
-            // the accumulator is drained: the MMAs of chunk c + 2 may overwrite it
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(&bar_acc_empty[ab]));
-          }
-          KT(4 + 8 * c + 4 * hp + 1);
-          worker_sync();
-          KT(4 + 8 * c + 4 * hp + 2);
-          // ---- coalesced pass over (row, 40 columns): C = base terms + scale * (acc + bias) ----
-#pragma unroll
-          for (int u = 0; u < EPT; ++u) {
-            const int idx = wt + u * WORKERS, row = idx / HALF, cl = idx % HALF, col = n0 + cl;
-            if (idx < total && col < N) {
-              const float bv = a.bias ? bias_scale * __ldg(a.bias + col) : 0.f;
-              float v = base_scale * bs[u] + scale * (stg[cl * STG_PITCH + row] + bv);
-              if (a.base2) v += __ldg(a.base2 + (size_t)(m0 + row) * a.ldbase2 + col);
-              a.C[(size_t)(m0 + row) * a.ldc + col] = v;
-            }
-          }
-          KT(4 + 8 * c + 4 * hp + 3);
-          worker_sync();        // staging is rewritten by the next pass
-        }
-      }
-    }
-  }
-
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS));
-  }
-}
 
 // chunked weight image: chunk c holds rows [80 c, 80 c + 80) of W [n x 128] (zeros beyond n), each chunk in the chain
 // format (chain_common.cuh) with one stage per K block of 16
@@ -595,9 +382,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_k128_rows(const k128::Args
 
 namespace tc { int* status_ptr(); }
 #ifdef K128_TRACE
-extern "C" int gnode_k128_trace(long long* out128) {
-  return (int)cudaMemcpyFromSymbol(out128, k128::g_k128_trace, sizeof(long long) * 128);
-}
 extern "C" int gnode_k128r_trace(long long* out128) {
   return (int)cudaMemcpyFromSymbol(out128, k128r::g_k128r_trace, sizeof(long long) * 128);
 }
@@ -643,10 +427,8 @@ int gemm_k128_rows(const GemmNT& g, cudaStream_t s) {
   if (!status_dev) { set_error("gemm_k128_rows: status symbol unavailable"); return GNODE_ERR_CUDA; }
   k128::Args a{};
   k128_args(g, status_dev, a);
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (first_use_on_device(reinterpret_cast<const void*>(&k128r::k_gemm_k128_rows))) {
     GN_CUDA(cudaFuncSetAttribute(k128r::k_gemm_k128_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, k128r::SMEM));
-    attr_set = true;
   }
   const int64_t m_tiles = (g.M + chain::TM - 1) / chain::TM;
   unsigned grid = (unsigned)(m_tiles < kNumSMs ? m_tiles : kNumSMs);
@@ -654,24 +436,6 @@ int gemm_k128_rows(const GemmNT& g, cudaStream_t s) {
   { const char* e = std::getenv("K128_GRID"); if (e && atoi(e) > 0 && (unsigned)atoi(e) < grid) grid = (unsigned)atoi(e); }
 #endif
   k128r::k_gemm_k128_rows<<<grid, k128r::NTHREADS, k128r::SMEM, s>>>(a);
-  GN_LAUNCHED();
-  return GNODE_OK;
-}
-
-int gemm_k128(const GemmNT& g, cudaStream_t s) {
-  int* status_dev = tc::status_ptr();
-  if (!status_dev) { set_error("gemm_k128: status symbol unavailable"); return GNODE_ERR_CUDA; }
-  k128::Args a{};
-  k128_args(g, status_dev, a);
-  static bool attr_set = false;
-  if (!attr_set) {
-    GN_CUDA(cudaFuncSetAttribute(k128::k_gemm_k128, cudaFuncAttributeMaxDynamicSharedMemorySize, k128::SMEM));
-    GN_CUDA(cudaFuncSetAttribute(k128::k_gemm_k128, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    attr_set = true;
-  }
-  const int64_t m_tiles = (g.M + chain::TM - 1) / chain::TM;
-  const unsigned grid = (unsigned)(m_tiles < 2 * kNumSMs ? m_tiles : 2 * kNumSMs);
-  k128::k_gemm_k128<<<grid, chain::THREADS, k128::SMEM, s>>>(a);
   GN_LAUNCHED();
   return GNODE_OK;
 }

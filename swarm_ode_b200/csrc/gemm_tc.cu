@@ -445,9 +445,20 @@ EncodeTiledFn encode_fn() {
 
 __device__ int g_tc_status_word = 0;   // barrier-timeout status of the tcgen05 kernels (0 = ok)
 int* status_ptr() {
-  static int* p = nullptr;
-  if (!p) cudaGetSymbolAddress(reinterpret_cast<void**>(&p), g_tc_status_word);
-  return p;
+  // the symbol has one instance (and one address) per device: cache per device ordinal, not per process
+  constexpr int kMaxDev = 64;
+  static int* cache[kMaxDev] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+  if (dev < 0 || dev >= kMaxDev) {
+    int* p = nullptr;
+    return cudaGetSymbolAddress(reinterpret_cast<void**>(&p), g_tc_status_word) == cudaSuccess ? p : nullptr;
+  }
+  if (!cache[dev]) {
+    int* p = nullptr;
+    if (cudaGetSymbolAddress(reinterpret_cast<void**>(&p), g_tc_status_word) == cudaSuccess) cache[dev] = p;
+  }
+  return cache[dev];
 }
 
 }  // namespace tc
@@ -517,10 +528,8 @@ int gemm_nt_tc(const GemmNT& g, cudaStream_t s) {
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("gemm_nt_tc: cuTensorMapEncodeTiled failed (%d)", (int)r); return GNODE_ERR_CUDA; }
   }
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (first_use_on_device(reinterpret_cast<const void*>(&tc::k_gemm_tc))) {
     GN_CUDA(cudaFuncSetAttribute(tc::k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(225 * 1024)));
-    attr_set = true;
   }
   if (M_tc > 0) {
     const int64_t total = a.m_tiles * a.n_tiles;
@@ -551,6 +560,16 @@ int gemm_tc_status(cudaStream_t s, int* out) {
 }
 
 }  // namespace gnode
+
+// Enqueues (no synchronisation) a copy of the tcgen05 status word of the current device into `host_word` (pinned host
+// memory): the deferred counterpart of gnode_tc_status for hot paths that must not block.
+extern "C" int gnode_tc_status_async(int32_t* host_word, gnode_stream_t stream) {
+  GN_ARG(host_word != nullptr, "gnode_tc_status_async: host_word is null");
+  int* status_dev = gnode::tc::status_ptr();
+  if (!status_dev) { gnode::set_error("gnode_tc_status_async: status symbol unavailable"); return GNODE_ERR_CUDA; }
+  GN_CUDA(cudaMemcpyAsync(host_word, status_dev, sizeof(int), cudaMemcpyDeviceToHost, static_cast<cudaStream_t>(stream)));
+  return GNODE_OK;
+}
 
 // Synchronises the stream and reports whether any tcgen05 kernel hit a barrier timeout since the last
 // call (0 = healthy).  Meant for tests / debugging; the hot path never calls it.

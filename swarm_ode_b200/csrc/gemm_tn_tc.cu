@@ -365,10 +365,8 @@ int gemm_tn_tc(const GemmTN& g, float* partials, cudaStream_t s) {
   if (n_raw < 2) { set_error("gemm_tn_tc: tile does not fit in shared memory"); return GNODE_ERR_ARG; }
   a.n_raw = n_raw;
   const size_t smem = n_raw * raw_stage + tctn::N_OP * op_stage;
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (first_use_on_device(reinterpret_cast<const void*>(&tctn::k_gemm_tn_tc))) {
     GN_CUDA(cudaFuncSetAttribute(tctn::k_gemm_tn_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(225 * 1024)));
-    attr_set = true;
   }
   tctn::k_gemm_tn_tc<<<p.grid, tctn::THREADS, smem, s>>>(a);
   GN_LAUNCHED();

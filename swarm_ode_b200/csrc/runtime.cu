@@ -2,6 +2,9 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <mutex>
+#include <set>
+#include <utility>
 
 #include "common.cuh"
 
@@ -22,6 +25,17 @@ void set_error(const char* fmt, ...) {
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 int current_engine() { return g_engine.load(std::memory_order_relaxed); }
 int current_fold() { return g_fold.load(std::memory_order_relaxed); }
+
+// Per-device one-time setup (cudaFuncSetAttribute and friends are per device, not per process): true exactly once for
+// every (key, current device) pair.
+bool first_use_on_device(const void* key) {
+  static std::mutex mu;
+  static std::set<std::pair<const void*, int>> seen;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return true;
+  std::lock_guard<std::mutex> lk(mu);
+  return seen.insert({key, dev}).second;
+}
 }  // namespace gnode
 
 extern "C" const char* gnode_last_error(void) { return gnode::g_err; }

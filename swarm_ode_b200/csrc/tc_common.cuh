@@ -7,7 +7,16 @@
 namespace gnode {
 namespace tc {
 
-constexpr uint32_t SPIN_LIMIT = 1u << 22;
+// Barrier waits are bounded in TIME (%globaltimer), not in polls: a slow clock, a profiler replay or time slicing must
+// not turn a healthy wait into a spurious timeout.  A wait that does expire flags the status word (surfaced by
+// gnode_tc_status and by the deferred checks of the Python layer) and the kernel winds down.
+constexpr uint64_t WAIT_LIMIT_NS = 4000000000ull;   // 4 s
+constexpr uint32_t FAST_POLLS = 2048;               // polls before the clock is consulted at all
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -35,8 +44,13 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t addr, uint32_t parity) {
 }
 // bounded wait: returns false (and flags the status word) on timeout
 __device__ __forceinline__ bool mbar_wait(uint32_t addr, uint32_t parity, int* status, int code) {
-  for (uint32_t i = 0; i < SPIN_LIMIT; ++i)
+  for (uint32_t i = 0; i < FAST_POLLS; ++i)
     if (mbar_try_wait(addr, parity)) return true;
+  const uint64_t t0 = globaltimer_ns();
+  do {
+    for (uint32_t i = 0; i < 256; ++i)
+      if (mbar_try_wait(addr, parity)) return true;
+  } while (globaltimer_ns() - t0 < WAIT_LIMIT_NS);
   if (status) atomicExch(status, code);
   return false;
 }

@@ -97,34 +97,53 @@ class CSRGraph:
         self.poll(wait=True)
         # this call gives the verdict for the graph: drop its deferred checks so that they do not raise again later
         _PENDING[:] = [c for c in _PENDING if not (isinstance(c, _TileCheck) and c.graph is self)]
-        if self.tile_err is not None and int(self.tile_err.item()) != 0:
-            raise _lib.GnodeError("an edge leaves its whole-graph tile: batch.ptr does not describe a disjoint union "
-                                  "of the graphs in edge_index")
+        if self.tile_err is not None:
+            _raise_tile_error(int(self.tile_err.item()), deferred=False)
+        _lib.tc_check(self.device)
 
     def schedule_tile_check(self) -> None:
-        """Called after the graph-resident kernels ran: ship the tile error flag to pinned memory without blocking;
-        a later poll_pending() raises if an edge was found outside its tile."""
+        """Called after the graph-resident kernels ran: ship the tile error flag and the tcgen05 barrier status word to
+        pinned memory without blocking; a later poll_pending() raises if an edge was found outside its tile, a graph
+        exceeded the announced tile capacity, or a barrier wait expired.  Completed checks are looked at here (loops
+        that reuse one batch never reach csr_for's cache-miss poll), and a graph keeps at most ONE outstanding check."""
+        poll_pending()
         if self.tile_err is None:
             return
-        chk = _TileCheck(self)
-        _PENDING.append(chk)
+        _PENDING[:] = [c for c in _PENDING if not (isinstance(c, _TileCheck) and c.graph is self)]
+        _PENDING.append(_TileCheck(self))
+
+
+def _raise_tile_error(code: int, deferred: bool) -> None:
+    tail = " (deferred check; results of that call are invalid)" if deferred else ""
+    if code == 2:
+        raise _lib.GnodeError("a graph of the batch has more nodes than Batch.max_graph_nodes announced: the whole-graph "
+                              "tiles could not be built and the integrator produced nothing" + tail)
+    if code != 0:
+        raise _lib.GnodeError("an edge leaves its whole-graph tile: batch.ptr does not describe a disjoint union of "
+                              "the graphs in edge_index" + tail)
 
 
 class _TileCheck:
     def __init__(self, g: "CSRGraph"):
         self.graph = g
         dev = g.device
-        self.host = torch.empty(1, dtype=torch.int32, pin_memory=True)
-        self.host.copy_(g.tile_err, non_blocking=True)
+        self.host = torch.zeros(2, dtype=torch.int32, pin_memory=True)     # [tile error flag, tcgen05 status word]
+        stream = torch.cuda.current_stream(dev)
+        self.host[:1].copy_(g.tile_err, non_blocking=True)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().gnode_tc_status_async(self.host.data_ptr() + 4, stream.cuda_stream), "gnode_tc_status_async")
         self.event = torch.cuda.Event()
-        self.event.record(torch.cuda.current_stream(dev))
+        self.event.record(stream)
 
     def poll(self) -> bool:
         if not self.event.query():
             return False
-        if int(self.host[0]) != 0:
-            raise _lib.GnodeError("an edge leaves its whole-graph tile: batch.ptr does not describe a disjoint union of "
-                                  "the graphs in edge_index (deferred check; results of that call are invalid)")
+        _raise_tile_error(int(self.host[0]), deferred=True)
+        if int(self.host[1]) != 0:
+            with torch.cuda.device(self.graph.device):      # read-and-clear, so that the next call starts healthy
+                _lib.lib().gnode_tc_status(_lib.stream_ptr(self.graph.device))
+            raise _lib.GnodeError(f"a tcgen05 kernel gave up on a barrier wait (code {int(self.host[1])}): the results of "
+                                  "that call are invalid (deferred check)")
         return True
 
 
@@ -156,7 +175,10 @@ def csr_for(edge_index: torch.Tensor, num_nodes: int, holder: Optional[object] =
     """CSR of ``edge_index``; cached on ``holder`` (e.g. the batch object) and in a small LRU keyed by
     the tensor's storage, shape and version counter.  Every cache entry keeps the keyed tensor alive,
     so its address cannot be recycled for a different edge list while the entry exists."""
-    key = (edge_index.data_ptr(), tuple(edge_index.shape), edge_index._version, int(num_nodes), str(edge_index.device))
+    # the tiling is part of the graph: the same edge list with and without `ptr` (or with another announced capacity)
+    # are different entries
+    key = (edge_index.data_ptr(), tuple(edge_index.shape), edge_index._version, int(num_nodes), str(edge_index.device),
+           graph_ptr.data_ptr() if graph_ptr is not None else 0, int(max_graph_nodes) if max_graph_nodes is not None else 0)
     if holder is not None:
         cached = getattr(holder, "__dict__", {}).get("_gnode_csr")
         if cached is not None and cached[0] == key:

@@ -177,7 +177,10 @@ def _fixed_forward(ctx, y0, graph: CSRGraph, method: int, t_host: Tuple[float, .
         if any(ctx.needs_input_grad) and T >= 2:   # (also true when called from _IntegrateDecodeFn: same ctx)
             nbytes = int(L.gnode_integrate_fixed_save_bytes(N, D, H, method, T))
             if nbytes > 0 and _save_fits(nbytes, y0.device):
-                save = torch.empty(nbytes, dtype=torch.uint8, device=y0.device)
+                try:
+                    save = torch.empty(nbytes, dtype=torch.uint8, device=y0.device)
+                except torch.OutOfMemoryError:      # a nearly full device: the backward recomputes the stages instead
+                    save = None
         with torch.cuda.device(y0.device):
             _lib.check(L.gnode_integrate_fixed(graph.ref(), C.byref(p), method, _lib.ptr(y0), tarr, T, _lib.ptr(sol),
                                                _lib.ptr(save), save.numel() if save is not None else 0,

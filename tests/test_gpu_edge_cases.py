@@ -169,3 +169,64 @@ def test_tiles_build_matches_greedy_packing(cuda, n_graphs, lo, hi):
     want = _greedy_tiles(ptr.tolist(), tm=csr.tile_rows)
     assert t[0] == len(want) - 1
     assert t[1:1 + len(want)] == want
+
+
+def test_understated_max_graph_nodes_is_reported(cuda):
+    """A batch whose host-side ``max_graph_nodes`` is smaller than its largest graph (a stale or hand-made PyG-style
+    batch): the tiles cannot be built (tiles[0] = -1), the chain kernels process nothing and flag it; validate() and
+    the deferred check raise instead of handing back an uninitialised solution."""
+    batch = S.synthetic.dense_batch(3, num_agents=140, node_dim_=32, seed=5)           # 140-node graphs
+    model = S.GraphODE(32, 3, 2, hidden_dim=64, ode_solver="rk4").to(cuda)
+    gb = batch.to(cuda)
+    gb.max_graph_nodes = 100                                 # understated: 128-row tiles cannot hold a 140-node graph
+    S.graph.poll_pending()
+    with torch.no_grad():
+        model(gb, torch.tensor([0.0, 1.0], device=cuda))
+    with pytest.raises(S.GnodeError, match="max_graph_nodes"):
+        S.graph.csr_for(gb.edge_index, gb.x.shape[0], holder=gb).validate()
+    # the deferred path: the flag travels with the next schedule / poll
+    gb2 = batch.to(cuda)
+    gb2.max_graph_nodes = 100
+    with torch.no_grad():
+        model(gb2, torch.tensor([0.0, 1.0], device=cuda))
+    torch.cuda.synchronize()
+    with pytest.raises(S.GnodeError, match="max_graph_nodes"):
+        S.graph.poll_pending()
+
+
+def test_pending_checks_do_not_grow_when_a_batch_is_reused(cuda):
+    """Loops that reuse one batch (evaluation, predict_trajectory roll-outs) keep at most one outstanding deferred check."""
+    batch, _ = S.synthetic.warehouse_batch(3, num_agvs=3, num_pickers=2, seed=6)
+    model = S.GraphODE(batch.x.shape[1], 3, 2, hidden_dim=64, ode_solver="euler").to(cuda)
+    gb = batch.to(cuda)
+    t = torch.tensor([0.0, 1.0], device=cuda)
+    torch.cuda.synchronize()
+    S.graph.poll_pending()
+    base = len(S.graph._PENDING)
+    with torch.no_grad():
+        for _ in range(20):
+            model(gb, t)
+    assert len(S.graph._PENDING) <= base + 2
+    torch.cuda.synchronize()
+    S.graph.poll_pending()
+
+
+def test_second_device_smoke():
+    """Per-device state (max dynamic shared memory attribute, status word address) is keyed by device: the same
+    process can run the tcgen05 path on cuda:1 after cuda:0."""
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs two CUDA devices")
+    batch, _ = S.synthetic.warehouse_batch(4, num_agvs=12, num_pickers=7, seed=7)
+    t = torch.tensor([0.0, 1.0])
+    outs = []
+    for d in (0, 1):
+        dev = torch.device("cuda", d)
+        model = S.GraphODE(batch.x.shape[1], 12, 7, hidden_dim=64, ode_solver="rk4")
+        S.synthetic.init_weights(model, seed=1, conv3_scale=0.1)
+        model = model.to(dev)
+        out = model(batch.to(dev), t.to(dev))
+        (out["trajectories"][-1] ** 2).mean().backward()
+        from swarm_ode_b200 import _lib
+        _lib.tc_check(dev)
+        outs.append(out["node_features"].detach().cpu())
+    assert torch.equal(outs[0], outs[1])      # deterministic kernels: bitwise the same on both devices
