@@ -60,6 +60,12 @@ typedef void* gnode_stream_t; /* cudaStream_t */
 #define GNODE_ENGINE_SIMT 1  /* fp32 FFMA everywhere: the parity anchor */
 #define GNODE_ENGINE_TC 2    /* force the tcgen05 path (error if the shape is unsupported) */
 
+/* element type of packed node features (gnode_unpack_features) */
+#define GNODE_PACK_U8 0
+#define GNODE_PACK_I16 1
+#define GNODE_PACK_F16 2
+#define GNODE_PACK_F32 3
+
 const char* gnode_last_error(void);
 int gnode_abi_version(void);
 /* process-wide selection of the GEMM engine (default AUTO); returns the previous value */
@@ -403,6 +409,18 @@ int gnode_mlp_integrate_dopri5_bwd(const gnode_mlp_params* p, const float* y0, i
  * ---------------------------------------------------------------------------------------- */
 int gnode_spatial_edges(const float* pos, int64_t n_snap, int32_t n_agents, float threshold,
                         int32_t* counts, int32_t* edges, gnode_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Lossless narrow transport of a host batch -- `batch.to(device)` of scripts/train_gde.py:475.
+ * The host packs node features in the narrowest type that reproduces every fp32 value exactly
+ * (warehouse observations are small integers) and edge lists as int32; these entry points widen
+ * them on the device into the fp32 `x` / int64 `edge_index` / int64 `batch` of the reference
+ * contract, bit-exact.  src / dst: device memory, 16-byte aligned; n: elements.
+ * ---------------------------------------------------------------------------------------- */
+int gnode_unpack_features(const void* src, int32_t kind /* GNODE_PACK_* */, int64_t n, float* dst, gnode_stream_t stream);
+int gnode_unpack_edges(const int32_t* src, int64_t n, int64_t* dst, gnode_stream_t stream);
+/* batch[i] = index of the graph that owns node i, from the graph offsets ptr [n_graphs + 1] (PyG Batch.batch / Batch.ptr) */
+int gnode_batch_vector(const int64_t* ptr, int64_t n_graphs, int64_t n_nodes, int64_t* batch, gnode_stream_t stream);
 
 #ifdef __cplusplus
 }

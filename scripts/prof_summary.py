@@ -7,6 +7,11 @@
 `launches`: per-kernel-class device time of ONE steady-state step (between two occurrences of the step marker
 kernel, default k_count = the first kernel of the CSR build), from the `--metrics gpu__time_duration.sum` pass.
 `full`: the headline counters of every profiled launch of a `--set full` report (read with `ncu -i ... --page raw`).
+`sass`: per-kernel counts of the Blackwell-specific SASS mnemonics (tcgen05 MMA, tensor-memory loads / stores, TMA / bulk
+copies, mbarrier waits) in the built library, from `cuobjdump -sass` -- the proof that the hot kernels are hand-written
+tcgen05 / TMEM / TMA code and not recompiled mma.sync:
+
+    python scripts/prof_summary.py sass swarm_ode_b200/libgnode_b200.so profiles/sass_summary.txt
 """
 import collections
 import csv
@@ -73,8 +78,52 @@ def full(src, dst):
     print(open(dst).read())
 
 
+SASS_MNEMONICS = ["UTCHMMA", "UTCQMMA", "UTCMMA", "LDTM", "STTM", "UTCBAR", "UTMALDG", "UTMASTG", "UBLKCP", "UBLKPF", "SYNCS",
+                  "HMMA", "FFMA", "LDS", "STS", "LDG", "STG", "BAR"]
+
+
+def sass(lib, dst):
+    txt = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
+    kernels, cur = collections.OrderedDict(), None
+    for line in txt.splitlines():
+        m = re.match(r"\s*Function : (\S+)", line)
+        if m:
+            cur = m.group(1)
+            kernels[cur] = collections.Counter()
+            continue
+        if cur is None:
+            continue
+        m = re.match(r"\s*/\*[0-9a-f]+\*/\s+(?:@!?U?P\d+\s+)?([A-Z][A-Z0-9_]*)", line)
+        if m:
+            op = m.group(1)
+            kernels[cur]["_total"] += 1
+            for mn in SASS_MNEMONICS:
+                if op == mn or op.startswith(mn + "."):
+                    kernels[cur][mn] += 1
+                    break
+            else:
+                kernels[cur][op.split(".")[0]] += 1
+    demangle = subprocess.run(["cu++filt"] + list(kernels), capture_output=True, text=True).stdout.splitlines()
+    names = dict(zip(kernels, demangle)) if len(demangle) == len(kernels) else {k: k for k in kernels}
+    cols = ["UTCHMMA", "UTCQMMA", "LDTM", "STTM", "UTCBAR", "UTMALDG", "UTMASTG", "UBLKCP", "SYNCS", "HMMA", "FFMA"]
+    with open(dst, "w") as out:
+        out.write(f"# cuobjdump -sass {lib}: instruction counts per kernel (sm_100a)\n")
+        out.write("# UTCHMMA / UTCQMMA = tcgen05.mma (kind::tf32 / f16), LDTM / STTM = tcgen05.ld / st (tensor memory), UTCBAR = tcgen05.commit,\n")
+        out.write("# UTMALDG / UTMASTG = TMA tensor load / store, UBLKCP = cp.async.bulk (1-D bulk copy), SYNCS = mbarrier ops, HMMA = mma.sync (none expected)\n\n")
+        out.write(f"{'kernel':70s} " + " ".join(f"{c:>8s}" for c in cols) + f" {'total':>8s}\n")
+        tot = collections.Counter()
+        for k, cnt in sorted(kernels.items(), key=lambda kv: -(kv[1]["UTCHMMA"] + kv[1]["UTCQMMA"] + kv[1]["LDTM"] + kv[1]["UBLKCP"] + kv[1]["UTMALDG"])):
+            nm = clean(names[k])[:70]
+            out.write(f"{nm:70s} " + " ".join(f"{cnt[c]:8d}" for c in cols) + f" {cnt['_total']:8d}\n")
+            tot.update(cnt)
+        out.write(f"\n{'ALL KERNELS (' + str(len(kernels)) + ')':70s} " + " ".join(f"{tot[c]:8d}" for c in cols) + f" {tot['_total']:8d}\n")
+    print(open(dst).read())
+
+
 if __name__ == "__main__":
-    if sys.argv[1] == "launches":
+    if sys.argv[1] == "sass":
+        sass(sys.argv[2], sys.argv[3])
+    elif sys.argv[1] == "launches":
         launches(sys.argv[2], sys.argv[3], *(sys.argv[4:5] or ["k_count"]))
     else:
         full(sys.argv[2], sys.argv[3])

@@ -6,7 +6,7 @@ multi-backend dispatch, no CPU fallback: importing the package is cheap and GPU-
 compute entry point raises unless the extension is built and the tensors live on a CUDA device.
 """
 from ._lib import GnodeError, set_engine, set_fold, launch_count, LIB_PATH  # noqa: F401
-from .data import (Batch, Data, GraphConverter, TrajectoryBatch, build_episode_batch, collate_trajectory_batches,  # noqa: F401
+from .data import (Batch, Data, GraphConverter, PackedBatch, TrajectoryBatch, build_episode_batch, collate_trajectory_batches,  # noqa: F401
                    extract_positions_from_graph, spatial_edges_cuda)
 from .graph import CSRGraph, csr_for  # noqa: F401
 from .modules import GraphODE, GraphODEFunc, ODEFunction, SAGEConv, BoundGraphODEFunc  # noqa: F401
@@ -16,7 +16,7 @@ from . import ops, synthetic  # noqa: F401
 
 __all__ = [
     "GnodeError", "set_engine", "set_fold", "launch_count", "LIB_PATH",
-    "Batch", "Data", "GraphConverter", "TrajectoryBatch", "build_episode_batch", "collate_trajectory_batches",
+    "Batch", "Data", "GraphConverter", "PackedBatch", "TrajectoryBatch", "build_episode_batch", "collate_trajectory_batches",
     "extract_positions_from_graph", "spatial_edges_cuda",
     "CSRGraph", "csr_for",
     "GraphODE", "GraphODEFunc", "ODEFunction", "SAGEConv", "BoundGraphODEFunc",

@@ -106,6 +106,122 @@ class Batch(Data):
 
 
 # ----------------------------------------------------------------------------------------------
+# Lossless narrow transport of a collated batch (host -> device)
+# ----------------------------------------------------------------------------------------------
+_PACK_TYPES = ((torch.uint8, _lib.PACK_U8, "u8"), (torch.int16, _lib.PACK_I16, "i16"), (torch.float16, _lib.PACK_F16, "f16"))
+
+
+def narrowest_exact_dtype(x: torch.Tensor):
+    """``(torch dtype, GNODE_PACK_* code, name)`` of the narrowest type that reproduces every element of the fp32 tensor
+    ``x`` exactly (u8, i16, f16, else f32).  The check is the round trip itself, element by element."""
+    if x.dtype != torch.float32:
+        raise _lib.GnodeError(f"node features must be float32 (got {x.dtype})")
+    finite = bool(torch.isfinite(x).all()) if x.numel() else True
+    if finite:
+        lo, hi = (float(x.min()), float(x.max())) if x.numel() else (0.0, 0.0)
+        for dt, code, name in _PACK_TYPES:
+            if dt == torch.uint8 and (lo < 0.0 or hi > 255.0):
+                continue
+            if dt == torch.int16 and (lo < -32768.0 or hi > 32767.0):
+                continue
+            if dt == torch.float16 and max(abs(lo), abs(hi)) > 65504.0:
+                continue
+            if torch.equal(x.to(dt).to(torch.float32), x) and not (dt != torch.float16 and bool(((x == 0) & torch.signbit(x)).any())):
+                return dt, code, name
+    return torch.float32, _lib.PACK_F32, "f32"
+
+
+class PackedBatch:
+    """A collated batch in its transport format: what ``batch.to(device)`` of the reference (scripts/train_gde.py:475)
+    moves over PCIe, made as small as it can be WITHOUT changing a single bit of what arrives.
+
+    * ``x`` travels in the narrowest type that reproduces every fp32 value exactly (warehouse observations are flags and
+      grid coordinates: u8; the choice is verified element by element when the batch is packed, i.e. at dataset-build
+      time), and is widened to fp32 on the device (``gnode_unpack_features``);
+    * ``edge_index`` travels as int32 (node ids < 2^31) and is widened to int64 (``gnode_unpack_edges``);
+    * ``batch`` is not transported at all: it is a function of ``ptr`` (``gnode_batch_vector``);
+    * ``ptr``, ``is_current_agent`` and the targets travel as they are.
+
+    ``to(device)`` returns an ordinary :class:`Batch` whose tensors are bit-identical to ``batch.to(device)``."""
+
+    def __init__(self, batch: "Batch", next_positions: Optional[torch.Tensor] = None):
+        if batch.x.is_cuda:
+            raise _lib.GnodeError("PackedBatch packs a HOST batch")
+        x = batch.x.contiguous()
+        dt, self.kind, self.kind_name = narrowest_exact_dtype(x)
+        self.x_shape = tuple(x.shape)
+        self.x_packed = x if dt == torch.float32 else x.to(dt)
+        ei = batch.edge_index
+        self.num_nodes = int(x.shape[0])
+        self.edges_int32 = self.num_nodes < 2 ** 31 and (ei.numel() == 0 or (int(ei.min()) >= 0 and int(ei.max()) < 2 ** 31))
+        self.edge_index = ei.to(torch.int32).contiguous() if self.edges_int32 else ei.contiguous()
+        self.ptr = getattr(batch, "ptr", None)
+        self.batch = None if self.ptr is not None else batch.batch      # without offsets the vector itself must travel
+        self.is_current_agent = getattr(batch, "is_current_agent", None)
+        self.num_graphs = getattr(batch, "num_graphs", None)
+        self.max_graph_nodes = getattr(batch, "max_graph_nodes", None)
+        self.next_positions = next_positions
+
+    def _tensors(self):
+        return [t for t in (self.x_packed, self.edge_index, self.ptr, self.batch, self.is_current_agent, self.next_positions)
+                if t is not None]
+
+    @property
+    def nbytes(self) -> int:
+        """Bytes one ``to(device)`` moves over the link."""
+        return sum(t.numel() * t.element_size() for t in self._tensors())
+
+    def pin_memory(self) -> "PackedBatch":
+        for k in ("x_packed", "edge_index", "ptr", "batch", "is_current_agent", "next_positions"):
+            v = getattr(self, k)
+            if v is not None and not v.is_pinned():
+                setattr(self, k, v.pin_memory())
+        return self
+
+    def to(self, device, non_blocking: bool = False):
+        """Upload and widen on ``device``'s current stream.  Returns ``batch`` or ``(batch, next_positions)``."""
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise _lib.GnodeError("PackedBatch.to() targets a CUDA device; libgnode_b200 has no CPU path")
+        L = _lib.lib()
+        with torch.cuda.device(device):
+            s = _lib.stream_ptr(device)
+            xp = self.x_packed.to(device, non_blocking=non_blocking)
+            if self.kind == _lib.PACK_F32:
+                x = xp
+            else:
+                x = torch.empty(self.x_shape, dtype=torch.float32, device=device)
+                _lib.check(L.gnode_unpack_features(_lib.ptr(xp), self.kind, x.numel(), _lib.ptr(x), s), "gnode_unpack_features")
+            ep = self.edge_index.to(device, non_blocking=non_blocking)
+            if self.edges_int32:
+                ei = torch.empty(tuple(ep.shape), dtype=torch.int64, device=device)
+                _lib.check(L.gnode_unpack_edges(_lib.ptr(ep), ep.numel(), _lib.ptr(ei), s), "gnode_unpack_edges")
+            else:
+                ei = ep
+            out = Batch(x=x, edge_index=ei)
+            if self.ptr is not None:
+                out.ptr = self.ptr.to(device, non_blocking=non_blocking)
+                out.batch = torch.empty(self.num_nodes, dtype=torch.int64, device=device)
+                _lib.check(L.gnode_batch_vector(_lib.ptr(out.ptr), out.ptr.numel() - 1, self.num_nodes, _lib.ptr(out.batch), s),
+                           "gnode_batch_vector")
+            else:
+                out.batch = self.batch.to(device, non_blocking=non_blocking)
+            if self.is_current_agent is not None:
+                out.is_current_agent = self.is_current_agent.to(device, non_blocking=non_blocking)
+            if self.num_graphs is not None:
+                out.num_graphs = self.num_graphs
+            if self.max_graph_nodes is not None:
+                out.max_graph_nodes = self.max_graph_nodes
+            # the packed device copies are read by kernels enqueued on this stream: keep the allocator from recycling them
+            # under a different stream before those kernels ran
+            for t in (xp, ep):
+                t.record_stream(torch.cuda.current_stream(device))
+        if self.next_positions is not None:
+            return out, self.next_positions.to(device, non_blocking=non_blocking)
+        return out
+
+
+# ----------------------------------------------------------------------------------------------
 # GraphConverter
 # ----------------------------------------------------------------------------------------------
 def _pair_edges(loc: np.ndarray, threshold: float) -> np.ndarray:
