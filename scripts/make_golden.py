@@ -232,9 +232,95 @@ def golden_hetero():
     print("hetero.npz:", len(out), "arrays")
 
 
+def mac_observation(rng, n_agv, n_pick, n_loc, racks, agv_targets=(), picker_targets=(), grid=(10, 10), p_requested=0.35):
+    """One observation array [n_agv + n_pick, 7 + 4 (n - 1) + 2 n_loc] with the row layout the reference's converter
+    reads (scripts/run_gnode.py:1079-1100): AGV rows [carry, carry_req, toggle, y, x, ty, tx, ...], picker rows
+    [y, x, ty, tx, ...]; the shelf pairs are read from row 0.  `agv_targets` / `picker_targets`: {agent: rack index}."""
+    D = 7 + 4 * (n_agv + n_pick - 1) + 2 * n_loc
+    obs = np.zeros((n_agv + n_pick, D), dtype=np.float32)
+    for a in range(n_agv):
+        obs[a, :3] = rng.integers(0, 2, 3)
+        obs[a, 3:5] = rng.integers(0, grid[0], 2)
+    for p in range(n_pick):
+        obs[n_agv + p, 0:2] = rng.integers(0, grid[0], 2)
+    for a, r in dict(agv_targets).items():
+        obs[a, 5], obs[a, 6] = (racks[r][1], racks[r][0]) if r >= 0 else (grid[0] + 3, grid[1] + 3)   # (ty, tx); -1: off every rack
+    for p, r in dict(picker_targets).items():
+        obs[n_agv + p, 2], obs[n_agv + p, 3] = racks[r][1], racks[r][0]
+    shelf = np.zeros(2 * n_loc, dtype=np.float32)
+    shelf[0::2] = rng.random(n_loc) < 0.8
+    shelf[1::2] = rng.random(n_loc) < p_requested
+    obs[0, 7 + 4 * (n_agv + n_pick - 1):] = shelf
+    obs[1:, 7:] = rng.integers(0, 5, size=(n_agv + n_pick - 1, D - 7))      # other rows' tails are never read by the converter
+    return obs
+
+
+def golden_multi_agent_converter():
+    """tests/golden/multi_agent_converter.npz: the reference's MultiAgentGraphConverter (scripts/run_gnode.py:1040-1326),
+    executed from its source text (the module itself cannot be imported: module-level wandb / gym / argparse code), on
+    synthetic observations -- node features and the six relations per case, and for the inputs the reference's code
+    cannot process, the type of the exception it raises."""
+    import ast
+    from oracle.pyg_ref import RefHeteroData
+    path = os.path.join(REF, "scripts/run_gnode.py")
+    tree = ast.parse(open(path).read())
+    ns = {"np": np, "torch": torch, "HeteroData": RefHeteroData}
+    for node in tree.body:
+        if isinstance(node, ast.ClassDef) and node.name == "MultiAgentGraphConverter":
+            exec(compile(ast.Module(body=[node], type_ignores=[]), path, "exec"), ns)
+    Conv = ns["MultiAgentGraphConverter"]
+    rng = np.random.default_rng(5)
+    out = {}
+
+    def racks_for(n_loc, grid):
+        cells = rng.permutation(grid[0] * grid[1])[:n_loc]
+        return [(int(c % grid[0]) + 1, int(c // grid[0]) + 1, int(g)) for c, g in zip(cells, rng.integers(0, 4, n_loc))]
+
+    def record(tag, conv, obs, racks):
+        out[f"{tag}/obs"] = obs
+        out[f"{tag}/racks"] = np.asarray(racks, dtype=np.int64)
+        try:
+            d = conv._build_graph_from_observation(obs, racks)
+        except Exception as e:  # noqa: BLE001 -- the exception TYPE is the golden value
+            out[f"{tag}/raises"] = np.array(type(e).__name__)
+            return
+        for k in ("agv", "picker", "location"):
+            out[f"{tag}/x/{k}"] = d[k].x.numpy()
+        for et, ei in d.edge_index_dict.items():
+            out[f"{tag}/edge/" + "__".join(et)] = ei.numpy()
+
+    shapes = {"small": (4, 3, 12, (10, 10)), "medium": (19, 9, 160, (25, 22))}
+    for name, (na, npk, nl, grid) in shapes.items():
+        racks = racks_for(nl, grid)
+        record(f"{name}/idle", Conv(na, npk), mac_observation(rng, na, npk, nl, racks, grid=grid), racks)
+        record(f"{name}/one_agv_target", Conv(na, npk), mac_observation(rng, na, npk, nl, racks, agv_targets={1: 2}, grid=grid), racks)
+        record(f"{name}/agv_target_off_rack", Conv(na, npk), mac_observation(rng, na, npk, nl, racks, agv_targets={na - 1: -1}, grid=grid), racks)
+        record(f"{name}/nothing_requested", Conv(na, npk), mac_observation(rng, na, npk, nl, racks, grid=grid, p_requested=0.0), racks)
+        record(f"{name}/two_agv_targets", Conv(na, npk), mac_observation(rng, na, npk, nl, racks, agv_targets={0: 1, 2: 3}, grid=grid), racks)
+        record(f"{name}/picker_target", Conv(na, npk), mac_observation(rng, na, npk, nl, racks, picker_targets={1: 4}, grid=grid), racks)
+        # a REUSED converter: the second call's edges are those of the first observation (stale agent / shelf info)
+        conv = Conv(na, npk)
+        record(f"{name}/reuse_first", conv, mac_observation(rng, na, npk, nl, racks, agv_targets={0: 5}, grid=grid), racks)
+        record(f"{name}/reuse_second", conv, mac_observation(rng, na, npk, nl, racks, grid=grid), racks)
+    # rack entries that are ndarray rows (what h5py hands back): unhashable in position_to_sections.get
+    na, npk, nl, grid = shapes["small"]
+    racks = racks_for(nl, grid)
+    obs = mac_observation(rng, na, npk, nl, racks, grid=grid)
+    out["small/ndarray_racks/obs"], out["small/ndarray_racks/racks"] = obs, np.asarray(racks, dtype=np.int64)
+    try:
+        Conv(na, npk)._build_graph_from_observation(obs, np.asarray(racks))
+    except Exception as e:  # noqa: BLE001
+        out["small/ndarray_racks/raises"] = np.array(type(e).__name__)
+    np.savez_compressed(os.path.join(OUT, "multi_agent_converter.npz"), **out)
+    print("multi_agent_converter.npz:", len(out), "arrays;", sorted(k for k in out if k.endswith("raises")),
+          [str(out[k]) for k in sorted(out) if k.endswith("raises")])
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["converter", "graph_ode", "hetero"]
+    which = sys.argv[1:] or ["converter", "graph_ode", "hetero", "multi_agent_converter"]
+    if "multi_agent_converter" in which:
+        golden_multi_agent_converter()
     if "converter" in which or "graph_ode" in which:
         ref = import_reference_train_gde()
         if "converter" in which:

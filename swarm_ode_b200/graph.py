@@ -175,15 +175,25 @@ def csr_for(edge_index: torch.Tensor, num_nodes: int, holder: Optional[object] =
     """CSR of ``edge_index``; cached on ``holder`` (e.g. the batch object) and in a small LRU keyed by
     the tensor's storage, shape and version counter.  Every cache entry keeps the keyed tensor alive,
     so its address cannot be recycled for a different edge list while the entry exists."""
-    # the tiling is part of the graph: the same edge list with and without `ptr` (or with another announced capacity)
-    # are different entries
-    key = (edge_index.data_ptr(), tuple(edge_index.shape), edge_index._version, int(num_nodes), str(edge_index.device),
-           graph_ptr.data_ptr() if graph_ptr is not None else 0, int(max_graph_nodes) if max_graph_nodes is not None else 0)
+    # the tiling is part of the graph: the same edge list with another `ptr` (or another announced capacity) is a
+    # different entry.  A caller that passes NO offsets accepts whatever entry exists for the edge list (a tiled graph
+    # serves every un-tiled use).
+    base = (edge_index.data_ptr(), tuple(edge_index.shape), edge_index._version, int(num_nodes), str(edge_index.device))
+    key = base + (graph_ptr.data_ptr() if graph_ptr is not None else 0, int(max_graph_nodes) if max_graph_nodes is not None else 0)
+
+    def matches(k):
+        return k == key or (graph_ptr is None and k[:5] == base)
+
     if holder is not None:
         cached = getattr(holder, "__dict__", {}).get("_gnode_csr")
-        if cached is not None and cached[0] == key:
+        if cached is not None and matches(cached[0]):
             return cached[1]
     entry = _CACHE.get(key)
+    if entry is None and graph_ptr is None:
+        for k in reversed(_CACHE):
+            if k[:5] == base:
+                key, entry = k, _CACHE[k]
+                break
     if entry is None or entry[0] is not edge_index and entry[0].data_ptr() != edge_index.data_ptr():
         if validate != "sync":
             poll_pending()

@@ -77,6 +77,38 @@ class HeteroData:
     def node_types(self) -> List[str]:
         return [k for k in self._stores if isinstance(k, str)]
 
+    @classmethod
+    def from_data_list(cls, data_list: "List[HeteroData]") -> "HeteroData":
+        """Disjoint union of many heterogeneous graphs (what ``torch_geometric.data.Batch.from_data_list`` does for
+        ``HeteroData`` [upstream PyG]): node features of every type concatenated, every relation's ``edge_index``
+        shifted by the node counts of the graphs before it, plus ``ptr`` per node type.  One forward of
+        ``HeteroGraphODENetwork`` over the union equals the concatenation of the per-graph forwards (no edge crosses
+        graphs) -- the batched form of the reference's one-graph-per-call use (scripts/run_gnode.py:115-151)."""
+        out = cls()
+        node_types: List[str] = []
+        edge_types: List[tuple] = []
+        for d in data_list:
+            for k in d._stores:
+                (node_types if isinstance(k, str) else edge_types).append(k) if k not in node_types and k not in edge_types else None
+        counts = {nt: [d[nt].num_nodes if nt in d._stores and "x" in d[nt].__dict__["_d"] else 0 for d in data_list] for nt in node_types}
+        for nt in node_types:
+            xs = [d[nt].x for d in data_list if nt in d._stores and "x" in d[nt].__dict__["_d"]]
+            out[nt].x = torch.cat(xs, dim=0)
+            ptr = torch.zeros(len(data_list) + 1, dtype=torch.long)
+            ptr[1:] = torch.cumsum(torch.tensor(counts[nt], dtype=torch.long), 0)
+            out[nt].ptr = ptr
+        for et in edge_types:
+            src, _rel, dst = et
+            parts = []
+            for g, d in enumerate(data_list):
+                if et in d._stores and "edge_index" in d[et].__dict__["_d"]:
+                    ei = d[et].edge_index
+                    off = torch.tensor([[int(out[src].ptr[g])], [int(out[dst].ptr[g])]], dtype=ei.dtype, device=ei.device)
+                    parts.append(ei + off)
+            out[et].edge_index = torch.cat(parts, dim=1) if parts else torch.empty((2, 0), dtype=torch.long)
+        out.num_graphs = len(data_list)
+        return out
+
     def to(self, device, non_blocking: bool = False) -> "HeteroData":
         for s in self._stores.values():
             d = s.__dict__["_d"]
@@ -307,3 +339,154 @@ class HeteroGraphODENetwork(nn.Module):
         return {"agv_q_values": self._head(agv, self.agv_action_head),
                 "picker_q_values": self._head(picker, self.picker_action_head),
                 "agv_embeddings": agv, "picker_embeddings": picker, "location_embeddings": loc}
+
+
+# ----------------------------------------------------------------------------------------------
+# MultiAgentGraphConverter (scripts/run_gnode.py:1040-1326)
+# ----------------------------------------------------------------------------------------------
+class MultiAgentGraphConverter:
+    """Drop-in for the reference's observation -> ``HeteroData`` converter (scripts/run_gnode.py:1040-1326): same
+    constructor, same ``_build_graph_from_observation(observation, rack_locations)``, same node features, the same six
+    relations with the same edges in the same order -- built with vectorised numpy instead of the reference's Python
+    pair loops.  Checked bit for bit against golden vectors produced by the reference's own class
+    (scripts/make_golden.py, tests/test_hetero_converter.py).
+
+    What the reference's code actually does (and this class reproduces, because a drop-in must):
+
+    * ``position_to_sections`` is emptied at the start of every call and refilled only AFTER the edges were built
+      (:1075, :1105-1106), so every section lookup during edge construction returns ``None``:
+      - a picker without a target is connected to every requested shelf (``None == None``, :1256-1270);
+      - an AGV WITH a target is connected to every picker (``agv_target_in_picker_section``, :1310-1314);
+      - two AGVs that both have a target raise ``KeyError`` (``_check_same_rack_group`` indexes the empty dict, :1322);
+    * a picker with a target compares a 3-tuple rack entry with a 2-vector (:1267): ``ValueError`` under numpy >= 2;
+    * ``rack_locations`` entries must be hashable ``(x, y, group)`` tuples (:1263): ndarray rows raise ``TypeError``;
+    * ``_current_agents_info`` / ``_current_shelves_info`` are appended to on every call and never cleared (:1088,
+      :1101), while the edge builders index them from 0: a converter that is REUSED keeps building the edges of its
+      FIRST observation.  ``fresh=True`` clears them per call instead (the mode a maintainer would want; the reference's
+      behaviour is the default).
+    """
+
+    def __init__(self, num_agvs, num_pickers, topk_tasks=5, max_comm_distance=5.0, max_task_distance=10.0, fresh: bool = False):
+        self.topk_tasks = topk_tasks
+        self.max_comm_distance = max_comm_distance
+        self.max_task_distance = max_task_distance
+        self.num_agv_nodes = num_agvs
+        self.num_picker_nodes = num_pickers
+        self.num_location_nodes = None
+        self.agv_feature_dim = 7       # [carrying_shelf, carrying_requested, toggle_loading, pos_y, pos_x, target_y, target_x]
+        self.picker_feature_dim = 4    # [pos_y, pos_x, target_y, target_x]
+        self.location_feature_dim = 2  # [has_shelf, is_requested]
+        self.fresh = fresh
+        self._current_agents_info: list = []
+        self._current_shelves_info: list = []
+        self._rack_locations: list = []
+        self.position_to_sections: dict = {}
+        self.edge_list = None
+
+    def reset(self):
+        self._current_agents_info, self._current_shelves_info = [], []
+
+    def _build_graph_from_observation(self, observation, rack_locations) -> "HeteroData":
+        import numpy as np
+        na, npk = self.num_agv_nodes, self.num_picker_nodes
+        self.num_location_nodes = len(rack_locations)
+        self._rack_locations = rack_locations
+        self.position_to_sections = {}
+        if self.fresh:
+            self.reset()
+        obs = [np.asarray(o) for o in observation]
+        agv_features = [obs[a][:self.agv_feature_dim].tolist() for a in range(min(na, len(obs)))]
+        picker_features = [obs[a][:self.picker_feature_dim].tolist() for a in range(na, len(obs))]
+        self._current_agents_info.extend(agv_features + picker_features)
+        shelf_data = obs[0][7 + 4 * (na + npk - 1):]
+        n_pairs = (len(shelf_data) + 1) // 2
+        if len(shelf_data) % 2:
+            raise IndexError("index %d is out of bounds for axis 0 with size %d" % (len(shelf_data), len(shelf_data)))
+        location_features = [[shelf_data[2 * i], shelf_data[2 * i + 1]] for i in range(n_pairs)]
+        self._current_shelves_info.extend([v for pair in location_features for v in pair])
+        self.edge_list = self._build_edges()
+        for (x, y, group_idx) in self._rack_locations:
+            self.position_to_sections[(x, y)] = group_idx
+
+        data = HeteroData()
+        for name, feats, n, dim in (("agv", agv_features, na, self.agv_feature_dim), ("picker", picker_features, npk, self.picker_feature_dim),
+                                    ("location", location_features, self.num_location_nodes, self.location_feature_dim)):
+            if feats:
+                data[name].num_nodes = n
+                data[name].x = torch.tensor(np.asarray(feats, dtype=np.float64), dtype=torch.float32)
+            else:
+                data[name].num_nodes = 0
+                data[name].x = torch.empty((0, dim), dtype=torch.float32)
+        for et, edges in zip(EDGE_TYPES, self.edge_list):
+            data[et].edge_index = (torch.from_numpy(edges).t().contiguous() if len(edges)
+                                   else torch.empty((2, 0), dtype=torch.long))
+        return data
+
+    def _build_edges(self):
+        """The six edge lists [agv->location, location->agv, agv<->agv, picker->location, agv->picker, picker->agv] as
+        int64 arrays [E, 2], in the reference's emission order, from the FIRST ``num_agvs + num_pickers`` entries of
+        ``_current_agents_info`` and the first ``2 * num_locations`` entries of ``_current_shelves_info``."""
+        import numpy as np
+        na, npk, nl = self.num_agv_nodes, self.num_picker_nodes, len(self._rack_locations)
+        info = self._current_agents_info
+        agv = np.asarray(info[:na], dtype=np.float64).reshape(na, -1) if na else np.zeros((0, 7))
+        pick = np.asarray(info[na:na + npk], dtype=np.float64).reshape(npk, -1) if npk else np.zeros((0, 4))
+        shelves = np.asarray(self._current_shelves_info[:2 * nl], dtype=np.float64).reshape(-1, 2)
+        requested = np.flatnonzero((shelves[:, 0] != 0) & (shelves[:, 1] != 0)) if len(shelves) else np.zeros(0, dtype=np.int64)
+        if len(shelves) < nl and len(requested):   # the reference slices a short list: missing locations unpack an empty slice
+            raise IndexError("list index out of range")
+        empty = np.zeros((0, 2), dtype=np.int64)
+
+        # ---- AGV -> location (:1199-1221): the first rack at the target, or every requested shelf when idle
+        agv_has_t = ~((agv[:, 5] == 0) & (agv[:, 6] == 0)) if na else np.zeros(0, dtype=bool)
+        a2l = []
+        if na:
+            racks_xy = np.asarray([[r[0], r[1]] for r in self._rack_locations], dtype=np.float64).reshape(-1, 2)
+            for a in range(na):
+                if agv_has_t[a]:
+                    hit = np.flatnonzero((racks_xy[:, 0] == agv[a, 6]) & (racks_xy[:, 1] == agv[a, 5]))
+                    if len(hit):
+                        a2l.append(np.array([[a, hit[0]]], dtype=np.int64))
+                elif len(requested):
+                    a2l.append(np.stack([np.full(len(requested), a, dtype=np.int64), requested], axis=1))
+        a2l = np.concatenate(a2l, axis=0) if a2l else empty
+        l2a = a2l[:, ::-1].copy()
+
+        # ---- AGV <-> AGV (:1223-1248): L1 distance <= max_comm_distance; two targets index the empty section map
+        a2a = empty
+        if na > 1:
+            with_t = np.flatnonzero(agv_has_t)
+            if len(with_t) >= 2:
+                i = int(with_t[0])
+                raise KeyError((np.float64(agv[i, 6]), np.float64(agv[i, 5])))
+            iu, ju = np.triu_indices(na, k=1)
+            dist = np.abs(agv[iu, 4] - agv[ju, 4]) + np.abs(agv[iu, 3] - agv[ju, 3])
+            hit = dist <= self.max_comm_distance
+            iu, ju = iu[hit], ju[hit]
+            a2a = np.empty((2 * len(iu), 2), dtype=np.int64)
+            a2a[0::2, 0], a2a[0::2, 1] = iu, ju
+            a2a[1::2, 0], a2a[1::2, 1] = ju, iu
+
+        # ---- picker -> location (:1250-1272)
+        p2l = []
+        if npk and nl:
+            for r in self._rack_locations:
+                hash(r)                                     # position_to_sections.get(rack_pos): unhashable entries raise TypeError
+            pick_has_t = ~((pick[:, 3] == 0) & (pick[:, 2] == 0))
+            for p in range(npk):
+                if pick_has_t[p]:
+                    raise ValueError("operands could not be broadcast together with shapes (%d,) (2,) " % len(self._rack_locations[0])
+                                     if len(self._rack_locations[0]) != 2 else "The truth value of an array with more than one element is ambiguous")
+                if len(requested):
+                    p2l.append(np.stack([np.full(len(requested), p, dtype=np.int64), requested], axis=1))
+        p2l = np.concatenate(p2l, axis=0) if p2l else empty
+
+        # ---- AGV -> picker, picker -> AGV (:1274-1318): close, or the AGV has a target (None == None section match)
+        a2p = empty
+        if na and npk:
+            dist = np.abs(agv[:, None, 4] - pick[None, :, 1]) + np.abs(agv[:, None, 3] - pick[None, :, 0])
+            hit = (dist <= self.max_comm_distance) | agv_has_t[:, None]
+            ai, pi = np.nonzero(hit)                        # row-major: AGV outer, picker inner, as the reference loops
+            a2p = np.stack([ai, pi], axis=1).astype(np.int64)
+        p2a = a2p[:, ::-1].copy()
+        return [a2l, l2a, a2a, p2l, a2p, p2a]

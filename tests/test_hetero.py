@@ -137,3 +137,37 @@ def test_cuda_hetero_conv_without_some_relations(cuda):
     assert set(got) == set(want) == {"location", "agv"}
     for k in want:
         assert rel_l2(got[k], want[k]) <= 1e-5, k
+
+
+@pytest.mark.gpu
+def test_cuda_batched_forward_over_many_hetero_graphs_from_the_converter(cuda):
+    """The reference calls the network on ONE HeteroData per step (scripts/run_gnode.py:115-151); here many graphs from
+    the (golden-checked) MultiAgentGraphConverter go through one forward as a disjoint union and every graph's Q-values and
+    embeddings must equal its own single-graph forward through the oracle."""
+    from swarm_ode_b200.hetero import MultiAgentGraphConverter
+    g = np.load(os.path.join(os.path.dirname(GOLDEN), "multi_agent_converter.npz"))
+    tags = ["medium/idle", "medium/one_agv_target", "medium/nothing_requested", "medium/agv_target_off_rack", "medium/reuse_first"]
+    datas, refs = [], []
+    for t in tags:
+        racks = [tuple(int(v) for v in r) for r in g[f"{t}/racks"]]
+        d = MultiAgentGraphConverter(19, 9)._build_graph_from_observation(g[f"{t}/obs"], racks)
+        datas.append(d)
+        r = RefHeteroData()
+        for k in ("agv", "picker", "location"):
+            r[k].x = d[k].x.clone()
+        for et in EDGE_TYPES:
+            r[et].edge_index = d[et].edge_index.clone()
+        refs.append(r)
+    dims = {"agv": 7, "picker": 4, "location": 2}
+    torch.manual_seed(3)
+    ref = HeteroGraphODENetworkRef(dims, action_size=5, hidden_dim=32, num_layers=2, ode_hidden_dim=16)
+    m = S.HeteroGraphODENetwork(dims, action_size=5, hidden_dim=32, num_layers=2, ode_hidden_dim=16)
+    m.load_state_dict(ref.state_dict())
+    m = m.to(cuda)
+    with torch.no_grad():
+        out = m(S.HeteroData.from_data_list(datas).to(cuda), integration_time=1.0)
+        wants = [ref(r, integration_time=1.0) for r in refs]
+    for k in KEYS:
+        want = torch.cat([w[k] for w in wants], dim=0)
+        assert out[k].shape == want.shape, k
+        assert rel_l2(out[k], want) <= FIXED_TOL, (k, rel_l2(out[k], want))
