@@ -70,7 +70,7 @@ __device__ __forceinline__ void chain_bwd_body(const BwdArgs& a, uint8_t* smem, 
 
   if (warp == 0) {
     // =========================== weight-image producer ===========================
-    if (lane == 0) {
+    {
       uint32_t s = 0, ph = 0;
       bool first_lap = true;
       for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
@@ -83,9 +83,12 @@ __device__ __forceinline__ void chain_bwd_body(const BwdArgs& a, uint8_t* smem, 
             for (int kbb = 0; kbb < nkb * nblk; ++kbb) {
               const int kb = kbb % nkb;
               if (!first_lap) wait_bar(smem_u32(&bar_b_empty[s]), ph ^ 1u, dead, status, 31);
-              const uint32_t bar = smem_u32(&bar_b_full[s]);
-              mbar_expect_tx(bar, bytes);
-              bulk_load_1d(smem_base + b_off + s * B_STAGE, img + (size_t)kb * bytes, bytes, bar);
+              if (elect_one()) {
+                const uint32_t bar = smem_u32(&bar_b_full[s]);
+                mbar_expect_tx(bar, bytes);
+                bulk_load_1d(smem_base + b_off + s * B_STAGE, img + (size_t)kb * bytes, bytes, bar);
+              }
+              __syncwarp();
               if (++s == n_slots) { s = 0; ph ^= 1u; first_lap = false; }
             }
           }
@@ -107,7 +110,7 @@ __device__ __forceinline__ void chain_bwd_body(const BwdArgs& a, uint8_t* smem, 
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           for (int kb = 0; kb < nkb; ++kb) {
             wait_bar(smem_u32(&bar_b_full[sb]), pb, dead, status, 32);
-            if (lane == 0) {
+            if (elect_one()) {
               issue_kblock(tmem_base + ACC_COL, tmem_base + ALO_COL, a_addr, (uint32_t)lbo_t, smem_base + b_off + sb * B_STAGE, W2H, kb, kb == 0);
               umma_commit(smem_u32(&bar_b_empty[sb]));
               if (kb == nkb - 1) umma_commit(smem_u32(&bar_acc_full));

@@ -19,6 +19,8 @@
 //   warp 1      TMEM alloc + MMA issue
 //   warps 2-9   workers: tile loads / combinations, residual operand, TMEM epilogues, aggregations, tile stores; they
 //               advance in lockstep through named barrier 1.
+#include <cstdlib>
+
 #include "chain_common.cuh"
 #include "field.cuh"
 
@@ -76,7 +78,8 @@ __device__ __forceinline__ void chain_fwd_body(const Args& a, uint8_t* smem, uin
 
   if (warp == 0) {
     // =========================== weight-image producer ===========================
-    if (lane == 0) {
+    // (the whole warp walks the schedule with warp-uniform state; one elected lane issues the copy: tc_common.cuh, elect_one)
+    {
       uint32_t s = 0, ph = 0;
       bool first_lap = true;
       for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
@@ -84,17 +87,19 @@ __device__ __forceinline__ void chain_fwd_body(const Args& a, uint8_t* smem, uin
         for (int st = 0; st < S; ++st) {
           for (int g = (st > 0 ? 0 : 1); g < 2; ++g) {           // g = 0: M13 (stage > 0 only), g = 1: w2cat
             const uint8_t* img = reinterpret_cast<const uint8_t*>(g == 0 ? a.img13 : a.img2);
-            // a ring slot / bulk copy carries one K block of the N = 128 image or two of the N = 64 image: a ring stage
-            // costs ~0.2 us of fixed time (copy completion, barrier wait, commit) on top of its MMAs ("what
-            // is next" (i)), so fewer, fatter stages
+            // a ring slot / bulk copy carries one K block of the N = 128 image or two of the N = 64 image: fewer, fatter
+            // ring stages (every stage costs a copy completion, a barrier wait and a commit on top of its MMAs)
             const int kps = g == 0 ? 1 : 2;
             const uint32_t bytes = g == 0 ? stage_bytes(W2H) : 2 * stage_bytes(WH);
             for (int b = 0; b < nblk; ++b) {
               for (int kb = 0; kb < W2H / KB16 / kps; ++kb) {
                 if (!first_lap) wait_bar(smem_u32(&bar_b_empty[s]), ph ^ 1u, dead, status, 21);
-                const uint32_t bar = smem_u32(&bar_b_full[s]);
-                mbar_expect_tx(bar, bytes);
-                bulk_load_1d(smem_base + b_off + s * B_STAGE, img + (size_t)kb * bytes, bytes, bar);
+                if (elect_one()) {
+                  const uint32_t bar = smem_u32(&bar_b_full[s]);
+                  mbar_expect_tx(bar, bytes);
+                  bulk_load_1d(smem_base + b_off + s * B_STAGE, img + (size_t)kb * bytes, bytes, bar);
+                }
+                __syncwarp();
                 if (++s == n_slots) { s = 0; ph ^= 1u; first_lap = false; }
               }
             }
@@ -117,7 +122,7 @@ __device__ __forceinline__ void chain_fwd_body(const Args& a, uint8_t* smem, uin
             const int kps = g == 0 ? 1 : 2;               // K blocks per ring slot
             for (int kb = 0; kb < W2H / KB16; kb += kps) {
               wait_bar(smem_u32(&bar_b_full[sb]), pb, dead, status, 22);
-              if (lane == 0) {
+              if (elect_one()) {
                 for (int j = 0; j < kps; ++j)
                   issue_kblock(tmem_base + ACC_COL, tmem_base + ALO_COL, smem_base + (uint32_t)(b * TM * 16), (uint32_t)lbo_t,
                                smem_base + b_off + sb * B_STAGE + (uint32_t)(j * stage_bytes(WH)), n, kb + j, kb + j == 0);
@@ -706,7 +711,11 @@ int chain_fwd(Sage3Ctx& c, FoldWs& f, const Tableau& tb, float dt, float* Cout, 
     GN_CUDA(cudaFuncSetAttribute(chain::k_chain_fwd, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
   }
   const bool big = a.tile_rows > chain::TR_MID;       // tiles of 145 .. 256 rows: one CTA per SM
-  chain::k_chain_fwd<<<(big ? 1 : 2) * kNumSMs, chain::THREADS, chain::smem_bytes_of(a.tile_rows), s>>>(a);
+  unsigned grid = (big ? 1 : 2) * kNumSMs;
+#ifdef CHAIN_TRACE
+  { const char* e = std::getenv("CHAIN_GRID"); if (e && atoi(e) > 0) grid = (unsigned)atoi(e); }
+#endif
+  chain::k_chain_fwd<<<grid, chain::THREADS, chain::smem_bytes_of(a.tile_rows), s>>>(a);
   GN_LAUNCHED();
   return GNODE_OK;
 }

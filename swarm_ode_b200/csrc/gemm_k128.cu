@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_k128_rows(const k128::Args
 
   if (warp == 0) {
     // =========================== weight-image producer ===========================
-    if (lane == 0) {
+    {
       uint32_t s = 0, ph = 0;
       bool first_lap = true;
       const uint8_t* img = reinterpret_cast<const uint8_t*>(a.img);
@@ -205,9 +205,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_k128_rows(const k128::Args
         for (int c = 0; c < n_chunks; ++c) {
           for (int kb = 0; kb < NKB; kb += KPS) {     // one bulk copy per KPS K blocks (they are adjacent in the image)
             if (!first_lap) wait_bar(smem_u32(&bar_b_empty[s]), ph ^ 1u, dead, status, 51);
-            const uint32_t bar = smem_u32(&bar_b_full[s]);
-            mbar_expect_tx(bar, KPS * KSTAGE);
-            bulk_load_1d(smem_base + B_OFF + s * (KPS * KSTAGE), img + ((size_t)c * NKB + kb) * KSTAGE, KPS * KSTAGE, bar);
+            if (elect_one()) {
+              const uint32_t bar = smem_u32(&bar_b_full[s]);
+              mbar_expect_tx(bar, KPS * KSTAGE);
+              bulk_load_1d(smem_base + B_OFF + s * (KPS * KSTAGE), img + ((size_t)c * NKB + kb) * KSTAGE, KPS * KSTAGE, bar);
+            }
+            __syncwarp();
             if (++s == (uint32_t)RING) { s = 0; ph ^= 1u; first_lap = false; }
           }
         }
@@ -223,7 +226,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_k128_rows(const k128::Args
       for (int c = 0; c < n_chunks; ++c) {
         for (int kb = 0; kb < NKB; kb += KPS) {
           wait_bar(smem_u32(&bar_b_full[sb]), pb, dead, status, 52);
-          if (lane == 0) {
+          if (elect_one()) {
 #pragma unroll
             for (int j = 0; j < KPS; ++j)
               issue_kblock(tmem_base + (uint32_t)(NCH * c), tmem_base + ALO, smem_base + T_OFF, (uint32_t)lbo_t,

@@ -237,7 +237,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
         TW(0, ok = mbar_wait(smem_u32(&bar_b_full[sb]), pb, status, 2));
         TW(1, ok = ok && mbar_wait(smem_u32(&bar_aop_full[sa]), pa, status, 2));
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        if (lane == 0) {
+        if (elect_one()) {
           const uint32_t a_hi = (smem_base + aop_off + sa * AOP_BYTES) >> 4, a_lo = a_hi + (A_PLANE >> 4);
           const uint32_t b_hi = (smem_base + b_off + sb * 2u * b_plane) >> 4, b_lo = b_hi + (b_plane >> 4);
 #ifdef TC_TRACE

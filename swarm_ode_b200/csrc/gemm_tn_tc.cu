@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tn_tc(const Args a) {
     for (int i = 0; i < nkb && ok; ++i) {
       ok = mbar_wait(smem_u32(&bar_op_full[so]), po, status, 12);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      if (lane == 0) {
+      if (elect_one()) {
         const uint32_t m_hi = (smem_base + op_off + so * op_stage) >> 4, m_lo = m_hi + (M_PLANE >> 4);
         const uint32_t n_hi0 = m_hi + ((2u * M_PLANE) >> 4), n_lo0 = n_hi0 + (n_plane >> 4);
         for (int ks = 0; ks < KS; ++ks) {                          // K step ks uses chunks 2ks, 2ks + 1 of every plane

@@ -18,6 +18,22 @@ __device__ __forceinline__ uint64_t globaltimer_ns() {
   return t;
 }
 
+// One lane of a converged warp (elect.sync).  The tcgen05 / bulk-copy issue sites use this instead of `lane == 0`: behind
+// a lane test the compiler treats the operands as divergent and wraps EVERY tcgen05.mma in an ELECT + 6 x R2UR + branch
+// waterfall (~180 cycles per instruction, measured: scripts/dev/probe_umma_rate.cu); behind elect.sync with warp-uniform
+// operands the descriptors live in uniform registers and the instruction issues directly.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xFFFFFFFF;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint32_t addr, uint32_t count) {
