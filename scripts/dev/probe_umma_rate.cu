@@ -5,6 +5,8 @@
 //   mode 2  A in TENSOR MEMORY (TS form), B shared no swizzle
 //   mode 3  A in tensor memory, B shared SWIZZLE_128B
 //   mode 4  A, B shared, MN-major no swizzle (the tile read "transposed": the weight-gradient form)
+// The issuing lane is chosen by elect.sync (a lane test makes the compiler wrap every MMA in a ~180-cycle waterfall, which is
+// what the first version of this probe measured: 185 .. 230 cycles whatever the mode or N).
 // Operand contents are zeros: only time is measured (clock64 around `iters` back-to-back MMAs + commit + wait).
 // build: nvcc -O2 -std=c++17 -gencode arch=compute_100a,code=sm_100a -I swarm_ode_b200/csrc scripts/dev/probe_umma_rate.cu -o gpurun_out/probe_umma_rate
 #include <cstdio>
@@ -56,12 +58,13 @@ __global__ void __launch_bounds__(128, 1) k_rate(int mode, int n, int iters, int
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tm = holder;
   const uint32_t a_base = smem_u32(smem), b_base = a_base + 80 * 1024;
-  if (tid == 0) {
+  if (warp == 1 && elect_one()) {
     const uint32_t lbo_a = 96 * 16 + 16, lbo_b = (uint32_t)n * 16 + 16;          // the chain kernels' chunk pitches
     const uint32_t idesc = make_idesc(n) | (mode == 4 ? ((1u << 15) | (1u << 16)) : 0u);
     long long t0 = clock64();
     for (int it = 0; it < iters; ++it) {
-      for (int kb = 0; kb < kblocks; ++kb) {                                       // one MMA per K = 8 step, walking the operands
+      #pragma unroll
+      for (int kb = 0; kb < 16; ++kb) {                                       // one MMA per K = 8 step, walking the operands
         uint64_t da, db;
         if (mode == 0 || mode == 2) {
           da = make_desc(a_base + (uint32_t)(2 * kb) * lbo_a, lbo_a);
