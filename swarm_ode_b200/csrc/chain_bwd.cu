@@ -50,7 +50,7 @@ struct BwdArgs {
 
 // TR / NB as in chain_fwd.cu: rows kept per chunk, 128-row blocks per tile.
 template <int TR, int NB>
-__device__ __forceinline__ void chain_bwd_body(const BwdArgs& a, uint8_t* smem, float* s_inv, uint64_t* bar_b_full,
+__device__ __forceinline__ void chain_bwd_body(const BwdArgs& a, uint8_t* smem, uint16_t* s_deg, uint64_t* bar_b_full,
                                                uint64_t* bar_b_empty, uint64_t* bar_a_ready_p, uint64_t* bar_acc_full_p,
                                                uint32_t tmem_base, int* dead_flag_p) {
   constexpr int lbo_t = lbo_t_of(TR);
@@ -66,7 +66,8 @@ __device__ __forceinline__ void chain_bwd_body(const BwdArgs& a, uint8_t* smem, 
   uint8_t* const T = smem;
   const uint32_t smem_base = smem_u32(smem);
   const int n_tiles = a.tiles[0];
-  auto blocks_of = [&](int t) { return (NB == 2 && a.tiles[2 + t] - a.tiles[1 + t] > TM) ? 2 : 1; };
+  auto rows_of = [&](int t) { return a.tiles[2 + t] - a.tiles[1 + t]; };
+  auto blocks_of = [&](int t) { return (NB == 2 && rows_of(t) > TM) ? 2 : 1; };
 
   if (warp == 0) {
     // =========================== weight-image producer ===========================
@@ -105,13 +106,14 @@ __device__ __forceinline__ void chain_bwd_body(const BwdArgs& a, uint8_t* smem, 
          for (int b = 0; b < nblk; ++b) {
           const int nkb = g == 0 ? W2H / KB16 : WH / KB16;
           const uint32_t a_addr = smem_base + (g == 0 ? 0u : (uint32_t)(16 * lbo_t)) + (uint32_t)(b * TM * 16);   // g = 1: right half of the tile
+          const int mm = (b == 1 && rows_of(t) - TM <= SHORT_BLOCK_ROWS) ? 64 : 128;
           wait_bar(smem_u32(&bar_a_ready), pa, dead, status, 33);
           pa ^= 1u;
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           for (int kb = 0; kb < nkb; ++kb) {
             wait_bar(smem_u32(&bar_b_full[sb]), pb, dead, status, 32);
             if (elect_one()) {
-              issue_kblock(tmem_base + ACC_COL, tmem_base + ALO_COL, a_addr, (uint32_t)lbo_t, smem_base + b_off + sb * B_STAGE, W2H, kb, kb == 0);
+              issue_kblock(tmem_base + ACC_COL, tmem_base + ALO_COL, a_addr, (uint32_t)lbo_t, smem_base + b_off + sb * B_STAGE, W2H, kb, kb == 0, mm);
               umma_commit(smem_u32(&bar_b_empty[sb]));
               if (kb == nkb - 1) umma_commit(smem_u32(&bar_acc_full));
             }
@@ -156,11 +158,13 @@ __device__ __forceinline__ void chain_bwd_body(const BwdArgs& a, uint8_t* smem, 
         }
         nbr[q] = v;
       }
+      // (kept as 16-bit in-degrees: the float table did not fit next to a second CTA with the two-slot ring of 140-row tiles)
       for (int rr = wt; rr < NB * TM; rr += WORKERS) {
-        float w = 0.f;
-        if (rr < nr) { const int d = a.rowptr[r0 + rr + 1] - a.rowptr[r0 + rr]; w = 1.0f / (float)(d > 1 ? d : 1); }
-        s_inv[rr] = w;
+        int d = 1;
+        if (rr < nr) { d = a.rowptr[r0 + rr + 1] - a.rowptr[r0 + rr]; if (d > 65535) { *a.err = 1; d = 65535; } }
+        s_deg[rr] = (uint16_t)(d > 1 ? d : 1);
       }
+      auto inv_deg_of = [&](int row) { return __frcp_rn((float)s_deg[row]); };   // == 1.0f / (float)deg, correctly rounded
       // A^T over chunks [c0, c0 + 8) of row 128 b + alane (block 1 walks its slice of the transposed CSR in global memory)
       auto aggregate_t = [&](int b, int c0, float4 (&acc)[8]) {
 #pragma unroll
@@ -170,7 +174,7 @@ __device__ __forceinline__ void chain_bwd_body(const BwdArgs& a, uint8_t* smem, 
 #pragma unroll
           for (int q = 0; q < NBR_REG; ++q) {
             if (nbr[q] >= 0) {
-              const float w = s_inv[nbr[q]];
+              const float w = inv_deg_of(nbr[q]);
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
                 const float4 v = *Tp(c0 + i, nbr[q]);
@@ -185,7 +189,7 @@ __device__ __forceinline__ void chain_bwd_body(const BwdArgs& a, uint8_t* smem, 
         for (int p = pb_; p < pe_; ++p) {
           const int nb = a.t_col[p] - r0;
           if (nb < 0 || nb >= nr) { *a.err = 1; continue; }
-          const float w = s_inv[nb];
+          const float w = inv_deg_of(nb);
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const float4 v = *Tp(c0 + i, nb);
@@ -406,7 +410,7 @@ __global__ void __launch_bounds__(THREADS, 2) k_chain_bwd(const BwdArgs a) {
   __shared__ __align__(8) uint64_t bar_acc_full;
   __shared__ uint32_t tmem_holder;
   __shared__ int dead_flag;
-  __shared__ float s_inv[2 * TM];
+  __shared__ uint16_t s_deg[2 * TM];
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -435,12 +439,12 @@ __global__ void __launch_bounds__(THREADS, 2) k_chain_bwd(const BwdArgs a) {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = tmem_holder;
   if (a.tile_rows <= TM) {
-    if (s_tr <= 96) chain_bwd_body<96, 1>(a, smem, s_inv, bar_b_full, bar_b_empty, &bar_a_ready, &bar_acc_full, tmem_base, &dead_flag);
-    else chain_bwd_body<128, 1>(a, smem, s_inv, bar_b_full, bar_b_empty, &bar_a_ready, &bar_acc_full, tmem_base, &dead_flag);
+    if (s_tr <= 96) chain_bwd_body<96, 1>(a, smem, s_deg, bar_b_full, bar_b_empty, &bar_a_ready, &bar_acc_full, tmem_base, &dead_flag);
+    else chain_bwd_body<128, 1>(a, smem, s_deg, bar_b_full, bar_b_empty, &bar_a_ready, &bar_acc_full, tmem_base, &dead_flag);
   } else if (a.tile_rows <= TR_MID) {
-    chain_bwd_body<TR_MID, 2>(a, smem, s_inv, bar_b_full, bar_b_empty, &bar_a_ready, &bar_acc_full, tmem_base, &dead_flag);
+    chain_bwd_body<TR_MID, 2>(a, smem, s_deg, bar_b_full, bar_b_empty, &bar_a_ready, &bar_acc_full, tmem_base, &dead_flag);
   } else {
-    chain_bwd_body<TR_BIG, 2>(a, smem, s_inv, bar_b_full, bar_b_empty, &bar_a_ready, &bar_acc_full, tmem_base, &dead_flag);
+    chain_bwd_body<TR_BIG, 2>(a, smem, s_deg, bar_b_full, bar_b_empty, &bar_a_ready, &bar_acc_full, tmem_base, &dead_flag);
   }
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

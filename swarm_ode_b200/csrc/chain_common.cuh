@@ -42,16 +42,25 @@ __host__ __device__ constexpr int stage_bytes(int n) { return 10 * lbo_b(n); }  
 constexpr int B_STAGE = 2 * stage_bytes(WH);  // 20800: ring slot = one K block of an N = 128 image (20640) or TWO of an N = 64 image
 constexpr int MAX_SLOTS = 4;
 constexpr int SMEM_BYTES = t_bytes_of(96) + 3 * B_STAGE;   // 112064: two CTAs per SM; 2 slots for 128-row tiles, 3 for <= 96 rows
-// Tiles of more than 128 rows (graphs of 129 .. 256 nodes) are processed as two 128-row blocks: up to TR_MID rows still
-// leave room for one ring slot next to a second CTA; beyond that one CTA per SM with the full tile and two slots.
-constexpr int TR_MID = 144, TR_BIG = 256;
+// Tiles of more than 128 rows (graphs of 129 .. 256 nodes) are processed as two 128-row blocks.  Up to TR_MID = 140 rows
+// (28 agents x 5 snapshots: the 19 AGV + 9 picker warehouse) the tile keeps exactly TR_MID rows per chunk (chunk pitch
+// 141 x 16 bytes: still an odd number of 16-byte units, so the 128-bit accesses stay conflict free), which leaves room for
+// a TWO-slot weight ring next to a second CTA on the SM (a one-slot ring serialises every bulk copy with the MMAs that
+// consume it: 7 us per block and contraction instead of 3.7).  Beyond that one CTA per SM with the full tile.
+constexpr int TR_MID = 140, TR_BIG = 256;
+constexpr int SMEM_BYTES_MID = t_bytes_of(TR_MID) + 2 * B_STAGE;   // 113792 (+ ~1.2 KB static: two CTAs need <= 115712 each)
 constexpr int SMEM_BYTES_BIG = t_bytes_of(TR_BIG) + 2 * B_STAGE;   // 173184
-__host__ __device__ constexpr int smem_bytes_of(int tr) { return tr <= TR_MID ? SMEM_BYTES : SMEM_BYTES_BIG; }
+__host__ __device__ constexpr int smem_bytes_of(int tr) { return tr <= TM ? SMEM_BYTES : (tr <= TR_MID ? SMEM_BYTES_MID : SMEM_BYTES_BIG); }
 __host__ __device__ constexpr int ring_slots(int tr) {
   return (smem_bytes_of(tr) - t_bytes_of(tr)) / B_STAGE > MAX_SLOTS ? MAX_SLOTS : (smem_bytes_of(tr) - t_bytes_of(tr)) / B_STAGE;
 }
 static_assert(B_STAGE >= stage_bytes(W2H), "slot too small");
-static_assert(ring_slots(128) >= 2 && ring_slots(TR_MID) >= 1 && ring_slots(TR_BIG) >= 2, "ring too small");
+static_assert(ring_slots(128) >= 2 && ring_slots(TR_MID) >= 2 && ring_slots(TR_BIG) >= 2, "ring too small");
+static_assert((lbo_t_of(TR_MID) / 16) % 2 == 1 && (lbo_t_of(96) / 16) % 2 == 1, "chunk pitch must be an odd number of 16-byte units");
+// A second block of at most 16 rows runs as M = 64 MMAs: rows 0 .. 15 of an M = 64 accumulator sit in lanes 0 .. 15 exactly
+// as for M = 128 (scripts/dev/probe_umma_m64.cu), and the TS form reads the residual row of lane L from lane L
+// (probe_umma_m64_ts.cu), so only the instruction descriptor changes; the tensor core reads half the A rows.
+constexpr int SHORT_BLOCK_ROWS = 16;
 
 inline size_t image_floats(int n, int k) { return (size_t)(k / KB16) * stage_bytes(n) / 4; }
 // img <- chain-format image of row-major W [n x k] (row stride ld); n % 8 == 0, k % 16 == 0
@@ -79,8 +88,8 @@ __device__ __forceinline__ void wait_bar(uint32_t addr, uint32_t parity, volatil
 }
 
 // instruction descriptor of kind::f16 with bf16 operands, fp32 accumulation, both K-major, M = 128
-__device__ __forceinline__ uint32_t make_idesc_bf16(int bn) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+__device__ __forceinline__ uint32_t make_idesc_bf16(int bn, int bm = 128) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(bm >> 4) << 24);
 }
 // D[tmem] (+)= A[tmem] . B[smem]^T, A = bf16 in tensor memory (TS form)
 __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t accumulate) {
@@ -96,10 +105,10 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, u
 
 // One K = 16 block of the three-term product: tile chunks [4 kb, 4 kb + 4) x weight stage at `bstage`.
 __device__ __forceinline__ void issue_kblock(uint32_t tmem_acc, uint32_t tmem_alo, uint32_t tile_addr, uint32_t lbo_t,
-                                             uint32_t bstage, int n, int kb, bool first) {
+                                             uint32_t bstage, int n, int kb, bool first, int m = 128) {
   const uint32_t lb = (uint32_t)lbo_b(n);
   const uint64_t dT = make_desc(0, lbo_t), dB = make_desc(0, lb);
-  const uint32_t idf = make_idesc(n), idb = make_idesc_bf16(n);
+  const uint32_t idf = make_idesc(n, m), idb = make_idesc_bf16(n, m);
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
     const uint64_t da = dT | (uint64_t)(((tile_addr + (uint32_t)(4 * kb + 2 * h) * lbo_t) >> 4) & 0x3FFF);

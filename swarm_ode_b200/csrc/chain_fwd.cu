@@ -74,7 +74,8 @@ __device__ __forceinline__ void chain_fwd_body(const Args& a, uint8_t* smem, uin
   uint8_t* const T = smem;
   const uint32_t smem_base = smem_u32(smem);
   const int n_tiles = a.tiles[0];
-  auto blocks_of = [&](int t) { return (NB == 2 && a.tiles[2 + t] - a.tiles[1 + t] > TM) ? 2 : 1; };
+  auto rows_of = [&](int t) { return a.tiles[2 + t] - a.tiles[1 + t]; };
+  auto blocks_of = [&](int t) { return (NB == 2 && rows_of(t) > TM) ? 2 : 1; };
 
   if (warp == 0) {
     // =========================== weight-image producer ===========================
@@ -120,12 +121,13 @@ __device__ __forceinline__ void chain_fwd_body(const Args& a, uint8_t* smem, uin
             pa ^= 1u;
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const int kps = g == 0 ? 1 : 2;               // K blocks per ring slot
+            const int mm = (b == 1 && rows_of(t) - TM <= SHORT_BLOCK_ROWS) ? 64 : 128;
             for (int kb = 0; kb < W2H / KB16; kb += kps) {
               wait_bar(smem_u32(&bar_b_full[sb]), pb, dead, status, 22);
               if (elect_one()) {
                 for (int j = 0; j < kps; ++j)
                   issue_kblock(tmem_base + ACC_COL, tmem_base + ALO_COL, smem_base + (uint32_t)(b * TM * 16), (uint32_t)lbo_t,
-                               smem_base + b_off + sb * B_STAGE + (uint32_t)(j * stage_bytes(WH)), n, kb + j, kb + j == 0);
+                               smem_base + b_off + sb * B_STAGE + (uint32_t)(j * stage_bytes(WH)), n, kb + j, kb + j == 0, mm);
                 umma_commit(smem_u32(&bar_b_empty[sb]));
                 if (kb + kps == W2H / KB16) umma_commit(smem_u32(&bar_acc_full));
               }

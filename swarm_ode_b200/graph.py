@@ -58,14 +58,14 @@ class CSRGraph:
                 _PENDING.append(self)
         # Whole-graph row tiles: let the integrators keep a tile on chip across the stages of a step.  Needs the batch's
         # graph offsets and the host-known size of its largest graph: tiles hold at most 128 rows, or -- for batches with
-        # graphs of 129 .. 256 nodes -- 144 / 256 rows, processed as two 128-row blocks by the chain kernels.
+        # graphs of 129 .. 256 nodes -- 140 / 256 rows, processed as two 128-row blocks by the chain kernels.
         self.tiles = None
         self.tile_err = None
         self.tile_rows = 0
         if (graph_ptr is not None and max_graph_nodes is not None and 0 < int(max_graph_nodes) <= 256
                 and graph_ptr.is_cuda and graph_ptr.numel() >= 2):
             m = int(max_graph_nodes)
-            self.tile_rows = 128 if m <= 128 else (144 if m <= 144 else 256)
+            self.tile_rows = 128 if m <= 128 else (140 if m <= 140 else 256)
             gp = graph_ptr.to(torch.int64).contiguous()
             self.tiles = torch.empty(gp.numel() + 1, dtype=torch.int32, device=dev)
             self.tile_err = torch.zeros(1, dtype=torch.int32, device=dev)

@@ -374,7 +374,7 @@ def test_graph_resident_chain_equals_kernel_per_op_path(cuda, fold_mode, solver,
     """With batch.ptr / max_graph_nodes present the folded stages run graph-resident (csrc/chain_fwd.cu): one CTA keeps
     a tile of whole graphs on chip for all stages.  Same arithmetic as the kernel-per-op folded path up to fp32
     summation order; graphs of 35 / 15 nodes pack several per tile, 125 nodes fill one; graphs of 140 (19 AGVs + 9 pickers:
-    BASELINE configs[2]), 205 and 255 nodes run as tiles of two 128-row blocks (144-row and 256-row variants), 130-node
+    BASELINE configs[2]), 205 and 255 nodes run as tiles of two 128-row blocks (140-row and 256-row variants), 130-node
     graphs (26 agents) likewise."""
     if fold_mode != "folded":
         pytest.skip("the chain kernel belongs to the folded integrator")
