@@ -361,10 +361,36 @@ def small_batch_leg(dev, solver, sizes=(32, 64, 256), iters=30):
         wall = (time.perf_counter() - w0) / iters * 1e3
         ms = e0.elapsed_time(e1) / iters
         units = b.x.shape[0] * RK_STAGES[solver]
-        rows.append({"graphs": B, "nodes": int(b.x.shape[0]), "ms_per_step": ms, "wall_ms_per_step": wall,
-                     "library_launches_per_step": (S.launch_count() - l0) / iters, "value": units / (ms * 1e-3)})
+        row = {"graphs": B, "nodes": int(b.x.shape[0]), "ms_per_step": ms, "wall_ms_per_step": wall,
+               "library_launches_per_step": (S.launch_count() - l0) / iters, "value": units / (ms * 1e-3)}
+        # the same step captured once into a CUDA graph (swarm_ode_b200/graphed.py): ONE launch per batch, the batch
+        # copied into the graph's static buffers inside the timed loop (a fresh batch per step, as in training)
+        try:
+            from swarm_ode_b200.graphed import GraphedTrainStep
+            model_g = S.GraphODE(D, 12, 7, hidden_dim=64, ode_solver=solver)
+            S.synthetic.init_weights(model_g, seed=1, conv3_scale=0.1)
+            model_g = model_g.to(dev)
+            opt_g = torch.optim.Adam(model_g.parameters(), lr=1e-3, weight_decay=1e-4, fused=True, capturable=True)
+            gs = GraphedTrainStep(model_g, opt_g, b, nx, t)
+            for _ in range(3):
+                gs.step(b, nx)
+            torch.cuda.synchronize()
+            w0 = time.perf_counter()
+            e0.record()
+            for _ in range(iters):
+                gs.step(b, nx)
+            e1.record()
+            torch.cuda.synchronize()
+            gs.check()
+            gms = e0.elapsed_time(e1) / iters
+            row.update({"graphed_ms_per_step": gms, "graphed_wall_ms_per_step": (time.perf_counter() - w0) / iters * 1e3,
+                        "graphed_launches_per_step": 1, "graphed_value": units / (gms * 1e-3)})
+        except Exception as e:   # reported, never fatal for the headline
+            row["graphed_error"] = f"{type(e).__name__}: {e}"[:300]
+        rows.append(row)
     return {"unit": "agent-state-steps/s", "solver": solver, "rows": rows,
-            "note": "full train step (CSR build, forward, loss, backward, clip, Adam) per batch; eager launches"}
+            "note": "full train step (CSR build, forward, loss, backward, clip, Adam) per batch: eager launches, and the "
+                    "same step replayed as one CUDA graph (graphed_*: swarm_ode_b200.graphed.GraphedTrainStep)"}
 
 
 DOPRI5_CONV3_SCALE = 8.0

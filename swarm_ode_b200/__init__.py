@@ -13,12 +13,13 @@ from .modules import GraphODE, GraphODEFunc, ODEFunction, SAGEConv, BoundGraphOD
 from .odeint import odeint  # noqa: F401
 from .hetero import HeteroData, HeteroConv, HeteroGraphODENetwork  # noqa: F401
 from . import ops, synthetic  # noqa: F401
+from .graphed import GraphedTrainStep  # noqa: F401
 
 __all__ = [
     "GnodeError", "set_engine", "set_fold", "launch_count", "LIB_PATH",
     "Batch", "Data", "GraphConverter", "PackedBatch", "TrajectoryBatch", "build_episode_batch", "collate_trajectory_batches",
     "extract_positions_from_graph", "spatial_edges_cuda",
-    "CSRGraph", "csr_for",
+    "CSRGraph", "csr_for", "GraphedTrainStep",
     "GraphODE", "GraphODEFunc", "ODEFunction", "SAGEConv", "BoundGraphODEFunc",
     "HeteroData", "HeteroConv", "HeteroGraphODENetwork",
     "odeint", "ops", "synthetic",

@@ -21,7 +21,7 @@ __global__ void k_count(const int64_t* __restrict__ ei, int64_t E, int64_t N,
   for (; e < E; e += stride) {
     int64_t s = ei[e], d = ei[E + e];
     if (s < 0 || s >= N || d < 0 || d >= N) {
-      *flag = 1;
+      if (!(s == -1 && d == -1)) *flag = 1;    // (-1, -1) is the padding edge of fixed-capacity edge buffers: skipped silently
       continue;
     }
     atomicAdd(&cnt_in[d], 1);

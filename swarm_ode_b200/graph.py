@@ -40,11 +40,19 @@ class CSRGraph:
         self._err_dev = torch.empty(1, dtype=torch.int32, device=dev)
         self._err_host = None
         self._err_event = None
+        self._device_checks = validate == "device"
         with torch.cuda.device(dev):
             if validate == "sync":
                 _lib.check(L.gnode_csr_build(_lib.ptr(edge_index), E, N, _lib.ptr(self.rowptr), _lib.ptr(self.col),
                                              _lib.ptr(self.t_rowptr), _lib.ptr(self.t_col), _lib.ptr(ws), ws.numel(),
                                              _lib.stream_ptr(dev)), "gnode_csr_build")
+            elif validate == "device":
+                # CUDA-graph capture (graphed.GraphedTrainStep): nothing but kernel launches.  The error flag stays on
+                # the device; whoever replays the graph reads it (CSRGraph.device_flags) when it wants a verdict.
+                self._err_dev.zero_()
+                _lib.check(L.gnode_csr_build_async(_lib.ptr(edge_index), E, N, _lib.ptr(self.rowptr), _lib.ptr(self.col),
+                                                   _lib.ptr(self.t_rowptr), _lib.ptr(self.t_col), _lib.ptr(self._err_dev),
+                                                   _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev)), "gnode_csr_build_async")
             else:
                 # no host synchronisation: out-of-range edges are skipped on the device and flagged; the flag travels
                 # to pinned host memory asynchronously and is looked at by poll() / validate()
@@ -69,6 +77,8 @@ class CSRGraph:
             gp = graph_ptr.to(torch.int64).contiguous()
             self.tiles = torch.empty(gp.numel() + 1, dtype=torch.int32, device=dev)
             self.tile_err = torch.zeros(1, dtype=torch.int32, device=dev)
+            if validate == "device":
+                self.tile_err.zero_()       # part of the captured graph: every replay starts from a clean flag
             with torch.cuda.device(dev):
                 _lib.check(L.gnode_tiles_build_rows(_lib.ptr(gp), gp.numel() - 1, self.tile_rows, _lib.ptr(self.tiles),
                                                     _lib.stream_ptr(dev)), "gnode_tiles_build_rows")
@@ -101,11 +111,19 @@ class CSRGraph:
             _raise_tile_error(int(self.tile_err.item()), deferred=False)
         _lib.tc_check(self.device)
 
+    def device_flags(self) -> torch.Tensor:
+        """[csr index error, tile error] as a device tensor (no synchronisation): for graphs built with
+        ``validate="device"``, whose checks are not scheduled automatically."""
+        te = self.tile_err if self.tile_err is not None else torch.zeros_like(self._err_dev)
+        return torch.cat([self._err_dev, te])
+
     def schedule_tile_check(self) -> None:
         """Called after the graph-resident kernels ran: ship the tile error flag and the tcgen05 barrier status word to
         pinned memory without blocking; a later poll_pending() raises if an edge was found outside its tile, a graph
         exceeded the announced tile capacity, or a barrier wait expired.  Completed checks are looked at here (loops
         that reuse one batch never reach csr_for's cache-miss poll), and a graph keeps at most ONE outstanding check."""
+        if self._device_checks:
+            return                      # captured graph: the flags are read by the replaying side (device_flags)
         poll_pending()
         if self.tile_err is None:
             return
@@ -195,7 +213,7 @@ def csr_for(edge_index: torch.Tensor, num_nodes: int, holder: Optional[object] =
                 key, entry = k, _CACHE[k]
                 break
     if entry is None or entry[0] is not edge_index and entry[0].data_ptr() != edge_index.data_ptr():
-        if validate != "sync":
+        if validate == "deferred":
             poll_pending()
         entry = (edge_index, CSRGraph(edge_index, num_nodes, validate=validate, graph_ptr=graph_ptr,
                                       max_graph_nodes=max_graph_nodes))

@@ -139,7 +139,8 @@ class GraphODE(nn.Module):
         batch = batch_data.batch
         # deferred index validation: no host synchronisation in the training step (a bad edge list raises at the
         # next call; its edges are skipped on the device meanwhile)
-        graph = csr_for(edge_index, x0.size(0), holder=batch_data, validate="deferred",
+        capturing = x0.is_cuda and torch.cuda.is_current_stream_capturing()
+        graph = csr_for(edge_index, x0.size(0), holder=batch_data, validate="device" if capturing else "deferred",
                         graph_ptr=getattr(batch_data, "ptr", None),
                         max_graph_nodes=getattr(batch_data, "max_graph_nodes", None))
         if self.ode_solver in ("euler", "midpoint", "rk4") and self.position_decoder.out_features <= 8:
