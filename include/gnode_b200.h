@@ -235,6 +235,15 @@ int gnode_integrate_fixed(const gnode_graph* g, const gnode_sage3_params* p, int
  * every saved time point); grad_y0 overwritten (NULL = not wanted: its D-wide contraction is skipped); param grads
  * accumulated (+=).  With save == NULL
  * each step's stages are recomputed from sol[j]; with the forward's save area they are not. */
+/* Opt-in ADJOINT backward of the fixed-grid solvers (torchdiffeq.odeint_adjoint semantics; the reference itself trains
+ * with plain odeint, /root/reference/scripts/train_gde.py:78-85, imported at :10): the augmented system (y, a, dL/dtheta)
+ * is integrated backwards over every output interval with the same Runge-Kutta scheme, y being reset to the stored sol[i]
+ * at every output time.  Needs only the forward's solution (no save area); same arguments as gnode_integrate_fixed_bwd. */
+size_t gnode_integrate_fixed_adjoint_workspace_bytes(int64_t n_nodes, int32_t node_dim, int32_t hidden_dim, int32_t method);
+int gnode_integrate_fixed_adjoint(const gnode_graph* g, const gnode_sage3_params* p, int32_t method,
+                                  const float* sol, const float* t, int32_t n_t, const float* grad_sol,
+                                  float* grad_y0, const gnode_sage3_grads* grads,
+                                  void* workspace, size_t workspace_bytes, gnode_stream_t stream);
 int gnode_integrate_fixed_bwd(const gnode_graph* g, const gnode_sage3_params* p, int32_t method,
                               const float* sol, const float* t, int32_t n_t, const float* grad_sol,
                               float* grad_y0, const gnode_sage3_grads* grads,

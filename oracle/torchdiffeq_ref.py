@@ -296,3 +296,49 @@ def odeint_ref(func: Callable, y0: torch.Tensor, t: torch.Tensor, *, rtol: float
         return _integrate_dopri5(func, y0, t, rtol, atol, st, first_step=opts.get("first_step") if dts is None else dts[0],
                                  imposed_dts=dts)
     raise ValueError(f"Invalid method \"{method}\"")
+
+
+# ----------------------------------------------------------------------------
+# Adjoint method (torchdiffeq.odeint_adjoint, fixed-grid solvers)
+# ----------------------------------------------------------------------------
+def odeint_adjoint_ref(func: Callable, params: List[torch.Tensor], y0: torch.Tensor, t: torch.Tensor, grad_sol: torch.Tensor,
+                       method: str):
+    """Restatement of ``OdeintAdjointMethod`` [upstream torchdiffeq 0.2.x, ``_impl/adjoint.py``] for the fixed-grid
+    solvers: forward solve under ``no_grad``; backward = for i = len(t)-1 .. 1 integrate the augmented state
+    ``(y, adj_y, adj_params)`` with dynamics ``(f, -adj_y^T df/dy, -adj_y^T df/dparams)`` over ``t[i-1:i+1].flip(0)``
+    with the same method (one step: the grid is ``t``), then ``y <- y[i-1]`` (the stored solution) and
+    ``adj_y += grad_y[i-1]``.  Returns ``(solution, dL/dy0, [dL/dparam])`` for the cotangent ``grad_sol`` of the
+    solution.  The time cotangent (``vjp_t``) is not formed: ``t`` does not require grad at the reference's call sites."""
+    assert method in _FIXED
+    with torch.no_grad():
+        sol = _integrate_fixed(func, y0, t, method, SolverStats())
+    adj_y = grad_sol[-1].clone()
+    adj_p = [torch.zeros_like(p) for p in params]
+    sizes = [p.numel() for p in params]
+
+    def pack(y, a, gp):
+        return torch.cat([y.reshape(-1), a.reshape(-1)] + [g.reshape(-1) for g in gp])
+
+    n = y0.numel()
+
+    def aug(tt, state):
+        y = state[:n].view_as(y0).detach().requires_grad_(True)
+        a = state[n:2 * n].view_as(y0)
+        with torch.enable_grad():
+            f = func(tt, y)
+            vjps = torch.autograd.grad(f, [y] + list(params), -a, allow_unused=True)
+        vjps = [torch.zeros_like(x) if v is None else v for v, x in zip(vjps, [y] + list(params))]
+        return pack(f.detach(), vjps[0], vjps[1:])
+
+    for i in range(len(t) - 1, 0, -1):
+        state = pack(sol[i], adj_y, adj_p)
+        tt = torch.stack([t[i], t[i - 1]])
+        with torch.no_grad():
+            out = _integrate_fixed(aug, state, tt, method, SolverStats())[1]
+        adj_y = out[n:2 * n].view_as(y0) + grad_sol[i - 1]
+        off = 2 * n
+        new_p = []
+        for p_, sz in zip(params, sizes):
+            new_p.append(out[off:off + sz].view_as(p_)); off += sz
+        adj_p = new_p
+    return sol, adj_y, adj_p

@@ -10,7 +10,7 @@ from .data import (Batch, Data, GraphConverter, PackedBatch, TrajectoryBatch, bu
                    extract_positions_from_graph, spatial_edges_cuda)
 from .graph import CSRGraph, csr_for  # noqa: F401
 from .modules import GraphODE, GraphODEFunc, ODEFunction, SAGEConv, BoundGraphODEFunc  # noqa: F401
-from .odeint import odeint  # noqa: F401
+from .odeint import odeint, odeint_adjoint  # noqa: F401
 from .hetero import HeteroData, HeteroConv, HeteroGraphODENetwork  # noqa: F401
 from . import ops, synthetic  # noqa: F401
 from .graphed import GraphedTrainStep  # noqa: F401
@@ -19,7 +19,7 @@ __all__ = [
     "GnodeError", "set_engine", "set_fold", "launch_count", "LIB_PATH",
     "Batch", "Data", "GraphConverter", "PackedBatch", "TrajectoryBatch", "build_episode_batch", "collate_trajectory_batches",
     "extract_positions_from_graph", "spatial_edges_cuda",
-    "CSRGraph", "csr_for", "GraphedTrainStep",
+    "CSRGraph", "csr_for", "GraphedTrainStep", "odeint_adjoint",
     "GraphODE", "GraphODEFunc", "ODEFunction", "SAGEConv", "BoundGraphODEFunc",
     "HeteroData", "HeteroConv", "HeteroGraphODENetwork",
     "odeint", "ops", "synthetic",

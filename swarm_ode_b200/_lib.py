@@ -105,6 +105,10 @@ _SIGNATURES = {
     "gnode_integrate_fixed_bwd": (C.c_int, [C.POINTER(GnodeGraph), C.POINTER(GnodeSage3Params), C.c_int32, _P,
                                             C.POINTER(C.c_float), C.c_int32, _P, _P, C.POINTER(GnodeSage3Grads), _P,
                                             C.c_size_t, _P, C.c_size_t, _P]),
+    "gnode_integrate_fixed_adjoint_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int32, C.c_int32, C.c_int32]),
+    "gnode_integrate_fixed_adjoint": (C.c_int, [C.POINTER(GnodeGraph), C.POINTER(GnodeSage3Params), C.c_int32, _P,
+                                                C.POINTER(C.c_float), C.c_int32, _P, _P, C.POINTER(GnodeSage3Grads), _P,
+                                                C.c_size_t, _P]),
     "gnode_integrate_fixed_bwd_decoded_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "gnode_integrate_fixed_bwd_decoded": (C.c_int, [C.POINTER(GnodeGraph), C.POINTER(GnodeSage3Params), C.c_int32, _P,
                                                     C.POINTER(C.c_float), C.c_int32, _P, _P, C.c_int32,

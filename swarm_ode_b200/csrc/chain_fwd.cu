@@ -42,6 +42,8 @@ struct Args {
   float csol[kMaxStages];               // dt * c_sol[s]
   uint32_t* mask[kMaxStages];           // optional [N, 4]: sign bits of h1 (words 0, 1) and h2 (words 2, 3) for the backward chain
   float* Cout;                          // optional: C = sum_s csol[s] cat2_s, written after the last stage
+  float* Cout2;                         // optional second combination with csol2 (dopri5: the error-estimate weights)
+  float csol2[kMaxStages];
   float c13_scale[kMaxStages];          // dt * sum_j beta[s][j]
   const float *c13, *b1, *b2;
   const float *img13, *img2;            // chain-format weight images of M13 [2H x 2H] and w2cat [H x 2H]
@@ -435,37 +437,49 @@ __device__ __forceinline__ void chain_fwd_body(const Args& a, uint8_t* smem, uin
         store_tile(a.cat2[st], st == S - 1 && a.Cout == nullptr);
         CT(16 * st + 12);
         if (st == S - 1 && a.Cout != nullptr) {
-          // C = sum_s csol[s] cat2_s: the last cat2 tile is still on chip, the earlier ones come back from L2
-          for (int hf = 0; hf < 2 * nblk; ++hf) {
-            const int ibase = wt + hf * SLOTS * WORKERS;
-            float4 acc[SLOTS];
-            const float cl = a.csol[st];
+          // C = sum_s csol[s] cat2_s (and, for dopri5, the same sum with the error-estimate weights): the last cat2 tile is
+          // still on chip, the earlier ones come back from L2 once for both combinations
+          constexpr int CS = SLOTS / 2;
+          const bool two = a.Cout2 != nullptr;
+          for (int q = 0; q < 4 * nblk; ++q) {
+            const int ibase = wt + q * CS * WORKERS;
+            float4 acc[CS], acc2[CS];
+            const float cl = a.csol[st], cl2 = two ? a.csol2[st] : 0.f;
 #pragma unroll
-            for (int u = 0; u < SLOTS; ++u) {
+            for (int u = 0; u < CS; ++u) {
               const int idx = ibase + u * WORKERS, r = idx >> 5, c4 = idx & 31;
-              acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (r < nr) { const float4 v = *Tp(c4, r); acc[u] = make_float4(cl * v.x, cl * v.y, cl * v.z, cl * v.w); }
+              acc[u] = make_float4(0.f, 0.f, 0.f, 0.f); acc2[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (r < nr) {
+                const float4 v = *Tp(c4, r);
+                acc[u] = make_float4(cl * v.x, cl * v.y, cl * v.z, cl * v.w);
+                acc2[u] = make_float4(cl2 * v.x, cl2 * v.y, cl2 * v.z, cl2 * v.w);
+              }
             }
             for (int j = 0; j < st; ++j) {
-              const float cf = a.csol[j];
-              if (cf == 0.f) continue;
+              const float cf = a.csol[j], cf2 = two ? a.csol2[j] : 0.f;
+              if (cf == 0.f && cf2 == 0.f) continue;
               const float* srcj = a.cat2[j];
-              float4 v[SLOTS];
+              float4 v[CS];
 #pragma unroll
-              for (int u = 0; u < SLOTS; ++u) {
+              for (int u = 0; u < CS; ++u) {
                 const int idx = ibase + u * WORKERS, r = idx >> 5, c4 = idx & 31;
                 v[u] = (r < nr) ? *reinterpret_cast<const float4*>(srcj + (size_t)(r0 + r) * W2H + 4 * c4) : make_float4(0.f, 0.f, 0.f, 0.f);
               }
 #pragma unroll
-              for (int u = 0; u < SLOTS; ++u) {
+              for (int u = 0; u < CS; ++u) {
                 acc[u].x = fmaf(cf, v[u].x, acc[u].x); acc[u].y = fmaf(cf, v[u].y, acc[u].y);
                 acc[u].z = fmaf(cf, v[u].z, acc[u].z); acc[u].w = fmaf(cf, v[u].w, acc[u].w);
+                acc2[u].x = fmaf(cf2, v[u].x, acc2[u].x); acc2[u].y = fmaf(cf2, v[u].y, acc2[u].y);
+                acc2[u].z = fmaf(cf2, v[u].z, acc2[u].z); acc2[u].w = fmaf(cf2, v[u].w, acc2[u].w);
               }
             }
 #pragma unroll
-            for (int u = 0; u < SLOTS; ++u) {
+            for (int u = 0; u < CS; ++u) {
               const int idx = ibase + u * WORKERS, r = idx >> 5, c4 = idx & 31;
-              if (r < nr) __stcs(reinterpret_cast<float4*>(a.Cout + (size_t)(r0 + r) * W2H + 4 * c4), acc[u]);
+              if (r < nr) {
+                __stcs(reinterpret_cast<float4*>(a.Cout + (size_t)(r0 + r) * W2H + 4 * c4), acc[u]);
+                if (two) __stcs(reinterpret_cast<float4*>(a.Cout2 + (size_t)(r0 + r) * W2H + 4 * c4), acc2[u]);
+              }
             }
           }
         }
@@ -685,7 +699,7 @@ int chain_pack_image(const float* W, int n, int k, int64_t ld, float* img, cudaS
 bool chain_shape_ok(int H) { return H == chain::WH; }
 bool chain_fwd_supported(const Sage3Ctx& c) { return c.H == chain::WH && c.use_tc && c.g_tiles != nullptr && c.ci2 != nullptr; }
 
-int chain_fwd(Sage3Ctx& c, FoldWs& f, const Tableau& tb, float dt, float* Cout, cudaStream_t s) {
+int chain_fwd(Sage3Ctx& c, FoldWs& f, const Tableau& tb, float dt, float* Cout, cudaStream_t s, float* Cout2, const double* coef2) {
   int* status_dev = tc::status_ptr();
   if (!status_dev) { set_error("chain_fwd: status symbol unavailable"); return GNODE_ERR_CUDA; }
   chain::Args a{};
@@ -698,6 +712,8 @@ int chain_fwd(Sage3Ctx& c, FoldWs& f, const Tableau& tb, float dt, float* Cout, 
     a.csol[st] = (float)tb.c_sol[st] * dt;
   }
   a.Cout = Cout;
+  a.Cout2 = (Cout && Cout2 && coef2) ? Cout2 : nullptr;
+  if (a.Cout2) for (int st = 0; st < tb.S; ++st) a.csol2[st] = (float)coef2[st] * dt;
   a.c13 = f.c13; a.b1 = c.b1; a.b2 = c.b2;
   a.img13 = f.ci13; a.img2 = c.ci2;
   a.rowptr = c.g.rowptr; a.col = c.g.col;

@@ -51,6 +51,7 @@ struct Sage3Ctx : Field {
   float *ci2 = nullptr, *ci2T = nullptr;   // chain-kernel images (chain_common.cuh) of w2cat [H x 2H] and w2catT [2H x H]
   float *ck3 = nullptr, *ck1T = nullptr;   // chunked images (gemm_k128.cu) of w3cat [D x 2H] and w1catT [D x 2H]
   bool use_tc = false;
+  bool skip_wgrad = false;             // vjp: data gradient only (adjoint stages whose solution weight is zero)
   float* z = nullptr;                  // [N, 2H]  x @ w1cat^T
   int n_slots = 1;
   float* cat1[kMaxStages] = {};        // [N, 2H]  [ mean(h1) | h1 ]
@@ -97,7 +98,9 @@ struct FoldWs {
   void bind_slots(Sage3Ctx& c, float* save, int j);
   int prepare(Sage3Ctx& c, cudaStream_t s);
   // fills cat1 / cat2 of every stage from y; with Cout also C = dt sum_s c_sol[s] cat2_s
-  int forward_stages(Sage3Ctx& c, const Tableau& tb, const float* y, float dt, cudaStream_t s, float* Cout = nullptr);
+  // Cout2 / coef2: a second combination  dt sum_s coef2[s] cat2_s  (dopri5: the error-estimate weights c_err)
+  int forward_stages(Sage3Ctx& c, const Tableau& tb, const float* y, float dt, cudaStream_t s, float* Cout = nullptr,
+                     float* Cout2 = nullptr, const double* coef2 = nullptr);
   int combine_solution(Sage3Ctx& c, const Tableau& tb, float dt, float* out, cudaStream_t s);
 };
 int integrate_fixed_folded(Sage3Ctx& c, FoldWs& f, const Tableau& tb, const float* y0, const float* t, int n_t,
@@ -122,7 +125,8 @@ size_t chain_image_floats(int n, int k);
 int chain_pack_image(const float* W, int n, int k, int64_t ld, float* img, cudaStream_t s);
 bool chain_shape_ok(int H);
 bool chain_fwd_supported(const Sage3Ctx& c);
-int chain_fwd(Sage3Ctx& c, FoldWs& f, const Tableau& tb, float dt, float* Cout, cudaStream_t s);
+int chain_fwd(Sage3Ctx& c, FoldWs& f, const Tableau& tb, float dt, float* Cout, cudaStream_t s, float* Cout2 = nullptr,
+              const double* coef2 = nullptr);
 bool chain_bwd_supported(const Sage3Ctx& c, const FoldWs& f);
 int chain_bwd(Sage3Ctx& c, FoldWs& f, const Tableau& tb, float dt, bool* has_u, cudaStream_t s);
 

@@ -203,7 +203,8 @@ int FoldWs::prepare(Sage3Ctx& c, cudaStream_t s) {
 }
 
 // Stages of one step: fills cat1[st], cat2[st] from y.  Z_0 is left in z0.
-int FoldWs::forward_stages(Sage3Ctx& c, const Tableau& tb, const float* y, float dt, cudaStream_t s, float* Cout) {
+int FoldWs::forward_stages(Sage3Ctx& c, const Tableau& tb, const float* y, float dt, cudaStream_t s, float* Cout, float* Cout2,
+                           const double* coef2) {
   const int H = c.H, H2 = 2 * c.H;
   const int64_t N = c.N;
   const int64_t nh = N * H2;
@@ -213,7 +214,7 @@ int FoldWs::forward_stages(Sage3Ctx& c, const Tableau& tb, const float* y, float
     q.Bsplit = c.use_tc ? c.s1 : nullptr;
     GN_TRY(gemm_nt(q, s));
   }
-  if (chain_fwd_supported(c)) return chain_fwd(c, *this, tb, dt, Cout, s);   // all stages of the step, graph-resident
+  if (chain_fwd_supported(c)) return chain_fwd(c, *this, tb, dt, Cout, s, Cout2, coef2);   // all stages of the step, graph-resident
   for (int st = 0; st < S; ++st) {
     const float* z = z0;
     if (st > 0) {
@@ -247,6 +248,13 @@ int FoldWs::forward_stages(Sage3Ctx& c, const Tableau& tb, const float* y, float
     GN_TRY(agg_mean_fwd(c.g, c2 + H, H2, c2, H2, H, nullptr, 0, nullptr, 0, s));     // A(h2)
   }
   if (Cout) GN_TRY(combine_solution(c, tb, dt, Cout, s));
+  if (Cout && Cout2 && coef2) {
+    LinComb lc{};
+    lc.out = Cout2; lc.base = nullptr; lc.n = nh; lc.n_terms = 0;
+    for (int j = 0; j < S; ++j)
+      if (coef2[j] != 0.0) { lc.in[lc.n_terms] = cat2[j]; lc.coef[lc.n_terms] = (float)coef2[j] * dt; ++lc.n_terms; }
+    GN_TRY(lincomb(lc, s));
+  }
   return GNODE_OK;
 }
 

@@ -289,6 +289,7 @@ int integrate_dopri5(Field& f, const float* y0, const double* t, int n_t, double
 // ------------------------------------------------------------------------------------------------
 struct Dopri5FoldBufs {
   float *ya, *yb, *k0, *k1, *xs, *err;   // [N, D] each
+  float* Cerr;                           // [N, 2H]  dt sum_s c_err[s] cat2_s
   double* partials; double* dsum;
 };
 
@@ -375,13 +376,16 @@ int integrate_dopri5_folded(Sage3Ctx& c, FoldWs& f, const float* y0, const doubl
     if (!(t0 + dt > t0)) { set_error("dopri5: underflow in dt %g", dt); return GNODE_ERR_SOLVER; }
     const float dtf = (float)dt;
     // seven stages, 2H-wide (stage 6's input is the 5th-order solution: beta[6] == c_sol, FSAL)
-    GN_TRY(f.forward_stages(c, tb, ya, dtf, s));
+    // both 2H-wide stage combinations (solution and error-estimate weights) come out of the stage kernel
+    GN_TRY(f.forward_stages(c, tb, ya, dtf, s, f.Cbuf, b.Cerr, tb.c_err));
     st.nfe += 6;
-    double csum;
-    GN_TRY(combine(tb.c_sol, dtf, &csum));
+    double csum = 0.0, cesum = 0.0;
+    for (int j = 0; j < 7; ++j) { csum += tb.c_sol[j]; cesum += tb.c_err[j]; }
     GN_TRY(project(f.Cbuf, yb, ya, (float)csum * dtf));                 // y1 = y0 + dt sum c_sol k
-    GN_TRY(combine(tb.c_err, dtf, &csum));
-    GN_TRY(project(f.Cbuf, b.err, nullptr, (float)csum * dtf));         // err = dt sum c_err k
+    GN_TRY(project(b.Cerr, b.err, nullptr, (float)cesum * dtf));        // err = dt sum c_err k
+    // (a norm accumulated in the epilogue of this projection -- no err write, no norm pass -- was built and measured in
+    // round 2: 7.5 ms against 2.9 + 1.8 ms for the two kernels at N = 2.3 M, D = 435; the four epilogue warps of the
+    // general engine cannot stream two D-wide operands, so the norm stays a separate copy-speed pass)
     LinComb le{};
     le.n = n; le.n_terms = 1; le.in[0] = b.err; le.coef[0] = 1.f;
     GN_TRY(error_sumsq(le, ya, yb, atolf, rtolf, b.partials, b.dsum, s));
@@ -404,8 +408,9 @@ int integrate_dopri5_folded(Sage3Ctx& c, FoldWs& f, const float* y0, const doubl
         // reference's quartic in the reference's operation order
         GN_TRY(project(f.cat2[0], b.k0, nullptr, 1.f));
         GN_TRY(project(f.cat2[6], b.k1, nullptr, 1.f));
-        GN_TRY(combine(tb.c_mid, dtf, &csum));
-        GN_TRY(project(f.Cbuf, b.xs, nullptr, (float)csum * dtf));
+        double cmsum;
+        GN_TRY(combine(tb.c_mid, dtf, &cmsum));
+        GN_TRY(project(f.Cbuf, b.xs, nullptr, (float)cmsum * dtf));
         while (next_out < n_t && t[next_out] <= t1) {
           const float x = (float)((t[next_out] - t0) / (t1 - t0));
           LinComb lm{};
@@ -648,6 +653,107 @@ extern "C" int gnode_integrate_fixed_bwd(const gnode_graph* g, const gnode_sage3
   return GNODE_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Adjoint backward of the fixed-grid solvers (torchdiffeq odeint_adjoint semantics; the reference trains with plain
+// odeint, scripts/train_gde.py:78-85 -- this is the opt-in alternative SURVEY 8-f4 lists).  For every interval
+// [t_{i-1}, t_i], last to first, the augmented system
+//     d/dt (y, a, g_theta) = ( f(y), -a^T df/dy, -a^T df/dtheta )
+// is integrated BACKWARDS over one step of the same Runge-Kutta scheme (h = t_{i-1} - t_i < 0) from (sol[i], a, g_theta);
+// then a += grad_sol[i-1] and y is reset to the stored sol[i-1], as torchdiffeq does.  Nothing of the forward pass is
+// kept but the solution at the output times: memory O(1) in the number of steps, gradients equal to those of
+// backprop-through-the-solver up to the discretisation error of the backward solve.
+//
+// One vjp per stage yields both parts: with the cotangent (-h c_s) A_s it returns h c_s K^a_s and adds h c_s K^theta_s to
+// the parameter gradients (vjp is linear in its cotangent); stages with c_s = 0 (midpoint's first) run a data-only vjp.
+// ------------------------------------------------------------------------------------------------
+extern "C" size_t gnode_integrate_fixed_adjoint_workspace_bytes(int64_t n_nodes, int32_t node_dim, int32_t hidden_dim,
+                                                                int32_t method) {
+  const Tableau* tb = tableau_for(method);
+  if (!tb || method == GNODE_DOPRI5) return 0;
+  Sage3Ctx c;
+  c.N = n_nodes; c.D = node_dim; c.H = hidden_dim;
+  Arena a(nullptr, 0);
+  c.carve(a, 1, true);
+  const size_t n = (size_t)n_nodes * node_dim;
+  for (int i = 0; i < 2 * tb->S + 4; ++i) a.take<float>(n);
+  return a.off;
+}
+
+extern "C" int gnode_integrate_fixed_adjoint(const gnode_graph* g, const gnode_sage3_params* p, int32_t method,
+                                             const float* sol, const float* t, int32_t n_t, const float* grad_sol,
+                                             float* grad_y0, const gnode_sage3_grads* grads, void* workspace,
+                                             size_t workspace_bytes, gnode_stream_t stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  GN_TRY(check_graph(g, "gnode_integrate_fixed_adjoint"));
+  GN_TRY(check_params(p, "gnode_integrate_fixed_adjoint"));
+  const Tableau* tbp = tableau_for(method);
+  GN_ARG(tbp && method != GNODE_DOPRI5, "gnode_integrate_fixed_adjoint: method %d is not a fixed-grid solver", method);
+  GN_ARG(sol && t && grad_sol && n_t >= 1, "gnode_integrate_fixed_adjoint: null pointer or empty time grid");
+  const Tableau& tb = *tbp;
+  const int S = tb.S;
+  Sage3Ctx c;
+  c.g = *g; c.g_tiles = nullptr; c.g_tile_err = nullptr; c.N = g->n_nodes; c.D = p->node_dim; c.H = p->hidden_dim;
+  Arena a(workspace, workspace_bytes);
+  c.carve(a, 1, true);
+  const size_t n = (size_t)c.N * c.D;
+  float *Ky[kMaxStages], *Q[kMaxStages];
+  for (int i = 0; i < S; ++i) { Ky[i] = a.take<float>(n); Q[i] = a.take<float>(n); }
+  float* Ys = a.take<float>(n);
+  float* As = a.take<float>(n);
+  float* gk = a.take<float>(n);
+  float* adj = a.take<float>(n);
+  GN_ARENA_OK(a, "gnode_integrate_fixed_adjoint");
+  GN_TRY(c.pack(*p, true, s));
+  GN_TRY(c.zero_param_grads(s));
+  const int64_t nn = (int64_t)n;
+
+  GN_CUDA(cudaMemcpyAsync(adj, grad_sol + (int64_t)(n_t - 1) * nn, sizeof(float) * n, cudaMemcpyDeviceToDevice, s));
+  for (int i = n_t - 1; i >= 1; --i) {
+    const float h = t[i - 1] - t[i];                 // negative: the augmented system runs backwards in time
+    const float* y = sol + (int64_t)i * nn;
+    double sigma[kMaxStages];                        // K^a_j = sigma_j Q_j
+    for (int st = 0; st < S; ++st) {
+      const float* Y = y;
+      const float* A = adj;
+      if (st > 0) {
+        GN_TRY(stage_input(tb, st, y, Ky, h, Ys, nn, s));
+        Y = Ys;
+        LinComb lc{};
+        lc.out = As; lc.base = adj; lc.n = nn; lc.n_terms = 0;
+        for (int j = 0; j < st; ++j) {
+          const float cf = (float)(tb.beta[st][j] * (double)h * sigma[j]);
+          if (cf == 0.f) continue;
+          lc.in[lc.n_terms] = Q[j]; lc.coef[lc.n_terms] = cf; ++lc.n_terms;
+        }
+        GN_TRY(lincomb(lc, s));
+        A = As;
+      }
+      GN_TRY(c.eval(Y, Ky[st], nullptr, 1.f, 0, s));           // K^y_s = f(Y_s); intermediates stay in slot 0
+      const double cs = tb.c_sol[st];
+      LinComb lg{};
+      lg.out = gk; lg.base = nullptr; lg.n = nn; lg.n_terms = 1; lg.in[0] = A;
+      if (cs != 0.0) { lg.coef[0] = (float)(-(double)h * cs); sigma[st] = 1.0 / ((double)h * cs); c.skip_wgrad = false; }
+      else { lg.coef[0] = -1.f; sigma[st] = 1.0; c.skip_wgrad = true; }
+      GN_TRY(lincomb(lg, s));
+      GN_TRY(c.vjp(Y, 0, gk, Q[st], s));
+      c.skip_wgrad = false;
+    }
+    // a <- a + h sum_s c_s K^a_s (+ the explicit cotangent of the earlier output point)
+    LinComb lc{};
+    lc.out = adj; lc.base = adj; lc.n = nn; lc.n_terms = 0;
+    for (int st = 0; st < S; ++st) {
+      const float cf = (float)((double)h * tb.c_sol[st] * sigma[st]);
+      if (cf == 0.f) continue;
+      lc.in[lc.n_terms] = Q[st]; lc.coef[lc.n_terms] = cf; ++lc.n_terms;
+    }
+    lc.in[lc.n_terms] = grad_sol + (int64_t)(i - 1) * nn; lc.coef[lc.n_terms] = 1.f; ++lc.n_terms;
+    GN_TRY(lincomb(lc, s));
+  }
+  if (grad_y0) GN_CUDA(cudaMemcpyAsync(grad_y0, adj, sizeof(float) * n, cudaMemcpyDeviceToDevice, s));
+  if (grads) GN_TRY(c.unpack_grads(*grads, s));
+  return GNODE_OK;
+}
+
 namespace gnode {
 
 int rk_step_bwd(Field& f, const Tableau& tb, const float* y, float dt, const RkBwdSrc* src, int n_src,
@@ -789,6 +895,7 @@ void carve_dopri5_fold(Arena& a, Sage3Ctx& c, FoldWs& f, Dopri5FoldBufs& b) {
   const size_t n = (size_t)c.N * c.D;
   b.ya = a.take<float>(n); b.yb = a.take<float>(n); b.k0 = a.take<float>(n);
   b.k1 = a.take<float>(n); b.xs = a.take<float>(n); b.err = a.take<float>(n);
+  b.Cerr = a.take<float>((size_t)c.N * 2 * c.H);
   b.partials = a.take<double>((size_t)norm_blocks((int64_t)n));
   b.dsum = a.take<double>(2);
 }

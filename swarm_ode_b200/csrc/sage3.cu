@@ -169,7 +169,7 @@ int Sage3Ctx::vjp(const float* x, int slot, const float* gk, float* gx, cudaStre
     q.Bsplit = use_tc ? s3T : nullptr;
     GN_TRY(gemm_nt(q, s));
   }
-  {  // dW3cat += gk^T @ cat2      [D, 2H]
+  if (!skip_wgrad) {  // dW3cat += gk^T @ cat2      [D, 2H]
     GemmTN q{};
     q.A = gk; q.lda = D; q.P = D; q.B = c2; q.ldb = H2; q.Q = H2; q.Nrows = N; q.C = dW3cat; q.ldc = H2;
     q.colsumA = db3;                                   // db3 += colsum(gk), fused into the same pass
@@ -184,7 +184,7 @@ int Sage3Ctx::vjp(const float* x, int slot, const float* gk, float* gx, cudaStre
     q.Bsplit = use_tc ? s2T : nullptr;
     GN_TRY(gemm_nt(q, s));
   }
-  {  // dW2cat += g_v2^T @ cat1    [H, 2H]
+  if (!skip_wgrad) {  // dW2cat += g_v2^T @ cat1    [H, 2H]
     GemmTN q{};
     q.A = gv2; q.lda = H; q.P = H; q.B = c1; q.ldb = H2; q.Q = H2; q.Nrows = N; q.C = dW2cat; q.ldc = H2;
     q.colsumA = db2;
@@ -200,12 +200,12 @@ int Sage3Ctx::vjp(const float* x, int slot, const float* gk, float* gx, cudaStre
     q.Bsplit = use_tc ? s1T : nullptr; q.Bchain = use_tc ? ck1T : nullptr;
     GN_TRY(gemm_nt(q, s));
   }
-  {  // dW1cat += gz^T @ x         [2H, D]
+  if (!skip_wgrad) {  // dW1cat += gz^T @ x         [2H, D]
     GemmTN q{};
     q.A = gz; q.lda = H2; q.P = H2; q.B = x; q.ldb = D; q.Q = D; q.Nrows = N; q.C = dW1cat; q.ldc = D;
     GN_TRY(gemm_tn(q, partials, s));
+    GN_TRY(colsum_accum(gz + H, H2, N, H, db1, 1.f, colpart, s));
   }
-  GN_TRY(colsum_accum(gz + H, H2, N, H, db1, 1.f, colpart, s));
   return GNODE_OK;
 }
 

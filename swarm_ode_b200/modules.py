@@ -120,8 +120,11 @@ class GraphODE(nn.Module):
     """Graph neural ODE for trajectory prediction (scripts/train_gde.py:47-106)."""
 
     def __init__(self, node_dim: int, num_agvs: int, num_pickers: int, hidden_dim: int = 64,
-                 ode_solver: str = "euler"):
+                 ode_solver: str = "euler", adjoint: bool = False):
         super().__init__()
+        # adjoint=True (extension; the reference has no such switch): gradients by the adjoint method instead of backprop
+        # through the solver -- odeint_adjoint semantics, fixed-grid solvers only
+        self.adjoint = bool(adjoint)
         self.node_dim = node_dim
         self.num_agvs = num_agvs
         self.num_pickers = num_pickers
@@ -143,6 +146,11 @@ class GraphODE(nn.Module):
         graph = csr_for(edge_index, x0.size(0), holder=batch_data, validate="device" if capturing else "deferred",
                         graph_ptr=getattr(batch_data, "ptr", None),
                         max_graph_nodes=getattr(batch_data, "max_graph_nodes", None))
+        if self.adjoint:
+            from .odeint import odeint_adjoint
+            solution = odeint_adjoint(self.ode_func.bind(graph), x0, time_span, method=self.ode_solver)
+            trajectories = ops.decode_positions(solution, self.position_decoder.weight, self.position_decoder.bias)
+            return {"trajectories": trajectories, "node_features": solution, "batch": batch}
         if self.ode_solver in ("euler", "midpoint", "rk4") and self.position_decoder.out_features <= 8:
             # solver + decoder as one autograd node: lets the backward pass use the factored cotangent of the
             # reference's training loss (see ops._IntegrateDecodeFn)

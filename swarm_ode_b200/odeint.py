@@ -43,7 +43,12 @@ def odeint(func, y0: torch.Tensor, t: torch.Tensor, *, rtol: float = 1e-7, atol:
         graph = func.graph_for(y0)
         params = func.func.param_list()
         if method in _FIXED:
+            if options.get("_adjoint"):
+                return ops.integrate_fixed_adjoint(y0, graph, params, t, method)
             return ops.integrate_fixed(y0, graph, params, t, method)
+        if options.get("_adjoint"):
+            raise GnodeError("odeint_adjoint: the adjoint backward exists for the fixed-grid solvers (euler, midpoint, rk4); "
+                             "dopri5 differentiates by replaying its accepted steps (odeint)")
         sol, stats = ops.integrate_dopri5(y0, graph, params, t, rtol, atol, allreduce=options.get("allreduce"),
                                           max_num_steps=int(options.get("max_num_steps", 0)))
         if sink is not None:
@@ -60,3 +65,16 @@ def odeint(func, y0: torch.Tensor, t: torch.Tensor, *, rtol: float = 1e-7, atol:
     raise GnodeError(
         f"odeint: unsupported vector field {type(func).__name__}. Pass GraphODEFunc.bind(edge_index) or an "
         "ODEFunction; arbitrary Python callables would need an eager fallback, which this package does not have.")
+
+
+def odeint_adjoint(func, y0: torch.Tensor, t: torch.Tensor, *, rtol: float = 1e-7, atol: float = 1e-9,
+                   method: Optional[str] = None, options: Optional[dict] = None, adjoint_params=None) -> torch.Tensor:
+    """``torchdiffeq.odeint_adjoint`` call shape for the graph field with a fixed-grid solver: same forward as ``odeint``,
+    gradients by the adjoint method (the augmented system integrated backwards with the same scheme; O(1) memory in the
+    number of steps).  The reference trains with plain ``odeint`` (scripts/train_gde.py:78-85); this is opt-in.
+    ``adjoint_params`` is accepted for signature compatibility (the field's own parameters are always used)."""
+    if not isinstance(func, BoundGraphODEFunc):
+        raise GnodeError("odeint_adjoint: only the graph field (GraphODEFunc.bind(edge_index)) has an adjoint backward")
+    opts = dict(options or {})
+    opts["_adjoint"] = True
+    return odeint(func, y0, t, rtol=rtol, atol=atol, method=method or "rk4", options=opts)

@@ -227,6 +227,48 @@ class _IntegrateFixedFn(torch.autograd.Function):
         return (gy0, None, None, None, *gw)
 
 
+class _IntegrateFixedAdjointFn(torch.autograd.Function):
+    """Fixed-grid solve whose backward is the ADJOINT method (torchdiffeq.odeint_adjoint semantics): nothing of the
+    forward is kept but the solution; the backward integrates (y, a, dL/dtheta) backwards (gnode_integrate_fixed_adjoint)."""
+
+    @staticmethod
+    def forward(ctx, y0, graph: CSRGraph, method: int, t_host: Tuple[float, ...], *w):
+        class _NoSave:                      # the shared forward keeps a save area only when a gradient is wanted
+            needs_input_grad = (False,)
+        holder = _NoSave()
+        sol, w = _fixed_forward(holder, y0, graph, method, t_host, w)
+        ctx.graph, ctx.method, ctx.t_host = graph, method, t_host
+        ctx.save_for_backward(sol, *w)
+        return sol
+
+    @staticmethod
+    def backward(ctx, gsol):
+        sol, *w = ctx.saved_tensors
+        gsol = _f32(gsol, "grad_solution")
+        T, N, D = sol.shape
+        H = w[0].shape[0]
+        p = _sage3_params(D, H, w)
+        gy0 = torch.empty((N, D), dtype=torch.float32, device=sol.device) if ctx.needs_input_grad[0] else None
+        gw = [torch.zeros_like(t) for t in w]
+        grads = _lib.GnodeSage3Grads(*[t.data_ptr() for t in gw])
+        L = _lib.lib()
+        ws = _ws(L.gnode_integrate_fixed_adjoint_workspace_bytes(N, D, H, ctx.method), sol.device)
+        tarr = _float_array(ctx.t_host)
+        with torch.cuda.device(sol.device):
+            _lib.check(L.gnode_integrate_fixed_adjoint(ctx.graph.ref(), C.byref(p), ctx.method, _lib.ptr(sol), tarr, T,
+                                                       _lib.ptr(gsol), _lib.ptr(gy0), C.byref(grads), _lib.ptr(ws),
+                                                       ws.numel(), _lib.stream_ptr(sol.device)),
+                       "gnode_integrate_fixed_adjoint")
+        return (gy0, None, None, None, *gw)
+
+
+def integrate_fixed_adjoint(y0, graph: CSRGraph, params: Sequence[torch.Tensor], t, method: str) -> torch.Tensor:
+    """``integrate_fixed`` with the adjoint backward (O(1) memory in the number of steps)."""
+    if method not in ("euler", "midpoint", "rk4"):
+        raise ValueError(f"not a fixed-grid method: {method}")
+    return _IntegrateFixedAdjointFn.apply(y0, graph, METHODS[method], _t_to_host(t), *params)
+
+
 _T_CACHE: dict = {}
 
 

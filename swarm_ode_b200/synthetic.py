@@ -223,3 +223,35 @@ def init_weights(module: torch.nn.Module, seed: int = 1, conv3_scale: float = 1.
             if conv3_scale != 1.0 and ".conv3." in "." + name:
                 vals = vals * conv3_scale
             p.copy_(vals.to(p.device))
+
+
+def multi_agent_observation(rng, num_agvs: int, num_pickers: int, racks, grid=(25, 22), p_requested: float = 0.35,
+                            agv_target_prob: float = 0.0):
+    """One joint observation in the row layout ``MultiAgentGraphConverter`` reads (scripts/run_gnode.py:1079-1100):
+    AGV rows ``[carrying, carrying_requested, toggle, y, x, target_y, target_x, ...]``, picker rows ``[y, x, target_y,
+    target_x, ...]``, and in row 0, after the ``7 + 4 (n - 1)`` agent entries, one ``(has_shelf, is_requested)`` pair per
+    rack.  ``racks``: list of ``(x, y, group)`` tuples.  At most ONE AGV gets a target (``agv_target_prob``): two AGVs with
+    targets make the reference's converter raise (hetero.MultiAgentGraphConverter docstring)."""
+    import numpy as np
+    n, n_loc = num_agvs + num_pickers, len(racks)
+    width = 7 + 4 * (n - 1) + 2 * n_loc
+    obs = np.zeros((n, width), dtype=np.float32)
+    obs[:num_agvs, 0:3] = rng.integers(0, 2, (num_agvs, 3))
+    obs[:num_agvs, 3] = rng.integers(0, grid[1], num_agvs)
+    obs[:num_agvs, 4] = rng.integers(0, grid[0], num_agvs)
+    obs[num_agvs:, 0] = rng.integers(0, grid[1], num_pickers)
+    obs[num_agvs:, 1] = rng.integers(0, grid[0], num_pickers)
+    if num_agvs and rng.random() < agv_target_prob:
+        a, r = int(rng.integers(0, num_agvs)), int(rng.integers(0, n_loc))
+        obs[a, 5], obs[a, 6] = racks[r][1], racks[r][0]
+    tail = np.zeros(2 * n_loc, dtype=np.float32)
+    tail[0::2] = rng.random(n_loc) < 0.8
+    tail[1::2] = rng.random(n_loc) < p_requested
+    obs[0, 7 + 4 * (n - 1):] = tail
+    return obs
+
+
+def rack_locations(rng, n_loc: int, grid=(25, 22), groups: int = 4):
+    """``n_loc`` distinct rack cells as hashable ``(x, y, group)`` tuples (what the converter's callers pass)."""
+    cells = rng.permutation(grid[0] * grid[1])[:n_loc]
+    return [(int(c % grid[0]) + 1, int(c // grid[0]) + 1, int(g)) for c, g in zip(cells, rng.integers(0, groups, n_loc))]

@@ -142,3 +142,22 @@ def test_backprop_through_fixed_solver_matches_closed_form():
 def test_invalid_method_raises():
     with pytest.raises(ValueError):
         odeint_ref(lambda t, y: y, torch.ones(1), torch.tensor([0.0, 1.0]), method="rk45")
+
+
+def test_oracle_adjoint_matches_backprop_at_small_steps():
+    """odeint_adjoint_ref (restated torchdiffeq adjoint) against autograd through odeint_ref: both are gradients of the
+    same loss and differ only by the O(dt^4) error of the backward rk4 solve."""
+    from oracle.torchdiffeq_ref import odeint_adjoint_ref
+    torch.manual_seed(0)
+    W = (torch.randn(5, 5, dtype=torch.float64) * 0.3).requires_grad_(True)
+    f = lambda t, x: torch.tanh(x @ W.T)
+    y0 = torch.randn(7, 5, dtype=torch.float64)
+    t = torch.linspace(0, 1, 41, dtype=torch.float64)
+    g = torch.randn(41, 7, 5, dtype=torch.float64)
+    sol, gy0, gp = odeint_adjoint_ref(f, [W], y0, t, g, "rk4")
+    y0r = y0.clone().requires_grad_(True)
+    s2 = odeint_ref(f, y0r, t, method="rk4")
+    (s2 * g).sum().backward()
+    assert torch.equal(sol, s2.detach())
+    assert float((gy0 - y0r.grad).norm() / y0r.grad.norm()) < 1e-8
+    assert float((gp[0] - W.grad).norm() / W.grad.norm()) < 1e-8
