@@ -18,8 +18,11 @@ namespace gnode {
 namespace k128 {
 using namespace chain;
 
-constexpr int NCH = 80;                               // output columns per accumulator chunk
-constexpr int KSTAGE = stage_bytes(NCH);              // 12960 bytes per K block of 16
+// Output columns per accumulator chunk: five chunks cover the row (all of it stays in tensor memory, 448 columns next to
+// the 64-column residual operand): 80 for N <= 400 (D = 399: the medium warehouse), 88 for N <= 440 (D = 435: 19 AGVs +
+// 9 pickers).  The weight image is chunked accordingly.
+constexpr int NCH_A = 80, NCH_B = 88, MAXN_A = 400, MAXN_B = 440;
+__host__ __device__ constexpr int nch_of(int n) { return n <= MAXN_A ? NCH_A : NCH_B; }
 constexpr int NKB = W2H / KB16;                       // 8
 
 struct Args {
@@ -34,10 +37,10 @@ struct Args {
   int dev_flags;   // K128_TRACE builds: bit 0 = weight producer fetches half of every stage (timing experiment)
 };
 
-// chunked weight image: chunk c holds rows [80 c, 80 c + 80) of W [n x 128] (zeros beyond n), each chunk in the chain
+// chunked weight image: chunk c holds rows [NCH c, NCH c + NCH) of W [n x 128] (zeros beyond n), each chunk in the chain
 // format (chain_common.cuh) with one stage per K block of 16
-__global__ void k_pack_k128(const float* __restrict__ W, int n, int64_t ld, uint4* __restrict__ img, int n_chunks) {
-  constexpr int units_per_chunk_plane = NCH + 1, units_per_stage = 10 * units_per_chunk_plane;
+__global__ void k_pack_k128(const float* __restrict__ W, int n, int64_t ld, uint4* __restrict__ img, int n_chunks, int NCH) {
+  const int units_per_chunk_plane = NCH + 1, units_per_stage = 10 * units_per_chunk_plane;
   const int64_t total = (int64_t)n_chunks * NKB * units_per_stage;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int u = (int)(i % units_per_stage);
@@ -100,18 +103,26 @@ __device__ long long g_k128r_trace[128];
 #else
 #define RT(i) do { } while (0)
 #endif
-using k128::NCH; using k128::NKB; using k128::KSTAGE;
+using k128::NKB;
 
-constexpr int KPS = 2;                    // K blocks per ring slot / bulk copy
-constexpr int RING = 2;                   // ring slots of KPS stages
-constexpr int GR = 16, NSLOT = 4, MAXN = 400;
+constexpr int GR = 16, NSLOT = 4;
 static_assert(NSLOT == 4 && TM / GR == 2 * NSLOT, "the span pipeline is written for two rounds of four 16-row slots per block");
-constexpr int T_OFF = 0, B_OFF = t_bytes_of(TM), S_OFF = B_OFF + RING * KPS * KSTAGE;     // 66048, 117888
-constexpr int BIAS_OFF = S_OFF + NSLOT * GR * MAXN * 4;                               // 220288
-constexpr int SMEM = BIAS_OFF + MAXN * 4;                                             // 221888: one CTA per SM
 constexpr int ALO = 448, TMEM_ALL = 512;
 constexpr int WARP_LOAD = 10, WARP_STORE = 11, NTHREADS = 12 * 32;
-static_assert(S_OFF % 16 == 0 && SMEM <= 232448, "span slots must be 16-byte aligned and fit");
+// Shape variants.  The span slots take 4 x 16 x MAXN floats; what is left next to the A tile is the weight ring:
+//   N <= 400: 80-column chunks, ring of 2 slots x 2 K blocks;  N <= 440: 88-column chunks, ring of 3 slots x 1 K block.
+template <int NCH_, int KPS_, int RING_, int MAXN_>
+struct Cfg {
+  static constexpr int NCH = NCH_, KPS = KPS_, RING = RING_, MAXN = MAXN_;
+  static constexpr int KSTAGE = stage_bytes(NCH_);                                      // bytes per K block of 16
+  static constexpr int T_OFF = 0, B_OFF = t_bytes_of(TM), S_OFF = B_OFF + RING_ * KPS_ * KSTAGE;
+  static constexpr int BIAS_OFF = S_OFF + NSLOT * GR * MAXN_ * 4;
+  static constexpr int SMEM = BIAS_OFF + MAXN_ * 4;                                     // one CTA per SM
+  static_assert(5 * NCH_ <= ALO && NCH_ % 8 == 0 && 5 * NCH_ >= MAXN_, "five accumulator chunks next to the residual operand");
+  static_assert(S_OFF % 16 == 0 && SMEM <= 232448, "span slots must be 16-byte aligned and fit");
+};
+using CfgA = Cfg<k128::NCH_A, 2, 2, k128::MAXN_A>;     // 221888 bytes
+using CfgB = Cfg<k128::NCH_B, 1, 3, k128::MAXN_B>;     // 223168 bytes
 
 // 8 TMEM columns starting at `col` of lane quadrant `eq` -> r[]
 __device__ __forceinline__ void tmem_ld8(uint32_t tmem_base, int eq, uint32_t col, uint32_t (&r)[8]) {
@@ -121,30 +132,40 @@ __device__ __forceinline__ void tmem_ld8(uint32_t tmem_base, int eq, uint32_t co
                : "r"(taddr));
 }
 
-// W accumulator columns [c0, c0 + W) of this thread's row: span slot in place (whole 16-row group) or global memory
+__device__ __forceinline__ void tmem_ld4(uint32_t tmem_base, int eq, uint32_t col, uint32_t (&r)[4]) {
+  const uint32_t taddr = tmem_base + ((uint32_t)(32 * eq) << 16) + col;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(taddr));
+}
+
+// W accumulator columns [c0, c0 + W) of this thread's row: span slot in place (whole 16-row group) or global memory.
+// has_base = false: C = scale * acc + bias (the slot holds no base rows and is written, not updated).
 template <int W>
 __device__ __forceinline__ void span_update(float* my_row, const float* biasS, int c0, const uint32_t (&r)[W], int N,
                                             float base_scale, float scale, bool whole, bool valid, const float* brow,
-                                            float* crow) {
+                                            float* crow, bool has_base) {
   if (whole) {
     if (c0 + W <= N) {
 #pragma unroll
       for (int j = 0; j < W; j += 4) {
         const float4 b4 = *reinterpret_cast<const float4*>(biasS + c0 + j);   // same address in every lane: broadcast
-        my_row[c0 + j] = base_scale * my_row[c0 + j] + scale * __uint_as_float(r[j]) + b4.x;
-        my_row[c0 + j + 1] = base_scale * my_row[c0 + j + 1] + scale * __uint_as_float(r[j + 1]) + b4.y;
-        my_row[c0 + j + 2] = base_scale * my_row[c0 + j + 2] + scale * __uint_as_float(r[j + 2]) + b4.z;
-        my_row[c0 + j + 3] = base_scale * my_row[c0 + j + 3] + scale * __uint_as_float(r[j + 3]) + b4.w;
+        float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
+        if (has_base) { o0 = base_scale * my_row[c0 + j]; o1 = base_scale * my_row[c0 + j + 1]; o2 = base_scale * my_row[c0 + j + 2]; o3 = base_scale * my_row[c0 + j + 3]; }
+        my_row[c0 + j] = o0 + scale * __uint_as_float(r[j]) + b4.x;
+        my_row[c0 + j + 1] = o1 + scale * __uint_as_float(r[j + 1]) + b4.y;
+        my_row[c0 + j + 2] = o2 + scale * __uint_as_float(r[j + 2]) + b4.z;
+        my_row[c0 + j + 3] = o3 + scale * __uint_as_float(r[j + 3]) + b4.w;
       }
     } else {
 #pragma unroll
       for (int j = 0; j < W; ++j)
-        if (c0 + j < N) my_row[c0 + j] = base_scale * my_row[c0 + j] + scale * __uint_as_float(r[j]) + biasS[c0 + j];
+        if (c0 + j < N) my_row[c0 + j] = (has_base ? base_scale * my_row[c0 + j] : 0.f) + scale * __uint_as_float(r[j]) + biasS[c0 + j];
     }
   } else if (valid) {
 #pragma unroll
     for (int j = 0; j < W; ++j)
-      if (c0 + j < N) crow[c0 + j] = base_scale * __ldg(brow + c0 + j) + scale * __uint_as_float(r[j]) + biasS[c0 + j];
+      if (c0 + j < N) crow[c0 + j] = (has_base ? base_scale * __ldg(brow + c0 + j) : 0.f) + scale * __uint_as_float(r[j]) + biasS[c0 + j];
   }
 }
 
@@ -152,11 +173,14 @@ __device__ __forceinline__ void bulk_store_1d(void* dst, uint32_t src, uint32_t 
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
 }
 
+template <class CFG>
 __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_k128_rows(const k128::Args a) {
+  constexpr int NCH = CFG::NCH, KPS = CFG::KPS, RING = CFG::RING, MAXN = CFG::MAXN, KSTAGE = CFG::KSTAGE;
+  constexpr int T_OFF = CFG::T_OFF, B_OFF = CFG::B_OFF, S_OFF = CFG::S_OFF, BIAS_OFF = CFG::BIAS_OFF;
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t bar_b_full[RING];
   __shared__ __align__(8) uint64_t bar_b_empty[RING];
-  __shared__ __align__(8) uint64_t bar_a_ready, bar_chunk_full[MAXN / NCH];   // accumulator chunk c complete
+  __shared__ __align__(8) uint64_t bar_a_ready, bar_chunk_full[5];   // accumulator chunk c complete
   __shared__ __align__(8) uint64_t bar_full[NSLOT], bar_done[NSLOT], bar_free[NSLOT];
   __shared__ uint32_t tmem_holder;
   __shared__ int dead_flag;
@@ -178,7 +202,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_k128_rows(const k128::Args
     dead_flag = 0;
     for (int s = 0; s < RING; ++s) { mbar_init(smem_u32(&bar_b_full[s]), 1); mbar_init(smem_u32(&bar_b_empty[s]), 1); }
     mbar_init(smem_u32(&bar_a_ready), WORKERS / 32);
-    for (int c = 0; c < MAXN / NCH; ++c) mbar_init(smem_u32(&bar_chunk_full[c]), 1);
+    for (int c = 0; c < 5; ++c) mbar_init(smem_u32(&bar_chunk_full[c]), 1);
     for (int s = 0; s < NSLOT; ++s) { mbar_init(smem_u32(&bar_full[s]), 1); mbar_init(smem_u32(&bar_done[s]), 2); mbar_init(smem_u32(&bar_free[s]), 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -250,8 +274,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_k128_rows(const k128::Args
           const int64_t r0 = t * TM + (int64_t)g * GR;
           const bool whole = r0 + GR <= M;
           const uint32_t bar = smem_u32(&bar_full[s]);
-          mbar_expect_tx(bar, whole ? slot_bytes : 0u);
-          if (whole) bulk_load_1d(smem_base + S_OFF + s * slot_bytes, a.base + r0 * N, slot_bytes, bar);
+          const bool fetch = whole && a.base != nullptr;       // without a base term the slot is only handed over
+          mbar_expect_tx(bar, fetch ? slot_bytes : 0u);
+          if (fetch) bulk_load_1d(smem_base + S_OFF + s * slot_bytes, a.base + r0 * N, slot_bytes, bar);
         }
       }
     }
@@ -341,7 +366,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_k128_rows(const k128::Args
       const int64_t grow = m0 + 32 * eq + lane;
       const bool valid = grow < M;
       const bool whole = m0 + 32 * eq + (lane & 16) + GR <= M;    // my 16-row group went through the slot
-      const float* brow = a.base + grow * a.ldbase;
+      const bool has_base = a.base != nullptr;
+      const float* brow = has_base ? a.base + grow * a.ldbase : nullptr;
       float* crow = a.C + grow * a.ldc;
       for (int c = 0; c < n_chunks; ++c) {
         if (eq < 2) {
@@ -349,18 +375,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_k128_rows(const k128::Args
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           if (c == n_chunks - 1) RT(1);
         }
-        const int c0 = NCH * c + (NCH / 2) * ehf;       // my 40 columns of the chunk
+        const int c0 = NCH * c + (NCH / 2) * ehf;       // my 40 (44) columns of the chunk
         {
           uint32_t r[32];
           tmem_ld32(tmem_base, eq, (uint32_t)c0, r);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          span_update<32>(my_row, biasS, c0, r, N, base_scale, scale, whole, valid, brow, crow);
+          span_update<32>(my_row, biasS, c0, r, N, base_scale, scale, whole, valid, brow, crow, has_base);
         }
         {
           uint32_t r[8];
           tmem_ld8(tmem_base, eq, (uint32_t)(c0 + 32), r);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          span_update<8>(my_row, biasS, c0 + 32, r, N, base_scale, scale, whole, valid, brow, crow);
+          span_update<8>(my_row, biasS, c0 + 32, r, N, base_scale, scale, whole, valid, brow, crow, has_base);
+        }
+        if (NCH / 2 > 40) {
+          uint32_t r[4];
+          tmem_ld4(tmem_base, eq, (uint32_t)(c0 + 40), r);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          span_update<4>(my_row, biasS, c0 + 40, r, N, base_scale, scale, whole, valid, brow, crow, has_base);
         }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -390,12 +422,16 @@ extern "C" int gnode_k128r_trace(long long* out128) {
 }
 #endif
 
-size_t gemm_k128_image_floats(int n) { return (size_t)((n + k128::NCH - 1) / k128::NCH) * k128::NKB * k128::KSTAGE / 4; }
+size_t gemm_k128_image_floats(int n) {
+  const int nch = k128::nch_of(n);
+  return (size_t)((n + nch - 1) / nch) * k128::NKB * chain::stage_bytes(nch) / 4;
+}
 
 int gemm_k128_pack(const float* W, int n, int64_t ld, float* img, cudaStream_t s) {
-  const int n_chunks = (n + k128::NCH - 1) / k128::NCH;
-  const int64_t total = (int64_t)n_chunks * k128::NKB * 10 * (k128::NCH + 1);
-  k128::k_pack_k128<<<(unsigned)ceil_div64(total, 256), 256, 0, s>>>(W, n, ld, reinterpret_cast<uint4*>(img), n_chunks);
+  const int nch = k128::nch_of(n);
+  const int n_chunks = (n + nch - 1) / nch;
+  const int64_t total = (int64_t)n_chunks * k128::NKB * 10 * (nch + 1);
+  k128::k_pack_k128<<<(unsigned)ceil_div64(total, 256), 256, 0, s>>>(W, n, ld, reinterpret_cast<uint4*>(img), n_chunks, nch);
   GN_LAUNCHED();
   return GNODE_OK;
 }
@@ -405,15 +441,16 @@ bool gemm_k128_supported(const GemmNT& g) {
          g.N >= 16 && (reinterpret_cast<uintptr_t>(g.A) & 15) == 0;
 }
 
-// dense rows on both sides, one base term, N <= 400: the row-major kernel
+// dense rows on both sides, at most one base term, N <= 440: the row-major kernel
 bool gemm_k128_rows_supported(const GemmNT& g) {
-  return gemm_k128_supported(g) && g.base != nullptr && g.base2 == nullptr && g.N <= k128r::MAXN && g.ldc == g.N &&
-         g.ldbase == g.N && (reinterpret_cast<uintptr_t>(g.base) & 15) == 0 && (reinterpret_cast<uintptr_t>(g.C) & 15) == 0;
+  return gemm_k128_supported(g) && g.base2 == nullptr && g.N <= k128::MAXN_B && g.ldc == g.N &&
+         (g.base == nullptr || (g.ldbase == g.N && (reinterpret_cast<uintptr_t>(g.base) & 15) == 0)) &&
+         (reinterpret_cast<uintptr_t>(g.C) & 15) == 0;
 }
 
 static void k128_args(const GemmNT& g, int* status_dev, k128::Args& a) {
   a.A = g.A; a.img = g.Bchain; a.C = g.C; a.ldc = g.ldc; a.M = g.M; a.N = g.N;
-  a.n_chunks = (g.N + k128::NCH - 1) / k128::NCH;
+  a.n_chunks = (g.N + k128::nch_of(g.N) - 1) / k128::nch_of(g.N);
   a.bias = g.bias; a.bias_scale = g.bias_scale;
   a.base = g.base; a.ldbase = g.ldbase; a.base_scale = g.base_scale;
   a.base2 = g.base ? g.base2 : nullptr; a.ldbase2 = g.ldbase2;
@@ -430,15 +467,22 @@ int gemm_k128_rows(const GemmNT& g, cudaStream_t s) {
   if (!status_dev) { set_error("gemm_k128_rows: status symbol unavailable"); return GNODE_ERR_CUDA; }
   k128::Args a{};
   k128_args(g, status_dev, a);
-  if (first_use_on_device(reinterpret_cast<const void*>(&k128r::k_gemm_k128_rows))) {
-    GN_CUDA(cudaFuncSetAttribute(k128r::k_gemm_k128_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, k128r::SMEM));
-  }
   const int64_t m_tiles = (g.M + chain::TM - 1) / chain::TM;
   unsigned grid = (unsigned)(m_tiles < kNumSMs ? m_tiles : kNumSMs);
 #ifdef K128_TRACE
   { const char* e = std::getenv("K128_GRID"); if (e && atoi(e) > 0 && (unsigned)atoi(e) < grid) grid = (unsigned)atoi(e); }
 #endif
-  k128r::k_gemm_k128_rows<<<grid, k128r::NTHREADS, k128r::SMEM, s>>>(a);
+  if (g.N <= k128::MAXN_A) {
+    if (first_use_on_device(reinterpret_cast<const void*>(&k128r::k_gemm_k128_rows<k128r::CfgA>))) {
+      GN_CUDA(cudaFuncSetAttribute(k128r::k_gemm_k128_rows<k128r::CfgA>, cudaFuncAttributeMaxDynamicSharedMemorySize, k128r::CfgA::SMEM));
+    }
+    k128r::k_gemm_k128_rows<k128r::CfgA><<<grid, k128r::NTHREADS, k128r::CfgA::SMEM, s>>>(a);
+  } else {
+    if (first_use_on_device(reinterpret_cast<const void*>(&k128r::k_gemm_k128_rows<k128r::CfgB>))) {
+      GN_CUDA(cudaFuncSetAttribute(k128r::k_gemm_k128_rows<k128r::CfgB>, cudaFuncAttributeMaxDynamicSharedMemorySize, k128r::CfgB::SMEM));
+    }
+    k128r::k_gemm_k128_rows<k128r::CfgB><<<grid, k128r::NTHREADS, k128r::CfgB::SMEM, s>>>(a);
+  }
   GN_LAUNCHED();
   return GNODE_OK;
 }

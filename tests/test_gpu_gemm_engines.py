@@ -130,10 +130,12 @@ def test_k128_wide_output_engine(cuda, m, n, terms):
     _lib.tc_check(cuda)
 
 
-@pytest.mark.parametrize("m,n", [(16, 399), (100, 399), (128 * 148 + 5, 399), (128 * 148 * 3 + 16 * 3 + 9, 399), (5000, 321), (5000, 64)])
+@pytest.mark.parametrize("m,n", [(16, 399), (100, 399), (128 * 148 + 5, 399), (128 * 148 * 3 + 16 * 3 + 9, 399), (5000, 321), (5000, 64),
+                                 (5000, 435), (128 * 148 + 21, 440), (3000, 401), (777, 432)])
 def test_k128_row_major_engine(cuda, m, n):
-    """Row-major variant (k_gemm_k128_rows: dense rows, one base term, N <= 400 -- the y_1 projection): whole 16-row spans
-    through shared memory, a ragged last group updated in global memory, several blocks per CTA; element-wise against float64."""
+    """Row-major variant (k_gemm_k128_rows: dense rows, at most one base term; 80-column chunks for N <= 400, 88-column
+    chunks for N <= 440 -- the y_1 / error / dense-output projections): whole 16-row spans through shared memory, a ragged
+    last group updated in global memory, several blocks per CTA; element-wise against float64, with and without a base."""
     g = torch.Generator().manual_seed(m + n)
     junk = torch.full((8 << 20,), float("nan"), device=cuda)
     del junk
@@ -152,3 +154,10 @@ def test_k128_row_major_engine(cuda, m, n):
         assert rel_l2(got, want) <= 5e-6, rel_l2(got, want)
         err = (got.double().cpu() - want).abs().max().item()
         assert err <= 2e-4, err          # no misplaced row / column anywhere (values are O(10))
+    # no base term: the span slots are written, not updated (they hold NaN from the poisoned heap or the previous call)
+    got = S.ops.gemm_k128(a.to(cuda), w.to(cuda), bias=bias.to(cuda), bias_scale=-1.25, scale=0.75)
+    _lib.tc_check(cuda)
+    want = 0.75 * (a.double() @ w.double().T - 1.25 * bias.double())
+    assert torch.isfinite(got).all()
+    assert rel_l2(got, want) <= 5e-6, rel_l2(got, want)
+    assert (got.double().cpu() - want).abs().max().item() <= 2e-4
