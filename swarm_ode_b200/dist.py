@@ -82,13 +82,15 @@ def dopri5_norm_allreduce(device=None, group=None) -> Optional[Callable[[float, 
 
 def masked_mse_train_step(model, optimizer, graphs, next_positions: torch.Tensor,
                           time_span: Optional[torch.Tensor] = None, max_norm: float = 1.0,
-                          group=None) -> torch.Tensor:
+                          group=None, distributed: Optional[bool] = None) -> torch.Tensor:
     """One training step of scripts/train_gde.py:478-495 on this rank's shard.
 
     forward -> masked MSE -> backward -> (all-reduce) -> clip_grad_norm_(1.0) -> optimizer.step().
     Returns the *global* loss (detached).  With one rank this is exactly the reference step
-    (with the reference's device-mismatch bug at :476/:490 corrected).
+    (with the reference's device-mismatch bug at :476/:490 corrected).  ``distributed=False`` keeps the step local to this
+    process even when a process group exists (a rank-0-only side computation must not enter a collective).
     """
+    use_dist = is_dist() if distributed is None else (bool(distributed) and is_dist())
     if time_span is None:
         time_span = torch.tensor([0.0, 1.0], device=graphs.x.device)
     optimizer.zero_grad(set_to_none=True)
@@ -104,7 +106,7 @@ def masked_mse_train_step(model, optimizer, graphs, next_positions: torch.Tensor
     else:
         loss = torch.nn.functional.mse_loss(pred[mask], target)
     loss.backward()
-    if is_dist():
+    if use_dist:
         # ONE collective per step and no host synchronisation: every rank contributes local_n * [grads, loss] and local_n
         # itself; dividing the sum by the global count reproduces the masked mean of the unsharded batch
         params = [p for p in model.parameters() if p.grad is not None]

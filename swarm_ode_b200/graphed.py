@@ -24,16 +24,15 @@ import torch
 from . import graph as G
 from ._lib import GnodeError
 from .data import Batch
-from .dist import is_dist, masked_mse_train_step
+from .dist import masked_mse_train_step
 
 
 class GraphedTrainStep:
     def __init__(self, model, optimizer, example: Batch, example_next: torch.Tensor,
                  time_span: Optional[torch.Tensor] = None, max_norm: float = 1.0,
                  edge_capacity: Optional[int] = None, warmup: int = 3):
-        if is_dist():
-            raise GnodeError("GraphedTrainStep captures a single-process step (the gradient all-reduce of the multi-GPU "
-                             "step is not captured); use dist.masked_mse_train_step under torch.distributed")
+        # The captured step is LOCAL to this process: no gradient all-reduce is captured.  Under torch.distributed use it only
+        # for per-rank work (e.g. rank-0 evaluation / side benches); data-parallel training uses dist.masked_mse_train_step.
         if not example.x.is_cuda:
             raise GnodeError("GraphedTrainStep needs a CUDA batch")
         if model.ode_solver not in ("euler", "midpoint", "rk4"):
@@ -83,7 +82,8 @@ class GraphedTrainStep:
 
     def _eager_on_static(self):
         self._drop_csr()
-        return masked_mse_train_step(self.model, self.optimizer, self.static, self.static_next, self.time_span, self.max_norm)
+        return masked_mse_train_step(self.model, self.optimizer, self.static, self.static_next, self.time_span, self.max_norm,
+                                     distributed=False)
 
     def _load(self, batch: Batch, nxt: torch.Tensor):
         E = int(batch.edge_index.size(1))
@@ -108,7 +108,8 @@ class GraphedTrainStep:
         """Copies the batch into the static buffers and replays the captured step; returns the loss (a device scalar that
         the next replay overwrites).  A batch that does not fit the captured shapes takes the eager step."""
         if not self.fits(batch, next_positions):
-            return masked_mse_train_step(self.model, self.optimizer, batch, next_positions, self.time_span, self.max_norm)
+            return masked_mse_train_step(self.model, self.optimizer, batch, next_positions, self.time_span, self.max_norm,
+                                         distributed=False)
         self._load(batch, next_positions)
         self.graph.replay()
         self.replays += 1
