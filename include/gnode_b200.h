@@ -65,6 +65,7 @@ typedef void* gnode_stream_t; /* cudaStream_t */
 #define GNODE_PACK_I16 1
 #define GNODE_PACK_F16 2
 #define GNODE_PACK_F32 3
+#define GNODE_PACK_BITS 4   /* column-wise bit packing: gnode_unpack_bits */
 
 const char* gnode_last_error(void);
 int gnode_abi_version(void);
@@ -427,6 +428,12 @@ int gnode_spatial_edges(const float* pos, int64_t n_snap, int32_t n_agents, floa
  * contract, bit-exact.  src / dst: device memory, 16-byte aligned; n: elements.
  * ---------------------------------------------------------------------------------------- */
 int gnode_unpack_features(const void* src, int32_t kind /* GNODE_PACK_* */, int64_t n, float* dst, gnode_stream_t stream);
+/* Column-wise bit-packed features (swarm_ode_b200/data.py:pack_bits): src [rows, row_bytes] bytes, column c of a row at bits
+ * [bit_offsets[c], bit_offsets[c + 1]) of the row's little-endian bit string (widths <= 8; device int32 [cols + 1]);
+ * row_bytes a multiple of 16 with at least one spare byte after the last bit.  dst: fp32 [rows, cols] -- what
+ * `batch.x.to(device)` of the reference delivers (scripts/train_gde.py:475), bit for bit. */
+int gnode_unpack_bits(const void* src, int64_t rows, int32_t cols, int32_t row_bytes, const int32_t* bit_offsets,
+                      float* dst, gnode_stream_t stream);
 int gnode_unpack_edges(const int32_t* src, int64_t n, int64_t* dst, gnode_stream_t stream);
 /* batch[i] = index of the graph that owns node i, from the graph offsets ptr [n_graphs + 1] (PyG Batch.batch / Batch.ptr) */
 int gnode_batch_vector(const int64_t* ptr, int64_t n_graphs, int64_t n_nodes, int64_t* batch, gnode_stream_t stream);

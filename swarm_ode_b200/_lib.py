@@ -18,7 +18,7 @@ LIB_PATH = os.path.join(_HERE, "libgnode_b200.so")
 # ---- constants mirrored from include/gnode_b200.h ----
 GNODE_EULER, GNODE_MIDPOINT, GNODE_RK4_38, GNODE_DOPRI5 = 0, 1, 2, 3
 ENGINE_AUTO, ENGINE_SIMT, ENGINE_TC = 0, 1, 2
-PACK_U8, PACK_I16, PACK_F16, PACK_F32 = 0, 1, 2, 3
+PACK_U8, PACK_I16, PACK_F16, PACK_F32, PACK_BITS = 0, 1, 2, 3, 4
 METHODS = {"euler": GNODE_EULER, "midpoint": GNODE_MIDPOINT, "rk4": GNODE_RK4_38, "dopri5": GNODE_DOPRI5}
 
 
@@ -155,6 +155,7 @@ _SIGNATURES = {
                                                  C.c_size_t, _P]),
     "gnode_spatial_edges": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_float, _P, _P, _P]),
     "gnode_unpack_features": (C.c_int, [_P, C.c_int32, C.c_int64, _P, _P]),
+    "gnode_unpack_bits": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int32, _P, _P, _P]),
     "gnode_unpack_edges": (C.c_int, [_P, C.c_int64, _P, _P]),
     "gnode_batch_vector": (C.c_int, [_P, C.c_int64, C.c_int64, _P, _P]),
 }

@@ -73,6 +73,39 @@ __global__ void __launch_bounds__(256) k_batch_vector(const int64_t* __restrict_
   }
 }
 
+// Column-wise bit packing (GNODE_PACK_BITS): every column c of the [rows, cols] matrix holds non-negative integers below
+// 2^w_c (w_c <= 8, chosen per column when the batch is packed); a row is the little-endian bit string of its columns,
+// column c at bits [off[c], off[c + 1]), padded to row_bytes (a multiple of 16, at least one byte beyond the last bit).
+// Warehouse observations are mostly flags (1 bit) and grid coordinates (5 bits): 105 bytes per 399-column row instead of
+// 399 (u8) or 1596 (fp32).  A block stages UNPACK_ROWS rows in shared memory (16-byte loads), then decodes (row, column)
+// pairs with consecutive threads on consecutive columns: coalesced fp32 stores.
+constexpr int UNPACK_ROWS = 32, UNPACK_MAX_COLS = 2048, UNPACK_MAX_ROW_BYTES = 1024;
+__global__ void __launch_bounds__(256) k_unpack_bits(const uint8_t* __restrict__ src, int64_t rows, int cols, int row_bytes,
+                                                     const int32_t* __restrict__ off, float* __restrict__ dst) {
+  extern __shared__ __align__(16) uint8_t ub_smem[];
+  int32_t* s_off = reinterpret_cast<int32_t*>(ub_smem);                       // [cols + 1]
+  uint8_t* s_rows = ub_smem + (((size_t)(cols + 1) * 4 + 15) & ~(size_t)15);  // [UNPACK_ROWS][row_bytes]
+  for (int i = threadIdx.x; i <= cols; i += blockDim.x) s_off[i] = off[i];
+  const int64_t n_chunks = (rows + UNPACK_ROWS - 1) / UNPACK_ROWS;
+  for (int64_t ch = blockIdx.x; ch < n_chunks; ch += gridDim.x) {
+    const int64_t r0 = ch * UNPACK_ROWS;
+    const int nr = (int)((rows - r0 < UNPACK_ROWS) ? (rows - r0) : UNPACK_ROWS);
+    __syncthreads();                                                           // table loaded / previous chunk decoded
+    const uint4* g = reinterpret_cast<const uint4*>(src + (size_t)r0 * row_bytes);
+    const int n16 = nr * (row_bytes / 16);
+    for (int i = threadIdx.x; i < n16; i += blockDim.x) reinterpret_cast<uint4*>(s_rows)[i] = __ldcs(g + i);
+    __syncthreads();
+    const int total = nr * cols;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+      const int r = i / cols, c = i - r * cols;
+      const int o = s_off[c], w = s_off[c + 1] - o;
+      const uint8_t* p = s_rows + (size_t)r * row_bytes + (o >> 3);
+      const uint32_t v = (((uint32_t)p[0] | ((uint32_t)p[1] << 8)) >> (o & 7)) & ((1u << w) - 1u);
+      dst[(size_t)(r0 + r) * cols + c] = (float)v;
+    }
+  }
+}
+
 unsigned grid_for(int64_t work) {
   int64_t b = ceil_div64(work, 256);
   const int64_t cap = (int64_t)kNumSMs * 16;
@@ -101,6 +134,28 @@ extern "C" int gnode_unpack_features(const void* src, int32_t kind, int64_t n, f
   if (kind == GNODE_PACK_U8) k_unpack_features<GNODE_PACK_U8><<<grid, 256, 0, s>>>(src, n, dst);
   else if (kind == GNODE_PACK_I16) k_unpack_features<GNODE_PACK_I16><<<grid, 256, 0, s>>>(src, n, dst);
   else k_unpack_features<GNODE_PACK_F16><<<grid, 256, 0, s>>>(src, n, dst);
+  GN_LAUNCHED();
+  return GNODE_OK;
+}
+
+extern "C" int gnode_unpack_bits(const void* src, int64_t rows, int32_t cols, int32_t row_bytes, const int32_t* bit_offsets,
+                                 float* dst, gnode_stream_t stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  GN_ARG(rows >= 0 && cols >= 1 && cols <= UNPACK_MAX_COLS && (rows == 0 || (src && dst && bit_offsets)), "gnode_unpack_bits: bad argument");
+  GN_ARG(row_bytes >= 16 && row_bytes % 16 == 0 && row_bytes <= UNPACK_MAX_ROW_BYTES, "gnode_unpack_bits: row_bytes must be a multiple of 16 in [16, %d]",
+         UNPACK_MAX_ROW_BYTES);
+  GN_ARG((reinterpret_cast<uintptr_t>(src) & 15) == 0, "gnode_unpack_bits: the packed buffer must be 16-byte aligned");
+  if (rows == 0) return GNODE_OK;
+  GN_PROF(s, 0.0, (double)rows * row_bytes + 4.0 * (double)rows * cols, "unpack_features kind=bits");
+  const size_t smem = (((size_t)(cols + 1) * 4 + 15) & ~(size_t)15) + (size_t)UNPACK_ROWS * row_bytes;
+  if (first_use_on_device(reinterpret_cast<const void*>(&k_unpack_bits))) {
+    GN_CUDA(cudaFuncSetAttribute(k_unpack_bits, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)((((size_t)(UNPACK_MAX_COLS + 1) * 4 + 15) & ~(size_t)15) + (size_t)UNPACK_ROWS * UNPACK_MAX_ROW_BYTES)));
+  }
+  const int64_t chunks = (rows + UNPACK_ROWS - 1) / UNPACK_ROWS;
+  const int64_t cap = (int64_t)kNumSMs * 8;
+  k_unpack_bits<<<(unsigned)(chunks < cap ? chunks : cap), 256, smem, s>>>(static_cast<const uint8_t*>(src), rows, cols, row_bytes,
+                                                                          bit_offsets, dst);
   GN_LAUNCHED();
   return GNODE_OK;
 }

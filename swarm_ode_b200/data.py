@@ -131,26 +131,90 @@ def narrowest_exact_dtype(x: torch.Tensor):
     return torch.float32, _lib.PACK_F32, "f32"
 
 
+BITS_MAX_COLS, BITS_MAX_ROW_BYTES = 2048, 1024      # limits of gnode_unpack_bits
+
+
+def pack_bits(x: torch.Tensor):
+    """Column-wise bit packing of an fp32 matrix whose entries are integers in [0, 255] (warehouse observations: flags and
+    grid coordinates).  Column ``c`` gets ``w_c = bit_length(max of the column)`` bits; a row is the little-endian bit string
+    of its columns, padded to a multiple of 16 bytes with at least one spare byte.  Returns ``(packed uint8 [rows,
+    row_bytes], bit_offsets int32 [cols + 1])`` or ``None`` when the matrix is not representable (negative, fractional,
+    > 255, -0.0, non-finite values; too many columns) -- the caller then falls back to a wider transport type.
+    Exactness is by construction (every value is an integer below 2^w_c) and is re-checked by ``unpack_bits_host``."""
+    if x.dim() != 2 or x.dtype != torch.float32 or x.shape[1] < 1 or x.shape[1] > BITS_MAX_COLS:
+        return None
+    rows, cols = x.shape
+    if rows == 0:
+        return None
+    if not bool(torch.isfinite(x).all()) or float(x.min()) < 0.0 or float(x.max()) > 255.0:
+        return None
+    xi = x.to(torch.uint8)
+    if not torch.equal(xi.to(torch.float32), x) or bool(((x == 0) & torch.signbit(x)).any()):
+        return None
+    xn = xi.numpy()
+    width = np.array([int(v).bit_length() for v in xn.max(axis=0)], dtype=np.int64)
+    off = np.zeros(cols + 1, dtype=np.int64)
+    off[1:] = np.cumsum(width)
+    row_bytes = int(((off[-1] + 7) // 8 + 1 + 15) // 16 * 16)
+    if row_bytes > BITS_MAX_ROW_BYTES:
+        return None
+    out = np.zeros((rows, row_bytes), dtype=np.uint8)
+    for c in range(cols):
+        if width[c] == 0:
+            continue
+        b, sh = int(off[c] >> 3), int(off[c] & 7)
+        v = xn[:, c].astype(np.uint16) << sh
+        out[:, b] |= (v & 0xFF).astype(np.uint8)
+        if sh + width[c] > 8:
+            out[:, b + 1] |= (v >> 8).astype(np.uint8)
+    return torch.from_numpy(out), torch.from_numpy(off.astype(np.int32))
+
+
+def unpack_bits_host(packed: torch.Tensor, bit_offsets: torch.Tensor) -> torch.Tensor:
+    """Host inverse of ``pack_bits`` (the arithmetic of ``gnode_unpack_bits``): used to verify a packed batch."""
+    p = packed.numpy().astype(np.uint16)
+    off = bit_offsets.numpy().astype(np.int64)
+    cols = off.shape[0] - 1
+    out = np.zeros((p.shape[0], cols), dtype=np.float32)
+    for c in range(cols):
+        w = int(off[c + 1] - off[c])
+        if w == 0:
+            continue
+        b, sh = int(off[c] >> 3), int(off[c] & 7)
+        out[:, c] = (((p[:, b] | (p[:, b + 1] << 8)) >> sh) & ((1 << w) - 1)).astype(np.float32)
+    return torch.from_numpy(out)
+
+
 class PackedBatch:
     """A collated batch in its transport format: what ``batch.to(device)`` of the reference (scripts/train_gde.py:475)
     moves over PCIe, made as small as it can be WITHOUT changing a single bit of what arrives.
 
-    * ``x`` travels in the narrowest type that reproduces every fp32 value exactly (warehouse observations are flags and
-      grid coordinates: u8; the choice is verified element by element when the batch is packed, i.e. at dataset-build
-      time), and is widened to fp32 on the device (``gnode_unpack_features``);
+    * ``x`` travels in the narrowest form that reproduces every fp32 value exactly -- column-wise bit packing for small
+      non-negative integers (warehouse observations are flags and grid coordinates: 105 bytes per 399-column row), else
+      u8 / i16 / f16 / f32; the choice is verified element by element when the batch is packed, i.e. at dataset-build
+      time -- and is widened to fp32 on the device (``gnode_unpack_bits`` / ``gnode_unpack_features``);
     * ``edge_index`` travels as int32 (node ids < 2^31) and is widened to int64 (``gnode_unpack_edges``);
     * ``batch`` is not transported at all: it is a function of ``ptr`` (``gnode_batch_vector``);
     * ``ptr``, ``is_current_agent`` and the targets travel as they are.
 
     ``to(device)`` returns an ordinary :class:`Batch` whose tensors are bit-identical to ``batch.to(device)``."""
 
-    def __init__(self, batch: "Batch", next_positions: Optional[torch.Tensor] = None):
+    def __init__(self, batch: "Batch", next_positions: Optional[torch.Tensor] = None, bits: bool = True):
         if batch.x.is_cuda:
             raise _lib.GnodeError("PackedBatch packs a HOST batch")
         x = batch.x.contiguous()
         dt, self.kind, self.kind_name = narrowest_exact_dtype(x)
         self.x_shape = tuple(x.shape)
         self.x_packed = x if dt == torch.float32 else x.to(dt)
+        self.bit_offsets = None
+        if bits and self.kind == _lib.PACK_U8:
+            # small non-negative integers: column-wise bit widths (flags 1 bit, coordinates 5 bits) beat one byte per value
+            pb = pack_bits(x)
+            if pb is not None and pb[0].shape[1] < x.shape[1]:
+                if not torch.equal(unpack_bits_host(*pb), x):          # the round trip itself, element by element
+                    raise _lib.GnodeError("pack_bits: round trip is not exact")
+                self.x_packed, self.bit_offsets = pb
+                self.kind, self.kind_name = _lib.PACK_BITS, "bits"
         ei = batch.edge_index
         self.num_nodes = int(x.shape[0])
         self.edges_int32 = self.num_nodes < 2 ** 31 and (ei.numel() == 0 or (int(ei.min()) >= 0 and int(ei.max()) < 2 ** 31))
@@ -163,8 +227,8 @@ class PackedBatch:
         self.next_positions = next_positions
 
     def _tensors(self):
-        return [t for t in (self.x_packed, self.edge_index, self.ptr, self.batch, self.is_current_agent, self.next_positions)
-                if t is not None]
+        return [t for t in (self.x_packed, self.bit_offsets, self.edge_index, self.ptr, self.batch, self.is_current_agent,
+                            self.next_positions) if t is not None]
 
     @property
     def nbytes(self) -> int:
@@ -172,7 +236,7 @@ class PackedBatch:
         return sum(t.numel() * t.element_size() for t in self._tensors())
 
     def pin_memory(self) -> "PackedBatch":
-        for k in ("x_packed", "edge_index", "ptr", "batch", "is_current_agent", "next_positions"):
+        for k in ("x_packed", "bit_offsets", "edge_index", "ptr", "batch", "is_current_agent", "next_positions"):
             v = getattr(self, k)
             if v is not None and not v.is_pinned():
                 setattr(self, k, v.pin_memory())
@@ -187,8 +251,14 @@ class PackedBatch:
         with torch.cuda.device(device):
             s = _lib.stream_ptr(device)
             xp = self.x_packed.to(device, non_blocking=non_blocking)
+            bo = None
             if self.kind == _lib.PACK_F32:
                 x = xp
+            elif self.kind == _lib.PACK_BITS:
+                bo = self.bit_offsets.to(device, non_blocking=non_blocking)
+                x = torch.empty(self.x_shape, dtype=torch.float32, device=device)
+                _lib.check(L.gnode_unpack_bits(_lib.ptr(xp), self.x_shape[0], self.x_shape[1], int(xp.shape[1]), _lib.ptr(bo),
+                                               _lib.ptr(x), s), "gnode_unpack_bits")
             else:
                 x = torch.empty(self.x_shape, dtype=torch.float32, device=device)
                 _lib.check(L.gnode_unpack_features(_lib.ptr(xp), self.kind, x.numel(), _lib.ptr(x), s), "gnode_unpack_features")
@@ -214,8 +284,9 @@ class PackedBatch:
                 out.max_graph_nodes = self.max_graph_nodes
             # the packed device copies are read by kernels enqueued on this stream: keep the allocator from recycling them
             # under a different stream before those kernels ran
-            for t in (xp, ep):
-                t.record_stream(torch.cuda.current_stream(device))
+            for t in (xp, ep, bo):
+                if t is not None:
+                    t.record_stream(torch.cuda.current_stream(device))
         if self.next_positions is not None:
             return out, self.next_positions.to(device, non_blocking=non_blocking)
         return out
