@@ -29,7 +29,16 @@ constexpr int CONV_WARPS = 8;
 constexpr int CONV_THREADS = CONV_WARPS * 32;
 constexpr int THREADS = (2 + CONV_WARPS) * 32;   // 320
 constexpr int MAX_RAW = 8, N_OP = 3;
-constexpr int N_TASKS = 5;               // converter tasks per thread: 2 * KS * (wm + wn) <= N_TASKS * CONV_THREADS
+constexpr int N_TASKS = 5;               // converter task budget: 2 * KS * (wm + wn) <= N_TASKS * CONV_THREADS
+// The converter chain of a stage (wait raw -> 4 loads, split -> wait operand slot -> 2 stores -> proxy fence -> arrive) is a
+// serial latency of ~1300 cycles per thread and stage however little work it holds, so the eight converter warps form
+// TN_GROUPS independent groups that take alternate stages: two chains in flight per CTA (narrow operands 0.42 -> 0.37 ms
+// over 1.56 M rows; four groups of two warps spill and lose, a fourth operand stage changes nothing: profiles/r2_ab_tn.txt).
+#ifndef TN_GROUPS
+#define TN_GROUPS 2
+#endif
+constexpr int GROUP_THREADS = CONV_THREADS / TN_GROUPS;
+constexpr int G_TASKS = N_TASKS * TN_GROUPS;   // tasks per thread of a group
 
 struct Args {
   const float* Am; int wm;     // M operand [rows, wm]
@@ -39,8 +48,8 @@ struct Args {
   int64_t n_kb;                // stages (8 * ks row blocks) in total
   int n_raw;                   // raw ring depth
   float* partials;             // [gridDim.x][wn][MW]
-  float* colpart_m;            // optional [gridDim.x][2 * ks][wm]: per-CTA, per-K-chunk column sums of the M operand
-  float* colpart_n;            // optional [gridDim.x][2 * ks][wn]
+  float* colpart_m;            // optional [gridDim.x][TN_GROUPS][2 * ks][wm]: per-CTA, per-group, per-K-chunk column sums of the M operand
+  float* colpart_n;            // optional [gridDim.x][TN_GROUPS][2 * ks][wn]
   int* status;
 };
 
@@ -73,8 +82,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tn_tc(const Args a) {
   const int nkb = (int)(kb1 - kb0);
 
   if (tid == 0) {
-    for (int s = 0; s < NR; ++s) { mbar_init(smem_u32(&bar_raw_full[s]), 1); mbar_init(smem_u32(&bar_raw_empty[s]), CONV_THREADS); }
-    for (int s = 0; s < N_OP; ++s) { mbar_init(smem_u32(&bar_op_full[s]), CONV_THREADS); mbar_init(smem_u32(&bar_op_empty[s]), 1); }
+    for (int s = 0; s < NR; ++s) { mbar_init(smem_u32(&bar_raw_full[s]), 1); mbar_init(smem_u32(&bar_raw_empty[s]), GROUP_THREADS); }
+    for (int s = 0; s < N_OP; ++s) { mbar_init(smem_u32(&bar_op_full[s]), GROUP_THREADS); mbar_init(smem_u32(&bar_op_empty[s]), 1); }
     mbar_init(smem_u32(&bar_acc_full), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -145,17 +154,17 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tn_tc(const Args a) {
     }
   } else {
     // =========================== converters ===========================
-    const int t = tid - 64;
+    const int t = (tid - 64) % GROUP_THREADS, grp = (tid - 64) / GROUP_THREADS;
     // Task tau = kc * (wm + wn) + column: K chunk kc (4 node rows) of one column of the M operand (column < wm) or of
     // the N operand.  src in floats from the raw stage base, dst in bytes from the operand-stage base (hi plane);
     // the lo plane sits lo_off bytes further.
-    int src[N_TASKS], pitch[N_TASKS];
-    uint32_t dst[N_TASKS], lo_off[N_TASKS];
+    int src[G_TASKS], pitch[G_TASKS];
+    uint32_t dst[G_TASKS], lo_off[G_TASKS];
     uint32_t valid = 0;
     const int wsum = wm + wn;
 #pragma unroll
-    for (int q = 0; q < N_TASKS; ++q) {
-      const int task = t + q * CONV_THREADS;
+    for (int q = 0; q < G_TASKS; ++q) {
+      const int task = t + q * GROUP_THREADS;
       src[q] = 0; pitch[q] = 0; dst[q] = 0; lo_off[q] = 0;
       if (task < 2 * KS * wsum) {
         const int kc = task / wsum, col = task - kc * wsum;
@@ -170,26 +179,27 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tn_tc(const Args a) {
         valid |= 1u << q;
       }
     }
-    float csum[N_TASKS];
+    float csum[G_TASKS];
 #pragma unroll
-    for (int q = 0; q < N_TASKS; ++q) csum[q] = 0.f;
-    uint32_t sr = 0, pr = 0, so = 0, po = 0;
-    bool first_lap_o = true, ok = true;
-    for (int i = 0; i < nkb && ok; ++i) {
+    for (int q = 0; q < G_TASKS; ++q) csum[q] = 0.f;
+    bool ok = true;
+    for (int i = grp; i < nkb && ok; i += TN_GROUPS) {
+      const uint32_t sr = (uint32_t)(i % NR), pr = (uint32_t)((i / NR) & 1);
+      const uint32_t so = (uint32_t)(i % N_OP), po = (uint32_t)((i / N_OP) & 1);
       ok = mbar_wait(smem_u32(&bar_raw_full[sr]), pr, status, 13);
       const float* raw = reinterpret_cast<const float*>(smem + (size_t)sr * raw_stage);
-      float v[N_TASKS][4];
+      float v[G_TASKS][4];
 #pragma unroll
-      for (int q = 0; q < N_TASKS; ++q) {
+      for (int q = 0; q < G_TASKS; ++q) {
         if (valid & (1u << q)) {
 #pragma unroll
           for (int e = 0; e < 4; ++e) v[q][e] = raw[src[q] + e * pitch[q]];
         }
       }
-      if (!first_lap_o) ok = ok && mbar_wait(smem_u32(&bar_op_empty[so]), po ^ 1u, status, 14);
+      if (i >= N_OP) ok = ok && mbar_wait(smem_u32(&bar_op_empty[so]), po ^ 1u, status, 14);
       uint8_t* op = smem + op_off + (size_t)so * op_stage;
 #pragma unroll
-      for (int q = 0; q < N_TASKS; ++q) {
+      for (int q = 0; q < G_TASKS; ++q) {
         if (valid & (1u << q)) {
           uint4 h;
           float4 l;
@@ -205,17 +215,16 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tn_tc(const Args a) {
       mbar_arrive(smem_u32(&bar_raw_empty[sr]));
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       mbar_arrive(smem_u32(&bar_op_full[so]));
-      if (++sr == (uint32_t)NR) { sr = 0; pr ^= 1u; }
-      if (++so == (uint32_t)N_OP) { so = 0; po ^= 1u; first_lap_o = false; }
     }
-    // per-CTA column sums: task (kc, column) -> partial [cta][kc][column] of its operand
+    // per-CTA column sums: task (kc, column) of group grp -> partial [cta][grp][kc][column] of its operand
 #pragma unroll
-    for (int q = 0; q < N_TASKS; ++q) {
+    for (int q = 0; q < G_TASKS; ++q) {
       if (valid & (1u << q)) {
-        const int task = t + q * CONV_THREADS;
+        const int task = t + q * GROUP_THREADS;
         const int kc = task / wsum, col = task - kc * wsum;
-        if (col < wm) { if (a.colpart_m) a.colpart_m[((size_t)blockIdx.x * 2 * KS + kc) * wm + col] = csum[q]; }
-        else if (a.colpart_n) a.colpart_n[((size_t)blockIdx.x * 2 * KS + kc) * wn + (col - wm)] = csum[q];
+        const size_t slot = ((size_t)blockIdx.x * TN_GROUPS + grp) * 2 * KS + kc;
+        if (col < wm) { if (a.colpart_m) a.colpart_m[slot * wm + col] = csum[q]; }
+        else if (a.colpart_n) a.colpart_n[slot * wn + (col - wm)] = csum[q];
       }
     }
     // =========================== epilogue (warps 2..5: TMEM lane quadrants 2, 3, 0, 1) ===========================
@@ -334,9 +343,9 @@ namespace tc { int* status_ptr(); }
 bool gemm_tn_tc_supported(const GemmTN& g) { return tctn::plan_for(g).ok; }
 
 size_t gemm_tn_tc_workspace_floats(int P, int Q) {
-  // worst case over both operand roles: kNumSMs partials of [wn][128], plus the column-sum partials [kNumSMs][2][P + Q]
+  // worst case over both operand roles: kNumSMs partials of [wn][128], plus the column-sum partials [kNumSMs][TN_GROUPS][2 ks <= 8][P + Q]
   const int wn = (Q <= tctn::MW && (P > tctn::MW || Q >= P)) ? P : Q;
-  return (size_t)kNumSMs * (size_t)wn * tctn::MW + (size_t)kNumSMs * 8 * (size_t)(P + Q);
+  return (size_t)kNumSMs * (size_t)wn * tctn::MW + (size_t)kNumSMs * 8 * TN_GROUPS * (size_t)(P + Q);
 }
 
 int gemm_tn_simt(const GemmTN& g, float* partials, cudaStream_t s);
@@ -356,7 +365,7 @@ int gemm_tn_tc(const GemmTN& g, float* partials, cudaStream_t s) {
   const float scale_n = p.m_is_b ? g.colsumA_scale : g.colsumB_scale;
   float* cp = partials + (size_t)p.grid * (size_t)p.wn * tctn::MW;
   a.colpart_m = out_m ? cp : nullptr;
-  a.colpart_n = out_n ? cp + (size_t)p.grid * 2 * p.ks * p.wm : nullptr;
+  a.colpart_n = out_n ? cp + (size_t)p.grid * TN_GROUPS * 2 * p.ks * p.wm : nullptr;
   const size_t raw_stage = 32 * (size_t)p.ks * (size_t)(p.wm + p.wn);
   const size_t op_stage = 4 * (size_t)p.ks * ((size_t)tctn::LBO_M + ((size_t)p.nt * p.bn * 16 + 16));
   const size_t budget = 220 * 1024;
@@ -374,7 +383,7 @@ int gemm_tn_tc(const GemmTN& g, float* partials, cudaStream_t s) {
   // C is [P, Q]: with the M operand = B (q = m) the partial index n is p -> rows of C are n
   tctn::k_reduce_tn<<<(unsigned)ceil_div64(cnt * 4, 256), 256, 0, s>>>(partials, p.grid, p.wn, p.wm, g.C, g.ldc,
                                                                     p.m_is_b ? 1 : 0, g.scale, a.colpart_m, out_m, scale_m,
-                                                                    a.colpart_n, out_n, scale_n, p.ks);
+                                                                    a.colpart_n, out_n, scale_n, p.ks * TN_GROUPS);
   GN_LAUNCHED();
   const int64_t done = p.n_kb * tctn::BKR * p.ks;
   if (done < g.Nrows) {   // trailing rows that do not fill a stage: FFMA kernel, accumulated on top
