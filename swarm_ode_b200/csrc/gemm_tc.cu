@@ -47,6 +47,11 @@ __host__ __device__ constexpr int raw_stride(int J) { return J == 4 ? 20 : 16; }
 __host__ __device__ constexpr int raw_bytes(int J) { return BM * raw_stride(J) * 4; }  // 8192 / 10240
 constexpr int STAGING_BYTES = 4 * 32 * 33 * 4;          // 16896
 constexpr int CONV_WARPS = 8;                           // converter warps (2 per SM sub-partition)
+// The converter chain of a stage (wait raw -> loads, split -> wait operand slot -> stores -> proxy fence -> arrive) is a serial
+// latency per stage however little work it holds: the eight warps form CONV_GROUPS groups of four that take alternate stages
+// (each group converts whole stages), so two chains are in flight per CTA (same finding as in gemm_tn_tc.cu).
+// Measured (profiles/r2_ab_tc.txt): K = 399, N = 128 (Z_0: main-loop bound) 0.42 -> 0.36 ms with two groups; N = 399, K = 128
+// (epilogue bound) 4 - 7 % slower: the launcher picks two groups when K >= N, one otherwise.
 constexpr int CONV_THREADS = CONV_WARPS * 32;
 constexpr int WARP_EPI0 = 2 + CONV_WARPS;               // first epilogue warp (10: 10 % 4 == 2, quadrants 2,3,0,1)
 constexpr int WARP_BPROD = WARP_EPI0 + 4;               // B producer warp
@@ -106,7 +111,9 @@ __device__ __forceinline__ void store_rows(const float* __restrict__ stg, int la
   }
 }
 
+template <int CONV_GROUPS>
 __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ CUtensorMap tmapA, const Args a) {
+  constexpr int GROUP_WARPS = CONV_WARPS / CONV_GROUPS;
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t bar_raw_full[MAX_RAW];
   __shared__ __align__(8) uint64_t bar_raw_empty[MAX_RAW];
@@ -145,8 +152,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
   if (tid == 0) {
     // converter barriers count WARPS (lane 0 arrives after __syncwarp): 256 per-thread arrivals on one barrier word are
     // 256 serialised shared-memory atomics per K block and barrier
-    for (int s = 0; s < NR; ++s) { mbar_init(smem_u32(&bar_raw_full[s]), 1); mbar_init(smem_u32(&bar_raw_empty[s]), CONV_WARPS); }
-    for (int s = 0; s < NA; ++s) { mbar_init(smem_u32(&bar_aop_full[s]), CONV_WARPS); }
+    for (int s = 0; s < NR; ++s) { mbar_init(smem_u32(&bar_raw_full[s]), 1); mbar_init(smem_u32(&bar_raw_empty[s]), GROUP_WARPS); }
+    for (int s = 0; s < NA; ++s) { mbar_init(smem_u32(&bar_aop_full[s]), GROUP_WARPS); }
     for (int s = 0; s < NB; ++s) { mbar_init(smem_u32(&bar_b_full[s]), 1); mbar_init(smem_u32(&bar_b_empty[s]), 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&bar_acc_full[b]), 1); mbar_init(smem_u32(&bar_acc_empty[b]), 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -271,11 +278,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
     }
   } else if (warp < WARP_EPI0) {
     // =========================== converters (raw -> tf32 hi/lo planes) ===========================
-    // 8 warps; a warp instruction covers two rows (r, r+4) x 16 k.  Warp cw owns row phase p = cw & 3 of the
-    // 8-row groups q in [8*(cw>>2), 8*(cw>>2)+8):  row = 8q + p + 4*half.
-    constexpr int QPW = 16 / (CONV_WARPS / 4);   // 8-row groups per warp
+    // A warp instruction covers two rows (r, r+4) x 16 k.  Within its group, warp gw owns row phase p = gw & 3 of the 8-row
+    // groups q in [QPW * (gw >> 2), QPW * (gw >> 2) + QPW):  row = 8q + p + 4*half.
+    constexpr int QPW = 16 / (GROUP_WARPS / 4);  // 8-row groups per warp
     const int cw = warp - 2;
-    const int p = cw & 3, q0 = (cw >> 2) * QPW;
+    const int grp = cw / GROUP_WARPS, gw = cw % GROUP_WARPS;
+    const int p = gw & 3, q0 = (gw >> 2) * QPW;
     const int half = lane >> 4, kk = lane & 15;
     const uint32_t kc_off = (uint32_t)(kk >> 2) * LBO_A + (uint32_t)(kk & 3) * 4u;
     // per-thread constant source / destination offsets of its rows
@@ -289,10 +297,15 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
       src_off[q] = ridx * RS + shift + kk;
       dst_off[q] = kc_off + (uint32_t)row * 16u;
     }
-    uint32_t sr = 0, pr = 0, sa = 0, pa = 0;
-    bool first_lap_a = true, ok = true;
+    uint32_t it = 0;
+    bool ok = true;
     for (int64_t t = tile0; t < total_tiles && ok; t += tstep) {
       for (int kb = 0; kb < nkb && ok; ++kb) {
+        const uint32_t i = it++;
+        if ((int)(i % CONV_GROUPS) != grp) continue;          // the other group's stage
+        const uint32_t sr = i % (uint32_t)NR, pr = (i / (uint32_t)NR) & 1u;
+        const uint32_t sa = i % (uint32_t)NA, pa = (i / (uint32_t)NA) & 1u;
+        const bool first_lap_a = i < (uint32_t)NA;
         if (cw == 0) TW(4, ok = mbar_wait(smem_u32(&bar_raw_full[sr]), pr, status, 3)); else ok = mbar_wait(smem_u32(&bar_raw_full[sr]), pr, status, 3);
         const float* raw = reinterpret_cast<const float*>(smem + raw_off + (size_t)sr * RAW_BYTES);
         float v[QPW];
@@ -320,8 +333,6 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
           mbar_arrive(smem_u32(&bar_raw_empty[sr]));                   // raw stage consumed (values are in registers)
           mbar_arrive(smem_u32(&bar_aop_full[sa]));
         }
-        if (++sr == (uint32_t)NR) { sr = 0; pr ^= 1u; }
-        if (++sa == (uint32_t)NA) { sa = 0; pa ^= 1u; first_lap_a = false; }
       }
     }
   } else {
@@ -528,13 +539,15 @@ int gemm_nt_tc(const GemmNT& g, cudaStream_t s) {
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("gemm_nt_tc: cuTensorMapEncodeTiled failed (%d)", (int)r); return GNODE_ERR_CUDA; }
   }
-  if (first_use_on_device(reinterpret_cast<const void*>(&tc::k_gemm_tc))) {
-    GN_CUDA(cudaFuncSetAttribute(tc::k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(225 * 1024)));
+  if (first_use_on_device(reinterpret_cast<const void*>(&tc::k_gemm_tc<1>))) {
+    GN_CUDA(cudaFuncSetAttribute(tc::k_gemm_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(225 * 1024)));
+    GN_CUDA(cudaFuncSetAttribute(tc::k_gemm_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(225 * 1024)));
   }
   if (M_tc > 0) {
     const int64_t total = a.m_tiles * a.n_tiles;
     const unsigned grid = (unsigned)(total < kNumSMs ? total : kNumSMs);
-    tc::k_gemm_tc<<<grid, tc::THREADS, smem, s>>>(tmap, a);
+    if (g.K >= g.N) tc::k_gemm_tc<2><<<grid, tc::THREADS, smem, s>>>(tmap, a);   // main-loop bound: two converter chains
+    else tc::k_gemm_tc<1><<<grid, tc::THREADS, smem, s>>>(tmap, a);
     GN_LAUNCHED();
   }
   if (M_tc < g.M) {   // up to 3 trailing rows that do not fill a super-row: FFMA kernel
