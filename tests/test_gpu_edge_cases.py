@@ -36,6 +36,7 @@ def _run(batch, D, H, solver, cuda, t, conv3_scale=0.05, seed=4):
     assert rel_l2(got["node_features"], want["node_features"]) <= FIXED_TOL
     assert rel_l2(got["trajectories"], want["trajectories"]) <= FIXED_TOL
     rp = dict(ref.named_parameters())
+    worst = (0.0, "", 0.0)
     for name, p in model.named_parameters():
         denom = float(rp[name].grad.norm())
         if denom == 0.0:
@@ -48,6 +49,11 @@ def _run(batch, D, H, solver, cuda, t, conv3_scale=0.05, seed=4):
             # backward contraction switched to FFMA leaves the figure unchanged; FFMA forward removes it).
             e_ours, e_ref32 = rel_l2(p.grad, r64[name].grad), rel_l2(rp[name].grad, r64[name].grad)
             assert e_ours <= GRAD_TOL, (name, rel_l2(p.grad, rp[name].grad), e_ours, e_ref32)
+            if e_ours > worst[0]:
+                worst = (e_ours, name, e_ref32)
+    # the margin under the relaxed tolerance, visible in the log (pytest -s / -rP)
+    print(f"edge-case gradients: worst rel-L2 vs float64 oracle {worst[0]:.2e} ({worst[1]}; the fp32 oracle itself: {worst[2]:.2e}), "
+          f"tolerance {GRAD_TOL:.0e}")
     from swarm_ode_b200 import _lib
     _lib.tc_check(cuda)
 

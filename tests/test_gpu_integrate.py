@@ -280,12 +280,16 @@ def test_dopri5_backward_matches_autograd_through_the_oracle(cuda, t_points, con
     assert rel_l2(out["node_features"], out_ref["node_features"]) <= FIXED_TOL
     assert abs(float(loss) - float(loss_ref)) <= 1e-4 * abs(float(loss_ref))
     rp, r64 = dict(ref.named_parameters()), dict(ref64.named_parameters())
+    worst = 0.0
     for name, p in model.named_parameters():
         assert p.grad is not None, name
         e32 = rel_l2(p.grad, rp[name].grad)
+        worst = max(worst, e32)
         if e32 > FIXED_TOL:
             e_ours, e_ref32 = rel_l2(p.grad, r64[name].grad), rel_l2(rp[name].grad, r64[name].grad)
             assert e_ours <= DOPRI5_GRAD_TOL, (name, e32, e_ours, e_ref32)
+    print(f"dopri5 backward: worst parameter-gradient rel-L2 vs the fp32 oracle {worst:.2e} (gate {FIXED_TOL:.0e}, "
+          f"{DOPRI5_GRAD_TOL:.0e} against float64 where a ReLU branch flip separates the two fp32 runs)")
     e32 = rel_l2(gb.x.grad, rb.x.grad)
     assert e32 <= FIXED_TOL or rel_l2(gb.x.grad, rb64.x.grad) <= DOPRI5_GRAD_TOL, (e32, rel_l2(gb.x.grad, rb64.x.grad))
 
