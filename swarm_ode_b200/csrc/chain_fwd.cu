@@ -395,7 +395,7 @@ __device__ __forceinline__ void chain_fwd_body(const Args& a, uint8_t* smem, uin
         for (int b = 0; b < nblk; ++b) {
           hand_off(b);
           CT(16 * st + 7);
-          if (b == 0) store_tile(a.cat1[st], true);
+          if (b == 0 && a.cat1[st] != nullptr) store_tile(a.cat1[st], true);   // (null: forward-only solve, nobody reads cat1)
           CT(16 * st + 8);
           wait_bar(smem_u32(&bar_acc_full), ph_acc, dead, status, 26);
           ph_acc ^= 1u;
@@ -705,7 +705,8 @@ int chain_fwd(Sage3Ctx& c, FoldWs& f, const Tableau& tb, float dt, float* Cout, 
   chain::Args a{};
   a.z0 = f.z0;
   for (int st = 0; st < tb.S; ++st) {
-    a.cat1[st] = f.cat1[st]; a.cat2[st] = f.cat2[st]; a.mask[st] = f.mask[st];
+    // cat1 and the ReLU sign bits exist for the backward pass only
+    a.cat1[st] = f.forward_only ? nullptr : f.cat1[st]; a.cat2[st] = f.cat2[st]; a.mask[st] = f.forward_only ? nullptr : f.mask[st];
     double bsum = 0.0;
     for (int j = 0; j < st; ++j) { a.coef[st][j] = (float)tb.beta[st][j] * dt; bsum += tb.beta[st][j]; }
     a.c13_scale[st] = (float)bsum * dt;

@@ -76,6 +76,7 @@ struct Sage3Ctx : Field {
 // ---- folded fixed-grid integration (fold.cu): D-wide contractions once per step instead of once per stage ----
 struct FoldWs {
   int S = 0;
+  bool forward_only = false;           // no backward will read this solve's stage slots: the stage kernel skips cat1 / sign bits
   float *M13 = nullptr, *M13T = nullptr, *c13 = nullptr;   // w1cat @ w3cat [2H, 2H], its transpose, w1cat @ b3 [2H]
   float *sM13 = nullptr, *sM13T = nullptr;                 // tf32 hi/lo planes of the two
   float *ci13 = nullptr, *ci13T = nullptr;                 // chain-kernel images of the two

@@ -272,6 +272,7 @@ int integrate_fixed_folded(Sage3Ctx& c, FoldWs& f, const Tableau& tb, const floa
   const int64_t n = c.numel();
   if (sol != y0) GN_CUDA(cudaMemcpyAsync(sol, y0, sizeof(float) * n, cudaMemcpyDeviceToDevice, s));
   GN_TRY(f.prepare(c, s));
+  f.forward_only = save == nullptr;     // without a save area a later backward recomputes the stages itself
   double csum = 0.0;
   for (int st = 0; st < tb.S; ++st) csum += tb.c_sol[st];
   for (int j = 0; j + 1 < n_t; ++j) {

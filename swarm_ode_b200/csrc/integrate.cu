@@ -312,6 +312,7 @@ int integrate_dopri5_folded(Sage3Ctx& c, FoldWs& f, const float* y0, const doubl
   GN_CUDA(cudaMemcpyAsync(ya, y0, sizeof(float) * n, cudaMemcpyDeviceToDevice, s));
   GN_TRY(f.prepare(c, s));
   f.bind_slots(c, nullptr, 0);
+  f.forward_only = true;                // the dopri5 backward replays its accepted steps: nothing of this solve is read back
 
   // k = scale_w * (W @ w3cat^T) + scale_b * b3   for a 2H-wide W; optional base
   auto project = [&](const float* W, float* out, const float* base, float bias_scale) -> int {
