@@ -231,6 +231,13 @@ int gnode_integrate_fixed(const gnode_graph* g, const gnode_sage3_params* p, int
                           const float* y0, const float* t, int32_t n_t, float* sol,
                           void* save, size_t save_bytes,
                           void* workspace, size_t workspace_bytes, gnode_stream_t stream);
+/* flags: GNODE_FIXED_SOL0_BY_CALLER -- sol[0] is NOT written (the first step reads y0 itself); the caller fills it before
+ * anything reads the solution (gnode_decoder_fwd_copy does, as a side effect of decoding the first time point). */
+#define GNODE_FIXED_SOL0_BY_CALLER 1
+int gnode_integrate_fixed_flags(const gnode_graph* g, const gnode_sage3_params* p, int32_t method,
+                                const float* y0, const float* t, int32_t n_t, float* sol,
+                                void* save, size_t save_bytes,
+                                void* workspace, size_t workspace_bytes, int32_t flags, gnode_stream_t stream);
 /* Backprop through the solver (discretise-then-optimise, like autograd through torchdiffeq's
  * fixed-grid loop).  sol is the forward output; grad_sol: device [n_t, n_nodes, D] (cotangent of
  * every saved time point); grad_y0 overwritten (NULL = not wanted: its D-wide contraction is skipped); param grads
@@ -318,6 +325,11 @@ size_t gnode_decoder_workspace_bytes(int64_t m, int32_t node_dim, int32_t n_out)
 int gnode_decoder_fwd(const float* x, int64_t m, int32_t node_dim, int32_t n_out, const float* w,
                       const float* b, float* out, gnode_stream_t stream);
 /* grad_x overwritten (may be NULL); grad_w / grad_b accumulated (+=, may be NULL). */
+/* The same, and the rows of x are also written to copy_out [m, node_dim] as they stream through (NULL: no copy).  Used for
+ * the first time point: `sol[0] = y0` of the solver (gnode_integrate_fixed_flags with GNODE_FIXED_SOL0_BY_CALLER) then costs no
+ * pass of its own. */
+int gnode_decoder_fwd_copy(const float* x, int64_t m, int32_t node_dim, int32_t n_out, const float* w,
+                           const float* b, float* out, float* copy_out, gnode_stream_t stream);
 int gnode_decoder_bwd(const float* x, const float* grad_out, int64_t m, int32_t node_dim,
                       int32_t n_out, const float* w, float* grad_x, float* grad_w, float* grad_b,
                       void* workspace, size_t workspace_bytes, gnode_stream_t stream);

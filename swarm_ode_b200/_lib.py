@@ -102,6 +102,8 @@ _SIGNATURES = {
     "gnode_integrate_fixed_save_bytes": (C.c_size_t, [C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "gnode_integrate_fixed": (C.c_int, [C.POINTER(GnodeGraph), C.POINTER(GnodeSage3Params), C.c_int32, _P,
                                         C.POINTER(C.c_float), C.c_int32, _P, _P, C.c_size_t, _P, C.c_size_t, _P]),
+    "gnode_integrate_fixed_flags": (C.c_int, [C.POINTER(GnodeGraph), C.POINTER(GnodeSage3Params), C.c_int32, _P,
+                                              C.POINTER(C.c_float), C.c_int32, _P, _P, C.c_size_t, _P, C.c_size_t, C.c_int32, _P]),
     "gnode_integrate_fixed_bwd": (C.c_int, [C.POINTER(GnodeGraph), C.POINTER(GnodeSage3Params), C.c_int32, _P,
                                             C.POINTER(C.c_float), C.c_int32, _P, _P, C.POINTER(GnodeSage3Grads), _P,
                                             C.c_size_t, _P, C.c_size_t, _P]),
@@ -124,6 +126,7 @@ _SIGNATURES = {
                                              C.POINTER(GnodeSage3Grads), _P, C.c_size_t, _P]),
     "gnode_decoder_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int32, C.c_int32]),
     "gnode_decoder_fwd": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int32, _P, _P, _P, _P]),
+    "gnode_decoder_fwd_copy": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int32, _P, _P, _P, _P, _P]),
     "gnode_decoder_bwd": (C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, C.c_size_t, _P]),
     "gnode_mlp_ode_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int32, C.c_int32, C.c_int32]),
     "gnode_mlp_rhs_fwd": (C.c_int, [C.POINTER(GnodeMlpParams), _P, C.c_int64, _P, _P, C.c_size_t, _P]),

@@ -13,7 +13,7 @@ constexpr int DEC_THREADS = 256;
 // Generic forward: a warp per row, weights re-read through L1 (any D, n_out <= 8).
 __global__ void __launch_bounds__(DEC_THREADS) k_decoder_fwd(const float* __restrict__ x, int64_t M, int D, int n_out,
                                                              const float* __restrict__ w, const float* __restrict__ b,
-                                                             float* __restrict__ out) {
+                                                             float* __restrict__ out, float* __restrict__ copy_out) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -24,6 +24,7 @@ __global__ void __launch_bounds__(DEC_THREADS) k_decoder_fwd(const float* __rest
     const float* xr = x + m * D;
     for (int c = lane; c < D; c += 32) {
       const float xv = __ldg(xr + c);
+      if (copy_out) copy_out[m * D + c] = xv;
 #pragma unroll
       for (int o = 0; o < kMaxOut; ++o)
         if (o < n_out) acc[o] = fmaf(xv, __ldg(w + (int64_t)o * D + c), acc[o]);
@@ -45,7 +46,7 @@ __global__ void __launch_bounds__(DEC_THREADS) k_decoder_fwd(const float* __rest
 template <int CPL>
 __global__ void __launch_bounds__(DEC_THREADS) k_decoder_fwd2(const float* __restrict__ x, int64_t M, int D,
                                                               const float* __restrict__ w, const float* __restrict__ b,
-                                                              float* __restrict__ out) {
+                                                              float* __restrict__ out, float* __restrict__ copy_out) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -67,6 +68,14 @@ __global__ void __launch_bounds__(DEC_THREADS) k_decoder_fwd2(const float* __res
       const int c = lane + 32 * k;
       va[k] = (c < D) ? __ldg(xa + c) : 0.f;
       vb[k] = (two && c < D) ? __ldg(xb + c) : 0.f;
+    }
+    if (copy_out) {      // the rows pass through registers anyway: also deliver them as a copy (sol[0] = y0 of the solver)
+      float* ca = copy_out + m * D;
+#pragma unroll
+      for (int k = 0; k < CPL; ++k) {
+        const int c = lane + 32 * k;
+        if (c < D) { __stcs(ca + c, va[k]); if (two) __stcs(ca + D + c, vb[k]); }
+      }
     }
     float a0 = 0.f, a1 = 0.f, c0 = 0.f, c1 = 0.f;
 #pragma unroll
@@ -231,20 +240,26 @@ extern "C" size_t gnode_decoder_workspace_bytes(int64_t m, int32_t node_dim, int
 
 extern "C" int gnode_decoder_fwd(const float* x, int64_t m, int32_t node_dim, int32_t n_out, const float* w,
                                  const float* b, float* out, gnode_stream_t stream) {
+  return gnode_decoder_fwd_copy(x, m, node_dim, n_out, w, b, out, nullptr, stream);
+}
+
+extern "C" int gnode_decoder_fwd_copy(const float* x, int64_t m, int32_t node_dim, int32_t n_out, const float* w,
+                                      const float* b, float* out, float* copy_out, gnode_stream_t stream) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   GN_ARG(n_out >= 1 && n_out <= kMaxOut && node_dim >= 1, "gnode_decoder_fwd: n_out must be in [1, %d]", kMaxOut);
   GN_ARG(x && w && out, "gnode_decoder_fwd: null pointer");
+  GN_ARG(copy_out != x, "gnode_decoder_fwd_copy: copy_out aliases x");
   if (m == 0) return GNODE_OK;
   GN_PROF(s, 2.0 * m * node_dim * n_out, 4.0 * (double)m * (node_dim + n_out), "decoder_fwd");
   int64_t blocks = ceil_div64(m * 32, DEC_THREADS);
   if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
   if (n_out == 2 && node_dim <= 32 * 16) {
-    if (node_dim <= 32 * 4) k_decoder_fwd2<4><<<(unsigned)blocks, DEC_THREADS, 0, s>>>(x, m, node_dim, w, b, out);
-    else if (node_dim <= 32 * 8) k_decoder_fwd2<8><<<(unsigned)blocks, DEC_THREADS, 0, s>>>(x, m, node_dim, w, b, out);
-    else if (node_dim <= 32 * 13) k_decoder_fwd2<13><<<(unsigned)blocks, DEC_THREADS, 0, s>>>(x, m, node_dim, w, b, out);
-    else k_decoder_fwd2<16><<<(unsigned)blocks, DEC_THREADS, 0, s>>>(x, m, node_dim, w, b, out);
+    if (node_dim <= 32 * 4) k_decoder_fwd2<4><<<(unsigned)blocks, DEC_THREADS, 0, s>>>(x, m, node_dim, w, b, out, copy_out);
+    else if (node_dim <= 32 * 8) k_decoder_fwd2<8><<<(unsigned)blocks, DEC_THREADS, 0, s>>>(x, m, node_dim, w, b, out, copy_out);
+    else if (node_dim <= 32 * 13) k_decoder_fwd2<13><<<(unsigned)blocks, DEC_THREADS, 0, s>>>(x, m, node_dim, w, b, out, copy_out);
+    else k_decoder_fwd2<16><<<(unsigned)blocks, DEC_THREADS, 0, s>>>(x, m, node_dim, w, b, out, copy_out);
   } else {
-    k_decoder_fwd<<<(unsigned)blocks, DEC_THREADS, 0, s>>>(x, m, node_dim, n_out, w, b, out);
+    k_decoder_fwd<<<(unsigned)blocks, DEC_THREADS, 0, s>>>(x, m, node_dim, n_out, w, b, out, copy_out);
   }
   GN_LAUNCHED();
   return GNODE_OK;

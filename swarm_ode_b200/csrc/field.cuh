@@ -104,8 +104,9 @@ struct FoldWs {
                      float* Cout2 = nullptr, const double* coef2 = nullptr);
   int combine_solution(Sage3Ctx& c, const Tableau& tb, float dt, float* out, cudaStream_t s);
 };
+// sol0_by_caller: sol[0] is not written here (the first step reads y0); the caller fills it (gnode_decoder_fwd_copy)
 int integrate_fixed_folded(Sage3Ctx& c, FoldWs& f, const Tableau& tb, const float* y0, const float* t, int n_t,
-                           float* sol, float* save, cudaStream_t s);
+                           float* sol, float* save, cudaStream_t s, bool sol0_by_caller = false);
 // Cotangent of the last time point given in factored form  G = g1 @ Wd  (g1 [N, n_out], Wd [n_out, D]): what the
 // position decoder hands back when the loss reaches the solution only through it (scripts/train_gde.py:486-490).
 struct LowRankG {
@@ -142,7 +143,8 @@ struct StepSaver {
   virtual float* const* begin_step(int j) = 0;
 };
 int integrate_fixed(Field& f, int method, const float* y0, const float* t, int n_t, float* sol,
-                    float* const* kbuf /* S-1 buffers */, float* xs, cudaStream_t s, StepSaver* saver = nullptr);
+                    float* const* kbuf /* S-1 buffers */, float* xs, cudaStream_t s, StepSaver* saver = nullptr,
+                    bool sol0_by_caller = false);
 
 // Backprop through explicit RK steps of a generic field in direct form (integrate.cu).  A cotangent source is a tensor
 // G together with the stage weights of the output it belongs to:  y_out = y + dt sum_s w[s] k_s  (c_sol for the step's

@@ -267,17 +267,17 @@ int FoldWs::combine_solution(Sage3Ctx& c, const Tableau& tb, float dt, float* ou
 }
 
 int integrate_fixed_folded(Sage3Ctx& c, FoldWs& f, const Tableau& tb, const float* y0, const float* t, int n_t,
-                           float* sol, float* save, cudaStream_t s) {
+                           float* sol, float* save, cudaStream_t s, bool sol0_by_caller) {
   const int H2 = 2 * c.H;
   const int64_t n = c.numel();
-  if (sol != y0) GN_CUDA(cudaMemcpyAsync(sol, y0, sizeof(float) * n, cudaMemcpyDeviceToDevice, s));
+  if (sol != y0 && !sol0_by_caller) GN_CUDA(cudaMemcpyAsync(sol, y0, sizeof(float) * n, cudaMemcpyDeviceToDevice, s));
   GN_TRY(f.prepare(c, s));
   f.forward_only = save == nullptr;     // without a save area a later backward recomputes the stages itself
   double csum = 0.0;
   for (int st = 0; st < tb.S; ++st) csum += tb.c_sol[st];
   for (int j = 0; j + 1 < n_t; ++j) {
     const float dt = t[j + 1] - t[j];
-    const float* y = sol + (int64_t)j * n;
+    const float* y = (j == 0 && sol0_by_caller) ? y0 : sol + (int64_t)j * n;
     float* y1 = sol + (int64_t)(j + 1) * n;
     f.bind_slots(c, save, j);
     GN_TRY(f.forward_stages(c, tb, y, dt, s, f.Cslot));

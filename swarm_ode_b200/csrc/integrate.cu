@@ -101,15 +101,15 @@ static int stage_input(const Tableau& tb, int s_idx, const float* y, float* cons
 // Fixed grid: grid == t, solution[j+1] = y_j + step(y_j)
 // ------------------------------------------------------------------------------------------------
 int integrate_fixed(Field& f, int method, const float* y0, const float* t, int n_t, float* sol,
-                    float* const* kbuf, float* xs_shared, cudaStream_t s, StepSaver* saver) {
+                    float* const* kbuf, float* xs_shared, cudaStream_t s, StepSaver* saver, bool sol0_by_caller) {
   const Tableau* tbp = tableau_for(method);
   if (!tbp || method == GNODE_DOPRI5) { set_error("integrate_fixed: bad method %d", method); return GNODE_ERR_ARG; }
   const Tableau& tb = *tbp;
   const int64_t n = f.numel();
-  if (sol != y0) GN_CUDA(cudaMemcpyAsync(sol, y0, sizeof(float) * n, cudaMemcpyDeviceToDevice, s));
+  if (sol != y0 && !sol0_by_caller) GN_CUDA(cudaMemcpyAsync(sol, y0, sizeof(float) * n, cudaMemcpyDeviceToDevice, s));
   for (int j = 0; j + 1 < n_t; ++j) {
     const float dt = t[j + 1] - t[j];
-    const float* y = sol + (int64_t)j * n;
+    const float* y = (j == 0 && sol0_by_caller) ? y0 : sol + (int64_t)j * n;
     float* y1 = sol + (int64_t)(j + 1) * n;
     const int S = tb.S;
     // with a saver every stage keeps its input and its layer intermediates (slot = stage) for the backward pass
@@ -528,7 +528,15 @@ extern "C" int gnode_integrate_fixed(const gnode_graph* g, const gnode_sage3_par
                                      const float* y0, const float* t, int32_t n_t, float* sol, void* save,
                                      size_t save_bytes, void* workspace, size_t workspace_bytes,
                                      gnode_stream_t stream) {
+  return gnode_integrate_fixed_flags(g, p, method, y0, t, n_t, sol, save, save_bytes, workspace, workspace_bytes, 0, stream);
+}
+
+extern "C" int gnode_integrate_fixed_flags(const gnode_graph* g, const gnode_sage3_params* p, int32_t method,
+                                           const float* y0, const float* t, int32_t n_t, float* sol, void* save,
+                                           size_t save_bytes, void* workspace, size_t workspace_bytes, int32_t flags,
+                                           gnode_stream_t stream) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const bool sol0_by_caller = (flags & GNODE_FIXED_SOL0_BY_CALLER) != 0 && sol != y0;
   GN_TRY(check_graph(g, "gnode_integrate_fixed"));
   GN_TRY(check_params(p, "gnode_integrate_fixed"));
   const Tableau* tb = tableau_for(method);
@@ -547,18 +555,18 @@ extern "C" int gnode_integrate_fixed(const gnode_graph* g, const gnode_sage3_par
     GN_TRY(c.pack(*p, false, s));
     if (save) GN_ARG(save_bytes >= gnode_integrate_fixed_save_bytes(c.N, c.D, c.H, method, n_t),
                      "gnode_integrate_fixed: save buffer too small (%zu bytes)", save_bytes);
-    return integrate_fixed_folded(c, f, *tb, y0, t, n_t, sol, static_cast<float*>(save), s);
+    return integrate_fixed_folded(c, f, *tb, y0, t, n_t, sol, static_cast<float*>(save), s, sol0_by_caller);
   }
   FixedWs w;
   carve_fixed(a, c, *tb, false, w);
   GN_ARENA_OK(a, "gnode_integrate_fixed");
   GN_TRY(c.pack(*p, false, s));
-  if (save == nullptr) return integrate_fixed(c, method, y0, t, n_t, sol, w.kbuf, w.xs[0], s);
+  if (save == nullptr) return integrate_fixed(c, method, y0, t, n_t, sol, w.kbuf, w.xs[0], s, nullptr, sol0_by_caller);
   GN_ARG(save_bytes >= gnode_integrate_fixed_save_bytes(c.N, c.D, c.H, method, n_t),
          "gnode_integrate_fixed: save buffer too small (%zu bytes)", save_bytes);
   Sage3Saver sv{};
   sv.c = &c; sv.S = tb->S; sv.n = (size_t)c.N * c.D; sv.nc = (size_t)c.N * 2 * c.H; sv.base = static_cast<float*>(save);
-  return integrate_fixed(c, method, y0, t, n_t, sol, w.kbuf, w.xs[0], s, &sv);
+  return integrate_fixed(c, method, y0, t, n_t, sol, w.kbuf, w.xs[0], s, &sv, sol0_by_caller);
 }
 
 extern "C" int gnode_integrate_fixed_bwd(const gnode_graph* g, const gnode_sage3_params* p, int32_t method,

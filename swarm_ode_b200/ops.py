@@ -153,9 +153,11 @@ def gnode_rhs(x, graph: CSRGraph, params: Sequence[torch.Tensor]) -> torch.Tenso
 # ----------------------------------------------------------------------------------------------
 # fixed-grid integration with backprop through the solver
 # ----------------------------------------------------------------------------------------------
-def _fixed_forward(ctx, y0, graph: CSRGraph, method: int, t_host: Tuple[float, ...], w):
+def _fixed_forward(ctx, y0, graph: CSRGraph, method: int, t_host: Tuple[float, ...], w, sol0_by_caller: bool = False):
     """Shared forward of the fixed-grid autograd nodes: runs the solve, keeps the save area on ``ctx``.
-    Returns ``(solution, contiguous parameter list)``; the caller does ``ctx.save_for_backward``."""
+    Returns ``(solution, contiguous parameter list)``; the caller does ``ctx.save_for_backward``.
+    ``sol0_by_caller``: ``solution[0]`` is left unwritten -- the caller fills it (the decoder of the first time point
+    streams ``y0`` anyway and delivers the copy as a side effect, ``gnode_decoder_fwd_copy``)."""
     if True:
         y0 = _f32(y0, "y0")
         w = [_f32(t, "param") for t in w]
@@ -182,9 +184,10 @@ def _fixed_forward(ctx, y0, graph: CSRGraph, method: int, t_host: Tuple[float, .
                 except torch.OutOfMemoryError:      # a nearly full device: the backward recomputes the stages instead
                     save = None
         with torch.cuda.device(y0.device):
-            _lib.check(L.gnode_integrate_fixed(graph.ref(), C.byref(p), method, _lib.ptr(y0), tarr, T, _lib.ptr(sol),
-                                               _lib.ptr(save), save.numel() if save is not None else 0,
-                                               _lib.ptr(ws), ws.numel(), _lib.stream_ptr(y0.device)),
+            _lib.check(L.gnode_integrate_fixed_flags(graph.ref(), C.byref(p), method, _lib.ptr(y0), tarr, T, _lib.ptr(sol),
+                                                     _lib.ptr(save), save.numel() if save is not None else 0,
+                                                     _lib.ptr(ws), ws.numel(), 1 if sol0_by_caller else 0,
+                                                     _lib.stream_ptr(y0.device)),
                        "gnode_integrate_fixed")
         graph.schedule_tile_check()
         ctx.graph, ctx.method, ctx.t_host, ctx.save = graph, method, t_host, save
@@ -493,15 +496,20 @@ class _IntegrateDecodeFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, y0, graph: CSRGraph, method: int, t_host: Tuple[float, ...], dec_w, dec_b, *w):
         ctx.set_materialize_grads(False)
-        sol, w = _fixed_forward(ctx, y0, graph, method, t_host, w)            # fills ctx.{graph,method,t_host,save,fold}
+        y0 = _f32(y0, "y0")
+        sol, w = _fixed_forward(ctx, y0, graph, method, t_host, w, sol0_by_caller=True)   # fills ctx.{graph,method,t_host,save,fold}
         dec_w, dec_b = _f32(dec_w, "position_decoder.weight"), _f32(dec_b, "position_decoder.bias")
         T, N, D = sol.shape
         n_out = dec_w.shape[0]
         traj = torch.empty((T, N, n_out), dtype=torch.float32, device=sol.device)
         L = _lib.lib()
         with torch.cuda.device(sol.device):
-            _lib.check(L.gnode_decoder_fwd(_lib.ptr(sol), T * N, D, n_out, _lib.ptr(dec_w), _lib.ptr(dec_b), _lib.ptr(traj),
-                                           _lib.stream_ptr(sol.device)), "gnode_decoder_fwd")
+            # first time point: decode y0 and write solution[0] in the same pass (no separate copy of the D-wide state)
+            _lib.check(L.gnode_decoder_fwd_copy(_lib.ptr(y0), N, D, n_out, _lib.ptr(dec_w), _lib.ptr(dec_b), _lib.ptr(traj),
+                                                _lib.ptr(sol), _lib.stream_ptr(sol.device)), "gnode_decoder_fwd_copy")
+            if T > 1:
+                _lib.check(L.gnode_decoder_fwd(_lib.ptr(sol[1:]), (T - 1) * N, D, n_out, _lib.ptr(dec_w), _lib.ptr(dec_b),
+                                               _lib.ptr(traj[1:]), _lib.stream_ptr(sol.device)), "gnode_decoder_fwd")
         ctx.save_for_backward(sol, dec_w, *w)
         return sol, traj
 
