@@ -217,7 +217,15 @@ __device__ __forceinline__ void chain_fwd_body(const Args& a, uint8_t* smem, uin
             }
           }
         }
-        for (int p = pb_; p < pe_; ++p) {          // neighbours beyond the NBR_REG kept in registers
+        // neighbours beyond the NBR_REG kept in registers: ids fetched eight at a time (one dependent global / L2 load per
+        // neighbour made rows of dense graphs a ~250-cycle latency chain per neighbour)
+        // Tiles of one block (NB = 1, the medium warehouse) keep the scalar loop: the eight-wide id batch costs the forward
+        // kernel 4 % there through register pressure (A/B in profiles/r2_ab_idbatch.txt); two-block tiles (graphs of 129 .. 256
+        // nodes, where dense graphs live) fetch ids eight at a time: forward chain of the 256-agent complete graphs 4.68 -> 2.27
+        // ms.  (The backward kernel keeps its scalar loop: every variant of the batch, and splitting it into two kernels as
+        // here, cost its one-block path 2.5 - 3.6 %.)
+        if (NB == 1) {
+        for (int p = pb_; p < pe_; ++p) {
           const int nb = a.col[p] - r0;
           if (nb < 0 || nb >= nr) { *a.err = 1; continue; }
 #pragma unroll
@@ -225,6 +233,24 @@ __device__ __forceinline__ void chain_fwd_body(const Args& a, uint8_t* smem, uin
             const float4 v = *Tp(c0 + i, nb);
             acc[i].x += v.x; acc[i].y += v.y; acc[i].z += v.z; acc[i].w += v.w;
           }
+        }
+        } else {
+        for (int p = pb_; p < pe_; p += 8) {
+          int ids[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) ids[q] = (p + q < pe_) ? __ldg(a.col + p + q) - r0 : -1;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const int nb = ids[q];
+            if (p + q >= pe_) continue;
+            if (nb < 0 || nb >= nr) { *a.err = 1; continue; }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 v = *Tp(c0 + i, nb);
+              acc[i].x += v.x; acc[i].y += v.y; acc[i].z += v.z; acc[i].w += v.w;
+            }
+          }
+        }
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i) { acc[i].x *= w; acc[i].y *= w; acc[i].z *= w; acc[i].w *= w; }
@@ -491,6 +517,10 @@ __device__ __forceinline__ void chain_fwd_body(const Args& a, uint8_t* smem, uin
 
 }
 
+// TWO_BLOCK selects the family of tile variants compiled into the kernel: tiles of <= 128 rows, or tiles of two 128-row
+// blocks (graphs of 129 .. 256 nodes).  Two kernels instead of one: register allocation of the hot one-block variants is
+// then independent of the two-block code (a shared kernel cost the one-block path 4 % when the two-block path changed).
+template <bool TWO_BLOCK>
 __global__ void __launch_bounds__(THREADS, 2) k_chain_fwd(const Args a) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t bar_b_full[MAX_SLOTS];
@@ -532,7 +562,7 @@ __global__ void __launch_bounds__(THREADS, 2) k_chain_fwd(const Args a) {
 #define CHAIN_TR_SMALL 96
 #endif
   // (the host launches with the shared memory of the variant the batch's largest graph needs: a.tile_rows)
-  if (a.tile_rows <= TM) {
+  if (!TWO_BLOCK) {
     if (s_tr <= CHAIN_TR_SMALL) chain_fwd_body<CHAIN_TR_SMALL, 1>(a, smem, bar_b_full, bar_b_empty, &bar_a_ready, &bar_acc_full, tmem_base, &dead_flag);
     else chain_fwd_body<128, 1>(a, smem, bar_b_full, bar_b_empty, &bar_a_ready, &bar_acc_full, tmem_base, &dead_flag);
   } else if (a.tile_rows <= TR_MID) {
@@ -725,16 +755,19 @@ int chain_fwd(Sage3Ctx& c, FoldWs& f, const Tableau& tb, float dt, float* Cout, 
   a.err = c.g_tile_err;
   GN_PROF(s, (double)c.N * tb.S * (2.0 * 128 * 128 + 2.0 * 128 * 64), 4.0 * (double)c.N * 128 * (2 + 2.0 * tb.S),
           "chain_fwd S=%d", tb.S);
-  if (first_use_on_device(reinterpret_cast<const void*>(&chain::k_chain_fwd))) {
-    GN_CUDA(cudaFuncSetAttribute(chain::k_chain_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, chain::SMEM_BYTES_BIG));
-    GN_CUDA(cudaFuncSetAttribute(chain::k_chain_fwd, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  if (first_use_on_device(reinterpret_cast<const void*>(&chain::k_chain_fwd<false>))) {
+    GN_CUDA(cudaFuncSetAttribute(chain::k_chain_fwd<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, chain::SMEM_BYTES));
+    GN_CUDA(cudaFuncSetAttribute(chain::k_chain_fwd<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    GN_CUDA(cudaFuncSetAttribute(chain::k_chain_fwd<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, chain::SMEM_BYTES_BIG));
+    GN_CUDA(cudaFuncSetAttribute(chain::k_chain_fwd<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
   }
   const bool big = a.tile_rows > chain::TR_MID;       // tiles of 145 .. 256 rows: one CTA per SM
   unsigned grid = (big ? 1 : 2) * kNumSMs;
 #ifdef CHAIN_TRACE
   { const char* e = std::getenv("CHAIN_GRID"); if (e && atoi(e) > 0) grid = (unsigned)atoi(e); }
 #endif
-  chain::k_chain_fwd<<<grid, chain::THREADS, chain::smem_bytes_of(a.tile_rows), s>>>(a);
+  if (a.tile_rows <= chain::TM) chain::k_chain_fwd<false><<<grid, chain::THREADS, chain::smem_bytes_of(a.tile_rows), s>>>(a);
+  else chain::k_chain_fwd<true><<<grid, chain::THREADS, chain::smem_bytes_of(a.tile_rows), s>>>(a);
   GN_LAUNCHED();
   return GNODE_OK;
 }
