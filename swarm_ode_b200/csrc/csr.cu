@@ -128,14 +128,15 @@ __global__ void k_fill(const int64_t* __restrict__ ei, int64_t E, int64_t N,
 
 constexpr int kShortRow = 16;
 
-// rank sort, one thread per short row (deg <= kShortRow); long rows are left to k_sort_long
+// rank sort, one thread per short row (deg <= kShortRow); long rows are listed for k_sort_long (a warp per row of a grid
+// over ALL rows cost 31 us per CSR on the 389 k-node bench batch, which has no long row at all)
 __global__ void k_sort_short(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ in,
-                             int32_t* __restrict__ out, int64_t N) {
+                             int32_t* __restrict__ out, int64_t N, int32_t* __restrict__ long_rows, int32_t* __restrict__ n_long) {
   int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (r >= N) return;
   int b = rowptr[r], e = rowptr[r + 1];
   int d = e - b;
-  if (d > kShortRow) return;
+  if (d > kShortRow) { long_rows[atomicAdd(n_long, 1)] = (int32_t)r; return; }
   int v[kShortRow];
 #pragma unroll
   for (int i = 0; i < kShortRow; ++i) v[i] = (i < d) ? in[b + i] : 0x7fffffff;
@@ -152,23 +153,24 @@ __global__ void k_sort_short(const int32_t* __restrict__ rowptr, const int32_t* 
   }
 }
 
-// rank sort, one warp per long row
+// rank sort, one warp per listed long row (the list order is arbitrary; every row is sorted on its own: deterministic)
 __global__ void k_sort_long(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ in,
-                            int32_t* __restrict__ out, int64_t N) {
-  int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-  int lane = threadIdx.x & 31;
-  if (r >= N) return;
-  int b = rowptr[r], e = rowptr[r + 1];
-  int d = e - b;
-  if (d <= kShortRow) return;
-  for (int i = lane; i < d; i += 32) {
-    int vi = in[b + i];
-    int rank = 0;
-    for (int j = 0; j < d; ++j) {
-      int vj = in[b + j];
-      rank += (vj < vi) || (vj == vi && j < i);
+                            int32_t* __restrict__ out, const int32_t* __restrict__ long_rows, const int32_t* __restrict__ n_long) {
+  const int lane = threadIdx.x & 31;
+  const int n = *n_long;
+  const int warps = (int)((gridDim.x * (int64_t)blockDim.x) >> 5);
+  for (int idx = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5); idx < n; idx += warps) {
+    const int r = long_rows[idx];
+    const int b = rowptr[r], d = rowptr[r + 1] - b;
+    for (int i = lane; i < d; i += 32) {
+      int vi = in[b + i];
+      int rank = 0;
+      for (int j = 0; j < d; ++j) {
+        int vj = in[b + j];
+        rank += (vj < vi) || (vj == vi && j < i);
+      }
+      out[b + rank] = vi;
     }
-    out[b + rank] = vi;
   }
 }
 
@@ -184,7 +186,7 @@ int scan_counts(const int32_t* cnt, int64_t N, int32_t* rowptr, int32_t* sums, c
 }
 
 struct CsrWs {
-  int32_t *cnt_in, *cnt_out, *sums, *col_u, *t_col_u, *flag;
+  int32_t *cnt_in, *cnt_out, *sums, *col_u, *t_col_u, *flag, *n_long;
 };
 
 CsrWs carve(Arena& a, int64_t N, int64_t E) {
@@ -195,6 +197,7 @@ CsrWs carve(Arena& a, int64_t N, int64_t E) {
   w.col_u = a.take<int32_t>(E > 0 ? E : 1);
   w.t_col_u = a.take<int32_t>(E > 0 ? E : 1);
   w.flag = a.take<int32_t>(1);
+  w.n_long = a.take<int32_t>(2);
   return w;
 }
 
@@ -241,14 +244,18 @@ extern "C" int gnode_csr_build_async(const int64_t* edge_index, int64_t E, int64
                                        w.col_u, w.t_col_u);
     GN_LAUNCHED();
     unsigned rb = (unsigned)ceil_div64(N, threads);
-    unsigned wb = (unsigned)ceil_div64(N * 32, threads);
-    k_sort_short<<<rb, threads, 0, s>>>(rowptr, w.col_u, col, N);
+    // long rows: listed by the short-row pass (the fill cursors cnt_in / cnt_out are free again and hold the lists), sorted by a
+    // fixed grid of warps that walks the list
+    int64_t wb64 = ceil_div64(N * 32, threads);
+    unsigned wb = (unsigned)(wb64 < kNumSMs * 8 ? wb64 : kNumSMs * 8);
+    GN_CUDA(cudaMemsetAsync(w.n_long, 0, 2 * sizeof(int32_t), s));
+    k_sort_short<<<rb, threads, 0, s>>>(rowptr, w.col_u, col, N, w.cnt_in, w.n_long);
     GN_LAUNCHED();
-    k_sort_long<<<wb, threads, 0, s>>>(rowptr, w.col_u, col, N);
+    k_sort_long<<<wb, threads, 0, s>>>(rowptr, w.col_u, col, w.cnt_in, w.n_long);
     GN_LAUNCHED();
-    k_sort_short<<<rb, threads, 0, s>>>(t_rowptr, w.t_col_u, t_col, N);
+    k_sort_short<<<rb, threads, 0, s>>>(t_rowptr, w.t_col_u, t_col, N, w.cnt_out, w.n_long + 1);
     GN_LAUNCHED();
-    k_sort_long<<<wb, threads, 0, s>>>(t_rowptr, w.t_col_u, t_col, N);
+    k_sort_long<<<wb, threads, 0, s>>>(t_rowptr, w.t_col_u, t_col, w.cnt_out, w.n_long + 1);
     GN_LAUNCHED();
   }
   return GNODE_OK;

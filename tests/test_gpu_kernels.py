@@ -12,7 +12,7 @@ pytestmark = pytest.mark.gpu
 
 
 # ---------------------------------------------------------------- CSR
-@pytest.mark.parametrize("n,e,seed", [(1, 0, 0), (7, 0, 1), (50, 200, 2), (1000, 5000, 3), (300, 30000, 4), (5000, 4, 5)])
+@pytest.mark.parametrize("n,e,seed", [(1, 0, 0), (7, 0, 1), (50, 200, 2), (1000, 5000, 3), (300, 30000, 4), (5000, 4, 5), (2000, 34000, 6), (40000, 90000, 7)])
 def test_csr_matches_numpy(cuda, n, e, seed):
     ei = random_graph(n, e, seed)
     g = S.CSRGraph(ei.to(cuda), n)
