@@ -156,18 +156,25 @@ __global__ void k_sort_short(const int32_t* __restrict__ rowptr, const int32_t* 
 // rank sort, one warp per listed long row (the list order is arbitrary; every row is sorted on its own: deterministic)
 __global__ void k_sort_long(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ in,
                             int32_t* __restrict__ out, const int32_t* __restrict__ long_rows, const int32_t* __restrict__ n_long) {
-  const int lane = threadIdx.x & 31;
+  constexpr int kStage = 512;                        // ids of a row staged in shared memory per warp (longer rows: from global)
+  __shared__ int32_t s_row[8][kStage];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int n = *n_long;
   const int warps = (int)((gridDim.x * (int64_t)blockDim.x) >> 5);
   for (int idx = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5); idx < n; idx += warps) {
     const int r = long_rows[idx];
     const int b = rowptr[r], d = rowptr[r + 1] - b;
+    const bool staged = d <= kStage;
+    __syncwarp();
+    if (staged) for (int i = lane; i < d; i += 32) s_row[wib][i] = in[b + i];
+    __syncwarp();
     for (int i = lane; i < d; i += 32) {
-      int vi = in[b + i];
+      const int vi = staged ? s_row[wib][i] : in[b + i];
       int rank = 0;
-      for (int j = 0; j < d; ++j) {
-        int vj = in[b + j];
-        rank += (vj < vi) || (vj == vi && j < i);
+      if (staged) {
+        for (int j = 0; j < d; ++j) { const int vj = s_row[wib][j]; rank += (vj < vi) || (vj == vi && j < i); }   // broadcast reads
+      } else {
+        for (int j = 0; j < d; ++j) { const int vj = in[b + j]; rank += (vj < vi) || (vj == vi && j < i); }
       }
       out[b + rank] = vi;
     }
