@@ -43,6 +43,9 @@ def parse():
     ap.add_argument("--checkpoint-every", type=int, default=50)
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--wandb", action="store_true")
+    ap.add_argument("--cuda-graph", action="store_true",
+                    help="single GPU, fixed-grid solver: replay the training step as ONE CUDA graph (swarm_ode_b200.GraphedTrainStep); "
+                         "at the reference's batch size of 32 the eager step is bound by ~100 launches, not by the GPU")
     return ap.parse_args()
 
 
@@ -77,7 +80,9 @@ def main():
     if world > 1:   # identical initial weights on every rank
         for p in model.parameters():
             dist.broadcast(p.data, src=0)
-    opt = torch.optim.Adam(model.parameters(), lr=args.lr, weight_decay=args.weight_decay, fused=True)
+    use_graph = args.cuda_graph and world == 1 and args.ode_solver != "dopri5"
+    opt = torch.optim.Adam(model.parameters(), lr=args.lr, weight_decay=args.weight_decay, fused=True, capturable=use_graph)
+    graphed = None
     save_dir = os.path.join(args.save_dir, time.strftime("%Y%m%d_%H%M%S"))
     if rank == 0:
         os.makedirs(save_dir, exist_ok=True)
@@ -102,7 +107,14 @@ def main():
             if world > 1 and len(perm[b0:b0 + args.batch_size]) < world:
                 continue
             batch = ds.collate(mine)
-            tot += masked_mse_train_step(model, opt, batch.graphs, batch.next_positions, time_span)
+            if use_graph and graphed is None and len(mine) == args.batch_size:
+                # captured on the first full batch; later batches are copied into its static buffers (a batch of another size,
+                # e.g. the last one of an epoch, takes the eager step)
+                graphed = S.GraphedTrainStep(model, opt, batch.graphs, batch.next_positions, time_span)
+            if graphed is not None:
+                tot += graphed.step(batch.graphs, batch.next_positions)
+            else:
+                tot += masked_mse_train_step(model, opt, batch.graphs, batch.next_positions, time_span)
             nb += 1
         train_loss = float(tot) / max(nb, 1)
         model.eval()
@@ -124,6 +136,8 @@ def main():
         # raises GnodeError instead of training on with invalid results
         S.graph.poll_pending()
         S._lib.tc_check(dev)
+        if graphed is not None:
+            graphed.check()
         if rank == 0:
             if val_loss < best:
                 best = val_loss

@@ -30,7 +30,7 @@ from .dist import masked_mse_train_step
 class GraphedTrainStep:
     def __init__(self, model, optimizer, example: Batch, example_next: torch.Tensor,
                  time_span: Optional[torch.Tensor] = None, max_norm: float = 1.0,
-                 edge_capacity: Optional[int] = None, warmup: int = 3):
+                 edge_capacity: Optional[int] = None, warmup: int = 3, preserve_state: bool = True):
         # The captured step is LOCAL to this process: no gradient all-reduce is captured.  Under torch.distributed use it only
         # for per-rank work (e.g. rank-0 evaluation / side benches); data-parallel training uses dist.masked_mse_train_step.
         if not example.x.is_cuda:
@@ -60,6 +60,12 @@ class GraphedTrainStep:
         self.static_next = torch.empty_like(example_next)
         self._shape = (tuple(example.x.shape), int(example_next.numel()), int(example.batch.numel()))
         self._load(example, example_next)
+        # The warm-up steps below are real optimizer steps: with preserve_state the weights and the optimizer state are put
+        # back afterwards, IN PLACE (the graph holds their addresses), so that training continues from where it was.
+        params = [p for g in optimizer.param_groups for p in g["params"]]
+        snap_p = [p.detach().clone() for p in params] if preserve_state else None
+        snap_s = ({id(p): {k: v.detach().clone() for k, v in optimizer.state[p].items() if torch.is_tensor(v)}
+                   for p in params if p in optimizer.state} if preserve_state else None)
         # warm-up on a side stream: grows every workspace, runs every first-use attribute call, fills the time-grid cache
         side = torch.cuda.Stream(dev)
         side.wait_stream(torch.cuda.current_stream(dev))
@@ -74,6 +80,16 @@ class GraphedTrainStep:
             self.loss = self._eager_on_static()
         self._csr = self.static.__dict__.get("_gnode_csr")
         self.replays = 0
+        if preserve_state:
+            with torch.no_grad():
+                for p, p0 in zip(params, snap_p):
+                    p.copy_(p0)
+                for p in params:
+                    for k, v in optimizer.state.get(p, {}).items():
+                        if torch.is_tensor(v):
+                            old = snap_s.get(id(p), {}).get(k)
+                            v.copy_(old) if old is not None else v.zero_()     # a state born in the warm-up starts from zero
+            optimizer.zero_grad(set_to_none=False)
 
     # -- helpers --------------------------------------------------------------------------------------------------
     def _drop_csr(self):

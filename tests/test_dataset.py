@@ -55,18 +55,35 @@ def test_device_dataset_equals_reference_construction(cuda):
 
 
 @pytest.mark.gpu
-def test_train_gde_entry_point_runs(cuda, tmp_path, monkeypatch):
+@pytest.mark.parametrize("extra", [[], ["--cuda-graph", "--ode-solver", "rk4"]])
+def test_train_gde_entry_point_runs(cuda, tmp_path, monkeypatch, extra):
     """scripts/train_gde.py on synthetic episodes: two epochs, finite decreasing-or-equal best loss, a loadable checkpoint
-    with the reference's state_dict keys."""
+    with the reference's state_dict keys; also with the training step replayed as a CUDA graph."""
     import importlib.util, os, sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     spec = importlib.util.spec_from_file_location("train_gde_entry", os.path.join(root, "scripts", "train_gde.py"))
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     monkeypatch.setattr(sys, "argv", ["train_gde.py", "--synthetic", "2", "--steps-per-episode", "12", "--num-agvs", "3",
-                                      "--num-pickers", "2", "--num-epochs", "2", "--batch-size", "8", "--save-dir", str(tmp_path)])
+                                      "--num-pickers", "2", "--num-epochs", "2", "--batch-size", "8", "--save-dir", str(tmp_path)] + extra)
     best = mod.main()
     assert np.isfinite(best)
     runs = os.listdir(tmp_path)
     sd = torch.load(os.path.join(tmp_path, runs[0], "best_model.pth"), map_location="cpu")
     assert "ode_func.conv1.lin_l.weight" in sd and "position_decoder.bias" in sd
+
+
+@pytest.mark.gpu
+def test_run_gnode_entry_point_runs(cuda, monkeypatch, capsys):
+    """scripts/run_gnode.py (stand-in for the reference's heterogeneous entry point): converter -> HeteroGraphODENetwork ->
+    TD(0) updates on synthetic joint observations; finite losses, Q-value shapes of the 19 AGV + 9 picker warehouse."""
+    import importlib.util, os, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("run_gnode_entry", os.path.join(root, "scripts", "run_gnode.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    monkeypatch.setattr(sys, "argv", ["run_gnode.py", "--steps", "3", "--batch-size", "4", "--locations", "24", "--action-size", "25",
+                                      "--hidden-dim", "64"])
+    mod.main()
+    out = capsys.readouterr().out
+    assert "agv_q (76, 25)" in out and "picker_q (36, 25)" in out and "nan" not in out.lower()

@@ -41,13 +41,9 @@ def test_graphed_step_equals_eager_step(cuda, solver):
     edge_counts = {int(b.edge_index.size(1)) for b, _ in batches}
     assert len(edge_counts) > 1
     gs = GraphedTrainStep(model_g, opt_g, batches[0][0], batches[0][1], t, edge_capacity=max(edge_counts) + 17)
-    # the capture's warm-up steps and the capture itself trained model_g / advanced opt_g: restart both sides equal
-    # (in place: the captured graph holds the addresses of the weights and of Adam's state tensors)
-    model_g.load_state_dict(model_e.state_dict())
-    for st in opt_g.state.values():
-        for v in st.values():
-            if torch.is_tensor(v):
-                v.zero_()
+    # preserve_state (default): the capture's warm-up steps left the weights and Adam's state where they were
+    for (n, pe), (_, pg) in zip(model_e.named_parameters(), model_g.named_parameters()):
+        assert torch.equal(pe, pg), n
     for b, nx in batches:
         le = masked_mse_train_step(model_e, opt_e, b, nx, t)
         lg = gs.step(b, nx)
