@@ -91,7 +91,7 @@ def main():
         if (step + 1) % args.target_every == 0:
             target.load_state_dict(net.state_dict())
         if step % 10 == 0 or step == args.steps - 1:
-            print(f"step {step:4d}  td loss {float(loss):.5f}  agv_q {tuple(out['agv_q_values'].shape)}  "
+            print(f"step {step:4d}  td loss {float(loss.detach()):.5f}  agv_q {tuple(out['agv_q_values'].shape)}  "
                   f"picker_q {tuple(out['picker_q_values'].shape)}")
     per = t_step / args.steps
     print(f"{args.steps} updates of {args.batch_size} joint observations ({n_agents} agents each): {per * 1e3:.2f} ms per update "

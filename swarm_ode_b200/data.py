@@ -151,38 +151,39 @@ def pack_bits(x: torch.Tensor):
     xi = x.to(torch.uint8)
     if not torch.equal(xi.to(torch.float32), x) or bool(((x == 0) & torch.signbit(x)).any()):
         return None
-    xn = xi.numpy()
-    width = np.array([int(v).bit_length() for v in xn.max(axis=0)], dtype=np.int64)
+    xt = np.ascontiguousarray(xi.numpy().T)                  # [cols, rows]: every column contiguous
+    width = np.array([int(v).bit_length() for v in xt.max(axis=1)], dtype=np.int64)
     off = np.zeros(cols + 1, dtype=np.int64)
     off[1:] = np.cumsum(width)
     row_bytes = int(((off[-1] + 7) // 8 + 1 + 15) // 16 * 16)
     if row_bytes > BITS_MAX_ROW_BYTES:
         return None
-    out = np.zeros((rows, row_bytes), dtype=np.uint8)
+    out_t = np.zeros((row_bytes, rows), dtype=np.uint8)      # byte-major while it is built, transposed once at the end
     for c in range(cols):
         if width[c] == 0:
             continue
         b, sh = int(off[c] >> 3), int(off[c] & 7)
-        v = xn[:, c].astype(np.uint16) << sh
-        out[:, b] |= (v & 0xFF).astype(np.uint8)
+        v = xt[c].astype(np.uint16) << sh
+        out_t[b] |= v.astype(np.uint8)                        # low byte (astype truncates)
         if sh + width[c] > 8:
-            out[:, b + 1] |= (v >> 8).astype(np.uint8)
-    return torch.from_numpy(out), torch.from_numpy(off.astype(np.int32))
+            out_t[b + 1] |= (v >> 8).astype(np.uint8)
+    return torch.from_numpy(np.ascontiguousarray(out_t.T)), torch.from_numpy(off.astype(np.int32))
 
 
 def unpack_bits_host(packed: torch.Tensor, bit_offsets: torch.Tensor) -> torch.Tensor:
     """Host inverse of ``pack_bits`` (the arithmetic of ``gnode_unpack_bits``): used to verify a packed batch."""
-    p = packed.numpy().astype(np.uint16)
+    pt = np.ascontiguousarray(packed.numpy().T)              # [row_bytes, rows]
     off = bit_offsets.numpy().astype(np.int64)
     cols = off.shape[0] - 1
-    out = np.zeros((p.shape[0], cols), dtype=np.float32)
+    out_t = np.zeros((cols, pt.shape[1]), dtype=np.uint8)
     for c in range(cols):
         w = int(off[c + 1] - off[c])
         if w == 0:
             continue
         b, sh = int(off[c] >> 3), int(off[c] & 7)
-        out[:, c] = (((p[:, b] | (p[:, b + 1] << 8)) >> sh) & ((1 << w) - 1)).astype(np.float32)
-    return torch.from_numpy(out)
+        v = pt[b].astype(np.uint16) | (pt[b + 1].astype(np.uint16) << 8)
+        out_t[c] = ((v >> sh) & ((1 << w) - 1)).astype(np.uint8)
+    return torch.from_numpy(np.ascontiguousarray(out_t.T)).to(torch.float32)
 
 
 class PackedBatch:
