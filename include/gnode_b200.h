@@ -77,6 +77,15 @@ int gnode_set_engine(int engine);
  * anchor).  Both agree to fp32 rounding.  A forward call with a save area and its backward call must use the same
  * setting. */
 int gnode_set_fold(int fold);
+/* process-wide switch of the two step-level re-associations of the folded dopri5 (default 1, or GNODE_DOPRI5_FSAL=0 in
+ * the environment); returns the previous value.  1 = (a) Z of stage 6 of an accepted step is handed to the next attempt
+ * as Z_0 = y_1 @ w1cat^T (FSAL in the folded space; a rejected step keeps its Z_0), so the D-wide input contraction runs
+ * once per solve, and (b) an output time inside a step is y0 + (dt sum_s w_s(x) cat2_s) @ w3cat^T with the dense-output
+ * weights w(x) of torchdiffeq's quartic (_interp_fit / _interp_evaluate of torchdiffeq/_impl/interp.py, expanded): one
+ * D-wide projection.  0 = Z_0 contracted from y on every attempt and the quartic evaluated D-wide in torchdiffeq's
+ * operation order.  Both agree to fp32 rounding (stands for the odeint(..., method='dopri5') call at
+ * scripts/train_gde.py:78-85). */
+int gnode_set_dopri5_fsal(int on);
 /* number of kernels this library has launched since load (all threads) */
 int64_t gnode_launch_count(void);
 /* Synchronises `stream` and reports whether a tcgen05 kernel hit one of its bounded barrier waits
@@ -238,6 +247,20 @@ int gnode_integrate_fixed_flags(const gnode_graph* g, const gnode_sage3_params* 
                                 const float* y0, const float* t, int32_t n_t, float* sol,
                                 void* save, size_t save_bytes,
                                 void* workspace, size_t workspace_bytes, int32_t flags, gnode_stream_t stream);
+/* GraphODE.forward on a fixed grid in ONE call (scripts/train_gde.py:67-100: odeint(...) at :78-85, then position_decoder
+ * over every time point at :88-94): sol [n_t, n_nodes, D] and traj [n_t, n_nodes, n_out] (dec_w [n_out, D], dec_b [n_out]
+ * in nn.Linear layout).  sol[0] = y0 is written while y0 streams through the decoder of the first time point; with the
+ * folded integrator, 2H = 128 and n_out <= 4 every later time point is decoded from the previous one and the step's
+ * 2H-wide stage combination, traj[j+1] = traj[j] + C_j @ (dec_w @ w3cat)^T + (dt_j sum c)(dec_w @ b3), so the D-wide
+ * solution is written once and not read back (fp32 rounding order only); otherwise the decoder runs over sol[1:].
+ * save / save_bytes as for gnode_integrate_fixed; sol must not alias y0. */
+size_t gnode_integrate_fixed_decoded_workspace_bytes(int64_t n_nodes, int32_t node_dim, int32_t hidden_dim,
+                                                     int32_t method, int32_t n_out);
+int gnode_integrate_fixed_decoded(const gnode_graph* g, const gnode_sage3_params* p, int32_t method,
+                                  const float* y0, const float* t, int32_t n_t, float* sol,
+                                  void* save, size_t save_bytes,
+                                  const float* dec_w, const float* dec_b, int32_t n_out, float* traj,
+                                  void* workspace, size_t workspace_bytes, gnode_stream_t stream);
 /* Backprop through the solver (discretise-then-optimise, like autograd through torchdiffeq's
  * fixed-grid loop).  sol is the forward output; grad_sol: device [n_t, n_nodes, D] (cotangent of
  * every saved time point); grad_y0 overwritten (NULL = not wanted: its D-wide contraction is skipped); param grads

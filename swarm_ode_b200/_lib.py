@@ -70,6 +70,7 @@ _SIGNATURES = {
     "gnode_abi_version": (C.c_int, []),
     "gnode_set_engine": (C.c_int, [C.c_int]),
     "gnode_set_fold": (C.c_int, [C.c_int]),
+    "gnode_set_dopri5_fsal": (C.c_int, [C.c_int]),
     "gnode_launch_count": (C.c_int64, []),
     "gnode_tc_status": (C.c_int, [_P]),
     "gnode_tc_status_async": (C.c_int, [_P, _P]),
@@ -104,6 +105,10 @@ _SIGNATURES = {
                                         C.POINTER(C.c_float), C.c_int32, _P, _P, C.c_size_t, _P, C.c_size_t, _P]),
     "gnode_integrate_fixed_flags": (C.c_int, [C.POINTER(GnodeGraph), C.POINTER(GnodeSage3Params), C.c_int32, _P,
                                               C.POINTER(C.c_float), C.c_int32, _P, _P, C.c_size_t, _P, C.c_size_t, C.c_int32, _P]),
+    "gnode_integrate_fixed_decoded_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    "gnode_integrate_fixed_decoded": (C.c_int, [C.POINTER(GnodeGraph), C.POINTER(GnodeSage3Params), C.c_int32, _P,
+                                                C.POINTER(C.c_float), C.c_int32, _P, _P, C.c_size_t, _P, _P, C.c_int32, _P,
+                                                _P, C.c_size_t, _P]),
     "gnode_integrate_fixed_bwd": (C.c_int, [C.POINTER(GnodeGraph), C.POINTER(GnodeSage3Params), C.c_int32, _P,
                                             C.POINTER(C.c_float), C.c_int32, _P, _P, C.POINTER(GnodeSage3Grads), _P,
                                             C.c_size_t, _P, C.c_size_t, _P]),
@@ -251,6 +256,12 @@ def set_engine(name: str) -> str:
 def set_fold(on: bool) -> bool:
     """Folded (True, default) or direct (False) evaluation of the RK stages; returns the previous setting."""
     return bool(lib().gnode_set_fold(1 if on else 0))
+
+
+def set_dopri5_fsal(on: bool) -> bool:
+    """Step-level re-associations of the folded dopri5 (Z_0 handed from stage 6 of an accepted step to the next attempt,
+    dense output as one projection) on (default) or off; returns the previous setting."""
+    return bool(lib().gnode_set_dopri5_fsal(1 if on else 0))
 
 
 def launch_count() -> int:

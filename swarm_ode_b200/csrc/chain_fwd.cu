@@ -44,6 +44,8 @@ struct Args {
   float* Cout;                          // optional: C = sum_s csol[s] cat2_s, written after the last stage
   float* Cout2;                         // optional second combination with csol2 (dopri5: the error-estimate weights)
   float csol2[kMaxStages];
+  float* Zlast;                         // optional [N, 2H]: Z of the LAST stage.  For an FSAL tableau (dopri5: the input of stage 6 is
+                                        // the step's solution) this is Z_0 of the next step: y_1 @ w1cat^T without touching y_1
   float c13_scale[kMaxStages];          // dt * sum_j beta[s][j]
   const float *c13, *b1, *b2;
   const float *img13, *img2;            // chain-format weight images of M13 [2H x 2H] and w2cat [H x 2H]
@@ -375,6 +377,16 @@ __device__ __forceinline__ void chain_fwd_body(const Args& a, uint8_t* smem, uin
             for (int u = 0; u < SLOTS; ++u) {
               const int idx = zbase + (SLOTS + u) * WORKERS, r = idx >> 5, c4 = idx & 31;
               if (r < nr) { float4* tp = Tp(c4, r); float4 v = *tp; v.x += z2[u].x; v.y += z2[u].y; v.z += z2[u].z; v.w += z2[u].w; *tp = v; }
+            }
+            worker_sync_w();
+          }
+          if (st == S - 1 && a.Zlast != nullptr) {
+            // Z of the last stage goes out as it stands in the tile (a pass of its own, outside the loops above: the
+            // fixed-grid solvers never take it and must not pay registers for it); the next phase rewrites the right
+            // half in place, hence the barrier
+            for (int idx = wt; idx < nr * 32; idx += WORKERS) {
+              const int r = idx >> 5, c4 = idx & 31;
+              __stcs(reinterpret_cast<float4*>(a.Zlast + (size_t)(r0 + r) * W2H + 4 * c4), *Tp(c4, r));
             }
             worker_sync_w();
           }
@@ -743,6 +755,7 @@ int chain_fwd(Sage3Ctx& c, FoldWs& f, const Tableau& tb, float dt, float* Cout, 
     a.csol[st] = (float)tb.c_sol[st] * dt;
   }
   a.Cout = Cout;
+  a.Zlast = (f.z_next && tb.S > 1) ? f.z_next : nullptr;
   a.Cout2 = (Cout && Cout2 && coef2) ? Cout2 : nullptr;
   if (a.Cout2) for (int st = 0; st < tb.S; ++st) a.csol2[st] = (float)coef2[st] * dt;
   a.c13 = f.c13; a.b1 = c.b1; a.b2 = c.b2;

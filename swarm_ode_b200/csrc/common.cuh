@@ -92,6 +92,7 @@ constexpr int kNumSMs = 148;  // B200
 // ---- engine selection (gemm.cu) ----
 int current_engine();
 int current_fold();
+int current_dopri5_fsal();
 
 // ---- dense contractions (gemm_simt.cu / gemm_tc.cu) ----
 // C[m, n] = epi( sum_k A[m, k] * B[n, k] )          (both operands K-contiguous, "NT")

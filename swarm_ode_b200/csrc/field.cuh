@@ -82,6 +82,11 @@ struct FoldWs {
   float *ci13 = nullptr, *ci13T = nullptr;                 // chain-kernel images of the two
   float *z0 = nullptr, *Cbuf = nullptr;                    // [N, 2H]
   float* Cslot = nullptr;                                  // C = dt sum_s c_s cat2_s of the current step (save area or Cbuf)
+  // FSAL in the folded space (dopri5): the input of the last stage is the step's solution y_1, so Z of that stage IS
+  // y_1 @ w1cat^T = Z_0 of the next step.  With z_next set the graph-resident stage kernel writes it there (z_next_valid
+  // says it did); with z0_ready set forward_stages takes z0 as given instead of contracting the D-wide state again.
+  float* z_next = nullptr;
+  bool z0_ready = false, z_next_valid = false;
   float* Vbuf = nullptr;                                   // [N, 2H] V_s of the kernel-per-op path
   float *cat1[kMaxStages] = {}, *cat2[kMaxStages] = {};   // stage slots of the current step
   uint32_t* mask[kMaxStages] = {};                         // [N, 4] ReLU sign bits per stage (chain kernels), same slots
@@ -105,8 +110,16 @@ struct FoldWs {
   int combine_solution(Sage3Ctx& c, const Tableau& tb, float dt, float* out, cudaStream_t s);
 };
 // sol0_by_caller: sol[0] is not written here (the first step reads y0); the caller fills it (gnode_decoder_fwd_copy)
+// Position decoder fused into the folded solve: traj[j + 1] = traj[j] + C_j @ (Wd @ w3cat)^T + (dt_j sum c) (Wd @ b3), the
+// decoded y_{j+1} without reading the D-wide state again (traj[0] is the caller's; n_out <= kDecodeLRMaxOut).
+constexpr int kDecodeLRMaxOut = 4;
+struct DecodeLR {
+  const float* Wd; int n_out;
+  float* traj;                    // [n_t, N, n_out]
+  float* P;                       // scratch [n_out * (2H + 1)]
+};
 int integrate_fixed_folded(Sage3Ctx& c, FoldWs& f, const Tableau& tb, const float* y0, const float* t, int n_t,
-                           float* sol, float* save, cudaStream_t s, bool sol0_by_caller = false);
+                           float* sol, float* save, cudaStream_t s, bool sol0_by_caller = false, const DecodeLR* dec = nullptr);
 // Cotangent of the last time point given in factored form  G = g1 @ Wd  (g1 [N, n_out], Wd [n_out, D]): what the
 // position decoder hands back when the loss reaches the solution only through it (scripts/train_gde.py:486-490).
 struct LowRankG {
@@ -122,6 +135,7 @@ int integrate_dopri5_folded_bwd(Sage3Ctx& c, FoldWs& f, const float* y0, const d
 size_t decoder_wgrad_partial_floats(int64_t M, int D, int n_out);
 int decoder_wgrad(const float* x, const float* g, int64_t M, int D, int n_out, float* partials, float* total, cudaStream_t s);
 int current_fold();
+int current_dopri5_fsal();
 // graph-resident forward chain of the folded stages (chain_fwd.cu)
 size_t chain_image_floats(int n, int k);
 int chain_pack_image(const float* W, int n, int k, int64_t ld, float* img, cudaStream_t s);

@@ -18,6 +18,7 @@
 // i.e. per step two D-wide data contractions (G @ w3cat, GZ @ w1cat) and two D-wide weight-gradient contractions.
 // This is a re-association of the reference arithmetic (fp32 rounding order only; parity gate: rel-L2 <= 1e-4); the
 // unfolded path (gnode_set_fold(0)) stays available as the straightforward anchor.
+#include <algorithm>
 #include <cstring>
 
 #include "field.cuh"
@@ -120,6 +121,62 @@ __global__ void k_lr_finish(const float* __restrict__ Wd, const float* __restric
   }
 }
 
+// ---- position decoder of the next time point from the 2H-wide step combination (integrate_fixed_folded with `dec`) ----
+//   y_1 = y + C @ w3cat^T + cs b3   =>   y_1 @ Wd^T + bd = (y @ Wd^T + bd) + C @ (Wd @ w3cat)^T + cs (Wd @ b3)
+// P[o * 2H + c] = sum_d Wd[o, d] w3cat[d, c],   P[n_out * 2H + o] = sum_d Wd[o, d] b3[d]      (fp64 accumulate, a warp per entry)
+__global__ void k_dec_prep(const float* __restrict__ Wd, const float* __restrict__ w3cat, const float* __restrict__ b3, int n_out,
+                           int D, int H2, float* __restrict__ P) {
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, l = threadIdx.x & 31;
+  if (i >= n_out * (H2 + 1)) return;
+  const int o = i / (H2 + 1), c = i % (H2 + 1);
+  double acc = 0.0;
+  if (c < H2) { for (int d = l; d < D; d += 32) acc += (double)Wd[(size_t)o * D + d] * (double)w3cat[(size_t)d * H2 + c]; }
+  else { for (int d = l; d < D; d += 32) acc += (double)Wd[(size_t)o * D + d] * (double)b3[d]; }
+#pragma unroll
+  for (int sft = 1; sft < 32; sft <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, sft);
+  if (l == 0) P[c < H2 ? o * H2 + c : n_out * H2 + o] = (float)acc;
+}
+// next[n, o] = prev[n, o] + sum_c C[n, c] P[o, c] + cs P[o, 2H]      (2H = 128: a warp per row, one float4 of C per lane,
+// four rows in flight per warp; fixed-order butterfly -> deterministic)
+template <int NO>
+__global__ void __launch_bounds__(256) k_decode_step(const float* __restrict__ C, const float* __restrict__ P, const float* __restrict__ prev,
+                                                     float* __restrict__ next, int64_t N, float cs) {
+  constexpr int H2 = 128, RW = 4;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  float4 pw[NO];
+#pragma unroll
+  for (int o = 0; o < NO; ++o) pw[o] = __ldg(reinterpret_cast<const float4*>(P + (size_t)o * H2) + lane);
+  for (int64_t r0 = warp * RW; r0 < N; r0 += n_warps * RW) {
+    float4 v[RW];
+#pragma unroll
+    for (int u = 0; u < RW; ++u)
+      v[u] = (r0 + u < N) ? __ldcs(reinterpret_cast<const float4*>(C + (r0 + u) * H2) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float acc[RW][NO];
+#pragma unroll
+    for (int u = 0; u < RW; ++u)
+#pragma unroll
+      for (int o = 0; o < NO; ++o)
+        acc[u][o] = fmaf(v[u].x, pw[o].x, fmaf(v[u].y, pw[o].y, fmaf(v[u].z, pw[o].z, v[u].w * pw[o].w)));
+#pragma unroll
+    for (int sft = 16; sft >= 1; sft >>= 1)
+#pragma unroll
+      for (int u = 0; u < RW; ++u)
+#pragma unroll
+        for (int o = 0; o < NO; ++o) acc[u][o] += __shfl_xor_sync(0xffffffffu, acc[u][o], sft);
+    if (lane < RW * NO) {
+      const int u = lane / NO, o = lane % NO;
+      float val = 0.f;
+#pragma unroll
+      for (int uu = 0; uu < RW; ++uu)
+#pragma unroll
+        for (int oo = 0; oo < NO; ++oo)
+          if (uu == u && oo == o) val = acc[uu][oo];
+      if (r0 + u < N) next[(r0 + u) * NO + o] = prev[(r0 + u) * NO + o] + val + cs * __ldg(P + (size_t)NO * H2 + o);
+    }
+  }
+}
+
 }  // namespace
 
 void FoldWs::carve(Arena& a, const Sage3Ctx& c, int S_, bool backward) {
@@ -208,13 +265,18 @@ int FoldWs::forward_stages(Sage3Ctx& c, const Tableau& tb, const float* y, float
   const int H = c.H, H2 = 2 * c.H;
   const int64_t N = c.N;
   const int64_t nh = N * H2;
-  {  // Z_0 = y @ w1cat^T
+  if (!z0_ready) {  // Z_0 = y @ w1cat^T
     GemmNT q{};
     q.A = y; q.lda = c.D; q.B = c.w1cat; q.ldb = c.D; q.C = z0; q.ldc = H2; q.M = N; q.N = H2; q.K = c.D;
     q.Bsplit = c.use_tc ? c.s1 : nullptr;
     GN_TRY(gemm_nt(q, s));
   }
-  if (chain_fwd_supported(c)) return chain_fwd(c, *this, tb, dt, Cout, s, Cout2, coef2);   // all stages of the step, graph-resident
+  z_next_valid = false;
+  if (chain_fwd_supported(c)) {   // all stages of the step, graph-resident
+    GN_TRY(chain_fwd(c, *this, tb, dt, Cout, s, Cout2, coef2));
+    z_next_valid = z_next != nullptr && tb.S > 1;
+    return GNODE_OK;
+  }
   for (int st = 0; st < S; ++st) {
     const float* z = z0;
     if (st > 0) {
@@ -267,11 +329,17 @@ int FoldWs::combine_solution(Sage3Ctx& c, const Tableau& tb, float dt, float* ou
 }
 
 int integrate_fixed_folded(Sage3Ctx& c, FoldWs& f, const Tableau& tb, const float* y0, const float* t, int n_t,
-                           float* sol, float* save, cudaStream_t s, bool sol0_by_caller) {
+                           float* sol, float* save, cudaStream_t s, bool sol0_by_caller, const DecodeLR* dec) {
   const int H2 = 2 * c.H;
   const int64_t n = c.numel();
   if (sol != y0 && !sol0_by_caller) GN_CUDA(cudaMemcpyAsync(sol, y0, sizeof(float) * n, cudaMemcpyDeviceToDevice, s));
   GN_TRY(f.prepare(c, s));
+  if (dec) {
+    if (H2 != 128 || dec->n_out < 1 || dec->n_out > kDecodeLRMaxOut) { set_error("integrate_fixed_folded: decoder shape not supported"); return GNODE_ERR_ARG; }
+    GN_PROF(s, 2.0 * dec->n_out * (H2 + 1) * c.D, 0.0, "decoder_prep");
+    k_dec_prep<<<(unsigned)ceil_div64((int64_t)dec->n_out * (H2 + 1) * 32, 256), 256, 0, s>>>(dec->Wd, c.w3cat, c.b3, dec->n_out, c.D, H2, dec->P);
+    GN_LAUNCHED();
+  }
   f.forward_only = save == nullptr;     // without a save area a later backward recomputes the stages itself
   double csum = 0.0;
   for (int st = 0; st < tb.S; ++st) csum += tb.c_sol[st];
@@ -286,6 +354,20 @@ int integrate_fixed_folded(Sage3Ctx& c, FoldWs& f, const Tableau& tb, const floa
     q.bias = c.b3; q.bias_scale = (float)csum * dt; q.base = y; q.ldbase = c.D;
     q.Bsplit = c.use_tc ? c.s3 : nullptr; q.Bchain = c.use_tc ? c.ck3 : nullptr; q.rows_engine = 1;
     GN_TRY(gemm_nt(q, s));
+    if (dec) {
+      const float* prev = dec->traj + (int64_t)j * c.N * dec->n_out;
+      float* next = dec->traj + (int64_t)(j + 1) * c.N * dec->n_out;
+      const float cs = (float)csum * dt;
+      GN_PROF(s, 2.0 * c.N * H2 * dec->n_out, 4.0 * (double)c.N * (H2 + 2 * dec->n_out), "decoder_step");
+      const unsigned grid = (unsigned)std::min<int64_t>(ceil_div64(c.N, 4 * 8), (int64_t)kNumSMs * 8);
+      switch (dec->n_out) {
+        case 1: k_decode_step<1><<<grid, 256, 0, s>>>(f.Cslot, dec->P, prev, next, c.N, cs); break;
+        case 2: k_decode_step<2><<<grid, 256, 0, s>>>(f.Cslot, dec->P, prev, next, c.N, cs); break;
+        case 3: k_decode_step<3><<<grid, 256, 0, s>>>(f.Cslot, dec->P, prev, next, c.N, cs); break;
+        default: k_decode_step<4><<<grid, 256, 0, s>>>(f.Cslot, dec->P, prev, next, c.N, cs); break;
+      }
+      GN_LAUNCHED();
+    }
   }
   return GNODE_OK;
 }

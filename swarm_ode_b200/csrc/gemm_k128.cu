@@ -147,16 +147,27 @@ __device__ __forceinline__ void span_update(float* my_row, const float* biasS, i
                                             float* crow, bool has_base) {
   if (whole) {
     if (c0 + W <= N) {
+      // all W base values first (W independent shared-memory loads in flight), then the stores: updating four columns at
+      // a time made every group wait for the stores of the one before it (the compiler cannot prove biasS and my_row
+      // distinct) behind a branch on has_base per group
+      float o[W];
+      if (has_base) {
+#pragma unroll
+        for (int j = 0; j < W; ++j) o[j] = base_scale * my_row[c0 + j];
+      } else {
+#pragma unroll
+        for (int j = 0; j < W; ++j) o[j] = 0.f;
+      }
 #pragma unroll
       for (int j = 0; j < W; j += 4) {
         const float4 b4 = *reinterpret_cast<const float4*>(biasS + c0 + j);   // same address in every lane: broadcast
-        float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
-        if (has_base) { o0 = base_scale * my_row[c0 + j]; o1 = base_scale * my_row[c0 + j + 1]; o2 = base_scale * my_row[c0 + j + 2]; o3 = base_scale * my_row[c0 + j + 3]; }
-        my_row[c0 + j] = o0 + scale * __uint_as_float(r[j]) + b4.x;
-        my_row[c0 + j + 1] = o1 + scale * __uint_as_float(r[j + 1]) + b4.y;
-        my_row[c0 + j + 2] = o2 + scale * __uint_as_float(r[j + 2]) + b4.z;
-        my_row[c0 + j + 3] = o3 + scale * __uint_as_float(r[j + 3]) + b4.w;
+        o[j] = o[j] + scale * __uint_as_float(r[j]) + b4.x;
+        o[j + 1] = o[j + 1] + scale * __uint_as_float(r[j + 1]) + b4.y;
+        o[j + 2] = o[j + 2] + scale * __uint_as_float(r[j + 2]) + b4.z;
+        o[j + 3] = o[j + 3] + scale * __uint_as_float(r[j + 3]) + b4.w;
       }
+#pragma unroll
+      for (int j = 0; j < W; ++j) my_row[c0 + j] = o[j];
     } else {
 #pragma unroll
       for (int j = 0; j < W; ++j)
@@ -377,22 +388,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_k128_rows(const k128::Args
         }
         const int c0 = NCH * c + (NCH / 2) * ehf;       // my 40 (44) columns of the chunk
         {
-          uint32_t r[32];
+          // every accumulator load of the chunk is issued before the one wait
+          uint32_t r[32], r8[8], r4[4];
           tmem_ld32(tmem_base, eq, (uint32_t)c0, r);
+          tmem_ld8(tmem_base, eq, (uint32_t)(c0 + 32), r8);
+          if (NCH / 2 > 40) tmem_ld4(tmem_base, eq, (uint32_t)(c0 + 40), r4);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
           span_update<32>(my_row, biasS, c0, r, N, base_scale, scale, whole, valid, brow, crow, has_base);
-        }
-        {
-          uint32_t r[8];
-          tmem_ld8(tmem_base, eq, (uint32_t)(c0 + 32), r);
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          span_update<8>(my_row, biasS, c0 + 32, r, N, base_scale, scale, whole, valid, brow, crow, has_base);
-        }
-        if (NCH / 2 > 40) {
-          uint32_t r[4];
-          tmem_ld4(tmem_base, eq, (uint32_t)(c0 + 40), r);
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          span_update<4>(my_row, biasS, c0 + 40, r, N, base_scale, scale, whole, valid, brow, crow, has_base);
+          span_update<8>(my_row, biasS, c0 + 32, r8, N, base_scale, scale, whole, valid, brow, crow, has_base);
+          if (NCH / 2 > 40) span_update<4>(my_row, biasS, c0 + 40, r4, N, base_scale, scale, whole, valid, brow, crow, has_base);
         }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

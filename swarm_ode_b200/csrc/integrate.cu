@@ -3,6 +3,7 @@
 // scripts/run_gnode.py:134-135), plus backprop through the fixed-grid solvers
 // (loss.backward(), scripts/train_gde.py:493).
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "field.cuh"
@@ -290,8 +291,21 @@ int integrate_dopri5(Field& f, const float* y0, const double* t, int n_t, double
 struct Dopri5FoldBufs {
   float *ya, *yb, *k0, *k1, *xs, *err;   // [N, D] each
   float* Cerr;                           // [N, 2H]  dt sum_s c_err[s] cat2_s
+  float* znext;                          // [N, 2H]  Z of stage 6 = Z_0 of the next step when this one is accepted
   double* partials; double* dsum;
 };
+
+// gnode_set_dopri5_fsal(0) / GNODE_DOPRI5_FSAL=0 switch the two step-level re-associations of the folded dopri5 off (A/B
+// and bisecting):
+//  * FSAL in the folded space: stage 6 of an attempt is evaluated at the step's solution, so its Z is y_1 @ w1cat^T; an
+//    accepted step hands it to the next attempt as Z_0 and a rejected step keeps its Z_0 (same y, new dt): the D-wide
+//    contraction Z_0 = y @ w1cat^T runs once per solve instead of once per attempt;
+//  * dense output as ONE projection: torchdiffeq's quartic through (y0, y1, y_mid, f0, f1) is linear in the seven stage
+//    derivatives and the y0 terms of its coefficients cancel, sol(x) = y0 + dt sum_s w_s(x) k_s (fold.cu:
+//    dopri5_dense_weights, the weights the backward pass already uses), so an output inside a step is a 2H-wide stage
+//    combination and one D-wide projection instead of three projections and a five-operand D-wide polynomial.
+// Both change fp32 rounding order only (parity gates: rel-L2 <= 1e-4, identical accept / reject lists).
+static bool dopri5_fsal_on() { return current_dopri5_fsal() != 0; }
 
 int integrate_dopri5_folded(Sage3Ctx& c, FoldWs& f, const float* y0, const double* t, int n_t, double rtol, double atol,
                             float* sol, gnode_dopri5_stats* stats, const gnode_dopri5_trace* trace,
@@ -313,6 +327,11 @@ int integrate_dopri5_folded(Sage3Ctx& c, FoldWs& f, const float* y0, const doubl
   GN_TRY(f.prepare(c, s));
   f.bind_slots(c, nullptr, 0);
   f.forward_only = true;                // the dopri5 backward replays its accepted steps: nothing of this solve is read back
+  const bool fsal = dopri5_fsal_on();
+  float* const z0_own = f.z0;           // restored on every way out (the buffers are swapped on accepted steps)
+  struct Restore { FoldWs& f; float* z0; ~Restore() { f.z0 = z0; f.z_next = nullptr; f.z0_ready = false; f.z_next_valid = false; } } restore{f, z0_own};
+  f.z_next = fsal ? b.znext : nullptr;
+  f.z0_ready = false;
 
   // k = scale_w * (W @ w3cat^T) + scale_b * b3   for a 2H-wide W; optional base
   auto project = [&](const float* W, float* out, const float* base, float bias_scale) -> int {
@@ -335,8 +354,22 @@ int integrate_dopri5_folded(Sage3Ctx& c, FoldWs& f, const float* y0, const doubl
     return lincomb(lc, s);
   };
 
-  // ---- _select_initial_step: two direct evaluations of the field (D-wide derivatives are needed for the norms) ----
-  GN_TRY(c.eval(ya, b.k0, nullptr, 1.f, 0, s));
+  // ---- _select_initial_step: f(y0) and f(y0 + h0 f(y0)), D-wide because the norms need the derivatives.  Folded form:
+  // stage 0 of a one-stage tableau, then stage 1 of the two-stage tableau beta_10 = 1 with dt = h0 (= the field at
+  // y0 + h0 k_0), each followed by one projection k = cat2 @ w3cat^T + b3; Z_0 of y0 stays for the first attempt.
+  // Without the re-associations (gnode_set_dopri5_fsal(0)): two direct evaluations of the field. ----
+  const int S_own = f.S;
+  struct RestoreS { FoldWs& f; int S; ~RestoreS() { f.S = S; } } restore_s{f, S_own};
+  Tableau t_init{};
+  t_init.S = 1;
+  if (fsal) {
+    f.S = 1;
+    GN_TRY(f.forward_stages(c, t_init, ya, 0.f, s));
+    f.z0_ready = true;
+    GN_TRY(project(f.cat2[0], b.k0, nullptr, 1.f));
+  } else {
+    GN_TRY(c.eval(ya, b.k0, nullptr, 1.f, 0, s));
+  }
   st.nfe++;
   double dt;
   {
@@ -348,10 +381,19 @@ int integrate_dopri5_folded(Sage3Ctx& c, FoldWs& f, const float* y0, const doubl
     float h0;
     if (d0 < 1e-5f || d1 < 1e-5f) h0 = 1e-6f; else h0 = 0.01f * d0 / d1;
     h0 = fabsf(h0);
-    LinComb lc{};
-    lc.out = b.xs; lc.base = ya; lc.in[0] = b.k0; lc.coef[0] = h0; lc.n_terms = 1; lc.n = n;
-    GN_TRY(lincomb(lc, s));
-    GN_TRY(c.eval(b.xs, b.k1, nullptr, 1.f, 0, s));
+    if (fsal) {
+      t_init.S = 2;
+      t_init.beta[1][0] = 1.0;
+      f.S = 2;
+      GN_TRY(f.forward_stages(c, t_init, ya, h0, s));
+      GN_TRY(project(f.cat2[1], b.k1, nullptr, 1.f));
+    } else {
+      LinComb lc{};
+      lc.out = b.xs; lc.base = ya; lc.in[0] = b.k0; lc.coef[0] = h0; lc.n_terms = 1; lc.n = n;
+      GN_TRY(lincomb(lc, s));
+      GN_TRY(c.eval(b.xs, b.k1, nullptr, 1.f, 0, s));
+    }
+    f.S = S_own;
     st.nfe++;
     GN_TRY(scaled_sumsq(b.k1, b.k0, ya, atolf, rtolf, n, b.partials, b.dsum, s));
     GN_TRY(nc.finish(&d2));
@@ -381,6 +423,8 @@ int integrate_dopri5_folded(Sage3Ctx& c, FoldWs& f, const float* y0, const doubl
     // both 2H-wide stage combinations (solution and error-estimate weights) come out of the stage kernel
     GN_TRY(f.forward_stages(c, tb, ya, dtf, s, f.Cbuf, b.Cerr, tb.c_err));
     st.nfe += 6;
+    const bool z_next_valid = f.z_next_valid;
+    if (fsal) f.z0_ready = true;        // Z_0 of ya is in f.z0 now: a rejected step reuses it as it is
     double csum = 0.0, cesum = 0.0;
     for (int j = 0; j < 7; ++j) { csum += tb.c_sol[j]; cesum += tb.c_err[j]; }
     GN_TRY(project(f.Cbuf, yb, ya, (float)csum * dtf));                 // y1 = y0 + dt sum c_sol k
@@ -405,7 +449,20 @@ int integrate_dopri5_folded(Sage3Ctx& c, FoldWs& f, const float* y0, const doubl
     if (margin < st.min_margin) st.min_margin = margin;
     if (accept) {
       st.n_accepted++;
-      if (next_out < n_t && t[next_out] <= t1) {
+      if (fsal) {
+        while (next_out < n_t && t[next_out] <= t1) {
+          float* out = sol + (int64_t)next_out * n;
+          if (t[next_out] == t1) {          // w(1) = c_sol: the interpolant at the end of the step is y1
+            GN_CUDA(cudaMemcpyAsync(out, yb, sizeof(float) * n, cudaMemcpyDeviceToDevice, s));
+          } else {
+            double w[7], wsum;
+            dopri5_dense_weights(tb, (t[next_out] - t0) / (t1 - t0), w);
+            GN_TRY(combine(w, dtf, &wsum));
+            GN_TRY(project(f.Cbuf, out, ya, (float)wsum * dtf));      // sol(x) = y0 + dt sum_s w_s(x) k_s
+          }
+          ++next_out;
+        }
+      } else if (next_out < n_t && t[next_out] <= t1) {
         // dense output needs D-wide f0 = k_0, f1 = k_6 and dt * sum c_mid k: three projections, then the
         // reference's quartic in the reference's operation order
         GN_TRY(project(f.cat2[0], b.k0, nullptr, 1.f));
@@ -426,6 +483,10 @@ int integrate_dopri5_folded(Sage3Ctx& c, FoldWs& f, const float* y0, const doubl
       }
       float* tmp = ya; ya = yb; yb = tmp;
       t_cur = t1;
+      if (fsal) {
+        if (z_next_valid) { float* z = f.z0; f.z0 = f.z_next; f.z_next = z; }   // Z of stage 6 = Z_0 of the new ya
+        else f.z0_ready = false;                                                // kernel-per-op stages: contract again
+      }
     }
     double factor;
     if (ratio == 0.f) {
@@ -529,6 +590,56 @@ extern "C" int gnode_integrate_fixed(const gnode_graph* g, const gnode_sage3_par
                                      size_t save_bytes, void* workspace, size_t workspace_bytes,
                                      gnode_stream_t stream) {
   return gnode_integrate_fixed_flags(g, p, method, y0, t, n_t, sol, save, save_bytes, workspace, workspace_bytes, 0, stream);
+}
+
+// GraphODE.forward on a fixed grid (scripts/train_gde.py:67-100): the solve AND position_decoder over every time point.
+// Folded integrator, n_out <= kDecodeLRMaxOut, 2H = 128: the first time point is decoded from y0 (which also delivers
+// sol[0] = y0), every later one from the previous one and the step's 2H-wide combination C -- the D-wide solution is
+// written once and never read back.  Otherwise: the solve, then the decoder over sol[1:].
+extern "C" size_t gnode_integrate_fixed_decoded_workspace_bytes(int64_t n_nodes, int32_t node_dim, int32_t hidden_dim,
+                                                                int32_t method, int32_t n_out) {
+  return gnode_integrate_fixed_workspace_bytes(n_nodes, node_dim, hidden_dim, method, 0) +
+         align_up(sizeof(float) * (size_t)(n_out > 0 ? n_out : 1) * (2 * (size_t)hidden_dim + 1));
+}
+
+extern "C" int gnode_integrate_fixed_decoded(const gnode_graph* g, const gnode_sage3_params* p, int32_t method,
+                                             const float* y0, const float* t, int32_t n_t, float* sol, void* save,
+                                             size_t save_bytes, const float* dec_w, const float* dec_b, int32_t n_out,
+                                             float* traj, void* workspace, size_t workspace_bytes, gnode_stream_t stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  GN_TRY(check_graph(g, "gnode_integrate_fixed_decoded"));
+  GN_TRY(check_params(p, "gnode_integrate_fixed_decoded"));
+  const Tableau* tb = tableau_for(method);
+  GN_ARG(tb && method != GNODE_DOPRI5, "gnode_integrate_fixed_decoded: method %d is not a fixed-grid solver", method);
+  GN_ARG(y0 && t && sol && traj && dec_w && dec_b && n_t >= 1 && n_out >= 1, "gnode_integrate_fixed_decoded: null pointer or empty time grid");
+  GN_ARG(sol != y0, "gnode_integrate_fixed_decoded: sol aliases y0");
+  for (int j = 0; j + 1 < n_t; ++j)
+    GN_ARG(t[j + 1] > t[j], "gnode_integrate_fixed_decoded: t must be strictly increasing");
+  const int64_t N = g->n_nodes;
+  const int D = p->node_dim, H = p->hidden_dim;
+  // first time point: decoded from y0, which is copied to sol[0] as it streams through
+  GN_TRY(gnode_decoder_fwd_copy(y0, N, D, n_out, dec_w, dec_b, traj, sol, stream));
+  if (n_t == 1) return GNODE_OK;
+  const bool lowrank = current_fold() && n_out <= kDecodeLRMaxOut && 2 * H == 128;
+  if (!lowrank) {
+    GN_TRY(gnode_integrate_fixed_flags(g, p, method, y0, t, n_t, sol, save, save_bytes, workspace, workspace_bytes,
+                                       GNODE_FIXED_SOL0_BY_CALLER, stream));
+    return gnode_decoder_fwd(sol + N * D, (int64_t)(n_t - 1) * N, D, n_out, dec_w, dec_b, traj + N * n_out, stream);
+  }
+  Sage3Ctx c;
+  c.g = *g; c.g_tiles = g->tiles; c.g_tile_err = g->tile_err; c.N = N; c.D = D; c.H = H;
+  Arena a(workspace, workspace_bytes);
+  FoldWs f;
+  c.carve(a, tb->S, false);
+  f.carve(a, c, tb->S, false);
+  DecodeLR dec{};
+  dec.Wd = dec_w; dec.n_out = n_out; dec.traj = traj;
+  dec.P = a.take<float>((size_t)n_out * (2 * (size_t)H + 1));
+  GN_ARENA_OK(a, "gnode_integrate_fixed_decoded");
+  GN_TRY(c.pack(*p, false, s));
+  if (save) GN_ARG(save_bytes >= gnode_integrate_fixed_save_bytes(c.N, c.D, c.H, method, n_t),
+                   "gnode_integrate_fixed_decoded: save buffer too small (%zu bytes)", save_bytes);
+  return integrate_fixed_folded(c, f, *tb, y0, t, n_t, sol, static_cast<float*>(save), s, true, &dec);
 }
 
 extern "C" int gnode_integrate_fixed_flags(const gnode_graph* g, const gnode_sage3_params* p, int32_t method,
@@ -906,6 +1017,7 @@ void carve_dopri5_fold(Arena& a, Sage3Ctx& c, FoldWs& f, Dopri5FoldBufs& b) {
   b.ya = a.take<float>(n); b.yb = a.take<float>(n); b.k0 = a.take<float>(n);
   b.k1 = a.take<float>(n); b.xs = a.take<float>(n); b.err = a.take<float>(n);
   b.Cerr = a.take<float>((size_t)c.N * 2 * c.H);
+  b.znext = a.take<float>((size_t)c.N * 2 * c.H);
   b.partials = a.take<double>((size_t)norm_blocks((int64_t)n));
   b.dsum = a.take<double>(2);
 }

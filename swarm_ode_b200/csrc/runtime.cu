@@ -2,6 +2,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <mutex>
 #include <set>
 #include <utility>
@@ -14,6 +15,7 @@ thread_local char g_err[1024] = "";
 std::atomic<int64_t> g_launches{0};
 std::atomic<int> g_engine{GNODE_ENGINE_AUTO};
 std::atomic<int> g_fold{1};
+std::atomic<int> g_dopri5_fsal{-1};   // -1: not set yet, take GNODE_DOPRI5_FSAL (default on)
 }  // namespace
 
 void set_error(const char* fmt, ...) {
@@ -25,6 +27,17 @@ void set_error(const char* fmt, ...) {
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 int current_engine() { return g_engine.load(std::memory_order_relaxed); }
 int current_fold() { return g_fold.load(std::memory_order_relaxed); }
+int current_dopri5_fsal() {
+  int v = g_dopri5_fsal.load(std::memory_order_relaxed);
+  if (v < 0) {
+    const char* e = std::getenv("GNODE_DOPRI5_FSAL");
+    v = (e && e[0] == '0') ? 0 : 1;
+    int expect = -1;
+    g_dopri5_fsal.compare_exchange_strong(expect, v);
+    v = g_dopri5_fsal.load(std::memory_order_relaxed);
+  }
+  return v;
+}
 
 // Per-device one-time setup (cudaFuncSetAttribute and friends are per device, not per process): true exactly once for
 // every (key, current device) pair.
@@ -45,4 +58,9 @@ extern "C" int gnode_set_engine(int engine) {
   return gnode::g_engine.exchange(engine);
 }
 extern "C" int gnode_set_fold(int fold) { return gnode::g_fold.exchange(fold ? 1 : 0); }
+extern "C" int gnode_set_dopri5_fsal(int on) {
+  const int prev = gnode::current_dopri5_fsal();
+  gnode::g_dopri5_fsal.store(on ? 1 : 0);
+  return prev;
+}
 extern "C" int64_t gnode_launch_count(void) { return gnode::g_launches.load(std::memory_order_relaxed); }

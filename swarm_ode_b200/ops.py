@@ -40,6 +40,19 @@ def _save_fits(nbytes: int, device) -> bool:
     return nbytes <= SAVE_FRACTION * free
 
 
+def _zeros_like_many(tensors: Sequence[torch.Tensor]) -> List[torch.Tensor]:
+    """Zero-filled gradient buffers for ``tensors`` as views of ONE flat allocation (one fill kernel instead of one per
+    parameter; every view starts on a 256-byte boundary, like a tensor of its own)."""
+    if not tensors:
+        return []
+    offs, total = [], 0
+    for t in tensors:
+        offs.append(total)
+        total += (t.numel() + 63) // 64 * 64
+    flat = torch.zeros(total, dtype=tensors[0].dtype, device=tensors[0].device)
+    return [flat[o:o + t.numel()].view(t.shape) for o, t in zip(offs, tensors)]
+
+
 def _ws(nbytes: int, device) -> torch.Tensor:
     return _lib.WORKSPACE.get(nbytes, device)
 
@@ -134,7 +147,7 @@ class _RhsFn(torch.autograd.Function):
         H = w[0].shape[0]
         p = _sage3_params(D, H, w)
         gx = torch.empty_like(x)
-        gw = [torch.zeros_like(t) for t in w]
+        gw = _zeros_like_many(w)
         grads = _lib.GnodeSage3Grads(*[t.data_ptr() for t in gw])
         L = _lib.lib()
         ws = _ws(L.gnode_rhs_workspace_bytes(N, D, H), x.device)
@@ -153,11 +166,13 @@ def gnode_rhs(x, graph: CSRGraph, params: Sequence[torch.Tensor]) -> torch.Tenso
 # ----------------------------------------------------------------------------------------------
 # fixed-grid integration with backprop through the solver
 # ----------------------------------------------------------------------------------------------
-def _fixed_forward(ctx, y0, graph: CSRGraph, method: int, t_host: Tuple[float, ...], w, sol0_by_caller: bool = False):
+def _fixed_forward(ctx, y0, graph: CSRGraph, method: int, t_host: Tuple[float, ...], w, decoder=None):
     """Shared forward of the fixed-grid autograd nodes: runs the solve, keeps the save area on ``ctx``.
-    Returns ``(solution, contiguous parameter list)``; the caller does ``ctx.save_for_backward``.
-    ``sol0_by_caller``: ``solution[0]`` is left unwritten -- the caller fills it (the decoder of the first time point
-    streams ``y0`` anyway and delivers the copy as a side effect, ``gnode_decoder_fwd_copy``)."""
+    Returns ``(solution, contiguous parameter list)`` -- with ``decoder = (weight, bias)`` ``(solution, parameter list,
+    trajectories)``: the solve and ``position_decoder`` over every time point in one library call
+    (``gnode_integrate_fixed_decoded``: ``solution[0] = y0`` is written while ``y0`` streams through the decoder of the
+    first time point, later time points are decoded from the 2H-wide step combination).  The caller does
+    ``ctx.save_for_backward``."""
     if True:
         y0 = _f32(y0, "y0")
         w = [_f32(t, "param") for t in w]
@@ -171,7 +186,14 @@ def _fixed_forward(ctx, y0, graph: CSRGraph, method: int, t_host: Tuple[float, .
         L = _lib.lib()
         fold = bool(L.gnode_set_fold(1))     # read the current setting (set-and-restore)
         L.gnode_set_fold(1 if fold else 0)
-        ws = _ws(L.gnode_integrate_fixed_workspace_bytes(N, D, H, method, 0), y0.device)
+        traj = None
+        if decoder is not None:
+            dec_w, dec_b = decoder
+            n_out = dec_w.shape[0]
+            traj = torch.empty((T, N, n_out), dtype=torch.float32, device=y0.device)
+            ws = _ws(L.gnode_integrate_fixed_decoded_workspace_bytes(N, D, H, method, n_out), y0.device)
+        else:
+            ws = _ws(L.gnode_integrate_fixed_workspace_bytes(N, D, H, method, 0), y0.device)
         tarr = _float_array(t_host)
         # When a backward will follow, keep the per-stage intermediates (autograd's "tape") so the backward does
         # not recompute every stage -- unless they would not fit comfortably in free device memory.
@@ -184,14 +206,22 @@ def _fixed_forward(ctx, y0, graph: CSRGraph, method: int, t_host: Tuple[float, .
                 except torch.OutOfMemoryError:      # a nearly full device: the backward recomputes the stages instead
                     save = None
         with torch.cuda.device(y0.device):
-            _lib.check(L.gnode_integrate_fixed_flags(graph.ref(), C.byref(p), method, _lib.ptr(y0), tarr, T, _lib.ptr(sol),
-                                                     _lib.ptr(save), save.numel() if save is not None else 0,
-                                                     _lib.ptr(ws), ws.numel(), 1 if sol0_by_caller else 0,
-                                                     _lib.stream_ptr(y0.device)),
-                       "gnode_integrate_fixed")
+            if decoder is not None:
+                _lib.check(L.gnode_integrate_fixed_decoded(graph.ref(), C.byref(p), method, _lib.ptr(y0), tarr, T, _lib.ptr(sol),
+                                                           _lib.ptr(save), save.numel() if save is not None else 0,
+                                                           _lib.ptr(dec_w), _lib.ptr(dec_b), n_out, _lib.ptr(traj),
+                                                           _lib.ptr(ws), ws.numel(), _lib.stream_ptr(y0.device)),
+                           "gnode_integrate_fixed_decoded")
+            else:
+                _lib.check(L.gnode_integrate_fixed_flags(graph.ref(), C.byref(p), method, _lib.ptr(y0), tarr, T, _lib.ptr(sol),
+                                                         _lib.ptr(save), save.numel() if save is not None else 0,
+                                                         _lib.ptr(ws), ws.numel(), 0, _lib.stream_ptr(y0.device)),
+                           "gnode_integrate_fixed")
         graph.schedule_tile_check()
         ctx.graph, ctx.method, ctx.t_host, ctx.save = graph, method, t_host, save
         ctx.fold = fold
+        if decoder is not None:
+            return sol, w, traj
         return sol, w
 
 
@@ -210,7 +240,7 @@ class _IntegrateFixedFn(torch.autograd.Function):
         H = w[0].shape[0]
         p = _sage3_params(D, H, w)
         gy0 = torch.empty((N, D), dtype=torch.float32, device=sol.device) if ctx.needs_input_grad[0] else None
-        gw = [torch.zeros_like(t) for t in w]
+        gw = _zeros_like_many(w)
         grads = _lib.GnodeSage3Grads(*[t.data_ptr() for t in gw])
         L = _lib.lib()
         prev_fold = L.gnode_set_fold(1 if ctx.fold else 0)   # the save area's layout is the forward's
@@ -252,7 +282,7 @@ class _IntegrateFixedAdjointFn(torch.autograd.Function):
         H = w[0].shape[0]
         p = _sage3_params(D, H, w)
         gy0 = torch.empty((N, D), dtype=torch.float32, device=sol.device) if ctx.needs_input_grad[0] else None
-        gw = [torch.zeros_like(t) for t in w]
+        gw = _zeros_like_many(w)
         grads = _lib.GnodeSage3Grads(*[t.data_ptr() for t in gw])
         L = _lib.lib()
         ws = _ws(L.gnode_integrate_fixed_adjoint_workspace_bytes(N, D, H, ctx.method), sol.device)
@@ -401,7 +431,7 @@ class _IntegrateDopri5Fn(torch.autograd.Function):
         p = _sage3_params(D, H, w)
         T, K = len(ctx.t_host), len(ctx.tau) - 1
         gy0 = torch.empty((N, D), dtype=torch.float32, device=y0.device) if ctx.needs_input_grad[0] else None
-        gw = [torch.zeros_like(t) for t in w]
+        gw = _zeros_like_many(w)
         grads = _lib.GnodeSage3Grads(*[t.data_ptr() for t in gw])
         L = _lib.lib()
         prev_fold = L.gnode_set_fold(1)                  # the replay runs on the folded integrator
@@ -497,19 +527,11 @@ class _IntegrateDecodeFn(torch.autograd.Function):
     def forward(ctx, y0, graph: CSRGraph, method: int, t_host: Tuple[float, ...], dec_w, dec_b, *w):
         ctx.set_materialize_grads(False)
         y0 = _f32(y0, "y0")
-        sol, w = _fixed_forward(ctx, y0, graph, method, t_host, w, sol0_by_caller=True)   # fills ctx.{graph,method,t_host,save,fold}
         dec_w, dec_b = _f32(dec_w, "position_decoder.weight"), _f32(dec_b, "position_decoder.bias")
-        T, N, D = sol.shape
-        n_out = dec_w.shape[0]
-        traj = torch.empty((T, N, n_out), dtype=torch.float32, device=sol.device)
-        L = _lib.lib()
-        with torch.cuda.device(sol.device):
-            # first time point: decode y0 and write solution[0] in the same pass (no separate copy of the D-wide state)
-            _lib.check(L.gnode_decoder_fwd_copy(_lib.ptr(y0), N, D, n_out, _lib.ptr(dec_w), _lib.ptr(dec_b), _lib.ptr(traj),
-                                                _lib.ptr(sol), _lib.stream_ptr(sol.device)), "gnode_decoder_fwd_copy")
-            if T > 1:
-                _lib.check(L.gnode_decoder_fwd(_lib.ptr(sol[1:]), (T - 1) * N, D, n_out, _lib.ptr(dec_w), _lib.ptr(dec_b),
-                                               _lib.ptr(traj[1:]), _lib.stream_ptr(sol.device)), "gnode_decoder_fwd")
+        if dec_w.shape[0] > 8:
+            raise GnodeError("position_decoder wider than 8 outputs is not supported by the fused decoder")
+        # the solve and the decoder in one call; fills ctx.{graph,method,t_host,save,fold}
+        sol, w, traj = _fixed_forward(ctx, y0, graph, method, t_host, w, decoder=(dec_w, dec_b))
         ctx.save_for_backward(sol, dec_w, *w)
         return sol, traj
 
@@ -524,10 +546,13 @@ class _IntegrateDecodeFn(torch.autograd.Function):
         need_y0 = ctx.needs_input_grad[0]
         need_dw, need_db = ctx.needs_input_grad[4], ctx.needs_input_grad[5]
         p = _sage3_params(D, H, w)
-        gw = [torch.zeros_like(t) for t in w]
+        want_dw, want_db = need_dw and g_traj is not None, need_db and g_traj is not None
+        extra = ([dec_w] if want_dw else []) + ([dec_w.new_empty(n_out)] if want_db else [])
+        bufs = _zeros_like_many(list(w) + extra)          # one fill for every parameter gradient of the step
+        gw, rest = bufs[:len(w)], bufs[len(w):]
         grads = _lib.GnodeSage3Grads(*[t.data_ptr() for t in gw])
-        g_dec_w = torch.zeros_like(dec_w) if (need_dw and g_traj is not None) else None
-        g_dec_b = torch.zeros(n_out, dtype=torch.float32, device=dev) if (need_db and g_traj is not None) else None
+        g_dec_w = rest.pop(0) if want_dw else None
+        g_dec_b = rest.pop(0) if want_db else None
         tarr = _float_array(ctx.t_host)
         if g_traj is not None:
             g_traj = _f32(g_traj, "grad_trajectories")
@@ -621,7 +646,7 @@ class _MlpRhsFn(torch.autograd.Function):
         p, H, h = _mlp_params(w)
         M = x.shape[0]
         gx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
-        gw = [torch.zeros_like(t) for t in w]
+        gw = _zeros_like_many(w)
         grads = _lib.GnodeMlpGrads(*[t.data_ptr() for t in gw])
         L = _lib.lib()
         ws = _ws(L.gnode_mlp_bwd_workspace_bytes(M, H, h, 0, 1), x.device)
@@ -694,7 +719,7 @@ class _MlpIntegrateFn(torch.autograd.Function):
         p, H, h = _mlp_params(w)
         M, T = y0.shape[0], len(ctx.t_host)
         gy0 = torch.empty_like(y0) if ctx.needs_input_grad[0] else None
-        gw = [torch.zeros_like(t) for t in w]
+        gw = _zeros_like_many(w)
         grads = _lib.GnodeMlpGrads(*[t.data_ptr() for t in gw])
         L = _lib.lib()
         m = METHODS[ctx.method]

@@ -68,6 +68,39 @@ def test_predict_trajectory_multi_step(cuda, solver, steps):
     assert rel_l2(got, want) <= FIXED_TOL
 
 
+@pytest.mark.parametrize("n_out", [1, 2, 3, 4, 6])
+@pytest.mark.parametrize("fold", [True, False])
+def test_fused_decoder_equals_decoder_over_the_solution(cuda, n_out, fold):
+    """gnode_integrate_fixed_decoded (GraphODE.forward, scripts/train_gde.py:78-94): time point j + 1 decoded from time
+    point j and the step's 2H-wide stage combination (folded integrator, n_out <= 4) must equal position_decoder applied
+    to the D-wide solution; n_out = 6 and the direct integrator take the plain decoder inside the same call."""
+    batch, _ = S.synthetic.warehouse_batch(6, seed=9)
+    D = batch.x.shape[1]
+    f = S.GraphODEFunc(D, 64)
+    S.synthetic.init_weights(f, seed=2, conv3_scale=0.05)
+    f = f.to(cuda)
+    g = torch.Generator().manual_seed(5)
+    dec_w = (torch.randn(n_out, D, generator=g) / D ** 0.5).to(cuda)
+    dec_b = torch.randn(n_out, generator=g).to(cuda)
+    gb = batch.to(cuda)
+    graph = S.csr_for(gb.edge_index, gb.x.shape[0], graph_ptr=gb.ptr, max_graph_nodes=95)
+    t = [0.0, 0.5, 1.0, 1.75, 2.0, 3.0]
+    prev = S._lib.set_fold(fold)
+    try:
+        with torch.no_grad():
+            sol, traj = S.ops.integrate_fixed_decode(gb.x, graph, f.param_list(), t, "rk4", dec_w, dec_b)
+            sol2 = S.ops.integrate_fixed(gb.x, graph, f.param_list(), t, "rk4")
+    finally:
+        S._lib.set_fold(prev)
+    S._lib.tc_check(cuda)
+    assert torch.equal(sol[0], gb.x) and torch.equal(sol, sol2)
+    want = torch.nn.functional.linear(sol.double(), dec_w.double(), dec_b.double())
+    err = rel_l2(traj, want)
+    print(f"fused decoder n_out={n_out} fold={fold}: rel-L2 vs float64 decoder over the solution {err:.2e}")
+    assert traj.shape == (len(t), gb.x.shape[0], n_out)
+    assert err <= 2e-6
+
+
 @pytest.mark.parametrize("solver,T", [("euler", 2), ("rk4", 2), ("midpoint", 2), ("rk4", 4)])
 def test_train_step_gradients(cuda, solver, T):
     batch, nxt = S.synthetic.warehouse_batch(8, seed=1)
@@ -213,6 +246,56 @@ def test_dopri5_many_steps_identical_decisions(cuda, scale, rtol, atol, t_points
     for a, b in zip(st.dts, rst.dts):
         assert abs(a - b) <= 1e-2 * abs(b)
     assert rel_l2(got, want) <= FIXED_TOL
+
+
+@pytest.mark.parametrize("tiled", [True, False])
+@pytest.mark.parametrize("scale,rtol,atol,t_points", [(6.0, 1e-4, 1e-5, [0.0, 1.0, 3.0]),
+                                                       (10.0, 1e-3, 1e-4, [0.0, 0.5, 1.0, 1.5, 2.0, 3.0])])
+def test_dopri5_folded_fsal_matches_the_step_by_step_form(cuda, tiled, scale, rtol, atol, t_points):
+    """gnode_set_dopri5_fsal: Z_0 handed from stage 6 of an accepted step to the next attempt and dense output as one
+    projection (default) against Z_0 contracted from y on every attempt and torchdiffeq's quartic evaluated D-wide.
+    Same decisions, same values to fp32 rounding, and both against the oracle (scripts/train_gde.py:78-85 with
+    ode_solver='dopri5').  tiled = graph-resident stage kernel (whole-graph tiles from `ptr`), else kernel per op."""
+    from oracle.torchdiffeq_ref import SolverStats, odeint_ref
+    from oracle.train_gde_ref import GraphODEFuncRef
+
+    batch, _ = S.synthetic.warehouse_batch(3, num_agvs=19, num_pickers=9, seed=4)
+    D = batch.x.shape[1]
+    fref = GraphODEFuncRef(D, 64)
+    S.synthetic.init_weights(fref, seed=1, conv3_scale=scale)
+    f = S.GraphODEFunc(D, 64)
+    f.load_state_dict(fref.state_dict())
+    f = f.to(cuda)
+    rst = SolverStats()
+    t = torch.tensor(t_points)
+    with torch.no_grad():
+        want = odeint_ref(lambda tt, x: fref(tt, x, batch.edge_index), batch.x, t, rtol=rtol, atol=atol, method="dopri5",
+                          stats=rst)
+        gb = batch.to(cuda)
+        if tiled:
+            g = S.csr_for(gb.edge_index, gb.x.shape[0], graph_ptr=gb.ptr, max_graph_nodes=140)
+        else:
+            g = S.csr_for(gb.edge_index, gb.x.shape[0])
+        prev = S._lib.set_dopri5_fsal(True)
+        try:
+            assert prev is True                      # the default
+            got_on, st_on = S.ops.integrate_dopri5(gb.x, g, f.param_list(), t_points, rtol, atol)
+            S._lib.set_dopri5_fsal(False)
+            got_off, st_off = S.ops.integrate_dopri5(gb.x, g, f.param_list(), t_points, rtol, atol)
+        finally:
+            S._lib.set_dopri5_fsal(prev)
+    S._lib.tc_check(cuda)
+    print(f"dopri5 fsal[{'tiles' if tiled else 'per-op'},{scale},{rtol}]: accepted {st_on.n_accepted}/{st_off.n_accepted}/{rst.n_accepted} "
+          f"attempted {st_on.n_attempted}/{st_off.n_attempted}/{rst.n_attempted} on-vs-off {rel_l2(got_on, got_off):.2e} "
+          f"on-vs-oracle {rel_l2(got_on, want):.2e} off-vs-oracle {rel_l2(got_off, want):.2e}")
+    assert rst.n_accepted >= 10
+    for st in (st_on, st_off):
+        assert st.accepted == rst.accepted and st.n_attempted == rst.n_attempted and st.nfe == rst.nfe
+        for a, b in zip(st.dts, rst.dts):
+            assert abs(a - b) <= 1e-2 * abs(b)
+    assert rel_l2(got_on, got_off) <= 5e-5      # the D-wide quartic of the off form cancels 32 |y| terms in fp32
+    assert rel_l2(got_on, want) <= FIXED_TOL
+    assert rel_l2(got_off, want) <= FIXED_TOL
 
 
 def test_odeint_entry_point_signature(cuda):
