@@ -475,6 +475,8 @@ bool chain_bwd_supported(const Sage3Ctx& c, const FoldWs& f) {
 int chain_bwd(Sage3Ctx& c, FoldWs& f, const Tableau& tb, float dt, bool* has_u, cudaStream_t s) {
   int* status_dev = tc::status_ptr();
   if (!status_dev) { set_error("chain_bwd: status symbol unavailable"); return GNODE_ERR_CUDA; }
+  if (c.pend_ci2T) { GN_TRY(chain_pack_image(c.w2catT, 2 * c.H, c.H, c.H, c.ci2T, s)); c.pend_ci2T = 0; }   // see chain_fwd
+  if (f.pend_ci13T) { GN_TRY(chain_pack_image(f.M13T, 2 * c.H, 2 * c.H, 2 * c.H, f.ci13T, s)); f.pend_ci13T = 0; }
   chain::BwdArgs a{};
   a.G3 = f.G3; a.GZ = f.GZ;
   int n_u = 0;

@@ -744,6 +744,9 @@ bool chain_fwd_supported(const Sage3Ctx& c) { return c.H == chain::WH && c.use_t
 int chain_fwd(Sage3Ctx& c, FoldWs& f, const Tableau& tb, float dt, float* Cout, cudaStream_t s, float* Cout2, const double* coef2) {
   int* status_dev = tc::status_ptr();
   if (!status_dev) { set_error("chain_fwd: status symbol unavailable"); return GNODE_ERR_CUDA; }
+  // weight images of this kernel: packed by the first launch that reads them (Sage3Ctx::pack / FoldWs::prepare only mark them)
+  if (c.pend_ci2) { GN_TRY(chain_pack_image(c.w2cat, c.H, 2 * c.H, 2 * c.H, c.ci2, s)); c.pend_ci2 = 0; }
+  if (f.pend_ci13) { GN_TRY(chain_pack_image(f.M13, 2 * c.H, 2 * c.H, 2 * c.H, f.ci13, s)); f.pend_ci13 = 0; }
   chain::Args a{};
   a.z0 = f.z0;
   for (int st = 0; st < tb.S; ++st) {

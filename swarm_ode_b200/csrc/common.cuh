@@ -93,6 +93,7 @@ constexpr int kNumSMs = 148;  // B200
 int current_engine();
 int current_fold();
 int current_dopri5_fsal();
+bool lazy_images_poisoned();   // GNODE_POISON_LAZY=1: lazily packed weight images start as NaN patterns (tests)
 
 // ---- dense contractions (gemm_simt.cu / gemm_tc.cu) ----
 // C[m, n] = epi( sum_k A[m, k] * B[n, k] )          (both operands K-contiguous, "NT")
@@ -115,6 +116,11 @@ struct GemmNT {
   const float* Bsplit = nullptr;   // optional: B pre-split into tf32 hi/lo planes (presplit_weights) -> tcgen05 engine
   const float* Bchain = nullptr;   // optional: chunked chain-format image of B (gemm_k128_pack) -> K = 128 wide-output engine
   int rows_engine = 0;             // the caller accepts the row-major K = 128 engine (three-term truncated product) when it fits
+  // Lazy images: a non-null flag that reads 1 says the image behind Bsplit / Bchain has NOT been packed yet; gemm_nt packs
+  // it (from B) only if the engine it picks reads it, and clears the flag.  (A training step packed 27 weight images per
+  // step and read 11 of them.)
+  int* Bsplit_pending = nullptr;
+  int* Bchain_pending = nullptr;
 };
 int gemm_nt(const GemmNT& g, cudaStream_t s);
 // tf32 hi/lo planes of a row-major weight matrix, zero padded to multiples of 16 (gemm_tc.cu)

@@ -51,6 +51,16 @@ struct Sage3Ctx : Field {
   float *ci2 = nullptr, *ci2T = nullptr;   // chain-kernel images (chain_common.cuh) of w2cat [H x 2H] and w2catT [2H x H]
   float *ck3 = nullptr, *ck1T = nullptr;   // chunked images (gemm_k128.cu) of w3cat [D x 2H] and w1catT [D x 2H]
   bool use_tc = false;
+  // images not packed yet (pack() only marks them; the first reader packs: gemm_nt through GemmNT::*_pending, the chain
+  // kernels through ensure_chain_images)
+  int pend_s1 = 0, pend_s2 = 0, pend_s3 = 0, pend_s1T = 0, pend_s2T = 0, pend_s3T = 0;
+  int pend_ci2 = 0, pend_ci2T = 0, pend_ck3 = 0, pend_ck1T = 0;
+  void use_w1(GemmNT& q) { q.Bsplit = use_tc ? s1 : nullptr; q.Bsplit_pending = &pend_s1; }
+  void use_w2(GemmNT& q) { q.Bsplit = use_tc ? s2 : nullptr; q.Bsplit_pending = &pend_s2; }
+  void use_w3(GemmNT& q) { q.Bsplit = use_tc ? s3 : nullptr; q.Bsplit_pending = &pend_s3; q.Bchain = use_tc ? ck3 : nullptr; q.Bchain_pending = &pend_ck3; }
+  void use_w1T(GemmNT& q) { q.Bsplit = use_tc ? s1T : nullptr; q.Bsplit_pending = &pend_s1T; q.Bchain = use_tc ? ck1T : nullptr; q.Bchain_pending = &pend_ck1T; }
+  void use_w2T(GemmNT& q) { q.Bsplit = use_tc ? s2T : nullptr; q.Bsplit_pending = &pend_s2T; }
+  void use_w3T(GemmNT& q) { q.Bsplit = use_tc ? s3T : nullptr; q.Bsplit_pending = &pend_s3T; }
   bool skip_wgrad = false;             // vjp: data gradient only (adjoint stages whose solution weight is zero)
   float* z = nullptr;                  // [N, 2H]  x @ w1cat^T
   int n_slots = 1;
@@ -80,6 +90,9 @@ struct FoldWs {
   float *M13 = nullptr, *M13T = nullptr, *c13 = nullptr;   // w1cat @ w3cat [2H, 2H], its transpose, w1cat @ b3 [2H]
   float *sM13 = nullptr, *sM13T = nullptr;                 // tf32 hi/lo planes of the two
   float *ci13 = nullptr, *ci13T = nullptr;                 // chain-kernel images of the two
+  int pend_sM13 = 0, pend_sM13T = 0, pend_ci13 = 0, pend_ci13T = 0;   // not packed yet (prepare() only marks them)
+  void use_M13(const Sage3Ctx& c, GemmNT& q) { q.Bsplit = c.use_tc ? sM13 : nullptr; q.Bsplit_pending = &pend_sM13; }
+  void use_M13T(const Sage3Ctx& c, GemmNT& q) { q.Bsplit = c.use_tc ? sM13T : nullptr; q.Bsplit_pending = &pend_sM13T; }
   float *z0 = nullptr, *Cbuf = nullptr;                    // [N, 2H]
   float* Cslot = nullptr;                                  // C = dt sum_s c_s cat2_s of the current step (save area or Cbuf)
   // FSAL in the folded space (dopri5): the input of the last stage is the step's solution y_1, so Z of that stage IS

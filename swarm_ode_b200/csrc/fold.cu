@@ -248,12 +248,14 @@ int FoldWs::prepare(Sage3Ctx& c, cudaStream_t s) {
     k_fold_weights<<<grid, 256, 0, s>>>(c.w1cat, c.w3cat, c.b3, H2, c.D, M13, M13T, c13);
     GN_LAUNCHED();
   }
-  if (c.use_tc) {
-    GN_TRY(presplit_weights(M13, H2, H2, H2, sM13, s));
-    GN_TRY(presplit_weights(M13T, H2, H2, H2, sM13T, s));
+  pend_sM13 = pend_sM13T = c.use_tc ? 1 : 0;                                    // packed by their first reader
+  pend_ci13 = pend_ci13T = (c.use_tc && chain_shape_ok(c.H)) ? 1 : 0;
+  if (c.use_tc && lazy_images_poisoned()) {
+    GN_CUDA(cudaMemsetAsync(sM13, 0xFF, sizeof(float) * presplit_floats(H2, H2), s));
+    GN_CUDA(cudaMemsetAsync(sM13T, 0xFF, sizeof(float) * presplit_floats(H2, H2), s));
     if (chain_shape_ok(c.H)) {
-      GN_TRY(chain_pack_image(M13, H2, H2, H2, ci13, s));
-      GN_TRY(chain_pack_image(M13T, H2, H2, H2, ci13T, s));
+      GN_CUDA(cudaMemsetAsync(ci13, 0xFF, sizeof(float) * chain_image_floats(H2, H2), s));
+      GN_CUDA(cudaMemsetAsync(ci13T, 0xFF, sizeof(float) * chain_image_floats(H2, H2), s));
     }
   }
   return GNODE_OK;
@@ -268,7 +270,7 @@ int FoldWs::forward_stages(Sage3Ctx& c, const Tableau& tb, const float* y, float
   if (!z0_ready) {  // Z_0 = y @ w1cat^T
     GemmNT q{};
     q.A = y; q.lda = c.D; q.B = c.w1cat; q.ldb = c.D; q.C = z0; q.ldc = H2; q.M = N; q.N = H2; q.K = c.D;
-    q.Bsplit = c.use_tc ? c.s1 : nullptr;
+    c.use_w1(q);
     GN_TRY(gemm_nt(q, s));
   }
   z_next_valid = false;
@@ -292,7 +294,7 @@ int FoldWs::forward_stages(Sage3Ctx& c, const Tableau& tb, const float* y, float
       GemmNT q{};
       q.A = Vbuf; q.lda = H2; q.B = M13; q.ldb = H2; q.C = c.z; q.ldc = H2; q.M = N; q.N = H2; q.K = H2;
       q.bias = c13; q.bias_scale = (float)bsum * dt; q.base = z0; q.ldbase = H2;
-      q.Bsplit = c.use_tc ? sM13 : nullptr;
+      use_M13(c, q);
       GN_TRY(gemm_nt(q, s));
       z = c.z;
     }
@@ -304,7 +306,7 @@ int FoldWs::forward_stages(Sage3Ctx& c, const Tableau& tb, const float* y, float
       GemmNT q{};
       q.A = c1; q.lda = H2; q.B = c.w2cat; q.ldb = H2; q.C = c2 + H; q.ldc = H2; q.M = N; q.N = H; q.K = H2;
       q.bias = c.b2; q.relu = 1;
-      q.Bsplit = c.use_tc ? c.s2 : nullptr;
+      c.use_w2(q);
       GN_TRY(gemm_nt(q, s));                                                          // h2
     }
     GN_TRY(agg_mean_fwd(c.g, c2 + H, H2, c2, H2, H, nullptr, 0, nullptr, 0, s));     // A(h2)
@@ -352,7 +354,7 @@ int integrate_fixed_folded(Sage3Ctx& c, FoldWs& f, const Tableau& tb, const floa
     GemmNT q{};   // y_1 = y + C @ w3cat^T + (dt sum c) b3
     q.A = f.Cslot; q.lda = H2; q.B = c.w3cat; q.ldb = H2; q.C = y1; q.ldc = c.D; q.M = c.N; q.N = c.D; q.K = H2;
     q.bias = c.b3; q.bias_scale = (float)csum * dt; q.base = y; q.ldbase = c.D;
-    q.Bsplit = c.use_tc ? c.s3 : nullptr; q.Bchain = c.use_tc ? c.ck3 : nullptr; q.rows_engine = 1;
+    c.use_w3(q); q.rows_engine = 1;
     GN_TRY(gemm_nt(q, s));
     if (dec) {
       const float* prev = dec->traj + (int64_t)j * c.N * dec->n_out;
@@ -392,7 +394,7 @@ static int fold_step_bwd(Sage3Ctx& c, FoldWs& f, const Tableau& tb, float dt, co
   } else {  // G3 = G @ w3cat     [N, 2H]
     GemmNT q{};
     q.A = G; q.lda = c.D; q.B = c.w3catT; q.ldb = c.D; q.C = f.G3; q.ldc = H2; q.M = N; q.N = H2; q.K = c.D;
-    q.Bsplit = c.use_tc ? c.s3T : nullptr;
+    c.use_w3T(q);
     GN_TRY(gemm_nt(q, s));
   }
   if (chain_bwd_supported(c, f)) {
@@ -447,7 +449,7 @@ static int fold_step_bwd(Sage3Ctx& c, FoldWs& f, const Tableau& tb, float dt, co
         GemmNT q{};   // gcat = dt c_st G3 + U @ M13
         q.A = f.U; q.lda = H2; q.B = f.M13T; q.ldb = H2; q.C = c.gcat; q.ldc = H2; q.M = N; q.N = H2; q.K = H2;
         q.base = f.G3; q.ldbase = H2; q.base_scale = cs_dt;
-        q.Bsplit = c.use_tc ? f.sM13T : nullptr;
+        f.use_M13T(c, q);
         GN_TRY(gemm_nt(q, s));
       } else {
         LinComb lg{};
@@ -461,7 +463,7 @@ static int fold_step_bwd(Sage3Ctx& c, FoldWs& f, const Tableau& tb, float dt, co
       {  // gcat = g_v2 @ w2cat   [N, 2H]
         GemmNT q{};
         q.A = c.gv2; q.lda = H; q.B = c.w2catT; q.ldb = H; q.C = c.gcat; q.ldc = H2; q.M = N; q.N = H2; q.K = H;
-        q.Bsplit = c.use_tc ? c.s2T : nullptr;
+        c.use_w2T(q);
         GN_TRY(gemm_nt(q, s));
       }
       {  // dW2cat += g_v2^T @ cat1
@@ -530,7 +532,7 @@ int integrate_fixed_folded_bwd(Sage3Ctx& c, FoldWs& f, const Tableau& tb, const 
       GemmNT q{};
       q.A = f.GZ; q.lda = H2; q.B = c.w1catT; q.ldb = H2; q.C = gout; q.ldc = c.D; q.M = N; q.N = c.D; q.K = H2;
       q.base = G; q.ldbase = c.D; q.base2 = grad_sol + (int64_t)j * n; q.ldbase2 = c.D;
-      q.Bsplit = c.use_tc ? c.s1T : nullptr; q.Bchain = c.use_tc ? c.ck1T : nullptr;
+      c.use_w1T(q);
       GN_TRY(gemm_nt(q, s));
     }
     G = gout;
@@ -592,7 +594,7 @@ int integrate_dopri5_folded_bwd(Sage3Ctx& c, FoldWs& f, const float* y0, const d
     GemmNT q{};   // y_{k+1} = y_k + C @ w3cat^T + (dt sum c) b3
     q.A = f.Cslot; q.lda = H2; q.B = c.w3cat; q.ldb = H2; q.C = ys + (int64_t)(k + 1) * n; q.ldc = c.D; q.M = N; q.N = c.D; q.K = H2;
     q.bias = c.b3; q.bias_scale = (float)csum * dt; q.base = y; q.ldbase = c.D;
-    q.Bsplit = c.use_tc ? c.s3 : nullptr; q.Bchain = c.use_tc ? c.ck3 : nullptr;
+    c.use_w3(q);
     q.rows_engine = 1;   // the replay takes no step-size decisions: the row-major engine may compute it
     GN_TRY(gemm_nt(q, s));
   }
@@ -634,7 +636,7 @@ int integrate_dopri5_folded_bwd(Sage3Ctx& c, FoldWs& f, const float* y0, const d
         g.A = f.GZ; g.lda = H2; g.B = c.w1catT; g.ldb = H2; g.C = gout; g.ldc = c.D; g.M = N; g.N = c.D; g.K = H2;
         g.base = G; g.ldbase = c.D;
         if (!first) { g.base2 = gout; g.ldbase2 = c.D; }
-        g.Bsplit = c.use_tc ? c.s1T : nullptr; g.Bchain = c.use_tc ? c.ck1T : nullptr;
+        c.use_w1T(g);
         GN_TRY(gemm_nt(g, s));
       }
       first = false;

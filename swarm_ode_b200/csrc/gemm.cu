@@ -23,6 +23,17 @@ int gemm_nt(const GemmNT& g, cudaStream_t s) {
   // projection of the fixed-grid solvers.
   const bool rows = g.rows_engine && rows_engine_on() && engine != GNODE_ENGINE_SIMT && gemm_k128_rows_supported(g);
   const bool tc = engine != GNODE_ENGINE_SIMT && gemm_nt_tc_supported(g);
+  if (rows) {
+    if (g.Bchain_pending && *g.Bchain_pending) {
+      GN_TRY(gemm_k128_pack(g.B, g.N, g.ldb, const_cast<float*>(g.Bchain), s));
+      *g.Bchain_pending = 0;
+    }
+  } else if (tc) {
+    if (g.Bsplit_pending && *g.Bsplit_pending) {
+      GN_TRY(presplit_weights(g.B, g.N, g.K, g.ldb, const_cast<float*>(g.Bsplit), s));
+      *g.Bsplit_pending = 0;
+    }
+  }
   GN_PROF(s, 2.0 * g.M * g.N * g.K, 4.0 * ((double)g.M * g.K + (double)g.N * g.K + (double)g.M * g.N * (g.base ? 2 : 1)),
           "gemm_nt[%s] N=%d K=%d", rows ? "k128 rows" : (tc ? "tcgen05" : "ffma"), g.N, g.K);
   if (engine == GNODE_ENGINE_SIMT) return gemm_nt_simt(g, s);

@@ -338,7 +338,7 @@ int integrate_dopri5_folded(Sage3Ctx& c, FoldWs& f, const float* y0, const doubl
     GemmNT q{};
     q.A = W; q.lda = H2; q.B = c.w3cat; q.ldb = H2; q.C = out; q.ldc = c.D; q.M = c.N; q.N = c.D; q.K = H2;
     q.bias = c.b3; q.bias_scale = bias_scale; q.base = base; q.ldbase = c.D;
-    q.Bsplit = c.use_tc ? c.s3 : nullptr; q.Bchain = c.use_tc ? c.ck3 : nullptr;
+    c.use_w3(q);
     q.rows_engine = 1;      // dense D-wide rows in and out: the row-major K = 128 engine when D <= 440 (gemm_k128.cu)
     return gemm_nt(q, s);
   };

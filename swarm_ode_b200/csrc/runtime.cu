@@ -27,6 +27,10 @@ void set_error(const char* fmt, ...) {
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 int current_engine() { return g_engine.load(std::memory_order_relaxed); }
 int current_fold() { return g_fold.load(std::memory_order_relaxed); }
+bool lazy_images_poisoned() {
+  static const bool on = [] { const char* e = std::getenv("GNODE_POISON_LAZY"); return e && e[0] == '1'; }();
+  return on;
+}
 int current_dopri5_fsal() {
   int v = g_dopri5_fsal.load(std::memory_order_relaxed);
   if (v < 0) {

@@ -76,22 +76,27 @@ int Sage3Ctx::pack(const gnode_sage3_params& p, bool backward, cudaStream_t s) {
   }
   GN_TRY(pack_segments(sg, n, s));
   use_tc = current_engine() != GNODE_ENGINE_SIMT;
-  if (use_tc) {
-    GN_TRY(presplit_weights(w1cat, 2 * H, D, D, s1, s));
-    GN_TRY(presplit_weights(w2cat, H, 2 * H, 2 * H, s2, s));
-    GN_TRY(presplit_weights(w3cat, D, 2 * H, 2 * H, s3, s));
+  // the tcgen05 images of the packed matrices are made by whoever reads them first (see field.cuh)
+  pend_s1 = pend_s2 = pend_s3 = use_tc ? 1 : 0;
+  pend_ci2 = pend_ck3 = (use_tc && chain_shape_ok(H)) ? 1 : 0;
+  pend_s1T = pend_s2T = pend_s3T = (use_tc && backward) ? 1 : 0;
+  pend_ci2T = pend_ck1T = (use_tc && backward && chain_shape_ok(H)) ? 1 : 0;
+  if (use_tc && lazy_images_poisoned()) {   // GNODE_POISON_LAZY=1 (tests): a reader that skips the flag sees NaNs, not stale images
+    GN_CUDA(cudaMemsetAsync(s1, 0xFF, sizeof(float) * presplit_floats(2 * H, D), s));
+    GN_CUDA(cudaMemsetAsync(s2, 0xFF, sizeof(float) * presplit_floats(H, 2 * H), s));
+    GN_CUDA(cudaMemsetAsync(s3, 0xFF, sizeof(float) * presplit_floats(D, 2 * H), s));
     if (chain_shape_ok(H)) {
-      GN_TRY(chain_pack_image(w2cat, H, 2 * H, 2 * H, ci2, s));
-      GN_TRY(gemm_k128_pack(w3cat, D, 2 * H, ck3, s));
-      if (backward) {
-        GN_TRY(chain_pack_image(w2catT, 2 * H, H, H, ci2T, s));
-        GN_TRY(gemm_k128_pack(w1catT, D, 2 * H, ck1T, s));
-      }
+      GN_CUDA(cudaMemsetAsync(ci2, 0xFF, sizeof(float) * chain_image_floats(H, 2 * H), s));
+      GN_CUDA(cudaMemsetAsync(ck3, 0xFF, sizeof(float) * gemm_k128_image_floats(D), s));
     }
     if (backward) {
-      GN_TRY(presplit_weights(w1catT, D, 2 * H, 2 * H, s1T, s));
-      GN_TRY(presplit_weights(w2catT, 2 * H, H, H, s2T, s));
-      GN_TRY(presplit_weights(w3catT, 2 * H, D, D, s3T, s));
+      GN_CUDA(cudaMemsetAsync(s1T, 0xFF, sizeof(float) * presplit_floats(D, 2 * H), s));
+      GN_CUDA(cudaMemsetAsync(s2T, 0xFF, sizeof(float) * presplit_floats(2 * H, H), s));
+      GN_CUDA(cudaMemsetAsync(s3T, 0xFF, sizeof(float) * presplit_floats(2 * H, D), s));
+      if (chain_shape_ok(H)) {
+        GN_CUDA(cudaMemsetAsync(ci2T, 0xFF, sizeof(float) * chain_image_floats(2 * H, H), s));
+        GN_CUDA(cudaMemsetAsync(ck1T, 0xFF, sizeof(float) * gemm_k128_image_floats(D), s));
+      }
     }
   }
   return GNODE_OK;
@@ -132,7 +137,7 @@ int Sage3Ctx::eval(const float* x, float* out, const float* base, float scale, i
   {  // Z = x @ w1cat^T
     GemmNT q{};
     q.A = x; q.lda = D; q.B = w1cat; q.ldb = D; q.C = z; q.ldc = H2; q.M = N; q.N = H2; q.K = D;
-    q.Bsplit = use_tc ? s1 : nullptr;
+    use_w1(q);
     GN_TRY(gemm_nt(q, s));
   }
   // h1 = relu(A(Z_l) + Z_r + b1) -> cat1[:, H:]
@@ -143,7 +148,7 @@ int Sage3Ctx::eval(const float* x, float* out, const float* base, float scale, i
     GemmNT q{};
     q.A = c1; q.lda = H2; q.B = w2cat; q.ldb = H2; q.C = c2 + H; q.ldc = H2; q.M = N; q.N = H; q.K = H2;
     q.bias = b2; q.relu = 1;
-    q.Bsplit = use_tc ? s2 : nullptr;
+    use_w2(q);
     GN_TRY(gemm_nt(q, s));
   }
   // A(h2) -> cat2[:, :H]
@@ -152,7 +157,7 @@ int Sage3Ctx::eval(const float* x, float* out, const float* base, float scale, i
     GemmNT q{};
     q.A = c2; q.lda = H2; q.B = w3cat; q.ldb = H2; q.C = out; q.ldc = D; q.M = N; q.N = D; q.K = H2;
     q.bias = b3; q.base = base; q.ldbase = D; q.scale = scale;
-    q.Bsplit = use_tc ? s3 : nullptr; q.Bchain = use_tc ? ck3 : nullptr;
+    use_w3(q);
     GN_TRY(gemm_nt(q, s));
   }
   return GNODE_OK;
@@ -166,7 +171,7 @@ int Sage3Ctx::vjp(const float* x, int slot, const float* gk, float* gx, cudaStre
   {  // gcat = gk @ w3cat          [N, 2H]
     GemmNT q{};
     q.A = gk; q.lda = D; q.B = w3catT; q.ldb = D; q.C = gcat; q.ldc = H2; q.M = N; q.N = H2; q.K = D;
-    q.Bsplit = use_tc ? s3T : nullptr;
+    use_w3T(q);
     GN_TRY(gemm_nt(q, s));
   }
   if (!skip_wgrad) {  // dW3cat += gk^T @ cat2      [D, 2H]
@@ -181,7 +186,7 @@ int Sage3Ctx::vjp(const float* x, int slot, const float* gk, float* gx, cudaStre
   {  // gcat = g_v2 @ w2cat        [N, 2H]
     GemmNT q{};
     q.A = gv2; q.lda = H; q.B = w2catT; q.ldb = H; q.C = gcat; q.ldc = H2; q.M = N; q.N = H2; q.K = H;
-    q.Bsplit = use_tc ? s2T : nullptr;
+    use_w2T(q);
     GN_TRY(gemm_nt(q, s));
   }
   if (!skip_wgrad) {  // dW2cat += g_v2^T @ cat1    [H, 2H]
@@ -197,7 +202,7 @@ int Sage3Ctx::vjp(const float* x, int slot, const float* gk, float* gx, cudaStre
   {  // gx = gz @ w1cat            [N, D]
     GemmNT q{};
     q.A = gz; q.lda = H2; q.B = w1catT; q.ldb = H2; q.C = gx; q.ldc = D; q.M = N; q.N = D; q.K = H2;
-    q.Bsplit = use_tc ? s1T : nullptr; q.Bchain = use_tc ? ck1T : nullptr;
+    use_w1T(q);
     GN_TRY(gemm_nt(q, s));
   }
   if (!skip_wgrad) {  // dW1cat += gz^T @ x         [2H, D]
