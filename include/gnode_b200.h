@@ -319,6 +319,15 @@ typedef struct {
  * of a norm; must return them summed over all ranks (torch.distributed all-reduce on the Python
  * side).  NULL = single rank. */
 typedef void (*gnode_allreduce_fn)(double* sumsq_and_count /* [2], in/out */, void* user);
+/* Device-side form of the same exchange, registered for the CALLING THREAD (NULL clears it) and used by its following
+ * gnode_integrate_dopri5 / gnode_mlp_integrate_dopri5 calls: per norm the library hands the hook the DEVICE address of the
+ * local sum of squares (one double inside the call's workspace); the hook enqueues an in-place SUM all-reduce over the
+ * data-parallel ranks on the solve's stream (ncclAllReduce / torch.distributed.all_reduce) and returns 0.  The host then
+ * reads the global sum with the one synchronisation per attempted step that the step-size decision needs -- no
+ * device -> host -> device round trip for the exchange.  The element count is summed once per solve through the host hook
+ * (gnode_allreduce_fn, which must be given as well). */
+typedef int (*gnode_allreduce_dev_fn)(double* device_sumsq /* [1], in/out, device memory */, void* user);
+int gnode_set_dopri5_device_allreduce(gnode_allreduce_dev_fn fn, void* user);
 
 size_t gnode_integrate_dopri5_workspace_bytes(int64_t n_nodes, int32_t node_dim, int32_t hidden_dim);
 int gnode_integrate_dopri5(const gnode_graph* g, const gnode_sage3_params* p, const float* y0,

@@ -62,6 +62,7 @@ class GnodeProfEntry(C.Structure):
 
 
 ALLREDUCE_FN = C.CFUNCTYPE(None, C.POINTER(C.c_double), C.c_void_p)
+ALLREDUCE_DEV_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p)
 
 _P = C.c_void_p
 _SIGNATURES = {
@@ -71,6 +72,7 @@ _SIGNATURES = {
     "gnode_set_engine": (C.c_int, [C.c_int]),
     "gnode_set_fold": (C.c_int, [C.c_int]),
     "gnode_set_dopri5_fsal": (C.c_int, [C.c_int]),
+    "gnode_set_dopri5_device_allreduce": (C.c_int, [ALLREDUCE_DEV_FN, C.c_void_p]),
     "gnode_launch_count": (C.c_int64, []),
     "gnode_tc_status": (C.c_int, [_P]),
     "gnode_tc_status_async": (C.c_int, [_P, _P]),

@@ -143,16 +143,33 @@ int integrate_fixed(Field& f, int method, const float* y0, const float* t, int n
 // ------------------------------------------------------------------------------------------------
 namespace {
 
+// device-side exchange of the norm registered for the calling thread (gnode_set_dopri5_device_allreduce)
+thread_local gnode_allreduce_dev_fn t_allreduce_dev = nullptr;
+thread_local void* t_allreduce_dev_user = nullptr;
+
 struct NormCtx {
   gnode_allreduce_fn allreduce; void* user; double* dsum; cudaStream_t s; int64_t n;
+  gnode_allreduce_dev_fn allreduce_dev = nullptr; void* dev_user = nullptr;
+  double n_global = 0.0;       // element count over all ranks (device-side exchange: fetched once through the host hook)
   // rms over all ranks of a local sum of squares already sitting in *dsum (device)
   int finish(float* out) {
     double h[2];
+    if (allreduce_dev) {
+      // the sum is exchanged where it lies: the hook enqueues an in-place SUM all-reduce of *dsum on the solve's stream
+      // (NCCL); the host reads the global sum with the one synchronisation the step-size decision needs anyway
+      if (n_global == 0.0) {
+        h[0] = 0.0; h[1] = (double)n;
+        if (allreduce) allreduce(h, user);
+        n_global = h[1];
+      }
+      if (allreduce_dev(dsum, dev_user) != 0) { set_error("dopri5: the device-side norm exchange failed"); return GNODE_ERR_SOLVER; }
+    }
     if (cudaMemcpyAsync(&h[0], dsum, sizeof(double), cudaMemcpyDeviceToHost, s) != cudaSuccess ||
         cudaStreamSynchronize(s) != cudaSuccess) {
       set_error("dopri5: device error while reading the error norm: %s", cudaGetErrorString(cudaGetLastError()));
       return GNODE_ERR_CUDA;
     }
+    if (allreduce_dev) { *out = (float)std::sqrt(h[0] / n_global); return GNODE_OK; }
     h[1] = (double)n;
     if (allreduce) allreduce(h, user);
     *out = (float)std::sqrt(h[0] / h[1]);
@@ -170,7 +187,7 @@ int integrate_dopri5(Field& f, const float* y0, const double* t, int n_t, double
   const float rtolf = (float)rtol, atolf = (float)atol;
   gnode_dopri5_stats st{};
   st.min_margin = INFINITY;
-  NormCtx nc{allreduce, allreduce_user, b.dsum, s, n};
+  NormCtx nc{allreduce, allreduce_user, b.dsum, s, n, t_allreduce_dev, t_allreduce_dev_user};
 
   float* k[7];
   for (int i = 0; i < 7; ++i) k[i] = b.k[i];
@@ -318,7 +335,7 @@ int integrate_dopri5_folded(Sage3Ctx& c, FoldWs& f, const float* y0, const doubl
   const float rtolf = (float)rtol, atolf = (float)atol;
   gnode_dopri5_stats st{};
   st.min_margin = INFINITY;
-  NormCtx nc{allreduce, allreduce_user, b.dsum, s, n};
+  NormCtx nc{allreduce, allreduce_user, b.dsum, s, n, t_allreduce_dev, t_allreduce_dev_user};
   float* ya = b.ya;
   float* yb = b.yb;
 
@@ -1022,6 +1039,12 @@ void carve_dopri5_fold(Arena& a, Sage3Ctx& c, FoldWs& f, Dopri5FoldBufs& b) {
   b.dsum = a.take<double>(2);
 }
 }  // namespace
+
+extern "C" int gnode_set_dopri5_device_allreduce(gnode_allreduce_dev_fn fn, void* user) {
+  t_allreduce_dev = fn;
+  t_allreduce_dev_user = user;
+  return GNODE_OK;
+}
 
 extern "C" size_t gnode_integrate_dopri5_workspace_bytes(int64_t n_nodes, int32_t node_dim, int32_t hidden_dim) {
   Sage3Ctx c;

@@ -77,6 +77,14 @@ def dopri5_norm_allreduce(device=None, group=None) -> Optional[Callable[[float, 
         s, c = t.tolist()
         return s, c
 
+    def device_allreduce(t: torch.Tensor) -> None:
+        """In-place SUM over the ranks of the local sum of squares where the library left it (device memory), enqueued
+        on the current stream: the per-attempt exchange of the GNODE solve; ``hook`` itself then runs once per solve
+        (for the global element count)."""
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+
+    if device is not None and torch.device(device).type == "cuda":
+        hook.device_allreduce = device_allreduce
     return hook
 
 
@@ -114,11 +122,12 @@ def masked_mse_train_step(model, optimizer, graphs, next_positions: torch.Tensor
         flat = torch.cat([p.grad.reshape(-1) for p in params] + [tail]).mul_(float(local_n))
         dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
         flat.div_(flat[-1].clamp_min(1.0))
-        off = 0
+        views, off = [], 0
         for p in params:
             n = p.grad.numel()
-            p.grad.copy_(flat[off:off + n].view_as(p.grad))
+            views.append(flat[off:off + n].view_as(p.grad))
             off += n
+        torch._foreach_copy_([p.grad for p in params], views)      # one launch, not one per parameter
         gl = flat[-2].clone()
     else:
         gl = loss.detach()

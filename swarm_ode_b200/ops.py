@@ -387,12 +387,38 @@ def _dopri5_forward(y0, graph: CSRGraph, w: Sequence[torch.Tensor], t_host: Sequ
     else:
         cb = C.cast(None, _lib.ALLREDUCE_FN)
 
+    # device-side exchange of the norm (``allreduce.device_allreduce(tensor)``: an in-place SUM all-reduce enqueued on the
+    # current stream, e.g. dist.dopri5_norm_allreduce): the library hands over the device address of the local sum, a view
+    # of the workspace tensor at that address goes to the hook -- no device -> host -> device round trip per attempt
+    dev_hook = getattr(allreduce, "device_allreduce", None) if allreduce is not None else None
+    dev_err: list = []
+    if dev_hook is not None:
+        base = ws.data_ptr()
+
+        def _cbd(ptr, _user):
+            try:
+                off = int(ptr) - base
+                dev_hook(ws[off:off + 8].view(torch.float64))
+                return 0
+            except BaseException as e:      # never unwind through the C frame
+                dev_err.append(e)
+                return 1
+        cbd = _lib.ALLREDUCE_DEV_FN(_cbd)
+    else:
+        cbd = C.cast(None, _lib.ALLREDUCE_DEV_FN)
+
     def call(st, tr):
         with torch.cuda.device(y0.device):
-            _lib.check(L.gnode_integrate_dopri5(graph.ref(), C.byref(p), _lib.ptr(y0), tarr, T, float(rtol),
-                                                float(atol), _lib.ptr(sol), st, tr, cb, None, int(max_num_steps),
-                                                _lib.ptr(ws), ws.numel(), _lib.stream_ptr(y0.device)),
-                       "gnode_integrate_dopri5")
+            L.gnode_set_dopri5_device_allreduce(cbd, None)
+            try:
+                rc = L.gnode_integrate_dopri5(graph.ref(), C.byref(p), _lib.ptr(y0), tarr, T, float(rtol),
+                                              float(atol), _lib.ptr(sol), st, tr, cb, None, int(max_num_steps),
+                                              _lib.ptr(ws), ws.numel(), _lib.stream_ptr(y0.device))
+            finally:
+                L.gnode_set_dopri5_device_allreduce(C.cast(None, _lib.ALLREDUCE_DEV_FN), None)
+            if dev_err:
+                raise dev_err[0]
+            _lib.check(rc, "gnode_integrate_dopri5")
 
     stats = _run_dopri5(call, trace_cap)
     graph.schedule_tile_check()

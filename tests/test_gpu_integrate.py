@@ -396,10 +396,13 @@ def test_dopri5_train_step(cuda):
         assert rel_l2(p.grad, rp[name].grad) <= DOPRI5_GRAD_TOL, (name, rel_l2(p.grad, rp[name].grad))
 
 
-def test_dopri5_two_rank_lockstep_reproduces_unsharded_decisions(cuda):
+@pytest.mark.parametrize("device_hook", [False, True])
+def test_dopri5_two_rank_lockstep_reproduces_unsharded_decisions(cuda, device_hook):
     """Two data-parallel 'ranks' run as two host threads (own CUDA stream each) on one GPU; their
     error-norm hooks rendezvous on the host and exchange (sum of squares, count) exactly as the NCCL /
-    gloo all-reduce does.  Every rank must then take the decisions of the unsharded batch."""
+    gloo all-reduce does.  Every rank must then take the decisions of the unsharded batch.
+    device_hook: the per-attempt exchange runs on the device copy of the sum (gnode_set_dopri5_device_allreduce, what
+    dist.dopri5_norm_allreduce does with NCCL); the host hook then only sums the element count, once per solve."""
     import threading
 
     batch, _ = S.synthetic.warehouse_batch(6, num_agvs=19, num_pickers=9, seed=9)
@@ -417,13 +420,30 @@ def test_dopri5_two_rank_lockstep_reproduces_unsharded_decisions(cuda):
     slots = [None, None]
     results, errors = [None, None], []
 
+    dev_slots = [None, None]
+    calls = {"host": [0, 0], "dev": [0, 0]}
+
     def hook_for(rank):
         def hook(s, c):
+            calls["host"][rank] += 1
             slots[rank] = (s, c)
             barrier.wait(timeout=60)
             tot = (slots[0][0] + slots[1][0], slots[0][1] + slots[1][1])
             barrier.wait(timeout=60)
             return tot
+
+        def device_allreduce(tt):
+            assert tt.is_cuda and tt.dtype == torch.float64 and tt.numel() == 1
+            calls["dev"][rank] += 1
+            dev_slots[rank] = tt.clone()
+            torch.cuda.current_stream().synchronize()
+            barrier.wait(timeout=60)
+            tt.copy_(dev_slots[0] + dev_slots[1])
+            torch.cuda.current_stream().synchronize()
+            barrier.wait(timeout=60)
+
+        if device_hook:
+            hook.device_allreduce = device_allreduce
         return hook
 
     def run(rank):
@@ -452,6 +472,11 @@ def test_dopri5_two_rank_lockstep_reproduces_unsharded_decisions(cuda):
             assert abs(a - b) <= 1e-5 * max(abs(b), 1e-9)
     got = torch.cat([results[0][0], results[1][0]], dim=1)
     assert rel_l2(got, full) <= 1e-5
+    n_norms = full_stats.n_attempted + 3             # three norms select the initial step, one per attempted step
+    if device_hook:
+        assert calls["dev"] == [n_norms, n_norms] and calls["host"] == [1, 1]
+    else:
+        assert calls["dev"] == [0, 0] and calls["host"] == [n_norms, n_norms]
 
 
 @pytest.mark.parametrize("n_agv,n_pick,graphs", [(12, 7, 9), (4, 3, 23), (2, 1, 40), (19, 6, 5), (19, 9, 7), (19, 9, 300), (30, 11, 4),
