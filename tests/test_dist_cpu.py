@@ -91,6 +91,12 @@ def _worker(rank, world, port, tmp):
         hook = D.dopri5_norm_allreduce()
         s, c = hook(float(rank + 1), 10.0 * (rank + 1))
         assert s == sum(r + 1 for r in range(world)) and c == 10.0 * sum(r + 1 for r in range(world))
+        # the device-side exchange is only offered for CUDA devices (gnode_set_dopri5_device_allreduce); its arithmetic is
+        # the same in-place SUM, checked here on the host tensor the hook would be handed on a GPU
+        assert not hasattr(hook, "device_allreduce")
+        t = torch.tensor([float(rank + 1)], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        assert float(t) == s
         open(os.path.join(tmp, f"ok{rank}"), "w").write("ok")
     finally:
         dist.destroy_process_group()
@@ -100,6 +106,20 @@ def test_two_rank_gloo_gradient_allreduce_and_norm_hook(tmp_path):
     world = 2
     mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
     assert all((tmp_path / f"ok{r}").exists() for r in range(world))
+
+
+def test_zeros_like_many_returns_independent_aligned_views():
+    """ops._zeros_like_many: one flat zero buffer behind the parameter-gradient tensors of a backward call."""
+    from swarm_ode_b200 import ops
+    like = [torch.ones(3, 5), torch.ones(7), torch.ones(64, 2), torch.ones(1)]
+    out = ops._zeros_like_many(like)
+    assert [o.shape for o in out] == [t.shape for t in like]
+    assert all(o.is_contiguous() and float(o.abs().sum()) == 0.0 for o in out)
+    base = out[0].data_ptr()
+    assert all((o.data_ptr() - base) % 256 == 0 for o in out)          # every view starts on a 256-byte boundary
+    out[1].fill_(3.0)                                                   # views do not overlap
+    assert float(out[0].abs().sum()) == 0.0 and float(out[2].abs().sum()) == 0.0 and float(out[1].sum()) == 21.0
+    assert ops._zeros_like_many([]) == []
 
 
 def test_single_process_helpers_are_identity():
