@@ -401,8 +401,10 @@ def dopri5_strong(args, rank, world, dev, pk, steps=3, warmup=1):
     """BASELINE configs[2] under the driver: adaptive dopri5 (rtol 1e-3, atol 1e-4) over partial-observation graphs of
     19 AGVs + 9 pickers (D = 435, 140 nodes per graph), `--dopri5-graphs` trajectories IN TOTAL sharded over the ranks
     (strong scaling); the error norm is global over the whole batch, so all ranks take the unsharded batch's step
-    decisions.  conv3 weights x 8 and t = 0..3 with three output points: 13 accepted steps and one rejection (with the
-    SURVEY's 0.1 scale the solve needs two steps and the controller is not exercised)."""
+    decisions.  conv3 weights x 8 and t = 0..3 with three output points: 13 accepted steps (with the SURVEY's 0.1 scale the
+    solve needs two steps and the controller is not exercised).  No attempt is rejected at this batch size -- the global RMS
+    norm averages over 10^9 elements of a smooth field (peak error ratio 0.77); rejected attempts are covered by the
+    small-batch regimes of tests/test_gpu_integrate.py, with accept / reject lists identical to the oracle's."""
     import swarm_ode_b200 as S
     from swarm_ode_b200 import dist as Dm
     lo, hi = Dm.shard_range(args.dopri5_graphs, rank, world)
