@@ -53,7 +53,10 @@ __global__ void k_fold_weights(const float* __restrict__ w1cat, const float* __r
 // small dense products applied once at the end of the backward pass (fp32, tiny):
 //   dW3cat[d, c] += sum_z w1cat[z, d] R[z, c]          dW1cat[z, d] += sum_c R[z, c] w3cat[d, c] + g1[z] b3[d]
 //   db3[d]       += sum_z g1[z] w1cat[z, d]
-__global__ void k_fold_param_grads(const float* __restrict__ w1cat, const float* __restrict__ w3cat, const float* __restrict__ b3,
+// w3catT [2H, D] (the transposed copy the backward context holds anyway): consecutive threads then read consecutive
+// addresses; w3cat[d, q] across threads d is a 512-byte stride = 32 lines per warp load, 128 times (the kernel took 46 us)
+__global__ void k_fold_param_grads(const float* __restrict__ w1cat, const float* __restrict__ w3cat, const float* __restrict__ w3catT,
+                                   const float* __restrict__ b3,
                                    const float* __restrict__ R, const float* __restrict__ g1, int H2, int D,
                                    float* __restrict__ dW3cat, float* __restrict__ dW1cat, float* __restrict__ db3) {
   const int d = blockIdx.x * blockDim.x + threadIdx.x;
@@ -63,7 +66,8 @@ __global__ void k_fold_param_grads(const float* __restrict__ w1cat, const float*
     float a3 = 0.f, a1 = 0.f;
     for (int q = 0; q < H2; ++q) {
       a3 = fmaf(w1cat[(size_t)q * D + d], R[(size_t)q * H2 + j], a3);       // z = q, c = j
-      a1 = fmaf(R[(size_t)j * H2 + q], w3cat[(size_t)d * H2 + q], a1);       // z = j, c = q
+      const float w3 = w3catT ? w3catT[(size_t)q * D + d] : w3cat[(size_t)d * H2 + q];
+      a1 = fmaf(R[(size_t)j * H2 + q], w3, a1);                              // z = j, c = q
     }
     dW3cat[(size_t)d * H2 + j] += a3;
     dW1cat[(size_t)j * D + d] += a1 + g1[j] * b3[d];
@@ -95,8 +99,9 @@ __global__ void k_lr_g3(const float* __restrict__ g1, const float* __restrict__ 
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;   // float4 index
   const int q = H2 / 4;
   if (i >= N * q) return;
-  const int64_t n = i / q;
-  const int c = (int)(i % q) * 4;
+  // (2H = 128: shifts; the general form is a 64-bit division by a run-time value per thread of a write-bound kernel)
+  const int64_t n = H2 == 128 ? (i >> 5) : i / q;
+  const int c = H2 == 128 ? ((int)(i & 31) << 2) : (int)(i % q) * 4;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int o = 0; o < n_out; ++o) {
     const float g = __ldg(g1 + n * n_out + o);
@@ -542,7 +547,7 @@ int integrate_fixed_folded_bwd(Sage3Ctx& c, FoldWs& f, const Tableau& tb, const 
   {
     GN_PROF(s, 4.0 * H2 * H2 * c.D, 0.0, "fold_param_grads");
     dim3 grid((unsigned)ceil_div64(c.D, 128), (unsigned)(H2 + 1));
-    k_fold_param_grads<<<grid, 128, 0, s>>>(c.w1cat, c.w3cat, c.b3, f.R, f.g1, H2, c.D, c.dW3cat, c.dW1cat, c.db3);
+    k_fold_param_grads<<<grid, 128, 0, s>>>(c.w1cat, c.w3cat, c.w3catT, c.b3, f.R, f.g1, H2, c.D, c.dW3cat, c.dW1cat, c.db3);
     GN_LAUNCHED();
   }
   return GNODE_OK;
@@ -655,7 +660,7 @@ int integrate_dopri5_folded_bwd(Sage3Ctx& c, FoldWs& f, const float* y0, const d
   {
     GN_PROF(s, 4.0 * H2 * H2 * c.D, 0.0, "fold_param_grads");
     dim3 grid((unsigned)ceil_div64(c.D, 128), (unsigned)(H2 + 1));
-    k_fold_param_grads<<<grid, 128, 0, s>>>(c.w1cat, c.w3cat, c.b3, f.R, f.g1, H2, c.D, c.dW3cat, c.dW1cat, c.db3);
+    k_fold_param_grads<<<grid, 128, 0, s>>>(c.w1cat, c.w3cat, c.w3catT, c.b3, f.R, f.g1, H2, c.D, c.dW3cat, c.dW1cat, c.db3);
     GN_LAUNCHED();
   }
   return GNODE_OK;
