@@ -57,7 +57,11 @@ __device__ __forceinline__ int block_excl_scan(int v, int* total) {
   return prefix + x - v;
 }
 
-__global__ void k_chunk_sums(const int32_t* __restrict__ cnt, int64_t N, int32_t* __restrict__ sums) {
+// (blockIdx.y = 0 / 1: the in-degree and the out-degree scan of a CSR build run in the same launches)
+__global__ void k_chunk_sums(const int32_t* __restrict__ cnt0, const int32_t* __restrict__ cnt1, int64_t N,
+                             int32_t* __restrict__ sums0, int32_t* __restrict__ sums1) {
+  const int32_t* __restrict__ cnt = blockIdx.y ? cnt1 : cnt0;
+  int32_t* __restrict__ sums = blockIdx.y ? sums1 : sums0;
   int64_t base = (int64_t)blockIdx.x * kScanChunk;
   int local = 0;
 #pragma unroll
@@ -71,7 +75,8 @@ __global__ void k_chunk_sums(const int32_t* __restrict__ cnt, int64_t N, int32_t
 }
 
 // single block: exclusive scan of the chunk sums in place
-__global__ void k_scan_sums(int32_t* __restrict__ sums, int64_t nb) {
+__global__ void k_scan_sums(int32_t* __restrict__ sums0, int32_t* __restrict__ sums1, int64_t nb) {
+  int32_t* __restrict__ sums = blockIdx.y ? sums1 : sums0;
   __shared__ int carry_s;
   if (threadIdx.x == 0) carry_s = 0;
   __syncthreads();
@@ -88,8 +93,12 @@ __global__ void k_scan_sums(int32_t* __restrict__ sums, int64_t nb) {
   }
 }
 
-__global__ void k_scan_final(const int32_t* __restrict__ cnt, int64_t N,
-                             const int32_t* __restrict__ sums, int32_t* __restrict__ rowptr) {
+__global__ void k_scan_final(const int32_t* __restrict__ cnt0, const int32_t* __restrict__ cnt1, int64_t N,
+                             const int32_t* __restrict__ sums0, const int32_t* __restrict__ sums1,
+                             int32_t* __restrict__ rowptr0, int32_t* __restrict__ rowptr1) {
+  const int32_t* __restrict__ cnt = blockIdx.y ? cnt1 : cnt0;
+  const int32_t* __restrict__ sums = blockIdx.y ? sums1 : sums0;
+  int32_t* __restrict__ rowptr = blockIdx.y ? rowptr1 : rowptr0;
   int64_t base = (int64_t)blockIdx.x * kScanChunk;
   int v[kScanItems];
   int local = 0;
@@ -130,8 +139,15 @@ constexpr int kShortRow = 16;
 
 // rank sort, one thread per short row (deg <= kShortRow); long rows are listed for k_sort_long (a warp per row of a grid
 // over ALL rows cost 31 us per CSR on the 389 k-node bench batch, which has no long row at all)
-__global__ void k_sort_short(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ in,
-                             int32_t* __restrict__ out, int64_t N, int32_t* __restrict__ long_rows, int32_t* __restrict__ n_long) {
+struct SortJob { const int32_t* rowptr; const int32_t* in; int32_t* out; int32_t* long_rows; int32_t* n_long; };
+// (blockIdx.y = 0 / 1: the CSR and the transposed CSR are sorted by the same launches)
+__global__ void k_sort_short(const SortJob j0, const SortJob j1, int64_t N) {
+  const SortJob& jb = blockIdx.y ? j1 : j0;
+  const int32_t* __restrict__ rowptr = jb.rowptr;
+  const int32_t* __restrict__ in = jb.in;
+  int32_t* __restrict__ out = jb.out;
+  int32_t* __restrict__ long_rows = jb.long_rows;
+  int32_t* __restrict__ n_long = jb.n_long;
   int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (r >= N) return;
   int b = rowptr[r], e = rowptr[r + 1];
@@ -154,8 +170,13 @@ __global__ void k_sort_short(const int32_t* __restrict__ rowptr, const int32_t* 
 }
 
 // rank sort, one warp per listed long row (the list order is arbitrary; every row is sorted on its own: deterministic)
-__global__ void k_sort_long(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ in,
-                            int32_t* __restrict__ out, const int32_t* __restrict__ long_rows, const int32_t* __restrict__ n_long) {
+__global__ void k_sort_long(const SortJob j0, const SortJob j1) {
+  const SortJob& jb = blockIdx.y ? j1 : j0;
+  const int32_t* __restrict__ rowptr = jb.rowptr;
+  const int32_t* __restrict__ in = jb.in;
+  int32_t* __restrict__ out = jb.out;
+  const int32_t* __restrict__ long_rows = jb.long_rows;
+  const int32_t* __restrict__ n_long = jb.n_long;
   constexpr int kStage = 512;                        // ids of a row staged in shared memory per warp (longer rows: from global)
   __shared__ int32_t s_row[8][kStage];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -181,19 +202,22 @@ __global__ void k_sort_long(const int32_t* __restrict__ rowptr, const int32_t* _
   }
 }
 
-int scan_counts(const int32_t* cnt, int64_t N, int32_t* rowptr, int32_t* sums, cudaStream_t s) {
+// exclusive scans of both degree arrays (in -> rowptr, out -> t_rowptr) in three launches
+int scan_counts2(const int32_t* cnt0, const int32_t* cnt1, int64_t N, int32_t* rowptr0, int32_t* rowptr1, int32_t* sums0,
+                 int32_t* sums1, cudaStream_t s) {
   int64_t nb = ceil_div64(N, kScanChunk);
-  k_chunk_sums<<<(unsigned)nb, kScanThreads, 0, s>>>(cnt, N, sums);
+  const dim3 grid((unsigned)nb, 2);
+  k_chunk_sums<<<grid, kScanThreads, 0, s>>>(cnt0, cnt1, N, sums0, sums1);
   GN_LAUNCHED();
-  k_scan_sums<<<1, kScanThreads, 0, s>>>(sums, nb);
+  k_scan_sums<<<dim3(1, 2), kScanThreads, 0, s>>>(sums0, sums1, nb);
   GN_LAUNCHED();
-  k_scan_final<<<(unsigned)nb, kScanThreads, 0, s>>>(cnt, N, sums, rowptr);
+  k_scan_final<<<grid, kScanThreads, 0, s>>>(cnt0, cnt1, N, sums0, sums1, rowptr0, rowptr1);
   GN_LAUNCHED();
   return GNODE_OK;
 }
 
 struct CsrWs {
-  int32_t *cnt_in, *cnt_out, *sums, *col_u, *t_col_u, *flag, *n_long;
+  int32_t *cnt_in, *cnt_out, *sums, *sums_out, *col_u, *t_col_u, *flag, *n_long;
 };
 
 CsrWs carve(Arena& a, int64_t N, int64_t E) {
@@ -201,6 +225,7 @@ CsrWs carve(Arena& a, int64_t N, int64_t E) {
   w.cnt_in = a.take<int32_t>(N + 1);
   w.cnt_out = a.take<int32_t>(N + 1);
   w.sums = a.take<int32_t>(ceil_div64(N > 0 ? N : 1, kScanChunk) + 1);
+  w.sums_out = a.take<int32_t>(ceil_div64(N > 0 ? N : 1, kScanChunk) + 1);
   w.col_u = a.take<int32_t>(E > 0 ? E : 1);
   w.t_col_u = a.take<int32_t>(E > 0 ? E : 1);
   w.flag = a.take<int32_t>(1);
@@ -233,8 +258,9 @@ extern "C" int gnode_csr_build_async(const int64_t* edge_index, int64_t E, int64
   GN_ARENA_OK(a, "gnode_csr_build");
 
   GN_PROF(s, 0.0, 16.0 * E + 8.0 * E + 8.0 * N, "csr_build");
-  GN_CUDA(cudaMemsetAsync(w.cnt_in, 0, sizeof(int32_t) * (N + 1), s));
-  GN_CUDA(cudaMemsetAsync(w.cnt_out, 0, sizeof(int32_t) * (N + 1), s));
+  // cnt_in and cnt_out are consecutive arena blocks: one fill covers both (and the padding between them)
+  const size_t cnt_span = (size_t)(reinterpret_cast<char*>(w.cnt_out + (N + 1)) - reinterpret_cast<char*>(w.cnt_in));
+  GN_CUDA(cudaMemsetAsync(w.cnt_in, 0, cnt_span, s));
   GN_CUDA(cudaMemsetAsync(error_flag, 0, sizeof(int32_t), s));
   const int threads = 256;
   unsigned eblocks = (unsigned)(E > 0 ? (ceil_div64(E, threads) < 148 * 16 ? ceil_div64(E, threads) : 148 * 16) : 1);
@@ -242,11 +268,9 @@ extern "C" int gnode_csr_build_async(const int64_t* edge_index, int64_t E, int64
     k_count<<<eblocks, threads, 0, s>>>(edge_index, E, N, w.cnt_in, w.cnt_out, error_flag);
     GN_LAUNCHED();
   }
-  GN_TRY(scan_counts(w.cnt_in, N, rowptr, w.sums, s));
-  GN_TRY(scan_counts(w.cnt_out, N, t_rowptr, w.sums, s));
+  GN_TRY(scan_counts2(w.cnt_in, w.cnt_out, N, rowptr, t_rowptr, w.sums, w.sums_out, s));
   if (E > 0) {
-    GN_CUDA(cudaMemsetAsync(w.cnt_in, 0, sizeof(int32_t) * (N + 1), s));
-    GN_CUDA(cudaMemsetAsync(w.cnt_out, 0, sizeof(int32_t) * (N + 1), s));
+    GN_CUDA(cudaMemsetAsync(w.cnt_in, 0, cnt_span, s));
     k_fill<<<eblocks, threads, 0, s>>>(edge_index, E, N, rowptr, t_rowptr, w.cnt_in, w.cnt_out,
                                        w.col_u, w.t_col_u);
     GN_LAUNCHED();
@@ -256,13 +280,10 @@ extern "C" int gnode_csr_build_async(const int64_t* edge_index, int64_t E, int64
     int64_t wb64 = ceil_div64(N * 32, threads);
     unsigned wb = (unsigned)(wb64 < kNumSMs * 8 ? wb64 : kNumSMs * 8);
     GN_CUDA(cudaMemsetAsync(w.n_long, 0, 2 * sizeof(int32_t), s));
-    k_sort_short<<<rb, threads, 0, s>>>(rowptr, w.col_u, col, N, w.cnt_in, w.n_long);
+    const SortJob j0{rowptr, w.col_u, col, w.cnt_in, w.n_long}, j1{t_rowptr, w.t_col_u, t_col, w.cnt_out, w.n_long + 1};
+    k_sort_short<<<dim3(rb, 2), threads, 0, s>>>(j0, j1, N);
     GN_LAUNCHED();
-    k_sort_long<<<wb, threads, 0, s>>>(rowptr, w.col_u, col, w.cnt_in, w.n_long);
-    GN_LAUNCHED();
-    k_sort_short<<<rb, threads, 0, s>>>(t_rowptr, w.t_col_u, t_col, N, w.cnt_out, w.n_long + 1);
-    GN_LAUNCHED();
-    k_sort_long<<<wb, threads, 0, s>>>(t_rowptr, w.t_col_u, t_col, w.cnt_out, w.n_long + 1);
+    k_sort_long<<<dim3(wb, 2), threads, 0, s>>>(j0, j1);
     GN_LAUNCHED();
   }
   return GNODE_OK;

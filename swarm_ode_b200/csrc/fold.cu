@@ -82,13 +82,17 @@ size_t padf(size_t floats) { return (floats + 63) & ~(size_t)63; }
 
 // ---- factored cotangent G = g1 @ Wd (rank n_out <= 8) ----
 // WdW3[o, c] = sum_d Wd[o, d] w3cat[d, c]      (fp64 accumulate; a warp per output, lanes split the D loop)
-__global__ void k_lr_prep(const float* __restrict__ Wd, const float* __restrict__ w3cat, int n_out, int D, int H2,
-                          float* __restrict__ WdW3) {
+__global__ void k_lr_prep(const float* __restrict__ Wd, const float* __restrict__ w3cat, const float* __restrict__ w3catT, int n_out,
+                          int D, int H2, float* __restrict__ WdW3) {
   const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, l = threadIdx.x & 31;
   if (i >= n_out * H2) return;
   const int o = i / H2, c = i % H2;
   double acc = 0.0;
-  for (int d = l; d < D; d += 32) acc += (double)Wd[(size_t)o * D + d] * (double)w3cat[(size_t)d * H2 + c];
+  if (w3catT) {     // the transposed copy of the backward context: the lanes read consecutive addresses
+    for (int d = l; d < D; d += 32) acc += (double)Wd[(size_t)o * D + d] * (double)w3catT[(size_t)c * D + d];
+  } else {
+    for (int d = l; d < D; d += 32) acc += (double)Wd[(size_t)o * D + d] * (double)w3cat[(size_t)d * H2 + c];
+  }
 #pragma unroll
   for (int sft = 1; sft < 32; sft <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, sft);
   if (l == 0) WdW3[i] = (float)acc;
@@ -109,6 +113,36 @@ __global__ void k_lr_g3(const float* __restrict__ g1, const float* __restrict__ 
     acc.x = fmaf(g, w.x, acc.x); acc.y = fmaf(g, w.y, acc.y); acc.z = fmaf(g, w.z, acc.z); acc.w = fmaf(g, w.w, acc.w);
   }
   *reinterpret_cast<float4*>(G3 + n * H2 + c) = acc;
+}
+// The same for 2H = 128 and n_out <= 4: a warp per row (lane = one float4 of the 512-byte row), the rank-n_out weights in
+// registers, four rows in flight per warp -- the kernel is a 199 MB write and should run at the store rate (the
+// thread-per-float4 form above reloads the weights per element and ran at 2.8 TB/s).
+template <int NO>
+__global__ void __launch_bounds__(256) k_lr_g3_128(const float* __restrict__ g1, const float* __restrict__ WdW3, int64_t N,
+                                                   float* __restrict__ G3) {
+  constexpr int H2 = 128, RW = 4;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  float4 w[NO];
+#pragma unroll
+  for (int o = 0; o < NO; ++o) w[o] = __ldg(reinterpret_cast<const float4*>(WdW3 + (size_t)o * H2) + lane);
+  for (int64_t n0 = warp * RW; n0 < N; n0 += n_warps * RW) {
+    float g[RW][NO];
+#pragma unroll
+    for (int u = 0; u < RW; ++u)
+#pragma unroll
+      for (int o = 0; o < NO; ++o) g[u][o] = (n0 + u < N) ? __ldg(g1 + (n0 + u) * NO + o) : 0.f;
+#pragma unroll
+    for (int u = 0; u < RW; ++u) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int o = 0; o < NO; ++o) {
+        acc.x = fmaf(g[u][o], w[o].x, acc.x); acc.y = fmaf(g[u][o], w[o].y, acc.y);
+        acc.z = fmaf(g[u][o], w[o].z, acc.z); acc.w = fmaf(g[u][o], w[o].w, acc.w);
+      }
+      if (n0 + u < N) *(reinterpret_cast<float4*>(G3 + (n0 + u) * H2) + lane) = acc;
+    }
+  }
 }
 // dW3cat[d, c] += sum_o Wd[o, d] X[o, c];   db3[d] += cs * sum_o Wd[o, d] X[n_out * H2 + o]     (X = g1^T [C | 1])
 __global__ void k_lr_finish(const float* __restrict__ Wd, const float* __restrict__ X, int n_out, int D, int H2, float cs,
@@ -392,9 +426,19 @@ static int fold_step_bwd(Sage3Ctx& c, FoldWs& f, const Tableau& tb, float dt, co
   for (int st = 0; st < S; ++st) csum += tb.c_sol[st];
   if (lr) {  // G = g1 @ Wd is never formed:  G3 = g1 @ (Wd @ w3cat)
     GN_PROF(s, 2.0 * N * lr->n_out * H2, 4.0 * (double)N * (H2 + lr->n_out), "lowrank_G3");
-    k_lr_prep<<<(unsigned)ceil_div64((int64_t)lr->n_out * H2 * 32, 256), 256, 0, s>>>(lr->Wd, c.w3cat, lr->n_out, c.D, H2, lr->WdW3);
+    k_lr_prep<<<(unsigned)ceil_div64((int64_t)lr->n_out * H2 * 32, 256), 256, 0, s>>>(lr->Wd, c.w3cat, c.w3catT, lr->n_out, c.D, H2, lr->WdW3);
     GN_LAUNCHED();
-    k_lr_g3<<<(unsigned)ceil_div64(N * (H2 / 4), 256), 256, 0, s>>>(lr->g1, lr->WdW3, N, lr->n_out, H2, f.G3);
+    if (H2 == 128 && lr->n_out <= 4) {
+      const unsigned grid = (unsigned)std::min<int64_t>(ceil_div64(N, 4 * 8), (int64_t)kNumSMs * 8);
+      switch (lr->n_out) {
+        case 1: k_lr_g3_128<1><<<grid, 256, 0, s>>>(lr->g1, lr->WdW3, N, f.G3); break;
+        case 2: k_lr_g3_128<2><<<grid, 256, 0, s>>>(lr->g1, lr->WdW3, N, f.G3); break;
+        case 3: k_lr_g3_128<3><<<grid, 256, 0, s>>>(lr->g1, lr->WdW3, N, f.G3); break;
+        default: k_lr_g3_128<4><<<grid, 256, 0, s>>>(lr->g1, lr->WdW3, N, f.G3); break;
+      }
+    } else {
+      k_lr_g3<<<(unsigned)ceil_div64(N * (H2 / 4), 256), 256, 0, s>>>(lr->g1, lr->WdW3, N, lr->n_out, H2, f.G3);
+    }
     GN_LAUNCHED();
   } else {  // G3 = G @ w3cat     [N, 2H]
     GemmNT q{};
