@@ -564,8 +564,8 @@ int integrate_fixed_folded_bwd(Sage3Ctx& c, FoldWs& f, const Tableau& tb, const 
   const int S = tb.S, H = c.H, H2 = 2 * c.H;
   const int64_t N = c.N, n = c.numel(), nh = N * H2;
   GN_TRY(f.prepare(c, s));
-  GN_CUDA(cudaMemsetAsync(f.R, 0, sizeof(float) * H2 * H2, s));
-  GN_CUDA(cudaMemsetAsync(f.g1, 0, sizeof(float) * H2, s));
+  // R and g1 are consecutive arena blocks (FoldWs::carve): one fill
+  GN_CUDA(cudaMemsetAsync(f.R, 0, (size_t)(reinterpret_cast<char*>(f.g1 + H2) - reinterpret_cast<char*>(f.R)), s));
 
   // G = cotangent of y_{j+1}: explicit part from grad_sol plus what flowed back from later steps
   const float* G = lr ? nullptr : grad_sol + (int64_t)(n_t - 1) * n;
@@ -628,8 +628,8 @@ int integrate_dopri5_folded_bwd(Sage3Ctx& c, FoldWs& f, const float* y0, const d
   const int H2 = 2 * c.H;
   const int64_t N = c.N, n = c.numel();
   GN_TRY(f.prepare(c, s));
-  GN_CUDA(cudaMemsetAsync(f.R, 0, sizeof(float) * H2 * H2, s));
-  GN_CUDA(cudaMemsetAsync(f.g1, 0, sizeof(float) * H2, s));
+  // R and g1 are consecutive arena blocks (FoldWs::carve): one fill
+  GN_CUDA(cudaMemsetAsync(f.R, 0, (size_t)(reinterpret_cast<char*>(f.g1 + H2) - reinterpret_cast<char*>(f.R)), s));
   f.bind_slots(c, nullptr, 0);
   double csum = 0.0;
   for (int st = 0; st < tb.S; ++st) csum += tb.c_sol[st];

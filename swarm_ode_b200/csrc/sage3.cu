@@ -103,12 +103,9 @@ int Sage3Ctx::pack(const gnode_sage3_params& p, bool backward, cudaStream_t s) {
 }
 
 int Sage3Ctx::zero_param_grads(cudaStream_t s) {
-  GN_CUDA(cudaMemsetAsync(dW1cat, 0, sizeof(float) * 2 * H * D, s));
-  GN_CUDA(cudaMemsetAsync(dW2cat, 0, sizeof(float) * H * 2 * H, s));
-  GN_CUDA(cudaMemsetAsync(dW3cat, 0, sizeof(float) * D * 2 * H, s));
-  GN_CUDA(cudaMemsetAsync(db1, 0, sizeof(float) * H, s));
-  GN_CUDA(cudaMemsetAsync(db2, 0, sizeof(float) * H, s));
-  GN_CUDA(cudaMemsetAsync(db3, 0, sizeof(float) * D, s));
+  // dW1cat .. db3 are consecutive arena blocks (carve): one fill covers all six and the padding between them
+  const size_t span = (size_t)(reinterpret_cast<char*>(db3 + D) - reinterpret_cast<char*>(dW1cat));
+  GN_CUDA(cudaMemsetAsync(dW1cat, 0, span, s));
   return GNODE_OK;
 }
 
