@@ -161,3 +161,45 @@ def test_oracle_adjoint_matches_backprop_at_small_steps():
     assert torch.equal(sol, s2.detach())
     assert float((gy0 - y0r.grad).norm() / y0r.grad.norm()) < 1e-8
     assert float((gp[0] - W.grad).norm() / W.grad.norm()) < 1e-8
+
+
+def _dense_weights(x: float):
+    """w_s(x) of csrc/fold.cu:dopri5_dense_weights, restated: the quartic of _interp_fit / _interp_evaluate expanded in the
+    seven stage derivatives (d = Kronecker delta, c = c_sol, m = c_mid)."""
+    from oracle.torchdiffeq_ref import DP_C_MID, DP_C_SOL
+    w = []
+    for s in range(7):
+        d0, d6, cs, ms = float(s == 0), float(s == 6), DP_C_SOL[s], DP_C_MID[s]
+        w.append(x * d0 + x ** 2 * (d6 - 4 * d0 - 5 * cs + 16 * ms) + x ** 3 * (5 * d0 - 3 * d6 + 14 * cs - 32 * ms)
+                 + x ** 4 * (2 * d6 - 2 * d0 - 8 * cs + 16 * ms))
+    return w
+
+
+@pytest.mark.parametrize("x", [0.0, 0.137, 0.5, 0.9, 1.0])
+def test_dense_output_is_a_stage_combination(x):
+    """The identity behind the one-projection dense output of the folded dopri5 (csrc/integrate.cu, gnode_set_dopri5_fsal):
+    torchdiffeq's quartic through (y0, y1, y_mid, f0, f1) equals y0 + dt sum_s w_s(x) k_s -- the y0 terms of its coefficients
+    cancel -- and w(1) = c_sol.  Checked against the oracle's own _interp_fit / _interp_evaluate in float64."""
+    from oracle.torchdiffeq_ref import DP_C_MID, DP_C_SOL, _interp_evaluate, _interp_fit_dopri5
+    g = torch.Generator().manual_seed(3)
+    y0 = torch.randn(5, 7, generator=g, dtype=torch.float64)
+    k = torch.randn(5, 7, 7, generator=g, dtype=torch.float64)            # [..., stage]
+    dt = torch.tensor(0.37, dtype=torch.float64)
+    y1 = y0 + k.matmul(dt * torch.tensor(DP_C_SOL, dtype=torch.float64))
+    coeffs = _interp_fit_dopri5(y0, y1, k, dt, torch.tensor(DP_C_MID, dtype=torch.float64))
+    t0, t1 = torch.tensor(2.0, dtype=torch.float64), torch.tensor(2.0, dtype=torch.float64) + dt
+    want = _interp_evaluate(coeffs, t0, t1, t0 + x * dt)
+    w = torch.tensor(_dense_weights(x), dtype=torch.float64)
+    got = y0 + k.matmul(dt * w)
+    assert torch.allclose(got, want, rtol=0, atol=1e-12 * float(want.abs().max() + 1))
+    if x == 1.0:
+        assert torch.allclose(w, torch.tensor(DP_C_SOL, dtype=torch.float64), rtol=0, atol=1e-13)
+        assert torch.allclose(got, y1, rtol=0, atol=1e-12)
+
+
+def test_last_dopri5_stage_is_evaluated_at_the_solution():
+    """FSAL: row 6 of the Dormand-Prince tableau equals c_sol, so stage 6 of an attempt sees y1 itself -- what lets the
+    folded solver hand Z of stage 6 to the next attempt as Z_0 = y1 @ w1cat^T (csrc/chain_fwd.cu: Args::Zlast)."""
+    from oracle.torchdiffeq_ref import DP_BETA, DP_C_SOL
+    assert list(DP_BETA[-1]) + [0] == list(DP_C_SOL)
+    assert abs(sum(DP_C_SOL) - 1.0) < 1e-15
